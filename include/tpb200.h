@@ -1,0 +1,184 @@
+/*
+ * tpb200.h -- C ABI of libtpb200.so: the B200-native (sm_100a) WCSPH right-hand side that
+ * drops in under TrixiParticles.jl's `Semidiscretization` / `semidiscretize` / `kick!` /
+ * `drift!` interface.  Host code in any language binds exactly these entry points
+ * (Julia: `ccall`; Python: ctypes, see trixiparticles.jl_b200/_lib.py).
+ *
+ * Conventions
+ *   - every function returns an int32 status (TPB_OK == 0); nothing throws across the ABI;
+ *     `tpb_last_error` gives the message for the last non-zero status.
+ *   - plain pointers and sizes only.  Arrays use the reference's memory layout: Julia
+ *     column-major `nvars x nparticles` matrices == particle-major C arrays.
+ *   - `eltype` (T) is the system element type, `coords_eltype` (cT) the coordinate type
+ *     (/root/reference/src/general/semidiscretization.jl:326-332).  Real parameters cross
+ *     the ABI as double; callers compute them in T first, so the conversion back is exact.
+ *   - one call at a time per handle from one host thread.  All device work of a handle is
+ *     issued on one CUDA stream (`tpb_set_stream`).  With TPB_MEM_DEVICE the calls are
+ *     stream-ordered and return without synchronising; with TPB_MEM_HOST they return after
+ *     the results are in the caller's buffers.  No allocation happens inside `tpb_kick` /
+ *     `tpb_drift` (reference: zero allocations per RHS, test/count_allocations.jl:111-121).
+ *
+ * Paths cited below are relative to /root/reference.
+ */
+#ifndef TPB200_H
+#define TPB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPB_VERSION_MAJOR 0
+#define TPB_VERSION_MINOR 1
+
+/* status codes */
+#define TPB_OK 0
+#define TPB_ERR_INVALID_ARGUMENT 1 /* reference: ArgumentError at construction */
+#define TPB_ERR_UNSUPPORTED 2      /* option outside the accelerated hot path */
+#define TPB_ERR_CUDA 3             /* CUDA runtime failure (message has the cudaError) */
+#define TPB_ERR_OUT_OF_BOUNDS 4    /* a particle left the FullGridCellList bounding box */
+#define TPB_ERR_STATE 5            /* call order violated (e.g. kick before semidiscretize) */
+#define TPB_ERR_CAPACITY 6         /* output buffer too small */
+
+/* element types */
+#define TPB_F32 0
+#define TPB_F64 1
+
+/* where the ODE vectors handed to kick/drift live */
+#define TPB_MEM_HOST 0
+#define TPB_MEM_DEVICE 1
+
+/* smoothing kernels (src/general/smoothing_kernels.jl:191-227, :434-455) */
+#define TPB_KERNEL_WENDLAND_C2 0
+#define TPB_KERNEL_SCHOENBERG_CUBIC 1
+
+/* density calculators (src/general/density_calculators.jl) */
+#define TPB_DENSITY_CONTINUITY 0
+#define TPB_DENSITY_SUMMATION 1
+
+/* fields for tpb_get_system_field (fluid.jl:312-326, wall_boundary/system.jl:339-350) */
+#define TPB_FIELD_PRESSURE 0
+#define TPB_FIELD_DENSITY 1
+#define TPB_FIELD_VOLUME 2 /* wall: boundary_model.cache.volume */
+
+typedef struct tpb_semi_s *tpb_semi_t; /* opaque; mirrors `Semidiscretization` */
+
+/* `Semidiscretization(systems...; neighborhood_search=GridNeighborhoodSearch{ND}(cell_list=
+ * FullGridCellList(; min_corner, max_corner)), parallelization_backend)`
+ * (semidiscretization.jl:106-110; examples/fluid/dam_break_2d_gpu.jl:30-33). */
+typedef struct {
+    int32_t struct_size;   /* = sizeof(tpb_config), for forward compatibility */
+    int32_t ndims;         /* 2 or 3 */
+    int32_t eltype;        /* TPB_F32 | TPB_F64 */
+    int32_t coords_eltype; /* TPB_F32 | TPB_F64, >= eltype */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t ode_memory;    /* TPB_MEM_HOST | TPB_MEM_DEVICE */
+    int32_t has_bounds;    /* 0: bounding box = extent of all initial coordinates */
+    int32_t max_points_per_cell; /* accepted for compatibility; the counting sort has no cap */
+    int32_t deterministic; /* 1: neighbours of a cell are ordered by particle index (default) */
+    int32_t interact_variant; /* 0 = auto; 1 = per-particle sweep; 2 = cell-tile sweep */
+    double min_corner[3];
+    double max_corner[3];
+} tpb_config;
+
+/* `WeaklyCompressibleSPHSystem` fields read by the RHS (wcsph/system.jl:65-86) */
+typedef struct {
+    int32_t struct_size;
+    int32_t kernel;                 /* TPB_KERNEL_* */
+    int32_t density_calculator;     /* TPB_DENSITY_* */
+    int32_t clip_negative_pressure; /* StateEquationCole CLIP */
+    int32_t has_viscosity;          /* ArtificialViscosityMonaghan | nothing */
+    int32_t has_diffusion;          /* DensityDiffusionMolteniColagrossi | nothing */
+    double smoothing_length;
+    double sound_speed, exponent, reference_density, background_pressure; /* StateEquationCole */
+    double alpha, beta, epsilon;    /* viscosity.jl:68-76 */
+    double delta;                   /* density_diffusion.jl:41-47 */
+    double acceleration[3];         /* system.acceleration */
+    double damping_coefficient;     /* SourceTermDamping (semidiscretization.jl:795-807); 0 = none */
+} tpb_fluid_params;
+
+/* `WallBoundarySystem(ic, BoundaryModelDummyParticles(density, mass,
+ * AdamiPressureExtrapolation(pressure_offset), kernel, h; state_equation,
+ * clip_negative_pressure))` (wall_boundary/system.jl:22-43, dummy_particles.jl:52-77,142-149) */
+typedef struct {
+    int32_t struct_size;
+    int32_t kernel;
+    int32_t clip_negative_pressure; /* boundary model flag */
+    int32_t reserved;
+    double smoothing_length;
+    double sound_speed, exponent, reference_density, background_pressure;
+    double pressure_offset;
+} tpb_wall_params;
+
+/* launch/traffic accounting of the last kick (what bench.py reports as gpu_launches) */
+typedef struct {
+    int64_t kernel_launches_total; /* since create */
+    int64_t kicks, drifts;
+    int64_t n_cells;
+    int32_t launches_last_kick, launches_last_drift;
+    int32_t interact_variant_used;
+    int32_t reserved;
+} tpb_stats;
+
+const char *tpb_version(void);
+
+/* message for the last failure on this handle (or of tpb_create when handle == NULL) */
+const char *tpb_last_error(tpb_semi_t semi);
+
+/* ---- construction: mirrors the `Semidiscretization` constructor ------------------------ */
+int32_t tpb_create(const tpb_config *config, tpb_semi_t *out);
+int32_t tpb_destroy(tpb_semi_t semi);
+
+/* Systems are numbered in call order == position in the ODE vectors
+ * (semidiscretization.jl:128-135).  `mass`: T[n].  Arrays are host pointers, copied. */
+int32_t tpb_add_fluid_system(tpb_semi_t semi, const tpb_fluid_params *params, int64_t n,
+                             const void *mass, int32_t *system_index);
+/* `coords`: cT[ND x n]; `hydrodynamic_mass`, `initial_density`: T[n]. */
+int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *params, int64_t n,
+                            const void *coords, const void *hydrodynamic_mass,
+                            const void *initial_density, int32_t *system_index);
+/* `interaction_matrix[system, neighbor]` (semidiscretization.jl:157-187); default all true */
+int32_t tpb_set_interaction(tpb_semi_t semi, int32_t system, int32_t neighbor, int32_t enabled);
+
+/* `semidiscretize(semi, tspan)` (semidiscretization.jl:293-396): sizes the cell grid, sorts
+ * the static wall particles, allocates every device buffer.  `u0_ode`: host cT[n_u] initial
+ * coordinates (used for the automatic bounding box; may be NULL when has_bounds != 0). */
+int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode);
+
+/* lengths of u_ode / v_ode and the 0-based range of one system inside them
+ * (`ranges_u` / `ranges_v`, semidiscretization.jl:128-135) */
+int32_t tpb_ode_sizes(tpb_semi_t semi, int64_t *n_u, int64_t *n_v);
+int32_t tpb_system_range(tpb_semi_t semi, int32_t system, int64_t *u_first, int64_t *u_len,
+                         int64_t *v_first, int64_t *v_len);
+
+/* ---- the hot path ----------------------------------------------------------------------- */
+/* `kick!(dv_ode, v_ode, u_ode, p, t)` (semidiscretization.jl:589-612): dv_ode is fully
+ * overwritten.  Host pointers are not retained after return. */
+int32_t tpb_kick(tpb_semi_t semi, void *dv_ode, const void *v_ode, const void *u_ode, double t);
+/* `drift!(du_ode, v_ode, u_ode, p, t)` (semidiscretization.jl:522-536) */
+int32_t tpb_drift(tpb_semi_t semi, void *du_ode, const void *v_ode, const void *u_ode, double t);
+
+/* ---- outputs / diagnostics ----------------------------------------------------------------- */
+/* system data after the last kick, in the system's own particle order; `out`: host T[n] */
+int32_t tpb_get_system_field(tpb_semi_t semi, int32_t system, int32_t field, void *out, int64_t n);
+/* Test hook: rebuilds the grids for `u_ode` and writes every ordered neighbour pair
+ * (i in `system`, j in `neighbor`, both 0-based) with |x_i - x_j|^2 <= R^2 for the radius of
+ * that ordered pair (neighborhood_search.jl:73-77,134-140), in unspecified order.
+ * `*count` receives the true number; TPB_ERR_CAPACITY if it exceeds `capacity`. */
+int32_t tpb_neighbor_pairs(tpb_semi_t semi, int32_t system, int32_t neighbor, const void *u_ode,
+                           int64_t capacity, int32_t *out_i, int32_t *out_j, int64_t *count);
+/* blocks until all queued work of the handle is done; returns a deferred device-side error
+ * (TPB_ERR_OUT_OF_BOUNDS) if one was raised by an asynchronous kick */
+int32_t tpb_synchronize(tpb_semi_t semi);
+/* `stream` is a cudaStream_t; NULL selects the handle's own stream */
+int32_t tpb_set_stream(tpb_semi_t semi, void *stream);
+int32_t tpb_get_stats(tpb_semi_t semi, tpb_stats *out);
+
+/* page-lock / unlock caller memory so TPB_MEM_HOST transfers run at full PCIe speed */
+int32_t tpb_host_register(void *ptr, int64_t bytes);
+int32_t tpb_host_unregister(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPB200_H */

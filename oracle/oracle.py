@@ -1,0 +1,230 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle_sph.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Nothing under trixiparticles.jl_b200/
+imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle_sph.so")
+
+KERNEL_WENDLAND_C2 = 0
+KERNEL_SCHOENBERG_CUBIC = 1
+DENSITY_CONTINUITY = 0
+DENSITY_SUMMATION = 1
+
+
+class FluidParams(C.Structure):
+    _fields_ = [
+        ("ndims", C.c_int32), ("kernel", C.c_int32), ("density_calculator", C.c_int32),
+        ("clip_negative_pressure", C.c_int32), ("has_viscosity", C.c_int32),
+        ("has_diffusion", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("smoothing_length", C.c_double), ("sound_speed", C.c_double),
+        ("exponent", C.c_double), ("reference_density", C.c_double),
+        ("background_pressure", C.c_double), ("alpha", C.c_double), ("beta", C.c_double),
+        ("epsilon", C.c_double), ("delta", C.c_double), ("acceleration", C.c_double * 3),
+        ("damping_coefficient", C.c_double),
+    ]
+
+
+class WallParams(C.Structure):
+    _fields_ = [
+        ("kernel", C.c_int32), ("clip_negative_pressure", C.c_int32),
+        ("eos_clip_negative_pressure", C.c_int32), ("reserved0", C.c_int32),
+        ("smoothing_length", C.c_double), ("sound_speed", C.c_double),
+        ("exponent", C.c_double), ("reference_density", C.c_double),
+        ("background_pressure", C.c_double), ("pressure_offset", C.c_double),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
+    srcs = [os.path.join(_HERE, f) for f in ("sph_oracle.c", "sph_oracle_impl.inc", "sph_oracle.h")]
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle_sph.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _declare(_lib)
+    return _lib
+
+
+_SUFFIX = {("float64", "float64"): "f64", ("float32", "float32"): "f32",
+           ("float32", "float64"): "f32c64"}
+
+
+def suffix(dtype, coords_dtype=None) -> str:
+    dtype = np.dtype(dtype)
+    coords_dtype = np.dtype(coords_dtype) if coords_dtype is not None else dtype
+    return _SUFFIX[(dtype.name, coords_dtype.name)]
+
+
+def _declare(L):
+    d, i, i64, p = C.c_double, C.c_int, C.c_int64, C.c_void_p
+    for s in ("f64", "f32", "f32c64"):
+        for name in ("orc_kernel", "orc_kernel_unsafe", "orc_kernel_deriv_div_r"):
+            f = getattr(L, f"{name}_{s}"); f.restype = d; f.argtypes = [i, i, d, d]
+        f = getattr(L, f"orc_eos_{s}"); f.restype = d; f.argtypes = [d, d, d, d, i, d]
+        f = getattr(L, f"orc_inverse_eos_{s}"); f.restype = d; f.argtypes = [d, d, d, d, d]
+        f = getattr(L, f"orc_viscosity_pair_{s}"); f.restype = None
+        f.argtypes = [i, i, d, d, d, d, d, d, d, d, p, p, p]
+        f = getattr(L, f"orc_interact_pair_{s}"); f.restype = None
+        f.argtypes = [C.POINTER(FluidParams), i, d, d, d, d, d, p, p, p, p, p]
+        for name in ("orc_pairs_bruteforce", "orc_pairs_grid"):
+            f = getattr(L, f"{name}_{s}"); f.restype = i64
+            f.argtypes = [i, i64, p, i64, p, d, i64, p, p]
+        f = getattr(L, f"orc_kick_{s}"); f.restype = i
+        f.argtypes = [C.POINTER(FluidParams), C.POINTER(WallParams), i64, p, i64, p, p, p, p, p,
+                      p, p, p, p, p, i, i]
+        f = getattr(L, f"orc_drift_{s}"); f.restype = None
+        f.argtypes = [i, i, i64, p, p]
+    L.orc_max_threads.restype = i
+    L.orc_max_threads.argtypes = []
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _vec3(x):
+    out = np.zeros(3, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64).ravel()
+    out[: x.size] = x
+    return out
+
+
+# ---------------------------------------------------------------- scalar helpers
+
+def kernel(kernel_id, ndims, r, h, dtype=np.float64):
+    return getattr(lib(), f"orc_kernel_{suffix(dtype)}")(kernel_id, ndims, float(r), float(h))
+
+
+def kernel_unsafe(kernel_id, ndims, r, h, dtype=np.float64):
+    return getattr(lib(), f"orc_kernel_unsafe_{suffix(dtype)}")(kernel_id, ndims, float(r), float(h))
+
+
+def kernel_deriv_div_r(kernel_id, ndims, r, h, dtype=np.float64):
+    return getattr(lib(), f"orc_kernel_deriv_div_r_{suffix(dtype)}")(kernel_id, ndims, float(r), float(h))
+
+
+def eos(c, gamma, rho0, p_bg, clip, density, dtype=np.float64):
+    return getattr(lib(), f"orc_eos_{suffix(dtype)}")(float(c), float(gamma), float(rho0),
+                                                      float(p_bg), int(clip), float(density))
+
+
+def inverse_eos(c, gamma, rho0, p_bg, pressure, dtype=np.float64):
+    return getattr(lib(), f"orc_inverse_eos_{suffix(dtype)}")(float(c), float(gamma), float(rho0),
+                                                              float(p_bg), float(pressure))
+
+
+def viscosity_pair(kernel_id, ndims, h, alpha, beta, epsilon, c, m_b, rho_a, rho_b, v_diff,
+                   pos_diff, dtype=np.float64):
+    vd, pd, out = _vec3(v_diff), _vec3(pos_diff), np.zeros(3)
+    getattr(lib(), f"orc_viscosity_pair_{suffix(dtype)}")(
+        kernel_id, ndims, float(h), float(alpha), float(beta), float(epsilon), float(c),
+        float(m_b), float(rho_a), float(rho_b), _ptr(vd), _ptr(pd), _ptr(out))
+    return out[:ndims]
+
+
+def interact_pair(fp: FluidParams, neighbor_is_wall, m_b, rho_a, rho_b, p_a, p_b, v_a, v_b,
+                  pos_diff, dtype=np.float64):
+    va, vb, pd, dv, drho = _vec3(v_a), _vec3(v_b), _vec3(pos_diff), np.zeros(3), np.zeros(1)
+    getattr(lib(), f"orc_interact_pair_{suffix(dtype)}")(
+        C.byref(fp), int(neighbor_is_wall), float(m_b), float(rho_a), float(rho_b), float(p_a),
+        float(p_b), _ptr(va), _ptr(vb), _ptr(pd), _ptr(dv), _ptr(drho))
+    return dv[: fp.ndims], float(drho[0])
+
+
+# ---------------------------------------------------------------- neighbour sets
+
+def neighbor_pairs(x, y, radius, dtype=None, grid=False):
+    """All (i, j) with |x_i - y_j|^2 <= R^2 (PointNeighbors predicate), sorted (i, j).
+
+    x, y: (n, ND) arrays (particle-major == Julia's ND x n column-major) of the coordinate
+    dtype; dtype = eltype(system) (defaults to the coordinate dtype)."""
+    x = np.ascontiguousarray(x)
+    y = np.ascontiguousarray(y, dtype=x.dtype)
+    dtype = np.dtype(dtype) if dtype is not None else x.dtype
+    s = suffix(dtype, x.dtype)
+    f = getattr(lib(), f"orc_pairs_{'grid' if grid else 'bruteforce'}_{s}")
+    nd = x.shape[1]
+    cap = max(1024, 64 * x.shape[0])
+    while True:
+        oi = np.empty(cap, dtype=np.int32)
+        oj = np.empty(cap, dtype=np.int32)
+        n = f(nd, x.shape[0], _ptr(x), y.shape[0], _ptr(y), float(radius), cap, _ptr(oi), _ptr(oj))
+        if n < 0:
+            raise MemoryError("oracle grid allocation failed")
+        if n <= cap:
+            return oi[:n].copy(), oj[:n].copy()
+        cap = int(n)
+
+
+# ---------------------------------------------------------------- kick! / drift!
+
+def kick(fp: FluidParams, wp, mass_f, coords_w, mass_w, v_ode, u_ode, dtype, use_grid=True,
+         nthreads=0):
+    """One `kick!` of Semidiscretization(fluid[, wall]).  Arrays are particle-major:
+    u_ode (n_f, ND) coordinate dtype; v_ode (n_f, nv) dtype.  Returns a dict."""
+    dtype = np.dtype(dtype)
+    u_ode = np.ascontiguousarray(u_ode)
+    cdt = u_ode.dtype
+    s = suffix(dtype, cdt)
+    v_ode = np.ascontiguousarray(v_ode, dtype=dtype)
+    mass_f = np.ascontiguousarray(mass_f, dtype=dtype)
+    n_f = u_ode.shape[0]
+    nd = fp.ndims
+    nv = nd if fp.density_calculator == DENSITY_SUMMATION else nd + 1
+    assert u_ode.shape == (n_f, nd) and v_ode.shape == (n_f, nv), (u_ode.shape, v_ode.shape)
+    if wp is not None and coords_w is not None and len(coords_w) > 0:
+        coords_w = np.ascontiguousarray(coords_w, dtype=cdt)
+        mass_w = np.ascontiguousarray(mass_w, dtype=dtype)
+        n_w = coords_w.shape[0]
+        wpp = C.byref(wp)
+    else:
+        coords_w = np.zeros((0, nd), dtype=cdt)
+        mass_w = np.zeros(0, dtype=dtype)
+        n_w = 0
+        wpp = None
+    out = dict(
+        dv=np.zeros((n_f, nv), dtype=dtype), pressure=np.zeros(n_f, dtype=dtype),
+        density=np.zeros(n_f, dtype=dtype), wall_pressure=np.zeros(n_w, dtype=dtype),
+        wall_density=np.zeros(n_w, dtype=dtype), wall_volume=np.zeros(n_w, dtype=dtype))
+    rc = getattr(lib(), f"orc_kick_{s}")(
+        C.byref(fp), wpp, n_f, _ptr(mass_f), n_w, _ptr(coords_w), _ptr(mass_w), _ptr(v_ode),
+        _ptr(u_ode), _ptr(out["dv"]), _ptr(out["pressure"]), _ptr(out["density"]),
+        _ptr(out["wall_pressure"]), _ptr(out["wall_density"]), _ptr(out["wall_volume"]),
+        int(bool(use_grid)), int(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"orc_kick failed: {rc}")
+    return out
+
+
+def drift(v_ode, ndims, coords_dtype):
+    v_ode = np.ascontiguousarray(v_ode)
+    s = suffix(v_ode.dtype, coords_dtype)
+    du = np.zeros((v_ode.shape[0], ndims), dtype=coords_dtype)
+    getattr(lib(), f"orc_drift_{s}")(ndims, v_ode.shape[1], v_ode.shape[0], _ptr(v_ode), _ptr(du))
+    return du
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())

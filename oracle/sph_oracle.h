@@ -1,0 +1,106 @@
+/*
+ * sph_oracle.h -- CPU oracle for the WCSPH right-hand side of TrixiParticles.jl.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain-C restatement of the reference's algorithm
+ * (each function cites the reference file:line it follows).  It is the checker for the
+ * CUDA path in trixiparticles.jl_b200/; only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load it.  The product path never
+ * links or calls anything in oracle/.
+ *
+ * Pinning: the oracle reproduces the reference's own known-answer tests
+ * (tests/test_oracle_golden.py): Monaghan viscosity pair, Adami kernel weights,
+ * Cole EOS inverse values, kernel normalisation, conservation properties, and the first
+ * samples of the dam-break surge-front trace.  The neighbour search itself lives in the
+ * third-party PointNeighbors.jl (compat 0.6.6, not under /root/reference); its published
+ * semantics are restated here (predicate d^2 <= R^2, pos_diff = x_i - y_j, self pair
+ * included) and anchored on the reference's call sites.
+ *
+ * Three precision combinations are compiled from one implementation file:
+ *   suffix _f64    : T = double, cT = double
+ *   suffix _f32    : T = float,  cT = float
+ *   suffix _f32c64 : T = float,  cT = double   (Float32 system with Float64 coordinates)
+ * where T = eltype(system) and cT = coordinates_eltype (semidiscretization.jl:326-332).
+ *
+ * All real-valued parameters cross this interface as double; callers compute them in the
+ * target precision first so the conversion back to T is exact.
+ */
+#ifndef SPH_ORACLE_H
+#define SPH_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_KERNEL_WENDLAND_C2 = 0, ORC_KERNEL_SCHOENBERG_CUBIC = 1 };
+enum { ORC_DENSITY_CONTINUITY = 0, ORC_DENSITY_SUMMATION = 1 };
+
+/* WeaklyCompressibleSPHSystem fields (wcsph/system.jl:65-86) that the RHS reads. */
+typedef struct {
+    int32_t ndims;                  /* 2 or 3 */
+    int32_t kernel;                 /* ORC_KERNEL_* */
+    int32_t density_calculator;     /* ORC_DENSITY_* */
+    int32_t clip_negative_pressure; /* StateEquationCole{..., CLIP} */
+    int32_t has_viscosity;          /* ArtificialViscosityMonaghan or nothing */
+    int32_t has_diffusion;          /* DensityDiffusionMolteniColagrossi or nothing */
+    int32_t reserved0, reserved1;
+    double smoothing_length;
+    double sound_speed, exponent, reference_density, background_pressure;
+    double alpha, beta, epsilon;    /* viscosity.jl:68-76 */
+    double delta;                   /* density_diffusion.jl:41-47 */
+    double acceleration[3];
+    double damping_coefficient;     /* SourceTermDamping, 0 = none */
+} orc_fluid_params;
+
+/* WallBoundarySystem + BoundaryModelDummyParticles{AdamiPressureExtrapolation}
+ * (wall_boundary/system.jl:22-43, dummy_particles.jl:52-77,142-149). */
+typedef struct {
+    int32_t kernel;
+    int32_t clip_negative_pressure; /* boundary model's own clip flag */
+    int32_t eos_clip_negative_pressure;
+    int32_t reserved0;
+    double smoothing_length;
+    double sound_speed, exponent, reference_density, background_pressure;
+    double pressure_offset;
+} orc_wall_params;
+
+#define ORC_DECLARE(SUF, T, CT)                                                              \
+    double orc_kernel_##SUF(int kernel, int ndims, double r, double h);                      \
+    double orc_kernel_unsafe_##SUF(int kernel, int ndims, double r, double h);               \
+    double orc_kernel_deriv_div_r_##SUF(int kernel, int ndims, double r, double h);          \
+    double orc_eos_##SUF(double c, double gamma, double rho0, double p_bg, int clip,         \
+                         double density);                                                    \
+    double orc_inverse_eos_##SUF(double c, double gamma, double rho0, double p_bg,           \
+                                 double pressure);                                           \
+    void orc_viscosity_pair_##SUF(int kernel, int ndims, double h, double alpha,             \
+                                  double beta, double epsilon, double sound_speed,           \
+                                  double m_b, double rho_a, double rho_b,                    \
+                                  const double *v_diff, const double *pos_diff,              \
+                                  double *dv_out);                                           \
+    void orc_interact_pair_##SUF(const orc_fluid_params *fp, int neighbor_is_wall,           \
+                                 double m_b, double rho_a, double rho_b, double p_a,         \
+                                 double p_b, const double *v_a, const double *v_b,           \
+                                 const double *pos_diff, double *dv_out, double *drho_out);  \
+    int64_t orc_pairs_bruteforce_##SUF(int ndims, int64_t nx, const CT *x, int64_t ny,       \
+                                       const CT *y, double radius, int64_t capacity,         \
+                                       int32_t *out_i, int32_t *out_j);                      \
+    int64_t orc_pairs_grid_##SUF(int ndims, int64_t nx, const CT *x, int64_t ny,             \
+                                 const CT *y, double radius, int64_t capacity,               \
+                                 int32_t *out_i, int32_t *out_j);                            \
+    int orc_kick_##SUF(const orc_fluid_params *fp, const orc_wall_params *wp, int64_t n_f,   \
+                       const T *mass_f, int64_t n_w, const CT *coords_w, const T *mass_w,    \
+                       const T *v_ode, const CT *u_ode, T *dv_ode, T *pressure_f,            \
+                       T *density_f, T *pressure_w, T *density_w, T *volume_w,               \
+                       int use_grid, int nthreads);                                          \
+    void orc_drift_##SUF(int ndims, int nvars_v, int64_t n_f, const T *v_ode, CT *du_ode);
+
+ORC_DECLARE(f64, double, double)
+ORC_DECLARE(f32, float, float)
+ORC_DECLARE(f32c64, float, double)
+
+int orc_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,27 @@
+"""trixiparticles.jl_b200 -- B200-native WCSPH right-hand side behind TrixiParticles.jl's
+`Semidiscretization` / `semidiscretize` / `kick!` / `drift!` interface.
+
+Only what the hot path needs lives here: the CUDA library (csrc/, built to libtpb200.so),
+its ctypes binding (_lib.py) and the host-side mirror of the reference interface.
+Import it as `import trixiparticles.jl_b200` (the `trixiparticles/` shim next to this
+directory maps the dotted name onto this folder).
+"""
+from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
+                    BoundaryModelDummyParticles, ContinuityDensity,
+                    DensityDiffusionMolteniColagrossi, SchoenbergCubicSplineKernel,
+                    SourceTermDamping, StateEquationCole, SummationDensity, WallBoundarySystem,
+                    WeaklyCompressibleSPHSystem, WendlandC2Kernel, compact_support)
+from .semidiscretization import (B200Backend, DynamicalODEProblem, FullGridCellList,
+                                 GridNeighborhoodSearch, Semidiscretization, drift_, kick_,
+                                 semidiscretize)
+from .setups import InitialCondition, RectangularShape, RectangularTank, union
+
+__all__ = [
+    "AdamiPressureExtrapolation", "ArtificialViscosityMonaghan", "BoundaryModelDummyParticles",
+    "ContinuityDensity", "DensityDiffusionMolteniColagrossi", "SchoenbergCubicSplineKernel",
+    "SourceTermDamping", "StateEquationCole", "SummationDensity", "WallBoundarySystem",
+    "WeaklyCompressibleSPHSystem", "WendlandC2Kernel", "compact_support", "B200Backend",
+    "DynamicalODEProblem", "FullGridCellList", "GridNeighborhoodSearch", "Semidiscretization",
+    "drift_", "kick_", "semidiscretize", "InitialCondition", "RectangularShape",
+    "RectangularTank", "union",
+]

@@ -1,0 +1,118 @@
+"""ctypes binding of libtpb200.so -- exactly the entry points declared in include/tpb200.h.
+
+There is no CPU fallback: if the CUDA library is missing this module raises on first use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libtpb200.so")
+
+TPB_OK = 0
+ERR_NAMES = {1: "INVALID_ARGUMENT", 2: "UNSUPPORTED", 3: "CUDA", 4: "OUT_OF_BOUNDS", 5: "STATE", 6: "CAPACITY"}
+F32, F64 = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+FIELD_PRESSURE, FIELD_DENSITY, FIELD_VOLUME = 0, 1, 2
+
+EXPORTS = [
+    "tpb_version", "tpb_last_error", "tpb_create", "tpb_destroy", "tpb_add_fluid_system",
+    "tpb_add_wall_system", "tpb_set_interaction", "tpb_semidiscretize", "tpb_ode_sizes",
+    "tpb_system_range", "tpb_kick", "tpb_drift", "tpb_get_system_field", "tpb_neighbor_pairs",
+    "tpb_synchronize", "tpb_set_stream", "tpb_get_stats", "tpb_host_register",
+    "tpb_host_unregister",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("ndims", C.c_int32), ("eltype", C.c_int32),
+        ("coords_eltype", C.c_int32), ("device", C.c_int32), ("ode_memory", C.c_int32),
+        ("has_bounds", C.c_int32), ("max_points_per_cell", C.c_int32),
+        ("deterministic", C.c_int32), ("interact_variant", C.c_int32),
+        ("min_corner", C.c_double * 3), ("max_corner", C.c_double * 3),
+    ]
+
+
+class FluidParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("kernel", C.c_int32), ("density_calculator", C.c_int32),
+        ("clip_negative_pressure", C.c_int32), ("has_viscosity", C.c_int32),
+        ("has_diffusion", C.c_int32), ("smoothing_length", C.c_double),
+        ("sound_speed", C.c_double), ("exponent", C.c_double), ("reference_density", C.c_double),
+        ("background_pressure", C.c_double), ("alpha", C.c_double), ("beta", C.c_double),
+        ("epsilon", C.c_double), ("delta", C.c_double), ("acceleration", C.c_double * 3),
+        ("damping_coefficient", C.c_double),
+    ]
+
+
+class WallParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("kernel", C.c_int32), ("clip_negative_pressure", C.c_int32),
+        ("reserved", C.c_int32), ("smoothing_length", C.c_double), ("sound_speed", C.c_double),
+        ("exponent", C.c_double), ("reference_density", C.c_double),
+        ("background_pressure", C.c_double), ("pressure_offset", C.c_double),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("kernel_launches_total", C.c_int64), ("kicks", C.c_int64), ("drifts", C.c_int64),
+        ("n_cells", C.c_int64), ("launches_last_kick", C.c_int32),
+        ("launches_last_drift", C.c_int32), ("interact_variant_used", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class TpbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"tpb200 error {code} ({ERR_NAMES.get(code, '?')}): {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libtpb200.so; raises loudly when it has not been built (no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise RuntimeError(
+            f"{SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback for the accelerated path.")
+    L = C.CDLL(SO)
+    i32, i64, p, d = C.c_int32, C.c_int64, C.c_void_p, C.c_double
+    L.tpb_version.restype = C.c_char_p; L.tpb_version.argtypes = []
+    L.tpb_last_error.restype = C.c_char_p; L.tpb_last_error.argtypes = [p]
+    L.tpb_create.restype = i32; L.tpb_create.argtypes = [C.POINTER(Config), C.POINTER(p)]
+    L.tpb_destroy.restype = i32; L.tpb_destroy.argtypes = [p]
+    L.tpb_add_fluid_system.restype = i32
+    L.tpb_add_fluid_system.argtypes = [p, C.POINTER(FluidParams), i64, p, C.POINTER(i32)]
+    L.tpb_add_wall_system.restype = i32
+    L.tpb_add_wall_system.argtypes = [p, C.POINTER(WallParams), i64, p, p, p, C.POINTER(i32)]
+    L.tpb_set_interaction.restype = i32; L.tpb_set_interaction.argtypes = [p, i32, i32, i32]
+    L.tpb_semidiscretize.restype = i32; L.tpb_semidiscretize.argtypes = [p, p]
+    L.tpb_ode_sizes.restype = i32; L.tpb_ode_sizes.argtypes = [p, C.POINTER(i64), C.POINTER(i64)]
+    L.tpb_system_range.restype = i32
+    L.tpb_system_range.argtypes = [p, i32] + [C.POINTER(i64)] * 4
+    L.tpb_kick.restype = i32; L.tpb_kick.argtypes = [p, p, p, p, d]
+    L.tpb_drift.restype = i32; L.tpb_drift.argtypes = [p, p, p, p, d]
+    L.tpb_get_system_field.restype = i32; L.tpb_get_system_field.argtypes = [p, i32, i32, p, i64]
+    L.tpb_neighbor_pairs.restype = i32
+    L.tpb_neighbor_pairs.argtypes = [p, i32, i32, p, i64, p, p, C.POINTER(i64)]
+    L.tpb_synchronize.restype = i32; L.tpb_synchronize.argtypes = [p]
+    L.tpb_set_stream.restype = i32; L.tpb_set_stream.argtypes = [p, p]
+    L.tpb_get_stats.restype = i32; L.tpb_get_stats.argtypes = [p, C.POINTER(Stats)]
+    L.tpb_host_register.restype = i32; L.tpb_host_register.argtypes = [p, i64]
+    L.tpb_host_unregister.restype = i32; L.tpb_host_unregister.argtypes = [p]
+    _lib = L
+    return L
+
+
+def check(handle, code):
+    if code != TPB_OK:
+        msg = load().tpb_last_error(handle)
+        raise TpbError(code, msg.decode() if msg else "")

@@ -1,0 +1,875 @@
+// tpb200.cu -- libtpb200.so: C ABI (include/tpb200.h) + host orchestration of the sm_100a
+// kernels in tpb_nhs.cuh / tpb_sweeps.cuh / tpb_tiles.cuh.
+//
+// Drop-in boundary: /root/reference/src/general/semidiscretization.jl `kick!` (:589-612) and
+// `drift!` (:522-536).  The library owns all device memory; nothing is allocated per call.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tpb200.h"
+#include "tpb_device.cuh"
+#include "tpb_nhs.cuh"
+#include "tpb_sweeps.cuh"
+#include "tpb_tiles.cuh"
+
+using namespace tpb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Semi {
+    tpb_config cfg{};
+    std::string err;
+    // systems (one fluid, at most one wall; numbered in call order)
+    int n_systems = 0;
+    int fluid_index = -1, wall_index = -1;
+    tpb_fluid_params fp{};
+    tpb_wall_params wp{};
+    int64_t n_f = 0, n_w = 0;
+    std::vector<unsigned char> h_mass_f, h_coords_w, h_mass_w, h_dens_w;
+    int interaction[2][2] = {{1, 1}, {1, 1}};
+    bool ready = false;
+
+    // geometry of the shared cell grid (double; typed copies are built per call)
+    double cell_size = 0, origin[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    int ncell[3] = {1, 1, 1};
+    int64_t ncells = 0;
+
+    // device
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    void *d_mass_f = nullptr;
+    void *d_u = nullptr, *d_v = nullptr, *d_dv = nullptr, *d_du = nullptr;  // host-mode staging
+    int *d_key = nullptr, *d_slot = nullptr, *d_tmp_perm = nullptr, *d_perm_f = nullptr;
+    int *d_count = nullptr, *d_fcell_start = nullptr, *d_wcell_start = nullptr;
+    int *d_block_sums = nullptr, *d_flags = nullptr;
+    int *h_flags = nullptr;  // pinned
+    void *d_A = nullptr, *d_B = nullptr, *d_P = nullptr;
+    void *d_Aw = nullptr, *d_Ww = nullptr, *d_volw = nullptr;
+    int *d_perm_w = nullptr;
+    void *d_scratch = nullptr;  // max(n_f, n_w) * sizeof(double): field unsort
+    TileState tiles;
+
+    tpb_stats stats{};
+    int launches_this_call = 0;
+    int deferred_status = TPB_OK;
+};
+
+inline size_t tsize(int eltype) { return eltype == TPB_F64 ? 8 : 4; }
+
+int fail(Semi *s, int code, const std::string &msg)
+{
+    if (s) s->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(S, EXPR)                                                                  \
+    do {                                                                                   \
+        cudaError_t e_ = (EXPR);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail((S), TPB_ERR_CUDA,                                                 \
+                        std::string(#EXPR) + ": " + cudaGetErrorString(e_));               \
+    } while (0)
+
+#define LAUNCH(S, KERNEL, GRID, BLOCK, SMEM, ...)                                          \
+    do {                                                                                   \
+        KERNEL<<<(GRID), (BLOCK), (SMEM), (S).stream>>>(__VA_ARGS__);                      \
+        (S).launches_this_call++;                                                          \
+        (S).stats.kernel_launches_total++;                                                 \
+    } while (0)
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------
+// host-side constants, computed in T with the reference's operation order
+template <typename T>
+T eps_of(T x)
+{
+    x = std::fabs(x);
+    return std::nextafter(x, std::numeric_limits<T>::infinity()) - x;
+}
+
+template <typename T>
+KernelConst<T> make_kernel_const(int kernel, int nd, double h_)
+{
+    const double pi = 3.14159265358979323846;
+    KernelConst<T> k;
+    k.h = (T)h_;
+    k.h_inv = (T)1 / k.h;
+    T sigma;
+    if (kernel == TPB_KERNEL_WENDLAND_C2)
+        sigma = nd == 2 ? (T)(7.0 / (4.0 * pi)) : (T)(21.0 / (16.0 * pi));
+    else
+        sigma = nd == 2 ? (T)(10.0 / (pi * 7.0)) : (T)(1.0 / pi);
+    k.nf = nd == 2 ? sigma * (k.h_inv * k.h_inv) : sigma * (k.h_inv * k.h_inv * k.h_inv);
+    k.m5nf = (T)(-5) * k.nf;
+    k.h_inv2 = k.h_inv * k.h_inv;
+    k.support = (T)2 * k.h;
+    return k;
+}
+
+template <typename T>
+EosConst<T> make_eos_const(double c_, double gamma_, double rho0_, double pbg_, int clip)
+{
+    EosConst<T> e;
+    T c = (T)c_, gamma = (T)gamma_, rho0 = (T)rho0_;
+    e.B = rho0 * (c * c) / gamma;
+    e.gamma = gamma;
+    e.inv_gamma = (T)1 / gamma;
+    e.rho0 = rho0;
+    e.p_bg = (T)pbg_;
+    e.clip = clip;
+    return e;
+}
+
+template <typename T>
+PairConst<T> make_pair_const(const tpb_fluid_params &fp, int nd)
+{
+    PairConst<T> k;
+    k.kern = make_kernel_const<T>(fp.kernel, nd, fp.smoothing_length);
+    T h = k.kern.h;
+    k.c = (T)fp.sound_speed;
+    k.alpha = (T)fp.alpha;
+    k.beta = (T)fp.beta;
+    k.eps = (T)fp.epsilon;
+    k.eps_h2 = k.eps * (h * h);
+    T h_avg = (h + h) / (T)2;
+    k.delta_h_c = (T)fp.delta * h_avg * k.c;
+    T R = (T)2 * h;
+    k.radius2 = R * R;
+    k.almostzero = std::sqrt(eps_of<T>(R * R));
+    k.has_viscosity = fp.has_viscosity;
+    k.has_diffusion = fp.has_diffusion;
+    return k;
+}
+
+template <typename CT>
+GridConst<CT> make_grid_const(const Semi &s)
+{
+    GridConst<CT> g;
+    for (int d = 0; d < 3; ++d) {
+        g.origin[d] = (CT)s.origin[d];
+        g.n[d] = s.ncell[d];
+        // outward-rounded bounding box in cT
+        CT lo = (CT)s.lo[d], hi = (CT)s.hi[d];
+        if ((double)lo > s.lo[d]) lo = std::nextafter(lo, -std::numeric_limits<CT>::infinity());
+        if ((double)hi < s.hi[d]) hi = std::nextafter(hi, std::numeric_limits<CT>::infinity());
+        g.lo[d] = lo;
+        g.hi[d] = hi;
+    }
+    g.inv_cell = (CT)(1.0 / s.cell_size);
+    g.ncells = (int)s.ncells;
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------
+int exclusive_scan(Semi &s, const int *d_in, int n, int *d_out)
+{
+    int nblocks = cdiv(n, SCAN_TILE);
+    if (nblocks > SCAN_TILE) return fail(&s, TPB_ERR_UNSUPPORTED, "cell grid too large for the scan");
+    LAUNCH(s, k_scan_block_sums, nblocks, SCAN_THREADS, 0, d_in, n, s.d_block_sums);
+    LAUNCH(s, k_scan_top, 1, SCAN_THREADS, 0, s.d_block_sums, nblocks);
+    LAUNCH(s, k_scan_final, nblocks, SCAN_THREADS, 0, d_in, n, s.d_block_sums, d_out);
+    return TPB_OK;
+}
+
+template <int ND, typename T, typename CT>
+struct Ops {
+    static constexpr int nv(const Semi &s) { return s.fp.density_calculator == TPB_DENSITY_SUMMATION ? ND : ND + 1; }
+
+    // ---- counting sort of one point set into the shared grid: key/slot/count/scan/scatter
+    static int bin_points(Semi &s, const CT *d_coords, int n, int *d_cell_start)
+    {
+        GridConst<CT> g = make_grid_const<CT>(s);
+        CUDA_TRY(&s, cudaMemsetAsync(s.d_count, 0, sizeof(int) * (size_t)s.ncells, s.stream));
+        if (n > 0)
+            LAUNCH(s, (k_cell_count<ND, CT>), cdiv(n, 256), 256, 0, d_coords, n, g, s.d_key,
+                   s.d_slot, s.d_count, s.d_flags);
+        int rc = exclusive_scan(s, s.d_count, (int)s.ncells, d_cell_start);
+        if (rc) return rc;
+        if (n > 0)
+            LAUNCH(s, k_scatter, cdiv(n, 256), 256, 0, s.d_key, s.d_slot, d_cell_start, n,
+                   s.d_tmp_perm);
+        return TPB_OK;
+    }
+
+    // ---- NHS rebuild of the fluid + EOS (update_nhs!, update_pressure!)
+    static int rebuild_fluid(Semi &s, const CT *d_u, const T *d_v)
+    {
+        int n = (int)s.n_f;
+        int rc = bin_points(s, d_u, n, s.d_fcell_start);
+        if (rc) return rc;
+        EosConst<T> eos = make_eos_const<T>(s.fp.sound_speed, s.fp.exponent, s.fp.reference_density,
+                                            s.fp.background_pressure, s.fp.clip_negative_pressure);
+        if (n > 0) {
+            if (s.fp.density_calculator == TPB_DENSITY_CONTINUITY)
+                LAUNCH(s, (k_reorder_fluid<ND, T, CT, 0>), cdiv(n, 256), 256, 0, d_u, d_v,
+                       (const T *)s.d_mass_f, s.d_key, s.d_fcell_start, s.d_tmp_perm, n,
+                       s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
+                       s.d_perm_f);
+            else
+                LAUNCH(s, (k_reorder_fluid<ND, T, CT, 1>), cdiv(n, 256), 256, 0, d_u, d_v,
+                       (const T *)s.d_mass_f, s.d_key, s.d_fcell_start, s.d_tmp_perm, n,
+                       s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
+                       s.d_perm_f);
+        }
+        return TPB_OK;
+    }
+
+    // ---- static wall: sorted once (initialize_neighborhood_searches!, neighborhood_search.jl:439-464)
+    static int init_wall(Semi &s)
+    {
+        int n = (int)s.n_w;
+        CT *d_coords = nullptr;
+        T *d_mass = nullptr, *d_dens = nullptr;
+        CUDA_TRY(&s, cudaMalloc(&d_coords, sizeof(CT) * ND * (size_t)std::max(n, 1)));
+        CUDA_TRY(&s, cudaMalloc(&d_mass, sizeof(T) * (size_t)std::max(n, 1)));
+        CUDA_TRY(&s, cudaMalloc(&d_dens, sizeof(T) * (size_t)std::max(n, 1)));
+        CUDA_TRY(&s, cudaMemcpyAsync(d_coords, s.h_coords_w.data(), sizeof(CT) * ND * (size_t)n,
+                                     cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(&s, cudaMemcpyAsync(d_mass, s.h_mass_w.data(), sizeof(T) * (size_t)n,
+                                     cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(&s, cudaMemcpyAsync(d_dens, s.h_dens_w.data(), sizeof(T) * (size_t)n,
+                                     cudaMemcpyHostToDevice, s.stream));
+        int rc = bin_points(s, d_coords, n, s.d_wcell_start);
+        if (rc) return rc;
+        if (n > 0)
+            LAUNCH(s, (k_reorder_wall<ND, T, CT>), cdiv(n, 256), 256, 0, d_coords, d_mass, d_dens,
+                   s.d_key, s.d_wcell_start, s.d_tmp_perm, n, (V4<CT> *)s.d_Aw, (V2<T> *)s.d_Ww,
+                   s.d_perm_w);
+        CUDA_TRY(&s, cudaMemsetAsync(s.d_volw, 0, sizeof(T) * (size_t)std::max(n, 1), s.stream));
+        CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
+        cudaFree(d_coords);
+        cudaFree(d_mass);
+        cudaFree(d_dens);
+        return TPB_OK;
+    }
+
+    template <int KERNEL>
+    static void launch_summation(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc,
+                                 const EosConst<T> &eos)
+    {
+        int n = (int)s.n_f;
+        LAUNCH(s, (k_summation_density<ND, T, CT, KERNEL>), cdiv(n, 128), 128, 0, n, g,
+               s.d_fcell_start, (const V4<CT> *)s.d_A, (int)(s.n_w > 0), s.d_wcell_start,
+               (const V4<CT> *)s.d_Aw, s.interaction[0][1], pc.kern, pc.radius2, eos,
+               (V4<T> *)s.d_B, (T *)s.d_P);
+    }
+
+    template <int KERNEL>
+    static void launch_adami(Semi &s, const GridConst<CT> &g)
+    {
+        int n = (int)s.n_w;
+        AdamiConst<T> k;
+        k.kern = make_kernel_const<T>(s.wp.kernel, ND, s.wp.smoothing_length);
+        k.eos = make_eos_const<T>(s.wp.sound_speed, s.wp.exponent, s.wp.reference_density,
+                                  s.wp.background_pressure, 0);
+        T R = (T)2 * k.kern.h;
+        k.radius2 = R * R;
+        for (int d = 0; d < 3; ++d) k.acc[d] = (T)s.fp.acceleration[d];
+        k.p_off = (T)s.wp.pressure_offset;
+        k.clip = s.wp.clip_negative_pressure;
+        LAUNCH(s, (k_adami<ND, T, CT, KERNEL>), cdiv(n, 128), 128, 0, n, g,
+               (const V4<CT> *)s.d_Aw, s.d_fcell_start, (const V4<CT> *)s.d_A,
+               (const V4<T> *)s.d_B, (const T *)s.d_P, s.interaction[1][0], k,
+               (V2<T> *)s.d_Ww, (T *)s.d_volw);
+    }
+
+    template <int KERNEL, int DENS>
+    static int launch_interact(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc, T *d_dv)
+    {
+        int n = (int)s.n_f;
+        SourceConst<T> src;
+        src.any = s.fp.damping_coefficient != 0.0;
+        for (int d = 0; d < 3; ++d) {
+            src.acc[d] = (T)s.fp.acceleration[d];
+            src.any |= s.fp.acceleration[d] != 0.0;
+        }
+        src.damping = (T)s.fp.damping_coefficient;
+        int has_wall = s.n_w > 0 && s.interaction[0][1];
+        int variant = s.cfg.interact_variant;
+        if (variant == 0) variant = tiles_supported<ND, T, CT>() ? 2 : 1;
+        if (variant == 2 && !tiles_supported<ND, T, CT>()) variant = 1;
+        s.stats.interact_variant_used = variant;
+        if (variant == 2) {
+            return launch_interact_tiles<ND, T, CT, KERNEL, DENS>(
+                s.tiles, s.stream, n, g, s.d_fcell_start, (const V4<CT> *)s.d_A,
+                (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f, s.interaction[0][0], has_wall,
+                s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv,
+                s.launches_this_call, s.stats.kernel_launches_total);
+        }
+        LAUNCH(s, (k_interact_pp<ND, T, CT, KERNEL, DENS>), cdiv(n, 128), 128, 0, n, g,
+               s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
+               s.d_perm_f, s.interaction[0][0], has_wall, s.d_wcell_start,
+               (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv);
+        return TPB_OK;
+    }
+
+    // ---- kick! on device pointers
+    static int kick_device(Semi &s, T *d_dv, const T *d_v, const CT *d_u)
+    {
+        if (s.n_f == 0) return TPB_OK;
+        int rc = rebuild_fluid(s, d_u, d_v);
+        if (rc) return rc;
+        GridConst<CT> g = make_grid_const<CT>(s);
+        PairConst<T> pc = make_pair_const<T>(s.fp, ND);
+        EosConst<T> eos = make_eos_const<T>(s.fp.sound_speed, s.fp.exponent, s.fp.reference_density,
+                                            s.fp.background_pressure, s.fp.clip_negative_pressure);
+        const bool summ = s.fp.density_calculator == TPB_DENSITY_SUMMATION;
+        if (summ) {
+            if (s.fp.kernel == 0) launch_summation<0>(s, g, pc, eos);
+            else launch_summation<1>(s, g, pc, eos);
+        }
+        if (s.n_w > 0) {
+            if (s.wp.kernel == 0) launch_adami<0>(s, g);
+            else launch_adami<1>(s, g);
+        }
+        if (s.fp.kernel == 0)
+            rc = summ ? launch_interact<0, 1>(s, g, pc, d_dv) : launch_interact<0, 0>(s, g, pc, d_dv);
+        else
+            rc = summ ? launch_interact<1, 1>(s, g, pc, d_dv) : launch_interact<1, 0>(s, g, pc, d_dv);
+        if (rc) return rc;
+        CUDA_TRY(&s, cudaGetLastError());
+        return TPB_OK;
+    }
+
+    static int kick(Semi &s, void *dv, const void *v, const void *u)
+    {
+        const size_t nu = sizeof(CT) * ND * (size_t)s.n_f, nvb = sizeof(T) * nv(s) * (size_t)s.n_f;
+        s.launches_this_call = 0;
+        int rc;
+        if (s.cfg.ode_memory == TPB_MEM_HOST) {
+            CUDA_TRY(&s, cudaMemcpyAsync(s.d_u, u, nu, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(&s, cudaMemcpyAsync(s.d_v, v, nvb, cudaMemcpyHostToDevice, s.stream));
+            rc = kick_device(s, (T *)s.d_dv, (const T *)s.d_v, (const CT *)s.d_u);
+            if (rc) return rc;
+            CUDA_TRY(&s, cudaMemcpyAsync(dv, s.d_dv, nvb, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(&s, cudaMemcpyAsync(s.h_flags, s.d_flags, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
+            if (*s.h_flags & 1)
+                return fail(&s, TPB_ERR_OUT_OF_BOUNDS,
+                            "particle coordinates are NaN or outside the FullGridCellList bounding box");
+        } else {
+            rc = kick_device(s, (T *)dv, (const T *)v, (const CT *)u);
+            if (rc) return rc;
+            CUDA_TRY(&s, cudaMemcpyAsync(s.h_flags, s.d_flags, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        }
+        s.stats.kicks++;
+        s.stats.launches_last_kick = s.launches_this_call;
+        return TPB_OK;
+    }
+
+    static int drift(Semi &s, void *du, const void *v, const void *u)
+    {
+        (void)u;
+        const size_t nu = sizeof(CT) * ND * (size_t)s.n_f, nvb = sizeof(T) * nv(s) * (size_t)s.n_f;
+        s.launches_this_call = 0;
+        int64_t total = s.n_f * ND;
+        if (total == 0) return TPB_OK;
+        if (s.cfg.ode_memory == TPB_MEM_HOST) {
+            CUDA_TRY(&s, cudaMemcpyAsync(s.d_v, v, nvb, cudaMemcpyHostToDevice, s.stream));
+            LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total, 256), 256, 0, total, nv(s), (const T *)s.d_v,
+                   (CT *)s.d_du);
+            CUDA_TRY(&s, cudaMemcpyAsync(du, s.d_du, nu, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
+        } else {
+            LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total, 256), 256, 0, total, nv(s), (const T *)v,
+                   (CT *)du);
+            CUDA_TRY(&s, cudaGetLastError());
+        }
+        s.stats.drifts++;
+        s.stats.launches_last_drift = s.launches_this_call;
+        return TPB_OK;
+    }
+
+    static int get_field(Semi &s, int system, int field, void *out, int64_t n)
+    {
+        T *scratch = (T *)s.d_scratch;
+        if (system == s.fluid_index) {
+            if (n != s.n_f) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
+            if (n == 0) return TPB_OK;
+            if (field == TPB_FIELD_PRESSURE)
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_perm_f, (const T *)s.d_P, 1, 0, scratch);
+            else if (field == TPB_FIELD_DENSITY)
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_perm_f, (const T *)s.d_B, 4, 3, scratch);
+            else
+                return fail(&s, TPB_ERR_INVALID_ARGUMENT, "unknown fluid field");
+        } else if (system == s.wall_index) {
+            if (n != s.n_w) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
+            if (n == 0) return TPB_OK;
+            if (field == TPB_FIELD_PRESSURE)
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_perm_w, (const T *)s.d_Ww, 2, 0, scratch);
+            else if (field == TPB_FIELD_DENSITY)
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_perm_w, (const T *)s.d_Ww, 2, 1, scratch);
+            else if (field == TPB_FIELD_VOLUME)
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_perm_w, (const T *)s.d_volw, 1, 0, scratch);
+            else
+                return fail(&s, TPB_ERR_INVALID_ARGUMENT, "unknown wall field");
+        } else {
+            return fail(&s, TPB_ERR_INVALID_ARGUMENT, "unknown system index");
+        }
+        CUDA_TRY(&s, cudaMemcpyAsync(out, scratch, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
+        return TPB_OK;
+    }
+
+    static int neighbor_pairs(Semi &s, int system, int neighbor, const void *u_ode, int64_t capacity,
+                              int32_t *out_i, int32_t *out_j, int64_t *count)
+    {
+        // rebuild the fluid grid for the given coordinates (velocities are irrelevant here)
+        const size_t nu = sizeof(CT) * ND * (size_t)s.n_f, nvb = sizeof(T) * nv(s) * (size_t)s.n_f;
+        const CT *d_u = (const CT *)u_ode;
+        T *d_vzero = nullptr;
+        CUDA_TRY(&s, cudaMalloc(&d_vzero, std::max(nvb, (size_t)16)));
+        CUDA_TRY(&s, cudaMemsetAsync(d_vzero, 0, std::max(nvb, (size_t)16), s.stream));
+        CT *d_utmp = nullptr;
+        if (s.cfg.ode_memory == TPB_MEM_HOST) {
+            CUDA_TRY(&s, cudaMalloc(&d_utmp, std::max(nu, (size_t)16)));
+            CUDA_TRY(&s, cudaMemcpyAsync(d_utmp, u_ode, nu, cudaMemcpyHostToDevice, s.stream));
+            d_u = d_utmp;
+        }
+        int rc = rebuild_fluid(s, d_u, d_vzero);
+        if (rc) return rc;
+        GridConst<CT> g = make_grid_const<CT>(s);
+        const bool x_fluid = system == s.fluid_index, y_fluid = neighbor == s.fluid_index;
+        if ((!x_fluid && system != s.wall_index) || (!y_fluid && neighbor != s.wall_index))
+            return fail(&s, TPB_ERR_INVALID_ARGUMENT, "unknown system index");
+        // radius of the ordered pair: compact_support(system, neighbor)
+        T h = x_fluid ? (T)s.fp.smoothing_length : (T)s.wp.smoothing_length;
+        T R = (T)2 * h;
+        T r2 = R * R;
+        int n_x = (int)(x_fluid ? s.n_f : s.n_w);
+        int *d_oi = nullptr, *d_oj = nullptr;
+        unsigned long long *d_counter = nullptr;
+        CUDA_TRY(&s, cudaMalloc(&d_oi, sizeof(int) * (size_t)std::max<int64_t>(capacity, 1)));
+        CUDA_TRY(&s, cudaMalloc(&d_oj, sizeof(int) * (size_t)std::max<int64_t>(capacity, 1)));
+        CUDA_TRY(&s, cudaMalloc(&d_counter, sizeof(unsigned long long)));
+        CUDA_TRY(&s, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), s.stream));
+        if (n_x > 0)
+            LAUNCH(s, (k_pairs<ND, T, CT>), cdiv(n_x, 128), 128, 0, n_x, g,
+                   (const V4<CT> *)(x_fluid ? s.d_A : s.d_Aw), x_fluid ? s.d_perm_f : s.d_perm_w,
+                   y_fluid ? s.d_fcell_start : s.d_wcell_start,
+                   (const V4<CT> *)(y_fluid ? s.d_A : s.d_Aw), y_fluid ? s.d_perm_f : s.d_perm_w, r2,
+                   (long long)capacity, d_oi, d_oj, d_counter);
+        unsigned long long h_count = 0;
+        CUDA_TRY(&s, cudaMemcpyAsync(&h_count, d_counter, sizeof(h_count), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
+        *count = (int64_t)h_count;
+        int64_t ncopy = std::min<int64_t>((int64_t)h_count, capacity);
+        if (ncopy > 0) {
+            CUDA_TRY(&s, cudaMemcpy(out_i, d_oi, sizeof(int) * (size_t)ncopy, cudaMemcpyDeviceToHost));
+            CUDA_TRY(&s, cudaMemcpy(out_j, d_oj, sizeof(int) * (size_t)ncopy, cudaMemcpyDeviceToHost));
+        }
+        cudaFree(d_oi); cudaFree(d_oj); cudaFree(d_counter); cudaFree(d_vzero);
+        if (d_utmp) cudaFree(d_utmp);
+        CUDA_TRY(&s, cudaMemcpy(s.h_flags, s.d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+        if (*s.h_flags & 1)
+            return fail(&s, TPB_ERR_OUT_OF_BOUNDS, "particle coordinates are NaN or outside the bounding box");
+        if ((int64_t)h_count > capacity) return fail(&s, TPB_ERR_CAPACITY, "pair buffer too small");
+        return TPB_OK;
+    }
+};
+
+#define DISPATCH(S, CALL)                                                                     \
+    do {                                                                                      \
+        const int nd_ = (S).cfg.ndims, t_ = (S).cfg.eltype, ct_ = (S).cfg.coords_eltype;      \
+        if (nd_ == 2 && t_ == TPB_F32 && ct_ == TPB_F32) return Ops<2, float, float>::CALL;   \
+        if (nd_ == 3 && t_ == TPB_F32 && ct_ == TPB_F32) return Ops<3, float, float>::CALL;   \
+        if (nd_ == 2 && t_ == TPB_F32 && ct_ == TPB_F64) return Ops<2, float, double>::CALL;  \
+        if (nd_ == 3 && t_ == TPB_F32 && ct_ == TPB_F64) return Ops<3, float, double>::CALL;  \
+        if (nd_ == 2 && t_ == TPB_F64 && ct_ == TPB_F64) return Ops<2, double, double>::CALL; \
+        if (nd_ == 3 && t_ == TPB_F64 && ct_ == TPB_F64) return Ops<3, double, double>::CALL; \
+        return fail(&(S), TPB_ERR_UNSUPPORTED, "unsupported ndims / eltype combination");     \
+    } while (0)
+
+int dispatch_init_wall(Semi &s) { DISPATCH(s, init_wall(s)); }
+int dispatch_kick(Semi &s, void *dv, const void *v, const void *u) { DISPATCH(s, kick(s, dv, v, u)); }
+int dispatch_drift(Semi &s, void *du, const void *v, const void *u) { DISPATCH(s, drift(s, du, v, u)); }
+int dispatch_get_field(Semi &s, int sys, int field, void *out, int64_t n) { DISPATCH(s, get_field(s, sys, field, out, n)); }
+int dispatch_pairs(Semi &s, int sys, int nb, const void *u, int64_t cap, int32_t *oi, int32_t *oj, int64_t *cnt)
+{
+    DISPATCH(s, neighbor_pairs(s, sys, nb, u, cap, oi, oj, cnt));
+}
+
+void free_device(Semi &s)
+{
+    void *ptrs[] = {s.d_mass_f, s.d_u, s.d_v, s.d_dv, s.d_du, s.d_key, s.d_slot, s.d_tmp_perm,
+                    s.d_perm_f, s.d_count, s.d_fcell_start, s.d_wcell_start, s.d_block_sums,
+                    s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_perm_w,
+                    s.d_scratch};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    tiles_free(s.tiles);
+    if (s.h_flags) cudaFreeHost(s.h_flags);
+    if (s.own_stream) cudaStreamDestroy(s.own_stream);
+}
+
+double as_double(const unsigned char *p, int eltype, size_t i)
+{
+    return eltype == TPB_F64 ? ((const double *)p)[i] : (double)((const float *)p)[i];
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char *tpb_version(void) { return "tpb200 0.1 (sm_100a)"; }
+
+const char *tpb_last_error(tpb_semi_t semi)
+{
+    return semi ? ((Semi *)semi)->err.c_str() : g_create_error.c_str();
+}
+
+int32_t tpb_create(const tpb_config *config, tpb_semi_t *out)
+{
+    if (!config || !out) return fail(nullptr, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (config->struct_size != (int32_t)sizeof(tpb_config))
+        return fail(nullptr, TPB_ERR_INVALID_ARGUMENT, "tpb_config.struct_size mismatch");
+    if (config->ndims != 2 && config->ndims != 3)
+        return fail(nullptr, TPB_ERR_INVALID_ARGUMENT, "ndims must be 2 or 3");
+    if ((config->eltype != TPB_F32 && config->eltype != TPB_F64) ||
+        (config->coords_eltype != TPB_F32 && config->coords_eltype != TPB_F64))
+        return fail(nullptr, TPB_ERR_INVALID_ARGUMENT, "eltype must be TPB_F32 or TPB_F64");
+    if (config->eltype == TPB_F64 && config->coords_eltype == TPB_F32)
+        return fail(nullptr, TPB_ERR_INVALID_ARGUMENT,
+                    "coordinates eltype must not be narrower than the system eltype");
+    if (config->ode_memory != TPB_MEM_HOST && config->ode_memory != TPB_MEM_DEVICE)
+        return fail(nullptr, TPB_ERR_INVALID_ARGUMENT, "ode_memory must be TPB_MEM_HOST or TPB_MEM_DEVICE");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TPB_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (config->device < 0 || config->device >= ndev)
+        return fail(nullptr, TPB_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    e = cudaSetDevice(config->device);
+    if (e != cudaSuccess) return fail(nullptr, TPB_ERR_CUDA, cudaGetErrorString(e));
+    Semi *s = new Semi();
+    s->cfg = *config;
+    e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(nullptr, TPB_ERR_CUDA, cudaGetErrorString(e));
+    }
+    s->stream = s->own_stream;
+    *out = (tpb_semi_t)s;
+    return TPB_OK;
+}
+
+int32_t tpb_destroy(tpb_semi_t semi)
+{
+    if (!semi) return TPB_OK;
+    Semi *s = (Semi *)semi;
+    cudaSetDevice(s->cfg.device);
+    cudaStreamSynchronize(s->stream);
+    free_device(*s);
+    delete s;
+    return TPB_OK;
+}
+
+int32_t tpb_add_fluid_system(tpb_semi_t semi, const tpb_fluid_params *p, int64_t n, const void *mass,
+                             int32_t *system_index)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !p || (n > 0 && !mass)) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (s->ready) return fail(s, TPB_ERR_STATE, "systems must be added before tpb_semidiscretize");
+    if (p->struct_size != (int32_t)sizeof(tpb_fluid_params))
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "tpb_fluid_params.struct_size mismatch");
+    if (s->fluid_index >= 0)
+        return fail(s, TPB_ERR_UNSUPPORTED, "only one fluid system per semidiscretization is supported");
+    if (p->kernel != TPB_KERNEL_WENDLAND_C2 && p->kernel != TPB_KERNEL_SCHOENBERG_CUBIC)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown smoothing kernel");
+    if (p->density_calculator != TPB_DENSITY_CONTINUITY && p->density_calculator != TPB_DENSITY_SUMMATION)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown density calculator");
+    if (!(p->smoothing_length > 0) || !(p->sound_speed > 0) || !(p->reference_density > 0) || p->exponent == 0)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "smoothing_length, sound_speed, reference_density must be positive");
+    if (p->has_diffusion && p->density_calculator == TPB_DENSITY_SUMMATION)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "density diffusion requires ContinuityDensity");
+    if (n < 0 || n > 0x7fffffff / 4) return fail(s, TPB_ERR_INVALID_ARGUMENT, "particle count out of range");
+    s->fp = *p;
+    s->n_f = n;
+    s->h_mass_f.assign((const unsigned char *)mass, (const unsigned char *)mass + tsize(s->cfg.eltype) * (size_t)n);
+    s->fluid_index = s->n_systems++;
+    if (system_index) *system_index = s->fluid_index;
+    return TPB_OK;
+}
+
+int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *p, int64_t n, const void *coords,
+                            const void *hydrodynamic_mass, const void *initial_density,
+                            int32_t *system_index)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !p || (n > 0 && (!coords || !hydrodynamic_mass || !initial_density)))
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (s->ready) return fail(s, TPB_ERR_STATE, "systems must be added before tpb_semidiscretize");
+    if (p->struct_size != (int32_t)sizeof(tpb_wall_params))
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "tpb_wall_params.struct_size mismatch");
+    if (s->wall_index >= 0)
+        return fail(s, TPB_ERR_UNSUPPORTED, "only one wall system per semidiscretization is supported");
+    if (p->kernel != TPB_KERNEL_WENDLAND_C2 && p->kernel != TPB_KERNEL_SCHOENBERG_CUBIC)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown smoothing kernel");
+    if (!(p->smoothing_length > 0) || !(p->sound_speed > 0) || !(p->reference_density > 0) || p->exponent == 0)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "smoothing_length, sound_speed, reference_density must be positive");
+    if (n < 0 || n > 0x7fffffff / 4) return fail(s, TPB_ERR_INVALID_ARGUMENT, "particle count out of range");
+    s->wp = *p;
+    s->n_w = n;
+    const size_t ts = tsize(s->cfg.eltype), cs = tsize(s->cfg.coords_eltype);
+    s->h_coords_w.assign((const unsigned char *)coords, (const unsigned char *)coords + cs * s->cfg.ndims * (size_t)n);
+    s->h_mass_w.assign((const unsigned char *)hydrodynamic_mass, (const unsigned char *)hydrodynamic_mass + ts * (size_t)n);
+    s->h_dens_w.assign((const unsigned char *)initial_density, (const unsigned char *)initial_density + ts * (size_t)n);
+    s->wall_index = s->n_systems++;
+    if (system_index) *system_index = s->wall_index;
+    return TPB_OK;
+}
+
+int32_t tpb_set_interaction(tpb_semi_t semi, int32_t system, int32_t neighbor, int32_t enabled)
+{
+    Semi *s = (Semi *)semi;
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    if (system < 0 || system >= s->n_systems || neighbor < 0 || neighbor >= s->n_systems)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "system index out of range");
+    // internal matrix is indexed [fluid=0|wall=1]
+    int a = system == s->fluid_index ? 0 : 1, b = neighbor == s->fluid_index ? 0 : 1;
+    s->interaction[a][b] = enabled ? 1 : 0;
+    return TPB_OK;
+}
+
+int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
+{
+    Semi *s = (Semi *)semi;
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    if (s->ready) return fail(s, TPB_ERR_STATE, "tpb_semidiscretize was already called");
+    if (s->fluid_index < 0) return fail(s, TPB_ERR_INVALID_ARGUMENT, "a fluid system is required");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    const int nd = s->cfg.ndims;
+    const size_t ts = tsize(s->cfg.eltype), cs = tsize(s->cfg.coords_eltype);
+
+    // search radii in T: compact_support = 2h (smoothing_kernels.jl:215,400)
+    auto radius = [&](double h) {
+        return s->cfg.eltype == TPB_F64 ? 2.0 * h : (double)(2.0f * (float)h);
+    };
+    double R = radius(s->fp.smoothing_length);
+    if (s->wall_index >= 0) R = std::max(R, radius(s->wp.smoothing_length));
+
+    // bounding box
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    if (s->cfg.has_bounds) {
+        for (int d = 0; d < nd; ++d) {
+            lo[d] = s->cfg.min_corner[d];
+            hi[d] = s->cfg.max_corner[d];
+            if (!(hi[d] > lo[d])) return fail(s, TPB_ERR_INVALID_ARGUMENT, "max_corner must exceed min_corner");
+        }
+    } else {
+        bool first = true;
+        auto extend = [&](const unsigned char *p, int64_t n) {
+            for (int64_t i = 0; i < n; ++i)
+                for (int d = 0; d < nd; ++d) {
+                    double v = as_double(p, s->cfg.coords_eltype, (size_t)i * nd + d);
+                    if (first && d == 0) { for (int e = 0; e < nd; ++e) lo[e] = hi[e] = as_double(p, s->cfg.coords_eltype, (size_t)i * nd + e); first = false; }
+                    lo[d] = std::min(lo[d], v);
+                    hi[d] = std::max(hi[d], v);
+                }
+        };
+        if (u0_ode && s->n_f > 0) extend((const unsigned char *)u0_ode, s->n_f);
+        if (s->n_w > 0) extend(s->h_coords_w.data(), s->n_w);
+        if (first) return fail(s, TPB_ERR_INVALID_ARGUMENT, "no coordinates to derive the bounding box from");
+        for (int d = 0; d < nd; ++d) { lo[d] -= 2 * R; hi[d] += 2 * R; }
+    }
+    // cell size = R (1 + margin): the margin absorbs the rounding of the cT cell-coordinate
+    // computation so that |x_i - x_j| <= R always implies adjacent cells
+    double eps_ct = s->cfg.coords_eltype == TPB_F64 ? 2.220446049250313e-16 : 1.1920929e-07;
+    double max_cells = 4;
+    for (int d = 0; d < nd; ++d) max_cells = std::max(max_cells, (hi[d] - lo[d]) / R + 4);
+    double max_abs = 0;
+    for (int d = 0; d < nd; ++d) max_abs = std::max(max_abs, std::max(std::fabs(lo[d]), std::fabs(hi[d])) / R + 4);
+    double margin = std::max(1e-6, 16 * eps_ct * std::max(max_cells, max_abs));
+    s->cell_size = R * (1 + margin);
+    s->ncells = 1;
+    for (int d = 0; d < 3; ++d) {
+        if (d < nd) {
+            s->lo[d] = lo[d];
+            s->hi[d] = hi[d];
+            s->origin[d] = lo[d] - 1.001 * s->cell_size;
+            s->ncell[d] = (int)std::floor((hi[d] - s->origin[d]) / s->cell_size) + 3;
+        } else {
+            s->lo[d] = s->hi[d] = s->origin[d] = 0;
+            s->ncell[d] = 1;
+        }
+        s->ncells *= s->ncell[d];
+    }
+    if (s->ncells + 4 > (int64_t)SCAN_TILE * SCAN_TILE || s->ncells > 0x7ffffff0)
+        return fail(s, TPB_ERR_UNSUPPORTED, "bounding box / search radius gives too many cells");
+
+    // device buffers
+    const size_t nf = (size_t)std::max<int64_t>(s->n_f, 1), nw = (size_t)std::max<int64_t>(s->n_w, 1);
+    const size_t nmax = std::max(nf, nw);
+    const int nvars = s->fp.density_calculator == TPB_DENSITY_SUMMATION ? nd : nd + 1;
+    CUDA_TRY(s, cudaMalloc(&s->d_mass_f, ts * nf));
+    CUDA_TRY(s, cudaMemcpy(s->d_mass_f, s->h_mass_f.data(), ts * (size_t)s->n_f, cudaMemcpyHostToDevice));
+    if (s->cfg.ode_memory == TPB_MEM_HOST) {
+        CUDA_TRY(s, cudaMalloc(&s->d_u, cs * nd * nf));
+        CUDA_TRY(s, cudaMalloc(&s->d_v, ts * nvars * nf));
+        CUDA_TRY(s, cudaMalloc(&s->d_dv, ts * nvars * nf));
+        CUDA_TRY(s, cudaMalloc(&s->d_du, cs * nd * nf));
+    }
+    CUDA_TRY(s, cudaMalloc(&s->d_key, sizeof(int) * nmax));
+    CUDA_TRY(s, cudaMalloc(&s->d_slot, sizeof(int) * nmax));
+    CUDA_TRY(s, cudaMalloc(&s->d_tmp_perm, sizeof(int) * nmax));
+    CUDA_TRY(s, cudaMalloc(&s->d_perm_f, sizeof(int) * nf));
+    CUDA_TRY(s, cudaMalloc(&s->d_perm_w, sizeof(int) * nw));
+    CUDA_TRY(s, cudaMalloc(&s->d_count, sizeof(int) * (size_t)(s->ncells + 4)));
+    CUDA_TRY(s, cudaMalloc(&s->d_fcell_start, sizeof(int) * (size_t)(s->ncells + 4)));
+    CUDA_TRY(s, cudaMalloc(&s->d_wcell_start, sizeof(int) * (size_t)(s->ncells + 4)));
+    CUDA_TRY(s, cudaMemset(s->d_wcell_start, 0, sizeof(int) * (size_t)(s->ncells + 4)));
+    CUDA_TRY(s, cudaMalloc(&s->d_block_sums, sizeof(int) * (size_t)SCAN_TILE));
+    CUDA_TRY(s, cudaMalloc(&s->d_flags, sizeof(int) * 4));
+    CUDA_TRY(s, cudaMemset(s->d_flags, 0, sizeof(int) * 4));
+    CUDA_TRY(s, cudaHostAlloc(&s->h_flags, sizeof(int) * 4, cudaHostAllocDefault));
+    s->h_flags[0] = 0;
+    // +1 record of slack so vector loads at the end of the last run stay inside the buffer
+    CUDA_TRY(s, cudaMalloc(&s->d_A, 4 * cs * (nf + 8)));
+    CUDA_TRY(s, cudaMalloc(&s->d_B, 4 * ts * (nf + 8)));
+    CUDA_TRY(s, cudaMalloc(&s->d_P, ts * (nf + 8)));
+    CUDA_TRY(s, cudaMalloc(&s->d_Aw, 4 * cs * (nw + 8)));
+    CUDA_TRY(s, cudaMalloc(&s->d_Ww, 2 * ts * (nw + 8)));
+    CUDA_TRY(s, cudaMalloc(&s->d_volw, ts * (nw + 8)));
+    CUDA_TRY(s, cudaMalloc(&s->d_scratch, sizeof(double) * nmax));
+    CUDA_TRY(s, cudaMemset(s->d_A, 0, 4 * cs * (nf + 8)));
+    CUDA_TRY(s, cudaMemset(s->d_B, 0, 4 * ts * (nf + 8)));
+    CUDA_TRY(s, cudaMemset(s->d_P, 0, ts * (nf + 8)));
+    CUDA_TRY(s, cudaMemset(s->d_Aw, 0, 4 * cs * (nw + 8)));
+    CUDA_TRY(s, cudaMemset(s->d_Ww, 0, 2 * ts * (nw + 8)));
+    int rc = tiles_alloc(s->tiles, s->ncells, s->n_f);
+    if (rc) return fail(s, TPB_ERR_CUDA, "tile scheduler allocation failed");
+
+    s->stats.n_cells = s->ncells;
+    if (s->wall_index >= 0) {
+        rc = dispatch_init_wall(*s);
+        if (rc) return rc;
+        CUDA_TRY(s, cudaMemcpy(s->h_flags, s->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+        if (*s->h_flags & 1)
+            return fail(s, TPB_ERR_OUT_OF_BOUNDS, "wall particles outside the bounding box");
+    }
+    s->h_mass_f.clear(); s->h_mass_f.shrink_to_fit();
+    s->h_mass_w.clear(); s->h_mass_w.shrink_to_fit();
+    s->h_dens_w.clear(); s->h_dens_w.shrink_to_fit();
+    s->ready = true;
+    return TPB_OK;
+}
+
+int32_t tpb_ode_sizes(tpb_semi_t semi, int64_t *n_u, int64_t *n_v)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || s->fluid_index < 0) return fail(s, TPB_ERR_STATE, "no fluid system");
+    const int nd = s->cfg.ndims;
+    const int nvars = s->fp.density_calculator == TPB_DENSITY_SUMMATION ? nd : nd + 1;
+    if (n_u) *n_u = s->n_f * nd;
+    if (n_v) *n_v = s->n_f * nvars;
+    return TPB_OK;
+}
+
+int32_t tpb_system_range(tpb_semi_t semi, int32_t system, int64_t *u_first, int64_t *u_len,
+                         int64_t *v_first, int64_t *v_len)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || system < 0 || system >= s->n_systems) return fail(s, TPB_ERR_INVALID_ARGUMENT, "system index out of range");
+    int64_t nu = 0, nv = 0;
+    tpb_ode_sizes(semi, &nu, &nv);
+    const bool is_fluid = system == s->fluid_index;
+    // the wall has no integrated particles: zero-length range placed after/before the fluid
+    const bool wall_first = s->wall_index >= 0 && s->wall_index < s->fluid_index;
+    if (u_first) *u_first = is_fluid ? 0 : (wall_first ? 0 : nu);
+    if (u_len) *u_len = is_fluid ? nu : 0;
+    if (v_first) *v_first = is_fluid ? 0 : (wall_first ? 0 : nv);
+    if (v_len) *v_len = is_fluid ? nv : 0;
+    return TPB_OK;
+}
+
+int32_t tpb_kick(tpb_semi_t semi, void *dv_ode, const void *v_ode, const void *u_ode, double t)
+{
+    (void)t;
+    Semi *s = (Semi *)semi;
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    if (!s->ready) return fail(s, TPB_ERR_STATE, "tpb_kick before tpb_semidiscretize");
+    if (s->n_f > 0 && (!dv_ode || !v_ode || !u_ode)) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null ODE vector");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    return dispatch_kick(*s, dv_ode, v_ode, u_ode);
+}
+
+int32_t tpb_drift(tpb_semi_t semi, void *du_ode, const void *v_ode, const void *u_ode, double t)
+{
+    (void)t;
+    Semi *s = (Semi *)semi;
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    if (!s->ready) return fail(s, TPB_ERR_STATE, "tpb_drift before tpb_semidiscretize");
+    if (s->n_f > 0 && (!du_ode || !v_ode)) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null ODE vector");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    return dispatch_drift(*s, du_ode, v_ode, u_ode);
+}
+
+int32_t tpb_get_system_field(tpb_semi_t semi, int32_t system, int32_t field, void *out, int64_t n)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !out) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->ready) return fail(s, TPB_ERR_STATE, "tpb_get_system_field before tpb_semidiscretize");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    return dispatch_get_field(*s, system, field, out, n);
+}
+
+int32_t tpb_neighbor_pairs(tpb_semi_t semi, int32_t system, int32_t neighbor, const void *u_ode,
+                           int64_t capacity, int32_t *out_i, int32_t *out_j, int64_t *count)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !count || (capacity > 0 && (!out_i || !out_j))) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->ready) return fail(s, TPB_ERR_STATE, "tpb_neighbor_pairs before tpb_semidiscretize");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    return dispatch_pairs(*s, system, neighbor, u_ode, capacity, out_i, out_j, count);
+}
+
+int32_t tpb_synchronize(tpb_semi_t semi)
+{
+    Semi *s = (Semi *)semi;
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    if (s->h_flags && (*s->h_flags & 1))
+        return fail(s, TPB_ERR_OUT_OF_BOUNDS,
+                    "particle coordinates are NaN or outside the FullGridCellList bounding box");
+    return TPB_OK;
+}
+
+int32_t tpb_set_stream(tpb_semi_t semi, void *stream)
+{
+    Semi *s = (Semi *)semi;
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    s->stream = stream ? (cudaStream_t)stream : s->own_stream;
+    return TPB_OK;
+}
+
+int32_t tpb_get_stats(tpb_semi_t semi, tpb_stats *out)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !out) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    *out = s->stats;
+    return TPB_OK;
+}
+
+int32_t tpb_host_register(void *ptr, int64_t bytes)
+{
+    return cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault) == cudaSuccess ? TPB_OK : TPB_ERR_CUDA;
+}
+
+int32_t tpb_host_unregister(void *ptr)
+{
+    return cudaHostUnregister(ptr) == cudaSuccess ? TPB_OK : TPB_ERR_CUDA;
+}
+
+}  // extern "C"

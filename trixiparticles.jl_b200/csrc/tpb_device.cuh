@@ -1,0 +1,260 @@
+// tpb_device.cuh -- device-side building blocks of the WCSPH right-hand side:
+// vector records, exactly-rounded neighbour predicate, smoothing kernels, Cole equation of
+// state and the per-pair physics.  Hand-written for sm_100a; no library calls.
+//
+// Paths cited are relative to /root/reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tpb {
+
+// ---------------------------------------------------------------------------------------
+// Sorted particle records (HBM layout, see DESIGN.md "Data layout"):
+//   A[j] = (x, y, z, m)      in cT   -- position + hydrodynamic mass
+//   B[j] = (vx, vy, vz, rho) in T    -- velocity + density          (fluid only)
+//   P[j] = p                 in T    -- pressure                    (fluid)
+//   W[j] = (p, rho)          in T    -- Adami pressure / density    (wall)
+// 16-byte records make every neighbour-cell run a 16-byte aligned, contiguous stream.
+template <typename T>
+struct alignas(16) V4 {
+    T x, y, z, w;
+};
+template <typename T>
+struct alignas(2 * sizeof(T)) V2 {
+    T x, y;
+};
+
+// ---------------------------------------------------------------------------------------
+// Exactly rounded primitives.  The neighbour predicate must reproduce
+//   pos_diff = convert.(T, x_i - y_j); d2 = dot(pos_diff, pos_diff); d2 <= R^2
+// bit for bit (PointNeighbors.jl foreach_neighbor; StaticArrays `dot` is a left-to-right
+// sum of products, Julia never contracts to fma), so nvcc must not fuse these.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+
+// div_fast (util.jl:3-5): exact division for Float64; for Float32 the reference's GPU path
+// uses LLVM fast division, mirrored here by the approximate (<= 2 ulp) hardware divide.
+__device__ __forceinline__ float div_fast(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double div_fast(double a, double b) { return a / b; }
+
+template <int ND, typename T, typename CT>
+__device__ __forceinline__ T pos_diff_d2(const V4<CT> &xi, const V4<CT> &xj, T (&pd)[3])
+{
+    pd[0] = (T)sub_rn(xi.x, xj.x);
+    pd[1] = (T)sub_rn(xi.y, xj.y);
+    T d2 = add_rn(mul_rn(pd[0], pd[0]), mul_rn(pd[1], pd[1]));
+    if (ND == 3) {
+        pd[2] = (T)sub_rn(xi.z, xj.z);
+        d2 = add_rn(d2, mul_rn(pd[2], pd[2]));
+    } else {
+        pd[2] = (T)0;
+    }
+    return d2;
+}
+
+// ---------------------------------------------------------------------------------------
+// Smoothing kernels.  Constants are prepared on the host in T with the reference's own
+// operation order (smoothing_kernels.jl:193-227, :436-455).
+template <typename T>
+struct KernelConst {
+    T h;        // smoothing length
+    T h_inv;    // 1 / h
+    T nf;       // normalization_factor(kernel, h_inv) = sigma * h_inv^ND
+    T m5nf;     // -5 * nf                (Wendland C2 derivative)
+    T h_inv2;   // h_inv * h_inv
+    T support;  // compact_support = 2h
+};
+
+template <int KERNEL, typename T>
+struct SmoothingKernel;
+
+// WendlandC2Kernel: W = nf (1-q/2)^4 (2q+1);  (dW/dr)/r = -5 nf (1-q/2)^3 h^-2
+template <typename T>
+struct SmoothingKernel<0, T> {
+    static __device__ __forceinline__ T w_unsafe(const KernelConst<T> &k, T r)
+    {
+        T q = r * k.h_inv;
+        T t = (T)1 - q / (T)2;
+        T t2 = t * t;
+        return k.nf * (t2 * t2) * ((T)2 * q + (T)1);
+    }
+    static __device__ __forceinline__ T dw_div_r(const KernelConst<T> &k, T r)
+    {
+        T q = r * k.h_inv;
+        T t = (T)1 - q / (T)2;
+        return k.m5nf * (t * t * t) * k.h_inv2;
+    }
+};
+
+// SchoenbergCubicSplineKernel: W = nf [(2-q)^3/4 - (q<1)(1-q)^3];
+// (dW/dr)/r = div_fast(nf [-3(2-q)^2/4 + 3(q<1)(1-q)^2] h^-1, r)
+template <typename T>
+struct SmoothingKernel<1, T> {
+    static __device__ __forceinline__ T w_unsafe(const KernelConst<T> &k, T r)
+    {
+        T q = r * k.h_inv;
+        T a = (T)2 - q, b = (T)1 - q;
+        T lt = q < (T)1 ? (T)1 : (T)0;
+        return k.nf * ((a * a * a) / (T)4 - lt * (b * b * b));
+    }
+    static __device__ __forceinline__ T dw_div_r(const KernelConst<T> &k, T r)
+    {
+        T q = r * k.h_inv;
+        T a = (T)2 - q, b = (T)1 - q;
+        T three_lt = q < (T)1 ? (T)3 : (T)0;
+        T result = (T)(-3) * (a * a) / (T)4 + three_lt * (b * b);
+        return div_fast(k.nf * result * k.h_inv, r);
+    }
+};
+
+// `kernel(k, r, h)`: strict r < compact_support (smoothing_kernels.jl:30-34)
+template <int KERNEL, typename T>
+__device__ __forceinline__ T kernel_safe(const KernelConst<T> &k, T r)
+{
+    return r < k.support ? SmoothingKernel<KERNEL, T>::w_unsafe(k, r) : (T)0;
+}
+
+// ---------------------------------------------------------------------------------------
+// StateEquationCole (state_equations.jl:117-139).  The power is evaluated in double and
+// rounded to T, which is how Julia evaluates Float32^Float32 and within 1 ulp of its
+// Float64 pow.
+template <typename T>
+struct EosConst {
+    T B;        // rho0 * c^2 / gamma
+    T gamma, inv_gamma, rho0, p_bg;
+    int clip;
+};
+
+template <typename T>
+__device__ __forceinline__ T eos_pressure(const EosConst<T> &e, T density)
+{
+    T x = density / e.rho0;  // IEEE division
+    T xp = (T)pow((double)x, (double)e.gamma);
+    T p = e.B * (xp - (T)1) + e.p_bg;
+    return e.clip ? (p > (T)0 ? p : (T)0) : p;
+}
+
+template <typename T>
+__device__ __forceinline__ T eos_inverse(const EosConst<T> &e, T pressure)
+{
+    T tmp = (pressure - e.p_bg) / e.B + (T)1;
+    return e.rho0 * (T)pow((double)tmp, (double)e.inv_gamma);
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-pair physics of `interact!` (wcsph/rhs.jl:47-118).
+template <typename T>
+struct PairConst {
+    KernelConst<T> kern;
+    T c;                  // sound speed
+    T alpha, beta, eps;   // ArtificialViscosityMonaghan
+    T eps_h2;             // epsilon * h^2
+    T delta_h_c;          // delta * h_avg * c      (density_diffusion.jl:236-239)
+    T almostzero;         // sqrt(eps(compact_support^2)) (rhs.jl:27-28)
+    T radius2;            // search_radius^2
+    int has_viscosity, has_diffusion;
+};
+
+// SAME: particle_system === neighbor_system (fluid-fluid); otherwise the neighbour is a
+// static free-slip wall: v_b = 0, no viscous term, no density diffusion.
+template <int ND, typename T, int KERNEL, int DENS, bool SAME>
+__device__ __forceinline__ void interact_pair(const PairConst<T> &k, T m_b, T rho_a, T rho_b,
+                                              T p_a, T p_b, const T (&v_a)[3],
+                                              const T (&v_b)[3], const T (&pd)[3], T dist,
+                                              T (&dv)[3], T &drho)
+{
+    const T wdr = SmoothingKernel<KERNEL, T>::dw_div_r(k.kern, dist);
+    T grad[3];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) grad[d] = wdr * pd[d];
+
+    // pressure_acceleration.jl:8-15 / :34-41
+    T f;
+    if (DENS == 0)
+        f = -m_b * div_fast(p_a + p_b, rho_a * rho_b);
+    else
+        f = -m_b * (div_fast(p_a, rho_a * rho_a) + div_fast(p_b, rho_b * rho_b));
+#pragma unroll
+    for (int d = 0; d < ND; ++d) dv[d] += f * grad[d];
+
+    T vd[3];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) vd[d] = SAME ? v_a[d] - v_b[d] : v_a[d];
+
+    // ArtificialViscosityMonaghan (viscosity.jl:89-132)
+    if (SAME && k.has_viscosity) {
+        T vr = vd[0] * pd[0] + vd[1] * pd[1];
+        if (ND == 3) vr += vd[2] * pd[2];
+        if (vr < (T)0) {
+            T rho_mean = (rho_a + rho_b) / (T)2;
+            T mu = div_fast(k.kern.h * vr, dist * dist + k.eps_h2);
+            T dvv = div_fast(m_b * k.alpha * k.c * mu + m_b * k.beta * (mu * mu), rho_mean);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) dv[d] += dvv * grad[d];
+        }
+    }
+
+    // continuity_equation! (fluid.jl:160-186) + density_diffusion! (density_diffusion.jl:213-240)
+    if (DENS == 0) {
+        T vg = vd[0] * grad[0] + vd[1] * grad[1];
+        if (ND == 3) vg += vd[2] * grad[2];
+        drho += div_fast(rho_a, rho_b) * m_b * vg;
+        if (SAME && k.has_diffusion) {
+            T volume_b = div_fast(m_b, rho_b);
+            T s = div_fast((T)2 * (rho_a - rho_b), dist * dist);
+            T pg = (s * pd[0]) * grad[0] + (s * pd[1]) * grad[1];
+            if (ND == 3) pg += (s * pd[2]) * grad[2];
+            drho += k.delta_h_c * (volume_b * pg);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Uniform cell grid shared by every point set (FullGridCellList semantics: padded bounding
+// box, particles may only live in cells 1..n-2 of each dimension, so the 3^ND neighbourhood
+// never leaves the grid).  Cell index is linear with x fastest: the three cells
+// {cx-1, cx, cx+1} of one (y, z) row are one contiguous run of sorted particles.
+template <typename CT>
+struct GridConst {
+    CT origin[3];
+    CT inv_cell;  // 1 / cell_size
+    CT lo[3], hi[3];  // valid coordinate range (bounding box), for the bounds check
+    int n[3];
+    int ncells;
+};
+
+template <int ND, typename CT>
+__device__ __forceinline__ bool cell_coords(const GridConst<CT> &g, CT x, CT y, CT z, int &cx,
+                                            int &cy, int &cz)
+{
+    // written so that NaN coordinates fail the test
+    bool ok = (x >= g.lo[0]) && (x <= g.hi[0]) && (y >= g.lo[1]) && (y <= g.hi[1]);
+    if (ND == 3) ok = ok && (z >= g.lo[2]) && (z <= g.hi[2]);
+    if (!ok) {
+        cx = cy = 1;
+        cz = ND == 3 ? 1 : 0;
+        return false;
+    }
+    cx = (int)floor((x - g.origin[0]) * g.inv_cell);
+    cy = (int)floor((y - g.origin[1]) * g.inv_cell);
+    cz = ND == 3 ? (int)floor((z - g.origin[2]) * g.inv_cell) : 0;
+    cx = min(max(cx, 1), g.n[0] - 2);
+    cy = min(max(cy, 1), g.n[1] - 2);
+    if (ND == 3) cz = min(max(cz, 1), g.n[2] - 2);
+    return true;
+}
+
+template <typename CT>
+__device__ __forceinline__ int cell_linear(const GridConst<CT> &g, int cx, int cy, int cz)
+{
+    return cx + g.n[0] * (cy + g.n[1] * cz);
+}
+
+}  // namespace tpb

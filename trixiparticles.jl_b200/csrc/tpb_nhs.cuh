@@ -1,0 +1,225 @@
+// tpb_nhs.cuh -- neighbourhood-search rebuild: the B200 counterpart of
+// PointNeighbors.update!(GridNeighborhoodSearch{FullGridCellList}) as called from
+// /root/reference/src/general/neighborhood_search.jl:479-506, :804-808.
+//
+// Instead of per-cell index vectors filled with atomics and then chased through memory, the
+// particles themselves are counting-sorted by linear cell index every rebuild, so that each
+// neighbour-cell row is one contiguous stream of 16-byte records:
+//   k_cell_count   key[i] = cell(u_i);  slot[i] = arrival number inside the cell
+//   scan           cell_start = exclusive_scan(count)          (three small kernels)
+//   k_scatter      tmp[cell_start[key[i]] + slot[i]] = i
+//   k_reorder      final position inside the cell = number of smaller particle indices in
+//                  that cell (deterministic, independent of atomic arrival order); gathers
+//                  the AoS ODE vectors into the sorted SoA records and applies the EOS.
+// All passes are pure streaming work (HBM-bound).
+#pragma once
+#include "tpb_device.cuh"
+
+namespace tpb {
+
+// ------------------------------------------------------------------ cell keys + histogram
+template <int ND, typename CT>
+__global__ void __launch_bounds__(256)
+k_cell_count(const CT *__restrict__ coords /* ND x n, AoS */, int n, GridConst<CT> g,
+             int *__restrict__ key, int *__restrict__ slot, int *__restrict__ count,
+             int *__restrict__ flags)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    CT x = coords[(int64_t)i * ND + 0];
+    CT y = coords[(int64_t)i * ND + 1];
+    CT z = ND == 3 ? coords[(int64_t)i * ND + 2] : (CT)0;
+    int cx, cy, cz;
+    if (!cell_coords<ND, CT>(g, x, y, z, cx, cy, cz)) atomicOr(flags, 1);
+    int c = cell_linear(g, cx, cy, cz);
+    key[i] = c;
+    slot[i] = atomicAdd(&count[c], 1);
+}
+
+// ------------------------------------------------------------------ exclusive scan (int32)
+// Three-phase scan: per-block sums, scan of block sums (single block), per-block scan + offset.
+// SCAN_ITEMS items per thread, 1024 threads per block.
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int warp_inclusive_scan(int v)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += t;
+    }
+    return v;
+}
+
+// inclusive scan across the block of one value per thread; returns the inclusive value and
+// the block total
+__device__ __forceinline__ int block_inclusive_scan(int v, int &total)
+{
+    __shared__ int warp_sums[32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = warp_inclusive_scan(v);
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        int ws = lane < nw ? warp_sums[lane] : 0;
+        ws = warp_inclusive_scan(ws);
+        warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    int offset = wid > 0 ? warp_sums[wid - 1] : 0;
+    total = warp_sums[((blockDim.x + 31) >> 5) - 1];
+    __syncthreads();
+    return inc + offset;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_block_sums(const int *__restrict__ in, int n, int *__restrict__ block_sums)
+{
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) s += in[base + k];
+    int total;
+    block_inclusive_scan(s, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of up to SCAN_TILE block sums in place
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_top(int *__restrict__ block_sums, int nblocks)
+{
+    int base = threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = base + k < nblocks ? block_sums[base + k] : 0;
+        s += v[k];
+    }
+    int total;
+    int inc = block_inclusive_scan(s, total);
+    int run = inc - s;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < nblocks) block_sums[base + k] = run;
+        run += v[k];
+    }
+}
+
+// out[i] = exclusive prefix of in; out[n] = total
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_final(const int *__restrict__ in, int n, const int *__restrict__ block_offsets,
+             int *__restrict__ out)
+{
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        s += v[k];
+    }
+    int total;
+    int inc = block_inclusive_scan(s, total);
+    int run = inc - s + block_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+        if (base + k == n - 1) out[n] = run;
+    }
+}
+
+// ------------------------------------------------------------------ scatter of indices
+__global__ void __launch_bounds__(256)
+k_scatter(const int *__restrict__ key, const int *__restrict__ slot,
+          const int *__restrict__ cell_start, int n, int *__restrict__ tmp_perm)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tmp_perm[cell_start[key[i]] + slot[i]] = i;
+}
+
+// rank of particle index i among the indices of its cell [a, b) in tmp_perm
+__device__ __forceinline__ int rank_in_cell(const int *__restrict__ tmp_perm, int a, int b, int i)
+{
+    int r = 0;
+    for (int t = a; t < b; ++t) r += tmp_perm[t] < i;
+    return r;
+}
+
+// ------------------------------------------------------------------ fluid reorder + EOS
+// Gathers the AoS ODE vectors (u: ND x n cT, v: NV x n T) into the sorted records.
+// DENS == 0 (ContinuityDensity): rho = last row of v, pressure = EOS(rho) here.
+// DENS == 1 (SummationDensity): rho/pressure are filled by the density sweep afterwards.
+template <int ND, typename T, typename CT, int DENS>
+__global__ void __launch_bounds__(256)
+k_reorder_fluid(const CT *__restrict__ u, const T *__restrict__ v, const T *__restrict__ mass,
+                const int *__restrict__ key, const int *__restrict__ cell_start,
+                const int *__restrict__ tmp_perm, int n, int deterministic, EosConst<T> eos,
+                V4<CT> *__restrict__ A, V4<T> *__restrict__ B, T *__restrict__ P,
+                int *__restrict__ perm)
+{
+    constexpr int NV = DENS == 0 ? ND + 1 : ND;
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int i = tmp_perm[s];
+    int dst = s;
+    if (deterministic) {
+        int c = key[i];
+        int a = cell_start[c], b = cell_start[c + 1];
+        dst = a + rank_in_cell(tmp_perm, a, b, i);
+    }
+    V4<CT> ra;
+    ra.x = u[(int64_t)i * ND + 0];
+    ra.y = u[(int64_t)i * ND + 1];
+    ra.z = ND == 3 ? u[(int64_t)i * ND + 2] : (CT)0;
+    ra.w = (CT)mass[i];
+    V4<T> rb;
+    rb.x = v[(int64_t)i * NV + 0];
+    rb.y = v[(int64_t)i * NV + 1];
+    rb.z = ND == 3 ? v[(int64_t)i * NV + 2] : (T)0;
+    if (DENS == 0) {
+        T rho = v[(int64_t)i * NV + ND];
+        rb.w = rho;
+        P[dst] = eos_pressure(eos, rho);
+    } else {
+        rb.w = (T)0;
+    }
+    A[dst] = ra;
+    B[dst] = rb;
+    perm[dst] = i;
+}
+
+// ------------------------------------------------------------------ wall reorder (once)
+template <int ND, typename T, typename CT>
+__global__ void __launch_bounds__(256)
+k_reorder_wall(const CT *__restrict__ coords, const T *__restrict__ mass,
+               const T *__restrict__ density0, const int *__restrict__ key,
+               const int *__restrict__ cell_start, const int *__restrict__ tmp_perm, int n,
+               V4<CT> *__restrict__ A, V2<T> *__restrict__ W, int *__restrict__ perm)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int i = tmp_perm[s];
+    int c = key[i];
+    int a = cell_start[c], b = cell_start[c + 1];
+    int dst = a + rank_in_cell(tmp_perm, a, b, i);
+    V4<CT> ra;
+    ra.x = coords[(int64_t)i * ND + 0];
+    ra.y = coords[(int64_t)i * ND + 1];
+    ra.z = ND == 3 ? coords[(int64_t)i * ND + 2] : (CT)0;
+    ra.w = (CT)mass[i];
+    A[dst] = ra;
+    V2<T> w;
+    w.x = (T)0;          // pressure (initial_boundary_pressure: zero for Adami)
+    w.y = density0[i];   // cache.density = copy(initial_density) (dummy_particles.jl:290-297)
+    W[dst] = w;
+    perm[dst] = i;
+}
+
+}  // namespace tpb

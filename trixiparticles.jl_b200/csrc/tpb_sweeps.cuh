@@ -1,0 +1,265 @@
+// tpb_sweeps.cuh -- neighbour sweeps, variant 1 ("per-particle"): one thread per sorted
+// particle walks the 3^(ND-1) contiguous neighbour-cell rows of the sorted records.
+// This is the general-purpose path (every ND / precision / kernel / density combination)
+// and the correctness anchor for the tiled variant in tpb_tiles.cuh.
+//
+// B200 counterpart of PointNeighbors `foreach_point_neighbor` + the loop bodies of
+//   interact!                 /root/reference/src/schemes/fluid/weakly_compressible_sph/rhs.jl:5-127
+//   summation_density!        /root/reference/src/general/density_calculators.jl:26-50
+//   boundary_pressure_extrapolation! + compute_adami_density!
+//                             /root/reference/src/schemes/boundary/wall_boundary/dummy_particles.jl:489-672
+//   add_source_terms!         /root/reference/src/general/semidiscretization.jl:668-731
+//   drift!                    /root/reference/src/general/semidiscretization.jl:522-571
+#pragma once
+#include "tpb_device.cuh"
+
+namespace tpb {
+
+// Visit the rows of the 3^ND neighbourhood of cell (cx, cy, cz): row(j0, j1) is called with
+// the sorted-index range [j0, j1) of the three cells {cx-1, cx, cx+1} of each (y, z) row.
+template <int ND, typename CT, typename F>
+__device__ __forceinline__ void for_neighbor_rows(const GridConst<CT> &g,
+                                                  const int *__restrict__ cell_start, int cx,
+                                                  int cy, int cz, F &&row)
+{
+#pragma unroll
+    for (int dz = (ND == 3 ? -1 : 0); dz <= (ND == 3 ? 1 : 0); ++dz) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            int c0 = cell_linear(g, cx - 1, cy + dy, cz + dz);
+            row(cell_start[c0], cell_start[c0 + 3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ summation density
+template <int ND, typename T, typename CT, int KERNEL>
+__global__ void __launch_bounds__(128)
+k_summation_density(int n_f, GridConst<CT> g, const int *__restrict__ fcell_start,
+                    const V4<CT> *__restrict__ A, int has_wall,
+                    const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
+                    int wall_enabled, KernelConst<T> kern, T radius2, EosConst<T> eos,
+                    V4<T> *__restrict__ B, T *__restrict__ P)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_f) return;
+    const V4<CT> xi = A[s];
+    int cx, cy, cz;
+    cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    T rho = (T)0;
+    for_neighbor_rows<ND, CT>(g, fcell_start, cx, cy, cz, [&](int j0, int j1) {
+        for (int j = j0; j < j1; ++j) {
+            const V4<CT> xj = A[j];
+            T pd[3];
+            T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+            if (d2 <= radius2) rho += (T)xj.w * kernel_safe<KERNEL, T>(kern, sqrt_rn(d2));
+        }
+    });
+    if (has_wall && wall_enabled) {
+        for_neighbor_rows<ND, CT>(g, wcell_start, cx, cy, cz, [&](int j0, int j1) {
+            for (int j = j0; j < j1; ++j) {
+                const V4<CT> xj = Aw[j];
+                T pd[3];
+                T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                if (d2 <= radius2) rho += (T)xj.w * kernel_safe<KERNEL, T>(kern, sqrt_rn(d2));
+            }
+        });
+    }
+    V4<T> b = B[s];
+    b.w = rho;
+    B[s] = b;
+    P[s] = eos_pressure(eos, rho);
+}
+
+// ------------------------------------------------------------------ Adami extrapolation
+// One thread per sorted wall particle; fluid neighbours from the fluid grid.
+//   p_w = sum_f (p_off + p_f + rho_f (g - a_w).r_wf) W(r_wf) / sum_f W(r_wf)   if sum W > eps()
+//   clip; rho_w = EOS^-1(p_w)
+template <typename T>
+struct AdamiConst {
+    KernelConst<T> kern;   // boundary model's kernel / smoothing length
+    EosConst<T> eos;       // boundary model's state equation
+    T radius2;             // compact_support(wall, fluid)^2 (neighborhood_search.jl:134-140)
+    T acc[3];              // acceleration_source(fluid) - current_acceleration(wall) (= 0)
+    T p_off;
+    int clip;
+};
+
+template <int ND, typename T, typename CT, int KERNEL>
+__global__ void __launch_bounds__(128)
+k_adami(int n_w, GridConst<CT> g, const V4<CT> *__restrict__ Aw,
+        const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
+        const V4<T> *__restrict__ B, const T *__restrict__ P, int interaction_enabled,
+        AdamiConst<T> k, V2<T> *__restrict__ W, T *__restrict__ volume)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_w) return;
+    const V4<CT> xi = Aw[w];
+    int cx, cy, cz;
+    cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    T p = (T)0, vol = (T)0;
+    if (interaction_enabled) {
+        for_neighbor_rows<ND, CT>(g, fcell_start, cx, cy, cz, [&](int j0, int j1) {
+            for (int j = j0; j < j1; ++j) {
+                const V4<CT> xj = A[j];
+                T pd[3];
+                T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                if (d2 <= k.radius2) {
+                    T dist = sqrt_rn(d2);
+                    T rho_f = B[j].w;
+                    T hyd = k.acc[0] * (rho_f * pd[0]) + k.acc[1] * (rho_f * pd[1]);
+                    if (ND == 3) hyd += k.acc[2] * (rho_f * pd[2]);
+                    T sum_p = k.p_off + P[j] + hyd;
+                    T kw = kernel_safe<KERNEL, T>(k.kern, dist);
+                    p += sum_p * kw;
+                    vol += kw;
+                }
+            }
+        });
+    }
+    if ((double)vol > 2.220446049250313e-16) p = p / vol;  // `volume > eps()`: eps(Float64)
+    if (k.clip) p = p > (T)0 ? p : (T)0;
+    V2<T> out;
+    out.x = p;
+    out.y = eos_inverse(k.eos, p);
+    W[w] = out;
+    volume[w] = vol;
+}
+
+// ------------------------------------------------------------------ interact! (variant 1)
+template <typename T>
+struct SourceConst {
+    T acc[3];
+    T damping;
+    int any;
+};
+
+template <int ND, typename T, typename CT, int KERNEL, int DENS>
+__global__ void __launch_bounds__(128)
+k_interact_pp(int n_f, GridConst<CT> g, const int *__restrict__ fcell_start,
+              const V4<CT> *__restrict__ A, const V4<T> *__restrict__ B,
+              const T *__restrict__ P, const int *__restrict__ perm, int ff_enabled,
+              int has_wall, const int *__restrict__ wcell_start,
+              const V4<CT> *__restrict__ Aw, const V2<T> *__restrict__ Ww, PairConst<T> k,
+              SourceConst<T> src, T *__restrict__ dv /* NV x n_f, ODE order */)
+{
+    constexpr int NV = DENS == 0 ? ND + 1 : ND;
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_f) return;
+    const V4<CT> xi = A[s];
+    const V4<T> bi = B[s];
+    const T p_a = P[s];
+    const T rho_a = bi.w;
+    const T v_a[3] = {bi.x, bi.y, bi.z};
+    int cx, cy, cz;
+    cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+
+    T dv_ff[3] = {0, 0, 0}, drho_ff = 0;
+    if (ff_enabled) {
+        for_neighbor_rows<ND, CT>(g, fcell_start, cx, cy, cz, [&](int j0, int j1) {
+            for (int j = j0; j < j1; ++j) {
+                const V4<CT> xj = A[j];
+                T pd[3];
+                T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                if (d2 <= k.radius2) {
+                    T dist = sqrt_rn(d2);
+                    if (dist >= k.almostzero) {
+                        const V4<T> bj = B[j];
+                        const T v_b[3] = {bj.x, bj.y, bj.z};
+                        interact_pair<ND, T, KERNEL, DENS, true>(k, (T)xj.w, rho_a, bj.w, p_a,
+                                                                P[j], v_a, v_b, pd, dist, dv_ff,
+                                                                drho_ff);
+                    }
+                }
+            }
+        });
+    }
+    T dv_fw[3] = {0, 0, 0}, drho_fw = 0;
+    if (has_wall) {
+        const T zero3[3] = {0, 0, 0};
+        for_neighbor_rows<ND, CT>(g, wcell_start, cx, cy, cz, [&](int j0, int j1) {
+            for (int j = j0; j < j1; ++j) {
+                const V4<CT> xj = Aw[j];
+                T pd[3];
+                T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                if (d2 <= k.radius2) {
+                    T dist = sqrt_rn(d2);
+                    if (dist >= k.almostzero) {
+                        const V2<T> wj = Ww[j];
+                        interact_pair<ND, T, KERNEL, DENS, false>(k, (T)xj.w, rho_a, wj.y, p_a,
+                                                                 wj.x, v_a, zero3, pd, dist,
+                                                                 dv_fw, drho_fw);
+                    }
+                }
+            }
+        });
+    }
+    // dv = ((0 + S_ff) + S_fw) + g [+ source]: same association as set_zero!, the two
+    // interact! calls and add_source_terms! (semidiscretization.jl:600, :809-829, :668-731)
+    const int64_t o = (int64_t)perm[s] * NV;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        T val = dv_ff[d] + dv_fw[d];
+        if (src.any) {
+            val += src.acc[d];
+            if (src.damping != (T)0) val += -src.damping * v_a[d];
+        }
+        dv[o + d] = val;
+    }
+    if (DENS == 0) dv[o + ND] = drho_ff + drho_fw;
+}
+
+// ------------------------------------------------------------------ drift!
+// du[1:ND, a] = v[1:ND, a]  (strided copy: v has NV rows, du has ND; T -> cT conversion)
+template <int ND, typename T, typename CT>
+__global__ void __launch_bounds__(256)
+k_drift(int64_t n_total /* n_f * ND */, int nv, const T *__restrict__ v, CT *__restrict__ du)
+{
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_total) return;
+    int64_t a = q / ND;
+    int d = (int)(q - a * ND);
+    du[q] = (CT)v[a * nv + d];
+}
+
+// ------------------------------------------------------------------ neighbour pair dump
+// Test hook behind tpb_neighbor_pairs: appends (orig_i, orig_j) for every accepted pair.
+template <int ND, typename T, typename CT>
+__global__ void __launch_bounds__(128)
+k_pairs(int n_x, GridConst<CT> g, const V4<CT> *__restrict__ X, const int *__restrict__ perm_x,
+        const int *__restrict__ ycell_start, const V4<CT> *__restrict__ Y,
+        const int *__restrict__ perm_y, T radius2, long long capacity, int *__restrict__ out_i,
+        int *__restrict__ out_j, unsigned long long *__restrict__ counter)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_x) return;
+    const V4<CT> xi = X[s];
+    int cx, cy, cz;
+    cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    for_neighbor_rows<ND, CT>(g, ycell_start, cx, cy, cz, [&](int j0, int j1) {
+        for (int j = j0; j < j1; ++j) {
+            T pd[3];
+            T d2 = pos_diff_d2<ND, T, CT>(xi, Y[j], pd);
+            if (d2 <= radius2) {
+                unsigned long long at = atomicAdd(counter, 1ull);
+                if ((long long)at < capacity) {
+                    out_i[at] = perm_x[s];
+                    out_j[at] = perm_y[j];
+                }
+            }
+        }
+    });
+}
+
+// scatter a sorted per-particle field back to the system's own particle order
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_unsort_scalar(int n, const int *__restrict__ perm, const T *__restrict__ sorted, int stride,
+                int offset, T *__restrict__ out)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    out[perm[s]] = sorted[(int64_t)s * stride + offset];
+}
+
+}  // namespace tpb

@@ -1,0 +1,125 @@
+"""The reference's example setups on the accelerated path, as functions.
+
+Each mirrors one script under /root/reference/examples/fluid/ (same parameter values and
+construction order) and returns `(fluid_system, boundary_system, tank)`.  `eltype` /
+`coordinates_eltype` play the role of `trixi_include_changeprecision` (docs/src/gpu.md:107-133).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
+                    BoundaryModelDummyParticles, ContinuityDensity,
+                    DensityDiffusionMolteniColagrossi, SchoenbergCubicSplineKernel,
+                    StateEquationCole, SummationDensity, WallBoundarySystem,
+                    WeaklyCompressibleSPHSystem, WendlandC2Kernel)
+from .setups import RectangularTank
+
+
+def dam_break_2d(particles_per_height=40, *, eltype=np.float64, coordinates_eltype=np.float64,
+                 density_calculator=None, alpha=0.02, delta=0.1, sound_speed_factor=20.0):
+    """examples/fluid/dam_break_2d.jl:19-97 (BASELINE config 1 at particles_per_height=40)."""
+    t = np.dtype(eltype).type
+    H = 0.6
+    W = 2 * H
+    dx = H / particles_per_height
+    gravity = 9.81
+    tank_size = (np.floor(5.366 * H / dx) * dx, 4.0)
+    sound_speed = sound_speed_factor * np.sqrt(gravity * H)
+    state_equation = StateEquationCole(sound_speed=float(t(sound_speed)), reference_density=1000.0,
+                                       exponent=1, clip_negative_pressure=False)
+    tank = RectangularTank(dx, (W, H), tank_size, 1000.0, n_layers=4, spacing_ratio=1,
+                           acceleration=(0.0, -gravity), state_equation=state_equation,
+                           coordinates_eltype=coordinates_eltype, eltype=eltype)
+    h = 2 * dx
+    kernel = WendlandC2Kernel(2)
+    dc = density_calculator or ContinuityDensity()
+    fluid = WeaklyCompressibleSPHSystem(
+        tank.fluid, smoothing_kernel=kernel, smoothing_length=h, density_calculator=dc,
+        state_equation=state_equation, viscosity=ArtificialViscosityMonaghan(alpha=alpha, beta=0.0),
+        density_diffusion=(None if isinstance(dc, SummationDensity)
+                           else DensityDiffusionMolteniColagrossi(delta=delta)),
+        acceleration=(0.0, -gravity))
+    model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass,
+                                        AdamiPressureExtrapolation(), kernel, h,
+                                        state_equation=state_equation, clip_negative_pressure=True)
+    wall = WallBoundarySystem(tank.boundary, model)
+    return fluid, wall, tank
+
+
+def hydrostatic_water_column_2d(fluid_particle_spacing=0.05, *, eltype=np.float32,
+                                coordinates_eltype=np.float32, density_calculator=None):
+    """examples/fluid/hydrostatic_water_column_2d.jl:13-69 (BASELINE config 2)."""
+    gravity = 9.81
+    dx = fluid_particle_spacing
+    state_equation = StateEquationCole(sound_speed=10.0, reference_density=1000.0, exponent=7,
+                                       clip_negative_pressure=False)
+    tank = RectangularTank(dx, (1.0, 0.9), (1.0, 1.0), 1000.0, n_layers=3,
+                           acceleration=(0.0, -gravity), state_equation=state_equation,
+                           coordinates_eltype=coordinates_eltype, eltype=eltype)
+    h = 1.2 * dx
+    kernel = SchoenbergCubicSplineKernel(2)
+    fluid = WeaklyCompressibleSPHSystem(
+        tank.fluid, smoothing_kernel=kernel, smoothing_length=h,
+        density_calculator=density_calculator or ContinuityDensity(),
+        state_equation=state_equation, viscosity=ArtificialViscosityMonaghan(alpha=0.02, beta=0.0),
+        acceleration=(0.0, -gravity))
+    model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass,
+                                        AdamiPressureExtrapolation(), kernel, h,
+                                        state_equation=state_equation)
+    wall = WallBoundarySystem(tank.boundary, model)
+    return fluid, wall, tank
+
+
+def dam_break_3d(fluid_particle_spacing=0.08, *, eltype=np.float32, coordinates_eltype=None,
+                 sound_speed=None, fluid_size=(2.0, 1.0, 1.0), tank_size=None):
+    """examples/fluid/dam_break_3d.jl:13-66 (BASELINE configs 3/4 at smaller spacings).
+
+    As SURVEY.md section 8(d) M3 prescribes, the headline runs use a static
+    `StateEquationCole(c = 20 sqrt(g * 1.0), exponent = 7)` instead of the script's
+    `StateEquationAdaptiveCole` (which only adds one global max|v| reduction per RHS)."""
+    gravity = 9.81
+    dx = fluid_particle_spacing
+    coordinates_eltype = coordinates_eltype or eltype
+    if tank_size is None:
+        tank_size = (np.floor(5.366 / dx) * dx, 4.0, 1.0)
+    c = sound_speed if sound_speed is not None else 20 * np.sqrt(gravity * 1.0)
+    state_equation = StateEquationCole(sound_speed=float(np.dtype(eltype).type(c)),
+                                       reference_density=1000.0, exponent=7)
+    tank = RectangularTank(dx, fluid_size, tank_size, 1000.0, n_layers=4, spacing_ratio=1,
+                           acceleration=(0.0, -gravity, 0.0), state_equation=state_equation,
+                           coordinates_eltype=coordinates_eltype, eltype=eltype)
+    h = 1.5 * dx
+    kernel = WendlandC2Kernel(3)
+    fluid = WeaklyCompressibleSPHSystem(
+        tank.fluid, smoothing_kernel=kernel, smoothing_length=h,
+        density_calculator=ContinuityDensity(), state_equation=state_equation,
+        viscosity=ArtificialViscosityMonaghan(alpha=0.02, beta=0.0),
+        density_diffusion=DensityDiffusionMolteniColagrossi(delta=0.1),
+        acceleration=(0.0, -gravity, 0.0))
+    model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass,
+                                        AdamiPressureExtrapolation(), kernel, h,
+                                        state_equation=state_equation, clip_negative_pressure=True)
+    wall = WallBoundarySystem(tank.boundary, model)
+    return fluid, wall, tank
+
+
+def perturbed_state(fluid, seed=1234, position_jitter=0.1, velocity_scale=0.05,
+                    density_jitter=0.01):
+    """positions + U(-0.1dx, 0.1dx), velocities U(-0.05c, 0.05c),
+    densities rho (1 +- 0.01), numpy default_rng(seed).  Removes exact-distance ties and
+    exercises the `vr < 0` viscosity branch.  Returns (u, v) particle-major arrays."""
+    rng = np.random.default_rng(seed)
+    ic = fluid.initial_condition
+    n, nd = ic.coordinates.shape
+    dx = ic.particle_spacing
+    c = float(fluid.state_equation.sound_speed)
+    u = ic.coordinates.astype(np.float64) + rng.uniform(-position_jitter * dx, position_jitter * dx, (n, nd))
+    vel = rng.uniform(-velocity_scale * c, velocity_scale * c, (n, nd))
+    rho = ic.density.astype(np.float64) * (1 + rng.uniform(-density_jitter, density_jitter, n))
+    u = u.astype(fluid.coordinates_eltype)
+    if fluid.v_nvariables == nd + 1:
+        v = np.concatenate([vel, rho[:, None]], axis=1).astype(fluid.eltype)
+    else:
+        v = vel.astype(fluid.eltype)
+    return np.ascontiguousarray(u), np.ascontiguousarray(v)

@@ -1,0 +1,193 @@
+"""Model-parameter types mirroring the reference's constructors (same names, same keywords).
+
+These are plain host-side records; all arithmetic on particles happens in the CUDA library.
+Reference: smoothing_kernels.jl:191-227,400,434-455; state_equations.jl:100-139;
+viscosity.jl:68-87; density_diffusion.jl:41-47; density_calculators.jl:1-24;
+wcsph/system.jl:65-225; wall_boundary/system.jl:22-60; dummy_particles.jl:52-149.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .setups import InitialCondition
+
+# ids shared with include/tpb200.h
+KERNEL_WENDLAND_C2 = 0
+KERNEL_SCHOENBERG_CUBIC = 1
+DENSITY_CONTINUITY = 0
+DENSITY_SUMMATION = 1
+
+
+@dataclass(frozen=True)
+class WendlandC2Kernel:
+    ndims: int
+    kernel_id: int = KERNEL_WENDLAND_C2
+
+
+@dataclass(frozen=True)
+class SchoenbergCubicSplineKernel:
+    ndims: int
+    kernel_id: int = KERNEL_SCHOENBERG_CUBIC
+
+
+def compact_support(kernel, h):
+    """`compact_support(kernel, h) = 2h` for both kernels (smoothing_kernels.jl:215, :400)."""
+    return 2 * h
+
+
+class ContinuityDensity:
+    density_id = DENSITY_CONTINUITY
+
+
+class SummationDensity:
+    density_id = DENSITY_SUMMATION
+
+
+@dataclass(frozen=True)
+class StateEquationCole:
+    """state_equations.jl:100-139.  Fields are stored as ELTYPE = typeof(sound_speed)."""
+    sound_speed: float
+    reference_density: float
+    exponent: float
+    background_pressure: float = 0.0
+    clip_negative_pressure: bool = False
+
+    def __call__(self, density, dtype=np.float64):
+        t = np.dtype(dtype).type
+        c, g, r0, pb = t(self.sound_speed), t(self.exponent), t(self.reference_density), t(self.background_pressure)
+        B = r0 * (c * c) / g
+        x = t(density) / r0
+        p = B * (t(np.float64(x) ** np.float64(g)) - t(1)) + pb
+        return max(t(0), p) if self.clip_negative_pressure else p
+
+    def inverse(self, pressure, dtype=np.float64):
+        t = np.dtype(dtype).type
+        c, g, r0, pb = t(self.sound_speed), t(self.exponent), t(self.reference_density), t(self.background_pressure)
+        B = r0 * (c * c) / g
+        tmp = (t(pressure) - pb) / B + t(1)
+        return r0 * t(np.float64(tmp) ** np.float64(t(1) / g))
+
+
+@dataclass(frozen=True)
+class ArtificialViscosityMonaghan:
+    alpha: float
+    beta: float = 0.0
+    epsilon: float = 0.01
+
+
+@dataclass(frozen=True)
+class DensityDiffusionMolteniColagrossi:
+    delta: float
+
+
+@dataclass(frozen=True)
+class SourceTermDamping:
+    damping_coefficient: float
+
+
+@dataclass(frozen=True)
+class AdamiPressureExtrapolation:
+    pressure_offset: float = 0.0
+    allow_loop_flipping: bool = True  # accepted for API parity; the GPU sweep is always wall-major
+
+
+class WeaklyCompressibleSPHSystem:
+    """wcsph/system.jl:65-225 -- only the options on the accelerated path are accepted;
+    anything else raises `ValueError` (the reference throws `ArgumentError`)."""
+
+    def __init__(self, initial_condition: InitialCondition, *, smoothing_kernel,
+                 smoothing_length, density_calculator, state_equation,
+                 viscosity: Optional[ArtificialViscosityMonaghan] = None,
+                 density_diffusion: Optional[DensityDiffusionMolteniColagrossi] = None,
+                 acceleration: Optional[Sequence[float]] = None, source_terms=None,
+                 correction=None, surface_tension=None, pressure_acceleration=None,
+                 shifting_technique=None, buffer_size=None, reference_particle_spacing=0):
+        nd = initial_condition.ndims
+        if smoothing_kernel.ndims != nd:
+            raise ValueError("smoothing kernel dimensionality doesn't match problem dimensionality")
+        if acceleration is None:
+            acceleration = (0.0,) * nd
+        if len(acceleration) != nd:
+            raise ValueError(f"`acceleration` must be of length {nd} for a {nd}D problem")
+        for name, val in (("correction", correction), ("surface_tension", surface_tension),
+                          ("pressure_acceleration", pressure_acceleration),
+                          ("shifting_technique", shifting_technique), ("buffer_size", buffer_size)):
+            if val is not None:
+                raise ValueError(f"`{name}` is outside the accelerated hot path (see DESIGN.md)")
+        if source_terms is not None and not isinstance(source_terms, SourceTermDamping):
+            raise ValueError("only `SourceTermDamping` source terms are supported")
+        if density_diffusion is not None and isinstance(density_calculator, SummationDensity):
+            raise ValueError("`density_diffusion` is not used with `SummationDensity`")
+        self.initial_condition = initial_condition
+        self.smoothing_kernel = smoothing_kernel
+        self.eltype = initial_condition.eltype
+        self.coordinates_eltype = initial_condition.coordinates_eltype
+        self.smoothing_length = self.eltype.type(smoothing_length)
+        self.density_calculator = density_calculator
+        self.state_equation = state_equation
+        self.viscosity = viscosity
+        self.density_diffusion = density_diffusion
+        self.acceleration = np.asarray(acceleration, dtype=self.eltype)
+        self.source_terms = source_terms
+        self.mass = initial_condition.mass.copy()
+        # filled by the semidiscretization after every kick (system.pressure / cache.density)
+        self.pressure = np.zeros(initial_condition.nparticles, dtype=self.eltype)
+
+    ndims = property(lambda self: self.initial_condition.ndims)
+    nparticles = property(lambda self: self.initial_condition.nparticles)
+    n_integrated_particles = property(lambda self: self.initial_condition.nparticles)
+    u_nvariables = property(lambda self: self.ndims)
+
+    @property
+    def v_nvariables(self):  # wcsph/system.jl:232-242
+        return self.ndims + (0 if isinstance(self.density_calculator, SummationDensity) else 1)
+
+
+class BoundaryModelDummyParticles:
+    """dummy_particles.jl:52-113 with `AdamiPressureExtrapolation`."""
+
+    def __init__(self, initial_density, hydrodynamic_mass, density_calculator, smoothing_kernel,
+                 smoothing_length, *, viscosity=None, state_equation=None, correction=None,
+                 clip_negative_pressure=False, reference_particle_spacing=0.0):
+        if not isinstance(density_calculator, AdamiPressureExtrapolation):
+            raise ValueError("only `AdamiPressureExtrapolation` is on the accelerated path")
+        if viscosity is not None or correction is not None:
+            raise ValueError("wall `viscosity`/`correction` are outside the accelerated hot path")
+        if state_equation is None:
+            raise ValueError("`AdamiPressureExtrapolation` needs a `state_equation`")
+        self.initial_density = np.asarray(initial_density)
+        self.hydrodynamic_mass = np.asarray(hydrodynamic_mass)
+        assert self.initial_density.shape == self.hydrodynamic_mass.shape
+        self.density_calculator = density_calculator
+        self.smoothing_kernel = smoothing_kernel
+        self.eltype = self.hydrodynamic_mass.dtype
+        self.smoothing_length = self.eltype.type(smoothing_length)
+        self.state_equation = state_equation
+        self.viscosity = None
+        self.clip_negative_pressure = bool(clip_negative_pressure)
+        n = self.hydrodynamic_mass.shape[0]
+        self.pressure = np.zeros(n, dtype=self.eltype)
+        self.cache = dict(density=self.initial_density.copy(), volume=np.zeros(n, dtype=self.eltype))
+
+
+class WallBoundarySystem:
+    """wall_boundary/system.jl:22-60 (static wall: `prescribed_motion=nothing`)."""
+
+    def __init__(self, initial_condition: InitialCondition, boundary_model, *,
+                 prescribed_motion=None, adhesion_coefficient=0.0):
+        if prescribed_motion is not None or adhesion_coefficient != 0.0:
+            raise ValueError("moving walls / adhesion are outside the accelerated hot path")
+        self.initial_condition = initial_condition
+        self.coordinates = initial_condition.coordinates
+        self.boundary_model = boundary_model
+        self.eltype = boundary_model.eltype
+        self.coordinates_eltype = initial_condition.coordinates_eltype
+
+    ndims = property(lambda self: self.initial_condition.ndims)
+    nparticles = property(lambda self: self.initial_condition.nparticles)
+    n_integrated_particles = property(lambda self: 0)  # wall_boundary/system.jl:78-90
+    u_nvariables = property(lambda self: 0)
+    v_nvariables = property(lambda self: 1)

@@ -1,0 +1,352 @@
+"""`Semidiscretization`, `semidiscretize`, `kick!`, `drift!` on the B200 library.
+
+Python mirror of /root/reference/src/general/semidiscretization.jl (constructor :106-191,
+ODE layout :128-135, `semidiscretize` :293-396, `drift!` :522-536, `kick!` :589-612) for the
+accelerated path: one `WeaklyCompressibleSPHSystem` plus an optional `WallBoundarySystem`.
+`kick!`/`drift!` are spelled `kick_`/`drift_` (Python has no `!`).  All particle arithmetic
+runs in libtpb200.so through the C ABI of include/tpb200.h; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
+                    DensityDiffusionMolteniColagrossi, SourceTermDamping, SummationDensity,
+                    WallBoundarySystem, WeaklyCompressibleSPHSystem)
+
+
+@dataclass
+class FullGridCellList:
+    """PointNeighbors `FullGridCellList(; min_corner, max_corner, max_points_per_cell=100)`."""
+    min_corner: Sequence[float]
+    max_corner: Sequence[float]
+    max_points_per_cell: int = 100
+
+
+@dataclass
+class GridNeighborhoodSearch:
+    """PointNeighbors `GridNeighborhoodSearch{NDIMS}(; cell_list, update_strategy)`."""
+    ndims: int
+    cell_list: Optional[FullGridCellList] = None
+    update_strategy: object = None  # accepted for API parity; the GPU rebuild is always parallel
+
+
+@dataclass
+class B200Backend:
+    """`parallelization_backend` selecting this library.
+
+    ode_memory: "host"  -- kick_/drift_ take numpy arrays (copied per call, like a CPU backend);
+                "device" -- they take torch CUDA tensors and are stream-ordered (GPU-resident).
+    """
+    device: int = 0
+    ode_memory: str = "host"
+    deterministic: bool = True
+    interact_variant: int = 0
+
+
+def _dtype_id(dt):
+    dt = np.dtype(dt)
+    if dt == np.float32:
+        return _lib.F32
+    if dt == np.float64:
+        return _lib.F64
+    raise ValueError(f"unsupported eltype {dt}")
+
+
+class Semidiscretization:
+    def __init__(self, *systems, neighborhood_search: Optional[GridNeighborhoodSearch] = None,
+                 parallelization_backend: Optional[B200Backend] = None, interaction_matrix=None):
+        if not systems:
+            raise ValueError("at least one system is required")
+        fluids = [s for s in systems if isinstance(s, WeaklyCompressibleSPHSystem)]
+        walls = [s for s in systems if isinstance(s, WallBoundarySystem)]
+        if len(fluids) + len(walls) != len(systems):
+            raise ValueError("only WeaklyCompressibleSPHSystem and WallBoundarySystem are on the accelerated path")
+        if len(fluids) != 1 or len(walls) > 1:
+            raise ValueError("the accelerated path takes exactly one fluid system and at most one wall system")
+        nd = {s.ndims for s in systems}
+        if len(nd) != 1:
+            raise ValueError("all systems must have the same number of dimensions")
+        # semidiscretization.jl:303-317
+        if len({np.dtype(s.eltype) for s in systems}) != 1:
+            raise ValueError("all systems must have the same eltype")
+        if len({np.dtype(s.coordinates_eltype) for s in systems}) != 1:
+            raise ValueError("all systems must have the same eltype for their coordinates")
+        self.systems = tuple(systems)
+        self.ndims = nd.pop()
+        self.eltype = np.dtype(systems[0].eltype)
+        self.coordinates_eltype = np.dtype(systems[0].coordinates_eltype)
+        if neighborhood_search is not None and neighborhood_search.ndims != self.ndims:
+            raise ValueError("neighborhood search dimensionality mismatch")
+        self.neighborhood_search = neighborhood_search
+        self.parallelization_backend = parallelization_backend or B200Backend()
+        n = len(systems)
+        if interaction_matrix is None:
+            interaction_matrix = np.ones((n, n), dtype=bool)
+        self.interaction_matrix = np.asarray(interaction_matrix, dtype=bool)
+        if self.interaction_matrix.shape != (n, n):
+            raise ValueError(f"`interaction_matrix` must be of size ({n}, {n})")
+        # ranges_u / ranges_v (0-based half-open), semidiscretization.jl:128-135
+        sizes_u = [s.u_nvariables * s.n_integrated_particles for s in systems]
+        sizes_v = [s.v_nvariables * s.n_integrated_particles for s in systems]
+        self.ranges_u = tuple((sum(sizes_u[:i]), sum(sizes_u[:i + 1])) for i in range(n))
+        self.ranges_v = tuple((sum(sizes_v[:i]), sum(sizes_v[:i + 1])) for i in range(n))
+        self._handle = None
+
+    # -- helpers ---------------------------------------------------------------------------
+    @property
+    def fluid(self) -> WeaklyCompressibleSPHSystem:
+        return next(s for s in self.systems if isinstance(s, WeaklyCompressibleSPHSystem))
+
+    @property
+    def wall(self) -> Optional[WallBoundarySystem]:
+        return next((s for s in self.systems if isinstance(s, WallBoundarySystem)), None)
+
+    def system_index(self, system) -> int:
+        return next(i for i, s in enumerate(self.systems) if s is system)
+
+    def wrap_u(self, u_ode, system):
+        a, b = self.ranges_u[self.system_index(system)]
+        return u_ode[a:b].reshape(system.n_integrated_particles, system.u_nvariables)
+
+    def wrap_v(self, v_ode, system):
+        a, b = self.ranges_v[self.system_index(system)]
+        return v_ode[a:b].reshape(system.n_integrated_particles, system.v_nvariables)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def close(self):
+        if self._handle is not None:
+            _lib.load().tpb_destroy(self._handle)
+            self._handle = None
+
+    # -- library plumbing ------------------------------------------------------------------
+    def _fluid_params(self, f: WeaklyCompressibleSPHSystem) -> _lib.FluidParams:
+        se = f.state_equation
+        p = _lib.FluidParams()
+        p.struct_size = C.sizeof(_lib.FluidParams)
+        p.kernel = f.smoothing_kernel.kernel_id
+        p.density_calculator = f.density_calculator.density_id
+        p.clip_negative_pressure = int(se.clip_negative_pressure)
+        p.has_viscosity = int(f.viscosity is not None)
+        p.has_diffusion = int(f.density_diffusion is not None)
+        t = self.eltype.type
+        p.smoothing_length = float(t(f.smoothing_length))
+        p.sound_speed = float(t(se.sound_speed))
+        p.exponent = float(t(se.exponent))
+        p.reference_density = float(t(se.reference_density))
+        p.background_pressure = float(t(se.background_pressure))
+        if f.viscosity is not None:
+            p.alpha, p.beta, p.epsilon = (float(t(f.viscosity.alpha)), float(t(f.viscosity.beta)),
+                                          float(t(f.viscosity.epsilon)))
+        if f.density_diffusion is not None:
+            p.delta = float(t(f.density_diffusion.delta))
+        for d in range(self.ndims):
+            p.acceleration[d] = float(f.acceleration[d])
+        if isinstance(f.source_terms, SourceTermDamping):
+            p.damping_coefficient = float(t(f.source_terms.damping_coefficient))
+        return p
+
+    def _wall_params(self, w: WallBoundarySystem) -> _lib.WallParams:
+        m = w.boundary_model
+        se = m.state_equation
+        t = self.eltype.type
+        p = _lib.WallParams()
+        p.struct_size = C.sizeof(_lib.WallParams)
+        p.kernel = m.smoothing_kernel.kernel_id
+        p.clip_negative_pressure = int(m.clip_negative_pressure)
+        p.smoothing_length = float(t(m.smoothing_length))
+        p.sound_speed = float(t(se.sound_speed))
+        p.exponent = float(t(se.exponent))
+        p.reference_density = float(t(se.reference_density))
+        p.background_pressure = float(t(se.background_pressure))
+        p.pressure_offset = float(t(m.density_calculator.pressure_offset))
+        return p
+
+    def _create(self, u0_ode: np.ndarray):
+        L = _lib.load()
+        be = self.parallelization_backend
+        cfg = _lib.Config()
+        cfg.struct_size = C.sizeof(_lib.Config)
+        cfg.ndims = self.ndims
+        cfg.eltype = _dtype_id(self.eltype)
+        cfg.coords_eltype = _dtype_id(self.coordinates_eltype)
+        cfg.device = be.device
+        cfg.ode_memory = _lib.MEM_DEVICE if be.ode_memory == "device" else _lib.MEM_HOST
+        cfg.deterministic = int(be.deterministic)
+        cfg.interact_variant = int(be.interact_variant)
+        nhs = self.neighborhood_search
+        if nhs is not None and nhs.cell_list is not None:
+            cfg.has_bounds = 1
+            cfg.max_points_per_cell = nhs.cell_list.max_points_per_cell
+            for d in range(self.ndims):
+                cfg.min_corner[d] = float(nhs.cell_list.min_corner[d])
+                cfg.max_corner[d] = float(nhs.cell_list.max_corner[d])
+        h = C.c_void_p()
+        _lib.check(None, L.tpb_create(C.byref(cfg), C.byref(h)))
+        self._handle = h
+        try:
+            for s in self.systems:
+                idx = C.c_int32(-1)
+                if isinstance(s, WeaklyCompressibleSPHSystem):
+                    mass = np.ascontiguousarray(s.mass, dtype=self.eltype)
+                    fp = self._fluid_params(s)
+                    _lib.check(h, L.tpb_add_fluid_system(h, C.byref(fp), s.nparticles,
+                                                         mass.ctypes.data, C.byref(idx)))
+                else:
+                    coords = np.ascontiguousarray(s.coordinates, dtype=self.coordinates_eltype)
+                    mass = np.ascontiguousarray(s.boundary_model.hydrodynamic_mass, dtype=self.eltype)
+                    dens = np.ascontiguousarray(s.boundary_model.initial_density, dtype=self.eltype)
+                    wp = self._wall_params(s)
+                    _lib.check(h, L.tpb_add_wall_system(h, C.byref(wp), s.nparticles,
+                                                        coords.ctypes.data, mass.ctypes.data,
+                                                        dens.ctypes.data, C.byref(idx)))
+                assert idx.value == self.system_index(s)
+            n = len(self.systems)
+            for i in range(n):
+                for j in range(n):
+                    if not self.interaction_matrix[i, j]:
+                        _lib.check(h, L.tpb_set_interaction(h, i, j, 0))
+            _lib.check(h, L.tpb_semidiscretize(h, u0_ode.ctypes.data))
+            nu, nv = C.c_int64(), C.c_int64()
+            _lib.check(h, L.tpb_ode_sizes(h, C.byref(nu), C.byref(nv)))
+            assert nu.value == self.ranges_u[-1][1] and nv.value == self.ranges_v[-1][1]
+        except Exception:
+            self.close()
+            raise
+
+    def _ptr(self, arr, n_expected, dtype, name):
+        """Raw pointer of an ODE vector, after checking type / size / residency."""
+        be = self.parallelization_backend
+        if be.ode_memory == "device":
+            import torch
+            if not (isinstance(arr, torch.Tensor) and arr.is_cuda):
+                raise TypeError(f"{name}: B200Backend(ode_memory='device') expects torch CUDA tensors")
+            if arr.device.index != be.device:
+                raise ValueError(f"{name} lives on cuda:{arr.device.index}, backend on cuda:{be.device}")
+            want = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+            if arr.dtype != want or not arr.is_contiguous() or arr.numel() != n_expected:
+                raise ValueError(f"{name}: expected contiguous {want} tensor of length {n_expected}")
+            return arr.data_ptr()
+        if not isinstance(arr, np.ndarray):
+            raise TypeError(f"{name}: B200Backend(ode_memory='host') expects numpy arrays")
+        if arr.dtype != np.dtype(dtype) or not arr.flags.c_contiguous or arr.size != n_expected:
+            raise ValueError(f"{name}: expected contiguous {np.dtype(dtype)} array of length {n_expected}")
+        return arr.ctypes.data
+
+    def _bind_stream(self):
+        if self.parallelization_backend.ode_memory == "device":
+            import torch
+            stream = torch.cuda.current_stream(self.parallelization_backend.device).cuda_stream
+            _lib.load().tpb_set_stream(self._handle, C.c_void_p(stream))
+
+    def synchronize(self):
+        _lib.check(self._handle, _lib.load().tpb_synchronize(self._handle))
+
+    def stats(self) -> _lib.Stats:
+        st = _lib.Stats()
+        _lib.check(self._handle, _lib.load().tpb_get_stats(self._handle, C.byref(st)))
+        return st
+
+    def system_field(self, system, field: str) -> np.ndarray:
+        """`system.pressure`, `cache.density`, `boundary_model.pressure/cache.density/cache.volume`
+        after the last kick (fluid.jl:312-326, wall_boundary/system.jl:339-350)."""
+        fid = {"pressure": _lib.FIELD_PRESSURE, "density": _lib.FIELD_DENSITY,
+               "volume": _lib.FIELD_VOLUME}[field]
+        out = np.zeros(system.nparticles, dtype=self.eltype)
+        _lib.check(self._handle, _lib.load().tpb_get_system_field(
+            self._handle, self.system_index(system), fid, out.ctypes.data, out.size))
+        return out
+
+    def neighbor_pairs(self, system, neighbor, u_ode):
+        """Sorted (i, j) neighbour pairs of the ordered system pair (test hook)."""
+        L = _lib.load()
+        nu = self.ranges_u[-1][1]
+        ptr = self._ptr(u_ode, nu, self.coordinates_eltype, "u_ode")
+        self._bind_stream()
+        cap = max(1024, 80 * max(system.nparticles, 1))
+        while True:
+            oi = np.empty(cap, dtype=np.int32)
+            oj = np.empty(cap, dtype=np.int32)
+            cnt = C.c_int64(0)
+            rc = L.tpb_neighbor_pairs(self._handle, self.system_index(system),
+                                      self.system_index(neighbor), ptr, cap, oi.ctypes.data,
+                                      oj.ctypes.data, C.byref(cnt))
+            if rc == 6:  # TPB_ERR_CAPACITY
+                cap = int(cnt.value)
+                continue
+            _lib.check(self._handle, rc)
+            n = cnt.value
+            order = np.lexsort((oj[:n], oi[:n]))
+            return oi[:n][order], oj[:n][order]
+
+
+@dataclass
+class DynamicalODEProblem:
+    """What `semidiscretize` returns: `DynamicalODEProblem(kick!, drift!, v0, u0, tspan, p)`
+    (semidiscretization.jl:391-395)."""
+    f1: object
+    f2: object
+    v0: object
+    u0: object
+    tspan: tuple
+    p: SimpleNamespace
+
+
+def semidiscretize(semi: Semidiscretization, tspan) -> DynamicalODEProblem:
+    """semidiscretization.jl:293-396: builds u0/v0 (`write_u0!`/`write_v0!`, fluid.jl:79-97,
+    wcsph/system.jl:440-445), initialises the neighbourhood search and moves everything to the
+    device."""
+    nu, nv = semi.ranges_u[-1][1], semi.ranges_v[-1][1]
+    u0 = np.zeros(nu, dtype=semi.coordinates_eltype)
+    v0 = np.zeros(nv, dtype=semi.eltype)
+    for s in semi.systems:
+        if s.n_integrated_particles == 0:
+            continue
+        u = semi.wrap_u(u0, s)
+        v = semi.wrap_v(v0, s)
+        u[:] = s.initial_condition.coordinates
+        v[:, : s.ndims] = s.initial_condition.velocity
+        if not isinstance(s.density_calculator, SummationDensity):
+            v[:, s.ndims] = s.initial_condition.density
+    semi._create(u0)
+    if semi.parallelization_backend.ode_memory == "device":
+        import torch
+        dev = torch.device("cuda", semi.parallelization_backend.device)
+        u0 = torch.from_numpy(u0).to(dev)
+        v0 = torch.from_numpy(v0).to(dev)
+    return DynamicalODEProblem(kick_, drift_, v0, u0, tuple(tspan), SimpleNamespace(semi=semi))
+
+
+def kick_(dv_ode, v_ode, u_ode, p, t):
+    """`kick!(dv_ode, v_ode, u_ode, p, t)` (semidiscretization.jl:589-612)."""
+    semi: Semidiscretization = p.semi
+    nu, nv = semi.ranges_u[-1][1], semi.ranges_v[-1][1]
+    pdv = semi._ptr(dv_ode, nv, semi.eltype, "dv_ode")
+    pv = semi._ptr(v_ode, nv, semi.eltype, "v_ode")
+    pu = semi._ptr(u_ode, nu, semi.coordinates_eltype, "u_ode")
+    semi._bind_stream()
+    _lib.check(semi._handle, _lib.load().tpb_kick(semi._handle, pdv, pv, pu, float(t)))
+    return dv_ode
+
+
+def drift_(du_ode, v_ode, u_ode, p, t):
+    """`drift!(du_ode, v_ode, u_ode, p, t)` (semidiscretization.jl:522-536)."""
+    semi: Semidiscretization = p.semi
+    nu, nv = semi.ranges_u[-1][1], semi.ranges_v[-1][1]
+    pdu = semi._ptr(du_ode, nu, semi.coordinates_eltype, "du_ode")
+    pv = semi._ptr(v_ode, nv, semi.eltype, "v_ode")
+    pu = semi._ptr(u_ode, nu, semi.coordinates_eltype, "u_ode")
+    semi._bind_stream()
+    _lib.check(semi._handle, _lib.load().tpb_drift(semi._handle, pdu, pv, pu, float(t)))
+    return du_ode
