@@ -1,0 +1,319 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  `-m gpu` only.
+
+Bars (BASELINE.json north_star): neighbour sets bit-exact as integer sets; one RHS within
+1e-12 relative in Float64 and 1e-5 in Float32.  "Relative" is the max-norm error divided by
+the max-norm of the oracle's result, per output block (acceleration rows / density row):
+the reference itself is not bit-reproducible across thread counts or update strategies
+(test/validation/validation.jl:49-50), so only a norm-wise comparison is meaningful.
+"""
+import numpy as np
+import pytest
+
+import trixiparticles.jl_b200 as tp
+from trixiparticles.jl_b200 import examples
+from oracle import adapter
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}
+
+
+def rel_inf(a, b):
+    scale = np.abs(b).max()
+    return np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / (scale if scale > 0 else 1.0)
+
+
+def make_semi(fluid, wall, **backend):
+    systems = (fluid,) if wall is None else (fluid, wall)
+    semi = tp.Semidiscretization(*systems, parallelization_backend=tp.B200Backend(**backend))
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    return semi, ode
+
+
+def run_kick(fluid, wall, u, v, **backend):
+    semi, ode = make_semi(fluid, wall, **backend)
+    u_ode = np.ascontiguousarray(u).reshape(-1)
+    v_ode = np.ascontiguousarray(v).reshape(-1)
+    dv_ode = np.full_like(v_ode, np.nan)
+    du_ode = np.full_like(u_ode, np.nan)
+    tp.kick_(dv_ode, v_ode, u_ode, ode.p, 0.0)
+    tp.drift_(du_ode, v_ode, u_ode, ode.p, 0.0)
+    out = dict(dv=dv_ode.reshape(v.shape), du=du_ode.reshape(u.shape),
+               pressure=semi.system_field(fluid, "pressure"),
+               density=semi.system_field(fluid, "density"), stats=semi.stats())
+    if wall is not None:
+        out.update(wall_pressure=semi.system_field(wall, "pressure"),
+                   wall_density=semi.system_field(wall, "density"),
+                   wall_volume=semi.system_field(wall, "volume"))
+    semi.close()
+    return out
+
+
+def check_against_oracle(fluid, wall, u, v, tol_scale=1.0, **backend):
+    nd = fluid.ndims
+    tol = TOL[np.dtype(fluid.eltype)] * tol_scale
+    got = run_kick(fluid, wall, u, v, **backend)
+    ref = adapter.kick(fluid, wall, u, v)
+    errs = {"acc": rel_inf(got["dv"][:, :nd], ref["dv"][:, :nd])}
+    if got["dv"].shape[1] > nd:
+        errs["drho"] = rel_inf(got["dv"][:, nd], ref["dv"][:, nd])
+    errs["pressure"] = rel_inf(got["pressure"], ref["pressure"])
+    errs["density"] = rel_inf(got["density"], ref["density"])
+    if wall is not None:
+        errs["wall_pressure"] = rel_inf(got["wall_pressure"], ref["wall_pressure"])
+        errs["wall_density"] = rel_inf(got["wall_density"], ref["wall_density"])
+        errs["wall_volume"] = rel_inf(got["wall_volume"], ref["wall_volume"])
+    assert np.isfinite(got["dv"]).all()
+    bad = {k: e for k, e in errs.items() if not e <= tol}
+    assert not bad, f"parity above {tol:g}: {bad} (all: {errs})"
+    # drift!: du = v[1:ND] exactly (converted to the coordinate type)
+    assert np.array_equal(got["du"], v[:, :nd].astype(u.dtype))
+    assert got["stats"].launches_last_kick > 0
+    return errs
+
+
+# ------------------------------------------------------------------ neighbour sets
+@pytest.mark.parametrize("config", ["dam_break_2d", "hydrostatic_2d", "dam_break_3d"])
+@pytest.mark.parametrize("jitter", [False, True])
+def test_neighbor_sets_bit_exact(oracle, config, jitter):
+    if config == "dam_break_2d":
+        fluid, wall, _ = examples.dam_break_2d(20)
+    elif config == "hydrostatic_2d":
+        fluid, wall, _ = examples.hydrostatic_water_column_2d()
+    else:
+        fluid, wall, _ = examples.dam_break_3d(0.125)
+    u = fluid.initial_condition.coordinates.copy()
+    if jitter:
+        u, _ = examples.perturbed_state(fluid)
+    semi, ode = make_semi(fluid, wall)
+    u_ode = np.ascontiguousarray(u).reshape(-1)
+    R_f = float(fluid.eltype.type(2) * fluid.smoothing_length)
+    R_w = float(wall.eltype.type(2) * wall.boundary_model.smoothing_length)
+    for (a, b, xa, xb, R) in [(fluid, fluid, u, u, R_f), (fluid, wall, u, wall.coordinates, R_f),
+                              (wall, fluid, wall.coordinates, u, R_w)]:
+        gi, gj = semi.neighbor_pairs(a, b, u_ode)
+        oi, oj = oracle.neighbor_pairs(xa, xb, R, dtype=fluid.eltype, grid=True)
+        assert len(gi) == len(oi), (config, len(gi), len(oi))
+        assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
+    semi.close()
+
+
+def test_neighbor_sets_bruteforce_definition(oracle):
+    """Small case checked against the O(N^2) definition itself, Float32 with ties."""
+    fluid, wall, _ = examples.hydrostatic_water_column_2d()
+    u = fluid.initial_condition.coordinates
+    semi, ode = make_semi(fluid, wall)
+    gi, gj = semi.neighbor_pairs(fluid, fluid, u.reshape(-1).copy())
+    R = float(np.float32(2) * fluid.smoothing_length)
+    oi, oj = oracle.neighbor_pairs(u, u, R, dtype=np.float32, grid=False)
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
+    semi.close()
+
+
+# ------------------------------------------------------------------ one RHS evaluation
+@pytest.mark.parametrize("variant", [1, 0])
+def test_kick_dam_break_2d_f64(oracle, variant):
+    """BASELINE config 1: examples/fluid/dam_break_2d.jl, 3200 + 3912 particles, Float64."""
+    fluid, wall, _ = examples.dam_break_2d(40)
+    assert (fluid.nparticles, wall.nparticles) == (3200, 3912)
+    ic = fluid.initial_condition
+    v0 = np.concatenate([ic.velocity, ic.density[:, None]], axis=1)
+    check_against_oracle(fluid, wall, ic.coordinates, v0, interact_variant=variant)
+    u, v = examples.perturbed_state(fluid)
+    check_against_oracle(fluid, wall, u, v, interact_variant=variant)
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+def test_kick_hydrostatic_2d_f32(oracle, variant):
+    """BASELINE config 2: hydrostatic_water_column_2d.jl, 360 + 276 particles, Float32."""
+    fluid, wall, _ = examples.hydrostatic_water_column_2d()
+    assert (fluid.nparticles, wall.nparticles) == (360, 276)
+    ic = fluid.initial_condition
+    v0 = np.concatenate([ic.velocity, ic.density[:, None]], axis=1)
+    check_against_oracle(fluid, wall, ic.coordinates, v0, interact_variant=variant)
+    u, v = examples.perturbed_state(fluid)
+    check_against_oracle(fluid, wall, u, v, interact_variant=variant)
+
+
+@pytest.mark.parametrize("eltype,cdtype", [(np.float32, np.float32), (np.float32, np.float64),
+                                           (np.float64, np.float64)])
+@pytest.mark.parametrize("variant", [1, 0])
+def test_kick_dam_break_3d(oracle, eltype, cdtype, variant):
+    """BASELINE config 3 geometry at a size the oracle finishes in seconds (dx = 0.1:
+    2000 fluid + 30k wall), all three precision combinations."""
+    fluid, wall, _ = examples.dam_break_3d(0.1, eltype=eltype, coordinates_eltype=cdtype)
+    u, v = examples.perturbed_state(fluid)
+    check_against_oracle(fluid, wall, u, v, interact_variant=variant)
+    ic = fluid.initial_condition
+    v0 = np.concatenate([ic.velocity, ic.density[:, None]], axis=1)
+    check_against_oracle(fluid, wall, ic.coordinates, v0, interact_variant=variant)
+
+
+def test_kick_dam_break_3d_medium(oracle):
+    """Same geometry at dx = 0.04 (31k fluid + 190k wall particles), Float32."""
+    fluid, wall, _ = examples.dam_break_3d(0.04)
+    u, v = examples.perturbed_state(fluid)
+    check_against_oracle(fluid, wall, u, v)
+
+
+@pytest.mark.parametrize("example", ["dam_break_2d", "hydrostatic_2d"])
+def test_kick_summation_density(oracle, example):
+    """SummationDensity variant (density_calculators.jl:26-50; dam_break_2d variant in
+    test/examples/examples_fluid.jl:160-164)."""
+    if example == "dam_break_2d":
+        fluid, wall, _ = examples.dam_break_2d(20, density_calculator=tp.SummationDensity())
+    else:
+        fluid, wall, _ = examples.hydrostatic_water_column_2d(density_calculator=tp.SummationDensity(),
+                                                              eltype=np.float64, coordinates_eltype=np.float64)
+    u, v = examples.perturbed_state(fluid)
+    assert v.shape[1] == 2
+    check_against_oracle(fluid, wall, u, v)
+
+
+def test_kick_fluid_only_and_source_damping(oracle):
+    """No wall system; SourceTermDamping (semidiscretization.jl:795-807)."""
+    ic = tp.RectangularShape(0.05, (14, 11), (0.0, 0.0), density=1000.0)
+    se = tp.StateEquationCole(sound_speed=10.0, reference_density=1000.0, exponent=7,
+                              background_pressure=100.0, clip_negative_pressure=True)
+    fluid = tp.WeaklyCompressibleSPHSystem(ic, smoothing_kernel=tp.SchoenbergCubicSplineKernel(2),
+                                           smoothing_length=0.06, density_calculator=tp.ContinuityDensity(),
+                                           state_equation=se,
+                                           viscosity=tp.ArtificialViscosityMonaghan(alpha=0.05, beta=0.3),
+                                           acceleration=(0.3, -9.81),
+                                           source_terms=tp.SourceTermDamping(2.5))
+    u, v = examples.perturbed_state(fluid)
+    check_against_oracle(fluid, None, u, v)
+
+
+def test_interaction_matrix_disables_wall(oracle):
+    """interaction_matrix[fluid, wall] = false (semidiscretization.jl:157-187)."""
+    fluid, wall, _ = examples.hydrostatic_water_column_2d(eltype=np.float64, coordinates_eltype=np.float64)
+    u, v = examples.perturbed_state(fluid)
+    semi = tp.Semidiscretization(fluid, wall, interaction_matrix=[[True, False], [True, True]])
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    dv = np.zeros(v.size)
+    tp.kick_(dv, v.reshape(-1).copy(), u.reshape(-1).copy(), ode.p, 0.0)
+    ref = adapter.kick(fluid, None, u, v)
+    assert rel_inf(dv.reshape(v.shape), ref["dv"]) <= 1e-12
+    semi.close()
+
+
+# ------------------------------------------------------------------ properties at scale
+def test_conservation_and_determinism_large():
+    """Size-independent properties at a size the oracle is not run on (dx = 0.02: 250k fluid +
+    0.7M wall particles, Float32): fluid-only momentum conservation, bitwise run-to-run
+    reproducibility, and invariance under a permutation of the particle order."""
+    fluid, wall, _ = examples.dam_break_3d(0.02)
+    u, v = examples.perturbed_state(fluid)
+    # (a) fluid-fluid forces are pairwise antisymmetric: sum m dv = 0 without wall and gravity
+    f2 = tp.WeaklyCompressibleSPHSystem(fluid.initial_condition, smoothing_kernel=fluid.smoothing_kernel,
+                                        smoothing_length=fluid.smoothing_length,
+                                        density_calculator=tp.ContinuityDensity(),
+                                        state_equation=fluid.state_equation, viscosity=fluid.viscosity,
+                                        density_diffusion=fluid.density_diffusion)
+    out = run_kick(f2, None, u, v)
+    acc = out["dv"][:, :3].astype(np.float64)
+    m = fluid.mass.astype(np.float64)[:, None]
+    assert np.abs((m * acc).sum(axis=0)).max() <= 2e-4 * np.abs(m * acc).sum(axis=0).max()
+    # (b) determinism
+    a = run_kick(fluid, wall, u, v)["dv"]
+    b = run_kick(fluid, wall, u, v)["dv"]
+    assert np.array_equal(a, b)
+    # (c) permutation invariance (same sets, possibly different summation order)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(fluid.nparticles)
+    ic = fluid.initial_condition
+    ic_p = tp.InitialCondition(ic.coordinates[perm], ic.velocity[perm], ic.mass[perm],
+                               ic.density[perm], ic.pressure[perm], ic.particle_spacing)
+    f3 = tp.WeaklyCompressibleSPHSystem(ic_p, smoothing_kernel=fluid.smoothing_kernel,
+                                        smoothing_length=fluid.smoothing_length,
+                                        density_calculator=tp.ContinuityDensity(),
+                                        state_equation=fluid.state_equation, viscosity=fluid.viscosity,
+                                        density_diffusion=fluid.density_diffusion,
+                                        acceleration=tuple(fluid.acceleration))
+    c = run_kick(f3, wall, u[perm], v[perm])["dv"]
+    assert rel_inf(c[:, :3], a[perm][:, :3]) <= 1e-5
+    assert rel_inf(c[:, 3], a[perm][:, 3]) <= 1e-5
+
+
+# ------------------------------------------------------------------ edge cases / errors
+def test_out_of_bounds_particle_is_reported():
+    fluid, wall, _ = examples.hydrostatic_water_column_2d()
+    semi, ode = make_semi(fluid, wall)
+    u = fluid.initial_condition.coordinates.copy()
+    u[5] = [50.0, 50.0]
+    v = np.zeros((fluid.nparticles, 3), dtype=np.float32)
+    v[:, 2] = 1000.0
+    from trixiparticles.jl_b200._lib import TpbError
+    with pytest.raises(TpbError) as e:
+        tp.kick_(np.zeros(v.size, np.float32), v.reshape(-1), u.reshape(-1), ode.p, 0.0)
+    assert e.value.code == 4
+    semi.close()
+
+
+def test_nan_coordinates_do_not_corrupt_memory():
+    fluid, wall, _ = examples.hydrostatic_water_column_2d()
+    semi, ode = make_semi(fluid, wall)
+    u = fluid.initial_condition.coordinates.copy()
+    u[7, 0] = np.nan
+    v = np.zeros((fluid.nparticles, 3), dtype=np.float32)
+    v[:, 2] = 1000.0
+    from trixiparticles.jl_b200._lib import TpbError
+    with pytest.raises(TpbError) as e:
+        tp.kick_(np.zeros(v.size, np.float32), v.reshape(-1), u.reshape(-1), ode.p, 0.0)
+    assert e.value.code == 4
+    semi.close()
+
+
+def test_full_grid_cell_list_bounds(oracle):
+    """User-supplied FullGridCellList box (examples/fluid/dam_break_2d_gpu.jl:30-33)."""
+    fluid, wall, tank = examples.dam_break_2d(20)
+    u, v = examples.perturbed_state(fluid)
+    lo = wall.coordinates.min(axis=0) - 0.01
+    hi = wall.coordinates.max(axis=0) + 0.01
+    nhs = tp.GridNeighborhoodSearch(2, cell_list=tp.FullGridCellList(lo, hi, max_points_per_cell=30))
+    semi = tp.Semidiscretization(fluid, wall, neighborhood_search=nhs)
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    dv = np.zeros(v.size)
+    tp.kick_(dv, v.reshape(-1).copy(), u.reshape(-1).copy(), ode.p, 0.0)
+    ref = adapter.kick(fluid, wall, u, v)
+    assert rel_inf(dv.reshape(v.shape)[:, :2], ref["dv"][:, :2]) <= 1e-12
+    semi.close()
+
+
+def test_device_resident_ode_vectors(oracle):
+    """B200Backend(ode_memory='device'): torch CUDA tensors, stream-ordered, no host copies."""
+    import torch
+    fluid, wall, _ = examples.dam_break_3d(0.1)
+    u, v = examples.perturbed_state(fluid)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    assert ode.u0.is_cuda and ode.v0.is_cuda
+    u_d = torch.from_numpy(u.reshape(-1).copy()).cuda()
+    v_d = torch.from_numpy(v.reshape(-1).copy()).cuda()
+    dv_d = torch.full_like(v_d, float("nan"))
+    du_d = torch.full_like(u_d, float("nan"))
+    tp.kick_(dv_d, v_d, u_d, ode.p, 0.0)
+    tp.drift_(du_d, v_d, u_d, ode.p, 0.0)
+    semi.synchronize()
+    ref = adapter.kick(fluid, wall, u, v)
+    got = dv_d.cpu().numpy().reshape(v.shape)
+    assert rel_inf(got[:, :3], ref["dv"][:, :3]) <= 1e-5
+    assert rel_inf(got[:, 3], ref["dv"][:, 3]) <= 1e-5
+    assert np.array_equal(du_d.cpu().numpy().reshape(u.shape), v[:, :3])
+    semi.close()
+
+
+def test_empty_fluid():
+    """Zero fluid particles: kick!/drift! are no-ops on zero-length ODE vectors."""
+    ic = tp.InitialCondition(np.zeros((0, 2)), np.zeros((0, 2)), np.zeros(0), np.zeros(0), np.zeros(0), 0.1)
+    se = tp.StateEquationCole(sound_speed=10.0, reference_density=1000.0, exponent=7)
+    fluid = tp.WeaklyCompressibleSPHSystem(ic, smoothing_kernel=tp.WendlandC2Kernel(2), smoothing_length=0.2,
+                                           density_calculator=tp.ContinuityDensity(), state_equation=se)
+    _, wall, _ = examples.hydrostatic_water_column_2d(eltype=np.float64, coordinates_eltype=np.float64)
+    semi = tp.Semidiscretization(fluid, wall)
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    assert ode.u0.size == 0 and ode.v0.size == 0
+    tp.kick_(np.zeros(0), np.zeros(0), np.zeros(0), ode.p, 0.0)
+    tp.drift_(np.zeros(0), np.zeros(0), np.zeros(0), ode.p, 0.0)
+    semi.close()

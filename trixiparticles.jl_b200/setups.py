@@ -172,10 +172,12 @@ def RectangularShape(particle_spacing, n_particles_per_dimension, min_coordinate
     return InitialCondition(coords, vel, masses, densities, press, float(particle_spacing))
 
 
-def _round_n_particles(size, spacing):
-    # rectangular_tank.jl:406-416 (Julia `round` = ties-to-even, as np.rint)
-    n = int(np.rint(size / spacing))
-    return n, n * spacing
+def _round_n_particles(size, spacing, t=np.float64):
+    # rectangular_tank.jl:406-416 (Julia `round` = ties-to-even, as np.rint); evaluated in
+    # ELTYPE like the reference (`size` and `spacing` are ELTYPE values there)
+    t = np.dtype(t).type
+    n = int(np.rint(t(size) / t(spacing)))
+    return n, float(t(n) * t(spacing))
 
 
 @dataclass
@@ -263,7 +265,7 @@ def RectangularTank(particle_spacing, fluid_size: Sequence[float], tank_size: Se
 
     n_f = []
     for d in range(ndims):
-        n, new = _round_n_particles(fluid_size_[d], spacing)
+        n, new = _round_n_particles(fluid_size_[d], spacing, t)
         n_f.append(n)
         fluid_size_[d] = new
     for d in range(ndims):
@@ -272,7 +274,7 @@ def RectangularTank(particle_spacing, fluid_size: Sequence[float], tank_size: Se
     n_b = []
     b_spacing = spacing / spacing_ratio
     for d in range(ndims):
-        n, new = _round_n_particles(tank_size_[d], b_spacing)
+        n, new = _round_n_particles(tank_size_[d], b_spacing, t)
         n_b.append(n)
         tank_size_[d] = new
 
