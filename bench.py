@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- particle-RHS evaluations per second of the WCSPH right-hand side on B200.
+
+One "step" = one `kick!` + one `drift!` (TrixiParticles.jl semidiscretization.jl:522-612:
+neighbourhood-search rebuild, EOS, Adami wall pressure, fluid-fluid and fluid-wall
+`interact!`, gravity, du = v) over one synthetic particle lattice.  Metric (BASELINE.json):
+particle-RHS evaluations / s = N_fluid * steps / time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+Own arm (default): the CUDA library through the reference-facing API.
+  value     device-resident ODE vectors (torch CUDA tensors), CUDA events, L2 flushed
+            between steps.
+  e2e       the same step through `B200Backend(ode_memory="host")`: pinned host ODE vectors,
+            host<->device copies inside the timed region.
+  roofline  the dominant kernel phase (interact!) timed with CUDA events inside the library
+            on the launching stream during the timed steps.
+  cpu_baseline  the CPU oracle (a port of the reference algorithm; Julia is not installed)
+            timed on this box's host cores on the same workload.
+Reference arm (--impl reference): the CPU oracle port, all host threads, same workload.
+
+N > 1 (torchrun): the lattice is slab-decomposed along x, one slab per rank, ghost layers are
+exchanged with NCCL send/recv every kick (see trixiparticles.jl_b200/slabs.py); "scaling" is
+"weak": every rank gets a slab of the N = 1 size.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle-RHS evals/s (particles x steps/s)"
+UNIT = "particle-RHS/s"
+
+# name -> (example, particle spacing).  SURVEY.md section 8(d) M3 / M4.
+WORKLOADS = {
+    "dam_break_3d_1m": ("dam_break_3d", 0.0126),     # 992 319 fluid + 1 599 800 wall
+    "dam_break_3d_10m": ("dam_break_3d", 0.00585),   # ~10 M fluid
+    "dam_break_3d_250k": ("dam_break_3d", 0.02),     # reduced sample for slow CPU legs
+    "dam_break_3d_small": ("dam_break_3d", 0.05),    # quick functional check
+    "dam_break_2d": ("dam_break_2d", 40),            # config 1 (Float64)
+}
+DEFAULT_WORKLOAD = "dam_break_3d_1m"
+
+# algorithmic bytes per particle (DESIGN.md "Roofline accounting")
+def bytes_per_particle(nd, tsize, csize):
+    pad16 = lambda b: (b + 15) // 16 * 16
+    nv = nd + 1
+    b_io = nd * csize + nv * tsize + tsize + nv * tsize + 2 * nd * tsize
+    b_nhs = 8 + 2 * (pad16(nd * csize + tsize) + pad16(nv * tsize)) + 8
+    step_fluid = b_io + b_nhs
+    step_wall = 2 * pad16(nd * csize + tsize) + 2 * (2 * tsize)
+    # interact! kernel alone: sorted records in (A, B, P, perm), dv out; wall tiles (A, W) in
+    k_fluid = pad16(nd * csize + tsize) + pad16(nv * tsize) + tsize + 4 + nv * tsize
+    k_wall = pad16(nd * csize + tsize) + 2 * tsize
+    return dict(step_fluid=step_fluid, step_wall=step_wall, kernel_fluid=k_fluid, kernel_wall=k_wall)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def make_workload(name):
+    from trixiparticles.jl_b200 import examples
+    ex, arg = WORKLOADS[name]
+    if ex == "dam_break_3d":
+        fluid, wall, _ = examples.dam_break_3d(arg)
+    else:
+        fluid, wall, _ = examples.dam_break_2d(arg)
+    ic = fluid.initial_condition
+    u = np.ascontiguousarray(ic.coordinates, dtype=fluid.coordinates_eltype)
+    v = np.ascontiguousarray(np.concatenate([ic.velocity, ic.density[:, None]], axis=1), dtype=fluid.eltype)
+    return fluid, wall, u, v
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if exe is None:
+            return
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        self.out = open(self.path, "w")
+        self.proc = subprocess.Popen([exe, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.device), "-lms", "200"], stdout=self.out,
+                                     stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.close()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+# ------------------------------------------------------------------ CPU legs (oracle port)
+def cpu_step_time(fluid, wall, u, v, reps, nthreads=0):
+    """Times `reps` oracle kick!+drift! evaluations; returns (seconds per step, threads)."""
+    from oracle import adapter, oracle as O
+    O.build()
+    nd = fluid.ndims
+    adapter.kick(fluid, wall, u, v, nthreads=nthreads)  # warm-up (page faults, thread pool)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        adapter.kick(fluid, wall, u, v, nthreads=nthreads)
+        O.drift(v, nd, u.dtype)
+    dt = (time.perf_counter() - t0) / reps
+    return dt, (nthreads or O.max_threads())
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; Julia is not installed in
+    this image, so the unmodified reference cannot run) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import adapter, oracle as O
+    O.build()
+    name = args.workload
+    fluid, wall, u, v = make_workload(name)
+    nd = fluid.ndims
+    t0 = time.perf_counter()
+    adapter.kick(fluid, wall, u, v)
+    t1 = time.perf_counter() - t0
+    sample = f"full workload {name}: {fluid.nparticles} fluid + {wall.nparticles} wall particles per step"
+    if (args.steps + args.warmup) * t1 > 240.0 and name != "dam_break_3d_250k":
+        small = "dam_break_3d_250k"
+        fluid, wall, u, v = make_workload(small)
+        sample = (f"reduced lattice {small} of the same geometry ({fluid.nparticles} fluid + "
+                  f"{wall.nparticles} wall per step) because the full {name} would exceed the time bound")
+    for _ in range(args.warmup):
+        adapter.kick(fluid, wall, u, v)
+        O.drift(v, nd, u.dtype)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        adapter.kick(fluid, wall, u, v)
+        O.drift(v, nd, u.dtype)
+    dt = time.perf_counter() - t0
+    value = fluid.nparticles * args.steps / dt
+    cores = O.max_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if np.dtype(fluid.eltype).itemsize == 4 else "f64", "data": "synthetic",
+        "config": {"workload": name, "n_fluid": fluid.nparticles, "n_wall": wall.nparticles,
+                   "note": "CPU oracle port of the reference algorithm (OpenMP); TrixiParticles.jl itself "
+                           "needs Julia, which this image does not have"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ own arm, one GPU
+def run_single(args):
+    import torch
+    import trixiparticles.jl_b200 as tp
+    from trixiparticles.jl_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the accelerated path has no CPU fallback")
+    _lib.load()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    fluid, wall, u, v = make_workload(args.workload)
+    nd, n_f, n_w = fluid.ndims, fluid.nparticles, wall.nparticles
+    tsize, csize = np.dtype(fluid.eltype).itemsize, np.dtype(fluid.coordinates_eltype).itemsize
+
+    # ---- device-resident arm
+    backend = tp.B200Backend(device=0, ode_memory="device", interact_variant=args.variant)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=backend)
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    u_d = torch.from_numpy(u.reshape(-1)).to(dev)
+    v_d = torch.from_numpy(v.reshape(-1)).to(dev)
+    dv_d = torch.empty_like(v_d)
+    du_d = torch.empty_like(u_d)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
+        ode.f2(du_d, v_d, u_d, ode.p, 0.0)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    semi.synchronize()
+    torch.cuda.synchronize()
+    st0 = semi.stats()
+    semi.set_profiling(args.steps)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    clocks = ClockSampler(0)
+    clocks.start()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)           # evict L2 (untimed: outside the event pair)
+        starts[k].record()
+        ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
+        mids[k].record()
+        ode.f2(du_d, v_d, u_d, ode.p, 0.0)
+        ends[k].record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    semi.synchronize()   # raises if a deferred device-side error (out of bounds) was flagged
+    ms_steps = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    ms_kick = np.array([s.elapsed_time(m) for s, m in zip(starts, mids)])
+    ms_drift = np.array([m.elapsed_time(e) for m, e in zip(mids, ends)])
+    phases = semi.phase_times()
+    st1 = semi.stats()
+    # keep the GPU busy a little longer if the timed region was too short for a clock sample
+    if t_wall < 1.0:
+        t_end = time.perf_counter() + 1.0
+        while time.perf_counter() < t_end:
+            step()
+        torch.cuda.synchronize()
+    clk = clocks.stop()
+    total_ms = float(ms_steps.sum())
+    value = n_f * args.steps / (total_ms * 1e-3)
+    launches = int(st1.kernel_launches_total - st0.kernel_launches_total)
+
+    # L2-warm variant (no flush), reported for information
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_warm = e0.elapsed_time(e1) / args.steps
+
+    # active wall particles = those with a fluid neighbour (Adami volume > 0)
+    n_w_active = int((semi.system_field(wall, "volume") > 0).sum())
+    # accepted pair counts (capacity 0 => only the count comes back)
+    pairs = {}
+    for name, a, b in (("fluid_fluid", fluid, fluid), ("fluid_wall", fluid, wall), ("wall_fluid", wall, fluid)):
+        pairs[name] = semi.count_neighbor_pairs(a, b, u_d)
+
+    # ---- roofline of the dominant kernel phase (interact!)
+    peak_gbs, peak_src, sm_max_mhz = load_peaks()
+    bpp = bytes_per_particle(nd, tsize, csize)
+    k_bytes = n_f * bpp["kernel_fluid"] + n_w_active * bpp["kernel_wall"]
+    k_ms = phases["interact"]
+    achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    step_bytes = n_f * bpp["step_fluid"] + n_w_active * bpp["step_wall"]
+    step_achieved = step_bytes / (total_ms / args.steps * 1e-3) / 1e9
+    # algorithmic flops: 80 / 55 / 12 per accepted pair, 9 per candidate
+    cand_per_particle = 729 if nd == 3 else 144 if args.workload == "dam_break_2d" else 9 * 16
+    flops = (pairs["fluid_fluid"] * 80 + pairs["fluid_wall"] * 55 + pairs["wall_fluid"] * 12
+             + 9.0 * cand_per_particle * (2 * n_f + n_w_active))
+    fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    roofline = {
+        "bound": "hbm", "kernel": "interact! phase (fluid-fluid + fluid-wall pair sweep)",
+        "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+        "peak_source": peak_src, "traffic": None,
+        "algorithmic_bytes_per_launch": k_bytes, "kernel_ms": k_ms,
+        "kernel_share_of_step": k_ms / (total_ms / args.steps),
+        "note": "the pair sweep is FP32-issue bound (about 300 flop per compulsory byte), see fp32 and DESIGN.md",
+        "step": {"achieved": step_achieved, "frac": step_achieved / peak_gbs, "algorithmic_bytes": step_bytes,
+                 "bytes_per_fluid_particle": bpp["step_fluid"], "bytes_per_active_wall_particle": bpp["step_wall"]},
+        "fp32": {"algorithmic_tflops": flops / (ms_kick.mean() * 1e-3) / 1e12, "nominal_peak_tflops": fp32_peak,
+                 "frac_of_nominal": flops / (ms_kick.mean() * 1e-3) / 1e12 / fp32_peak,
+                 "pairs": pairs},
+    }
+    semi.close()
+    del u_d, v_d, dv_d, du_d, flush
+    torch.cuda.empty_cache()
+
+    # ---- e2e arm: host ODE vectors through the same API, copies inside the timed region
+    e2e = run_e2e(tp, torch, fluid, wall, u, v, args)
+
+    # ---- CPU baseline (oracle port) on this box's host cores, bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        dt, cores = cpu_step_time(fluid, wall, u, v, reps=1)
+        reps = int(min(8, max(2, 12.0 / max(dt, 1e-3))))
+        dt, cores = cpu_step_time(fluid, wall, u, v, reps=reps)
+        cpu = {"value": n_f / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{reps} kick!+drift! evaluations of the full workload ({n_f} fluid + {n_w} wall) "
+                         f"with the OpenMP CPU oracle, {1e3 * dt:.1f} ms each"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if tsize == 4 else "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "n_fluid": n_f, "n_wall": n_w, "n_wall_active": n_w_active,
+                   "ndims": nd, "coords_dtype": "f32" if csize == 4 else "f64",
+                   "kernel": "WendlandC2" if fluid.smoothing_kernel.kernel_id == 0 else "SchoenbergCubicSpline",
+                   "nhs": "rebuilt every kick", "l2": "flushed between steps (256 MiB write, untimed)",
+                   "interact_variant": int(st1.interact_variant_used)},
+        "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        "phases_ms": {**{k: phases[k] for k in _lib.PHASES}, "kick": float(ms_kick.mean()),
+                      "drift": float(ms_drift.mean()), "step_min": float(ms_steps.min()),
+                      "step_median": float(np.median(ms_steps)), "step_l2_warm": ms_warm},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def run_e2e(tp, torch, fluid, wall, u, v, args):
+    """Host-pointer mode of the C ABI (what a CPU-side integrator sees): pinned host ODE
+    vectors, H2D of u and v and D2H of dv in `kick!`, H2D of v and D2H of du in `drift!`."""
+    backend = tp.B200Backend(device=0, ode_memory="host", interact_variant=args.variant)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=backend)
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+
+    def pinned(a):
+        t = torch.empty(a.size, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+        t.numpy()[:] = a.reshape(-1)
+        return t
+
+    tu, tv = pinned(u), pinned(v)
+    tdv, tdu = pinned(np.zeros_like(v)), pinned(np.zeros_like(u))
+    hu, hv, hdv, hdu = tu.numpy(), tv.numpy(), tdv.numpy(), tdu.numpy()
+    for _ in range(max(args.warmup, 3)):
+        ode.f1(hdv, hv, hu, ode.p, 0.0)
+        ode.f2(hdu, hv, hu, ode.p, 0.0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ode.f1(hdv, hv, hu, ode.p, 0.0)   # returns after dv is in host memory
+        ode.f2(hdu, hv, hu, ode.p, 0.0)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert np.isfinite(hdv).all() and np.array_equal(hdu.reshape(u.shape), v[:, : fluid.ndims].astype(u.dtype))
+    semi.close()
+    return {"value": fluid.nparticles * args.steps / dt, "unit": UNIT,
+            "h2d_bytes_per_step": int(hu.nbytes + 2 * hv.nbytes), "d2h_bytes_per_step": int(hdv.nbytes + hdu.nbytes),
+            "ms_per_step": 1e3 * dt / args.steps, "timing": "host wall clock around the synchronous host-pointer calls"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", type=int, default=0, help="interact kernel variant (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 or world > 1:
+        from trixiparticles.jl_b200 import slabs_bench
+        slabs_bench.run(args)
+        return
+    run_single(args)
+
+
+if __name__ == "__main__":
+    main()

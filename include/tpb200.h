@@ -174,6 +174,20 @@ int32_t tpb_synchronize(tpb_semi_t semi);
 int32_t tpb_set_stream(tpb_semi_t semi, void *stream);
 int32_t tpb_get_stats(tpb_semi_t semi, tpb_stats *out);
 
+/* Phase timing of `tpb_kick` with CUDA events on the handle's stream (the reference's
+ * TimerOutputs sections "update systems and nhs" / "system interaction",
+ * semidiscretization.jl:596-606).  `tpb_set_profiling(max_kicks)` arms recording for the next
+ * `max_kicks` kicks (0 disables); `tpb_get_phase_times` synchronises, writes the mean
+ * duration in ms of each phase into ms_mean[TPB_N_PHASES - 1] and re-arms. */
+#define TPB_PHASE_REBUILD 0  /* NHS rebuild: cell keys, counting sort, reorder + EOS */
+#define TPB_PHASE_DENSITY 1  /* summation density sweep (SummationDensity only) */
+#define TPB_PHASE_BOUNDARY 2 /* Adami wall pressure extrapolation */
+#define TPB_PHASE_INTERACT 3 /* fluid-fluid + fluid-wall interact!, source terms */
+#define TPB_PHASE_END 4
+#define TPB_N_PHASES 5
+int32_t tpb_set_profiling(tpb_semi_t semi, int32_t max_kicks);
+int32_t tpb_get_phase_times(tpb_semi_t semi, double *ms_mean, int32_t *n_kicks);
+
 /* page-lock / unlock caller memory so TPB_MEM_HOST transfers run at full PCIe speed */
 int32_t tpb_host_register(void *ptr, int64_t bytes);
 int32_t tpb_host_unregister(void *ptr);

@@ -21,8 +21,9 @@ EXPORTS = [
     "tpb_add_wall_system", "tpb_set_interaction", "tpb_semidiscretize", "tpb_ode_sizes",
     "tpb_system_range", "tpb_kick", "tpb_drift", "tpb_get_system_field", "tpb_neighbor_pairs",
     "tpb_synchronize", "tpb_set_stream", "tpb_get_stats", "tpb_host_register",
-    "tpb_host_unregister",
+    "tpb_host_unregister", "tpb_set_profiling", "tpb_get_phase_times",
 ]
+PHASES = ("rebuild", "density", "boundary", "interact")
 
 
 class Config(C.Structure):
@@ -108,6 +109,9 @@ def load():
     L.tpb_get_stats.restype = i32; L.tpb_get_stats.argtypes = [p, C.POINTER(Stats)]
     L.tpb_host_register.restype = i32; L.tpb_host_register.argtypes = [p, i64]
     L.tpb_host_unregister.restype = i32; L.tpb_host_unregister.argtypes = [p]
+    L.tpb_set_profiling.restype = i32; L.tpb_set_profiling.argtypes = [p, i32]
+    L.tpb_get_phase_times.restype = i32
+    L.tpb_get_phase_times.argtypes = [p, C.POINTER(d), C.POINTER(i32)]
     _lib = L
     return L
 

@@ -59,7 +59,18 @@ struct Semi {
     tpb_stats stats{};
     int launches_this_call = 0;
     int deferred_status = TPB_OK;
+
+    // phase profiling (tpb_set_profiling): one row of TPB_N_PHASES + 1 events per recorded kick
+    std::vector<cudaEvent_t> prof_events;
+    int prof_capacity = 0, prof_kicks = 0;
 };
+
+// event marking the start of phase `ph` of the kick being recorded (ph == TPB_N_PHASES - 1: end)
+inline void prof_mark(Semi &s, int ph)
+{
+    if (s.prof_capacity > 0 && s.prof_kicks < s.prof_capacity)
+        cudaEventRecord(s.prof_events[(size_t)s.prof_kicks * TPB_N_PHASES + ph], s.stream);
+}
 
 inline size_t tsize(int eltype) { return eltype == TPB_F64 ? 8 : 4; }
 
@@ -219,6 +230,7 @@ struct Ops {
                        s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
                        s.d_perm_f);
         }
+        if (use_tiles(s)) return build_tile_table(s, s.d_fcell_start, s.tiles.d_frow_tile_start);
         return TPB_OK;
     }
 
@@ -244,6 +256,8 @@ struct Ops {
                    s.d_key, s.d_wcell_start, s.d_tmp_perm, n, (V4<CT> *)s.d_Aw, (V2<T> *)s.d_Ww,
                    s.d_perm_w);
         CUDA_TRY(&s, cudaMemsetAsync(s.d_volw, 0, sizeof(T) * (size_t)std::max(n, 1), s.stream));
+        rc = build_tile_table(s, s.d_wcell_start, s.tiles.d_wrow_tile_start);
+        if (rc) return rc;
         CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
         cudaFree(d_coords);
         cudaFree(d_mass);
@@ -262,8 +276,30 @@ struct Ops {
                (V4<T> *)s.d_B, (T *)s.d_P);
     }
 
+    // ---- tile table of one sorted point set: tiles per cell row + exclusive scan
+    static int build_tile_table(Semi &s, const int *d_cell_start, int *d_row_tile_start)
+    {
+        const int nrows = s.tiles.nrows;
+        LAUNCH(s, k_row_tiles, cdiv(nrows, 256), 256, 0, d_cell_start, s.ncell[0], nrows,
+               s.tiles.d_row_tiles);
+        return exclusive_scan(s, s.tiles.d_row_tiles, nrows, d_row_tile_start);
+    }
+
+    static int use_tiles(Semi &s)
+    {
+        int variant = s.cfg.interact_variant;
+        return variant == 0 || variant == 2;
+    }
+
+    template <typename K>
+    static int set_smem(Semi &s, K kernel, size_t bytes)
+    {
+        CUDA_TRY(&s, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        return TPB_OK;
+    }
+
     template <int KERNEL>
-    static void launch_adami(Semi &s, const GridConst<CT> &g)
+    static int launch_adami(Semi &s, const GridConst<CT> &g)
     {
         int n = (int)s.n_w;
         AdamiConst<T> k;
@@ -275,10 +311,26 @@ struct Ops {
         for (int d = 0; d < 3; ++d) k.acc[d] = (T)s.fp.acceleration[d];
         k.p_off = (T)s.wp.pressure_offset;
         k.clip = s.wp.clip_negative_pressure;
+        if (use_tiles(s)) {
+            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, s.tiles.list_len);
+            const size_t smem = tile_smem_bytes<T, CT>(cap, s.tiles.list_len);
+            static bool attr_set = false;
+            if (!attr_set) {
+                int rc = set_smem(s, k_adami_tiles<ND, T, CT, KERNEL>, 227 * 1024);
+                if (rc) return rc;
+                attr_set = true;
+            }
+            LAUNCH(s, (k_adami_tiles<ND, T, CT, KERNEL>), s.tiles.max_wtiles, TILE_TB, smem, g,
+                   s.tiles.d_wrow_tile_start, s.tiles.nrows, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
+                   s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
+                   s.interaction[1][0], k, (V2<T> *)s.d_Ww, (T *)s.d_volw, cap, s.tiles.list_len);
+            return TPB_OK;
+        }
         LAUNCH(s, (k_adami<ND, T, CT, KERNEL>), cdiv(n, 128), 128, 0, n, g,
                (const V4<CT> *)s.d_Aw, s.d_fcell_start, (const V4<CT> *)s.d_A,
                (const V4<T> *)s.d_B, (const T *)s.d_P, s.interaction[1][0], k,
                (V2<T> *)s.d_Ww, (T *)s.d_volw);
+        return TPB_OK;
     }
 
     template <int KERNEL, int DENS>
@@ -293,16 +345,22 @@ struct Ops {
         }
         src.damping = (T)s.fp.damping_coefficient;
         int has_wall = s.n_w > 0 && s.interaction[0][1];
-        int variant = s.cfg.interact_variant;
-        if (variant == 0) variant = tiles_supported<ND, T, CT>() ? 2 : 1;
-        if (variant == 2 && !tiles_supported<ND, T, CT>()) variant = 1;
-        s.stats.interact_variant_used = variant;
-        if (variant == 2) {
-            return launch_interact_tiles<ND, T, CT, KERNEL, DENS>(
-                s.tiles, s.stream, n, g, s.d_fcell_start, (const V4<CT> *)s.d_A,
-                (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f, s.interaction[0][0], has_wall,
-                s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv,
-                s.launches_this_call, s.stats.kernel_launches_total);
+        s.stats.interact_variant_used = use_tiles(s) ? 2 : 1;
+        if (use_tiles(s)) {
+            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, s.tiles.list_len);
+            const size_t smem = tile_smem_bytes<T, CT>(cap, s.tiles.list_len);
+            static bool attr_set = false;
+            if (!attr_set) {
+                int rc = set_smem(s, k_interact_tiles<ND, T, CT, KERNEL, DENS>, 227 * 1024);
+                if (rc) return rc;
+                attr_set = true;
+            }
+            LAUNCH(s, (k_interact_tiles<ND, T, CT, KERNEL, DENS>), s.tiles.max_ftiles, TILE_TB, smem, g,
+                   s.tiles.d_frow_tile_start, s.tiles.nrows, s.d_fcell_start, (const V4<CT> *)s.d_A,
+                   (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f, s.interaction[0][0], has_wall,
+                   s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv, cap,
+                   s.tiles.list_len);
+            return TPB_OK;
         }
         LAUNCH(s, (k_interact_pp<ND, T, CT, KERNEL, DENS>), cdiv(n, 128), 128, 0, n, g,
                s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
@@ -315,6 +373,7 @@ struct Ops {
     static int kick_device(Semi &s, T *d_dv, const T *d_v, const CT *d_u)
     {
         if (s.n_f == 0) return TPB_OK;
+        prof_mark(s, TPB_PHASE_REBUILD);
         int rc = rebuild_fluid(s, d_u, d_v);
         if (rc) return rc;
         GridConst<CT> g = make_grid_const<CT>(s);
@@ -322,19 +381,24 @@ struct Ops {
         EosConst<T> eos = make_eos_const<T>(s.fp.sound_speed, s.fp.exponent, s.fp.reference_density,
                                             s.fp.background_pressure, s.fp.clip_negative_pressure);
         const bool summ = s.fp.density_calculator == TPB_DENSITY_SUMMATION;
+        prof_mark(s, TPB_PHASE_DENSITY);
         if (summ) {
             if (s.fp.kernel == 0) launch_summation<0>(s, g, pc, eos);
             else launch_summation<1>(s, g, pc, eos);
         }
+        prof_mark(s, TPB_PHASE_BOUNDARY);
         if (s.n_w > 0) {
-            if (s.wp.kernel == 0) launch_adami<0>(s, g);
-            else launch_adami<1>(s, g);
+            rc = s.wp.kernel == 0 ? launch_adami<0>(s, g) : launch_adami<1>(s, g);
+            if (rc) return rc;
         }
+        prof_mark(s, TPB_PHASE_INTERACT);
         if (s.fp.kernel == 0)
             rc = summ ? launch_interact<0, 1>(s, g, pc, d_dv) : launch_interact<0, 0>(s, g, pc, d_dv);
         else
             rc = summ ? launch_interact<1, 1>(s, g, pc, d_dv) : launch_interact<1, 0>(s, g, pc, d_dv);
         if (rc) return rc;
+        prof_mark(s, TPB_PHASE_END);
+        if (s.prof_capacity > 0 && s.prof_kicks < s.prof_capacity) s.prof_kicks++;
         CUDA_TRY(&s, cudaGetLastError());
         return TPB_OK;
     }
@@ -506,6 +570,8 @@ void free_device(Semi &s)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     tiles_free(s.tiles);
+    for (cudaEvent_t e : s.prof_events) cudaEventDestroy(e);
+    s.prof_events.clear();
     if (s.h_flags) cudaFreeHost(s.h_flags);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
 }
@@ -747,7 +813,7 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     CUDA_TRY(s, cudaMemset(s->d_P, 0, ts * (nf + 8)));
     CUDA_TRY(s, cudaMemset(s->d_Aw, 0, 4 * cs * (nw + 8)));
     CUDA_TRY(s, cudaMemset(s->d_Ww, 0, 2 * ts * (nw + 8)));
-    int rc = tiles_alloc(s->tiles, s->ncells, s->n_f);
+    int rc = tiles_alloc(s->tiles, s->ncell[1] * s->ncell[2], s->n_f, s->n_w);
     if (rc) return fail(s, TPB_ERR_CUDA, "tile scheduler allocation failed");
 
     s->stats.n_cells = s->ncells;
@@ -859,6 +925,40 @@ int32_t tpb_get_stats(tpb_semi_t semi, tpb_stats *out)
     Semi *s = (Semi *)semi;
     if (!s || !out) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
     *out = s->stats;
+    return TPB_OK;
+}
+
+int32_t tpb_set_profiling(tpb_semi_t semi, int32_t max_kicks)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || max_kicks < 0) return fail(s, TPB_ERR_INVALID_ARGUMENT, "invalid argument");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
+    s->prof_events.assign((size_t)max_kicks * TPB_N_PHASES, nullptr);
+    for (auto &e : s->prof_events) CUDA_TRY(s, cudaEventCreate(&e));
+    s->prof_capacity = max_kicks;
+    s->prof_kicks = 0;
+    return TPB_OK;
+}
+
+int32_t tpb_get_phase_times(tpb_semi_t semi, double *ms_mean, int32_t *n_kicks)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !ms_mean) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    for (int ph = 0; ph < TPB_N_PHASES - 1; ++ph) ms_mean[ph] = 0.0;
+    for (int k = 0; k < s->prof_kicks; ++k)
+        for (int ph = 0; ph < TPB_N_PHASES - 1; ++ph) {
+            float ms = 0.f;
+            CUDA_TRY(s, cudaEventElapsedTime(&ms, s->prof_events[(size_t)k * TPB_N_PHASES + ph],
+                                             s->prof_events[(size_t)k * TPB_N_PHASES + ph + 1]));
+            ms_mean[ph] += ms;
+        }
+    if (s->prof_kicks > 0)
+        for (int ph = 0; ph < TPB_N_PHASES - 1; ++ph) ms_mean[ph] /= s->prof_kicks;
+    if (n_kicks) *n_kicks = s->prof_kicks;
+    s->prof_kicks = 0;
     return TPB_OK;
 }
 

@@ -1,31 +1,506 @@
-// tpb_tiles.cuh -- neighbour sweeps, variant 2 ("cell tiles"): placeholder until the tiled
-// kernel lands; reports itself unsupported so the per-particle sweep is used.
+// tpb_tiles.cuh -- neighbour sweeps, variant 2 ("cell tiles"): the production path.
+//
+// B200 counterpart of PointNeighbors `foreach_point_neighbor` + the loop bodies of
+//   interact!                 /root/reference/src/schemes/fluid/weakly_compressible_sph/rhs.jl:5-127
+//   boundary_pressure_extrapolation! + compute_adami_density!
+//                             /root/reference/src/schemes/boundary/wall_boundary/dummy_particles.jl:489-672
+//
+// Work decomposition.  Sorted particles of one cell row (fixed cy, cz; x fastest) are a
+// contiguous range; it is cut into balanced "tiles" of <= TILE_TB target particles, one
+// thread block each, one thread per target.  The 3^(ND-1) neighbour rows of a tile are 3 / 9
+// contiguous runs of sorted records: one elected thread stages them into shared memory with
+// 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) -- UBLKCP in SASS.
+//
+// Per thread, two alternating phases remove the SIMT divergence of the naive loop
+// (only 17 % of the 729 candidates of a 3-D particle are neighbours):
+//   phase 1  scan the candidates of the own 3^ND cells (every lane of a warp reads the same
+//            record: shared-memory broadcast), apply a cheap conservative distance filter and
+//            append accepted tile indices to a private 16-bit list in shared memory;
+//   phase 2  walk the list densely (all lanes busy): exact reference predicate
+//            d^2 <= R^2 (bit-exact arithmetic, tpb_device.cuh) and the pair physics.
+// Accumulators live in registers; each particle's dv is written once; no atomics.
 #pragma once
 #include "tpb_device.cuh"
 #include "tpb_sweeps.cuh"
 
 namespace tpb {
 
-struct TileState {
-    int dummy = 0;
-};
+constexpr int TILE_TB = 128;      // threads (= max target particles) per tile
+constexpr int TILE_MAXSEG = 12;   // segments per staged chunk (>= 3^(ND-1))
 
-inline int tiles_alloc(TileState &, int64_t, int64_t) { return 0; }
-inline void tiles_free(TileState &) {}
-
-template <int ND, typename T, typename CT>
-constexpr bool tiles_supported()
+// ------------------------------------------------------------------ PTX helpers (sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
-    return false;
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`.
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TPB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TPB_DONE_%=;\n"
+        "bra TPB_WAIT_%=;\n"
+        "TPB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <int ND, typename T, typename CT, int KERNEL, int DENS>
-int launch_interact_tiles(TileState &, cudaStream_t, int, const GridConst<CT> &, const int *,
-                          const V4<CT> *, const V4<T> *, const T *, const int *, int, int,
-                          const int *, const V4<CT> *, const V2<T> *, const PairConst<T> &,
-                          const SourceConst<T> &, T *, int &, int64_t &)
+// ------------------------------------------------------------------ tile table
+// row_tiles[r] = number of tiles of cell row r (r = cy + n1 * cz)
+__global__ void __launch_bounds__(256)
+k_row_tiles(const int *__restrict__ cell_start, int n0, int nrows, int *__restrict__ row_tiles)
 {
-    return 2;  // TPB_ERR_UNSUPPORTED
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    int cnt = cell_start[(int64_t)(r + 1) * n0] - cell_start[(int64_t)r * n0];
+    row_tiles[r] = (cnt + TILE_TB - 1) / TILE_TB;
+}
+
+struct TileHdr {
+    int p0, p1, cy, cz, cxmin, cxmax;
+    int g0[9], g1[9];  // candidate range of every neighbour row (current neighbour set)
+    int q, gpos;       // staging cursor: next row, next record in it
+    int nseg, pad;
+    int seg_row[TILE_MAXSEG], seg_begin[TILE_MAXSEG], seg_end[TILE_MAXSEG], seg_base[TILE_MAXSEG];
+};
+constexpr int TILE_HDR_BYTES = 16 + ((sizeof(TileHdr) + 15) / 16) * 16;  // mbarrier + header
+
+// shared-memory carve-up of one block
+template <typename T, typename CT>
+struct TileSmem {
+    uint64_t *bar;
+    TileHdr *hdr;
+    unsigned short *list;  // [list_len][TILE_TB]
+    V4<CT> *tA;            // [cap]
+    unsigned char *tB;     // [cap] of V4<T> (fluid neighbours) or V2<T> (wall neighbours)
+    T *tP;                 // [cap]
+    int cap, list_len;
+    __device__ TileSmem(unsigned char *base, int cap_, int list_len_) : cap(cap_), list_len(list_len_)
+    {
+        bar = (uint64_t *)base;
+        hdr = (TileHdr *)(base + 16);
+        list = (unsigned short *)(base + TILE_HDR_BYTES);
+        unsigned char *p = base + TILE_HDR_BYTES + (size_t)list_len * TILE_TB * sizeof(unsigned short);
+        tA = (V4<CT> *)p;
+        p += (size_t)cap * sizeof(V4<CT>);
+        tB = p;
+        p += (size_t)cap * sizeof(V4<T>);
+        tP = (T *)p;
+    }
+};
+template <typename T, typename CT>
+inline size_t tile_smem_bytes(int cap, int list_len)
+{
+    return TILE_HDR_BYTES + (size_t)list_len * TILE_TB * sizeof(unsigned short) +
+           (size_t)cap * (sizeof(V4<CT>) + sizeof(V4<T>) + sizeof(T));
+}
+
+// Locate the tile of this block: binary search of the row, balanced split of the row's
+// particles.  Executed by thread 0; results in hdr.  Returns false if the block has no tile.
+template <int ND, typename CT>
+__device__ __forceinline__ void tile_locate(TileHdr *hdr, const GridConst<CT> &g,
+                                            const int *__restrict__ row_tile_start, int nrows,
+                                            const int *__restrict__ cell_start,
+                                            const V4<CT> *__restrict__ X, int tile)
+{
+    int lo = 0, hi = nrows;  // row_tile_start[lo] <= tile < row_tile_start[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (row_tile_start[mid] <= tile) lo = mid; else hi = mid;
+    }
+    const int r = lo;
+    const int first = row_tile_start[r], nt = row_tile_start[r + 1] - first, k = tile - first;
+    const int rs = cell_start[(int64_t)r * g.n[0]], re = cell_start[(int64_t)(r + 1) * g.n[0]];
+    const long long cnt = re - rs;
+    hdr->p0 = rs + (int)(cnt * k / nt);
+    hdr->p1 = rs + (int)(cnt * (k + 1) / nt);
+    hdr->cy = r % g.n[1];
+    hdr->cz = r / g.n[1];
+    int cx, cy, cz;
+    const V4<CT> xa = X[hdr->p0], xb = X[hdr->p1 - 1];
+    cell_coords<ND, CT>(g, xa.x, xa.y, xa.z, cx, cy, cz);
+    hdr->cxmin = cx;
+    cell_coords<ND, CT>(g, xb.x, xb.y, xb.z, cx, cy, cz);
+    hdr->cxmax = cx;
+}
+
+// Conservative phase-1 filter.  Float coordinates: fused arithmetic with a small margin on the
+// radius (never rejects a pair the exact predicate accepts); otherwise the exact predicate.
+template <int ND, typename T, typename CT>
+struct Filter {
+    T r2;
+    __device__ __forceinline__ Filter(T radius2) : r2(radius2) {}
+    __device__ __forceinline__ bool operator()(const V4<CT> &xi, const V4<CT> &xj) const
+    {
+        T pd[3];
+        return pos_diff_d2<ND, T, CT>(xi, xj, pd) <= r2;
+    }
+};
+template <int ND>
+struct Filter<ND, float, float> {
+    float r2;
+    __device__ __forceinline__ Filter(float radius2) : r2(radius2 * (1.0f + 8.0f * 1.1920929e-07f)) {}
+    __device__ __forceinline__ bool operator()(const V4<float> &xi, const V4<float> &xj) const
+    {
+        float dx = xi.x - xj.x, dy = xi.y - xj.y;
+        float d2 = fmaf(dy, dy, dx * dx);
+        if (ND == 3) {
+            float dz = xi.z - xj.z;
+            d2 = fmaf(dz, dz, d2);
+        }
+        return d2 <= r2;
+    }
+};
+
+// One neighbour set as the sweep sees it.  R1 = second record type (V4<T> fluid: v, rho;
+// V2<T> wall: p, rho); HAS_P: a third scalar array (fluid pressure).
+template <typename T, typename CT, typename R1_, bool HAS_P_>
+struct NbSet {
+    using R1 = R1_;
+    static constexpr bool HAS_P = HAS_P_;
+    const int *__restrict__ cell_start;
+    const V4<CT> *__restrict__ A;
+    const R1 *__restrict__ B;
+    const T *__restrict__ P;
+};
+
+// Sweep all neighbours (of one set) of the tile's targets.  `body(xj, bj, pj)` is called for
+// every candidate that passed the filter; it applies the exact predicate itself.
+// Must be called by all threads of the block.
+template <int ND, typename T, typename CT, typename NB, typename BODY>
+__device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<CT> &g, const NB &nb,
+                                           bool valid, int cx, const V4<CT> &xi, T radius2,
+                                           uint32_t &parity, BODY &&body)
+{
+    using R1 = typename NB::R1;
+    constexpr int NROWS = ND == 3 ? 9 : 3;
+    const int tid = threadIdx.x;
+    TileHdr *hdr = sm.hdr;
+    R1 *tB = (R1 *)sm.tB;
+    const Filter<ND, T, CT> filter(radius2);
+
+    __syncthreads();  // the previous sweep is done with hdr and the staged tile
+    if (tid < NROWS) {
+        const int dy = tid % 3 - 1, dz = ND == 3 ? tid / 3 - 1 : 0;
+        const int c_lo = cell_linear(g, hdr->cxmin - 1, hdr->cy + dy, hdr->cz + dz);
+        hdr->g0[tid] = nb.cell_start[c_lo];
+        hdr->g1[tid] = nb.cell_start[c_lo + (hdr->cxmax - hdr->cxmin) + 3];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        hdr->q = 0;
+        hdr->gpos = hdr->g0[0];
+    }
+
+    int cnt = 0;  // entries in this thread's list
+    unsigned short *const my_list = sm.list + tid;
+    auto flush = [&]() {
+        for (int e = 0; e < cnt; ++e) {
+            const int idx = my_list[e * TILE_TB];
+            if constexpr (NB::HAS_P)
+                body(sm.tA[idx], tB[idx], sm.tP[idx]);
+            else
+                body(sm.tA[idx], tB[idx], (T)0);
+        }
+        cnt = 0;
+    };
+
+    while (true) {
+        // ---- thread 0: next chunk of whole rows (or one piece of an oversized row)
+        if (tid == 0) {
+            int q = hdr->q, gpos = hdr->gpos, used = 0, nseg = 0;
+            uint32_t bytes = 0;
+            while (q < NROWS && nseg < TILE_MAXSEG) {
+                const int gend_row = hdr->g1[q];
+                if (gpos >= gend_row) {
+                    ++q;
+                    if (q < NROWS) gpos = hdr->g0[q];
+                    continue;
+                }
+                const int a = gpos & ~3;  // 4 records: every array stays 16-byte aligned
+                const int need = ((gend_row + 3) & ~3) - a;
+                int gend;
+                if (need <= sm.cap - used) {
+                    gend = gend_row;
+                } else if (nseg == 0) {
+                    gend = a + sm.cap;  // piece of an oversized row (cap is a multiple of 4)
+                } else {
+                    break;
+                }
+                const int len = ((gend + 3) & ~3) - a;
+                hdr->seg_row[nseg] = q;
+                hdr->seg_begin[nseg] = gpos;
+                hdr->seg_end[nseg] = gend;
+                hdr->seg_base[nseg] = used - a;  // tile index of record j = seg_base + j
+                if (nseg == 0) fence_proxy_async();
+                bulk_g2s(sm.tA + used, nb.A + a, (uint32_t)(len * sizeof(V4<CT>)), sm.bar);
+                bulk_g2s(tB + used, nb.B + a, (uint32_t)(len * sizeof(R1)), sm.bar);
+                bytes += (uint32_t)(len * (sizeof(V4<CT>) + sizeof(R1)));
+                if constexpr (NB::HAS_P) {
+                    bulk_g2s(sm.tP + used, nb.P + a, (uint32_t)(len * sizeof(T)), sm.bar);
+                    bytes += (uint32_t)(len * sizeof(T));
+                }
+                used += len;
+                ++nseg;
+                gpos = gend;
+                if (gend < gend_row) break;  // oversized row: continue with it next chunk
+            }
+            hdr->q = q;
+            hdr->gpos = gpos;
+            hdr->nseg = nseg;
+            if (nseg > 0) mbar_expect_tx(sm.bar, bytes);
+        }
+        __syncthreads();
+        const int nseg = hdr->nseg;
+        if (nseg == 0) break;
+        mbar_wait(sm.bar, parity);
+        parity ^= 1u;
+
+        for (int si = 0; si < nseg; ++si) {
+            const int q = hdr->seg_row[si];
+            const int dy = q % 3 - 1, dz = ND == 3 ? q / 3 - 1 : 0;
+            int j = 0, j1 = 0;
+            if (valid) {
+                const int c0 = cell_linear(g, cx - 1, hdr->cy + dy, hdr->cz + dz);
+                j = max(nb.cell_start[c0], hdr->seg_begin[si]);
+                j1 = min(nb.cell_start[c0 + 3], hdr->seg_end[si]);
+            }
+            const V4<CT> *const tAj = sm.tA + hdr->seg_base[si];  // indexed by global record j
+            const int base = hdr->seg_base[si];
+            while (true) {
+                // phase 1: filter candidates into the private list
+                while (j + 4 <= j1 && cnt + 4 <= sm.list_len) {
+                    const V4<CT> x0 = tAj[j], x1 = tAj[j + 1], x2 = tAj[j + 2], x3 = tAj[j + 3];
+                    if (filter(xi, x0)) my_list[cnt++ * TILE_TB] = (unsigned short)(base + j);
+                    if (filter(xi, x1)) my_list[cnt++ * TILE_TB] = (unsigned short)(base + j + 1);
+                    if (filter(xi, x2)) my_list[cnt++ * TILE_TB] = (unsigned short)(base + j + 2);
+                    if (filter(xi, x3)) my_list[cnt++ * TILE_TB] = (unsigned short)(base + j + 3);
+                    j += 4;
+                }
+                while (j < j1 && cnt < sm.list_len) {
+                    if (filter(xi, tAj[j])) my_list[cnt++ * TILE_TB] = (unsigned short)(base + j);
+                    ++j;
+                }
+                if (!__any_sync(0xffffffffu, j < j1)) break;
+                flush();  // phase 2 (some list of the warp is full)
+            }
+        }
+        flush();  // list entries point into this chunk: drain before it is replaced
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ interact! (variant 2)
+template <int ND, typename T, typename CT, int KERNEL, int DENS>
+__global__ void __launch_bounds__(TILE_TB, 2)
+k_interact_tiles(GridConst<CT> g, const int *__restrict__ row_tile_start, int nrows,
+                 const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
+                 const V4<T> *__restrict__ B, const T *__restrict__ P,
+                 const int *__restrict__ perm, int ff_enabled, int has_wall,
+                 const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
+                 const V2<T> *__restrict__ Ww, PairConst<T> k, SourceConst<T> src,
+                 T *__restrict__ dv, int cap, int list_len)
+{
+    constexpr int NV = DENS == 0 ? ND + 1 : ND;
+    extern __shared__ __align__(16) unsigned char tile_smem_raw[];
+    const int tile = blockIdx.x;
+    if (tile >= row_tile_start[nrows]) return;
+    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len);
+    if (threadIdx.x == 0) {
+        tile_locate<ND, CT>(sm.hdr, g, row_tile_start, nrows, fcell_start, A, tile);
+        mbar_init(sm.bar, 1);
+    }
+    __syncthreads();
+    const int s = sm.hdr->p0 + threadIdx.x;
+    const bool valid = s < sm.hdr->p1;
+    V4<CT> xi = {};
+    V4<T> bi = {};
+    T p_a = 0;
+    int cx = sm.hdr->cxmin, cy, cz;
+    if (valid) {
+        xi = A[s];
+        bi = B[s];
+        p_a = P[s];
+        cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    }
+    const T rho_a = bi.w;
+    const T v_a[3] = {bi.x, bi.y, bi.z};
+    uint32_t parity = 0;
+
+    T dv_ff[3] = {0, 0, 0}, drho_ff = 0;
+    if (ff_enabled) {
+        NbSet<T, CT, V4<T>, true> nb{fcell_start, A, B, P};
+        tile_sweep<ND, T, CT>(sm, g, nb, valid, cx, xi, k.radius2, parity,
+                              [&](const V4<CT> &xj, const V4<T> &bj, T pj) {
+                                  T pd[3];
+                                  const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                                  if (d2 <= k.radius2) {
+                                      const T dist = sqrt_rn(d2);
+                                      if (dist >= k.almostzero) {
+                                          const T v_b[3] = {bj.x, bj.y, bj.z};
+                                          interact_pair<ND, T, KERNEL, DENS, true>(
+                                              k, (T)xj.w, rho_a, bj.w, p_a, pj, v_a, v_b, pd, dist, dv_ff,
+                                              drho_ff);
+                                      }
+                                  }
+                              });
+    }
+    T dv_fw[3] = {0, 0, 0}, drho_fw = 0;
+    if (has_wall) {
+        const T zero3[3] = {0, 0, 0};
+        NbSet<T, CT, V2<T>, false> nb{wcell_start, Aw, Ww, nullptr};
+        tile_sweep<ND, T, CT>(sm, g, nb, valid, cx, xi, k.radius2, parity,
+                              [&](const V4<CT> &xj, const V2<T> &wj, T) {
+                                  T pd[3];
+                                  const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                                  if (d2 <= k.radius2) {
+                                      const T dist = sqrt_rn(d2);
+                                      if (dist >= k.almostzero)
+                                          interact_pair<ND, T, KERNEL, DENS, false>(
+                                              k, (T)xj.w, rho_a, wj.y, p_a, wj.x, v_a, zero3, pd, dist,
+                                              dv_fw, drho_fw);
+                                  }
+                              });
+    }
+    if (!valid) return;
+    // dv = ((0 + S_ff) + S_fw) + g [+ source]  (semidiscretization.jl:600, :809-829, :668-731)
+    const int64_t o = (int64_t)perm[s] * NV;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        T val = dv_ff[d] + dv_fw[d];
+        if (src.any) {
+            val += src.acc[d];
+            if (src.damping != (T)0) val += -src.damping * v_a[d];
+        }
+        dv[o + d] = val;
+    }
+    if (DENS == 0) dv[o + ND] = drho_ff + drho_fw;
+}
+
+// ------------------------------------------------------------------ Adami (variant 2)
+// Targets: wall particles (tiles over the wall's sorted order); neighbours: fluid.
+template <int ND, typename T, typename CT, int KERNEL>
+__global__ void __launch_bounds__(TILE_TB, 2)
+k_adami_tiles(GridConst<CT> g, const int *__restrict__ row_tile_start, int nrows,
+              const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
+              const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
+              const V4<T> *__restrict__ B, const T *__restrict__ P, int interaction_enabled,
+              AdamiConst<T> k, V2<T> *__restrict__ W, T *__restrict__ volume, int cap, int list_len)
+{
+    extern __shared__ __align__(16) unsigned char tile_smem_raw[];
+    const int tile = blockIdx.x;
+    if (tile >= row_tile_start[nrows]) return;
+    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len);
+    if (threadIdx.x == 0) {
+        tile_locate<ND, CT>(sm.hdr, g, row_tile_start, nrows, wcell_start, Aw, tile);
+        mbar_init(sm.bar, 1);
+    }
+    __syncthreads();
+    const int w = sm.hdr->p0 + threadIdx.x;
+    const bool valid = w < sm.hdr->p1;
+    V4<CT> xi = {};
+    int cx = sm.hdr->cxmin, cy, cz;
+    if (valid) {
+        xi = Aw[w];
+        cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    }
+    uint32_t parity = 0;
+    T p = (T)0, vol = (T)0;
+    if (interaction_enabled) {
+        NbSet<T, CT, V4<T>, true> nb{fcell_start, A, B, P};
+        tile_sweep<ND, T, CT>(sm, g, nb, valid, cx, xi, k.radius2, parity,
+                              [&](const V4<CT> &xj, const V4<T> &bj, T pj) {
+                                  T pd[3];
+                                  const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                                  if (d2 <= k.radius2) {
+                                      const T dist = sqrt_rn(d2);
+                                      const T rho_f = bj.w;
+                                      T hyd = k.acc[0] * (rho_f * pd[0]) + k.acc[1] * (rho_f * pd[1]);
+                                      if (ND == 3) hyd += k.acc[2] * (rho_f * pd[2]);
+                                      const T sum_p = k.p_off + pj + hyd;
+                                      const T kw = kernel_safe<KERNEL, T>(k.kern, dist);
+                                      p += sum_p * kw;
+                                      vol += kw;
+                                  }
+                              });
+    }
+    if (!valid) return;
+    if ((double)vol > 2.220446049250313e-16) p = p / vol;  // `volume > eps()`: eps(Float64)
+    if (k.clip) p = p > (T)0 ? p : (T)0;
+    V2<T> out;
+    out.x = p;
+    out.y = eos_inverse(k.eos, p);
+    W[w] = out;
+    volume[w] = vol;
+}
+
+// ------------------------------------------------------------------ host side
+struct TileState {
+    int *d_row_tiles = nullptr;        // [nrows]
+    int *d_frow_tile_start = nullptr;  // [nrows + 1] fluid tiles (rebuilt every kick)
+    int *d_wrow_tile_start = nullptr;  // [nrows + 1] wall tiles (static)
+    int nrows = 0;
+    int max_ftiles = 0, max_wtiles = 0;
+    int smem_budget = 100 * 1024;  // bytes per block: two blocks per SM
+    int list_len = 96;
+};
+
+inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
+{
+    t.nrows = nrows;
+    t.max_ftiles = (int)((n_f + TILE_TB - 1) / TILE_TB) + nrows;
+    t.max_wtiles = (int)((n_w + TILE_TB - 1) / TILE_TB) + nrows;
+    if (cudaMalloc(&t.d_row_tiles, sizeof(int) * (size_t)(nrows + 4)) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_frow_tile_start, sizeof(int) * (size_t)(nrows + 4)) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_wrow_tile_start, sizeof(int) * (size_t)(nrows + 4)) != cudaSuccess) return 1;
+    cudaMemset(t.d_frow_tile_start, 0, sizeof(int) * (size_t)(nrows + 4));
+    cudaMemset(t.d_wrow_tile_start, 0, sizeof(int) * (size_t)(nrows + 4));
+    return 0;
+}
+inline void tiles_free(TileState &t)
+{
+    if (t.d_row_tiles) cudaFree(t.d_row_tiles);
+    if (t.d_frow_tile_start) cudaFree(t.d_frow_tile_start);
+    if (t.d_wrow_tile_start) cudaFree(t.d_wrow_tile_start);
+    t = TileState();
+}
+
+// records per staged chunk for a shared-memory budget (multiple of 4, 16-bit indexable)
+template <typename T, typename CT>
+inline int tile_capacity(int smem_budget, int list_len)
+{
+    const size_t fixed = TILE_HDR_BYTES + (size_t)list_len * TILE_TB * sizeof(unsigned short);
+    const size_t rec = sizeof(V4<CT>) + sizeof(V4<T>) + sizeof(T);
+    int cap = (int)(((size_t)smem_budget - fixed) / rec);
+    cap &= ~3;
+    return cap > 65532 ? 65532 : cap;
 }
 
 }  // namespace tpb

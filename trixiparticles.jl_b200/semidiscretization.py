@@ -248,7 +248,9 @@ class Semidiscretization:
         if self.parallelization_backend.ode_memory == "device":
             import torch
             stream = torch.cuda.current_stream(self.parallelization_backend.device).cuda_stream
-            _lib.load().tpb_set_stream(self._handle, C.c_void_p(stream))
+            # torch's default stream has the handle 0, which tpb_set_stream reads as "use the
+            # handle's own stream": pass cudaStreamLegacy (0x1) for it instead
+            _lib.load().tpb_set_stream(self._handle, C.c_void_p(stream if stream else 1))
 
     def synchronize(self):
         _lib.check(self._handle, _lib.load().tpb_synchronize(self._handle))
@@ -257,6 +259,19 @@ class Semidiscretization:
         st = _lib.Stats()
         _lib.check(self._handle, _lib.load().tpb_get_stats(self._handle, C.byref(st)))
         return st
+
+    def set_profiling(self, max_kicks: int):
+        """Arm CUDA-event phase timing for the next `max_kicks` kicks (0 disables)."""
+        _lib.check(self._handle, _lib.load().tpb_set_profiling(self._handle, int(max_kicks)))
+
+    def phase_times(self) -> dict:
+        """Mean duration in ms of each kick phase since profiling was armed (synchronises)."""
+        ms = (C.c_double * len(_lib.PHASES))()
+        n = C.c_int32(0)
+        _lib.check(self._handle, _lib.load().tpb_get_phase_times(self._handle, ms, C.byref(n)))
+        out = {name: ms[i] for i, name in enumerate(_lib.PHASES)}
+        out["n_kicks"] = n.value
+        return out
 
     def system_field(self, system, field: str) -> np.ndarray:
         """`system.pressure`, `cache.density`, `boundary_model.pressure/cache.density/cache.volume`
@@ -267,6 +282,18 @@ class Semidiscretization:
         _lib.check(self._handle, _lib.load().tpb_get_system_field(
             self._handle, self.system_index(system), fid, out.ctypes.data, out.size))
         return out
+
+    def count_neighbor_pairs(self, system, neighbor, u_ode) -> int:
+        """Number of ordered neighbour pairs of (system, neighbor) for coordinates `u_ode`."""
+        L = _lib.load()
+        ptr = self._ptr(u_ode, self.ranges_u[-1][1], self.coordinates_eltype, "u_ode")
+        self._bind_stream()
+        cnt = C.c_int64(0)
+        rc = L.tpb_neighbor_pairs(self._handle, self.system_index(system),
+                                  self.system_index(neighbor), ptr, 0, None, None, C.byref(cnt))
+        if rc not in (0, 6):  # TPB_ERR_CAPACITY is expected: only the count is wanted
+            _lib.check(self._handle, rc)
+        return int(cnt.value)
 
     def neighbor_pairs(self, system, neighbor, u_ode):
         """Sorted (i, j) neighbour pairs of the ordered system pair (test hook)."""
