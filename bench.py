@@ -270,6 +270,13 @@ def run_single(args):
     value = n_f * args.steps / (total_ms * 1e-3)
     launches = int(st1.kernel_launches_total - st0.kernel_launches_total)
 
+    if args.quick:
+        print(json.dumps({"quick": True, "workload": args.workload, "ms_per_step": total_ms / args.steps,
+                          "value": value, "phases_ms": phases, "kick_ms": float(ms_kick.mean()),
+                          "variant": int(st1.interact_variant_used),
+                          "env": {k: v for k, v in os.environ.items() if k.startswith("TPB_")}}))
+        return
+
     # L2-warm variant (no flush), reported for information
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -390,6 +397,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--variant", type=int, default=0, help="interact kernel variant (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

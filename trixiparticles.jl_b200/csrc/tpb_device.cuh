@@ -217,6 +217,111 @@ __device__ __forceinline__ void interact_pair(const PairConst<T> &k, T m_b, T rh
 }
 
 // ---------------------------------------------------------------------------------------
+// Float32 fast path of the same pair physics for the cell-tile sweep (tpb_tiles.cuh).
+// Same formulas as `interact_pair`, regrouped so that one pair costs ~60 issue slots:
+//   * the hardware approximations rcp.approx.ftz / rsqrt.approx.ftz (<= 2 ulp) stand in for
+//     `div_fast` and sqrt -- the reference's own GPU path divides with LLVM fast division
+//     (util.jl:3-5), and its Float32 accuracy bar is 1e-5;
+//   * grad W = wdr * pos_diff is never formed: dv += [m_b (f + visc) wdr] * pos_diff,
+//     v_ab . grad W = wdr (v_ab . pos_diff), and the Molteni-Colagrossi term collapses to
+//     psi . grad W = 2 (rho_a - rho_b) wdr because pos_diff . pos_diff / r^2 = 1;
+//   * the `vr < 0` viscosity switch is min(vr, 0); a rejected pair gets m_b = 0.
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct FastConst {
+    float r2, az2;         // search radius^2, almostzero^2
+    float h_inv, nfh;      // 1/h; cubic spline: nf * h_inv
+    float c_t, c_w;        // Wendland C2: t = 1 + c_t r, wdr = c_w t^3
+    float h, eps_h2;       // viscosity
+    float ac2, b2;         // 2 alpha c, 2 beta
+    float dhc2;            // 2 delta h c (0 without density diffusion)
+};
+
+__host__ __device__ inline FastConst make_fast_const(const PairConst<float> &k)
+{
+    FastConst f;
+    f.r2 = k.radius2;
+    f.az2 = k.almostzero * k.almostzero;
+    f.h_inv = k.kern.h_inv;
+    f.nfh = k.kern.nf * k.kern.h_inv;
+    f.c_t = -0.5f * k.kern.h_inv;
+    f.c_w = k.kern.m5nf * k.kern.h_inv2;
+    f.h = k.kern.h;
+    f.eps_h2 = k.eps_h2;
+    f.ac2 = k.has_viscosity ? 2.0f * k.alpha * k.c : 0.0f;
+    f.b2 = k.has_viscosity ? 2.0f * k.beta : 0.0f;
+    f.dhc2 = k.has_diffusion ? 2.0f * k.delta_h_c : 0.0f;
+    return f;
+}
+
+// (dW/dr)/r from d2 (already clamped to a finite non-zero value); rs = 1/r
+template <int KERNEL>
+__device__ __forceinline__ float fast_wdr(const FastConst &c, float dist, float rs)
+{
+    if (KERNEL == 0) {
+        const float t = fmaf(dist, c.c_t, 1.0f);
+        return c.c_w * (t * t * t);
+    } else {
+        const float q = dist * c.h_inv;
+        const float a = 2.0f - q, b = 1.0f - q;
+        const float inner = q < 1.0f ? 3.0f * (b * b) : 0.0f;
+        return c.nfh * fmaf(-0.75f * a, a, inner) * rs;
+    }
+}
+
+// Exact reference predicate + fast physics.  pa_term: DENS == 1 ? p_a / rho_a^2 : unused.
+template <int ND, int KERNEL, int DENS, bool SAME>
+__device__ __forceinline__ void interact_pair_fast(const FastConst &c, const V4<float> &xi,
+                                                   const V4<float> &xj, float rho_a, float p_a,
+                                                   float pa_term, const float (&v_a)[3], float vbx,
+                                                   float vby, float vbz, float rho_b, float p_b,
+                                                   float (&dv)[3], float &drho)
+{
+    float pd[3];
+    float d2 = pos_diff_d2<ND, float, float>(xi, xj, pd);  // exactly rounded, as the reference
+    const bool ok = d2 <= c.r2 && d2 >= c.az2;
+    d2 = ok ? d2 : c.r2;
+    const float mb = ok ? xj.w : 0.0f;
+    const float rs = rsqrt_approx(d2);
+    const float dist = d2 * rs;
+    const float mw = mb * fast_wdr<KERNEL>(c, dist, rs);
+    const float rb = rcp_approx(rho_b);
+    float f;
+    if (DENS == 0)
+        f = -(p_a + p_b) * (rb * rcp_approx(rho_a));
+    else
+        f = -(pa_term + p_b * (rb * rb));
+    const float vdx = SAME ? v_a[0] - vbx : v_a[0], vdy = SAME ? v_a[1] - vby : v_a[1];
+    const float vdz = ND == 3 ? (SAME ? v_a[2] - vbz : v_a[2]) : 0.0f;
+    float vr = fmaf(vdy, pd[1], vdx * pd[0]);
+    if (ND == 3) vr = fmaf(vdz, pd[2], vr);
+    if (SAME && (c.ac2 != 0.0f || c.b2 != 0.0f)) {
+        const float mu = (c.h * fminf(vr, 0.0f)) * rcp_approx(d2 + c.eps_h2);
+        f = fmaf(fmaf(c.b2, mu, c.ac2) * mu, rcp_approx(rho_a + rho_b), f);
+    }
+    const float s = mw * f;
+    dv[0] = fmaf(s, pd[0], dv[0]);
+    dv[1] = fmaf(s, pd[1], dv[1]);
+    if (ND == 3) dv[2] = fmaf(s, pd[2], dv[2]);
+    if (DENS == 0) {
+        float t1 = rho_a * vr;
+        if (SAME) t1 = fmaf(c.dhc2, rho_a - rho_b, t1);
+        drho = fmaf(mw * rb, t1, drho);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Uniform cell grid shared by every point set (FullGridCellList semantics: padded bounding
 // box, particles may only live in cells 1..n-2 of each dimension, so the 3^ND neighbourhood
 // never leaves the grid).  Cell index is linear with x fastest: the three cells

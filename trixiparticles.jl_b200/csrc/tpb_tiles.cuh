@@ -20,6 +20,9 @@
 //            d^2 <= R^2 (bit-exact arithmetic, tpb_device.cuh) and the pair physics.
 // Accumulators live in registers; each particle's dv is written once; no atomics.
 #pragma once
+#include <cstdlib>
+#include <type_traits>
+
 #include "tpb_device.cuh"
 #include "tpb_sweeps.cuh"
 
@@ -219,17 +222,25 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
         hdr->gpos = hdr->g0[0];
     }
 
-    int cnt = 0;  // entries in this thread's list
+    // private list: entry e of thread t lives at list[e * TILE_TB + t] (conflict-free)
     unsigned short *const my_list = sm.list + tid;
+    unsigned short *const my_end = my_list + (size_t)sm.list_len * TILE_TB;
+    unsigned short *lp = my_list;  // append position
+    auto visit = [&](int idx) {
+        if constexpr (NB::HAS_P)
+            body(sm.tA[idx], tB[idx], sm.tP[idx]);
+        else
+            body(sm.tA[idx], tB[idx], (T)0);
+    };
     auto flush = [&]() {
-        for (int e = 0; e < cnt; ++e) {
-            const int idx = my_list[e * TILE_TB];
-            if constexpr (NB::HAS_P)
-                body(sm.tA[idx], tB[idx], sm.tP[idx]);
-            else
-                body(sm.tA[idx], tB[idx], (T)0);
+        const unsigned short *e = my_list;
+        for (; e + 2 * TILE_TB <= lp; e += 2 * TILE_TB) {  // two pairs in flight for ILP
+            const int i0 = e[0], i1 = e[TILE_TB];
+            visit(i0);
+            visit(i1);
         }
-        cnt = 0;
+        if (e < lp) visit(e[0]);
+        lp = my_list;
     };
 
     while (true) {
@@ -296,16 +307,17 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
             const int base = hdr->seg_base[si];
             while (true) {
                 // phase 1: filter candidates into the private list
-                while (j + 4 <= j1 && cnt + 4 <= sm.list_len) {
+                while (j + 4 <= j1 && lp + 4 * TILE_TB <= my_end) {
                     const V4<CT> x0 = tAj[j], x1 = tAj[j + 1], x2 = tAj[j + 2], x3 = tAj[j + 3];
-                    if (filter(xi, x0)) my_list[cnt++ * TILE_TB] = (unsigned short)(base + j);
-                    if (filter(xi, x1)) my_list[cnt++ * TILE_TB] = (unsigned short)(base + j + 1);
-                    if (filter(xi, x2)) my_list[cnt++ * TILE_TB] = (unsigned short)(base + j + 2);
-                    if (filter(xi, x3)) my_list[cnt++ * TILE_TB] = (unsigned short)(base + j + 3);
+                    const int b0 = base + j;
+                    if (filter(xi, x0)) { *lp = (unsigned short)b0; lp += TILE_TB; }
+                    if (filter(xi, x1)) { *lp = (unsigned short)(b0 + 1); lp += TILE_TB; }
+                    if (filter(xi, x2)) { *lp = (unsigned short)(b0 + 2); lp += TILE_TB; }
+                    if (filter(xi, x3)) { *lp = (unsigned short)(b0 + 3); lp += TILE_TB; }
                     j += 4;
                 }
-                while (j < j1 && cnt < sm.list_len) {
-                    if (filter(xi, tAj[j])) my_list[cnt++ * TILE_TB] = (unsigned short)(base + j);
+                while (j < j1 && lp < my_end) {
+                    if (filter(xi, tAj[j])) { *lp = (unsigned short)(base + j); lp += TILE_TB; }
                     ++j;
                 }
                 if (!__any_sync(0xffffffffu, j < j1)) break;
@@ -354,11 +366,25 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ row_tile_start, int nr
     const T v_a[3] = {bi.x, bi.y, bi.z};
     uint32_t parity = 0;
 
+    constexpr bool FAST = std::is_same<T, float>::value && std::is_same<CT, float>::value;
+    FastConst fc = {};
+    float pa_term = 0.f;
+    if constexpr (FAST) {
+        fc = make_fast_const(k);
+        pa_term = valid ? p_a / (rho_a * rho_a) : 0.f;
+    }
+
     T dv_ff[3] = {0, 0, 0}, drho_ff = 0;
     if (ff_enabled) {
         NbSet<T, CT, V4<T>, true> nb{fcell_start, A, B, P};
         tile_sweep<ND, T, CT>(sm, g, nb, valid, cx, xi, k.radius2, parity,
                               [&](const V4<CT> &xj, const V4<T> &bj, T pj) {
+                                  if constexpr (FAST) {
+                                      interact_pair_fast<ND, KERNEL, DENS, true>(
+                                          fc, xi, xj, rho_a, p_a, pa_term, v_a, bj.x, bj.y, bj.z, bj.w, pj,
+                                          dv_ff, drho_ff);
+                                      return;
+                                  }
                                   T pd[3];
                                   const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
                                   if (d2 <= k.radius2) {
@@ -378,6 +404,12 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ row_tile_start, int nr
         NbSet<T, CT, V2<T>, false> nb{wcell_start, Aw, Ww, nullptr};
         tile_sweep<ND, T, CT>(sm, g, nb, valid, cx, xi, k.radius2, parity,
                               [&](const V4<CT> &xj, const V2<T> &wj, T) {
+                                  if constexpr (FAST) {
+                                      interact_pair_fast<ND, KERNEL, DENS, false>(
+                                          fc, xi, xj, rho_a, p_a, pa_term, v_a, 0.f, 0.f, 0.f, wj.y, wj.x,
+                                          dv_fw, drho_fw);
+                                      return;
+                                  }
                                   T pd[3];
                                   const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
                                   if (d2 <= k.radius2) {
@@ -468,13 +500,17 @@ struct TileState {
     int *d_wrow_tile_start = nullptr;  // [nrows + 1] wall tiles (static)
     int nrows = 0;
     int max_ftiles = 0, max_wtiles = 0;
-    int smem_budget = 100 * 1024;  // bytes per block: two blocks per SM
-    int list_len = 96;
+    int smem_budget = 112 * 1024;  // bytes per block: two blocks per SM
+    int list_len = 160;            // private list entries per thread (one flush per sweep in 3-D)
 };
 
 inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
 {
     t.nrows = nrows;
+    // tuning overrides (bytes of shared memory per block, list entries per thread)
+    if (const char *e = getenv("TPB_TILE_SMEM")) t.smem_budget = atoi(e);
+    if (const char *e = getenv("TPB_TILE_LIST")) t.list_len = atoi(e);
+    if (t.smem_budget > 227 * 1024) t.smem_budget = 227 * 1024;
     t.max_ftiles = (int)((n_f + TILE_TB - 1) / TILE_TB) + nrows;
     t.max_wtiles = (int)((n_w + TILE_TB - 1) / TILE_TB) + nrows;
     if (cudaMalloc(&t.d_row_tiles, sizeof(int) * (size_t)(nrows + 4)) != cudaSuccess) return 1;
