@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,6 +42,8 @@ struct Semi {
     double cell_size = 0, origin[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     int ncell[3] = {1, 1, 1};
     int64_t ncells = 0;
+    int xsplit = 1;       // cells are cell_size / xsplit wide in x
+    double gap_tol = 0;   // rounding bound of cell-boundary coordinates in cT
 
     // device
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -175,7 +178,11 @@ GridConst<CT> make_grid_const(const Semi &s)
         g.hi[d] = hi;
     }
     g.inv_cell = (CT)(1.0 / s.cell_size);
+    g.inv_cell_x = (CT)((double)s.xsplit / s.cell_size);
+    g.cell = (CT)s.cell_size;
+    g.gap_tol = (CT)s.gap_tol;
     g.ncells = (int)s.ncells;
+    g.sx = s.xsplit;
     return g;
 }
 
@@ -230,7 +237,8 @@ struct Ops {
                        s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
                        s.d_perm_f);
         }
-        if (use_tiles(s)) return build_tile_table(s, s.d_fcell_start, s.tiles.d_frow_tile_start);
+        if (use_tiles(s))
+            return build_tile_table(s, s.d_fcell_start, s.tiles.d_frow_tile_start, s.tiles.d_ftile_desc);
         return TPB_OK;
     }
 
@@ -256,7 +264,7 @@ struct Ops {
                    s.d_key, s.d_wcell_start, s.d_tmp_perm, n, (V4<CT> *)s.d_Aw, (V2<T> *)s.d_Ww,
                    s.d_perm_w);
         CUDA_TRY(&s, cudaMemsetAsync(s.d_volw, 0, sizeof(T) * (size_t)std::max(n, 1), s.stream));
-        rc = build_tile_table(s, s.d_wcell_start, s.tiles.d_wrow_tile_start);
+        rc = build_tile_table(s, s.d_wcell_start, s.tiles.d_wrow_tile_start, s.tiles.d_wtile_desc);
         if (rc) return rc;
         CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
         cudaFree(d_coords);
@@ -277,12 +285,16 @@ struct Ops {
     }
 
     // ---- tile table of one sorted point set: tiles per cell row + exclusive scan
-    static int build_tile_table(Semi &s, const int *d_cell_start, int *d_row_tile_start)
+    static int build_tile_table(Semi &s, const int *d_cell_start, int *d_row_tile_start, int4 *d_desc)
     {
         const int nrows = s.tiles.nrows;
         LAUNCH(s, k_row_tiles, cdiv(nrows, 256), 256, 0, d_cell_start, s.ncell[0], nrows,
                s.tiles.d_row_tiles);
-        return exclusive_scan(s, s.tiles.d_row_tiles, nrows, d_row_tile_start);
+        int rc = exclusive_scan(s, s.tiles.d_row_tiles, nrows, d_row_tile_start);
+        if (rc) return rc;
+        LAUNCH(s, k_fill_tiles, cdiv(nrows, 256), 256, 0, d_cell_start, s.ncell[0], nrows,
+               d_row_tile_start, d_desc);
+        return TPB_OK;
     }
 
     static int use_tiles(Semi &s)
@@ -320,8 +332,16 @@ struct Ops {
                 if (rc) return rc;
                 attr_set = true;
             }
+            CUDA_TRY(&s, cudaMemsetAsync(s.tiles.d_n_wactive, 0, sizeof(int), s.stream));
+            T p_empty = (T)0;  // empty sum, clipped or not: p = 0
+            T rho_empty = k.eos.rho0 * (T)std::pow((double)((p_empty - k.eos.p_bg) / k.eos.B + (T)1),
+                                                   (double)k.eos.inv_gamma);
+            LAUNCH(s, (k_wall_tile_prep<ND, T, CT>), cdiv((int64_t)s.tiles.max_wtiles * 32, 256), 256, 0, g,
+                   s.tiles.d_wrow_tile_start + s.tiles.nrows, s.tiles.d_wtile_desc, (const V4<CT> *)s.d_Aw,
+                   s.d_fcell_start, rho_empty, (V2<T> *)s.d_Ww, (T *)s.d_volw, s.tiles.d_wactive,
+                   s.tiles.d_n_wactive);
             LAUNCH(s, (k_adami_tiles<ND, T, CT, KERNEL>), s.tiles.max_wtiles, TILE_TB, smem, g,
-                   s.tiles.d_wrow_tile_start, s.tiles.nrows, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
+                   s.tiles.d_n_wactive, s.tiles.d_wactive, s.tiles.d_wtile_desc, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
                    s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
                    s.interaction[1][0], k, (V2<T> *)s.d_Ww, (T *)s.d_volw, cap, s.tiles.list_len);
             return TPB_OK;
@@ -356,7 +376,7 @@ struct Ops {
                 attr_set = true;
             }
             LAUNCH(s, (k_interact_tiles<ND, T, CT, KERNEL, DENS>), s.tiles.max_ftiles, TILE_TB, smem, g,
-                   s.tiles.d_frow_tile_start, s.tiles.nrows, s.d_fcell_start, (const V4<CT> *)s.d_A,
+                   s.tiles.d_frow_tile_start + s.tiles.nrows, s.tiles.d_ftile_desc, s.d_fcell_start, (const V4<CT> *)s.d_A,
                    (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f, s.interaction[0][0], has_wall,
                    s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv, cap,
                    s.tiles.list_len);
@@ -515,7 +535,19 @@ struct Ops {
         CUDA_TRY(&s, cudaMalloc(&d_oj, sizeof(int) * (size_t)std::max<int64_t>(capacity, 1)));
         CUDA_TRY(&s, cudaMalloc(&d_counter, sizeof(unsigned long long)));
         CUDA_TRY(&s, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), s.stream));
-        if (n_x > 0)
+        if (n_x > 0 && use_tiles(s)) {
+            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, s.tiles.list_len);
+            const size_t smem = tile_smem_bytes<T, CT>(cap, s.tiles.list_len);
+            int rc2 = set_smem(s, k_pairs_tiles<ND, T, CT>, 227 * 1024);
+            if (rc2) return rc2;
+            LAUNCH(s, (k_pairs_tiles<ND, T, CT>), x_fluid ? s.tiles.max_ftiles : s.tiles.max_wtiles, TILE_TB,
+                   smem, g, (x_fluid ? s.tiles.d_frow_tile_start : s.tiles.d_wrow_tile_start) + s.tiles.nrows,
+                   x_fluid ? s.tiles.d_ftile_desc : s.tiles.d_wtile_desc,
+                   (const V4<CT> *)(x_fluid ? s.d_A : s.d_Aw), x_fluid ? s.d_perm_f : s.d_perm_w,
+                   y_fluid ? s.d_fcell_start : s.d_wcell_start,
+                   (const V4<CT> *)(y_fluid ? s.d_A : s.d_Aw), y_fluid ? s.d_perm_f : s.d_perm_w, r2,
+                   (long long)capacity, d_oi, d_oj, d_counter, cap, s.tiles.list_len);
+        } else if (n_x > 0)
             LAUNCH(s, (k_pairs<ND, T, CT>), cdiv(n_x, 128), 128, 0, n_x, g,
                    (const V4<CT> *)(x_fluid ? s.d_A : s.d_Aw), x_fluid ? s.d_perm_f : s.d_perm_w,
                    y_fluid ? s.d_fcell_start : s.d_wcell_start,
@@ -770,6 +802,21 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
             s->ncell[d] = 1;
         }
         s->ncells *= s->ncell[d];
+    }
+    // x-split: finer cells along x (the fastest index) let the tile sweep clip each row to the
+    // chord of the search sphere; bounded so that the cell table stays scannable
+    {
+        int want = 1;  // lock-step sweeps gain nothing from finer x cells (experiments)
+        if (const char *e = getenv("TPB_XSPLIT")) want = std::max(1, atoi(e));
+        const int64_t limit = (int64_t)SCAN_TILE * SCAN_TILE - 8;
+        while (want > 1 && s->ncells * want > limit) --want;
+        s->xsplit = want;
+        s->ncell[0] *= want;
+        s->ncells *= want;
+        double max_coord = 0;
+        for (int d = 0; d < nd; ++d)
+            max_coord = std::max(max_coord, std::max(std::fabs(s->origin[d]), std::fabs(hi[d]) + 2 * s->cell_size));
+        s->gap_tol = 16 * eps_ct * max_coord;
     }
     if (s->ncells + 4 > (int64_t)SCAN_TILE * SCAN_TILE || s->ncells > 0x7ffffff0)
         return fail(s, TPB_ERR_UNSUPPORTED, "bounding box / search radius gives too many cells");

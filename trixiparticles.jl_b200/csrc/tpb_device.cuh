@@ -323,16 +323,22 @@ __device__ __forceinline__ void interact_pair_fast(const FastConst &c, const V4<
 
 // ---------------------------------------------------------------------------------------
 // Uniform cell grid shared by every point set (FullGridCellList semantics: padded bounding
-// box, particles may only live in cells 1..n-2 of each dimension, so the 3^ND neighbourhood
-// never leaves the grid).  Cell index is linear with x fastest: the three cells
-// {cx-1, cx, cx+1} of one (y, z) row are one contiguous run of sorted particles.
+// box, particles may only live in interior cells, so the neighbourhood never leaves the grid).
+// Cells are `cell` wide in y and z and `cell / sx` wide in x ("x-split"): the cell index is
+// linear with x fastest, so the 2 sx + 1 cells {cx - sx .. cx + sx} of one (y, z) row are one
+// contiguous run of sorted particles, and the finer x resolution lets a sweep clip that run to
+// the chord of the search sphere in that row (tpb_tiles.cuh).
 template <typename CT>
 struct GridConst {
     CT origin[3];
-    CT inv_cell;  // 1 / cell_size
+    CT inv_cell;    // 1 / cell  (y, z)
+    CT inv_cell_x;  // sx / cell (x)
+    CT cell;        // cell size in y, z
+    CT gap_tol;     // bound on the rounding of cell-boundary positions (window clipping)
     CT lo[3], hi[3];  // valid coordinate range (bounding box), for the bounds check
     int n[3];
     int ncells;
+    int sx;         // x-split factor
 };
 
 template <int ND, typename CT>
@@ -343,14 +349,15 @@ __device__ __forceinline__ bool cell_coords(const GridConst<CT> &g, CT x, CT y, 
     bool ok = (x >= g.lo[0]) && (x <= g.hi[0]) && (y >= g.lo[1]) && (y <= g.hi[1]);
     if (ND == 3) ok = ok && (z >= g.lo[2]) && (z <= g.hi[2]);
     if (!ok) {
-        cx = cy = 1;
+        cx = g.sx;
+        cy = 1;
         cz = ND == 3 ? 1 : 0;
         return false;
     }
-    cx = (int)floor((x - g.origin[0]) * g.inv_cell);
+    cx = (int)floor((x - g.origin[0]) * g.inv_cell_x);
     cy = (int)floor((y - g.origin[1]) * g.inv_cell);
     cz = ND == 3 ? (int)floor((z - g.origin[2]) * g.inv_cell) : 0;
-    cx = min(max(cx, 1), g.n[0] - 2);
+    cx = min(max(cx, g.sx), g.n[0] - g.sx - 1);
     cy = min(max(cy, 1), g.n[1] - 2);
     if (ND == 3) cz = min(max(cz, 1), g.n[2] - 2);
     return true;

@@ -15,8 +15,8 @@
 
 namespace tpb {
 
-// Visit the rows of the 3^ND neighbourhood of cell (cx, cy, cz): row(j0, j1) is called with
-// the sorted-index range [j0, j1) of the three cells {cx-1, cx, cx+1} of each (y, z) row.
+// Visit the rows of the neighbourhood of cell (cx, cy, cz): row(j0, j1) is called with the
+// sorted-index range [j0, j1) of the cells {cx - sx .. cx + sx} of each of the 3^(ND-1) rows.
 template <int ND, typename CT, typename F>
 __device__ __forceinline__ void for_neighbor_rows(const GridConst<CT> &g,
                                                   const int *__restrict__ cell_start, int cx,
@@ -26,8 +26,8 @@ __device__ __forceinline__ void for_neighbor_rows(const GridConst<CT> &g,
     for (int dz = (ND == 3 ? -1 : 0); dz <= (ND == 3 ? 1 : 0); ++dz) {
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
-            int c0 = cell_linear(g, cx - 1, cy + dy, cz + dz);
-            row(cell_start[c0], cell_start[c0 + 3]);
+            int c0 = cell_linear(g, cx - g.sx, cy + dy, cz + dz);
+            row(cell_start[c0], cell_start[c0 + 2 * g.sx + 1]);
         }
     }
 }

@@ -86,6 +86,21 @@ k_row_tiles(const int *__restrict__ cell_start, int n0, int nrows, int *__restri
     row_tiles[r] = (cnt + TILE_TB - 1) / TILE_TB;
 }
 
+// tile descriptors: (first target, one past the last target, cell row, unused)
+__global__ void __launch_bounds__(256)
+k_fill_tiles(const int *__restrict__ cell_start, int n0, int nrows,
+             const int *__restrict__ row_tile_start, int4 *__restrict__ desc)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const int first = row_tile_start[r], nt = row_tile_start[r + 1] - first;
+    if (nt == 0) return;
+    const int rs = cell_start[(int64_t)r * n0], re = cell_start[(int64_t)(r + 1) * n0];
+    const long long cnt = re - rs;
+    for (int k = 0; k < nt; ++k)
+        desc[first + k] = make_int4(rs + (int)(cnt * k / nt), rs + (int)(cnt * (k + 1) / nt), r, 0);
+}
+
 struct TileHdr {
     int p0, p1, cy, cz, cxmin, cxmax;
     int g0[9], g1[9];  // candidate range of every neighbour row (current neighbour set)
@@ -94,6 +109,7 @@ struct TileHdr {
     int seg_row[TILE_MAXSEG], seg_begin[TILE_MAXSEG], seg_end[TILE_MAXSEG], seg_base[TILE_MAXSEG];
 };
 constexpr int TILE_HDR_BYTES = 16 + ((sizeof(TileHdr) + 15) / 16) * 16;  // mbarrier + header
+constexpr int TILE_ROWTAB_BYTES = 0;
 
 // shared-memory carve-up of one block
 template <typename T, typename CT>
@@ -121,33 +137,23 @@ struct TileSmem {
 template <typename T, typename CT>
 inline size_t tile_smem_bytes(int cap, int list_len)
 {
-    return TILE_HDR_BYTES + (size_t)list_len * TILE_TB * sizeof(unsigned short) +
+    return TILE_HDR_BYTES + TILE_ROWTAB_BYTES + (size_t)list_len * TILE_TB * sizeof(unsigned short) +
            (size_t)cap * (sizeof(V4<CT>) + sizeof(V4<T>) + sizeof(T));
 }
 
-// Locate the tile of this block: binary search of the row, balanced split of the row's
-// particles.  Executed by thread 0; results in hdr.  Returns false if the block has no tile.
+// Load the tile descriptor of this block into hdr (thread 0).
 template <int ND, typename CT>
 __device__ __forceinline__ void tile_locate(TileHdr *hdr, const GridConst<CT> &g,
-                                            const int *__restrict__ row_tile_start, int nrows,
-                                            const int *__restrict__ cell_start,
+                                            const int4 *__restrict__ tile_desc,
                                             const V4<CT> *__restrict__ X, int tile)
 {
-    int lo = 0, hi = nrows;  // row_tile_start[lo] <= tile < row_tile_start[hi]
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (row_tile_start[mid] <= tile) lo = mid; else hi = mid;
-    }
-    const int r = lo;
-    const int first = row_tile_start[r], nt = row_tile_start[r + 1] - first, k = tile - first;
-    const int rs = cell_start[(int64_t)r * g.n[0]], re = cell_start[(int64_t)(r + 1) * g.n[0]];
-    const long long cnt = re - rs;
-    hdr->p0 = rs + (int)(cnt * k / nt);
-    hdr->p1 = rs + (int)(cnt * (k + 1) / nt);
-    hdr->cy = r % g.n[1];
-    hdr->cz = r / g.n[1];
+    const int4 d = tile_desc[tile];
+    hdr->p0 = d.x;
+    hdr->p1 = d.y;
+    hdr->cy = d.z % g.n[1];
+    hdr->cz = d.z / g.n[1];
     int cx, cy, cz;
-    const V4<CT> xa = X[hdr->p0], xb = X[hdr->p1 - 1];
+    const V4<CT> xa = X[d.x], xb = X[d.y - 1];
     cell_coords<ND, CT>(g, xa.x, xa.y, xa.z, cx, cy, cz);
     hdr->cxmin = cx;
     cell_coords<ND, CT>(g, xb.x, xb.y, xb.z, cx, cy, cz);
@@ -166,14 +172,26 @@ struct Filter {
         return pos_diff_d2<ND, T, CT>(xi, xj, pd) <= r2;
     }
 };
+// Blackwell packed FP32 (FADD2 / FMUL2): x and y of one record are an aligned register pair
+// straight out of LDS.128, so (dx, dy) and (dx^2, dy^2) cost one issue slot each.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
 template <int ND>
 struct Filter<ND, float, float> {
     float r2;
     __device__ __forceinline__ Filter(float radius2) : r2(radius2 * (1.0f + 8.0f * 1.1920929e-07f)) {}
     __device__ __forceinline__ bool operator()(const V4<float> &xi, const V4<float> &xj) const
     {
-        float dx = xi.x - xj.x, dy = xi.y - xj.y;
-        float d2 = fmaf(dy, dy, dx * dx);
+        unsigned long long dxy, sq;
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dxy) : "l"(pack_f32x2(xi.x, xi.y)), "l"(pack_f32x2(xj.x, xj.y)));
+        asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(sq) : "l"(dxy));
+        float sx, sy;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(sx), "=f"(sy) : "l"(sq));
+        float d2 = sx + sy;
         if (ND == 3) {
             float dz = xi.z - xj.z;
             d2 = fmaf(dz, dz, d2);
@@ -181,6 +199,10 @@ struct Filter<ND, float, float> {
         return d2 <= r2;
     }
 };
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
 
 // One neighbour set as the sweep sees it.  R1 = second record type (V4<T> fluid: v, rho;
 // V2<T> wall: p, rho); HAS_P: a third scalar array (fluid pressure).
@@ -208,15 +230,20 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
     TileHdr *hdr = sm.hdr;
     R1 *tB = (R1 *)sm.tB;
     const Filter<ND, T, CT> filter(radius2);
-
     __syncthreads();  // the previous sweep is done with hdr and the staged tile
     if (tid < NROWS) {
         const int dy = tid % 3 - 1, dz = ND == 3 ? tid / 3 - 1 : 0;
-        const int c_lo = cell_linear(g, hdr->cxmin - 1, hdr->cy + dy, hdr->cz + dz);
+        const int c_lo = cell_linear(g, hdr->cxmin - g.sx, hdr->cy + dy, hdr->cz + dz);
         hdr->g0[tid] = nb.cell_start[c_lo];
-        hdr->g1[tid] = nb.cell_start[c_lo + (hdr->cxmax - hdr->cxmin) + 3];
+        hdr->g1[tid] = nb.cell_start[c_lo + (hdr->cxmax - hdr->cxmin) + 2 * g.sx + 1];
     }
     __syncthreads();
+    {
+        int total = 0;  // block-uniform: no candidates at all (e.g. wall far from any fluid)
+#pragma unroll
+        for (int q = 0; q < NROWS; ++q) total += hdr->g1[q] - hdr->g0[q];
+        if (total == 0) return;
+    }
     if (tid == 0) {
         hdr->q = 0;
         hdr->gpos = hdr->g0[0];
@@ -224,8 +251,10 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
 
     // private list: entry e of thread t lives at list[e * TILE_TB + t] (conflict-free)
     unsigned short *const my_list = sm.list + tid;
-    unsigned short *const my_end = my_list + (size_t)sm.list_len * TILE_TB;
-    unsigned short *lp = my_list;  // append position
+    const uint32_t list_a = smem_u32(my_list);
+    const uint32_t list_end_a = list_a + (uint32_t)sm.list_len * TILE_TB * 2u;
+    constexpr uint32_t ESTEP = TILE_TB * 2u;  // bytes between consecutive entries of one thread
+    uint32_t lpa = list_a;                    // append position (shared-memory address)
     auto visit = [&](int idx) {
         if constexpr (NB::HAS_P)
             body(sm.tA[idx], tB[idx], sm.tP[idx]);
@@ -234,13 +263,16 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
     };
     auto flush = [&]() {
         const unsigned short *e = my_list;
-        for (; e + 2 * TILE_TB <= lp; e += 2 * TILE_TB) {  // two pairs in flight for ILP
-            const int i0 = e[0], i1 = e[TILE_TB];
+        const unsigned short *const lp = my_list + (lpa - list_a) / 2u;
+        for (; e + 4 * TILE_TB <= lp; e += 4 * TILE_TB) {  // four pairs in flight for ILP
+            const int i0 = e[0], i1 = e[TILE_TB], i2 = e[2 * TILE_TB], i3 = e[3 * TILE_TB];
             visit(i0);
             visit(i1);
+            visit(i2);
+            visit(i3);
         }
-        if (e < lp) visit(e[0]);
-        lp = my_list;
+        for (; e < lp; e += TILE_TB) visit(e[0]);
+        lpa = list_a;
     };
 
     while (true) {
@@ -291,36 +323,47 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
         __syncthreads();
         const int nseg = hdr->nseg;
         if (nseg == 0) break;
+
         mbar_wait(sm.bar, parity);
         parity ^= 1u;
 
+        // ---- lock-step scan: all lanes of a warp walk the candidate run of their own cell
+        // neighbourhood in step (lanes of the same cell read the same record: broadcast)
         for (int si = 0; si < nseg; ++si) {
             const int q = hdr->seg_row[si];
             const int dy = q % 3 - 1, dz = ND == 3 ? q / 3 - 1 : 0;
             int j = 0, j1 = 0;
             if (valid) {
-                const int c0 = cell_linear(g, cx - 1, hdr->cy + dy, hdr->cz + dz);
+                const int c0 = cell_linear(g, cx - g.sx, hdr->cy + dy, hdr->cz + dz);
                 j = max(nb.cell_start[c0], hdr->seg_begin[si]);
-                j1 = min(nb.cell_start[c0 + 3], hdr->seg_end[si]);
+                j1 = min(nb.cell_start[c0 + 2 * g.sx + 1], hdr->seg_end[si]);
             }
-            const V4<CT> *const tAj = sm.tA + hdr->seg_base[si];  // indexed by global record j
             const int base = hdr->seg_base[si];
+            int t = base + j;            // tile index of the next candidate
+            const int t1 = base + j1;
             while (true) {
                 // phase 1: filter candidates into the private list
-                while (j + 4 <= j1 && lp + 4 * TILE_TB <= my_end) {
-                    const V4<CT> x0 = tAj[j], x1 = tAj[j + 1], x2 = tAj[j + 2], x3 = tAj[j + 3];
-                    const int b0 = base + j;
-                    if (filter(xi, x0)) { *lp = (unsigned short)b0; lp += TILE_TB; }
-                    if (filter(xi, x1)) { *lp = (unsigned short)(b0 + 1); lp += TILE_TB; }
-                    if (filter(xi, x2)) { *lp = (unsigned short)(b0 + 2); lp += TILE_TB; }
-                    if (filter(xi, x3)) { *lp = (unsigned short)(b0 + 3); lp += TILE_TB; }
-                    j += 4;
+                constexpr int U = 8;
+                while (t + U <= t1 && lpa + U * ESTEP <= list_end_a) {
+                    V4<CT> xc[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) xc[u] = sm.tA[t + u];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (filter(xi, xc[u])) {
+                            sts_u16(lpa, (uint32_t)(t + u));
+                            lpa += ESTEP;
+                        }
+                    t += U;
                 }
-                while (j < j1 && lp < my_end) {
-                    if (filter(xi, tAj[j])) { *lp = (unsigned short)(base + j); lp += TILE_TB; }
-                    ++j;
+                while (t < t1 && lpa < list_end_a) {
+                    if (filter(xi, sm.tA[t])) {
+                        sts_u16(lpa, (uint32_t)t);
+                        lpa += ESTEP;
+                    }
+                    ++t;
                 }
-                if (!__any_sync(0xffffffffu, j < j1)) break;
+                if (!__any_sync(0xffffffffu, t < t1)) break;
                 flush();  // phase 2 (some list of the warp is full)
             }
         }
@@ -332,7 +375,7 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
 // ------------------------------------------------------------------ interact! (variant 2)
 template <int ND, typename T, typename CT, int KERNEL, int DENS>
 __global__ void __launch_bounds__(TILE_TB, 2)
-k_interact_tiles(GridConst<CT> g, const int *__restrict__ row_tile_start, int nrows,
+k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
                  const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
                  const V4<T> *__restrict__ B, const T *__restrict__ P,
                  const int *__restrict__ perm, int ff_enabled, int has_wall,
@@ -343,10 +386,10 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ row_tile_start, int nr
     constexpr int NV = DENS == 0 ? ND + 1 : ND;
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     const int tile = blockIdx.x;
-    if (tile >= row_tile_start[nrows]) return;
+    if (tile >= *n_tiles) return;
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len);
     if (threadIdx.x == 0) {
-        tile_locate<ND, CT>(sm.hdr, g, row_tile_start, nrows, fcell_start, A, tile);
+        tile_locate<ND, CT>(sm.hdr, g, tile_desc, A, tile);
         mbar_init(sm.bar, 1);
     }
     __syncthreads();
@@ -437,21 +480,63 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ row_tile_start, int nr
 }
 
 // ------------------------------------------------------------------ Adami (variant 2)
-// Targets: wall particles (tiles over the wall's sorted order); neighbours: fluid.
+// Most wall particles of a tank are far from any fluid.  One warp per wall tile checks whether
+// the tile's neighbour rows hold any fluid particle: if not, it writes the result of an empty
+// sum (p = 0, rho = EOS^-1(0), volume = 0) directly; otherwise the tile is appended to the
+// active list that k_adami_tiles runs over.
+template <int ND, typename T, typename CT>
+__global__ void __launch_bounds__(256)
+k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
+                 const V4<CT> *__restrict__ Aw, const int *__restrict__ fcell_start, T rho_empty,
+                 V2<T> *__restrict__ W, T *__restrict__ volume, int *__restrict__ active,
+                 int *__restrict__ n_active)
+{
+    constexpr int NROWS = ND == 3 ? 9 : 3;
+    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (tile >= *n_tiles) return;
+    const int4 d = tile_desc[tile];
+    int cxmin, cxmax, cy, cz;
+    {
+        const V4<CT> xa = Aw[d.x], xb = Aw[d.y - 1];
+        cell_coords<ND, CT>(g, xa.x, xa.y, xa.z, cxmin, cy, cz);
+        cell_coords<ND, CT>(g, xb.x, xb.y, xb.z, cxmax, cy, cz);
+    }
+    int cnt = 0;
+    if (lane < NROWS) {
+        const int dy = lane % 3 - 1, dz = ND == 3 ? lane / 3 - 1 : 0;
+        const int c_lo = cell_linear(g, cxmin - g.sx, cy + dy, cz + dz);
+        cnt = fcell_start[c_lo + (cxmax - cxmin) + 2 * g.sx + 1] - fcell_start[c_lo];
+    }
+    const bool any = __any_sync(0xffffffffu, cnt > 0);
+    if (any) {
+        if (lane == 0) active[atomicAdd(n_active, 1)] = tile;
+        return;
+    }
+    V2<T> empty;
+    empty.x = (T)0;
+    empty.y = rho_empty;
+    for (int w = d.x + lane; w < d.y; w += 32) {
+        W[w] = empty;
+        volume[w] = (T)0;
+    }
+}
+
+// Targets: wall particles (active tiles over the wall's sorted order); neighbours: fluid.
 template <int ND, typename T, typename CT, int KERNEL>
 __global__ void __launch_bounds__(TILE_TB, 2)
-k_adami_tiles(GridConst<CT> g, const int *__restrict__ row_tile_start, int nrows,
-              const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
+k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__restrict__ active,
+              const int4 *__restrict__ tile_desc, const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
               const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
               const V4<T> *__restrict__ B, const T *__restrict__ P, int interaction_enabled,
               AdamiConst<T> k, V2<T> *__restrict__ W, T *__restrict__ volume, int cap, int list_len)
 {
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
-    const int tile = blockIdx.x;
-    if (tile >= row_tile_start[nrows]) return;
+    if ((int)blockIdx.x >= *n_active) return;
+    const int tile = active[blockIdx.x];
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len);
     if (threadIdx.x == 0) {
-        tile_locate<ND, CT>(sm.hdr, g, row_tile_start, nrows, wcell_start, Aw, tile);
+        tile_locate<ND, CT>(sm.hdr, g, tile_desc, Aw, tile);
         mbar_init(sm.bar, 1);
     }
     __syncthreads();
@@ -471,6 +556,18 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ row_tile_start, int nrows
                               [&](const V4<CT> &xj, const V4<T> &bj, T pj) {
                                   T pd[3];
                                   const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                                  if constexpr (std::is_same<T, float>::value) {
+                                      // branch-free Float32 form: a rejected pair gets weight 0
+                                      const bool ok = d2 <= k.radius2;
+                                      const float d2s = ok ? d2 : 1.0f;
+                                      const float dist = d2s * rsqrt_approx(fmaxf(d2s, 1e-30f));
+                                      float hyd = k.acc[0] * (bj.w * pd[0]) + k.acc[1] * (bj.w * pd[1]);
+                                      if (ND == 3) hyd += k.acc[2] * (bj.w * pd[2]);
+                                      const float kw = ok ? kernel_safe<KERNEL, float>(k.kern, dist) : 0.0f;
+                                      p = fmaf(k.p_off + pj + hyd, kw, p);
+                                      vol += kw;
+                                      return;
+                                  }
                                   if (d2 <= k.radius2) {
                                       const T dist = sqrt_rn(d2);
                                       const T rho_f = bj.w;
@@ -493,11 +590,59 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ row_tile_start, int nrows
     volume[w] = vol;
 }
 
+// ------------------------------------------------------------------ neighbour pair dump
+// Test hook behind tpb_neighbor_pairs (variant 2): the same tile sweep, filter and window
+// clipping as interact!, with a body that records (orig_i, orig_j) of every pair accepted by
+// the exact predicate.  The neighbour permutation rides in the second record slot.
+template <int ND, typename T, typename CT>
+__global__ void __launch_bounds__(TILE_TB, 2)
+k_pairs_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
+              const V4<CT> *__restrict__ X, const int *__restrict__ perm_x,
+              const int *__restrict__ ycell_start, const V4<CT> *__restrict__ Y,
+              const int *__restrict__ perm_y, T radius2, long long capacity, int *__restrict__ out_i,
+              int *__restrict__ out_j, unsigned long long *__restrict__ counter, int cap, int list_len)
+{
+    extern __shared__ __align__(16) unsigned char tile_smem_raw[];
+    const int tile = blockIdx.x;
+    if (tile >= *n_tiles) return;
+    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len);
+    if (threadIdx.x == 0) {
+        tile_locate<ND, CT>(sm.hdr, g, tile_desc, X, tile);
+        mbar_init(sm.bar, 1);
+    }
+    __syncthreads();
+    const int s = sm.hdr->p0 + threadIdx.x;
+    const bool valid = s < sm.hdr->p1;
+    V4<CT> xi = {};
+    int cx = sm.hdr->cxmin, cy, cz, orig_i = 0;
+    if (valid) {
+        xi = X[s];
+        orig_i = perm_x[s];
+        cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    }
+    uint32_t parity = 0;
+    NbSet<T, CT, int, false> nb{ycell_start, Y, perm_y, nullptr};
+    tile_sweep<ND, T, CT>(sm, g, nb, valid, cx, xi, radius2, parity, [&](const V4<CT> &xj, const int &pj, T) {
+        T pd[3];
+        if (pos_diff_d2<ND, T, CT>(xi, xj, pd) <= radius2) {
+            unsigned long long at = atomicAdd(counter, 1ull);
+            if ((long long)at < capacity) {
+                out_i[at] = orig_i;
+                out_j[at] = pj;
+            }
+        }
+    });
+}
+
 // ------------------------------------------------------------------ host side
 struct TileState {
     int *d_row_tiles = nullptr;        // [nrows]
     int *d_frow_tile_start = nullptr;  // [nrows + 1] fluid tiles (rebuilt every kick)
     int *d_wrow_tile_start = nullptr;  // [nrows + 1] wall tiles (static)
+    int4 *d_ftile_desc = nullptr;      // [max_ftiles]
+    int4 *d_wtile_desc = nullptr;      // [max_wtiles]
+    int *d_wactive = nullptr;          // [max_wtiles] wall tiles with fluid in reach (per kick)
+    int *d_n_wactive = nullptr;        // [1]
     int nrows = 0;
     int max_ftiles = 0, max_wtiles = 0;
     int smem_budget = 112 * 1024;  // bytes per block: two blocks per SM
@@ -516,6 +661,10 @@ inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
     if (cudaMalloc(&t.d_row_tiles, sizeof(int) * (size_t)(nrows + 4)) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_frow_tile_start, sizeof(int) * (size_t)(nrows + 4)) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_wrow_tile_start, sizeof(int) * (size_t)(nrows + 4)) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_ftile_desc, sizeof(int4) * (size_t)t.max_ftiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_wtile_desc, sizeof(int4) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_wactive, sizeof(int) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_n_wactive, sizeof(int) * 4) != cudaSuccess) return 1;
     cudaMemset(t.d_frow_tile_start, 0, sizeof(int) * (size_t)(nrows + 4));
     cudaMemset(t.d_wrow_tile_start, 0, sizeof(int) * (size_t)(nrows + 4));
     return 0;
@@ -525,6 +674,10 @@ inline void tiles_free(TileState &t)
     if (t.d_row_tiles) cudaFree(t.d_row_tiles);
     if (t.d_frow_tile_start) cudaFree(t.d_frow_tile_start);
     if (t.d_wrow_tile_start) cudaFree(t.d_wrow_tile_start);
+    if (t.d_ftile_desc) cudaFree(t.d_ftile_desc);
+    if (t.d_wtile_desc) cudaFree(t.d_wtile_desc);
+    if (t.d_wactive) cudaFree(t.d_wactive);
+    if (t.d_n_wactive) cudaFree(t.d_n_wactive);
     t = TileState();
 }
 
@@ -532,7 +685,7 @@ inline void tiles_free(TileState &t)
 template <typename T, typename CT>
 inline int tile_capacity(int smem_budget, int list_len)
 {
-    const size_t fixed = TILE_HDR_BYTES + (size_t)list_len * TILE_TB * sizeof(unsigned short);
+    const size_t fixed = TILE_HDR_BYTES + TILE_ROWTAB_BYTES + (size_t)list_len * TILE_TB * sizeof(unsigned short);
     const size_t rec = sizeof(V4<CT>) + sizeof(V4<T>) + sizeof(T);
     int cap = (int)(((size_t)smem_budget - fixed) / rec);
     cap &= ~3;
