@@ -151,6 +151,15 @@ int32_t tpb_ode_sizes(tpb_semi_t semi, int64_t *n_u, int64_t *n_v);
 int32_t tpb_system_range(tpb_semi_t semi, int32_t system, int64_t *u_first, int64_t *u_len,
                          int64_t *v_first, int64_t *v_len);
 
+/* ---- slab decomposition (one handle per GPU) -------------------------
+ * The fluid system was added with a capacity of n particles.  A rank keeps its owned particles
+ * in rows [0, n_targets) of the ODE vectors and appends the ghost particles received from its
+ * slab neighbours in rows [n_targets, n_active): all n_active particles are binned and act as
+ * neighbours, only the first n_targets get a dv.  Ghost masses travel with the particles. */
+int32_t tpb_set_fluid_count(tpb_semi_t semi, int64_t n_active, int64_t n_targets);
+/* overwrite mass[first, first + count): host or device pointer according to ode_memory */
+int32_t tpb_set_fluid_mass(tpb_semi_t semi, int64_t first, int64_t count, const void *mass);
+
 /* ---- the hot path ----------------------------------------------------------------------- */
 /* `kick!(dv_ode, v_ode, u_ode, p, t)` (semidiscretization.jl:589-612): dv_ode is fully
  * overwritten.  Host pointers are not retained after return. */

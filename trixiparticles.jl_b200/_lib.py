@@ -22,6 +22,7 @@ EXPORTS = [
     "tpb_system_range", "tpb_kick", "tpb_drift", "tpb_get_system_field", "tpb_neighbor_pairs",
     "tpb_synchronize", "tpb_set_stream", "tpb_get_stats", "tpb_host_register",
     "tpb_host_unregister", "tpb_set_profiling", "tpb_get_phase_times",
+    "tpb_set_fluid_count", "tpb_set_fluid_mass",
 ]
 PHASES = ("rebuild", "density", "boundary", "interact")
 
@@ -112,6 +113,8 @@ def load():
     L.tpb_set_profiling.restype = i32; L.tpb_set_profiling.argtypes = [p, i32]
     L.tpb_get_phase_times.restype = i32
     L.tpb_get_phase_times.argtypes = [p, C.POINTER(d), C.POINTER(i32)]
+    L.tpb_set_fluid_count.restype = i32; L.tpb_set_fluid_count.argtypes = [p, i64, i64]
+    L.tpb_set_fluid_mass.restype = i32; L.tpb_set_fluid_mass.argtypes = [p, i64, i64, p]
     _lib = L
     return L
 

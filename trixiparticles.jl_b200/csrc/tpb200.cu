@@ -33,7 +33,8 @@ struct Semi {
     int fluid_index = -1, wall_index = -1;
     tpb_fluid_params fp{};
     tpb_wall_params wp{};
-    int64_t n_f = 0, n_w = 0;
+    int64_t n_f = 0, n_w = 0;   // n_f: capacity of the fluid system (particles allocated)
+    int64_t n_act = 0, n_tgt = 0;  // particles binned as neighbours / particles that get a dv (slab ghosts: n_tgt < n_act)
     std::vector<unsigned char> h_mass_f, h_coords_w, h_mass_w, h_dens_w;
     int interaction[2][2] = {{1, 1}, {1, 1}};
     bool ready = false;
@@ -220,7 +221,7 @@ struct Ops {
     // ---- NHS rebuild of the fluid + EOS (update_nhs!, update_pressure!)
     static int rebuild_fluid(Semi &s, const CT *d_u, const T *d_v)
     {
-        int n = (int)s.n_f;
+        int n = (int)s.n_act;
         int rc = bin_points(s, d_u, n, s.d_fcell_start);
         if (rc) return rc;
         EosConst<T> eos = make_eos_const<T>(s.fp.sound_speed, s.fp.exponent, s.fp.reference_density,
@@ -277,7 +278,7 @@ struct Ops {
     static void launch_summation(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc,
                                  const EosConst<T> &eos)
     {
-        int n = (int)s.n_f;
+        int n = (int)s.n_act;
         LAUNCH(s, (k_summation_density<ND, T, CT, KERNEL>), cdiv(n, 128), 128, 0, n, g,
                s.d_fcell_start, (const V4<CT> *)s.d_A, (int)(s.n_w > 0), s.d_wcell_start,
                (const V4<CT> *)s.d_Aw, s.interaction[0][1], pc.kern, pc.radius2, eos,
@@ -356,7 +357,7 @@ struct Ops {
     template <int KERNEL, int DENS>
     static int launch_interact(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc, T *d_dv)
     {
-        int n = (int)s.n_f;
+        int n = (int)s.n_act;
         SourceConst<T> src;
         src.any = s.fp.damping_coefficient != 0.0;
         for (int d = 0; d < 3; ++d) {
@@ -378,21 +379,21 @@ struct Ops {
             LAUNCH(s, (k_interact_tiles<ND, T, CT, KERNEL, DENS>), s.tiles.max_ftiles, TILE_TB, smem, g,
                    s.tiles.d_frow_tile_start + s.tiles.nrows, s.tiles.d_ftile_desc, s.d_fcell_start, (const V4<CT> *)s.d_A,
                    (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f, s.interaction[0][0], has_wall,
-                   s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv, cap,
-                   s.tiles.list_len);
+                   s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv,
+                   (int)s.n_tgt, cap, s.tiles.list_len);
             return TPB_OK;
         }
         LAUNCH(s, (k_interact_pp<ND, T, CT, KERNEL, DENS>), cdiv(n, 128), 128, 0, n, g,
                s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
                s.d_perm_f, s.interaction[0][0], has_wall, s.d_wcell_start,
-               (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv);
+               (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv, (int)s.n_tgt);
         return TPB_OK;
     }
 
     // ---- kick! on device pointers
     static int kick_device(Semi &s, T *d_dv, const T *d_v, const CT *d_u)
     {
-        if (s.n_f == 0) return TPB_OK;
+        if (s.n_act == 0) return TPB_OK;
         prof_mark(s, TPB_PHASE_REBUILD);
         int rc = rebuild_fluid(s, d_u, d_v);
         if (rc) return rc;
@@ -425,7 +426,7 @@ struct Ops {
 
     static int kick(Semi &s, void *dv, const void *v, const void *u)
     {
-        const size_t nu = sizeof(CT) * ND * (size_t)s.n_f, nvb = sizeof(T) * nv(s) * (size_t)s.n_f;
+        const size_t nu = sizeof(CT) * ND * (size_t)s.n_act, nvb = sizeof(T) * nv(s) * (size_t)s.n_act;
         s.launches_this_call = 0;
         int rc;
         if (s.cfg.ode_memory == TPB_MEM_HOST) {
@@ -452,9 +453,9 @@ struct Ops {
     static int drift(Semi &s, void *du, const void *v, const void *u)
     {
         (void)u;
-        const size_t nu = sizeof(CT) * ND * (size_t)s.n_f, nvb = sizeof(T) * nv(s) * (size_t)s.n_f;
+        const size_t nu = sizeof(CT) * ND * (size_t)s.n_tgt, nvb = sizeof(T) * nv(s) * (size_t)s.n_tgt;
         s.launches_this_call = 0;
-        int64_t total = s.n_f * ND;
+        int64_t total = s.n_tgt * ND;
         if (total == 0) return TPB_OK;
         if (s.cfg.ode_memory == TPB_MEM_HOST) {
             CUDA_TRY(&s, cudaMemcpyAsync(s.d_v, v, nvb, cudaMemcpyHostToDevice, s.stream));
@@ -476,7 +477,7 @@ struct Ops {
     {
         T *scratch = (T *)s.d_scratch;
         if (system == s.fluid_index) {
-            if (n != s.n_f) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
+            if (n != s.n_act) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
             if (n == 0) return TPB_OK;
             if (field == TPB_FIELD_PRESSURE)
                 LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_perm_f, (const T *)s.d_P, 1, 0, scratch);
@@ -507,7 +508,7 @@ struct Ops {
                               int32_t *out_i, int32_t *out_j, int64_t *count)
     {
         // rebuild the fluid grid for the given coordinates (velocities are irrelevant here)
-        const size_t nu = sizeof(CT) * ND * (size_t)s.n_f, nvb = sizeof(T) * nv(s) * (size_t)s.n_f;
+        const size_t nu = sizeof(CT) * ND * (size_t)s.n_act, nvb = sizeof(T) * nv(s) * (size_t)s.n_act;
         const CT *d_u = (const CT *)u_ode;
         T *d_vzero = nullptr;
         CUDA_TRY(&s, cudaMalloc(&d_vzero, std::max(nvb, (size_t)16)));
@@ -528,7 +529,7 @@ struct Ops {
         T h = x_fluid ? (T)s.fp.smoothing_length : (T)s.wp.smoothing_length;
         T R = (T)2 * h;
         T r2 = R * R;
-        int n_x = (int)(x_fluid ? s.n_f : s.n_w);
+        int n_x = (int)(x_fluid ? s.n_act : s.n_w);
         int *d_oi = nullptr, *d_oj = nullptr;
         unsigned long long *d_counter = nullptr;
         CUDA_TRY(&s, cudaMalloc(&d_oi, sizeof(int) * (size_t)std::max<int64_t>(capacity, 1)));
@@ -693,7 +694,7 @@ int32_t tpb_add_fluid_system(tpb_semi_t semi, const tpb_fluid_params *p, int64_t
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "density diffusion requires ContinuityDensity");
     if (n < 0 || n > 0x7fffffff / 4) return fail(s, TPB_ERR_INVALID_ARGUMENT, "particle count out of range");
     s->fp = *p;
-    s->n_f = n;
+    s->n_f = n; s->n_act = n; s->n_tgt = n;
     s->h_mass_f.assign((const unsigned char *)mass, (const unsigned char *)mass + tsize(s->cfg.eltype) * (size_t)n);
     s->fluid_index = s->n_systems++;
     if (system_index) *system_index = s->fluid_index;
@@ -884,8 +885,8 @@ int32_t tpb_ode_sizes(tpb_semi_t semi, int64_t *n_u, int64_t *n_v)
     if (!s || s->fluid_index < 0) return fail(s, TPB_ERR_STATE, "no fluid system");
     const int nd = s->cfg.ndims;
     const int nvars = s->fp.density_calculator == TPB_DENSITY_SUMMATION ? nd : nd + 1;
-    if (n_u) *n_u = s->n_f * nd;
-    if (n_v) *n_v = s->n_f * nvars;
+    if (n_u) *n_u = s->n_act * nd;
+    if (n_v) *n_v = s->n_act * nvars;
     return TPB_OK;
 }
 
@@ -972,6 +973,36 @@ int32_t tpb_get_stats(tpb_semi_t semi, tpb_stats *out)
     Semi *s = (Semi *)semi;
     if (!s || !out) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
     *out = s->stats;
+    return TPB_OK;
+}
+
+int32_t tpb_set_fluid_count(tpb_semi_t semi, int64_t n_active, int64_t n_targets)
+{
+    Semi *s = (Semi *)semi;
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    if (n_active < 0 || n_active > s->n_f || n_targets < 0 || n_targets > n_active)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "need 0 <= n_targets <= n_active <= capacity of the fluid system");
+    if (n_targets < n_active && s->fp.density_calculator == TPB_DENSITY_SUMMATION)
+        return fail(s, TPB_ERR_UNSUPPORTED, "ghost particles need ContinuityDensity (their density travels with them)");
+    s->n_act = n_active;
+    s->n_tgt = n_targets;
+    return TPB_OK;
+}
+
+int32_t tpb_set_fluid_mass(tpb_semi_t semi, int64_t first, int64_t count, const void *mass)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || (count > 0 && !mass)) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->ready) return fail(s, TPB_ERR_STATE, "tpb_set_fluid_mass before tpb_semidiscretize");
+    if (first < 0 || count < 0 || first + count > s->n_f)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "mass range outside the fluid system");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    const size_t ts = tsize(s->cfg.eltype);
+    CUDA_TRY(s, cudaMemcpyAsync((unsigned char *)s->d_mass_f + ts * (size_t)first, mass, ts * (size_t)count,
+                                s->cfg.ode_memory == TPB_MEM_DEVICE ? cudaMemcpyDeviceToDevice
+                                                                    : cudaMemcpyHostToDevice,
+                                s->stream));
+    if (s->cfg.ode_memory == TPB_MEM_HOST) CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     return TPB_OK;
 }
 

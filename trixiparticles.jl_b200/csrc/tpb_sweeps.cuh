@@ -141,11 +141,12 @@ k_interact_pp(int n_f, GridConst<CT> g, const int *__restrict__ fcell_start,
               const T *__restrict__ P, const int *__restrict__ perm, int ff_enabled,
               int has_wall, const int *__restrict__ wcell_start,
               const V4<CT> *__restrict__ Aw, const V2<T> *__restrict__ Ww, PairConst<T> k,
-              SourceConst<T> src, T *__restrict__ dv /* NV x n_f, ODE order */)
+              SourceConst<T> src, T *__restrict__ dv /* NV x n_f, ODE order */, int n_targets)
 {
     constexpr int NV = DENS == 0 ? ND + 1 : ND;
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_f) return;
+    if (perm[s] >= n_targets) return;  // slab ghost: neighbour only
     const V4<CT> xi = A[s];
     const V4<T> bi = B[s];
     const T p_a = P[s];

@@ -381,7 +381,7 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
                  const int *__restrict__ perm, int ff_enabled, int has_wall,
                  const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
                  const V2<T> *__restrict__ Ww, PairConst<T> k, SourceConst<T> src,
-                 T *__restrict__ dv, int cap, int list_len)
+                 T *__restrict__ dv, int n_targets, int cap, int list_len)
 {
     constexpr int NV = DENS == 0 ? ND + 1 : ND;
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
@@ -394,7 +394,9 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     }
     __syncthreads();
     const int s = sm.hdr->p0 + threadIdx.x;
-    const bool valid = s < sm.hdr->p1;
+    // slab ghosts (original index >= n_targets) are neighbours only: no dv is computed for them
+    const bool valid = s < sm.hdr->p1 && perm[s] < n_targets;
+    if (!__syncthreads_or(valid)) return;
     V4<CT> xi = {};
     V4<T> bi = {};
     T p_a = 0;

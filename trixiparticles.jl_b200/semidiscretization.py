@@ -48,6 +48,7 @@ class B200Backend:
     ode_memory: str = "host"
     deterministic: bool = True
     interact_variant: int = 0
+    ghost_capacity: int = 0  # extra fluid rows for slab ghosts (slabs.py); 0 on a single GPU
 
 
 def _dtype_id(dt):
@@ -200,8 +201,10 @@ class Semidiscretization:
                 idx = C.c_int32(-1)
                 if isinstance(s, WeaklyCompressibleSPHSystem):
                     mass = np.ascontiguousarray(s.mass, dtype=self.eltype)
+                    if be.ghost_capacity:
+                        mass = np.concatenate([mass, np.zeros(be.ghost_capacity, dtype=self.eltype)])
                     fp = self._fluid_params(s)
-                    _lib.check(h, L.tpb_add_fluid_system(h, C.byref(fp), s.nparticles,
+                    _lib.check(h, L.tpb_add_fluid_system(h, C.byref(fp), mass.size,
                                                          mass.ctypes.data, C.byref(idx)))
                 else:
                     coords = np.ascontiguousarray(s.coordinates, dtype=self.coordinates_eltype)
@@ -218,6 +221,9 @@ class Semidiscretization:
                     if not self.interaction_matrix[i, j]:
                         _lib.check(h, L.tpb_set_interaction(h, i, j, 0))
             _lib.check(h, L.tpb_semidiscretize(h, u0_ode.ctypes.data))
+            if be.ghost_capacity:
+                n_own = self.fluid.nparticles
+                _lib.check(h, L.tpb_set_fluid_count(h, n_own, n_own))
             nu, nv = C.c_int64(), C.c_int64()
             _lib.check(h, L.tpb_ode_sizes(h, C.byref(nu), C.byref(nv)))
             assert nu.value == self.ranges_u[-1][1] and nv.value == self.ranges_v[-1][1]

@@ -1,0 +1,385 @@
+"""1-D slab decomposition of the WCSPH right-hand side over the GPUs of one box.
+
+The reference has no distributed path at all; this is the B200
+design for it.  One process per GPU owns the fluid particles of one slab `[x_k, x_{k+1})`.  Per
+`kick!`:
+
+  1. every rank selects its owned particles that lie within `halo` of a slab face and sends
+     `(x, v, rho, m)` to that neighbour (NCCL send/recv over NVLink; counts first, then the
+     payload -- one small host sync per kick);
+  2. the received ghosts are appended behind the owned particles in the rank's extended
+     `u`/`v` buffers and `tpb_set_fluid_count(n_owned + n_ghost, n_owned)` tells the library that
+     the tail is neighbours-only;
+  3. `tpb_kick` runs the usual rebuild + Adami + interact on the local set.
+
+`halo = R_fluid + R_wall + skin`: a wall particle within `R_fluid` of an owned fluid particle needs
+all fluid within `R_wall` of itself for its Adami pressure, so the fluid ghost layer is two search
+radii wide and the wall pressure needs no second exchange; `skin` is how far an owned particle may
+drift out of its slab before `rebalance` (re-partition by position, a `SortingCallback`-like event:
+particle <-> ODE index may only change between time steps) becomes necessary.  Wall particles are
+static: each rank keeps those within `R_fluid + skin` of its slab.
+
+The partition / selection / exchange logic is tensor-backend agnostic (CPU tensors + gloo in the
+tests, CUDA tensors + NCCL on the box); only `SlabSemidiscretization` needs the CUDA library.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Optional
+
+import numpy as np
+
+from .setups import InitialCondition
+
+
+# ------------------------------------------------------------------ layout (pure numpy)
+@dataclass
+class SlabLayout:
+    planes: np.ndarray   # world + 1 slab faces along x; planes[0] = -inf, planes[-1] = +inf
+    halo: float          # fluid ghost layer width
+    wall_reach: float    # wall particles kept within this distance of the slab
+    skin: float
+
+    @property
+    def world(self) -> int:
+        return len(self.planes) - 1
+
+    def owner(self, x: np.ndarray) -> np.ndarray:
+        """Rank owning coordinate(s) x: slab k is [planes[k], planes[k+1])."""
+        return np.clip(np.searchsorted(self.planes, x, side="right") - 1, 0, self.world - 1)
+
+
+def make_layout(x_fluid: np.ndarray, world: int, radius_fluid: float, radius_wall: float,
+                skin: Optional[float] = None) -> SlabLayout:
+    """Faces between lattice columns such that every slab holds the same number of fluid
+    particles (+-1 column): the dam-break column fills only part of the tank, equal-width slabs
+    would leave most GPUs idle."""
+    skin = float(radius_fluid) if skin is None else float(skin)
+    xs = np.sort(np.asarray(x_fluid, dtype=np.float64))
+    planes = [-np.inf]
+    for k in range(1, world):
+        i = int(round(len(xs) * k / world))
+        i = min(max(i, 1), len(xs) - 1)
+        # move to a column boundary: first index whose x differs from its predecessor
+        while i < len(xs) - 1 and xs[i] == xs[i - 1]:
+            i += 1
+        planes.append(0.5 * (xs[i - 1] + xs[i]))
+    planes.append(np.inf)
+    planes = np.asarray(planes)
+    halo = float(radius_fluid) + float(radius_wall) + skin
+    widths = np.diff(planes[1:-1]) if world > 2 else np.array([np.inf])
+    if world > 1 and (np.any(np.diff(planes) <= 0) or np.any(widths < halo)):
+        raise ValueError("slabs are thinner than the ghost layer: use fewer ranks or a larger problem")
+    return SlabLayout(planes=planes, halo=halo, wall_reach=float(radius_fluid) + skin, skin=skin)
+
+
+def subset_ic(ic: InitialCondition, idx: np.ndarray) -> InitialCondition:
+    return InitialCondition(coordinates=np.ascontiguousarray(ic.coordinates[idx]),
+                            velocity=np.ascontiguousarray(ic.velocity[idx]),
+                            mass=np.ascontiguousarray(ic.mass[idx]),
+                            density=np.ascontiguousarray(ic.density[idx]),
+                            pressure=np.ascontiguousarray(ic.pressure[idx]),
+                            particle_spacing=ic.particle_spacing)
+
+
+def local_systems(fluid, wall, layout: SlabLayout, rank: int):
+    """The rank's own systems: owned fluid particles, wall particles within reach of the slab.
+    Returns (fluid_k, wall_k, owned_index, wall_index) with indices into the global systems."""
+    x = fluid.initial_condition.coordinates[:, 0].astype(np.float64)
+    owned = np.nonzero(layout.owner(x) == rank)[0]
+    fluid_k = copy.copy(fluid)
+    fluid_k.initial_condition = subset_ic(fluid.initial_condition, owned)
+    fluid_k.mass = fluid.mass[owned].copy()
+    fluid_k.pressure = np.zeros(len(owned), dtype=fluid.eltype)
+    wall_k, widx = None, None
+    if wall is not None:
+        xw = wall.coordinates[:, 0].astype(np.float64)
+        lo, hi = layout.planes[rank] - layout.wall_reach, layout.planes[rank + 1] + layout.wall_reach
+        widx = np.nonzero((xw >= lo) & (xw <= hi))[0]
+        wall_k = copy.copy(wall)
+        wall_k.initial_condition = subset_ic(wall.initial_condition, widx)
+        wall_k.coordinates = wall_k.initial_condition.coordinates
+        model = copy.copy(wall.boundary_model)
+        model.initial_density = wall.boundary_model.initial_density[widx].copy()
+        model.hydrodynamic_mass = wall.boundary_model.hydrodynamic_mass[widx].copy()
+        model.pressure = np.zeros(len(widx), dtype=wall.eltype)
+        model.cache = dict(density=model.initial_density.copy(), volume=np.zeros(len(widx), dtype=wall.eltype))
+        wall_k.boundary_model = model
+    return fluid_k, wall_k, owned, widx
+
+
+# ------------------------------------------------------------------ transports
+class DistTransport:
+    """Neighbour exchange over torch.distributed point-to-point ops (NCCL on the box, gloo in
+    the CPU tests).  Counts travel first, then exactly-sized payloads."""
+
+    def __init__(self, rank: int, world: int, group=None):
+        self.rank, self.world, self.group = rank, world, group
+
+    def exchange(self, to_left, to_right):
+        import torch
+        import torch.distributed as dist
+        dev, dt, k = to_left.device, to_left.dtype, to_left.shape[1]
+        left = self.rank - 1 if self.rank > 0 else None
+        right = self.rank + 1 if self.rank < self.world - 1 else None
+        nsend = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=dev)
+        nrecv = torch.zeros(2, dtype=torch.int64, device=dev)
+        ops = []
+        if left is not None:
+            ops += [dist.P2POp(dist.isend, nsend[0:1], left, self.group),
+                    dist.P2POp(dist.irecv, nrecv[0:1], left, self.group)]
+        if right is not None:
+            ops += [dist.P2POp(dist.isend, nsend[1:2], right, self.group),
+                    dist.P2POp(dist.irecv, nrecv[1:2], right, self.group)]
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        n_l, n_r = (int(c) for c in nrecv.tolist())       # the one host sync of a kick
+        from_left = torch.empty((n_l, k), dtype=dt, device=dev)
+        from_right = torch.empty((n_r, k), dtype=dt, device=dev)
+        ops = []
+        if left is not None:
+            if to_left.shape[0]:
+                ops.append(dist.P2POp(dist.isend, to_left, left, self.group))
+            if n_l:
+                ops.append(dist.P2POp(dist.irecv, from_left, left, self.group))
+        if right is not None:
+            if to_right.shape[0]:
+                ops.append(dist.P2POp(dist.isend, to_right, right, self.group))
+            if n_r:
+                ops.append(dist.P2POp(dist.irecv, from_right, right, self.group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        return from_left, from_right
+
+
+class LocalMailbox:
+    """In-process stand-in for the interconnect: lets several slab ranks live in one process
+    (single-GPU tests).  All ranks `post`, then all ranks `collect`."""
+
+    def __init__(self, world: int):
+        self.world = world
+        self.box = {}
+
+    def transport(self, rank: int) -> "LocalTransport":
+        return LocalTransport(self, rank)
+
+
+class LocalTransport:
+    def __init__(self, mailbox: LocalMailbox, rank: int):
+        self.mb, self.rank, self.world = mailbox, rank, mailbox.world
+
+    def post(self, to_left, to_right):
+        if self.rank > 0:
+            self.mb.box[(self.rank, self.rank - 1)] = to_left
+        if self.rank < self.world - 1:
+            self.mb.box[(self.rank, self.rank + 1)] = to_right
+
+    def collect(self, like):
+        empty = like[:0]
+        from_left = self.mb.box.pop((self.rank - 1, self.rank), empty)
+        from_right = self.mb.box.pop((self.rank + 1, self.rank), empty)
+        return from_left, from_right
+
+
+# ------------------------------------------------------------------ halo selection + packing
+class HaloExchange:
+    """Selects and exchanges the ghost layer of one rank.  Works on torch tensors of any device:
+    u (n, ND) coordinates, v (n, NV) velocity + density, mass (n,).  Payload row =
+    (x[ND], v[NV], m), all converted to the coordinate dtype for transport when needed."""
+
+    def __init__(self, layout: SlabLayout, rank: int, transport):
+        self.layout, self.rank, self.transport = layout, rank, transport
+        self.lo, self.hi = float(layout.planes[rank]), float(layout.planes[rank + 1])
+
+    def select(self, u):
+        """Owned particles inside the left / right neighbour's ghost layer."""
+        import torch
+        x = u[:, 0]
+        if self.rank > 0:
+            idx_l = torch.nonzero(x < self.lo + self.layout.halo).squeeze(1)
+        else:
+            idx_l = torch.empty(0, dtype=torch.int64, device=u.device)
+        if self.rank < self.layout.world - 1:
+            idx_r = torch.nonzero(x >= self.hi - self.layout.halo).squeeze(1)
+        else:
+            idx_r = torch.empty(0, dtype=torch.int64, device=u.device)
+        return idx_l, idx_r
+
+    def check_drift(self, u) -> bool:
+        """True while every owned particle is within `skin` of its slab (else: rebalance)."""
+        x = u[:, 0]
+        ok = True
+        if self.rank > 0:
+            ok = ok and bool((x >= self.lo - self.layout.skin).all())
+        if self.rank < self.layout.world - 1:
+            ok = ok and bool((x < self.hi + self.layout.skin).all())
+        return ok
+
+    @staticmethod
+    def pack(u, v, mass, idx):
+        import torch
+        dt = u.dtype
+        return torch.cat([u.index_select(0, idx), v.index_select(0, idx).to(dt),
+                          mass.index_select(0, idx).to(dt).unsqueeze(1)], dim=1).contiguous()
+
+    @staticmethod
+    def unpack(payload, nd, nv, vdtype):
+        return (payload[:, :nd].contiguous(), payload[:, nd:nd + nv].to(vdtype).contiguous(),
+                payload[:, nd + nv].to(vdtype).contiguous())
+
+    def exchange(self, u, v, mass):
+        """Returns the ghosts (u_g, v_g, m_g) of this rank: left neighbour's first."""
+        import torch
+        nd, nv = u.shape[1], v.shape[1]
+        idx_l, idx_r = self.select(u)
+        to_l, to_r = self.pack(u, v, mass, idx_l), self.pack(u, v, mass, idx_r)
+        if isinstance(self.transport, LocalTransport):
+            raise RuntimeError("LocalTransport is two-phase: use post() / collect()")
+        from_l, from_r = self.transport.exchange(to_l, to_r)
+        return self.unpack(torch.cat([from_l, from_r], dim=0), nd, nv, v.dtype)
+
+    # two-phase form for the in-process transport
+    def post(self, u, v, mass):
+        idx_l, idx_r = self.select(u)
+        self.transport.post(self.pack(u, v, mass, idx_l), self.pack(u, v, mass, idx_r))
+
+    def collect(self, u, v):
+        import torch
+        like = torch.empty((0, u.shape[1] + v.shape[1] + 1), dtype=u.dtype, device=u.device)
+        from_l, from_r = self.transport.collect(like)
+        return self.unpack(torch.cat([from_l, from_r], dim=0), u.shape[1], v.shape[1], v.dtype)
+
+
+# ------------------------------------------------------------------ the per-rank GPU object
+class SlabSemidiscretization:
+    """One slab of `Semidiscretization(fluid, wall)` on one GPU.
+
+    `ode = slab.semidiscretize(tspan)` returns the rank's part of the `DynamicalODEProblem`:
+    `ode.u0` / `ode.v0` are the owned particles (torch CUDA tensors, views of the extended
+    buffers that also hold the ghosts), `ode.f1` = kick!, `ode.f2` = drift!."""
+
+    def __init__(self, fluid, wall, *, rank: int, world: int, device: int = 0, transport=None,
+                 skin: Optional[float] = None, ghost_capacity: Optional[int] = None,
+                 interact_variant: int = 0):
+        import torch
+        from . import _lib
+        from .semidiscretization import (B200Backend, FullGridCellList, GridNeighborhoodSearch,
+                                         Semidiscretization)
+        self.rank, self.world = rank, world
+        self.global_n_fluid = fluid.nparticles
+        t = fluid.eltype.type
+        R_f = float(t(2) * fluid.smoothing_length)
+        R_w = float(t(2) * wall.boundary_model.smoothing_length) if wall is not None else R_f
+        self.layout = make_layout(fluid.initial_condition.coordinates[:, 0], world, R_f, R_w, skin)
+        self.fluid, self.wall, self.owned_index, self.wall_index = local_systems(fluid, wall, self.layout, rank)
+        self.n_owned = self.fluid.nparticles
+        nd = fluid.ndims
+        # ghost capacity: 1.5 x the initial ghost count of this rank + slack
+        x = fluid.initial_condition.coordinates[:, 0].astype(np.float64)
+        lo, hi = self.layout.planes[rank], self.layout.planes[rank + 1]
+        n_ghost0 = int(((x >= lo - self.layout.halo) & (x < hi + self.layout.halo)).sum()) - self.n_owned
+        self.ghost_capacity = int(ghost_capacity if ghost_capacity is not None else 1.5 * n_ghost0 + 4096)
+        if world == 1:
+            self.ghost_capacity = 0
+        # bounding box of the rank: slab + ghost layer in x, the whole tank in y, z
+        allc = [fluid.initial_condition.coordinates.astype(np.float64)]
+        if wall is not None:
+            allc.append(wall.coordinates.astype(np.float64))
+        allc = np.concatenate(allc)
+        gmin, gmax = allc.min(axis=0) - 2 * max(R_f, R_w), allc.max(axis=0) + 2 * max(R_f, R_w)
+        pad = self.layout.halo + max(R_f, R_w)
+        mn, mx = gmin.copy(), gmax.copy()
+        mn[0] = max(gmin[0], lo - pad) if np.isfinite(lo) else gmin[0]
+        mx[0] = min(gmax[0], hi + pad) if np.isfinite(hi) else gmax[0]
+        nhs = GridNeighborhoodSearch(nd, cell_list=FullGridCellList(min_corner=mn, max_corner=mx))
+        backend = B200Backend(device=device, ode_memory="device", interact_variant=interact_variant)
+        backend.ghost_capacity = self.ghost_capacity
+        systems = (self.fluid,) if self.wall is None else (self.fluid, self.wall)
+        self.semi = Semidiscretization(*systems, neighborhood_search=nhs, parallelization_backend=backend)
+        self.device = torch.device("cuda", device)
+        self.transport = transport if transport is not None else DistTransport(rank, world)
+        self.halo = HaloExchange(self.layout, rank, self.transport)
+        self.nd, self.nv = nd, self.fluid.v_nvariables
+        self._lib = _lib
+        self.n_ghost = 0
+
+    # -- setup ---------------------------------------------------------------------------
+    def semidiscretize(self, tspan):
+        import torch
+        from .semidiscretization import DynamicalODEProblem, semidiscretize
+        ode0 = semidiscretize(self.semi, tspan)        # creates the handle with capacity
+        cap = self.n_owned + self.ghost_capacity
+        cdt, vdt = ode0.u0.dtype, ode0.v0.dtype
+        self.u_ext = torch.zeros((cap, self.nd), dtype=cdt, device=self.device)
+        self.v_ext = torch.zeros((cap, self.nv), dtype=vdt, device=self.device)
+        self.u_ext[: self.n_owned] = ode0.u0.view(self.n_owned, self.nd)
+        self.v_ext[: self.n_owned] = ode0.v0.view(self.n_owned, self.nv)
+        self.mass = torch.from_numpy(np.ascontiguousarray(self.fluid.mass)).to(self.device)
+        u0 = self.u_ext[: self.n_owned].view(-1)
+        v0 = self.v_ext[: self.n_owned].view(-1)
+        return DynamicalODEProblem(self.kick_, self.drift_, v0, u0, tuple(tspan), SimpleNamespace(semi=self))
+
+    def close(self):
+        self.semi.close()
+
+    # -- per kick ------------------------------------------------------------------------
+    def _stage_owned(self, v_ode, u_ode):
+        """Owned rows into the extended buffers (no copy when the caller works on the views)."""
+        if u_ode.data_ptr() != self.u_ext.data_ptr():
+            self.u_ext[: self.n_owned].copy_(u_ode.view(self.n_owned, self.nd))
+        if v_ode.data_ptr() != self.v_ext.data_ptr():
+            self.v_ext[: self.n_owned].copy_(v_ode.view(self.n_owned, self.nv))
+
+    def _install_ghosts(self, ghosts):
+        u_g, v_g, m_g = ghosts
+        n_g = u_g.shape[0]
+        if n_g > self.ghost_capacity:
+            raise RuntimeError(f"rank {self.rank}: {n_g} ghosts exceed the capacity {self.ghost_capacity}")
+        n0 = self.n_owned
+        L, h = self._lib.load(), self.semi._handle
+        if n_g:
+            self.u_ext[n0:n0 + n_g] = u_g
+            self.v_ext[n0:n0 + n_g] = v_g
+            self.semi._bind_stream()
+            self._lib.check(h, L.tpb_set_fluid_mass(h, n0, n_g, C.c_void_p(m_g.data_ptr())))
+        self._lib.check(h, L.tpb_set_fluid_count(h, n0 + n_g, n0))
+        self.n_ghost = n_g
+
+    def _compute(self, dv_ode, t):
+        L, h = self._lib.load(), self.semi._handle
+        self.semi._bind_stream()
+        self._lib.check(h, L.tpb_kick(h, C.c_void_p(dv_ode.data_ptr()), C.c_void_p(self.v_ext.data_ptr()),
+                                      C.c_void_p(self.u_ext.data_ptr()), float(t)))
+
+    def kick_(self, dv_ode, v_ode, u_ode, p, t):
+        self._stage_owned(v_ode, u_ode)
+        if self.world > 1:
+            u, v = self.u_ext[: self.n_owned], self.v_ext[: self.n_owned]
+            self._install_ghosts(self.halo.exchange(u, v, self.mass))
+        self._compute(dv_ode, t)
+        return dv_ode
+
+    # two-phase form (LocalTransport): all ranks post, then all ranks finish
+    def kick_post(self, v_ode, u_ode):
+        self._stage_owned(v_ode, u_ode)
+        self.halo.post(self.u_ext[: self.n_owned], self.v_ext[: self.n_owned], self.mass)
+
+    def kick_finish(self, dv_ode, t=0.0):
+        self._install_ghosts(self.halo.collect(self.u_ext[: self.n_owned], self.v_ext[: self.n_owned]))
+        self._compute(dv_ode, t)
+        return dv_ode
+
+    def drift_(self, du_ode, v_ode, u_ode, p, t):
+        L, h = self._lib.load(), self.semi._handle
+        self.semi._bind_stream()
+        self._lib.check(h, L.tpb_drift(h, C.c_void_p(du_ode.data_ptr()), C.c_void_p(v_ode.data_ptr()),
+                                       C.c_void_p(u_ode.data_ptr()), float(t)))
+        return du_ode
+
+    def needs_rebalance(self, u_ode) -> bool:
+        return not self.halo.check_drift(u_ode.view(self.n_owned, self.nd))
