@@ -203,12 +203,12 @@ struct Ops {
     static constexpr int nv(const Semi &s) { return s.fp.density_calculator == TPB_DENSITY_SUMMATION ? ND : ND + 1; }
 
     // ---- counting sort of one point set into the shared grid: key/slot/count/scan/scatter
-    static int bin_points(Semi &s, const CT *d_coords, int n, int *d_cell_start)
+    static int bin_points(Semi &s, const CT *d_coords, int n, int n_targets, int *d_cell_start)
     {
         GridConst<CT> g = make_grid_const<CT>(s);
         CUDA_TRY(&s, cudaMemsetAsync(s.d_count, 0, sizeof(int) * (size_t)s.ncells, s.stream));
         if (n > 0)
-            LAUNCH(s, (k_cell_count<ND, CT>), cdiv(n, 256), 256, 0, d_coords, n, g, s.d_key,
+            LAUNCH(s, (k_cell_count<ND, CT>), cdiv(n, 256), 256, 0, d_coords, n, n_targets, g, s.d_key,
                    s.d_slot, s.d_count, s.d_flags);
         int rc = exclusive_scan(s, s.d_count, (int)s.ncells, d_cell_start);
         if (rc) return rc;
@@ -222,7 +222,7 @@ struct Ops {
     static int rebuild_fluid(Semi &s, const CT *d_u, const T *d_v)
     {
         int n = (int)s.n_act;
-        int rc = bin_points(s, d_u, n, s.d_fcell_start);
+        int rc = bin_points(s, d_u, n, (int)s.n_tgt, s.d_fcell_start);
         if (rc) return rc;
         EosConst<T> eos = make_eos_const<T>(s.fp.sound_speed, s.fp.exponent, s.fp.reference_density,
                                             s.fp.background_pressure, s.fp.clip_negative_pressure);
@@ -230,12 +230,12 @@ struct Ops {
             if (s.fp.density_calculator == TPB_DENSITY_CONTINUITY)
                 LAUNCH(s, (k_reorder_fluid<ND, T, CT, 0>), cdiv(n, 256), 256, 0, d_u, d_v,
                        (const T *)s.d_mass_f, s.d_key, s.d_fcell_start, s.d_tmp_perm, n,
-                       s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
+                       s.d_fcell_start + s.ncells, s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
                        s.d_perm_f);
             else
                 LAUNCH(s, (k_reorder_fluid<ND, T, CT, 1>), cdiv(n, 256), 256, 0, d_u, d_v,
                        (const T *)s.d_mass_f, s.d_key, s.d_fcell_start, s.d_tmp_perm, n,
-                       s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
+                       s.d_fcell_start + s.ncells, s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
                        s.d_perm_f);
         }
         if (use_tiles(s))
@@ -258,7 +258,7 @@ struct Ops {
                                      cudaMemcpyHostToDevice, s.stream));
         CUDA_TRY(&s, cudaMemcpyAsync(d_dens, s.h_dens_w.data(), sizeof(T) * (size_t)n,
                                      cudaMemcpyHostToDevice, s.stream));
-        int rc = bin_points(s, d_coords, n, s.d_wcell_start);
+        int rc = bin_points(s, d_coords, n, n, s.d_wcell_start);
         if (rc) return rc;
         if (n > 0)
             LAUNCH(s, (k_reorder_wall<ND, T, CT>), cdiv(n, 256), 256, 0, d_coords, d_mass, d_dens,
@@ -476,24 +476,25 @@ struct Ops {
     static int get_field(Semi &s, int system, int field, void *out, int64_t n)
     {
         T *scratch = (T *)s.d_scratch;
+        CUDA_TRY(&s, cudaMemsetAsync(scratch, 0, sizeof(T) * (size_t)std::max<int64_t>(n, 1), s.stream));
         if (system == s.fluid_index) {
             if (n != s.n_act) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
             if (n == 0) return TPB_OK;
             if (field == TPB_FIELD_PRESSURE)
-                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_perm_f, (const T *)s.d_P, 1, 0, scratch);
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_fcell_start + s.ncells, s.d_perm_f, (const T *)s.d_P, 1, 0, scratch);
             else if (field == TPB_FIELD_DENSITY)
-                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_perm_f, (const T *)s.d_B, 4, 3, scratch);
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_fcell_start + s.ncells, s.d_perm_f, (const T *)s.d_B, 4, 3, scratch);
             else
                 return fail(&s, TPB_ERR_INVALID_ARGUMENT, "unknown fluid field");
         } else if (system == s.wall_index) {
             if (n != s.n_w) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
             if (n == 0) return TPB_OK;
             if (field == TPB_FIELD_PRESSURE)
-                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_perm_w, (const T *)s.d_Ww, 2, 0, scratch);
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_wcell_start + s.ncells, s.d_perm_w, (const T *)s.d_Ww, 2, 0, scratch);
             else if (field == TPB_FIELD_DENSITY)
-                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_perm_w, (const T *)s.d_Ww, 2, 1, scratch);
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_wcell_start + s.ncells, s.d_perm_w, (const T *)s.d_Ww, 2, 1, scratch);
             else if (field == TPB_FIELD_VOLUME)
-                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_perm_w, (const T *)s.d_volw, 1, 0, scratch);
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_wcell_start + s.ncells, s.d_perm_w, (const T *)s.d_volw, 1, 0, scratch);
             else
                 return fail(&s, TPB_ERR_INVALID_ARGUMENT, "unknown wall field");
         } else {
@@ -549,7 +550,8 @@ struct Ops {
                    (const V4<CT> *)(y_fluid ? s.d_A : s.d_Aw), y_fluid ? s.d_perm_f : s.d_perm_w, r2,
                    (long long)capacity, d_oi, d_oj, d_counter, cap, s.tiles.list_len);
         } else if (n_x > 0)
-            LAUNCH(s, (k_pairs<ND, T, CT>), cdiv(n_x, 128), 128, 0, n_x, g,
+            LAUNCH(s, (k_pairs<ND, T, CT>), cdiv(n_x, 128), 128, 0, n_x,
+                   (x_fluid ? s.d_fcell_start : s.d_wcell_start) + s.ncells, g,
                    (const V4<CT> *)(x_fluid ? s.d_A : s.d_Aw), x_fluid ? s.d_perm_f : s.d_perm_w,
                    y_fluid ? s.d_fcell_start : s.d_wcell_start,
                    (const V4<CT> *)(y_fluid ? s.d_A : s.d_Aw), y_fluid ? s.d_perm_f : s.d_perm_w, r2,

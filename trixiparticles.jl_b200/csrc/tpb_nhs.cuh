@@ -20,13 +20,18 @@ namespace tpb {
 // ------------------------------------------------------------------ cell keys + histogram
 template <int ND, typename CT>
 __global__ void __launch_bounds__(256)
-k_cell_count(const CT *__restrict__ coords /* ND x n, AoS */, int n, GridConst<CT> g,
+k_cell_count(const CT *__restrict__ coords /* ND x n, AoS */, int n, int n_targets, GridConst<CT> g,
              int *__restrict__ key, int *__restrict__ slot, int *__restrict__ count,
              int *__restrict__ flags)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     CT x = coords[(int64_t)i * ND + 0];
+    if (i >= n_targets && !(x == x)) {  // empty slab-ghost slot (NaN x): not binned, not an error
+        key[i] = -1;
+        slot[i] = 0;
+        return;
+    }
     CT y = coords[(int64_t)i * ND + 1];
     CT z = ND == 3 ? coords[(int64_t)i * ND + 2] : (CT)0;
     int cx, cy, cz;
@@ -141,6 +146,7 @@ k_scatter(const int *__restrict__ key, const int *__restrict__ slot,
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (key[i] < 0) return;  // empty slab-ghost slot
     tmp_perm[cell_start[key[i]] + slot[i]] = i;
 }
 
@@ -160,13 +166,13 @@ template <int ND, typename T, typename CT, int DENS>
 __global__ void __launch_bounds__(256)
 k_reorder_fluid(const CT *__restrict__ u, const T *__restrict__ v, const T *__restrict__ mass,
                 const int *__restrict__ key, const int *__restrict__ cell_start,
-                const int *__restrict__ tmp_perm, int n, int deterministic, EosConst<T> eos,
-                V4<CT> *__restrict__ A, V4<T> *__restrict__ B, T *__restrict__ P,
-                int *__restrict__ perm)
+                const int *__restrict__ tmp_perm, int n, const int *__restrict__ n_sorted,
+                int deterministic, EosConst<T> eos, V4<CT> *__restrict__ A, V4<T> *__restrict__ B,
+                T *__restrict__ P, int *__restrict__ perm)
 {
     constexpr int NV = DENS == 0 ? ND + 1 : ND;
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    if (s >= n || s >= *n_sorted) return;  // n_sorted < n when ghost slots are empty
     int i = tmp_perm[s];
     int dst = s;
     if (deterministic) {

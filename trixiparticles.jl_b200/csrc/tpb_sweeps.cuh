@@ -35,14 +35,14 @@ __device__ __forceinline__ void for_neighbor_rows(const GridConst<CT> &g,
 // ------------------------------------------------------------------ summation density
 template <int ND, typename T, typename CT, int KERNEL>
 __global__ void __launch_bounds__(128)
-k_summation_density(int n_f, GridConst<CT> g, const int *__restrict__ fcell_start,
+k_summation_density(int n_f_cap, GridConst<CT> g, const int *__restrict__ fcell_start,
                     const V4<CT> *__restrict__ A, int has_wall,
                     const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
                     int wall_enabled, KernelConst<T> kern, T radius2, EosConst<T> eos,
                     V4<T> *__restrict__ B, T *__restrict__ P)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_f) return;
+    if (s >= n_f_cap || s >= fcell_start[g.ncells]) return;
     const V4<CT> xi = A[s];
     int cx, cy, cz;
     cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
@@ -145,7 +145,7 @@ k_interact_pp(int n_f, GridConst<CT> g, const int *__restrict__ fcell_start,
 {
     constexpr int NV = DENS == 0 ? ND + 1 : ND;
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_f) return;
+    if (s >= n_f || s >= fcell_start[g.ncells]) return;
     if (perm[s] >= n_targets) return;  // slab ghost: neighbour only
     const V4<CT> xi = A[s];
     const V4<T> bi = B[s];
@@ -227,13 +227,14 @@ k_drift(int64_t n_total /* n_f * ND */, int nv, const T *__restrict__ v, CT *__r
 // Test hook behind tpb_neighbor_pairs: appends (orig_i, orig_j) for every accepted pair.
 template <int ND, typename T, typename CT>
 __global__ void __launch_bounds__(128)
-k_pairs(int n_x, GridConst<CT> g, const V4<CT> *__restrict__ X, const int *__restrict__ perm_x,
+k_pairs(int n_x, const int *__restrict__ n_sorted_x, GridConst<CT> g, const V4<CT> *__restrict__ X,
+        const int *__restrict__ perm_x,
         const int *__restrict__ ycell_start, const V4<CT> *__restrict__ Y,
         const int *__restrict__ perm_y, T radius2, long long capacity, int *__restrict__ out_i,
         int *__restrict__ out_j, unsigned long long *__restrict__ counter)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_x) return;
+    if (s >= n_x || s >= *n_sorted_x) return;
     const V4<CT> xi = X[s];
     int cx, cy, cz;
     cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
@@ -255,11 +256,11 @@ k_pairs(int n_x, GridConst<CT> g, const V4<CT> *__restrict__ X, const int *__res
 // scatter a sorted per-particle field back to the system's own particle order
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_unsort_scalar(int n, const int *__restrict__ perm, const T *__restrict__ sorted, int stride,
-                int offset, T *__restrict__ out)
+k_unsort_scalar(int n, const int *__restrict__ n_sorted, const int *__restrict__ perm,
+                const T *__restrict__ sorted, int stride, int offset, T *__restrict__ out)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    if (s >= n || s >= *n_sorted) return;
     out[perm[s]] = sorted[(int64_t)s * stride + offset];
 }
 

@@ -4,12 +4,14 @@ The reference has no distributed path at all; this 
 design for it.  One process per GPU owns the fluid particles of one slab `[x_k, x_{k+1})`.  Per
 `kick!`:
 
-  1. every rank selects its owned particles that lie within `halo` of a slab face and sends
-     `(x, v, rho, m)` to that neighbour (NCCL send/recv over NVLink; counts first, then the
-     payload -- one small host sync per kick);
-  2. the received ghosts are appended behind the owned particles in the rank's extended
-     `u`/`v` buffers and `tpb_set_fluid_count(n_owned + n_ghost, n_owned)` tells the library that
-     the tail is neighbours-only;
+  1. every rank sends one fixed-size message `(x, v, rho)` per slab face (NCCL send/recv over
+     NVLink): a row per *candidate* particle (owned, within `halo + skin` of the face when the
+     partition was made); candidates currently outside the neighbour's ghost layer carry
+     `x = NaN`.  Sizes and slot order are fixed between rebalances, masses travel once -- no
+     host synchronisation, deterministic summation order;
+  2. the received rows land behind the owned particles in the rank's extended `u`/`v` buffers;
+     `tpb_set_fluid_count(n_owned + n_slots, n_owned)` (once) told the library that the tail is
+     neighbours-only and that NaN rows there are empty slots;
   3. `tpb_kick` runs the usual rebuild + Adami + interact on the local set.
 
 `halo = R_fluid + R_wall + skin`: a wall particle within `R_fluid` of an owned fluid particle needs
@@ -113,48 +115,56 @@ def local_systems(fluid, wall, layout: SlabLayout, rank: int):
 
 # ------------------------------------------------------------------ transports
 class DistTransport:
-    """Neighbour exchange over torch.distributed point-to-point ops (NCCL on the box, gloo in
-    the CPU tests).  Counts travel first, then exactly-sized payloads."""
+    """Neighbour exchange over torch.distributed point-to-point ops (NCCL over NVLink on the
+    box, gloo in the CPU tests)."""
 
     def __init__(self, rank: int, world: int, group=None):
         self.rank, self.world, self.group = rank, world, group
+        self.left = rank - 1 if rank > 0 else None
+        self.right = rank + 1 if rank < world - 1 else None
 
-    def exchange(self, to_left, to_right):
+    def _run(self, ops):
+        import torch.distributed as dist
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+
+    def exchange_var(self, to_left, to_right):
+        """Setup-time exchange of variable-size messages (counts first; host sync)."""
         import torch
         import torch.distributed as dist
         dev, dt, k = to_left.device, to_left.dtype, to_left.shape[1]
-        left = self.rank - 1 if self.rank > 0 else None
-        right = self.rank + 1 if self.rank < self.world - 1 else None
         nsend = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=dev)
         nrecv = torch.zeros(2, dtype=torch.int64, device=dev)
         ops = []
-        if left is not None:
-            ops += [dist.P2POp(dist.isend, nsend[0:1], left, self.group),
-                    dist.P2POp(dist.irecv, nrecv[0:1], left, self.group)]
-        if right is not None:
-            ops += [dist.P2POp(dist.isend, nsend[1:2], right, self.group),
-                    dist.P2POp(dist.irecv, nrecv[1:2], right, self.group)]
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
-        n_l, n_r = (int(c) for c in nrecv.tolist())       # the one host sync of a kick
+        if self.left is not None:
+            ops += [dist.P2POp(dist.isend, nsend[0:1], self.left, self.group),
+                    dist.P2POp(dist.irecv, nrecv[0:1], self.left, self.group)]
+        if self.right is not None:
+            ops += [dist.P2POp(dist.isend, nsend[1:2], self.right, self.group),
+                    dist.P2POp(dist.irecv, nrecv[1:2], self.right, self.group)]
+        self._run(ops)
+        n_l, n_r = (int(c) for c in nrecv.tolist())
         from_left = torch.empty((n_l, k), dtype=dt, device=dev)
         from_right = torch.empty((n_r, k), dtype=dt, device=dev)
-        ops = []
-        if left is not None:
-            if to_left.shape[0]:
-                ops.append(dist.P2POp(dist.isend, to_left, left, self.group))
-            if n_l:
-                ops.append(dist.P2POp(dist.irecv, from_left, left, self.group))
-        if right is not None:
-            if to_right.shape[0]:
-                ops.append(dist.P2POp(dist.isend, to_right, right, self.group))
-            if n_r:
-                ops.append(dist.P2POp(dist.irecv, from_right, right, self.group))
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
+        self.exchange_fixed(to_left, to_right, from_left, from_right)
         return from_left, from_right
+
+    def exchange_fixed(self, to_left, to_right, from_left, from_right):
+        """Per-kick exchange: all four message sizes are known, nothing touches the host."""
+        import torch.distributed as dist
+        ops = []
+        if self.left is not None:
+            if to_left.shape[0]:
+                ops.append(dist.P2POp(dist.isend, to_left, self.left, self.group))
+            if from_left.shape[0]:
+                ops.append(dist.P2POp(dist.irecv, from_left, self.left, self.group))
+        if self.right is not None:
+            if to_right.shape[0]:
+                ops.append(dist.P2POp(dist.isend, to_right, self.right, self.group))
+            if from_right.shape[0]:
+                ops.append(dist.P2POp(dist.irecv, from_right, self.right, self.group))
+        self._run(ops)
 
 
 class LocalMailbox:
@@ -170,89 +180,123 @@ class LocalMailbox:
 
 
 class LocalTransport:
+    two_phase = True
+
     def __init__(self, mailbox: LocalMailbox, rank: int):
         self.mb, self.rank, self.world = mailbox, rank, mailbox.world
 
-    def post(self, to_left, to_right):
+    def post(self, to_left, to_right, tag=""):
         if self.rank > 0:
-            self.mb.box[(self.rank, self.rank - 1)] = to_left
+            self.mb.box[(tag, self.rank, self.rank - 1)] = to_left.clone()
         if self.rank < self.world - 1:
-            self.mb.box[(self.rank, self.rank + 1)] = to_right
+            self.mb.box[(tag, self.rank, self.rank + 1)] = to_right.clone()
 
-    def collect(self, like):
+    def collect(self, like, tag=""):
         empty = like[:0]
-        from_left = self.mb.box.pop((self.rank - 1, self.rank), empty)
-        from_right = self.mb.box.pop((self.rank + 1, self.rank), empty)
+        from_left = self.mb.box.pop((tag, self.rank - 1, self.rank), empty)
+        from_right = self.mb.box.pop((tag, self.rank + 1, self.rank), empty)
         return from_left, from_right
 
 
 # ------------------------------------------------------------------ halo selection + packing
 class HaloExchange:
-    """Selects and exchanges the ghost layer of one rank.  Works on torch tensors of any device:
-    u (n, ND) coordinates, v (n, NV) velocity + density, mass (n,).  Payload row =
-    (x[ND], v[NV], m), all converted to the coordinate dtype for transport when needed."""
+    """Fixed-slot ghost exchange of one rank (no host synchronisation per kick).
+
+    At `setup` (semidiscretize / rebalance) every rank fixes its *candidate* lists: the owned
+    particles within `halo + skin` of a slab face -- a superset of whatever can be inside the
+    neighbour's ghost layer until the next rebalance.  Every kick it sends one row
+    `(x[ND], v[NV])` per candidate; candidates currently outside the ghost layer get `x = NaN`,
+    which the library treats as an empty ghost slot.  Message sizes, slot order (and therefore
+    the summation order on the receiving rank) are fixed; masses travel once, at setup.
+    Works on torch tensors of any device: u (n, ND) coordinates, v (n, NV) velocity + density."""
 
     def __init__(self, layout: SlabLayout, rank: int, transport):
         self.layout, self.rank, self.transport = layout, rank, transport
         self.lo, self.hi = float(layout.planes[rank]), float(layout.planes[rank + 1])
+        self.has_left, self.has_right = rank > 0, rank < layout.world - 1
+        self.ready = False
 
-    def select(self, u):
-        """Owned particles inside the left / right neighbour's ghost layer."""
+    # -- setup -----------------------------------------------------------------------------
+    def candidates(self, u):
         import torch
         x = u[:, 0]
-        if self.rank > 0:
-            idx_l = torch.nonzero(x < self.lo + self.layout.halo).squeeze(1)
+        reach = self.layout.halo + self.layout.skin
+        empty = torch.empty(0, dtype=torch.int64, device=u.device)
+        cand_l = torch.nonzero(x < self.lo + reach).squeeze(1) if self.has_left else empty
+        cand_r = torch.nonzero(x >= self.hi - reach).squeeze(1) if self.has_right else empty
+        return cand_l, cand_r
+
+    def setup_post(self, u, mass):
+        self.cand_l, self.cand_r = self.candidates(u)
+        self._m_l = mass.index_select(0, self.cand_l).unsqueeze(1).contiguous()
+        self._m_r = mass.index_select(0, self.cand_r).unsqueeze(1).contiguous()
+        if getattr(self.transport, "two_phase", False):
+            self.transport.post(self._m_l, self._m_r, tag="mass")
+
+    def setup_finish(self, u, v):
+        import torch
+        if getattr(self.transport, "two_phase", False):
+            m_l, m_r = self.transport.collect(self._m_l, tag="mass")
         else:
-            idx_l = torch.empty(0, dtype=torch.int64, device=u.device)
-        if self.rank < self.layout.world - 1:
-            idx_r = torch.nonzero(x >= self.hi - self.layout.halo).squeeze(1)
-        else:
-            idx_r = torch.empty(0, dtype=torch.int64, device=u.device)
-        return idx_l, idx_r
+            m_l, m_r = self.transport.exchange_var(self._m_l, self._m_r)
+        self.ghost_mass = torch.cat([m_l, m_r], dim=0).squeeze(1).contiguous()
+        self.n_from_l, self.n_from_r = m_l.shape[0], m_r.shape[0]
+        k = u.shape[1] + v.shape[1]
+        self.recv_l = torch.empty((self.n_from_l, k), dtype=u.dtype, device=u.device)
+        self.recv_r = torch.empty((self.n_from_r, k), dtype=u.dtype, device=u.device)
+        self.ready = True
+
+    def setup(self, u, v, mass):
+        self.setup_post(u, mass)
+        self.setup_finish(u, v)
+
+    @property
+    def n_ghost_slots(self) -> int:
+        return self.n_from_l + self.n_from_r
+
+    # -- per kick --------------------------------------------------------------------------
+    def pack(self, u, v):
+        """Rows (x, v) of the candidates; x[0] = NaN marks a candidate outside the ghost layer."""
+        import torch
+        out = []
+        for cand, keep in ((self.cand_l, lambda x: x < self.lo + self.layout.halo),
+                           (self.cand_r, lambda x: x >= self.hi - self.layout.halo)):
+            rows = torch.cat([u.index_select(0, cand), v.index_select(0, cand).to(u.dtype)], dim=1)
+            x = rows[:, 0]
+            rows[:, 0] = torch.where(keep(x), x, torch.full_like(x, float("nan")))
+            out.append(rows)
+        return out
 
     def check_drift(self, u) -> bool:
         """True while every owned particle is within `skin` of its slab (else: rebalance)."""
         x = u[:, 0]
         ok = True
-        if self.rank > 0:
+        if self.has_left:
             ok = ok and bool((x >= self.lo - self.layout.skin).all())
-        if self.rank < self.layout.world - 1:
+        if self.has_right:
             ok = ok and bool((x < self.hi + self.layout.skin).all())
         return ok
 
-    @staticmethod
-    def pack(u, v, mass, idx):
-        import torch
-        dt = u.dtype
-        return torch.cat([u.index_select(0, idx), v.index_select(0, idx).to(dt),
-                          mass.index_select(0, idx).to(dt).unsqueeze(1)], dim=1).contiguous()
+    def exchange(self, u, v):
+        """Returns (u_g, v_g): one row per ghost slot (left neighbour's first)."""
+        to_l, to_r = self.pack(u, v)
+        self.transport.exchange_fixed(to_l, to_r, self.recv_l, self.recv_r)
+        return self._unpack(u, v)
 
-    @staticmethod
-    def unpack(payload, nd, nv, vdtype):
-        return (payload[:, :nd].contiguous(), payload[:, nd:nd + nv].to(vdtype).contiguous(),
-                payload[:, nd + nv].to(vdtype).contiguous())
-
-    def exchange(self, u, v, mass):
-        """Returns the ghosts (u_g, v_g, m_g) of this rank: left neighbour's first."""
-        import torch
-        nd, nv = u.shape[1], v.shape[1]
-        idx_l, idx_r = self.select(u)
-        to_l, to_r = self.pack(u, v, mass, idx_l), self.pack(u, v, mass, idx_r)
-        if isinstance(self.transport, LocalTransport):
-            raise RuntimeError("LocalTransport is two-phase: use post() / collect()")
-        from_l, from_r = self.transport.exchange(to_l, to_r)
-        return self.unpack(torch.cat([from_l, from_r], dim=0), nd, nv, v.dtype)
-
-    # two-phase form for the in-process transport
-    def post(self, u, v, mass):
-        idx_l, idx_r = self.select(u)
-        self.transport.post(self.pack(u, v, mass, idx_l), self.pack(u, v, mass, idx_r))
+    def post(self, u, v):
+        to_l, to_r = self.pack(u, v)
+        self.transport.post(to_l, to_r, tag="halo")
 
     def collect(self, u, v):
+        fl, fr = self.transport.collect(self.recv_l, tag="halo")
+        self.recv_l, self.recv_r = fl, fr
+        return self._unpack(u, v)
+
+    def _unpack(self, u, v):
         import torch
-        like = torch.empty((0, u.shape[1] + v.shape[1] + 1), dtype=u.dtype, device=u.device)
-        from_l, from_r = self.transport.collect(like)
-        return self.unpack(torch.cat([from_l, from_r], dim=0), u.shape[1], v.shape[1], v.dtype)
+        nd, nv = u.shape[1], v.shape[1]
+        both = torch.cat([self.recv_l, self.recv_r], dim=0)
+        return both[:, :nd], both[:, nd:nd + nv].to(v.dtype)
 
 
 # ------------------------------------------------------------------ the per-rank GPU object
@@ -279,11 +323,13 @@ class SlabSemidiscretization:
         self.fluid, self.wall, self.owned_index, self.wall_index = local_systems(fluid, wall, self.layout, rank)
         self.n_owned = self.fluid.nparticles
         nd = fluid.ndims
-        # ghost capacity: 1.5 x the initial ghost count of this rank + slack
+        # ghost slots = the neighbours' candidate counts (particles within halo + skin of the
+        # faces): computed from the global lattice here, confirmed by the setup exchange
         x = fluid.initial_condition.coordinates[:, 0].astype(np.float64)
         lo, hi = self.layout.planes[rank], self.layout.planes[rank + 1]
-        n_ghost0 = int(((x >= lo - self.layout.halo) & (x < hi + self.layout.halo)).sum()) - self.n_owned
-        self.ghost_capacity = int(ghost_capacity if ghost_capacity is not None else 1.5 * n_ghost0 + 4096)
+        reach = self.layout.halo + self.layout.skin
+        n_slots = int(((x >= lo - reach) & (x < lo)).sum() + ((x >= hi) & (x < hi + reach)).sum())
+        self.ghost_capacity = int(ghost_capacity if ghost_capacity is not None else n_slots)
         if world == 1:
             self.ghost_capacity = 0
         # bounding box of the rank: slab + ghost layer in x, the whole tank in y, z
@@ -292,7 +338,7 @@ class SlabSemidiscretization:
             allc.append(wall.coordinates.astype(np.float64))
         allc = np.concatenate(allc)
         gmin, gmax = allc.min(axis=0) - 2 * max(R_f, R_w), allc.max(axis=0) + 2 * max(R_f, R_w)
-        pad = self.layout.halo + max(R_f, R_w)
+        pad = self.layout.halo + self.layout.skin + max(R_f, R_w)
         mn, mx = gmin.copy(), gmax.copy()
         mn[0] = max(gmin[0], lo - pad) if np.isfinite(lo) else gmin[0]
         mx[0] = min(gmax[0], hi + pad) if np.isfinite(hi) else gmax[0]
@@ -309,7 +355,7 @@ class SlabSemidiscretization:
         self.n_ghost = 0
 
     # -- setup ---------------------------------------------------------------------------
-    def semidiscretize(self, tspan):
+    def semidiscretize(self, tspan, finish=True):
         import torch
         from .semidiscretization import DynamicalODEProblem, semidiscretize
         ode0 = semidiscretize(self.semi, tspan)        # creates the handle with capacity
@@ -319,10 +365,30 @@ class SlabSemidiscretization:
         self.v_ext = torch.zeros((cap, self.nv), dtype=vdt, device=self.device)
         self.u_ext[: self.n_owned] = ode0.u0.view(self.n_owned, self.nd)
         self.v_ext[: self.n_owned] = ode0.v0.view(self.n_owned, self.nv)
+        self.u_ext[self.n_owned:, 0] = float("nan")    # empty ghost slots
         self.mass = torch.from_numpy(np.ascontiguousarray(self.fluid.mass)).to(self.device)
         u0 = self.u_ext[: self.n_owned].view(-1)
         v0 = self.v_ext[: self.n_owned].view(-1)
-        return DynamicalODEProblem(self.kick_, self.drift_, v0, u0, tuple(tspan), SimpleNamespace(semi=self))
+        self.ode = DynamicalODEProblem(self.kick_, self.drift_, v0, u0, tuple(tspan), SimpleNamespace(semi=self))
+        if self.world > 1:
+            self.halo.setup_post(self.u_ext[: self.n_owned], self.mass)
+            if finish:
+                self.setup_finish()
+        return self.ode
+
+    def setup_finish(self):
+        """Second half of the setup exchange (separate only for the in-process transport)."""
+        n0 = self.n_owned
+        self.halo.setup_finish(self.u_ext[:n0], self.v_ext[:n0])
+        n_g = self.halo.n_ghost_slots
+        if n_g > self.ghost_capacity:
+            raise RuntimeError(f"rank {self.rank}: {n_g} ghost slots exceed the capacity {self.ghost_capacity}")
+        L, h = self._lib.load(), self.semi._handle
+        self.semi._bind_stream()
+        if n_g:
+            self._lib.check(h, L.tpb_set_fluid_mass(h, n0, n_g, C.c_void_p(self.halo.ghost_mass.data_ptr())))
+        self._lib.check(h, L.tpb_set_fluid_count(h, n0 + n_g, n0))
+        self.n_ghost = n_g
 
     def close(self):
         self.semi.close()
@@ -336,19 +402,11 @@ class SlabSemidiscretization:
             self.v_ext[: self.n_owned].copy_(v_ode.view(self.n_owned, self.nv))
 
     def _install_ghosts(self, ghosts):
-        u_g, v_g, m_g = ghosts
-        n_g = u_g.shape[0]
-        if n_g > self.ghost_capacity:
-            raise RuntimeError(f"rank {self.rank}: {n_g} ghosts exceed the capacity {self.ghost_capacity}")
-        n0 = self.n_owned
-        L, h = self._lib.load(), self.semi._handle
+        u_g, v_g = ghosts
+        n0, n_g = self.n_owned, self.n_ghost
         if n_g:
             self.u_ext[n0:n0 + n_g] = u_g
             self.v_ext[n0:n0 + n_g] = v_g
-            self.semi._bind_stream()
-            self._lib.check(h, L.tpb_set_fluid_mass(h, n0, n_g, C.c_void_p(m_g.data_ptr())))
-        self._lib.check(h, L.tpb_set_fluid_count(h, n0 + n_g, n0))
-        self.n_ghost = n_g
 
     def _compute(self, dv_ode, t):
         L, h = self._lib.load(), self.semi._handle
@@ -359,15 +417,15 @@ class SlabSemidiscretization:
     def kick_(self, dv_ode, v_ode, u_ode, p, t):
         self._stage_owned(v_ode, u_ode)
         if self.world > 1:
-            u, v = self.u_ext[: self.n_owned], self.v_ext[: self.n_owned]
-            self._install_ghosts(self.halo.exchange(u, v, self.mass))
+            n0 = self.n_owned
+            self._install_ghosts(self.halo.exchange(self.u_ext[:n0], self.v_ext[:n0]))
         self._compute(dv_ode, t)
         return dv_ode
 
     # two-phase form (LocalTransport): all ranks post, then all ranks finish
     def kick_post(self, v_ode, u_ode):
         self._stage_owned(v_ode, u_ode)
-        self.halo.post(self.u_ext[: self.n_owned], self.v_ext[: self.n_owned], self.mass)
+        self.halo.post(self.u_ext[: self.n_owned], self.v_ext[: self.n_owned])
 
     def kick_finish(self, dv_ode, t=0.0):
         self._install_ghosts(self.halo.collect(self.u_ext[: self.n_owned], self.v_ext[: self.n_owned]))
