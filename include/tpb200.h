@@ -183,6 +183,21 @@ int32_t tpb_synchronize(tpb_semi_t semi);
 int32_t tpb_set_stream(tpb_semi_t semi, void *stream);
 int32_t tpb_get_stats(tpb_semi_t semi, tpb_stats *out);
 
+/* ---- device ODE-vector algebra ----------------------------------------------------------------
+ * What a GPU-resident ODE-vector type binds for the integrator's broadcasts (the reference's
+ * CPU counterpart is `ThreadedBroadcastArray`, util.jl:183-303).  TPB_MEM_DEVICE handles only;
+ * pointers are device pointers, work is queued on the handle's stream. */
+/* y = a * x + b * y */
+int32_t tpb_vec_axpby(tpb_semi_t semi, int64_t n, int32_t eltype, double a, const void *x, double b, void *y);
+/* one 2N-storage Runge-Kutta stage: tmp = A * tmp + dt * rhs; state += B * tmp */
+int32_t tpb_vec_rk2n_stage(tpb_semi_t semi, int64_t n, int32_t eltype, double A, double B, double dt,
+                           const void *rhs, void *tmp, void *state);
+int32_t tpb_vec_fill(tpb_semi_t semi, int64_t n, int32_t eltype, double value, void *x);
+/* max_k x[offset + k * stride], k < count, to the host (synchronises); `max_x_coord` of
+ * general/custom_quantities.jl is (count = nparticles, stride = ND, offset = 0) on u_ode */
+int32_t tpb_vec_strided_max(tpb_semi_t semi, int64_t count, int32_t eltype, int32_t stride, int32_t offset,
+                            const void *x, double *out_host);
+
 /* Phase timing of `tpb_kick` with CUDA events on the handle's stream (the reference's
  * TimerOutputs sections "update systems and nhs" / "system interaction",
  * semidiscretization.jl:596-606).  `tpb_set_profiling(max_kicks)` arms recording for the next

@@ -23,6 +23,7 @@ EXPORTS = [
     "tpb_synchronize", "tpb_set_stream", "tpb_get_stats", "tpb_host_register",
     "tpb_host_unregister", "tpb_set_profiling", "tpb_get_phase_times",
     "tpb_set_fluid_count", "tpb_set_fluid_mass",
+    "tpb_vec_axpby", "tpb_vec_rk2n_stage", "tpb_vec_fill", "tpb_vec_strided_max",
 ]
 PHASES = ("rebuild", "density", "boundary", "interact")
 
@@ -113,6 +114,11 @@ def load():
     L.tpb_set_profiling.restype = i32; L.tpb_set_profiling.argtypes = [p, i32]
     L.tpb_get_phase_times.restype = i32
     L.tpb_get_phase_times.argtypes = [p, C.POINTER(d), C.POINTER(i32)]
+    L.tpb_vec_axpby.restype = i32; L.tpb_vec_axpby.argtypes = [p, i64, i32, d, p, d, p]
+    L.tpb_vec_rk2n_stage.restype = i32; L.tpb_vec_rk2n_stage.argtypes = [p, i64, i32, d, d, d, p, p, p]
+    L.tpb_vec_fill.restype = i32; L.tpb_vec_fill.argtypes = [p, i64, i32, d, p]
+    L.tpb_vec_strided_max.restype = i32
+    L.tpb_vec_strided_max.argtypes = [p, i64, i32, i32, i32, p, C.POINTER(d)]
     L.tpb_set_fluid_count.restype = i32; L.tpb_set_fluid_count.argtypes = [p, i64, i64]
     L.tpb_set_fluid_mass.restype = i32; L.tpb_set_fluid_mass.argtypes = [p, i64, i64, p]
     _lib = L

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -18,6 +19,7 @@
 #include "tpb_nhs.cuh"
 #include "tpb_sweeps.cuh"
 #include "tpb_tiles.cuh"
+#include "tpb_vec.cuh"
 
 using namespace tpb;
 
@@ -1005,6 +1007,76 @@ int32_t tpb_set_fluid_mass(tpb_semi_t semi, int64_t first, int64_t count, const 
                                                                     : cudaMemcpyHostToDevice,
                                 s->stream));
     if (s->cfg.ode_memory == TPB_MEM_HOST) CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    return TPB_OK;
+}
+
+// ---- device ODE-vector algebra (TPB_MEM_DEVICE handles; stream-ordered) -------------------
+namespace {
+int vec_check(Semi *s, int64_t n, int32_t eltype)
+{
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    if (s->cfg.ode_memory != TPB_MEM_DEVICE)
+        return fail(s, TPB_ERR_STATE, "tpb_vec_* need a TPB_MEM_DEVICE handle (device pointers)");
+    if (n < 0 || (eltype != TPB_F32 && eltype != TPB_F64)) return fail(s, TPB_ERR_INVALID_ARGUMENT, "bad vector length or eltype");
+    cudaError_t e = cudaSetDevice(s->cfg.device);
+    if (e != cudaSuccess) return fail(s, TPB_ERR_CUDA, cudaGetErrorString(e));
+    return TPB_OK;
+}
+inline int vec_grid(int64_t n) { return (int)std::min<int64_t>(std::max<int64_t>((n + 255) / 256, 1), 148 * 16); }
+}  // namespace
+
+int32_t tpb_vec_axpby(tpb_semi_t semi, int64_t n, int32_t eltype, double a, const void *x, double b, void *y)
+{
+    Semi *s = (Semi *)semi;
+    int rc = vec_check(s, n, eltype);
+    if (rc || n == 0) return rc;
+    if (eltype == TPB_F32) LAUNCH(*s, k_vec_axpby<float>, vec_grid(n), 256, 0, n, a, (const float *)x, b, (float *)y);
+    else LAUNCH(*s, k_vec_axpby<double>, vec_grid(n), 256, 0, n, a, (const double *)x, b, (double *)y);
+    CUDA_TRY(s, cudaGetLastError());
+    return TPB_OK;
+}
+
+int32_t tpb_vec_rk2n_stage(tpb_semi_t semi, int64_t n, int32_t eltype, double A, double B, double dt,
+                           const void *rhs, void *tmp, void *state)
+{
+    Semi *s = (Semi *)semi;
+    int rc = vec_check(s, n, eltype);
+    if (rc || n == 0) return rc;
+    if (eltype == TPB_F32)
+        LAUNCH(*s, k_vec_rk2n_stage<float>, vec_grid(n), 256, 0, n, A, B, dt, (const float *)rhs, (float *)tmp, (float *)state);
+    else
+        LAUNCH(*s, k_vec_rk2n_stage<double>, vec_grid(n), 256, 0, n, A, B, dt, (const double *)rhs, (double *)tmp, (double *)state);
+    CUDA_TRY(s, cudaGetLastError());
+    return TPB_OK;
+}
+
+int32_t tpb_vec_fill(tpb_semi_t semi, int64_t n, int32_t eltype, double value, void *x)
+{
+    Semi *s = (Semi *)semi;
+    int rc = vec_check(s, n, eltype);
+    if (rc || n == 0) return rc;
+    if (eltype == TPB_F32) LAUNCH(*s, k_vec_fill<float>, vec_grid(n), 256, 0, n, value, (float *)x);
+    else LAUNCH(*s, k_vec_fill<double>, vec_grid(n), 256, 0, n, value, (double *)x);
+    CUDA_TRY(s, cudaGetLastError());
+    return TPB_OK;
+}
+
+int32_t tpb_vec_strided_max(tpb_semi_t semi, int64_t count, int32_t eltype, int32_t stride, int32_t offset,
+                            const void *x, double *out_host)
+{
+    Semi *s = (Semi *)semi;
+    int rc = vec_check(s, count, eltype);
+    if (rc) return rc;
+    if (!out_host || stride <= 0 || offset < 0) return fail(s, TPB_ERR_INVALID_ARGUMENT, "bad argument");
+    double *d_out = (double *)s->d_scratch;  // >= 8 bytes
+    const double ninf = -std::numeric_limits<double>::infinity();
+    CUDA_TRY(s, cudaMemcpyAsync(d_out, &ninf, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (count > 0) {
+        if (eltype == TPB_F32) LAUNCH(*s, k_vec_strided_max<float>, vec_grid(count), 256, 0, count, stride, offset, (const float *)x, d_out);
+        else LAUNCH(*s, k_vec_strided_max<double>, vec_grid(count), 256, 0, count, stride, offset, (const double *)x, d_out);
+    }
+    CUDA_TRY(s, cudaMemcpyAsync(out_host, d_out, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     return TPB_OK;
 }
 

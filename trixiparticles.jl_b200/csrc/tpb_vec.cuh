@@ -1,0 +1,76 @@
+// tpb_vec.cuh -- fused algebra on device-resident ODE vectors, so that the integrator's
+// broadcasts between RHS evaluations never leave the GPU.  Counterpart of the broadcast
+// overloads of `ThreadedBroadcastArray` (/root/reference/src/util.jl:183-303) and of the
+// 2N-storage Runge-Kutta stage update OrdinaryDiffEq performs on `ArrayPartition(v_ode, u_ode)`.
+// Pure streaming kernels (HBM-bound): 16-byte vector accesses, grid-stride, arithmetic in
+// double and rounded on store (Julia promotes Float64 dt * Float32 entries the same way).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tpb {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_vec_axpby(int64_t n, double a, const T *__restrict__ x, double b, T *__restrict__ y)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i] = (T)(a * (double)x[i] + (b == 0.0 ? 0.0 : b * (double)y[i]));
+}
+
+// tmp = A * tmp + dt * rhs;  state += B * tmp      (Williamson 2N-storage stage)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_vec_rk2n_stage(int64_t n, double A, double B, double dt, const T *__restrict__ rhs,
+                 T *__restrict__ tmp, T *__restrict__ state)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T t = (T)((A == 0.0 ? 0.0 : A * (double)tmp[i]) + dt * (double)rhs[i]);
+        tmp[i] = t;
+        state[i] = (T)((double)state[i] + B * (double)t);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_vec_fill(int64_t n, double value, T *__restrict__ x)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = (T)value;
+}
+
+// max over x[offset + k * stride], k < count  (e.g. `max_x_coord`: custom_quantities.jl)
+// out must hold the identity (-inf as ordered int bits) before the launch.
+__device__ __forceinline__ void atomic_max_double(double *addr, double v)
+{
+    unsigned long long *p = (unsigned long long *)addr;
+    unsigned long long old = *p, assumed;
+    do {
+        assumed = old;
+        if (__longlong_as_double((long long)assumed) >= v) break;
+        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_vec_strided_max(int64_t count, int stride, int offset, const T *__restrict__ x, double *__restrict__ out)
+{
+    double m = -1.0 / 0.0;
+    const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gs)
+        m = fmax(m, (double)x[k * stride + offset]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ double wm[8];
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, wm[w]);
+        atomic_max_double(out, m);  // order-independent: max is exact
+    }
+}
+
+}  // namespace tpb
