@@ -307,10 +307,17 @@ def run_single(args):
     flops = (pairs["fluid_fluid"] * 80 + pairs["fluid_wall"] * 55 + pairs["wall_fluid"] * 12
              + 9.0 * cand_per_particle * (2 * n_f + n_w_active))
     fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+        with open(tpath) as f:
+            rec = json.load(f).get(args.workload)
+        if rec:
+            traffic, traffic_src = rec["dram_bytes_read"] + rec["dram_bytes_write"], rec["source"]
     roofline = {
         "bound": "hbm", "kernel": "interact! phase (fluid-fluid + fluid-wall pair sweep)",
         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-        "peak_source": peak_src, "traffic": None,
+        "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": k_bytes, "kernel_ms": k_ms,
         "kernel_share_of_step": k_ms / (total_ms / args.steps),
         "note": "the pair sweep is FP32-issue bound (about 300 flop per compulsory byte), see fp32 and DESIGN.md",
