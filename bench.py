@@ -216,6 +216,11 @@ def run_single(args):
     fluid, wall, u, v = make_workload(args.workload)
     nd, n_f, n_w = fluid.ndims, fluid.nparticles, wall.nparticles
     tsize, csize = np.dtype(fluid.eltype).itemsize, np.dtype(fluid.coordinates_eltype).itemsize
+    if args.e2e_only:
+        e2e = run_e2e(tp, torch, fluid, wall, u, v, args)
+        e2e["env"] = {k: v for k, v in os.environ.items() if k.startswith("TPB_")}
+        print(json.dumps(e2e))
+        return
 
     # ---- device-resident arm
     backend = tp.B200Backend(device=0, ode_memory="device", interact_variant=args.variant)
@@ -405,6 +410,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="interact kernel variant (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
+    ap.add_argument("--e2e-only", action="store_true", help="host-pointer (e2e) timing only (tuning runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

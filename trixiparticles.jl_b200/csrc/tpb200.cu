@@ -65,6 +65,7 @@ struct Semi {
     tpb_stats stats{};
     int launches_this_call = 0;
     int deferred_status = TPB_OK;
+    bool host_zero_copy = true;  // TPB_MEM_HOST: use mapped page-locked ODE vectors in place (TPB_HOST_ZEROCOPY=0 disables)
 
     // phase profiling (tpb_set_profiling): one row of TPB_N_PHASES + 1 events per recorded kick
     std::vector<cudaEvent_t> prof_events;
@@ -79,6 +80,18 @@ inline void prof_mark(Semi &s, int ph)
 }
 
 inline size_t tsize(int eltype) { return eltype == TPB_F64 ? 8 : 4; }
+
+// Device-side alias of a page-locked, mapped host pointer (cudaHostAlloc / cudaHostRegister,
+// e.g. through tpb_host_register); nullptr for pageable memory.
+inline void *mapped_host_alias(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
 
 int fail(Semi *s, int code, const std::string &msg)
 {
@@ -434,9 +447,14 @@ struct Ops {
         if (s.cfg.ode_memory == TPB_MEM_HOST) {
             CUDA_TRY(&s, cudaMemcpyAsync(s.d_u, u, nu, cudaMemcpyHostToDevice, s.stream));
             CUDA_TRY(&s, cudaMemcpyAsync(s.d_v, v, nvb, cudaMemcpyHostToDevice, s.stream));
-            rc = kick_device(s, (T *)s.d_dv, (const T *)s.d_v, (const CT *)s.d_u);
+            // Page-locked (pinned / tpb_host_register'ed) dv: the interact! kernel stores every
+            // particle's dv straight into the mapped host buffer, so the device->host transfer
+            // rides along with the kernel instead of following it.
+            void *dv_alias = s.host_zero_copy ? mapped_host_alias(dv) : nullptr;
+            rc = kick_device(s, (T *)(dv_alias ? dv_alias : s.d_dv), (const T *)s.d_v, (const CT *)s.d_u);
             if (rc) return rc;
-            CUDA_TRY(&s, cudaMemcpyAsync(dv, s.d_dv, nvb, cudaMemcpyDeviceToHost, s.stream));
+            if (!dv_alias)
+                CUDA_TRY(&s, cudaMemcpyAsync(dv, s.d_dv, nvb, cudaMemcpyDeviceToHost, s.stream));
             CUDA_TRY(&s, cudaMemcpyAsync(s.h_flags, s.d_flags, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
             CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
             if (*s.h_flags & 1)
@@ -460,10 +478,19 @@ struct Ops {
         int64_t total = s.n_tgt * ND;
         if (total == 0) return TPB_OK;
         if (s.cfg.ode_memory == TPB_MEM_HOST) {
-            CUDA_TRY(&s, cudaMemcpyAsync(s.d_v, v, nvb, cudaMemcpyHostToDevice, s.stream));
-            LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total, 256), 256, 0, total, nv(s), (const T *)s.d_v,
-                   (CT *)s.d_du);
-            CUDA_TRY(&s, cudaMemcpyAsync(du, s.d_du, nu, cudaMemcpyDeviceToHost, s.stream));
+            // Page-locked v and du: one kernel streams v in and du out over PCIe at the same
+            // time (full duplex) instead of copy -> kernel -> copy.
+            const void *v_alias = s.host_zero_copy ? mapped_host_alias(v) : nullptr;
+            void *du_alias = s.host_zero_copy ? mapped_host_alias(du) : nullptr;
+            if (v_alias && du_alias) {
+                LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total, 256), 256, 0, total, nv(s), (const T *)v_alias,
+                       (CT *)du_alias);
+            } else {
+                CUDA_TRY(&s, cudaMemcpyAsync(s.d_v, v, nvb, cudaMemcpyHostToDevice, s.stream));
+                LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total, 256), 256, 0, total, nv(s), (const T *)s.d_v,
+                       (CT *)s.d_du);
+                CUDA_TRY(&s, cudaMemcpyAsync(du, s.d_du, nu, cudaMemcpyDeviceToHost, s.stream));
+            }
             CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
         } else {
             LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total, 256), 256, 0, total, nv(s), (const T *)v,
@@ -663,6 +690,7 @@ int32_t tpb_create(const tpb_config *config, tpb_semi_t *out)
         return fail(nullptr, TPB_ERR_CUDA, cudaGetErrorString(e));
     }
     s->stream = s->own_stream;
+    if (const char *z = getenv("TPB_HOST_ZEROCOPY")) s->host_zero_copy = atoi(z) != 0;
     *out = (tpb_semi_t)s;
     return TPB_OK;
 }

@@ -469,6 +469,7 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     if (!valid) return;
     // dv = ((0 + S_ff) + S_fw) + g [+ source]  (semidiscretization.jl:600, :809-829, :668-731)
     const int64_t o = (int64_t)perm[s] * NV;
+    T out[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
         T val = dv_ff[d] + dv_fw[d];
@@ -476,9 +477,19 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
             val += src.acc[d];
             if (src.damping != (T)0) val += -src.damping * v_a[d];
         }
-        dv[o + d] = val;
+        out[d] = val;
     }
-    if (DENS == 0) dv[o + ND] = drho_ff + drho_fw;
+    if (DENS == 0) out[ND] = drho_ff + drho_fw;
+    // one 16-byte store per particle where the layout allows it (3-D Float32 with density):
+    // dv may be a mapped host buffer, where every store instruction is a PCIe write
+    if (NV == 4 && sizeof(T) == 4 && (reinterpret_cast<uintptr_t>(dv) & 15) == 0) {
+        V4<T> o4;
+        o4.x = out[0], o4.y = out[1], o4.z = out[2], o4.w = out[3];
+        *reinterpret_cast<V4<T> *>(dv + o) = o4;
+    } else {
+#pragma unroll
+        for (int d = 0; d < NV; ++d) dv[o + d] = out[d];
+    }
 }
 
 // ------------------------------------------------------------------ Adami (variant 2)
