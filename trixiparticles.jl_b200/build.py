@@ -31,6 +31,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, *NVCC_FLAGS]
+    cmd += os.environ.get("TPB_NVCC_EXTRA", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", SO, os.path.join(CSRC, "tpb200.cu")]

@@ -253,8 +253,14 @@ struct Ops {
                        s.d_fcell_start + s.ncells, s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
                        s.d_perm_f);
         }
-        if (use_tiles(s))
-            return build_tile_table(s, s.d_fcell_start, s.tiles.d_frow_tile_start, s.tiles.d_ftile_desc);
+        if (use_tiles(s)) {
+            rc = build_tile_table(s, s.d_fcell_start, s.tiles.d_frow_tile_start, s.tiles.d_ftile_desc);
+            if (rc) return rc;
+            LAUNCH(s, (k_tile_ranges<ND>), cdiv((int64_t)s.tiles.max_ftiles * 32, 256), 256, 0, s.ncell[0],
+                   s.ncell[1], s.xsplit, s.tiles.d_frow_tile_start + s.tiles.nrows, s.tiles.d_ftile_desc,
+                   s.d_fcell_start, s.d_fcell_start, s.n_w > 0 ? s.d_wcell_start : (const int *)nullptr,
+                   s.tiles.d_ftile_rng, 18, s.tiles.d_ftile_ext);
+        }
         return TPB_OK;
     }
 
@@ -355,9 +361,10 @@ struct Ops {
             LAUNCH(s, (k_wall_tile_prep<ND, T, CT>), cdiv((int64_t)s.tiles.max_wtiles * 32, 256), 256, 0, g,
                    s.tiles.d_wrow_tile_start + s.tiles.nrows, s.tiles.d_wtile_desc, (const V4<CT> *)s.d_Aw,
                    s.d_fcell_start, rho_empty, (V2<T> *)s.d_Ww, (T *)s.d_volw, s.tiles.d_wactive,
-                   s.tiles.d_n_wactive);
+                   s.tiles.d_n_wactive, s.tiles.d_wtile_rng, s.tiles.d_wtile_ext);
             LAUNCH(s, (k_adami_tiles<ND, T, CT, KERNEL>), s.tiles.max_wtiles, TILE_TB, smem, g,
-                   s.tiles.d_n_wactive, s.tiles.d_wactive, s.tiles.d_wtile_desc, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
+                   s.tiles.d_n_wactive, s.tiles.d_wactive, s.tiles.d_wtile_desc, s.tiles.d_wtile_ext,
+                   s.tiles.d_wtile_rng, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
                    s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
                    s.interaction[1][0], k, (V2<T> *)s.d_Ww, (T *)s.d_volw, cap, s.tiles.list_len);
             return TPB_OK;
@@ -392,7 +399,8 @@ struct Ops {
                 attr_set = true;
             }
             LAUNCH(s, (k_interact_tiles<ND, T, CT, KERNEL, DENS>), s.tiles.max_ftiles, TILE_TB, smem, g,
-                   s.tiles.d_frow_tile_start + s.tiles.nrows, s.tiles.d_ftile_desc, s.d_fcell_start, (const V4<CT> *)s.d_A,
+                   s.tiles.d_frow_tile_start + s.tiles.nrows, s.tiles.d_ftile_desc, s.tiles.d_ftile_ext,
+                   s.tiles.d_ftile_rng, s.d_fcell_start, (const V4<CT> *)s.d_A,
                    (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f, s.interaction[0][0], has_wall,
                    s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv,
                    (int)s.n_tgt, cap, s.tiles.list_len);
@@ -571,9 +579,15 @@ struct Ops {
             const size_t smem = tile_smem_bytes<T, CT>(cap, s.tiles.list_len);
             int rc2 = set_smem(s, k_pairs_tiles<ND, T, CT>, 227 * 1024);
             if (rc2) return rc2;
-            LAUNCH(s, (k_pairs_tiles<ND, T, CT>), x_fluid ? s.tiles.max_ftiles : s.tiles.max_wtiles, TILE_TB,
-                   smem, g, (x_fluid ? s.tiles.d_frow_tile_start : s.tiles.d_wrow_tile_start) + s.tiles.nrows,
-                   x_fluid ? s.tiles.d_ftile_desc : s.tiles.d_wtile_desc,
+            const int max_tiles = x_fluid ? s.tiles.max_ftiles : s.tiles.max_wtiles;
+            const int *n_tiles = (x_fluid ? s.tiles.d_frow_tile_start : s.tiles.d_wrow_tile_start) + s.tiles.nrows;
+            LAUNCH(s, (k_tile_ranges<ND>), cdiv((int64_t)max_tiles * 32, 256), 256, 0, s.ncell[0], s.ncell[1],
+                   s.xsplit, n_tiles, x_fluid ? s.tiles.d_ftile_desc : s.tiles.d_wtile_desc,
+                   x_fluid ? s.d_fcell_start : s.d_wcell_start, y_fluid ? s.d_fcell_start : s.d_wcell_start,
+                   (const int *)nullptr, s.tiles.d_ptile_rng, 9, s.tiles.d_ptile_ext);
+            LAUNCH(s, (k_pairs_tiles<ND, T, CT>), max_tiles, TILE_TB,
+                   smem, g, n_tiles,
+                   x_fluid ? s.tiles.d_ftile_desc : s.tiles.d_wtile_desc, s.tiles.d_ptile_ext, s.tiles.d_ptile_rng,
                    (const V4<CT> *)(x_fluid ? s.d_A : s.d_Aw), x_fluid ? s.d_perm_f : s.d_perm_w,
                    y_fluid ? s.d_fcell_start : s.d_wcell_start,
                    (const V4<CT> *)(y_fluid ? s.d_A : s.d_Aw), y_fluid ? s.d_perm_f : s.d_perm_w, r2,
@@ -604,6 +618,14 @@ struct Ops {
     }
 };
 
+#ifdef TPB_DEV_ONLY_3D_F32  // development builds: one instantiation, quick to compile
+#define DISPATCH(S, CALL)                                                                     \
+    do {                                                                                      \
+        const int nd_ = (S).cfg.ndims, t_ = (S).cfg.eltype, ct_ = (S).cfg.coords_eltype;      \
+        if (nd_ == 3 && t_ == TPB_F32 && ct_ == TPB_F32) return Ops<3, float, float>::CALL;   \
+        return fail(&(S), TPB_ERR_UNSUPPORTED, "development build: 3-D Float32 only");        \
+    } while (0)
+#else
 #define DISPATCH(S, CALL)                                                                     \
     do {                                                                                      \
         const int nd_ = (S).cfg.ndims, t_ = (S).cfg.eltype, ct_ = (S).cfg.coords_eltype;      \
@@ -615,6 +637,7 @@ struct Ops {
         if (nd_ == 3 && t_ == TPB_F64 && ct_ == TPB_F64) return Ops<3, double, double>::CALL; \
         return fail(&(S), TPB_ERR_UNSUPPORTED, "unsupported ndims / eltype combination");     \
     } while (0)
+#endif
 
 int dispatch_init_wall(Semi &s) { DISPATCH(s, init_wall(s)); }
 int dispatch_kick(Semi &s, void *dv, const void *v, const void *u) { DISPATCH(s, kick(s, dv, v, u)); }

@@ -20,6 +20,7 @@
 //            d^2 <= R^2 (bit-exact arithmetic, tpb_device.cuh) and the pair physics.
 // Accumulators live in registers; each particle's dv is written once; no atomics.
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -101,11 +102,62 @@ k_fill_tiles(const int *__restrict__ cell_start, int n0, int nrows,
         desc[first + k] = make_int4(rs + (int)(cnt * k / nt), rs + (int)(cnt * (k + 1) / nt), r, 0);
 }
 
+// Candidate ranges of every tile, one warp per tile: for each of the 3^(ND-1) neighbour rows the
+// run of sorted records [g0, g1) covering the cells {cxmin - sx .. cxmax + sx} of that row, in up
+// to two neighbour sets (lanes 0..8: set 0, lanes 9..17: set 1).  Computed once per rebuild so
+// that the sweeps start their TMA copies without a dependent chain of global loads.
+//   rng[tile * stride + 9 * set + q] = (g0, g1);   ext[tile] = (cxmin, cxmax, total set 0, total set 1)
+template <int ND>
+__global__ void __launch_bounds__(256)
+k_tile_ranges(int n0, int n1, int sx, const int *__restrict__ n_tiles, const int4 *__restrict__ desc,
+              const int *__restrict__ xcell_start, const int *__restrict__ nb0_cell_start,
+              const int *__restrict__ nb1_cell_start, int2 *__restrict__ rng, int stride,
+              int4 *__restrict__ ext)
+{
+    constexpr int NROWS = ND == 3 ? 9 : 3;
+    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (tile >= *n_tiles) return;
+    const int4 d = desc[tile];
+    const int row0 = d.z * n0;
+    // cell of the first / last target: last cell of the row whose start is <= the sorted index
+    int cx[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int target = e == 0 ? d.x : d.y - 1;
+        int lo = row0, hi = row0 + n0;  // xcell_start[lo] <= target < xcell_start[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (xcell_start[mid] <= target) lo = mid; else hi = mid;
+        }
+        cx[e] = lo - row0;
+    }
+    const int set = lane / 9, q = lane - 9 * set;
+    const int *nb = set == 0 ? nb0_cell_start : nb1_cell_start;
+    int g0 = 0, g1 = 0;
+    if (lane < 18 && q < NROWS && nb != nullptr) {
+        const int dy = q % 3 - 1, dz = ND == 3 ? q / 3 - 1 : 0;
+        const int cy = d.z % n1, cz = d.z / n1;
+        const int c_lo = (cx[0] - sx) + n0 * ((cy + dy) + n1 * (cz + dz));
+        g0 = nb[c_lo];
+        g1 = nb[c_lo + (cx[1] - cx[0]) + 2 * sx + 1];
+        rng[(int64_t)tile * stride + lane] = make_int2(g0, g1);
+    }
+    int cnt0 = set == 0 ? g1 - g0 : 0, cnt1 = set == 1 ? g1 - g0 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt0 += __shfl_xor_sync(0xffffffffu, cnt0, o);
+        cnt1 += __shfl_xor_sync(0xffffffffu, cnt1, o);
+    }
+    if (lane == 0) ext[tile] = make_int4(cx[0], cx[1], cnt0, cnt1);
+}
+
 struct TileHdr {
     int p0, p1, cy, cz, cxmin, cxmax;
+    int tot0, tot1;    // candidates in neighbour set 0 / 1 (k_tile_ranges)
     int g0[9], g1[9];  // candidate range of every neighbour row (current neighbour set)
     int q, gpos;       // staging cursor: next row, next record in it
-    int nseg, pad;
+    int nseg, last;    // segments of the staged chunk; last: nothing left to stage after it
     int seg_row[TILE_MAXSEG], seg_begin[TILE_MAXSEG], seg_end[TILE_MAXSEG], seg_base[TILE_MAXSEG];
 };
 constexpr int TILE_HDR_BYTES = 16 + ((sizeof(TileHdr) + 15) / 16) * 16;  // mbarrier + header
@@ -142,22 +194,18 @@ inline size_t tile_smem_bytes(int cap, int list_len)
 }
 
 // Load the tile descriptor of this block into hdr (thread 0).
-template <int ND, typename CT>
-__device__ __forceinline__ void tile_locate(TileHdr *hdr, const GridConst<CT> &g,
-                                            const int4 *__restrict__ tile_desc,
-                                            const V4<CT> *__restrict__ X, int tile)
+__device__ __forceinline__ void tile_locate(TileHdr *hdr, int n1, const int4 *__restrict__ tile_desc,
+                                            const int4 *__restrict__ tile_ext, int tile)
 {
-    const int4 d = tile_desc[tile];
+    const int4 d = tile_desc[tile], e = tile_ext[tile];
     hdr->p0 = d.x;
     hdr->p1 = d.y;
-    hdr->cy = d.z % g.n[1];
-    hdr->cz = d.z / g.n[1];
-    int cx, cy, cz;
-    const V4<CT> xa = X[d.x], xb = X[d.y - 1];
-    cell_coords<ND, CT>(g, xa.x, xa.y, xa.z, cx, cy, cz);
-    hdr->cxmin = cx;
-    cell_coords<ND, CT>(g, xb.x, xb.y, xb.z, cx, cy, cz);
-    hdr->cxmax = cx;
+    hdr->cy = d.z % n1;
+    hdr->cz = d.z / n1;
+    hdr->cxmin = e.x;
+    hdr->cxmax = e.y;
+    hdr->tot0 = e.z;
+    hdr->tot1 = e.w;
 }
 
 // Conservative phase-1 filter.  Float coordinates: fused arithmetic with a small margin on the
@@ -216,38 +264,82 @@ struct NbSet {
     const T *__restrict__ P;
 };
 
-// Sweep all neighbours (of one set) of the tile's targets.  `body(xj, bj, pj)` is called for
-// every candidate that passed the filter; it applies the exact predicate itself.
-// Must be called by all threads of the block.
-template <int ND, typename T, typename CT, typename NB, typename BODY>
-__device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<CT> &g, const NB &nb,
-                                           bool valid, int cx, const V4<CT> &xi, T radius2,
-                                           uint32_t &parity, BODY &&body)
+// Stage the neighbour rows of a sweep (warp 0 only, all 32 lanes; the staging area must be
+// free).  `rng[q]` = candidate range of neighbour row q (k_tile_ranges).  Usual case: all rows
+// fit into the staging area, then lane q issues the TMA copies of row q itself -- no serial
+// loop; otherwise the chunked path of tile_sweep_staged takes over.
+template <int ND, typename T, typename CT, typename NB>
+__device__ __forceinline__ void tile_stage(TileSmem<T, CT> &sm, const NB &nb, const int2 *__restrict__ rng)
 {
     using R1 = typename NB::R1;
     constexpr int NROWS = ND == 3 ? 9 : 3;
+    constexpr uint32_t REC_BYTES = sizeof(V4<CT>) + sizeof(R1) + (NB::HAS_P ? sizeof(T) : 0);
+    const int tid = threadIdx.x;
+    TileHdr *hdr = sm.hdr;
+    R1 *tB = (R1 *)sm.tB;
+    int g0 = 0, g1 = 0;
+    if (tid < NROWS) {
+        const int2 r = rng[tid];
+        g0 = r.x;
+        g1 = r.y;
+        hdr->g0[tid] = g0;
+        hdr->g1[tid] = g1;
+    }
+    const int a = g0 & ~3;  // 4 records: every array stays 16-byte aligned
+    const int len = g1 > g0 ? ((g1 + 3) & ~3) - a : 0;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, NROWS - 1);
+    const unsigned nonempty = __ballot_sync(0xffffffffu, len > 0);
+    if (total > 0 && total <= sm.cap) {
+        if (tid == 0) {
+            hdr->nseg = __popc(nonempty);
+            hdr->last = 1;
+            hdr->q = NROWS;
+            mbar_expect_tx(sm.bar, (uint32_t)total * REC_BYTES);
+        }
+        __syncwarp();
+        if (len > 0) {
+            const int used = incl - len;
+            const int k = __popc(nonempty & ((1u << tid) - 1u));
+            hdr->seg_row[k] = tid;
+            hdr->seg_begin[k] = g0;
+            hdr->seg_end[k] = g1;
+            hdr->seg_base[k] = used - a;  // tile index of record j = seg_base + j
+            fence_proxy_async();
+            bulk_g2s(sm.tA + used, nb.A + a, (uint32_t)(len * sizeof(V4<CT>)), sm.bar);
+            bulk_g2s(tB + used, nb.B + a, (uint32_t)(len * sizeof(R1)), sm.bar);
+            if constexpr (NB::HAS_P) bulk_g2s(sm.tP + used, nb.P + a, (uint32_t)(len * sizeof(T)), sm.bar);
+        }
+    } else if (tid == 0) {
+        hdr->nseg = 0;
+        hdr->last = total == 0;  // no candidates at all (e.g. fluid far from any wall)
+        hdr->q = 0;
+        hdr->gpos = g0;
+    }
+}
+
+// Sweep all neighbours (of one set) of the tile's targets after tile_stage and a block barrier.
+// `body(xj, bj, pj)` is called for every candidate that passed the filter; it applies the exact
+// predicate itself.  Must be called by all threads of the block.
+template <int ND, typename T, typename CT, typename NB, typename BODY>
+__device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const GridConst<CT> &g, const NB &nb,
+                                                  bool valid, int cx, const V4<CT> &xi, T radius2,
+                                                  uint32_t &parity, BODY &&body)
+{
+    using R1 = typename NB::R1;
+    constexpr int NROWS = ND == 3 ? 9 : 3;
+    constexpr uint32_t REC_BYTES = sizeof(V4<CT>) + sizeof(R1) + (NB::HAS_P ? sizeof(T) : 0);
     const int tid = threadIdx.x;
     TileHdr *hdr = sm.hdr;
     R1 *tB = (R1 *)sm.tB;
     const Filter<ND, T, CT> filter(radius2);
-    __syncthreads();  // the previous sweep is done with hdr and the staged tile
-    if (tid < NROWS) {
-        const int dy = tid % 3 - 1, dz = ND == 3 ? tid / 3 - 1 : 0;
-        const int c_lo = cell_linear(g, hdr->cxmin - g.sx, hdr->cy + dy, hdr->cz + dz);
-        hdr->g0[tid] = nb.cell_start[c_lo];
-        hdr->g1[tid] = nb.cell_start[c_lo + (hdr->cxmax - hdr->cxmin) + 2 * g.sx + 1];
-    }
-    __syncthreads();
-    {
-        int total = 0;  // block-uniform: no candidates at all (e.g. wall far from any fluid)
-#pragma unroll
-        for (int q = 0; q < NROWS; ++q) total += hdr->g1[q] - hdr->g0[q];
-        if (total == 0) return;
-    }
-    if (tid == 0) {
-        hdr->q = 0;
-        hdr->gpos = hdr->g0[0];
-    }
+    bool staged = hdr->nseg > 0;
+    if (!staged && hdr->last) return;
 
     // private list: entry e of thread t lives at list[e * TILE_TB + t] (conflict-free)
     unsigned short *const my_list = sm.list + tid;
@@ -255,6 +347,11 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
     const uint32_t list_end_a = list_a + (uint32_t)sm.list_len * TILE_TB * 2u;
     constexpr uint32_t ESTEP = TILE_TB * 2u;  // bytes between consecutive entries of one thread
     uint32_t lpa = list_a;                    // append position (shared-memory address)
+    auto room = [&](int n) { return lpa + n * ESTEP <= list_end_a; };
+    auto append = [&](uint32_t v) {
+        sts_u16(lpa, v);
+        lpa += ESTEP;
+    };
     auto visit = [&](int idx) {
         if constexpr (NB::HAS_P)
             body(sm.tA[idx], tB[idx], sm.tP[idx]);
@@ -276,52 +373,59 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
     };
 
     while (true) {
-        // ---- thread 0: next chunk of whole rows (or one piece of an oversized row)
-        if (tid == 0) {
-            int q = hdr->q, gpos = hdr->gpos, used = 0, nseg = 0;
-            uint32_t bytes = 0;
-            while (q < NROWS && nseg < TILE_MAXSEG) {
-                const int gend_row = hdr->g1[q];
-                if (gpos >= gend_row) {
+        // ---- oversized neighbourhood: thread 0 stages the next chunk of whole rows (or one
+        // piece of an oversized row)
+        if (!staged) {
+            if (tid == 0) {
+                int q = hdr->q, gpos = hdr->gpos, used = 0, nseg = 0;
+                uint32_t bytes = 0;
+                while (q < NROWS && nseg < TILE_MAXSEG) {
+                    const int gend_row = hdr->g1[q];
+                    if (gpos >= gend_row) {
+                        ++q;
+                        if (q < NROWS) gpos = hdr->g0[q];
+                        continue;
+                    }
+                    const int a = gpos & ~3;
+                    const int need = ((gend_row + 3) & ~3) - a;
+                    int gend;
+                    if (need <= sm.cap - used) {
+                        gend = gend_row;
+                    } else if (nseg == 0) {
+                        gend = a + sm.cap;  // piece of an oversized row (cap is a multiple of 4)
+                    } else {
+                        break;
+                    }
+                    const int len = ((gend + 3) & ~3) - a;
+                    hdr->seg_row[nseg] = q;
+                    hdr->seg_begin[nseg] = gpos;
+                    hdr->seg_end[nseg] = gend;
+                    hdr->seg_base[nseg] = used - a;
+                    if (nseg == 0) fence_proxy_async();
+                    bulk_g2s(sm.tA + used, nb.A + a, (uint32_t)(len * sizeof(V4<CT>)), sm.bar);
+                    bulk_g2s(tB + used, nb.B + a, (uint32_t)(len * sizeof(R1)), sm.bar);
+                    if constexpr (NB::HAS_P) bulk_g2s(sm.tP + used, nb.P + a, (uint32_t)(len * sizeof(T)), sm.bar);
+                    bytes += (uint32_t)len * REC_BYTES;
+                    used += len;
+                    ++nseg;
+                    gpos = gend;
+                    if (gend < gend_row) break;  // oversized row: continue with it next chunk
+                }
+                while (q < NROWS && gpos >= hdr->g1[q]) {  // skip exhausted / empty rows
                     ++q;
                     if (q < NROWS) gpos = hdr->g0[q];
-                    continue;
                 }
-                const int a = gpos & ~3;  // 4 records: every array stays 16-byte aligned
-                const int need = ((gend_row + 3) & ~3) - a;
-                int gend;
-                if (need <= sm.cap - used) {
-                    gend = gend_row;
-                } else if (nseg == 0) {
-                    gend = a + sm.cap;  // piece of an oversized row (cap is a multiple of 4)
-                } else {
-                    break;
-                }
-                const int len = ((gend + 3) & ~3) - a;
-                hdr->seg_row[nseg] = q;
-                hdr->seg_begin[nseg] = gpos;
-                hdr->seg_end[nseg] = gend;
-                hdr->seg_base[nseg] = used - a;  // tile index of record j = seg_base + j
-                if (nseg == 0) fence_proxy_async();
-                bulk_g2s(sm.tA + used, nb.A + a, (uint32_t)(len * sizeof(V4<CT>)), sm.bar);
-                bulk_g2s(tB + used, nb.B + a, (uint32_t)(len * sizeof(R1)), sm.bar);
-                bytes += (uint32_t)(len * (sizeof(V4<CT>) + sizeof(R1)));
-                if constexpr (NB::HAS_P) {
-                    bulk_g2s(sm.tP + used, nb.P + a, (uint32_t)(len * sizeof(T)), sm.bar);
-                    bytes += (uint32_t)(len * sizeof(T));
-                }
-                used += len;
-                ++nseg;
-                gpos = gend;
-                if (gend < gend_row) break;  // oversized row: continue with it next chunk
+                hdr->q = q;
+                hdr->gpos = gpos;
+                hdr->nseg = nseg;
+                hdr->last = q >= NROWS;
+                if (nseg > 0) mbar_expect_tx(sm.bar, bytes);
             }
-            hdr->q = q;
-            hdr->gpos = gpos;
-            hdr->nseg = nseg;
-            if (nseg > 0) mbar_expect_tx(sm.bar, bytes);
+            __syncthreads();
         }
-        __syncthreads();
+        staged = false;
         const int nseg = hdr->nseg;
+        const bool last = hdr->last != 0;
         if (nseg == 0) break;
 
         mbar_wait(sm.bar, parity);
@@ -344,23 +448,17 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
             while (true) {
                 // phase 1: filter candidates into the private list
                 constexpr int U = 8;
-                while (t + U <= t1 && lpa + U * ESTEP <= list_end_a) {
+                while (t + U <= t1 && room(U)) {
                     V4<CT> xc[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) xc[u] = sm.tA[t + u];
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        if (filter(xi, xc[u])) {
-                            sts_u16(lpa, (uint32_t)(t + u));
-                            lpa += ESTEP;
-                        }
+                        if (filter(xi, xc[u])) append((uint32_t)(t + u));
                     t += U;
                 }
-                while (t < t1 && lpa < list_end_a) {
-                    if (filter(xi, sm.tA[t])) {
-                        sts_u16(lpa, (uint32_t)t);
-                        lpa += ESTEP;
-                    }
+                while (t < t1 && room(1)) {
+                    if (filter(xi, sm.tA[t])) append((uint32_t)t);
                     ++t;
                 }
                 if (!__any_sync(0xffffffffu, t < t1)) break;
@@ -368,14 +466,28 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
             }
         }
         flush();  // list entries point into this chunk: drain before it is replaced
+        if (last) break;  // the next sweep's leading barrier protects the staged tile
         __syncthreads();
     }
+}
+
+// stage + sweep; must be called by all threads of the block
+template <int ND, typename T, typename CT, typename NB, typename BODY>
+__device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<CT> &g, const NB &nb,
+                                           const int2 *__restrict__ rng, bool valid, int cx,
+                                           const V4<CT> &xi, T radius2, uint32_t &parity, BODY &&body)
+{
+    __syncthreads();  // the previous sweep is done with hdr and the staged tile
+    if (threadIdx.x < 32) tile_stage<ND, T, CT>(sm, nb, rng);
+    __syncthreads();
+    tile_sweep_staged<ND, T, CT>(sm, g, nb, valid, cx, xi, radius2, parity, body);
 }
 
 // ------------------------------------------------------------------ interact! (variant 2)
 template <int ND, typename T, typename CT, int KERNEL, int DENS>
 __global__ void __launch_bounds__(TILE_TB, 2)
 k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
+                 const int4 *__restrict__ tile_ext, const int2 *__restrict__ tile_rng,
                  const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
                  const V4<T> *__restrict__ B, const T *__restrict__ P,
                  const int *__restrict__ perm, int ff_enabled, int has_wall,
@@ -388,15 +500,28 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     const int tile = blockIdx.x;
     if (tile >= *n_tiles) return;
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len);
-    if (threadIdx.x == 0) {
-        tile_locate<ND, CT>(sm.hdr, g, tile_desc, A, tile);
-        mbar_init(sm.bar, 1);
+    const int2 *rng = tile_rng + (int64_t)tile * 18;
+    const NbSet<T, CT, V4<T>, true> nb_f{fcell_start, A, B, P};
+    if (threadIdx.x < 32) {
+        // warp 0 starts the TMA copies of the fluid sweep before anything else happens
+        if (threadIdx.x == 0) {
+            tile_locate(sm.hdr, g.n[1], tile_desc, tile_ext, tile);
+            mbar_init(sm.bar, 1);
+        }
+        __syncwarp();
+        if (ff_enabled) tile_stage<ND, T, CT>(sm, nb_f, rng);
     }
     __syncthreads();
+    const bool any_fw = sm.hdr->tot1 > 0;
     const int s = sm.hdr->p0 + threadIdx.x;
     // slab ghosts (original index >= n_targets) are neighbours only: no dv is computed for them
     const bool valid = s < sm.hdr->p1 && perm[s] < n_targets;
-    if (!__syncthreads_or(valid)) return;
+    uint32_t parity = 0;
+    if (!__syncthreads_or(valid)) {
+        // ghost-only tile: let the copies in flight land before the shared memory is released
+        if (ff_enabled && sm.hdr->nseg > 0) mbar_wait(sm.bar, parity);
+        return;
+    }
     V4<CT> xi = {};
     V4<T> bi = {};
     T p_a = 0;
@@ -409,7 +534,6 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     }
     const T rho_a = bi.w;
     const T v_a[3] = {bi.x, bi.y, bi.z};
-    uint32_t parity = 0;
 
     constexpr bool FAST = std::is_same<T, float>::value && std::is_same<CT, float>::value;
     FastConst fc = {};
@@ -421,8 +545,7 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
 
     T dv_ff[3] = {0, 0, 0}, drho_ff = 0;
     if (ff_enabled) {
-        NbSet<T, CT, V4<T>, true> nb{fcell_start, A, B, P};
-        tile_sweep<ND, T, CT>(sm, g, nb, valid, cx, xi, k.radius2, parity,
+        tile_sweep_staged<ND, T, CT>(sm, g, nb_f, valid, cx, xi, k.radius2, parity,
                               [&](const V4<CT> &xj, const V4<T> &bj, T pj) {
                                   if constexpr (FAST) {
                                       interact_pair_fast<ND, KERNEL, DENS, true>(
@@ -444,10 +567,10 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
                               });
     }
     T dv_fw[3] = {0, 0, 0}, drho_fw = 0;
-    if (has_wall) {
+    if (has_wall && any_fw) {
         const T zero3[3] = {0, 0, 0};
         NbSet<T, CT, V2<T>, false> nb{wcell_start, Aw, Ww, nullptr};
-        tile_sweep<ND, T, CT>(sm, g, nb, valid, cx, xi, k.radius2, parity,
+        tile_sweep<ND, T, CT>(sm, g, nb, rng + 9, valid, cx, xi, k.radius2, parity,
                               [&](const V4<CT> &xj, const V2<T> &wj, T) {
                                   if constexpr (FAST) {
                                       interact_pair_fast<ND, KERNEL, DENS, false>(
@@ -502,7 +625,7 @@ __global__ void __launch_bounds__(256)
 k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
                  const V4<CT> *__restrict__ Aw, const int *__restrict__ fcell_start, T rho_empty,
                  V2<T> *__restrict__ W, T *__restrict__ volume, int *__restrict__ active,
-                 int *__restrict__ n_active)
+                 int *__restrict__ n_active, int2 *__restrict__ rng, int4 *__restrict__ ext)
 {
     constexpr int NROWS = ND == 3 ? 9 : 3;
     const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -519,11 +642,18 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     if (lane < NROWS) {
         const int dy = lane % 3 - 1, dz = ND == 3 ? lane / 3 - 1 : 0;
         const int c_lo = cell_linear(g, cxmin - g.sx, cy + dy, cz + dz);
-        cnt = fcell_start[c_lo + (cxmax - cxmin) + 2 * g.sx + 1] - fcell_start[c_lo];
+        const int g0 = fcell_start[c_lo], g1 = fcell_start[c_lo + (cxmax - cxmin) + 2 * g.sx + 1];
+        cnt = g1 - g0;
+        rng[(int64_t)tile * 9 + lane] = make_int2(g0, g1);
     }
-    const bool any = __any_sync(0xffffffffu, cnt > 0);
-    if (any) {
-        if (lane == 0) active[atomicAdd(n_active, 1)] = tile;
+    int total = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (total > 0) {
+        if (lane == 0) {
+            ext[tile] = make_int4(cxmin, cxmax, total, 0);
+            active[atomicAdd(n_active, 1)] = tile;
+        }
         return;
     }
     V2<T> empty;
@@ -539,7 +669,8 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
 template <int ND, typename T, typename CT, int KERNEL>
 __global__ void __launch_bounds__(TILE_TB, 2)
 k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__restrict__ active,
-              const int4 *__restrict__ tile_desc, const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
+              const int4 *__restrict__ tile_desc, const int4 *__restrict__ tile_ext,
+              const int2 *__restrict__ tile_rng, const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
               const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
               const V4<T> *__restrict__ B, const T *__restrict__ P, int interaction_enabled,
               AdamiConst<T> k, V2<T> *__restrict__ W, T *__restrict__ volume, int cap, int list_len)
@@ -549,7 +680,7 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
     const int tile = active[blockIdx.x];
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len);
     if (threadIdx.x == 0) {
-        tile_locate<ND, CT>(sm.hdr, g, tile_desc, Aw, tile);
+        tile_locate(sm.hdr, g.n[1], tile_desc, tile_ext, tile);
         mbar_init(sm.bar, 1);
     }
     __syncthreads();
@@ -565,7 +696,7 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
     T p = (T)0, vol = (T)0;
     if (interaction_enabled) {
         NbSet<T, CT, V4<T>, true> nb{fcell_start, A, B, P};
-        tile_sweep<ND, T, CT>(sm, g, nb, valid, cx, xi, k.radius2, parity,
+        tile_sweep<ND, T, CT>(sm, g, nb, tile_rng + (int64_t)tile * 9, valid, cx, xi, k.radius2, parity,
                               [&](const V4<CT> &xj, const V4<T> &bj, T pj) {
                                   T pd[3];
                                   const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
@@ -610,6 +741,7 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
 template <int ND, typename T, typename CT>
 __global__ void __launch_bounds__(TILE_TB, 2)
 k_pairs_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
+              const int4 *__restrict__ tile_ext, const int2 *__restrict__ tile_rng,
               const V4<CT> *__restrict__ X, const int *__restrict__ perm_x,
               const int *__restrict__ ycell_start, const V4<CT> *__restrict__ Y,
               const int *__restrict__ perm_y, T radius2, long long capacity, int *__restrict__ out_i,
@@ -620,7 +752,7 @@ k_pairs_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__re
     if (tile >= *n_tiles) return;
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len);
     if (threadIdx.x == 0) {
-        tile_locate<ND, CT>(sm.hdr, g, tile_desc, X, tile);
+        tile_locate(sm.hdr, g.n[1], tile_desc, tile_ext, tile);
         mbar_init(sm.bar, 1);
     }
     __syncthreads();
@@ -635,7 +767,7 @@ k_pairs_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__re
     }
     uint32_t parity = 0;
     NbSet<T, CT, int, false> nb{ycell_start, Y, perm_y, nullptr};
-    tile_sweep<ND, T, CT>(sm, g, nb, valid, cx, xi, radius2, parity, [&](const V4<CT> &xj, const int &pj, T) {
+    tile_sweep<ND, T, CT>(sm, g, nb, tile_rng + (int64_t)tile * 9, valid, cx, xi, radius2, parity, [&](const V4<CT> &xj, const int &pj, T) {
         T pd[3];
         if (pos_diff_d2<ND, T, CT>(xi, xj, pd) <= radius2) {
             unsigned long long at = atomicAdd(counter, 1ull);
@@ -654,6 +786,12 @@ struct TileState {
     int *d_wrow_tile_start = nullptr;  // [nrows + 1] wall tiles (static)
     int4 *d_ftile_desc = nullptr;      // [max_ftiles]
     int4 *d_wtile_desc = nullptr;      // [max_wtiles]
+    int4 *d_ftile_ext = nullptr;       // [max_ftiles] (cxmin, cxmax, fluid candidates, wall candidates)
+    int4 *d_wtile_ext = nullptr;       // [max_wtiles] (cxmin, cxmax, fluid candidates, 0), active tiles only
+    int2 *d_ftile_rng = nullptr;       // [max_ftiles][18] candidate ranges: 9 fluid rows, 9 wall rows
+    int2 *d_wtile_rng = nullptr;       // [max_wtiles][9]  candidate ranges of the wall tiles in the fluid
+    int4 *d_ptile_ext = nullptr;       // tpb_neighbor_pairs scratch
+    int2 *d_ptile_rng = nullptr;
     int *d_wactive = nullptr;          // [max_wtiles] wall tiles with fluid in reach (per kick)
     int *d_n_wactive = nullptr;        // [1]
     int nrows = 0;
@@ -676,6 +814,13 @@ inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
     if (cudaMalloc(&t.d_wrow_tile_start, sizeof(int) * (size_t)(nrows + 4)) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_ftile_desc, sizeof(int4) * (size_t)t.max_ftiles) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_wtile_desc, sizeof(int4) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+    const size_t max_tiles = (size_t)std::max(t.max_ftiles, t.max_wtiles);
+    if (cudaMalloc(&t.d_ftile_ext, sizeof(int4) * (size_t)t.max_ftiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_wtile_ext, sizeof(int4) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_ftile_rng, sizeof(int2) * 18 * (size_t)t.max_ftiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_wtile_rng, sizeof(int2) * 9 * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_ptile_ext, sizeof(int4) * max_tiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_ptile_rng, sizeof(int2) * 9 * max_tiles) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_wactive, sizeof(int) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_n_wactive, sizeof(int) * 4) != cudaSuccess) return 1;
     cudaMemset(t.d_frow_tile_start, 0, sizeof(int) * (size_t)(nrows + 4));
@@ -689,6 +834,12 @@ inline void tiles_free(TileState &t)
     if (t.d_wrow_tile_start) cudaFree(t.d_wrow_tile_start);
     if (t.d_ftile_desc) cudaFree(t.d_ftile_desc);
     if (t.d_wtile_desc) cudaFree(t.d_wtile_desc);
+    if (t.d_ftile_ext) cudaFree(t.d_ftile_ext);
+    if (t.d_wtile_ext) cudaFree(t.d_wtile_ext);
+    if (t.d_ftile_rng) cudaFree(t.d_ftile_rng);
+    if (t.d_wtile_rng) cudaFree(t.d_wtile_rng);
+    if (t.d_ptile_ext) cudaFree(t.d_ptile_ext);
+    if (t.d_ptile_rng) cudaFree(t.d_ptile_rng);
     if (t.d_wactive) cudaFree(t.d_wactive);
     if (t.d_n_wactive) cudaFree(t.d_n_wactive);
     t = TileState();
