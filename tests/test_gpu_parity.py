@@ -156,6 +156,35 @@ def test_kick_dam_break_3d_medium(oracle):
     check_against_oracle(fluid, wall, u, v)
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("smem,list_len", [(24 * 1024, 16), (12 * 1024, 8)])
+def test_chunked_staging_small_shared_memory(oracle, monkeypatch, smem, list_len):
+    """Neighbourhoods that do not fit into the staging area are swept in chunks of rows (or pieces
+    of one row) and lists that fill up are drained early: force both with a tiny shared-memory
+    budget (tuning overrides read at tpb_create) and require the same parity and neighbour sets."""
+    monkeypatch.setenv("TPB_TILE_SMEM", str(smem))
+    monkeypatch.setenv("TPB_TILE_LIST", str(list_len))
+    monkeypatch.setenv("TPB_TILE_LIST_SPLIT", str(list_len))
+    fluid, wall, _ = examples.dam_break_3d(0.05)
+    u, v = examples.perturbed_state(fluid)
+    check_against_oracle(fluid, wall, u, v)
+    fluid, wall, _ = examples.dam_break_2d(20)
+    u, v = examples.perturbed_state(fluid)
+    check_against_oracle(fluid, wall, u, v)
+    fluid, wall, _ = examples.dam_break_3d(0.1)
+    u, _ = examples.perturbed_state(fluid)
+    semi, ode = make_semi(fluid, wall)
+    u_ode = np.ascontiguousarray(u).reshape(-1)
+    R_f = float(fluid.eltype.type(2) * fluid.smoothing_length)
+    R_w = float(wall.eltype.type(2) * wall.boundary_model.smoothing_length)
+    for (a, b, xa, xb, R) in [(fluid, fluid, u, u, R_f), (fluid, wall, u, wall.coordinates, R_f),
+                              (wall, fluid, wall.coordinates, u, R_w)]:
+        gi, gj = semi.neighbor_pairs(a, b, u_ode)
+        oi, oj = oracle.neighbor_pairs(xa, xb, R, dtype=fluid.eltype, grid=True)
+        assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
+    semi.close()
+
+
 @pytest.mark.parametrize("example", ["dam_break_2d", "hydrostatic_2d"])
 def test_kick_summation_density(oracle, example):
     """SummationDensity variant (density_calculators.jl:26-50; dam_break_2d variant in

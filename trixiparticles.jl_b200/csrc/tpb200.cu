@@ -215,6 +215,9 @@ int exclusive_scan(Semi &s, const int *d_in, int n, int *d_out)
 
 template <int ND, typename T, typename CT>
 struct Ops {
+    // threads per target particle in the tile sweeps (tpb_tiles.cuh): the Float32 kernels fit
+    // 2 x 384 threads into the register file; the Float64 ones keep one thread per target
+    static constexpr int KS = std::is_same<T, float>::value && std::is_same<CT, float>::value ? TPB_SPLIT : 1;
     static constexpr int nv(const Semi &s) { return s.fp.density_calculator == TPB_DENSITY_SUMMATION ? ND : ND + 1; }
 
     // ---- counting sort of one point set into the shared grid: key/slot/count/scan/scatter
@@ -346,11 +349,12 @@ struct Ops {
         k.p_off = (T)s.wp.pressure_offset;
         k.clip = s.wp.clip_negative_pressure;
         if (use_tiles(s)) {
-            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, s.tiles.list_len);
-            const size_t smem = tile_smem_bytes<T, CT>(cap, s.tiles.list_len);
+            const int list_len = s.tiles.list(KS);
+            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, list_len, KS);
+            const size_t smem = tile_smem_bytes<T, CT>(cap, list_len, KS);
             static bool attr_set = false;
             if (!attr_set) {
-                int rc = set_smem(s, k_adami_tiles<ND, T, CT, KERNEL>, 227 * 1024);
+                int rc = set_smem(s, k_adami_tiles<KS, ND, T, CT, KERNEL>, 227 * 1024);
                 if (rc) return rc;
                 attr_set = true;
             }
@@ -362,11 +366,11 @@ struct Ops {
                    s.tiles.d_wrow_tile_start + s.tiles.nrows, s.tiles.d_wtile_desc, (const V4<CT> *)s.d_Aw,
                    s.d_fcell_start, rho_empty, (V2<T> *)s.d_Ww, (T *)s.d_volw, s.tiles.d_wactive,
                    s.tiles.d_n_wactive, s.tiles.d_wtile_rng, s.tiles.d_wtile_ext);
-            LAUNCH(s, (k_adami_tiles<ND, T, CT, KERNEL>), s.tiles.max_wtiles, TILE_TB, smem, g,
+            LAUNCH(s, (k_adami_tiles<KS, ND, T, CT, KERNEL>), s.tiles.max_wtiles, KS * TILE_TB, smem, g,
                    s.tiles.d_n_wactive, s.tiles.d_wactive, s.tiles.d_wtile_desc, s.tiles.d_wtile_ext,
                    s.tiles.d_wtile_rng, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
                    s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
-                   s.interaction[1][0], k, (V2<T> *)s.d_Ww, (T *)s.d_volw, cap, s.tiles.list_len);
+                   s.interaction[1][0], k, (V2<T> *)s.d_Ww, (T *)s.d_volw, cap, list_len);
             return TPB_OK;
         }
         LAUNCH(s, (k_adami<ND, T, CT, KERNEL>), cdiv(n, 128), 128, 0, n, g,
@@ -390,20 +394,21 @@ struct Ops {
         int has_wall = s.n_w > 0 && s.interaction[0][1];
         s.stats.interact_variant_used = use_tiles(s) ? 2 : 1;
         if (use_tiles(s)) {
-            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, s.tiles.list_len);
-            const size_t smem = tile_smem_bytes<T, CT>(cap, s.tiles.list_len);
+            const int list_len = s.tiles.list(KS);
+            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, list_len, KS);
+            const size_t smem = tile_smem_bytes<T, CT>(cap, list_len, KS);
             static bool attr_set = false;
             if (!attr_set) {
-                int rc = set_smem(s, k_interact_tiles<ND, T, CT, KERNEL, DENS>, 227 * 1024);
+                int rc = set_smem(s, k_interact_tiles<KS, ND, T, CT, KERNEL, DENS>, 227 * 1024);
                 if (rc) return rc;
                 attr_set = true;
             }
-            LAUNCH(s, (k_interact_tiles<ND, T, CT, KERNEL, DENS>), s.tiles.max_ftiles, TILE_TB, smem, g,
+            LAUNCH(s, (k_interact_tiles<KS, ND, T, CT, KERNEL, DENS>), s.tiles.max_ftiles, KS * TILE_TB, smem, g,
                    s.tiles.d_frow_tile_start + s.tiles.nrows, s.tiles.d_ftile_desc, s.tiles.d_ftile_ext,
                    s.tiles.d_ftile_rng, s.d_fcell_start, (const V4<CT> *)s.d_A,
                    (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f, s.interaction[0][0], has_wall,
                    s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv,
-                   (int)s.n_tgt, cap, s.tiles.list_len);
+                   (int)s.n_tgt, cap, list_len);
             return TPB_OK;
         }
         LAUNCH(s, (k_interact_pp<ND, T, CT, KERNEL, DENS>), cdiv(n, 128), 128, 0, n, g,
@@ -575,9 +580,10 @@ struct Ops {
         CUDA_TRY(&s, cudaMalloc(&d_counter, sizeof(unsigned long long)));
         CUDA_TRY(&s, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), s.stream));
         if (n_x > 0 && use_tiles(s)) {
-            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, s.tiles.list_len);
-            const size_t smem = tile_smem_bytes<T, CT>(cap, s.tiles.list_len);
-            int rc2 = set_smem(s, k_pairs_tiles<ND, T, CT>, 227 * 1024);
+            const int list_len = s.tiles.list(KS);
+            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, list_len, KS);
+            const size_t smem = tile_smem_bytes<T, CT>(cap, list_len, KS);
+            int rc2 = set_smem(s, k_pairs_tiles<KS, ND, T, CT>, 227 * 1024);
             if (rc2) return rc2;
             const int max_tiles = x_fluid ? s.tiles.max_ftiles : s.tiles.max_wtiles;
             const int *n_tiles = (x_fluid ? s.tiles.d_frow_tile_start : s.tiles.d_wrow_tile_start) + s.tiles.nrows;
@@ -585,13 +591,13 @@ struct Ops {
                    s.xsplit, n_tiles, x_fluid ? s.tiles.d_ftile_desc : s.tiles.d_wtile_desc,
                    x_fluid ? s.d_fcell_start : s.d_wcell_start, y_fluid ? s.d_fcell_start : s.d_wcell_start,
                    (const int *)nullptr, s.tiles.d_ptile_rng, 9, s.tiles.d_ptile_ext);
-            LAUNCH(s, (k_pairs_tiles<ND, T, CT>), max_tiles, TILE_TB,
+            LAUNCH(s, (k_pairs_tiles<KS, ND, T, CT>), max_tiles, KS * TILE_TB,
                    smem, g, n_tiles,
                    x_fluid ? s.tiles.d_ftile_desc : s.tiles.d_wtile_desc, s.tiles.d_ptile_ext, s.tiles.d_ptile_rng,
                    (const V4<CT> *)(x_fluid ? s.d_A : s.d_Aw), x_fluid ? s.d_perm_f : s.d_perm_w,
                    y_fluid ? s.d_fcell_start : s.d_wcell_start,
                    (const V4<CT> *)(y_fluid ? s.d_A : s.d_Aw), y_fluid ? s.d_perm_f : s.d_perm_w, r2,
-                   (long long)capacity, d_oi, d_oj, d_counter, cap, s.tiles.list_len);
+                   (long long)capacity, d_oi, d_oj, d_counter, cap, list_len);
         } else if (n_x > 0)
             LAUNCH(s, (k_pairs<ND, T, CT>), cdiv(n_x, 128), 128, 0, n_x,
                    (x_fluid ? s.d_fcell_start : s.d_wcell_start) + s.ncells, g,

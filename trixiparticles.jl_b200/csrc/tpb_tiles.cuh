@@ -19,6 +19,12 @@
 //   phase 2  walk the list densely (all lanes busy): exact reference predicate
 //            d^2 <= R^2 (bit-exact arithmetic, tpb_device.cuh) and the pair physics.
 // Accumulators live in registers; each particle's dv is written once; no atomics.
+//
+// KS threads per target ("split", KS = 3 for Float32): thread k of a target scans every KS-th group
+// of four candidates of each neighbour row, so a block of KS * 128 threads shares ONE staged tile.
+// Shared memory limits an SM to two tiles; the split raises the resident warps from 8 to 24, which
+// is what hides the shared-memory and ALU latencies of both phases.  The KS partial sums of a
+// target are combined through shared memory in a fixed order (tile_reduce).
 #pragma once
 #include <algorithm>
 #include <cstdlib>
@@ -27,10 +33,19 @@
 #include "tpb_device.cuh"
 #include "tpb_sweeps.cuh"
 
+// tuning knobs (compile time)
+#ifndef TPB_P2_UNROLL
+#define TPB_P2_UNROLL 4  // pairs in flight in phase 2
+#endif
+#ifndef TPB_SPLIT
+#define TPB_SPLIT 3  // threads per target particle in the Float32 sweeps
+#endif
+
 namespace tpb {
 
-constexpr int TILE_TB = 128;      // threads (= max target particles) per tile
+constexpr int TILE_TB = 128;      // target particles per tile; a block has KS * TILE_TB threads
 constexpr int TILE_MAXSEG = 12;   // segments per staged chunk (>= 3^(ND-1))
+constexpr int TILE_TABW = 16;     // cell_start entries per neighbour row kept in shared memory
 
 // ------------------------------------------------------------------ PTX helpers (sm_100a)
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -159,6 +174,10 @@ struct TileHdr {
     int q, gpos;       // staging cursor: next row, next record in it
     int nseg, last;    // segments of the staged chunk; last: nothing left to stage after it
     int seg_row[TILE_MAXSEG], seg_begin[TILE_MAXSEG], seg_end[TILE_MAXSEG], seg_base[TILE_MAXSEG];
+    // cell_start of the current neighbour set over the cells {cxmin - sx .. cxmax + sx + 1} of
+    // every neighbour row (tab_w entries per row; 0: tile too long, read global memory instead)
+    int tab_w;
+    int tab[9 * TILE_TABW];
 };
 constexpr int TILE_HDR_BYTES = 16 + ((sizeof(TileHdr) + 15) / 16) * 16;  // mbarrier + header
 constexpr int TILE_ROWTAB_BYTES = 0;
@@ -168,17 +187,17 @@ template <typename T, typename CT>
 struct TileSmem {
     uint64_t *bar;
     TileHdr *hdr;
-    unsigned short *list;  // [list_len][TILE_TB]
+    unsigned short *list;  // [list_len][nt], nt = threads per block
     V4<CT> *tA;            // [cap]
     unsigned char *tB;     // [cap] of V4<T> (fluid neighbours) or V2<T> (wall neighbours)
     T *tP;                 // [cap]
     int cap, list_len;
-    __device__ TileSmem(unsigned char *base, int cap_, int list_len_) : cap(cap_), list_len(list_len_)
+    __device__ TileSmem(unsigned char *base, int cap_, int list_len_, int nt) : cap(cap_), list_len(list_len_)
     {
         bar = (uint64_t *)base;
         hdr = (TileHdr *)(base + 16);
         list = (unsigned short *)(base + TILE_HDR_BYTES);
-        unsigned char *p = base + TILE_HDR_BYTES + (size_t)list_len * TILE_TB * sizeof(unsigned short);
+        unsigned char *p = base + TILE_HDR_BYTES + (size_t)list_len * nt * sizeof(unsigned short);
         tA = (V4<CT> *)p;
         p += (size_t)cap * sizeof(V4<CT>);
         tB = p;
@@ -186,11 +205,17 @@ struct TileSmem {
         tP = (T *)p;
     }
 };
+// bytes per staged record
 template <typename T, typename CT>
-inline size_t tile_smem_bytes(int cap, int list_len)
+constexpr size_t tile_record_bytes()
 {
-    return TILE_HDR_BYTES + TILE_ROWTAB_BYTES + (size_t)list_len * TILE_TB * sizeof(unsigned short) +
-           (size_t)cap * (sizeof(V4<CT>) + sizeof(V4<T>) + sizeof(T));
+    return sizeof(V4<CT>) + sizeof(V4<T>) + sizeof(T);
+}
+template <typename T, typename CT>
+inline size_t tile_smem_bytes(int cap, int list_len, int ks = 1)
+{
+    return TILE_HDR_BYTES + TILE_ROWTAB_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short) +
+           (size_t)cap * tile_record_bytes<T, CT>();
 }
 
 // Load the tile descriptor of this block into hdr (thread 0).
@@ -252,6 +277,29 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
 }
 
+// Appending to the private list.  The append position is never updated in place: a predicated
+// `@p add lpa, lpa, 256` right after `@p st [lpa]` has to wait until the store has read its
+// address register (a write-after-read stall of ~20 cycles per candidate, serialised over the
+// whole unrolled loop); `add` into a fresh register + `selp` keeps the chain at ALU latency.
+template <int ESTEP>
+__device__ __forceinline__ uint32_t list_append(uint32_t lpa, uint32_t idx, bool pass)
+{
+    uint32_t next;
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 ".reg .b32 t;\n"
+                 ".reg .b16 h;\n"
+                 "setp.ne.u32 p, %2, 0;\n"
+                 "cvt.u16.u32 h, %3;\n"
+                 "@p st.shared.u16 [%1], h;\n"
+                 "add.u32 t, %1, %4;\n"
+                 "selp.u32 %0, t, %1, p;\n"
+                 "}"
+                 : "=r"(next)
+                 : "r"(lpa), "r"((uint32_t)pass), "r"(idx), "n"(ESTEP)
+                 : "memory");
+    return next;
+}
 // One neighbour set as the sweep sees it.  R1 = second record type (V4<T> fluid: v, rho;
 // V2<T> wall: p, rho); HAS_P: a third scalar array (fluid pressure).
 template <typename T, typename CT, typename R1_, bool HAS_P_>
@@ -269,7 +317,8 @@ struct NbSet {
 // fit into the staging area, then lane q issues the TMA copies of row q itself -- no serial
 // loop; otherwise the chunked path of tile_sweep_staged takes over.
 template <int ND, typename T, typename CT, typename NB>
-__device__ __forceinline__ void tile_stage(TileSmem<T, CT> &sm, const NB &nb, const int2 *__restrict__ rng)
+__device__ __forceinline__ void tile_stage(TileSmem<T, CT> &sm, const NB &nb, const int2 *__restrict__ rng,
+                                           int sx, int n0, int n1)
 {
     using R1 = typename NB::R1;
     constexpr int NROWS = ND == 3 ? 9 : 3;
@@ -284,6 +333,18 @@ __device__ __forceinline__ void tile_stage(TileSmem<T, CT> &sm, const NB &nb, co
         g1 = r.y;
         hdr->g0[tid] = g0;
         hdr->g1[tid] = g1;
+    }
+    {
+        // per-lane candidate windows come from this table instead of global memory
+        const int w = hdr->cxmax - hdr->cxmin + 2 * sx + 2;
+        const bool fits = w <= TILE_TABW;
+        if (tid == 0) hdr->tab_w = fits ? w : 0;
+        if (fits)
+            for (int k = tid; k < NROWS * w; k += 32) {
+                const int q = k / w, c = k - q * w;
+                const int dy = q % 3 - 1, dz = ND == 3 ? q / 3 - 1 : 0;
+                hdr->tab[k] = nb.cell_start[(hdr->cxmin - sx + c) + n0 * ((hdr->cy + dy) + n1 * (hdr->cz + dz))];
+            }
     }
     const int a = g0 & ~3;  // 4 records: every array stays 16-byte aligned
     const int len = g1 > g0 ? ((g1 + 3) & ~3) - a : 0;
@@ -325,33 +386,35 @@ __device__ __forceinline__ void tile_stage(TileSmem<T, CT> &sm, const NB &nb, co
 
 // Sweep all neighbours (of one set) of the tile's targets after tile_stage and a block barrier.
 // `body(xj, bj, pj)` is called for every candidate that passed the filter; it applies the exact
-// predicate itself.  Must be called by all threads of the block.
-template <int ND, typename T, typename CT, typename NB, typename BODY>
+// predicate itself.  Must be called by all KS * TILE_TB threads of the block; thread
+// `threadIdx.x` works for target `threadIdx.x % TILE_TB` and takes the groups of four candidates
+// number kg, kg + KS, ... (kg = threadIdx.x / TILE_TB) of every neighbour row.
+template <int KS, int ND, typename T, typename CT, typename NB, typename BODY>
 __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const GridConst<CT> &g, const NB &nb,
                                                   bool valid, int cx, const V4<CT> &xi, T radius2,
                                                   uint32_t &parity, BODY &&body)
 {
     using R1 = typename NB::R1;
     constexpr int NROWS = ND == 3 ? 9 : 3;
+    constexpr int NT = KS * TILE_TB;  // threads per block
     constexpr uint32_t REC_BYTES = sizeof(V4<CT>) + sizeof(R1) + (NB::HAS_P ? sizeof(T) : 0);
     const int tid = threadIdx.x;
+    const int kg = KS > 1 ? tid / TILE_TB : 0;  // warp-uniform
     TileHdr *hdr = sm.hdr;
     R1 *tB = (R1 *)sm.tB;
     const Filter<ND, T, CT> filter(radius2);
     bool staged = hdr->nseg > 0;
     if (!staged && hdr->last) return;
+    // chunked mode: thread 0 is about to rewrite the header every thread has just read
+    if (!staged) __syncthreads();
 
-    // private list: entry e of thread t lives at list[e * TILE_TB + t] (conflict-free)
+    // private list: entry e of thread t lives at list[e * NT + t] (conflict-free)
     unsigned short *const my_list = sm.list + tid;
     const uint32_t list_a = smem_u32(my_list);
-    const uint32_t list_end_a = list_a + (uint32_t)sm.list_len * TILE_TB * 2u;
-    constexpr uint32_t ESTEP = TILE_TB * 2u;  // bytes between consecutive entries of one thread
-    uint32_t lpa = list_a;                    // append position (shared-memory address)
+    const uint32_t list_end_a = list_a + (uint32_t)sm.list_len * NT * 2u;
+    constexpr uint32_t ESTEP = NT * 2u;  // bytes between consecutive entries of one thread
+    uint32_t lpa = list_a;               // append position (shared-memory address)
     auto room = [&](int n) { return lpa + n * ESTEP <= list_end_a; };
-    auto append = [&](uint32_t v) {
-        sts_u16(lpa, v);
-        lpa += ESTEP;
-    };
     auto visit = [&](int idx) {
         if constexpr (NB::HAS_P)
             body(sm.tA[idx], tB[idx], sm.tP[idx]);
@@ -361,14 +424,15 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
     auto flush = [&]() {
         const unsigned short *e = my_list;
         const unsigned short *const lp = my_list + (lpa - list_a) / 2u;
-        for (; e + 4 * TILE_TB <= lp; e += 4 * TILE_TB) {  // four pairs in flight for ILP
-            const int i0 = e[0], i1 = e[TILE_TB], i2 = e[2 * TILE_TB], i3 = e[3 * TILE_TB];
-            visit(i0);
-            visit(i1);
-            visit(i2);
-            visit(i3);
+        constexpr int PF = TPB_P2_UNROLL;  // pairs in flight for ILP
+        for (; e + PF * NT <= lp; e += PF * NT) {
+            int idx[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) idx[u] = e[u * NT];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) visit(idx[u]);
         }
-        for (; e < lp; e += TILE_TB) visit(e[0]);
+        for (; e < lp; e += NT) visit(e[0]);
         lpa = list_a;
     };
 
@@ -426,6 +490,7 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
         staged = false;
         const int nseg = hdr->nseg;
         const bool last = hdr->last != 0;
+        const int tab_w = hdr->tab_w;
         if (nseg == 0) break;
 
         mbar_wait(sm.bar, parity);
@@ -438,28 +503,51 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
             const int dy = q % 3 - 1, dz = ND == 3 ? q / 3 - 1 : 0;
             int j = 0, j1 = 0;
             if (valid) {
-                const int c0 = cell_linear(g, cx - g.sx, hdr->cy + dy, hdr->cz + dz);
-                j = max(nb.cell_start[c0], hdr->seg_begin[si]);
-                j1 = min(nb.cell_start[c0 + 2 * g.sx + 1], hdr->seg_end[si]);
+                int lo, hi;
+                if (tab_w > 0) {
+                    const int *row = hdr->tab + q * tab_w + (cx - hdr->cxmin);
+                    lo = row[0];
+                    hi = row[2 * g.sx + 1];
+                } else {
+                    const int c0 = cell_linear(g, cx - g.sx, hdr->cy + dy, hdr->cz + dz);
+                    lo = nb.cell_start[c0];
+                    hi = nb.cell_start[c0 + 2 * g.sx + 1];
+                }
+                j = max(lo, hdr->seg_begin[si]);
+                j1 = min(hi, hdr->seg_end[si]);
             }
             const int base = hdr->seg_base[si];
-            int t = base + j;            // tile index of the next candidate
-            const int t1 = base + j1;
+            const int t0 = base + j;      // tile index of the first candidate
+            const int t1 = base + j1;     // one past the last
+            // groups of four candidates counted from the lane's own first candidate
+            int t = t0 + 4 * kg;
+            constexpr int STEP = 4 * KS;
             while (true) {
                 // phase 1: filter candidates into the private list
-                constexpr int U = 8;
-                while (t + U <= t1 && room(U)) {
-                    V4<CT> xc[U];
+                while (t + STEP + 4 <= t1 && room(8)) {
+                    V4<CT> xc[8];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) xc[u] = sm.tA[t + u];
+                    for (int u = 0; u < 4; ++u) xc[u] = sm.tA[t + u];
 #pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        if (filter(xi, xc[u])) append((uint32_t)(t + u));
-                    t += U;
+                    for (int u = 0; u < 4; ++u) xc[4 + u] = sm.tA[t + STEP + u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + u), filter(xi, xc[u]));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + STEP + u), filter(xi, xc[4 + u]));
+                    t += 2 * STEP;
                 }
-                while (t < t1 && room(1)) {
-                    if (filter(xi, sm.tA[t])) append((uint32_t)t);
-                    ++t;
+                while (t < t1 && room(4)) {
+                    // one group, the last one possibly partial (records past t1 are staged
+                    // neighbours of other lanes or padding: read, never appended)
+                    V4<CT> xc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) xc[u] = sm.tA[t + u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + u), t + u < t1 && filter(xi, xc[u]));
+                    t += STEP;
                 }
                 if (!__any_sync(0xffffffffu, t < t1)) break;
                 flush();  // phase 2 (some list of the warp is full)
@@ -472,20 +560,50 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
 }
 
 // stage + sweep; must be called by all threads of the block
-template <int ND, typename T, typename CT, typename NB, typename BODY>
+template <int KS, int ND, typename T, typename CT, typename NB, typename BODY>
 __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<CT> &g, const NB &nb,
                                            const int2 *__restrict__ rng, bool valid, int cx,
                                            const V4<CT> &xi, T radius2, uint32_t &parity, BODY &&body)
 {
     __syncthreads();  // the previous sweep is done with hdr and the staged tile
-    if (threadIdx.x < 32) tile_stage<ND, T, CT>(sm, nb, rng);
+    if (threadIdx.x < 32) tile_stage<ND, T, CT>(sm, nb, rng, g.sx, g.n[0], g.n[1]);
     __syncthreads();
-    tile_sweep_staged<ND, T, CT>(sm, g, nb, valid, cx, xi, radius2, parity, body);
+    tile_sweep_staged<KS, ND, T, CT>(sm, g, nb, valid, cx, xi, radius2, parity, body);
+}
+
+// Combine the KS partial results of every target: afterwards the threads with
+// threadIdx.x < TILE_TB hold val = ((val_0 + val_1) + val_2) ...  Must be called by all threads
+// of the block after the last sweep (the scratch space is the list area).
+template <int KS, int NVAL, typename T, typename CT>
+__device__ __forceinline__ void tile_reduce(TileSmem<T, CT> &sm, T (&val)[NVAL])
+{
+    if constexpr (KS > 1) {
+        T *scratch = (T *)sm.list;  // [(KS - 1) * NVAL][TILE_TB]
+        const int ti = threadIdx.x % TILE_TB, kg = threadIdx.x / TILE_TB;
+        __syncthreads();  // every thread has drained its list
+        if (kg > 0) {
+#pragma unroll
+            for (int n = 0; n < NVAL; ++n) scratch[((kg - 1) * NVAL + n) * TILE_TB + ti] = val[n];
+        }
+        __syncthreads();
+        if (kg == 0) {
+#pragma unroll
+            for (int k = 1; k < KS; ++k)
+#pragma unroll
+                for (int n = 0; n < NVAL; ++n) val[n] += scratch[((k - 1) * NVAL + n) * TILE_TB + ti];
+        }
+    }
+}
+// list entries per thread that make the list area large enough for tile_reduce
+template <typename T>
+constexpr int tile_min_list_len(int ks, int nval)
+{
+    return ks > 1 ? ((ks - 1) * nval * (int)sizeof(T) + 2 * ks - 1) / (2 * ks) : 1;
 }
 
 // ------------------------------------------------------------------ interact! (variant 2)
-template <int ND, typename T, typename CT, int KERNEL, int DENS>
-__global__ void __launch_bounds__(TILE_TB, 2)
+template <int KS, int ND, typename T, typename CT, int KERNEL, int DENS>
+__global__ void __launch_bounds__(KS * TILE_TB, 2)
 k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
                  const int4 *__restrict__ tile_ext, const int2 *__restrict__ tile_rng,
                  const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
@@ -499,7 +617,7 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     const int tile = blockIdx.x;
     if (tile >= *n_tiles) return;
-    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len);
+    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
     const int2 *rng = tile_rng + (int64_t)tile * 18;
     const NbSet<T, CT, V4<T>, true> nb_f{fcell_start, A, B, P};
     if (threadIdx.x < 32) {
@@ -509,29 +627,35 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
             mbar_init(sm.bar, 1);
         }
         __syncwarp();
-        if (ff_enabled) tile_stage<ND, T, CT>(sm, nb_f, rng);
+        if (ff_enabled) tile_stage<ND, T, CT>(sm, nb_f, rng, g.sx, g.n[0], g.n[1]);
     }
-    __syncthreads();
-    const bool any_fw = sm.hdr->tot1 > 0;
-    const int s = sm.hdr->p0 + threadIdx.x;
+    // every thread reads the descriptor itself (one broadcast transaction) and starts loading its
+    // own particle while warp 0 is staging; the barrier below also publishes the header
+    const int4 desc = tile_desc[tile];
+    const int4 ext = tile_ext[tile];
+    const int s = desc.x + threadIdx.x % TILE_TB;
+    const bool in_tile = s < desc.y;
+    V4<CT> xi = {};
+    V4<T> bi = {};
+    T p_a = 0;
+    int orig = n_targets;
+    if (in_tile) {
+        orig = perm[s];
+        xi = A[s];
+        bi = B[s];
+        p_a = P[s];
+    }
     // slab ghosts (original index >= n_targets) are neighbours only: no dv is computed for them
-    const bool valid = s < sm.hdr->p1 && perm[s] < n_targets;
+    const bool valid = in_tile && orig < n_targets;
+    const bool any_fw = ext.w > 0;
     uint32_t parity = 0;
     if (!__syncthreads_or(valid)) {
         // ghost-only tile: let the copies in flight land before the shared memory is released
         if (ff_enabled && sm.hdr->nseg > 0) mbar_wait(sm.bar, parity);
         return;
     }
-    V4<CT> xi = {};
-    V4<T> bi = {};
-    T p_a = 0;
-    int cx = sm.hdr->cxmin, cy, cz;
-    if (valid) {
-        xi = A[s];
-        bi = B[s];
-        p_a = P[s];
-        cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
-    }
+    int cx = ext.x, cy, cz;
+    if (valid) cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
     const T rho_a = bi.w;
     const T v_a[3] = {bi.x, bi.y, bi.z};
 
@@ -543,9 +667,12 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
         pa_term = valid ? p_a / (rho_a * rho_a) : 0.f;
     }
 
-    T dv_ff[3] = {0, 0, 0}, drho_ff = 0;
+    // acc[0..3]: fluid-fluid sums (dv, drho); acc[4..7]: fluid-wall sums
+    T acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    T(&dv_ff)[3] = *reinterpret_cast<T(*)[3]>(acc);
+    T &drho_ff = acc[3];
     if (ff_enabled) {
-        tile_sweep_staged<ND, T, CT>(sm, g, nb_f, valid, cx, xi, k.radius2, parity,
+        tile_sweep_staged<KS, ND, T, CT>(sm, g, nb_f, valid, cx, xi, k.radius2, parity,
                               [&](const V4<CT> &xj, const V4<T> &bj, T pj) {
                                   if constexpr (FAST) {
                                       interact_pair_fast<ND, KERNEL, DENS, true>(
@@ -566,11 +693,12 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
                                   }
                               });
     }
-    T dv_fw[3] = {0, 0, 0}, drho_fw = 0;
+    T(&dv_fw)[3] = *reinterpret_cast<T(*)[3]>(acc + 4);
+    T &drho_fw = acc[7];
     if (has_wall && any_fw) {
         const T zero3[3] = {0, 0, 0};
         NbSet<T, CT, V2<T>, false> nb{wcell_start, Aw, Ww, nullptr};
-        tile_sweep<ND, T, CT>(sm, g, nb, rng + 9, valid, cx, xi, k.radius2, parity,
+        tile_sweep<KS, ND, T, CT>(sm, g, nb, rng + 9, valid, cx, xi, k.radius2, parity,
                               [&](const V4<CT> &xj, const V2<T> &wj, T) {
                                   if constexpr (FAST) {
                                       interact_pair_fast<ND, KERNEL, DENS, false>(
@@ -589,9 +717,10 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
                                   }
                               });
     }
-    if (!valid) return;
+    tile_reduce<KS, 8>(sm, acc);
+    if (!valid || threadIdx.x >= TILE_TB) return;
     // dv = ((0 + S_ff) + S_fw) + g [+ source]  (semidiscretization.jl:600, :809-829, :668-731)
-    const int64_t o = (int64_t)perm[s] * NV;
+    const int64_t o = (int64_t)orig * NV;
     T out[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
@@ -666,8 +795,8 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
 }
 
 // Targets: wall particles (active tiles over the wall's sorted order); neighbours: fluid.
-template <int ND, typename T, typename CT, int KERNEL>
-__global__ void __launch_bounds__(TILE_TB, 2)
+template <int KS, int ND, typename T, typename CT, int KERNEL>
+__global__ void __launch_bounds__(KS * TILE_TB, 2)
 k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__restrict__ active,
               const int4 *__restrict__ tile_desc, const int4 *__restrict__ tile_ext,
               const int2 *__restrict__ tile_rng, const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
@@ -678,13 +807,13 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     if ((int)blockIdx.x >= *n_active) return;
     const int tile = active[blockIdx.x];
-    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len);
+    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
     if (threadIdx.x == 0) {
         tile_locate(sm.hdr, g.n[1], tile_desc, tile_ext, tile);
         mbar_init(sm.bar, 1);
     }
     __syncthreads();
-    const int w = sm.hdr->p0 + threadIdx.x;
+    const int w = sm.hdr->p0 + threadIdx.x % TILE_TB;
     const bool valid = w < sm.hdr->p1;
     V4<CT> xi = {};
     int cx = sm.hdr->cxmin, cy, cz;
@@ -693,10 +822,11 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
         cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
     }
     uint32_t parity = 0;
-    T p = (T)0, vol = (T)0;
+    T acc[2] = {0, 0};
+    T &p = acc[0], &vol = acc[1];
     if (interaction_enabled) {
         NbSet<T, CT, V4<T>, true> nb{fcell_start, A, B, P};
-        tile_sweep<ND, T, CT>(sm, g, nb, tile_rng + (int64_t)tile * 9, valid, cx, xi, k.radius2, parity,
+        tile_sweep<KS, ND, T, CT>(sm, g, nb, tile_rng + (int64_t)tile * 9, valid, cx, xi, k.radius2, parity,
                               [&](const V4<CT> &xj, const V4<T> &bj, T pj) {
                                   T pd[3];
                                   const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
@@ -724,7 +854,8 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
                                   }
                               });
     }
-    if (!valid) return;
+    tile_reduce<KS, 2>(sm, acc);
+    if (!valid || threadIdx.x >= TILE_TB) return;
     if ((double)vol > 2.220446049250313e-16) p = p / vol;  // `volume > eps()`: eps(Float64)
     if (k.clip) p = p > (T)0 ? p : (T)0;
     V2<T> out;
@@ -738,8 +869,8 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
 // Test hook behind tpb_neighbor_pairs (variant 2): the same tile sweep, filter and window
 // clipping as interact!, with a body that records (orig_i, orig_j) of every pair accepted by
 // the exact predicate.  The neighbour permutation rides in the second record slot.
-template <int ND, typename T, typename CT>
-__global__ void __launch_bounds__(TILE_TB, 2)
+template <int KS, int ND, typename T, typename CT>
+__global__ void __launch_bounds__(KS * TILE_TB, 2)
 k_pairs_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
               const int4 *__restrict__ tile_ext, const int2 *__restrict__ tile_rng,
               const V4<CT> *__restrict__ X, const int *__restrict__ perm_x,
@@ -750,13 +881,13 @@ k_pairs_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__re
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     const int tile = blockIdx.x;
     if (tile >= *n_tiles) return;
-    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len);
+    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
     if (threadIdx.x == 0) {
         tile_locate(sm.hdr, g.n[1], tile_desc, tile_ext, tile);
         mbar_init(sm.bar, 1);
     }
     __syncthreads();
-    const int s = sm.hdr->p0 + threadIdx.x;
+    const int s = sm.hdr->p0 + threadIdx.x % TILE_TB;
     const bool valid = s < sm.hdr->p1;
     V4<CT> xi = {};
     int cx = sm.hdr->cxmin, cy, cz, orig_i = 0;
@@ -767,7 +898,7 @@ k_pairs_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__re
     }
     uint32_t parity = 0;
     NbSet<T, CT, int, false> nb{ycell_start, Y, perm_y, nullptr};
-    tile_sweep<ND, T, CT>(sm, g, nb, tile_rng + (int64_t)tile * 9, valid, cx, xi, radius2, parity, [&](const V4<CT> &xj, const int &pj, T) {
+    tile_sweep<KS, ND, T, CT>(sm, g, nb, tile_rng + (int64_t)tile * 9, valid, cx, xi, radius2, parity, [&](const V4<CT> &xj, const int &pj, T) {
         T pd[3];
         if (pos_diff_d2<ND, T, CT>(xi, xj, pd) <= radius2) {
             unsigned long long at = atomicAdd(counter, 1ull);
@@ -798,6 +929,8 @@ struct TileState {
     int max_ftiles = 0, max_wtiles = 0;
     int smem_budget = 112 * 1024;  // bytes per block: two blocks per SM
     int list_len = 160;            // private list entries per thread (one flush per sweep in 3-D)
+    int list_len_split = 64;       // the same with TPB_SPLIT threads per target
+    int list(int ks) const { return ks > 1 ? list_len_split : list_len; }
 };
 
 inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
@@ -806,6 +939,9 @@ inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
     // tuning overrides (bytes of shared memory per block, list entries per thread)
     if (const char *e = getenv("TPB_TILE_SMEM")) t.smem_budget = atoi(e);
     if (const char *e = getenv("TPB_TILE_LIST")) t.list_len = atoi(e);
+    if (const char *e = getenv("TPB_TILE_LIST_SPLIT")) t.list_len_split = atoi(e);
+    t.list_len = std::max(t.list_len, 8);  // tile_reduce's scratch space is the list area
+    t.list_len_split = std::max(t.list_len_split, (tile_min_list_len<double>(TPB_SPLIT, 8) + 7) & ~7);
     if (t.smem_budget > 227 * 1024) t.smem_budget = 227 * 1024;
     t.max_ftiles = (int)((n_f + TILE_TB - 1) / TILE_TB) + nrows;
     t.max_wtiles = (int)((n_w + TILE_TB - 1) / TILE_TB) + nrows;
@@ -847,12 +983,13 @@ inline void tiles_free(TileState &t)
 
 // records per staged chunk for a shared-memory budget (multiple of 4, 16-bit indexable)
 template <typename T, typename CT>
-inline int tile_capacity(int smem_budget, int list_len)
+inline int tile_capacity(int smem_budget, int list_len, int ks = 1)
 {
-    const size_t fixed = TILE_HDR_BYTES + TILE_ROWTAB_BYTES + (size_t)list_len * TILE_TB * sizeof(unsigned short);
-    const size_t rec = sizeof(V4<CT>) + sizeof(V4<T>) + sizeof(T);
-    int cap = (int)(((size_t)smem_budget - fixed) / rec);
+    const size_t fixed = TILE_HDR_BYTES + TILE_ROWTAB_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short);
+    const size_t rec = tile_record_bytes<T, CT>();
+    int cap = (size_t)smem_budget > fixed ? (int)(((size_t)smem_budget - fixed) / rec) : 0;
     cap &= ~3;
+    if (cap < 32) cap = 32;  // a budget below the fixed part is exceeded rather than refused
     return cap > 65532 ? 65532 : cap;
 }
 
