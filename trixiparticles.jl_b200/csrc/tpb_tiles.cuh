@@ -180,7 +180,7 @@ struct TileHdr {
     int tab[9 * TILE_TABW];
 };
 constexpr int TILE_HDR_BYTES = 16 + ((sizeof(TileHdr) + 15) / 16) * 16;  // mbarrier + header
-constexpr int TILE_ROWTAB_BYTES = 0;
+constexpr int TILE_RED_VALS = 4;  // values per thread tile_reduce can combine (needs 2x list entries)
 
 // shared-memory carve-up of one block
 template <typename T, typename CT>
@@ -197,7 +197,7 @@ struct TileSmem {
         bar = (uint64_t *)base;
         hdr = (TileHdr *)(base + 16);
         list = (unsigned short *)(base + TILE_HDR_BYTES);
-        unsigned char *p = base + TILE_HDR_BYTES + (size_t)list_len * nt * sizeof(unsigned short);
+        unsigned char *p = (unsigned char *)list + (size_t)list_len * nt * sizeof(unsigned short);
         tA = (V4<CT> *)p;
         p += (size_t)cap * sizeof(V4<CT>);
         tB = p;
@@ -214,15 +214,13 @@ constexpr size_t tile_record_bytes()
 template <typename T, typename CT>
 inline size_t tile_smem_bytes(int cap, int list_len, int ks = 1)
 {
-    return TILE_HDR_BYTES + TILE_ROWTAB_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short) +
+    return TILE_HDR_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short) +
            (size_t)cap * tile_record_bytes<T, CT>();
 }
 
 // Load the tile descriptor of this block into hdr (thread 0).
-__device__ __forceinline__ void tile_locate(TileHdr *hdr, int n1, const int4 *__restrict__ tile_desc,
-                                            const int4 *__restrict__ tile_ext, int tile)
+__device__ __forceinline__ void tile_locate(TileHdr *hdr, int n1, const int4 &d, const int4 &e)
 {
-    const int4 d = tile_desc[tile], e = tile_ext[tile];
     hdr->p0 = d.x;
     hdr->p1 = d.y;
     hdr->cy = d.z % n1;
@@ -318,7 +316,7 @@ struct NbSet {
 // loop; otherwise the chunked path of tile_sweep_staged takes over.
 template <int ND, typename T, typename CT, typename NB>
 __device__ __forceinline__ void tile_stage(TileSmem<T, CT> &sm, const NB &nb, const int2 *__restrict__ rng,
-                                           int sx, int n0, int n1)
+                                           int cxmin, int cxmax, int cy, int cz, int sx, int n0, int n1)
 {
     using R1 = typename NB::R1;
     constexpr int NROWS = ND == 3 ? 9 : 3;
@@ -326,25 +324,32 @@ __device__ __forceinline__ void tile_stage(TileSmem<T, CT> &sm, const NB &nb, co
     const int tid = threadIdx.x;
     TileHdr *hdr = sm.hdr;
     R1 *tB = (R1 *)sm.tB;
+    // all global loads first (row ranges and the per-lane window table are independent), so
+    // that the TMA copies start after ONE memory latency; the table is written out afterwards
     int g0 = 0, g1 = 0;
     if (tid < NROWS) {
         const int2 r = rng[tid];
         g0 = r.x;
         g1 = r.y;
+    }
+    // per-lane candidate windows come from this table instead of global memory
+    const int tab_w = cxmax - cxmin + 2 * sx + 2;
+    const bool tab_fits = tab_w <= TILE_TABW;
+    constexpr int NTV = (NROWS * TILE_TABW + 31) / 32;
+    int tv[NTV];
+#pragma unroll
+    for (int i = 0; i < NTV; ++i) {
+        const int k = tid + 32 * i;
+        tv[i] = 0;
+        if (tab_fits && k < NROWS * tab_w) {
+            const int q = k / tab_w, c = k - q * tab_w;
+            const int dy = q % 3 - 1, dz = ND == 3 ? q / 3 - 1 : 0;
+            tv[i] = nb.cell_start[(cxmin - sx + c) + n0 * ((cy + dy) + n1 * (cz + dz))];
+        }
+    }
+    if (tid < NROWS) {
         hdr->g0[tid] = g0;
         hdr->g1[tid] = g1;
-    }
-    {
-        // per-lane candidate windows come from this table instead of global memory
-        const int w = hdr->cxmax - hdr->cxmin + 2 * sx + 2;
-        const bool fits = w <= TILE_TABW;
-        if (tid == 0) hdr->tab_w = fits ? w : 0;
-        if (fits)
-            for (int k = tid; k < NROWS * w; k += 32) {
-                const int q = k / w, c = k - q * w;
-                const int dy = q % 3 - 1, dz = ND == 3 ? q / 3 - 1 : 0;
-                hdr->tab[k] = nb.cell_start[(hdr->cxmin - sx + c) + n0 * ((hdr->cy + dy) + n1 * (hdr->cz + dz))];
-            }
     }
     const int a = g0 & ~3;  // 4 records: every array stays 16-byte aligned
     const int len = g1 > g0 ? ((g1 + 3) & ~3) - a : 0;
@@ -381,6 +386,12 @@ __device__ __forceinline__ void tile_stage(TileSmem<T, CT> &sm, const NB &nb, co
         hdr->last = total == 0;  // no candidates at all (e.g. fluid far from any wall)
         hdr->q = 0;
         hdr->gpos = g0;
+    }
+    if (tid == 0) hdr->tab_w = tab_fits ? tab_w : 0;
+#pragma unroll
+    for (int i = 0; i < NTV; ++i) {
+        const int k = tid + 32 * i;
+        if (tab_fits && k < NROWS * tab_w) hdr->tab[k] = tv[i];
     }
 }
 
@@ -566,39 +577,66 @@ __device__ __forceinline__ void tile_sweep(TileSmem<T, CT> &sm, const GridConst<
                                            const V4<CT> &xi, T radius2, uint32_t &parity, BODY &&body)
 {
     __syncthreads();  // the previous sweep is done with hdr and the staged tile
-    if (threadIdx.x < 32) tile_stage<ND, T, CT>(sm, nb, rng, g.sx, g.n[0], g.n[1]);
+    if (threadIdx.x < 32)
+        tile_stage<ND, T, CT>(sm, nb, rng, sm.hdr->cxmin, sm.hdr->cxmax, sm.hdr->cy, sm.hdr->cz, g.sx, g.n[0],
+                              g.n[1]);
     __syncthreads();
     tile_sweep_staged<KS, ND, T, CT>(sm, g, nb, valid, cx, xi, radius2, parity, body);
 }
 
+// bar.sync / bar.arrive on barrier `id` (1..4, warp-uniform) for COUNT threads; the id is an
+// immediate so that the kernel reserves five hardware barriers, not all sixteen
+template <bool WAIT, int COUNT>
+__device__ __forceinline__ void named_barrier(int id)
+{
+#define TPB_BAR(ID)                                                                   \
+    if (WAIT)                                                                         \
+        asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");            \
+    else                                                                              \
+        asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+    switch (id) {
+    case 1: TPB_BAR(1) break;
+    case 2: TPB_BAR(2) break;
+    case 3: TPB_BAR(3) break;
+    default: TPB_BAR(4) break;
+    }
+#undef TPB_BAR
+}
+
 // Combine the KS partial results of every target: afterwards the threads with
-// threadIdx.x < TILE_TB hold val = ((val_0 + val_1) + val_2) ...  Must be called by all threads
-// of the block after the last sweep (the scratch space is the list area).
+// threadIdx.x < TILE_TB hold val = ((val_0 + val_1) + val_2) ...; the other threads are done.
+// Only the KS warps that share 32 targets meet (named barrier 1 + warp % 4): the writers
+// arrive and leave, the reader waits for them -- nobody waits for the slowest warp of the block.
+// Scratch space without extra shared memory: the 16-bit list slots of entry e of the threads
+// 2m and 2m + 1 form one aligned 32-bit word; thread 2m parks its values in the words of the
+// entries 0..3, thread 2m + 1 in those of the entries 4..7 -- slots only this pair of lanes
+// ever touches, so warps that are still sweeping are not disturbed.
 template <int KS, int NVAL, typename T, typename CT>
 __device__ __forceinline__ void tile_reduce(TileSmem<T, CT> &sm, T (&val)[NVAL])
 {
+    static_assert(NVAL <= TILE_RED_VALS, "tile_reduce: scratch space too small");
     if constexpr (KS > 1) {
-        T *scratch = (T *)sm.list;  // [(KS - 1) * NVAL][TILE_TB]
+        static_assert(sizeof(T) == 4, "tile_reduce: 32-bit values only");
+        constexpr int NT = KS * TILE_TB;
         const int ti = threadIdx.x % TILE_TB, kg = threadIdx.x / TILE_TB;
-        __syncthreads();  // every thread has drained its list
+        const int bar_id = 1 + ti / 32;
+        auto slot = [&](int tid, int n) {
+            return reinterpret_cast<T *>(sm.list + (n + TILE_RED_VALS * (tid & 1)) * NT + (tid & ~1));
+        };
+        __syncwarp();  // both lanes of a pair have drained their lists
         if (kg > 0) {
 #pragma unroll
-            for (int n = 0; n < NVAL; ++n) scratch[((kg - 1) * NVAL + n) * TILE_TB + ti] = val[n];
-        }
-        __syncthreads();
-        if (kg == 0) {
+            for (int n = 0; n < NVAL; ++n) *slot(threadIdx.x, n) = val[n];
+            __threadfence_block();
+            named_barrier<false, 32 * KS>(bar_id);
+        } else {
+            named_barrier<true, 32 * KS>(bar_id);
 #pragma unroll
             for (int k = 1; k < KS; ++k)
 #pragma unroll
-                for (int n = 0; n < NVAL; ++n) val[n] += scratch[((k - 1) * NVAL + n) * TILE_TB + ti];
+                for (int n = 0; n < NVAL; ++n) val[n] += *slot(k * TILE_TB + ti, n);
         }
     }
-}
-// list entries per thread that make the list area large enough for tile_reduce
-template <typename T>
-constexpr int tile_min_list_len(int ks, int nval)
-{
-    return ks > 1 ? ((ks - 1) * nval * (int)sizeof(T) + 2 * ks - 1) / (2 * ks) : 1;
 }
 
 // ------------------------------------------------------------------ interact! (variant 2)
@@ -620,19 +658,21 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
     const int2 *rng = tile_rng + (int64_t)tile * 18;
     const NbSet<T, CT, V4<T>, true> nb_f{fcell_start, A, B, P};
-    if (threadIdx.x < 32) {
-        // warp 0 starts the TMA copies of the fluid sweep before anything else happens
-        if (threadIdx.x == 0) {
-            tile_locate(sm.hdr, g.n[1], tile_desc, tile_ext, tile);
-            mbar_init(sm.bar, 1);
-        }
-        __syncwarp();
-        if (ff_enabled) tile_stage<ND, T, CT>(sm, nb_f, rng, g.sx, g.n[0], g.n[1]);
-    }
     // every thread reads the descriptor itself (one broadcast transaction) and starts loading its
     // own particle while warp 0 is staging; the barrier below also publishes the header
     const int4 desc = tile_desc[tile];
     const int4 ext = tile_ext[tile];
+    if (threadIdx.x < 32) {
+        // warp 0 starts the TMA copies of the fluid sweep before anything else happens
+        if (threadIdx.x == 0) {
+            tile_locate(sm.hdr, g.n[1], desc, ext);
+            mbar_init(sm.bar, 1);
+        }
+        __syncwarp();
+        if (ff_enabled)
+            tile_stage<ND, T, CT>(sm, nb_f, rng, ext.x, ext.y, desc.z % g.n[1], desc.z / g.n[1], g.sx, g.n[0],
+                                  g.n[1]);
+    }
     const int s = desc.x + threadIdx.x % TILE_TB;
     const bool in_tile = s < desc.y;
     V4<CT> xi = {};
@@ -717,21 +757,24 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
                                   }
                               });
     }
-    tile_reduce<KS, 8>(sm, acc);
+    // the threads of a target combine (S_ff + S_fw); Float64 (one thread per target) keeps the
+    // reference's order dv = ((0 + S_ff) + S_fw) + g
+    T part[4] = {acc[0] + acc[4], acc[1] + acc[5], acc[2] + acc[6], acc[3] + acc[7]};
+    tile_reduce<KS, 4>(sm, part);
     if (!valid || threadIdx.x >= TILE_TB) return;
     // dv = ((0 + S_ff) + S_fw) + g [+ source]  (semidiscretization.jl:600, :809-829, :668-731)
     const int64_t o = (int64_t)orig * NV;
     T out[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
-        T val = dv_ff[d] + dv_fw[d];
+        T val = part[d];
         if (src.any) {
             val += src.acc[d];
             if (src.damping != (T)0) val += -src.damping * v_a[d];
         }
         out[d] = val;
     }
-    if (DENS == 0) out[ND] = drho_ff + drho_fw;
+    if (DENS == 0) out[ND] = part[3];
     // one 16-byte store per particle where the layout allows it (3-D Float32 with density):
     // dv may be a mapped host buffer, where every store instruction is a PCIe write
     if (NV == 4 && sizeof(T) == 4 && (reinterpret_cast<uintptr_t>(dv) & 15) == 0) {
@@ -809,7 +852,7 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
     const int tile = active[blockIdx.x];
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
     if (threadIdx.x == 0) {
-        tile_locate(sm.hdr, g.n[1], tile_desc, tile_ext, tile);
+        tile_locate(sm.hdr, g.n[1], tile_desc[tile], tile_ext[tile]);
         mbar_init(sm.bar, 1);
     }
     __syncthreads();
@@ -883,7 +926,7 @@ k_pairs_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__re
     if (tile >= *n_tiles) return;
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
     if (threadIdx.x == 0) {
-        tile_locate(sm.hdr, g.n[1], tile_desc, tile_ext, tile);
+        tile_locate(sm.hdr, g.n[1], tile_desc[tile], tile_ext[tile]);
         mbar_init(sm.bar, 1);
     }
     __syncthreads();
@@ -940,8 +983,8 @@ inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
     if (const char *e = getenv("TPB_TILE_SMEM")) t.smem_budget = atoi(e);
     if (const char *e = getenv("TPB_TILE_LIST")) t.list_len = atoi(e);
     if (const char *e = getenv("TPB_TILE_LIST_SPLIT")) t.list_len_split = atoi(e);
-    t.list_len = std::max(t.list_len, 8);  // tile_reduce's scratch space is the list area
-    t.list_len_split = std::max(t.list_len_split, (tile_min_list_len<double>(TPB_SPLIT, 8) + 7) & ~7);
+    t.list_len = std::max(t.list_len, 8);
+    t.list_len_split = std::max(t.list_len_split, 8);
     if (t.smem_budget > 227 * 1024) t.smem_budget = 227 * 1024;
     t.max_ftiles = (int)((n_f + TILE_TB - 1) / TILE_TB) + nrows;
     t.max_wtiles = (int)((n_w + TILE_TB - 1) / TILE_TB) + nrows;
@@ -985,7 +1028,7 @@ inline void tiles_free(TileState &t)
 template <typename T, typename CT>
 inline int tile_capacity(int smem_budget, int list_len, int ks = 1)
 {
-    const size_t fixed = TILE_HDR_BYTES + TILE_ROWTAB_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short);
+    const size_t fixed = TILE_HDR_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short);
     const size_t rec = tile_record_bytes<T, CT>();
     int cap = (size_t)smem_budget > fixed ? (int)(((size_t)smem_budget - fixed) / rec) : 0;
     cap &= ~3;
