@@ -29,7 +29,7 @@ def test_layout_partitions_every_particle_once():
         assert np.array_equal(allidx, np.arange(fluid.nparticles))
         counts = [len(o) for o in owned]
         assert max(counts) - min(counts) <= 2 * 20 + 1  # at most one lattice column apart
-        assert layout.halo == pytest.approx(3 * R)
+        assert layout.halo == pytest.approx(2.25 * R)  # R_fluid + R_wall + skin, skin = R / 4
 
 
 def test_layout_rejects_slabs_thinner_than_halo():
@@ -50,7 +50,7 @@ def test_local_mailbox_exchange_matches_definition():
     for r in range(world):
         _, _, owned, _ = local_systems(fluid, wall, layout, r)
         parts.append(owned)
-        halos.append(HaloExchange(layout, r, mb.transport(r)))
+        halos.append(HaloExchange(layout, r, mb.transport(r), wall.coordinates))
     tu = [torch.from_numpy(u[o]) for o in parts]
     tv = [torch.from_numpy(v[o]) for o in parts]
     tm = [torch.from_numpy(fluid.mass[o]) for o in parts]
@@ -66,12 +66,21 @@ def test_local_mailbox_exchange_matches_definition():
         live = ~torch.isnan(ug[:, 0])
         lo, hi = layout.planes[r], layout.planes[r + 1]
         x = u[:, 0]
-        expect = np.nonzero(((x >= lo - layout.halo) & (x < lo)) | ((x >= hi) & (x < hi + layout.halo)))[0]
+        depth = np.where(x < lo, lo - x, x - hi)        # distance behind the slab's faces
+        outside = (x < lo) | (x >= hi)
+        within_halo = np.nonzero(outside & (depth <= layout.halo))[0]
+        # needed: everything within R_fluid + skin of a face, and deeper only what is within
+        # R_wall of a wall particle (Adami pressure of the wall particles the slab interacts with)
+        from scipy.spatial import cKDTree
+        d_wall, _ = cKDTree(wall.coordinates.astype(np.float64)).query(u.astype(np.float64))
+        needed = np.nonzero(outside & ((depth < layout.direct) | ((depth < layout.halo) & (d_wall <= R))))[0]
         got = {tuple(row) for row in ug[live].numpy()}
-        assert got == {tuple(row) for row in u[expect]}
-        # masses of the live slots are the masses of exactly those particles
-        assert sorted(halos[r].ghost_mass[live].tolist()) == sorted(fluid.mass[expect].tolist())
-        assert int(live.sum()) < len(ug)  # the candidate set is a strict superset (skin)
+        assert got <= {tuple(row) for row in u[within_halo]}
+        assert got >= {tuple(row) for row in u[needed]}
+        assert len(got) < len(within_halo)  # the second radius is a shell along the walls only
+        got_mass = dict(zip((tuple(row) for row in ug[live].numpy()), halos[r].ghost_mass[live].tolist()))
+        for i in needed:
+            assert got_mass[tuple(u[i])] == fluid.mass[i]
 
 
 def _free_port():
@@ -91,7 +100,7 @@ def _worker(rank, world, port, out):
         u, v = examples.perturbed_state(fluid)
         ref = adapter.kick(fluid, wall, u, v)["dv"]
         fluid_k, wall_k, owned, widx = local_systems(fluid, wall, layout, rank)
-        halo = HaloExchange(layout, rank, DistTransport(rank, world))
+        halo = HaloExchange(layout, rank, DistTransport(rank, world), wall.coordinates)
         tu, tv, tm = torch.from_numpy(u[owned]), torch.from_numpy(v[owned]), torch.from_numpy(fluid.mass[owned])
         assert halo.check_drift(tu)
         halo.setup(tu, tv, tm)

@@ -15,11 +15,14 @@ design for it.  One process per GPU owns the fluid particles of one slab `[x_k, 
   3. `tpb_kick` runs the usual rebuild + Adami + interact on the local set.
 
 `halo = R_fluid + R_wall + skin`: a wall particle within `R_fluid` of an owned fluid particle needs
-all fluid within `R_wall` of itself for its Adami pressure, so the fluid ghost layer is two search
-radii wide and the wall pressure needs no second exchange; `skin` is how far an owned particle may
-drift out of its slab before `rebalance` (re-partition by position, a `SortingCallback`-like event:
-particle <-> ODE index may only change between time steps) becomes necessary.  Wall particles are
-static: each rank keeps those within `R_fluid + skin` of its slab.
+all fluid within `R_wall` of itself for its Adami pressure, so the fluid ghost layer reaches two
+search radii deep and the wall pressure needs no second exchange -- but beyond `R_fluid + skin`
+only the fluid within `R_wall` of a wall particle is needed, so the second radius of the layer is
+a thin shell along the tank walls, not a full slice (`candidate_mask`).  `skin` is how far a
+particle may move (and an owned particle drift out of its slab) before `rebalance` (re-partition
+by position, a `SortingCallback`-like event: particle <-> ODE index may only change between time
+steps) becomes necessary.  Wall particles are static: each rank keeps those within
+`R_fluid + skin` of its slab.
 
 The partition / selection / exchange logic is tensor-backend agnostic (CPU tensors + gloo in the
 tests, CUDA tensors + NCCL on the box); only `SlabSemidiscretization` needs the CUDA library.
@@ -41,9 +44,11 @@ from .setups import InitialCondition
 @dataclass
 class SlabLayout:
     planes: np.ndarray   # world + 1 slab faces along x; planes[0] = -inf, planes[-1] = +inf
-    halo: float          # fluid ghost layer width
+    halo: float          # fluid ghost layer width (deepest ghost: R_fluid + R_wall + skin)
     wall_reach: float    # wall particles kept within this distance of the slab
     skin: float
+    direct: float = 0.0  # R_fluid + skin: every particle this close to the face is a ghost
+    near_wall: float = 0.0  # R_wall: deeper ghosts are only those this close to a wall particle
 
     @property
     def world(self) -> int:
@@ -59,7 +64,7 @@ def make_layout(x_fluid: np.ndarray, world: int, radius_fluid: float, radius_wal
     """Faces between lattice columns such that every slab holds the same number of fluid
     particles (+-1 column): the dam-break column fills only part of the tank, equal-width slabs
     would leave most GPUs idle."""
-    skin = float(radius_fluid) if skin is None else float(skin)
+    skin = 0.25 * float(radius_fluid) if skin is None else float(skin)
     xs = np.sort(np.asarray(x_fluid, dtype=np.float64))
     planes = [-np.inf]
     for k in range(1, world):
@@ -75,7 +80,37 @@ def make_layout(x_fluid: np.ndarray, world: int, radius_fluid: float, radius_wal
     widths = np.diff(planes[1:-1]) if world > 2 else np.array([np.inf])
     if world > 1 and (np.any(np.diff(planes) <= 0) or np.any(widths < halo)):
         raise ValueError("slabs are thinner than the ghost layer: use fewer ranks or a larger problem")
-    return SlabLayout(planes=planes, halo=halo, wall_reach=float(radius_fluid) + skin, skin=skin)
+    return SlabLayout(planes=planes, halo=halo, wall_reach=float(radius_fluid) + skin, skin=skin,
+                      direct=float(radius_fluid) + skin, near_wall=float(radius_wall))
+
+
+def wall_tree(wall_coordinates):
+    """KD-tree of the wall particles for `candidate_mask` (None without a wall)."""
+    if wall_coordinates is None or hasattr(wall_coordinates, "query"):
+        return wall_coordinates
+    if len(wall_coordinates) == 0:
+        return None
+    from scipy.spatial import cKDTree
+    return cKDTree(np.asarray(wall_coordinates, dtype=np.float64))
+
+
+def candidate_mask(coords: np.ndarray, face: float, side: int, layout: SlabLayout, tree) -> np.ndarray:
+    """Which particles (owned by the slab on the far side of `face`) are ghost *candidates* of
+    the slab on the near side: side = -1: the owner lies to the right of the face (x >= face),
+    side = +1: to the left (x < face).  A candidate is within `direct + skin` of the face, or
+    within `halo + skin` of it and within `near_wall + skin` of a wall particle; the extra
+    `skin` covers the motion until the next rebalance (HaloExchange.check_drift)."""
+    coords = np.asarray(coords, dtype=np.float64)
+    x = coords[:, 0]
+    depth = (x - face) if side < 0 else (face - x)   # > 0 (>= 0) inside the owner's slab
+    owned = depth >= 0 if side < 0 else depth > 0
+    mask = owned & (depth < layout.direct + layout.skin)
+    if tree is not None:
+        band = np.nonzero(owned & ~mask & (depth < layout.halo + layout.skin))[0]
+        if len(band):
+            d, _ = tree.query(coords[band], k=1, distance_upper_bound=layout.near_wall + layout.skin)
+            mask[band[np.isfinite(d)]] = True
+    return mask
 
 
 def subset_ic(ic: InitialCondition, idx: np.ndarray) -> InitialCondition:
@@ -210,24 +245,31 @@ class HaloExchange:
     the summation order on the receiving rank) are fixed; masses travel once, at setup.
     Works on torch tensors of any device: u (n, ND) coordinates, v (n, NV) velocity + density."""
 
-    def __init__(self, layout: SlabLayout, rank: int, transport):
+    def __init__(self, layout: SlabLayout, rank: int, transport, wall_coordinates=None):
         self.layout, self.rank, self.transport = layout, rank, transport
         self.lo, self.hi = float(layout.planes[rank]), float(layout.planes[rank + 1])
         self.has_left, self.has_right = rank > 0, rank < layout.world - 1
+        self.tree = wall_tree(wall_coordinates)
         self.ready = False
 
     # -- setup -----------------------------------------------------------------------------
     def candidates(self, u):
+        """Setup-time selection on the host (`candidate_mask`); returns index tensors on u's device."""
         import torch
-        x = u[:, 0]
-        reach = self.layout.halo + self.layout.skin
+        coords = u.detach().cpu().numpy()
         empty = torch.empty(0, dtype=torch.int64, device=u.device)
-        cand_l = torch.nonzero(x < self.lo + reach).squeeze(1) if self.has_left else empty
-        cand_r = torch.nonzero(x >= self.hi - reach).squeeze(1) if self.has_right else empty
+
+        def pick(face, side):
+            idx = np.nonzero(candidate_mask(coords, face, side, self.layout, self.tree))[0]
+            return torch.from_numpy(idx).to(u.device)
+
+        cand_l = pick(self.lo, -1) if self.has_left else empty
+        cand_r = pick(self.hi, +1) if self.has_right else empty
         return cand_l, cand_r
 
     def setup_post(self, u, mass):
         self.cand_l, self.cand_r = self.candidates(u)
+        self.u_setup = u.clone()
         self._m_l = mass.index_select(0, self.cand_l).unsqueeze(1).contiguous()
         self._m_r = mass.index_select(0, self.cand_r).unsqueeze(1).contiguous()
         if getattr(self.transport, "two_phase", False):
@@ -268,9 +310,13 @@ class HaloExchange:
         return out
 
     def check_drift(self, u) -> bool:
-        """True while every owned particle is within `skin` of its slab (else: rebalance)."""
+        """True while every owned particle is within `skin` of its slab and, once the candidate
+        lists are fixed, has moved less than `skin` since then (else: rebalance)."""
         x = u[:, 0]
         ok = True
+        if self.ready:
+            moved2 = ((u - self.u_setup) ** 2).sum(dim=1).max() if len(u) else 0.0
+            ok = ok and float(moved2) < self.layout.skin ** 2
         if self.has_left:
             ok = ok and bool((x >= self.lo - self.layout.skin).all())
         if self.has_right:
@@ -325,10 +371,14 @@ class SlabSemidiscretization:
         nd = fluid.ndims
         # ghost slots = the neighbours' candidate counts (particles within halo + skin of the
         # faces): computed from the global lattice here, confirmed by the setup exchange
-        x = fluid.initial_condition.coordinates[:, 0].astype(np.float64)
         lo, hi = self.layout.planes[rank], self.layout.planes[rank + 1]
-        reach = self.layout.halo + self.layout.skin
-        n_slots = int(((x >= lo - reach) & (x < lo)).sum() + ((x >= hi) & (x < hi + reach)).sum())
+        gcoords = fluid.initial_condition.coordinates
+        tree = wall_tree(wall.coordinates if wall is not None else None)
+        n_slots = 0
+        if rank > 0:
+            n_slots += int(candidate_mask(gcoords, lo, +1, self.layout, tree).sum())
+        if rank < world - 1:
+            n_slots += int(candidate_mask(gcoords, hi, -1, self.layout, tree).sum())
         self.ghost_capacity = int(ghost_capacity if ghost_capacity is not None else n_slots)
         if world == 1:
             self.ghost_capacity = 0
@@ -349,7 +399,7 @@ class SlabSemidiscretization:
         self.semi = Semidiscretization(*systems, neighborhood_search=nhs, parallelization_backend=backend)
         self.device = torch.device("cuda", device)
         self.transport = transport if transport is not None else DistTransport(rank, world)
-        self.halo = HaloExchange(self.layout, rank, self.transport)
+        self.halo = HaloExchange(self.layout, rank, self.transport, tree)
         self.nd, self.nv = nd, self.fluid.v_nvariables
         self._lib = _lib
         self.n_ghost = 0
