@@ -212,6 +212,35 @@ int32_t tpb_vec_strided_max(tpb_semi_t semi, int64_t count, int32_t eltype, int3
 int32_t tpb_set_profiling(tpb_semi_t semi, int32_t max_kicks);
 int32_t tpb_get_phase_times(tpb_semi_t semi, double *ms_mean, int32_t *n_kicks);
 
+/* ---- ghost exchange between the slabs of one box over peer memory ------------------------------
+ * The reference has no distributed path; SURVEY.md section 8(e) describes the decomposition.
+ * One process per GPU.  `tpb_peer_alloc` returns zeroed device memory that `tpb_peer_export` can
+ * describe in 64 bytes (CUDA IPC); the neighbour process maps it with `tpb_peer_import`.
+ * `tpb_halo_pack` (sender): one kernel gathers the rows (x[ND], v[NV]) of `candidates` from the
+ * ODE vectors, marks rows whose x is not on the live side of `threshold` (side < 0: x < threshold,
+ * side > 0: x >= threshold) with x = NaN, stores them into the neighbour's receive area
+ * (`peer_u`, `peer_v`) over NVLink and, from its last block, publishes `epoch` in `peer_flag`.
+ * `done_counter` is a 64-bit device counter private to this (sender, neighbour) pair;
+ * `done_target_blocks` is the number of blocks all earlier calls on it have launched, `*blocks_out`
+ * the number this call launched.  `tpb_halo_install` (receiver): one kernel waits until the flags
+ * (NULL: no neighbour on that side) hold at least `epoch`, then copies `n_rows` rows from the
+ * receive area behind the owned particles (`u_ghost`, `v_ghost`).  A neighbour that does not
+ * deliver within `timeout_s` sets bit 1 of `*timed_out_flag` (device int; NULL: the handle's own
+ * status word, reported by the next `tpb_synchronize` as TPB_ERR_STATE) instead of hanging the GPU.
+ * All work is queued on the handle's stream; nothing synchronises with the host. */
+int32_t tpb_peer_alloc(int64_t bytes, void **out);
+int32_t tpb_peer_free(void *ptr);
+int32_t tpb_peer_export(void *ptr, void *handle64);
+int32_t tpb_peer_import(const void *handle64, void **out);
+int32_t tpb_peer_close(void *ptr);
+int32_t tpb_halo_pack(tpb_semi_t semi, int32_t side, double threshold, const void *u, const void *v,
+                      const int64_t *candidates, int64_t n_candidates, void *peer_u, void *peer_v,
+                      void *done_counter, int64_t done_target_blocks, void *peer_flag, uint32_t epoch,
+                      int32_t *blocks_out);
+int32_t tpb_halo_install(tpb_semi_t semi, int64_t n_rows, const void *stage_u, const void *stage_v,
+                         void *u_ghost, void *v_ghost, const void *flag_left, const void *flag_right,
+                         uint32_t epoch, double timeout_s, void *timed_out_flag);
+
 /* page-lock / unlock caller memory so TPB_MEM_HOST transfers run at full PCIe speed */
 int32_t tpb_host_register(void *ptr, int64_t bytes);
 int32_t tpb_host_unregister(void *ptr);

@@ -24,6 +24,8 @@ EXPORTS = [
     "tpb_host_unregister", "tpb_set_profiling", "tpb_get_phase_times",
     "tpb_set_fluid_count", "tpb_set_fluid_mass",
     "tpb_vec_axpby", "tpb_vec_rk2n_stage", "tpb_vec_fill", "tpb_vec_strided_max",
+    "tpb_peer_alloc", "tpb_peer_free", "tpb_peer_export", "tpb_peer_import", "tpb_peer_close",
+    "tpb_halo_pack", "tpb_halo_install",
 ]
 PHASES = ("rebuild", "density", "boundary", "interact")
 
@@ -110,6 +112,16 @@ def load():
     L.tpb_set_stream.restype = i32; L.tpb_set_stream.argtypes = [p, p]
     L.tpb_get_stats.restype = i32; L.tpb_get_stats.argtypes = [p, C.POINTER(Stats)]
     L.tpb_host_register.restype = i32; L.tpb_host_register.argtypes = [p, i64]
+    u32 = C.c_uint32
+    L.tpb_peer_alloc.restype = i32; L.tpb_peer_alloc.argtypes = [i64, C.POINTER(p)]
+    L.tpb_peer_free.restype = i32; L.tpb_peer_free.argtypes = [p]
+    L.tpb_peer_export.restype = i32; L.tpb_peer_export.argtypes = [p, p]
+    L.tpb_peer_import.restype = i32; L.tpb_peer_import.argtypes = [p, C.POINTER(p)]
+    L.tpb_peer_close.restype = i32; L.tpb_peer_close.argtypes = [p]
+    L.tpb_halo_pack.restype = i32
+    L.tpb_halo_pack.argtypes = [p, i32, d, p, p, p, i64, p, p, p, i64, p, u32, C.POINTER(i32)]
+    L.tpb_halo_install.restype = i32
+    L.tpb_halo_install.argtypes = [p, i64, p, p, p, p, p, p, u32, d, p]
     L.tpb_host_unregister.restype = i32; L.tpb_host_unregister.argtypes = [p]
     L.tpb_set_profiling.restype = i32; L.tpb_set_profiling.argtypes = [p, i32]
     L.tpb_get_phase_times.restype = i32

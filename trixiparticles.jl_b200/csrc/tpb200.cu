@@ -20,6 +20,7 @@
 #include "tpb_sweeps.cuh"
 #include "tpb_tiles.cuh"
 #include "tpb_vec.cuh"
+#include "tpb_halo.cuh"
 
 using namespace tpb;
 
@@ -1018,6 +1019,8 @@ int32_t tpb_synchronize(tpb_semi_t semi)
     if (s->h_flags && (*s->h_flags & 1))
         return fail(s, TPB_ERR_OUT_OF_BOUNDS,
                     "particle coordinates are NaN or outside the FullGridCellList bounding box");
+    if (s->h_flags && (*s->h_flags & 2))
+        return fail(s, TPB_ERR_STATE, "ghost exchange: a neighbour rank did not deliver its rows in time");
     return TPB_OK;
 }
 
@@ -1168,6 +1171,103 @@ int32_t tpb_get_phase_times(tpb_semi_t semi, double *ms_mean, int32_t *n_kicks)
         for (int ph = 0; ph < TPB_N_PHASES - 1; ++ph) ms_mean[ph] /= s->prof_kicks;
     if (n_kicks) *n_kicks = s->prof_kicks;
     s->prof_kicks = 0;
+    return TPB_OK;
+}
+
+// ---- ghost exchange over peer memory (tpb_halo.cuh)
+int32_t tpb_peer_alloc(int64_t bytes, void **out)
+{
+    if (!out || bytes <= 0) return TPB_ERR_INVALID_ARGUMENT;
+    void *p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return TPB_ERR_CUDA;
+    if (cudaMemset(p, 0, (size_t)bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        cudaFree(p);
+        return TPB_ERR_CUDA;
+    }
+    *out = p;
+    return TPB_OK;
+}
+
+int32_t tpb_peer_free(void *ptr)
+{
+    return cudaFree(ptr) == cudaSuccess ? TPB_OK : TPB_ERR_CUDA;
+}
+
+int32_t tpb_peer_export(void *ptr, void *handle64)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, ptr) != cudaSuccess) return TPB_ERR_CUDA;
+    std::memcpy(handle64, &h, sizeof(h));
+    return TPB_OK;
+}
+
+int32_t tpb_peer_import(const void *handle64, void **out)
+{
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return TPB_ERR_CUDA;
+    }
+    *out = p;
+    return TPB_OK;
+}
+
+int32_t tpb_peer_close(void *ptr)
+{
+    return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? TPB_OK : TPB_ERR_CUDA;
+}
+
+int32_t tpb_halo_pack(tpb_semi_t semi, int32_t side, double threshold, const void *u, const void *v,
+                      const int64_t *candidates, int64_t n_candidates, void *peer_u, void *peer_v,
+                      void *done_counter, int64_t done_target_blocks, void *peer_flag, uint32_t epoch,
+                      int32_t *blocks_out)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !s->ready) return fail(s, TPB_ERR_STATE, "tpb_halo_pack: handle not semidiscretized");
+    const int nd = s->cfg.ndims;
+    const int nv = s->fp.density_calculator == TPB_DENSITY_SUMMATION ? nd : nd + 1;
+    const int blocks = (int)std::min<int64_t>(std::max<int64_t>((n_candidates + 255) / 256, 1), 148 * 4);
+    if (blocks_out) *blocks_out = blocks;
+    const unsigned long long target = (unsigned long long)(done_target_blocks + blocks);
+    const bool f32 = s->cfg.eltype == TPB_F32, c32 = s->cfg.coords_eltype == TPB_F32;
+#define TPB_PACK(T, CT)                                                                                  \
+    LAUNCH(*s, (k_halo_pack<T, CT>), blocks, 256, 0, nd, nv, (const CT *)u, (const T *)v, candidates,    \
+           n_candidates, (CT)threshold, (int)side, (CT *)peer_u, (T *)peer_v,                            \
+           (unsigned long long *)done_counter, target, (uint32_t *)peer_flag, epoch)
+    if (f32 && c32) TPB_PACK(float, float);
+    else if (f32) TPB_PACK(float, double);
+    else if (c32) return fail(s, TPB_ERR_INVALID_ARGUMENT, "Float64 systems need Float64 coordinates");
+    else TPB_PACK(double, double);
+#undef TPB_PACK
+    CUDA_TRY(s, cudaGetLastError());
+    return TPB_OK;
+}
+
+int32_t tpb_halo_install(tpb_semi_t semi, int64_t n_rows, const void *stage_u, const void *stage_v,
+                         void *u_ghost, void *v_ghost, const void *flag_left, const void *flag_right,
+                         uint32_t epoch, double timeout_s, void *timed_out_flag)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !s->ready) return fail(s, TPB_ERR_STATE, "tpb_halo_install: handle not semidiscretized");
+    const int nd = s->cfg.ndims;
+    const int nv = s->fp.density_calculator == TPB_DENSITY_SUMMATION ? nd : nd + 1;
+    const int64_t n_u = n_rows * nd, n_v = n_rows * nv;
+    const int blocks = (int)std::min<int64_t>(std::max<int64_t>((n_v + 255) / 256, 1), 148 * 2);
+    const unsigned long long timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    const bool f32 = s->cfg.eltype == TPB_F32, c32 = s->cfg.coords_eltype == TPB_F32;
+#define TPB_INSTALL(T, CT)                                                                               \
+    LAUNCH(*s, (k_halo_install<T, CT>), blocks, 256, 0, n_u, n_v, (const CT *)stage_u, (const T *)stage_v, \
+           (CT *)u_ghost, (T *)v_ghost, (const uint32_t *)flag_left, (const uint32_t *)flag_right, epoch, \
+           timeout_ns, timed_out_flag ? (int *)timed_out_flag : s->d_flags)
+    if (f32 && c32) TPB_INSTALL(float, float);
+    else if (f32) TPB_INSTALL(float, double);
+    else if (c32) return fail(s, TPB_ERR_INVALID_ARGUMENT, "Float64 systems need Float64 coordinates");
+    else TPB_INSTALL(double, double);
+#undef TPB_INSTALL
+    CUDA_TRY(s, cudaGetLastError());
     return TPB_OK;
 }
 

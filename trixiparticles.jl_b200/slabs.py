@@ -345,6 +345,110 @@ class HaloExchange:
         return both[:, :nd], both[:, nd:nd + nv].to(v.dtype)
 
 
+# ------------------------------------------------------------------ exchange over peer memory
+class PeerHalo:
+    """Per-kick ghost exchange through the neighbours' device memory (csrc/tpb_halo.cuh): one
+    pack-and-store kernel per neighbour, one wait-and-install kernel, no NCCL call and no torch
+    op on the path.  Set up after `HaloExchange.setup_finish` (candidate lists and slot counts
+    are known); needs one process per GPU with CUDA IPC between them (one box)."""
+
+    ALIGN = 256
+
+    def __init__(self, slab, group=None, timeout_s: float = 20.0):
+        import torch
+        import torch.distributed as dist
+        self.slab, self.halo = slab, slab.halo
+        self.L, self.lib = slab._lib.load(), slab._lib
+        self.rank, self.world = slab.rank, slab.world
+        self.timeout_s = float(timeout_s)
+        nd, nv = slab.nd, slab.nv
+        csize = slab.u_ext.element_size()
+        tsize = slab.v_ext.element_size()
+        n_g = self.halo.n_ghost_slots
+        up = lambda b: (b + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        # receive area: [stage_u p0 | stage_u p1 | stage_v p0 | stage_v p1 | flags | local words]
+        self.off_u = [0, up(n_g * nd * csize)]
+        self.off_v = [self.off_u[1] + up(n_g * nd * csize)]
+        self.off_v.append(self.off_v[0] + up(n_g * nv * tsize))
+        self.off_flag = self.off_v[1] + up(n_g * nv * tsize)      # +0: from left, +4: from right
+        self.off_local = self.off_flag + self.ALIGN               # +0/+8: done counters, +16: timed_out
+        total = self.off_local + self.ALIGN
+        base = C.c_void_p()
+        if self.L.tpb_peer_alloc(total, C.byref(base)) != 0:
+            raise RuntimeError("tpb_peer_alloc failed")
+        self.base = base.value
+        handle = C.create_string_buffer(64)
+        if self.L.tpb_peer_export(C.c_void_p(self.base), handle) != 0:
+            raise RuntimeError("tpb_peer_export failed (CUDA IPC unavailable)")
+        mine = dict(handle=bytes(handle.raw), off_u=self.off_u, off_v=self.off_v, off_flag=self.off_flag,
+                    n_from_l=self.halo.n_from_l, n_from_r=self.halo.n_from_r)
+        infos = [None] * self.world
+        dist.all_gather_object(infos, mine, group=group)
+        self.peers = {}
+        ok = 1
+        for side, nb in ((-1, self.rank - 1), (+1, self.rank + 1)):
+            if nb < 0 or nb >= self.world:
+                continue
+            ptr = C.c_void_p()
+            if self.L.tpb_peer_import(C.create_string_buffer(infos[nb]["handle"], 64), C.byref(ptr)) != 0:
+                ok = 0
+                continue
+            self.peers[side] = (ptr.value, infos[nb])
+        flag = torch.tensor([ok], dtype=torch.int32, device=slab.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag) == 0:
+            self.close()
+            raise RuntimeError("tpb_peer_import failed on some rank (no peer access between the GPUs?)")
+        self.epoch = 0
+        self.blocks_done = {-1: 0, +1: 0}
+        self.launches = 0
+
+    def exchange(self):
+        """Queue this kick's exchange on the handle's stream (after the owned rows of
+        u_ext / v_ext are final, before tpb_kick)."""
+        s, h, L = self.slab, self.slab.semi._handle, self.L
+        halo, lay = self.halo, self.halo.layout
+        s.semi._bind_stream()
+        self.epoch += 1
+        e, par = self.epoch & 0xFFFFFFFF, self.epoch & 1
+        nd, nv = s.nd, s.nv
+        csize, tsize = s.u_ext.element_size(), s.v_ext.element_size()
+        u_ptr, v_ptr = s.u_ext.data_ptr(), s.v_ext.data_ptr()
+        for side, cand, thr in ((-1, halo.cand_l, halo.lo + lay.halo), (+1, halo.cand_r, halo.hi - lay.halo)):
+            if side not in self.peers:
+                continue
+            pbase, info = self.peers[side]
+            # my rows land behind the rows of the neighbour's left neighbour when I am its right one
+            row0 = info["n_from_l"] if side < 0 else 0
+            peer_u = pbase + info["off_u"][par] + row0 * nd * csize
+            peer_v = pbase + info["off_v"][par] + row0 * nv * tsize
+            peer_flag = pbase + info["off_flag"] + (4 if side < 0 else 0)
+            done = self.base + self.off_local + (0 if side < 0 else 8)
+            blocks = C.c_int32(0)
+            self.lib.check(h, L.tpb_halo_pack(h, side, float(thr), C.c_void_p(u_ptr), C.c_void_p(v_ptr),
+                                              C.c_void_p(cand.data_ptr()), int(cand.numel()),
+                                              C.c_void_p(peer_u), C.c_void_p(peer_v), C.c_void_p(done),
+                                              self.blocks_done[side], C.c_void_p(peer_flag), e, C.byref(blocks)))
+            self.blocks_done[side] += blocks.value
+            self.launches += 1
+        n0, n_g = s.n_owned, halo.n_ghost_slots
+        fl = C.c_void_p(self.base + self.off_flag) if -1 in self.peers else C.c_void_p(None)
+        fr = C.c_void_p(self.base + self.off_flag + 4) if +1 in self.peers else C.c_void_p(None)
+        self.lib.check(h, L.tpb_halo_install(h, n_g, C.c_void_p(self.base + self.off_u[par]),
+                                             C.c_void_p(self.base + self.off_v[par]),
+                                             C.c_void_p(u_ptr + n0 * nd * csize), C.c_void_p(v_ptr + n0 * nv * tsize),
+                                             fl, fr, e, self.timeout_s, C.c_void_p(None)))
+        self.launches += 1
+
+    def close(self):
+        for ptr, _ in getattr(self, "peers", {}).values():
+            self.L.tpb_peer_close(C.c_void_p(ptr))
+        self.peers = {}
+        if getattr(self, "base", None):
+            self.L.tpb_peer_free(C.c_void_p(self.base))
+            self.base = None
+
+
 # ------------------------------------------------------------------ the per-rank GPU object
 class SlabSemidiscretization:
     """One slab of `Semidiscretization(fluid, wall)` on one GPU.
@@ -398,6 +502,7 @@ class SlabSemidiscretization:
         systems = (self.fluid,) if self.wall is None else (self.fluid, self.wall)
         self.semi = Semidiscretization(*systems, neighborhood_search=nhs, parallelization_backend=backend)
         self.device = torch.device("cuda", device)
+        self.peer = None
         self.transport = transport if transport is not None else DistTransport(rank, world)
         self.halo = HaloExchange(self.layout, rank, self.transport, tree)
         self.nd, self.nv = nd, self.fluid.v_nvariables
@@ -439,9 +544,28 @@ class SlabSemidiscretization:
             self._lib.check(h, L.tpb_set_fluid_mass(h, n0, n_g, C.c_void_p(self.halo.ghost_mass.data_ptr())))
         self._lib.check(h, L.tpb_set_fluid_count(h, n0 + n_g, n0))
         self.n_ghost = n_g
+        # exchange over peer memory when every rank is its own process on a GPU of this box
+        self.peer = None
+        import os
+        if isinstance(self.transport, DistTransport) and os.environ.get("TPB_HALO", "peer") == "peer":
+            try:
+                self.peer = PeerHalo(self, group=self.transport.group)
+            except RuntimeError as err:
+                import sys
+                print(f"[slabs] rank {self.rank}: peer-memory halo unavailable ({err}); using NCCL send/recv",
+                      file=sys.stderr)
+                self.peer = None
 
     def close(self):
+        if getattr(self, "peer", None) is not None:
+            self.peer.close()
+            self.peer = None
         self.semi.close()
+
+    @property
+    def halo_transport(self) -> str:
+        return "peer memory (pack-and-store kernel + flag)" if getattr(self, "peer", None) is not None \
+            else "NCCL send/recv"
 
     # -- per kick ------------------------------------------------------------------------
     def _stage_owned(self, v_ode, u_ode):
@@ -467,8 +591,11 @@ class SlabSemidiscretization:
     def kick_(self, dv_ode, v_ode, u_ode, p, t):
         self._stage_owned(v_ode, u_ode)
         if self.world > 1:
-            n0 = self.n_owned
-            self._install_ghosts(self.halo.exchange(self.u_ext[:n0], self.v_ext[:n0]))
+            if self.peer is not None:
+                self.peer.exchange()
+            else:
+                n0 = self.n_owned
+                self._install_ghosts(self.halo.exchange(self.u_ext[:n0], self.v_ext[:n0]))
         self._compute(dv_ode, t)
         return dv_ode
 

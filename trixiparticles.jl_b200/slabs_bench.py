@@ -127,7 +127,7 @@ def run(args):
                        "n_fluid": n_f, "n_wall": n_w, "n_fluid_per_rank": [int(tmin[2]), int(tmax[2])],
                        "n_ghost_per_rank": [int(tmin[3]), int(tmax[3])],
                        "n_wall_per_rank": [int(tmin[4]), int(tmax[4])], "ndims": 3,
-                       "nhs": "rebuilt every kick", "halo": "2R + skin, NCCL send/recv every kick",
+                       "nhs": "rebuilt every kick", "halo": f"R + skin, 2R + skin along the walls; every kick over {slab.halo_transport}",
                        "l2": "flushed between steps (256 MiB write, untimed)",
                        "timing": "sum of per-step CUDA-event times, max over ranks",
                        "bracket_s": t_bracket},
