@@ -290,7 +290,7 @@ struct Ops {
                    s.d_key, s.d_wcell_start, s.d_tmp_perm, n, (V4<CT> *)s.d_Aw, (V2<T> *)s.d_Ww,
                    s.d_perm_w);
         CUDA_TRY(&s, cudaMemsetAsync(s.d_volw, 0, sizeof(T) * (size_t)std::max(n, 1), s.stream));
-        rc = build_tile_table(s, s.d_wcell_start, s.tiles.d_wrow_tile_start, s.tiles.d_wtile_desc);
+        rc = build_tile_table(s, s.d_wcell_start, s.tiles.d_wrow_tile_start, s.tiles.d_wtile_desc, true);
         if (rc) return rc;
         CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
         cudaFree(d_coords);
@@ -311,9 +311,27 @@ struct Ops {
     }
 
     // ---- tile table of one sorted point set: tiles per cell row + exclusive scan
-    static int build_tile_table(Semi &s, const int *d_cell_start, int *d_row_tile_start, int4 *d_desc)
+    static int build_tile_table(Semi &s, const int *d_cell_start, int *d_row_tile_start, int4 *d_desc,
+                                bool cut_at_gaps = false)
     {
         const int nrows = s.tiles.nrows;
+        if (cut_at_gaps) {
+            const int gap = 2 * s.xsplit;
+            LAUNCH(s, k_row_tiles_gaps<false>, cdiv(nrows, 128), 128, 0, d_cell_start, s.ncell[0], nrows, gap,
+                   s.tiles.d_row_tiles, (const int *)nullptr, (int4 *)nullptr);
+            int rc = exclusive_scan(s, s.tiles.d_row_tiles, nrows, d_row_tile_start);
+            if (rc) return rc;
+            // static point set, built once: size the tile arrays to the exact count
+            int n_tiles = 0;
+            CUDA_TRY(&s, cudaMemcpyAsync(&n_tiles, d_row_tile_start + nrows, sizeof(int), cudaMemcpyDeviceToHost,
+                                         s.stream));
+            CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
+            if (tiles_reserve_wall(s.tiles, n_tiles)) return fail(&s, TPB_ERR_CUDA, "out of device memory (wall tiles)");
+            d_desc = s.tiles.d_wtile_desc;
+            LAUNCH(s, k_row_tiles_gaps<true>, cdiv(nrows, 128), 128, 0, d_cell_start, s.ncell[0], nrows, gap,
+                   (int *)nullptr, (const int *)d_row_tile_start, d_desc);
+            return TPB_OK;
+        }
         LAUNCH(s, k_row_tiles, cdiv(nrows, 256), 256, 0, d_cell_start, s.ncell[0], nrows,
                s.tiles.d_row_tiles);
         int rc = exclusive_scan(s, s.tiles.d_row_tiles, nrows, d_row_tile_start);

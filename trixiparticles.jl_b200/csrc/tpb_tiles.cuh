@@ -117,6 +117,46 @@ k_fill_tiles(const int *__restrict__ cell_start, int n0, int nrows,
         desc[first + k] = make_int4(rs + (int)(cnt * k / nt), rs + (int)(cnt * (k + 1) / nt), r, 0);
 }
 
+// The same two steps for a static point set (the wall, built once): a row is first cut into
+// segments wherever `gap` or more consecutive cells are empty, then every segment is split into
+// balanced tiles.  Without the cut, the one tile of a tank-wall row that holds both its left and
+// its right wall particles would span the whole tank and stage every fluid particle in between.
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_row_tiles_gaps(const int *__restrict__ cell_start, int n0, int nrows, int gap,
+                 int *__restrict__ row_tiles, const int *__restrict__ row_tile_start, int4 *__restrict__ desc)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const int *cs = cell_start + (int64_t)r * n0;
+    int nt = 0, seg_first = 0, seg_cnt = 0, empty_run = 0;
+    int out = FILL ? row_tile_start[r] : 0;
+    auto close_segment = [&]() {
+        const int k_tiles = (seg_cnt + TILE_TB - 1) / TILE_TB;
+        if (FILL)
+            for (int k = 0; k < k_tiles; ++k)
+                desc[out++] = make_int4(seg_first + (int)((long long)seg_cnt * k / k_tiles),
+                                        seg_first + (int)((long long)seg_cnt * (k + 1) / k_tiles), r, 0);
+        nt += k_tiles;
+        seg_cnt = 0;
+    };
+    int prev = cs[0];
+    for (int c = 0; c < n0; ++c) {
+        const int next = cs[c + 1];
+        const int cnt = next - prev;
+        if (cnt == 0) {
+            if (++empty_run == gap && seg_cnt > 0) close_segment();
+        } else {
+            if (seg_cnt == 0) seg_first = prev;
+            seg_cnt += cnt;
+            empty_run = 0;
+        }
+        prev = next;
+    }
+    if (seg_cnt > 0) close_segment();
+    if (!FILL) row_tiles[r] = nt;
+}
+
 // Candidate ranges of every tile, one warp per tile: for each of the 3^(ND-1) neighbour rows the
 // run of sorted records [g0, g1) covering the cells {cxmin - sx .. cxmax + sx} of that row, in up
 // to two neighbour sets (lanes 0..8: set 0, lanes 9..17: set 1).  Computed once per rebuild so
@@ -987,7 +1027,7 @@ inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
     t.list_len_split = std::max(t.list_len_split, 8);
     if (t.smem_budget > 227 * 1024) t.smem_budget = 227 * 1024;
     t.max_ftiles = (int)((n_f + TILE_TB - 1) / TILE_TB) + nrows;
-    t.max_wtiles = (int)((n_w + TILE_TB - 1) / TILE_TB) + nrows;
+    t.max_wtiles = (int)((n_w + TILE_TB - 1) / TILE_TB) + nrows;  // grown by tiles_reserve_wall if needed
     if (cudaMalloc(&t.d_row_tiles, sizeof(int) * (size_t)(nrows + 4)) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_frow_tile_start, sizeof(int) * (size_t)(nrows + 4)) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_wrow_tile_start, sizeof(int) * (size_t)(nrows + 4)) != cudaSuccess) return 1;
@@ -1004,6 +1044,29 @@ inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
     if (cudaMalloc(&t.d_n_wactive, sizeof(int) * 4) != cudaSuccess) return 1;
     cudaMemset(t.d_frow_tile_start, 0, sizeof(int) * (size_t)(nrows + 4));
     cudaMemset(t.d_wrow_tile_start, 0, sizeof(int) * (size_t)(nrows + 4));
+    return 0;
+}
+// The wall's tile table is built once; rows cut at gaps may need more tiles than the first guess.
+inline int tiles_reserve_wall(TileState &t, int n_tiles)
+{
+    if (n_tiles <= t.max_wtiles) return 0;
+    t.max_wtiles = n_tiles;
+    cudaFree(t.d_wtile_desc);
+    cudaFree(t.d_wtile_ext);
+    cudaFree(t.d_wtile_rng);
+    cudaFree(t.d_wactive);
+    t.d_wtile_desc = nullptr, t.d_wtile_ext = nullptr, t.d_wtile_rng = nullptr, t.d_wactive = nullptr;
+    if (cudaMalloc(&t.d_wtile_desc, sizeof(int4) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_wtile_ext, sizeof(int4) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_wtile_rng, sizeof(int2) * 9 * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_wactive, sizeof(int) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+    if (t.max_wtiles > t.max_ftiles) {
+        cudaFree(t.d_ptile_ext);
+        cudaFree(t.d_ptile_rng);
+        t.d_ptile_ext = nullptr, t.d_ptile_rng = nullptr;
+        if (cudaMalloc(&t.d_ptile_ext, sizeof(int4) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+        if (cudaMalloc(&t.d_ptile_rng, sizeof(int2) * 9 * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+    }
     return 0;
 }
 inline void tiles_free(TileState &t)
