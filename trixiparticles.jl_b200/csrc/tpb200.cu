@@ -45,6 +45,7 @@ struct Semi {
     // geometry of the shared cell grid (double; typed copies are built per call)
     double cell_size = 0, origin[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     int ncell[3] = {1, 1, 1};
+    int row_axis = 0;  // coordinate axis of the cell rows; origin/lo/hi/ncell hold entries 0 and row_axis swapped
     int64_t ncells = 0;
     int xsplit = 1;       // cells are cell_size / xsplit wide in x
     double gap_tol = 0;   // rounding bound of cell-boundary coordinates in cT
@@ -200,6 +201,7 @@ GridConst<CT> make_grid_const(const Semi &s)
     g.gap_tol = (CT)s.gap_tol;
     g.ncells = (int)s.ncells;
     g.sx = s.xsplit;
+    g.ax = s.row_axis;
     return g;
 }
 
@@ -883,6 +885,21 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
             s->ncell[d] = 1;
         }
         s->ncells *= s->ncell[d];
+    }
+    // Rows (the fastest cell index; one row = one contiguous run of sorted records, the unit the
+    // tile sweeps stage and split into tiles) run along the longest side of the bounding box: long
+    // rows give full tiles and little staging overhead, and a slab of a decomposed domain is
+    // thin along the decomposition axis.  Ties keep x.
+    {
+        int ax = 0;
+        for (int d = 1; d < nd; ++d)
+            if (s->hi[d] - s->lo[d] > (s->hi[ax] - s->lo[ax]) * (1 + 1e-9)) ax = d;
+        if (const char *e = getenv("TPB_ROW_AXIS")) ax = std::min(std::max(atoi(e), 0), nd - 1);
+        s->row_axis = ax;
+        std::swap(s->lo[0], s->lo[ax]);
+        std::swap(s->hi[0], s->hi[ax]);
+        std::swap(s->origin[0], s->origin[ax]);
+        std::swap(s->ncell[0], s->ncell[ax]);
     }
     // x-split: finer cells along x (the fastest index) let the tile sweep clip each row to the
     // chord of the search sphere; bounded so that the cell table stays scannable

@@ -339,12 +339,24 @@ struct GridConst {
     int n[3];
     int ncells;
     int sx;         // x-split factor
+    int ax;         // coordinate axis of the rows (fastest cell index); every per-axis field above is
+                    // stored with the entries 0 and ax swapped ("cell-axis order")
 };
 
 template <int ND, typename CT>
 __device__ __forceinline__ bool cell_coords(const GridConst<CT> &g, CT x, CT y, CT z, int &cx,
                                             int &cy, int &cz)
 {
+    // rows run along coordinate axis g.ax (the longest side of the bounding box): cell axis 0
+    if (g.ax == 1) {
+        const CT t = x;
+        x = y;
+        y = t;
+    } else if (ND == 3 && g.ax == 2) {
+        const CT t = x;
+        x = z;
+        z = t;
+    }
     // written so that NaN coordinates fail the test
     bool ok = (x >= g.lo[0]) && (x <= g.hi[0]) && (y >= g.lo[1]) && (y <= g.hi[1]);
     if (ND == 3) ok = ok && (z >= g.lo[2]) && (z <= g.hi[2]);
