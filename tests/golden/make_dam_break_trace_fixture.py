@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Extracts the surge-front trace (and the run parameters that pin it) of the reference's
+"""Extracts the surge-front and pressure-sensor traces (and the run parameters that pin them) of the reference's
 2-D dam-break validation run into a small fixture.  Source (read-only reference tree):
 /root/reference/validation/dam_break_2d/validation_reference_wcsph_40.json, the file the
 reference's own test/validation/validation.jl:48-68 compares against.  Run in the build
@@ -26,6 +26,8 @@ out = {
     "max_x_coord_fluid_1": d["max_x_coord_fluid_1"]["values"],
     "pressure_P1_fluid_1": d["pressure_P1_fluid_1"]["values"],
     "pressure_P2_fluid_1": d["pressure_P2_fluid_1"]["values"],
+    "pressure_P3_fluid_1": d["pressure_P3_fluid_1"]["values"],
+    "pressure_P4_fluid_1": d["pressure_P4_fluid_1"]["values"],
 }
 json.dump(out, open(DST, "w"))
 print(DST, os.path.getsize(DST), "bytes; sound_speed =", out["sound_speed"])

@@ -14,6 +14,7 @@ from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
 from .semidiscretization import (B200Backend, DynamicalODEProblem, FullGridCellList,
                                  GridNeighborhoodSearch, Semidiscretization, drift_, kick_,
                                  semidiscretize)
+from .interpolation import interpolate_line, interpolate_points
 from .setups import InitialCondition, RectangularShape, RectangularTank, union
 
 __all__ = [
@@ -23,5 +24,5 @@ __all__ = [
     "WeaklyCompressibleSPHSystem", "WendlandC2Kernel", "compact_support", "B200Backend",
     "DynamicalODEProblem", "FullGridCellList", "GridNeighborhoodSearch", "Semidiscretization",
     "drift_", "kick_", "semidiscretize", "InitialCondition", "RectangularShape",
-    "RectangularTank", "union",
+    "RectangularTank", "union", "interpolate_line", "interpolate_points",
 ]
