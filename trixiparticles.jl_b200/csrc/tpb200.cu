@@ -334,6 +334,11 @@ struct Ops {
                    (int *)nullptr, (const int *)d_row_tile_start, d_desc);
             return TPB_OK;
         }
+        if (nrows <= TILE_TABLE_MAX_ROWS) {
+            LAUNCH(s, k_row_tile_table, 1, SCAN_THREADS, 0, d_cell_start, s.ncell[0], nrows, d_row_tile_start,
+                   d_desc);
+            return TPB_OK;
+        }
         LAUNCH(s, k_row_tiles, cdiv(nrows, 256), 256, 0, d_cell_start, s.ncell[0], nrows,
                s.tiles.d_row_tiles);
         int rc = exclusive_scan(s, s.tiles.d_row_tiles, nrows, d_row_tile_start);
@@ -370,9 +375,13 @@ struct Ops {
         k.p_off = (T)s.wp.pressure_offset;
         k.clip = s.wp.clip_negative_pressure;
         if (use_tiles(s)) {
-            const int list_len = s.tiles.list(KS);
-            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, list_len, KS);
+            const int list_len = KS > 1 ? s.tiles.adami_list_len : s.tiles.list(KS);
+            const int budget = KS > 1 ? std::min(s.tiles.adami_smem_budget, s.tiles.smem_budget) : s.tiles.smem_budget;
+            const int cap = tile_capacity<T, CT>(budget, list_len, KS);
             const size_t smem = tile_smem_bytes<T, CT>(cap, list_len, KS);
+            int grid = s.tiles.max_wtiles;  // one block per tile slot; surplus blocks exit at once
+            if (const char *e = getenv("TPB_ADAMI_GRID"))  // tuning: fewer blocks, each walking several tiles
+                if (atoi(e) > 0) grid = std::min(grid, atoi(e));
             static bool attr_set = false;
             if (!attr_set) {
                 int rc = set_smem(s, k_adami_tiles<KS, ND, T, CT, KERNEL>, 227 * 1024);
@@ -387,7 +396,7 @@ struct Ops {
                    s.tiles.d_wrow_tile_start + s.tiles.nrows, s.tiles.d_wtile_desc, (const V4<CT> *)s.d_Aw,
                    s.d_fcell_start, rho_empty, (V2<T> *)s.d_Ww, (T *)s.d_volw, s.tiles.d_wactive,
                    s.tiles.d_n_wactive, s.tiles.d_wtile_rng, s.tiles.d_wtile_ext);
-            LAUNCH(s, (k_adami_tiles<KS, ND, T, CT, KERNEL>), s.tiles.max_wtiles, KS * TILE_TB, smem, g,
+            LAUNCH(s, (k_adami_tiles<KS, ND, T, CT, KERNEL>), grid, KS * TILE_TB, smem, g,
                    s.tiles.d_n_wactive, s.tiles.d_wactive, s.tiles.d_wtile_desc, s.tiles.d_wtile_ext,
                    s.tiles.d_wtile_rng, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
                    s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
