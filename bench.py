@@ -19,9 +19,10 @@ Own arm (default): the CUDA library through the reference-facing API.
             timed on this box's host cores on the same workload.
 Reference arm (--impl reference): the CPU oracle port, all host threads, same workload.
 
-N > 1 (torchrun): the lattice is slab-decomposed along x, one slab per rank, ghost layers are
-exchanged with NCCL send/recv every kick (see trixiparticles.jl_b200/slabs.py); "scaling" is
-"weak": every rank gets a slab of the N = 1 size.
+N > 1 (torchrun): the lattice is slab-decomposed along x, one slab per rank, ghost particles are
+exchanged every kick over peer memory (one pack-and-store kernel per neighbour; NCCL send/recv
+with TPB_HALO=nccl; see trixiparticles.jl_b200/slabs.py); "scaling" is "weak": every rank gets a
+slab of the N = 1 size.
 """
 from __future__ import annotations
 
@@ -312,20 +313,25 @@ def run_single(args):
     flops = (pairs["fluid_fluid"] * 80 + pairs["fluid_wall"] * 55 + pairs["wall_fluid"] * 12
              + 9.0 * cand_per_particle * (2 * n_f + n_w_active))
     fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12
-    traffic, traffic_src = None, None
+    traffic, traffic_src, limiters = None, None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
         with open(tpath) as f:
             rec = json.load(f).get(args.workload)
         if rec:
             traffic, traffic_src = rec["dram_bytes_read"] + rec["dram_bytes_write"], rec["source"]
+            limiters = {k: rec[k] for k in ("shared_memory_pipe_pct_of_peak", "issue_slots_pct_of_peak",
+                                            "fma_pipe_pct_of_peak", "alu_pipe_pct_of_peak", "l2_hit_rate_pct",
+                                            "limiters_note") if k in rec}
     roofline = {
         "bound": "hbm", "kernel": "interact! phase (fluid-fluid + fluid-wall pair sweep)",
         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
         "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": k_bytes, "kernel_ms": k_ms,
         "kernel_share_of_step": k_ms / (total_ms / args.steps),
-        "note": "the pair sweep is FP32-issue bound (about 300 flop per compulsory byte), see fp32 and DESIGN.md",
+        "note": "the pair sweep is bound by the shared-memory pipe and the issue slots (about 300 flop per "
+                "compulsory byte), see limiters, fp32 and DESIGN.md",
+        "limiters": limiters,
         "step": {"achieved": step_achieved, "frac": step_achieved / peak_gbs, "algorithmic_bytes": step_bytes,
                  "bytes_per_fluid_particle": bpp["step_fluid"], "bytes_per_active_wall_particle": bpp["step_wall"]},
         "fp32": {"algorithmic_tflops": flops / (ms_kick.mean() * 1e-3) / 1e12, "nominal_peak_tflops": fp32_peak,

@@ -140,3 +140,76 @@ def test_peer_memory_halo_matches_nccl_and_single_gpu():
     for block in (slice(0, 3), slice(3, 4)):
         err = np.abs(got[:, block] - ref[:, block]).max() / np.abs(ref[:, block]).max()
         assert err <= 1e-5, (block, err)
+
+
+def _loop_worker(rank, world, port, out, n_steps, dt):
+    import os
+    import torch
+    import torch.distributed as dist
+    from trixiparticles.jl_b200.time_integration import CarpenterKennedy2N54
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        fluid, wall, _ = examples.dam_break_3d(0.05)
+        R = float(np.float32(2) * fluid.smoothing_length)
+        # a skin of R / 20 forces several rebalances within the run
+        slab = SlabSemidiscretization(fluid, wall, rank=rank, world=world, device=rank, skin=0.05 * R)
+        slab.semidiscretize((0.0, n_steps * dt))
+        t, v, u = slab.solve(CarpenterKennedy2N54(williamson_condition=False), dt=dt, n_steps=n_steps,
+                             check_every=5)
+        out.put((rank, slab.owned_index.copy(), u.cpu().numpy().reshape(-1, 3), v.cpu().numpy().reshape(-1, 4),
+                 int(getattr(slab, "n_rebalances", 0)), slab.halo_transport))
+        dist.barrier()
+        slab.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_time_loop_with_rebalance_matches_single_gpu():
+    """60 steps of CarpenterKennedy2N54 on the 3-D dam break (16 000 fluid particles), two
+    processes on two GPUs with a tiny skin so that particles migrate between the slabs several
+    times (`rebalance`: histogram planes, `migrate`, new handles), against the single-GPU loop.
+    Stated tolerance: 1e-4 of the fluid height in position, 1e-3 of sqrt(g H) in velocity, 1e-4 of
+    the reference density (Float32, different summation order per step)."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    from trixiparticles.jl_b200.time_integration import CarpenterKennedy2N54, solve
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n_steps = 60
+    fluid, wall, _ = examples.dam_break_3d(0.05)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    from trixiparticles.jl_b200.time_integration import StepsizeCallback
+    dt = StepsizeCallback(cfl=0.9).dt(semi)
+    ode = tp.semidiscretize(semi, (0.0, n_steps * dt))
+    sol = solve(ode, CarpenterKennedy2N54(williamson_condition=False), dt=dt)
+    assert sol.nsteps == n_steps
+    ref_u = sol.u.cpu().numpy().reshape(-1, 3)
+    ref_v = sol.v.cpu().numpy().reshape(-1, 4)
+    semi.close()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_loop_worker, args=(r, world, port, out, n_steps, dt), daemon=True)
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    got_u, got_v = np.full_like(ref_u, np.nan), np.full_like(ref_v, np.nan)
+    for _ in range(world):
+        rank, owned, u, v, n_reb, transport = out.get(timeout=400)
+        assert n_reb >= 1, "the run was meant to rebalance"
+        assert transport.startswith("peer memory")
+        got_u[owned], got_v[owned] = u, v
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.isfinite(got_u).all() and np.isfinite(got_v).all()      # every particle owned exactly once
+    errs = (np.abs(got_u - ref_u).max(), np.abs(got_v[:, :3] - ref_v[:, :3]).max() / np.sqrt(9.81 * 1.0),
+            np.abs(got_v[:, 3] - ref_v[:, 3]).max() / 1000.0)
+    assert errs[0] <= 1e-4 and errs[1] <= 1e-3 and errs[2] <= 1e-4, errs

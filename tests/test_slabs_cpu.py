@@ -142,3 +142,47 @@ def test_gloo_two_rank_halo_exchange_reproduces_global_kick(oracle):
     for rank, err, n_owned, n_ghost in res:
         assert err < 1e-12, (rank, err)
         assert n_owned > 0 and n_ghost > 0
+
+
+def _rebalance_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from trixiparticles.jl_b200.slabs import balanced_planes, migrate
+        g = torch.Generator().manual_seed(1234 + rank)
+        n = 1000 + 700 * rank                                   # unbalanced on purpose
+        x = torch.rand(n, generator=g, dtype=torch.float64) ** 2 * (1 + rank)   # skewed, overlapping ranges
+        ids = torch.arange(n, dtype=torch.int64) + 100000 * rank
+        planes = balanced_planes(x, world)
+        dest = torch.bucketize(x, torch.as_tensor(planes[1:-1], dtype=torch.float64), right=True)
+        ids2, x2, f2 = migrate([ids.view(-1, 1), x.view(-1, 1), x.to(torch.float32).view(-1, 1) * 2], dest, rank, world)
+        assert len(ids2) == len(x2) == len(f2)
+        assert bool(((x2[:, 0] >= planes[rank]) & (x2[:, 0] < planes[rank + 1])).all())
+        assert torch.equal(f2[:, 0], x2[:, 0].to(torch.float32) * 2)              # rows stay together
+        out.put((rank, planes.tolist(), ids2[:, 0].tolist(), n))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_rebalance_planes_and_migration_conserve_particles():
+    """world_size 3 over gloo: the histogram planes give equal counts and `migrate` delivers
+    every particle exactly once to the rank that owns its position."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rebalance_worker, args=(r, world, port, out), daemon=True) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    total = sum(r[3] for r in res)
+    assert all(r[1] == res[0][1] for r in res)                 # every rank computed the same planes
+    got = sorted(i for r in res for i in r[2])
+    expect = sorted(i + 100000 * r for r in range(world) for i in range(1000 + 700 * r))
+    assert got == expect
+    counts = [len(r[2]) for r in res]
+    assert max(counts) - min(counts) <= 0.02 * total, counts   # equal counts up to a few histogram bins

@@ -131,21 +131,95 @@ def local_systems(fluid, wall, layout: SlabLayout, rank: int):
     fluid_k.initial_condition = subset_ic(fluid.initial_condition, owned)
     fluid_k.mass = fluid.mass[owned].copy()
     fluid_k.pressure = np.zeros(len(owned), dtype=fluid.eltype)
-    wall_k, widx = None, None
-    if wall is not None:
-        xw = wall.coordinates[:, 0].astype(np.float64)
-        lo, hi = layout.planes[rank] - layout.wall_reach, layout.planes[rank + 1] + layout.wall_reach
-        widx = np.nonzero((xw >= lo) & (xw <= hi))[0]
-        wall_k = copy.copy(wall)
-        wall_k.initial_condition = subset_ic(wall.initial_condition, widx)
-        wall_k.coordinates = wall_k.initial_condition.coordinates
-        model = copy.copy(wall.boundary_model)
-        model.initial_density = wall.boundary_model.initial_density[widx].copy()
-        model.hydrodynamic_mass = wall.boundary_model.hydrodynamic_mass[widx].copy()
-        model.pressure = np.zeros(len(widx), dtype=wall.eltype)
-        model.cache = dict(density=model.initial_density.copy(), volume=np.zeros(len(widx), dtype=wall.eltype))
-        wall_k.boundary_model = model
+    wall_k, widx = local_wall(wall, layout, rank)
     return fluid_k, wall_k, owned, widx
+
+
+def local_wall(wall, layout: SlabLayout, rank: int):
+    """The wall particles within `wall_reach` of slab `rank` (static: a subset of the global wall)."""
+    if wall is None:
+        return None, None
+    xw = wall.coordinates[:, 0].astype(np.float64)
+    lo, hi = layout.planes[rank] - layout.wall_reach, layout.planes[rank + 1] + layout.wall_reach
+    widx = np.nonzero((xw >= lo) & (xw <= hi))[0]
+    wall_k = copy.copy(wall)
+    wall_k.initial_condition = subset_ic(wall.initial_condition, widx)
+    wall_k.coordinates = wall_k.initial_condition.coordinates
+    model = copy.copy(wall.boundary_model)
+    model.initial_density = wall.boundary_model.initial_density[widx].copy()
+    model.hydrodynamic_mass = wall.boundary_model.hydrodynamic_mass[widx].copy()
+    model.pressure = np.zeros(len(widx), dtype=wall.eltype)
+    model.cache = dict(density=model.initial_density.copy(), volume=np.zeros(len(widx), dtype=wall.eltype))
+    wall_k.boundary_model = model
+    return wall_k, widx
+
+
+# ------------------------------------------------------------------ rebalance: planes + migration
+def balanced_planes(x, world: int, group=None, nbins: int = 1 << 14) -> np.ndarray:
+    """Slab faces such that every slab holds the same number of particles (+- one histogram bin),
+    from a global histogram of the owned x coordinates (torch tensor on any device; one
+    all_reduce each for the range and the counts -- no rank ever sees another rank's particles)."""
+    import torch
+    import torch.distributed as dist
+    x = x.to(torch.float64)
+    big = torch.finfo(torch.float64).max
+    rng = torch.stack([x.min() if x.numel() else torch.tensor(big, device=x.device, dtype=torch.float64),
+                       -x.max() if x.numel() else torch.tensor(big, device=x.device, dtype=torch.float64)])
+    if world > 1:
+        dist.all_reduce(rng, op=dist.ReduceOp.MIN, group=group)
+    xmin, xmax = float(rng[0]), float(-rng[1])
+    width = max((xmax - xmin) / nbins, 1e-300) * (1 + 1e-12)
+    idx = ((x - xmin) / width).to(torch.int64).clamp_(0, nbins - 1)
+    hist = torch.bincount(idx, minlength=nbins)
+    if world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    cum = torch.cumsum(hist, 0).cpu().numpy()
+    total = int(cum[-1])
+    planes = [-np.inf]
+    for k in range(1, world):
+        b = int(np.searchsorted(cum, total * k / world, side="left"))
+        planes.append(xmin + (b + 1) * width)
+    planes.append(np.inf)
+    return np.asarray(planes)
+
+
+def migrate(payload, dest, rank: int, world: int, group=None):
+    """Send row i of every tensor in `payload` (2-D, same number of rows) to rank `dest[i]`.
+    Returns the rows this rank now owns, ordered by source rank (own rows in their place): a
+    count exchange (all_gather of one row of the count matrix) followed by variable-size
+    point-to-point messages -- NCCL send/recv over NVLink on the box, gloo in the tests."""
+    import torch
+    import torch.distributed as dist
+    order = torch.argsort(dest, stable=True)
+    counts = torch.bincount(dest, minlength=world)
+    if world == 1:
+        return [t[order] for t in payload]
+    rows = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(rows, counts, group=group)
+    matrix = torch.stack(rows).cpu()                     # matrix[src, dst]
+    send_off = torch.cumsum(counts, 0).cpu().tolist()
+    send_off = [0] + send_off
+    out = []
+    for t in payload:
+        ts = t[order].contiguous()
+        chunks, ops = [], []
+        for src in range(world):
+            n = int(matrix[src, rank])
+            if src == rank:
+                chunks.append(ts[send_off[rank]:send_off[rank + 1]])
+                continue
+            buf = torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            chunks.append(buf)
+            if n:
+                ops.append(dist.P2POp(dist.irecv, buf, src, group))
+        for dst in range(world):
+            if dst != rank and send_off[dst + 1] > send_off[dst]:
+                ops.append(dist.P2POp(dist.isend, ts[send_off[dst]:send_off[dst + 1]], dst, group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        out.append(torch.cat(chunks, dim=0))
+    return out
 
 
 # ------------------------------------------------------------------ transports
@@ -469,10 +543,12 @@ class SlabSemidiscretization:
         t = fluid.eltype.type
         R_f = float(t(2) * fluid.smoothing_length)
         R_w = float(t(2) * wall.boundary_model.smoothing_length) if wall is not None else R_f
+        self._radii = (R_f, R_w)
+        self._wall_global = wall
+        self._device_index, self._interact_variant, self._transport_arg = device, interact_variant, transport
+        self._lib = _lib
         self.layout = make_layout(fluid.initial_condition.coordinates[:, 0], world, R_f, R_w, skin)
         self.fluid, self.wall, self.owned_index, self.wall_index = local_systems(fluid, wall, self.layout, rank)
-        self.n_owned = self.fluid.nparticles
-        nd = fluid.ndims
         # ghost slots = the neighbours' candidate counts (particles within halo + skin of the
         # faces): computed from the global lattice here, confirmed by the setup exchange
         lo, hi = self.layout.planes[rank], self.layout.planes[rank + 1]
@@ -483,30 +559,45 @@ class SlabSemidiscretization:
             n_slots += int(candidate_mask(gcoords, lo, +1, self.layout, tree).sum())
         if rank < world - 1:
             n_slots += int(candidate_mask(gcoords, hi, -1, self.layout, tree).sum())
-        self.ghost_capacity = int(ghost_capacity if ghost_capacity is not None else n_slots)
-        if world == 1:
-            self.ghost_capacity = 0
-        # bounding box of the rank: slab + ghost layer in x, the whole tank in y, z
+        # global bounding box: the whole tank (every slab shares it in y, z)
         allc = [fluid.initial_condition.coordinates.astype(np.float64)]
         if wall is not None:
             allc.append(wall.coordinates.astype(np.float64))
         allc = np.concatenate(allc)
-        gmin, gmax = allc.min(axis=0) - 2 * max(R_f, R_w), allc.max(axis=0) + 2 * max(R_f, R_w)
+        self._gbox = (allc.min(axis=0) - 2 * max(R_f, R_w), allc.max(axis=0) + 2 * max(R_f, R_w))
+        self._tree = tree
+        self._build(int(ghost_capacity if ghost_capacity is not None else n_slots))
+
+    def _build(self, n_slots: int):
+        """Everything that depends on the partition: the rank's Semidiscretization (bounding box =
+        slab + ghost layer in x), transport and halo objects.  `self.fluid`, `self.wall`,
+        `self.layout`, `self.owned_index` are set."""
+        import torch
+        from .semidiscretization import (B200Backend, FullGridCellList, GridNeighborhoodSearch,
+                                         Semidiscretization)
+        rank, world, device = self.rank, self.world, self._device_index
+        R_f, R_w = self._radii
+        nd = self.fluid.ndims
+        tree = self._tree
+        self.n_owned = self.fluid.nparticles
+        lo, hi = self.layout.planes[rank], self.layout.planes[rank + 1]
+        self.ghost_capacity = 0 if world == 1 else int(n_slots)
+        # bounding box of the rank: slab + ghost layer in x, the whole tank in y, z
+        gmin, gmax = self._gbox
         pad = self.layout.halo + self.layout.skin + max(R_f, R_w)
         mn, mx = gmin.copy(), gmax.copy()
         mn[0] = max(gmin[0], lo - pad) if np.isfinite(lo) else gmin[0]
         mx[0] = min(gmax[0], hi + pad) if np.isfinite(hi) else gmax[0]
         nhs = GridNeighborhoodSearch(nd, cell_list=FullGridCellList(min_corner=mn, max_corner=mx))
-        backend = B200Backend(device=device, ode_memory="device", interact_variant=interact_variant)
+        backend = B200Backend(device=device, ode_memory="device", interact_variant=self._interact_variant)
         backend.ghost_capacity = self.ghost_capacity
         systems = (self.fluid,) if self.wall is None else (self.fluid, self.wall)
         self.semi = Semidiscretization(*systems, neighborhood_search=nhs, parallelization_backend=backend)
         self.device = torch.device("cuda", device)
         self.peer = None
-        self.transport = transport if transport is not None else DistTransport(rank, world)
+        self.transport = self._transport_arg if self._transport_arg is not None else DistTransport(rank, world)
         self.halo = HaloExchange(self.layout, rank, self.transport, tree)
         self.nd, self.nv = nd, self.fluid.v_nvariables
-        self._lib = _lib
         self.n_ghost = 0
 
     # -- setup ---------------------------------------------------------------------------
@@ -618,3 +709,112 @@ class SlabSemidiscretization:
 
     def needs_rebalance(self, u_ode) -> bool:
         return not self.halo.check_drift(u_ode.view(self.n_owned, self.nd))
+
+    # -- rebalance: new partition by position, particles migrate to their new owners ----------
+    def rebalance(self, tspan=None):
+        """Re-partition by the current positions (the state in `u_ext` / `v_ext`, i.e. in the
+        views `ode.u0` / `ode.v0`): new slab faces of equal fluid count from a global histogram,
+        every particle (x, v, rho, m, global index) moves to its new owner (`migrate`), the rank's
+        Semidiscretization, ghost slots and exchange areas are rebuilt.  Collective: every rank
+        calls it between two time steps (a `SortingCallback`-like event, sorting.jl:94-114 --
+        particle <-> ODE index changes).  Returns the new `DynamicalODEProblem`; the owned rows
+        are ordered by global particle index (`self.owned_index`)."""
+        import torch
+        import torch.distributed as dist
+        from .model import ContinuityDensity
+        if self.nv != self.nd + 1:
+            raise ValueError("rebalance needs ContinuityDensity (the density travels in v_ode)")
+        group = getattr(self.transport, "group", None)
+        n0, nd = self.n_owned, self.nd
+        u, v = self.u_ext[:n0], self.v_ext[:n0]
+        planes = balanced_planes(u[:, 0], self.world, group)
+        old = self.layout
+        layout = SlabLayout(planes=planes, halo=old.halo, wall_reach=old.wall_reach, skin=old.skin,
+                            direct=old.direct, near_wall=old.near_wall)
+        if self.world > 2 and np.any(np.diff(planes[1:-1]) < layout.halo):
+            raise ValueError("slabs are thinner than the ghost layer: use fewer ranks or a larger problem")
+        dest = torch.bucketize(u[:, 0].to(torch.float64).contiguous(),
+                               torch.as_tensor(planes[1:-1], dtype=torch.float64, device=u.device), right=True)
+        ids = torch.from_numpy(np.ascontiguousarray(self.owned_index, dtype=np.int64)).to(u.device)
+        ids, u, v, mass = migrate([ids.view(-1, 1), u, v, self.mass.view(-1, 1)], dest, self.rank, self.world, group)
+        order = torch.argsort(ids[:, 0])
+        ids, u, v, mass = ids[order, 0], u[order], v[order], mass[order, 0]
+        # the rank's new systems
+        un, vn, mn = u.cpu().numpy(), v.cpu().numpy(), mass.cpu().numpy()
+        tspan = tuple(tspan) if tspan is not None else self.ode.tspan
+        template = self.fluid
+        fluid_k = copy.copy(template)
+        fluid_k.initial_condition = InitialCondition(
+            coordinates=np.ascontiguousarray(un), velocity=np.ascontiguousarray(vn[:, :nd]),
+            mass=np.ascontiguousarray(mn), density=np.ascontiguousarray(vn[:, nd]),
+            pressure=np.zeros(len(un), dtype=template.eltype),
+            particle_spacing=template.initial_condition.particle_spacing)
+        fluid_k.mass = np.ascontiguousarray(mn)
+        fluid_k.pressure = np.zeros(len(un), dtype=template.eltype)
+        wall_k, widx = local_wall(self._wall_global, layout, self.rank)
+        # ghost slots: the neighbours' candidate counts under the new partition
+        n_slots = 0
+        if self.world > 1:
+            lo, hi = float(planes[self.rank]), float(planes[self.rank + 1])
+            mine = torch.zeros(2, dtype=torch.int64, device=u.device)
+            if self.rank > 0:
+                mine[0] = int(candidate_mask(un, lo, -1, layout, self._tree).sum())
+            if self.rank < self.world - 1:
+                mine[1] = int(candidate_mask(un, hi, +1, layout, self._tree).sum())
+            allc = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allc, mine, group=group)
+            if self.rank > 0:
+                n_slots += int(allc[self.rank - 1][1])
+            if self.rank < self.world - 1:
+                n_slots += int(allc[self.rank + 1][0])
+        # swap the handle
+        self.close()
+        self.fluid, self.wall, self.wall_index = fluid_k, wall_k, widx
+        self.owned_index = ids.cpu().numpy()
+        self.layout = layout
+        self.n_rebalances = getattr(self, "n_rebalances", 0) + 1
+        self._build(n_slots)
+        return self.semidiscretize(tspan)
+
+    # -- time loop ---------------------------------------------------------------------------
+    def solve(self, alg, *, dt: float, n_steps: int, check_every: int = 10, t0: float = 0.0):
+        """`n_steps` fixed steps of the 2N-storage Runge-Kutta scheme `alg`
+        (time_integration.CarpenterKennedy2N54) on the rank's particles: per stage one kick!
+        (ghost exchange + RHS) and one drift!, stage updates fused on the device.  Every
+        `check_every` steps all ranks agree (one all_reduce) whether some particle has moved
+        further than the skin allows and `rebalance` if so.  Returns (t, v, u): the owned rows
+        of the final state, matching `self.owned_index`."""
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        L = _lib.load()
+        group = getattr(self.transport, "group", None)
+
+        def stage(A, B, rhs, tmp, state):
+            eltype = _lib.F32 if state.dtype == torch.float32 else _lib.F64
+            self.semi._bind_stream()
+            _lib.check(self.semi._handle, L.tpb_vec_rk2n_stage(
+                self.semi._handle, state.numel(), eltype, float(A), float(B), float(dt),
+                C.c_void_p(rhs.data_ptr()), C.c_void_p(tmp.data_ptr()), C.c_void_p(state.data_ptr())))
+
+        def buffers():
+            v, u = self.ode.v0, self.ode.u0   # views of the extended buffers: no staging copies
+            return v, u, torch.zeros_like(v), torch.zeros_like(u), torch.zeros_like(v), torch.zeros_like(u)
+
+        v, u, dv, du, tmp_v, tmp_u = buffers()
+        t = float(t0)
+        for step in range(int(n_steps)):
+            if self.world > 1 and step % check_every == 0:
+                flag = torch.tensor([1 if self.needs_rebalance(u) else 0], dtype=torch.int32, device=u.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+                if int(flag):
+                    self.rebalance()
+                    v, u, dv, du, tmp_v, tmp_u = buffers()
+            for A, B, c in zip(alg.A, alg.B, alg.c):
+                self.kick_(dv, v, u, self.ode.p, t + c * dt)
+                self.drift_(du, v, u, self.ode.p, t + c * dt)
+                stage(A, B, dv, tmp_v, v)
+                stage(A, B, du, tmp_u, u)
+            t += dt
+        self.semi.synchronize()
+        return t, v, u
