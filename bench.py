@@ -77,13 +77,19 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
-def make_workload(name):
+def make_workload(name, eltype=None, coords=None):
     from trixiparticles.jl_b200 import examples
     ex, arg = WORKLOADS[name]
+    dt = {None: None, "f32": np.float32, "f64": np.float64}
+    kw = {}
+    if dt[eltype] is not None:
+        kw["eltype"] = dt[eltype]
+    if dt[coords] is not None:
+        kw["coordinates_eltype"] = dt[coords]
     if ex == "dam_break_3d":
-        fluid, wall, _ = examples.dam_break_3d(arg)
+        fluid, wall, _ = examples.dam_break_3d(arg, **kw)
     else:
-        fluid, wall, _ = examples.dam_break_2d(arg)
+        fluid, wall, _ = examples.dam_break_2d(arg, **kw)
     ic = fluid.initial_condition
     u = np.ascontiguousarray(ic.coordinates, dtype=fluid.coordinates_eltype)
     v = np.ascontiguousarray(np.concatenate([ic.velocity, ic.density[:, None]], axis=1), dtype=fluid.eltype)
@@ -214,7 +220,7 @@ def run_single(args):
     _lib.load()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    fluid, wall, u, v = make_workload(args.workload)
+    fluid, wall, u, v = make_workload(args.workload, args.eltype, args.coords)
     nd, n_f, n_w = fluid.ndims, fluid.nparticles, wall.nparticles
     tsize, csize = np.dtype(fluid.eltype).itemsize, np.dtype(fluid.coordinates_eltype).itemsize
     if args.e2e_only:
@@ -414,6 +420,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--variant", type=int, default=0, help="interact kernel variant (0 = auto)")
+    ap.add_argument("--eltype", default=None, choices=["f32", "f64"], help="eltype(system) (default: the example's)")
+    ap.add_argument("--coords", default=None, choices=["f32", "f64"], help="coordinates_eltype (default: eltype)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
     ap.add_argument("--e2e-only", action="store_true", help="host-pointer (e2e) timing only (tuning runs)")
