@@ -51,6 +51,8 @@ extern "C" {
 /* smoothing kernels (src/general/smoothing_kernels.jl:191-227, :434-455) */
 #define TPB_KERNEL_WENDLAND_C2 0
 #define TPB_KERNEL_SCHOENBERG_CUBIC 1
+#define TPB_KERNEL_WENDLAND_C4 2 /* smoothing_kernels.jl:489-514 */
+#define TPB_KERNEL_WENDLAND_C6 3 /* smoothing_kernels.jl:548-574 */
 
 /* density calculators (src/general/density_calculators.jl) */
 #define TPB_DENSITY_CONTINUITY 0

@@ -17,6 +17,8 @@ _SO = os.path.join(_HERE, "liboracle_sph.so")
 
 KERNEL_WENDLAND_C2 = 0
 KERNEL_SCHOENBERG_CUBIC = 1
+KERNEL_WENDLAND_C4 = 2
+KERNEL_WENDLAND_C6 = 3
 DENSITY_CONTINUITY = 0
 DENSITY_SUMMATION = 1
 

@@ -32,7 +32,8 @@
 extern "C" {
 #endif
 
-enum { ORC_KERNEL_WENDLAND_C2 = 0, ORC_KERNEL_SCHOENBERG_CUBIC = 1 };
+enum { ORC_KERNEL_WENDLAND_C2 = 0, ORC_KERNEL_SCHOENBERG_CUBIC = 1, ORC_KERNEL_WENDLAND_C4 = 2,
+       ORC_KERNEL_WENDLAND_C6 = 3 };
 enum { ORC_DENSITY_CONTINUITY = 0, ORC_DENSITY_SUMMATION = 1 };
 
 /* WeaklyCompressibleSPHSystem fields (wcsph/system.jl:65-86) that the RHS reads. */

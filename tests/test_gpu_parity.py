@@ -185,6 +185,23 @@ def test_chunked_staging_small_shared_memory(oracle, monkeypatch, smem, list_len
     semi.close()
 
 
+@pytest.mark.parametrize("kernel_cls", ["WendlandC4Kernel", "WendlandC6Kernel"])
+@pytest.mark.parametrize("config", ["dam_break_2d_f64", "dam_break_3d_f32"])
+def test_kick_wendland_c4_c6(oracle, kernel_cls, config):
+    """The higher-order Wendland kernels of the reference's GPU test matrix
+    (test/examples/gpu.jl:349-394; smoothing_kernels.jl:489-574), fluid and wall model."""
+    import copy
+    if config == "dam_break_2d_f64":
+        fluid, wall, _ = examples.dam_break_2d(20)
+    else:
+        fluid, wall, _ = examples.dam_break_3d(0.1)
+    kernel = getattr(tp, kernel_cls)(fluid.ndims)
+    fluid.smoothing_kernel = kernel
+    wall.boundary_model.smoothing_kernel = kernel
+    u, v = examples.perturbed_state(fluid)
+    check_against_oracle(fluid, wall, u, v)
+
+
 @pytest.mark.parametrize("example", ["dam_break_2d", "hydrostatic_2d"])
 def test_kick_summation_density(oracle, example):
     """SummationDensity variant (density_calculators.jl:26-50; dam_break_2d variant in

@@ -6,7 +6,7 @@ import pytest
 import trixiparticles.jl_b200 as tp
 from oracle import adapter
 
-WC2, CUBIC = 0, 1
+WC2, CUBIC, WC4, WC6 = 0, 1, 2, 3
 
 
 # test/schemes/fluid/viscosity.jl:2-42
@@ -62,7 +62,7 @@ def test_cole_inverse_roundtrip(oracle):
 
 
 # test/general/smoothing_kernels.jl:61-73 (normalisation) and :99-132 (derivative)
-@pytest.mark.parametrize("kernel", [WC2, CUBIC])
+@pytest.mark.parametrize("kernel", [WC2, CUBIC, WC4, WC6])
 @pytest.mark.parametrize("nd", [2, 3])
 def test_kernel_normalisation_and_derivative(oracle, kernel, nd):
     from scipy.integrate import quad
@@ -80,8 +80,27 @@ def test_kernel_normalisation_and_derivative(oracle, kernel, nd):
         assert oracle.kernel(kernel, nd, np.nextafter(2 * h, 0), h) >= 0.0
 
 
+def test_wendland_c4_c6_closed_forms(oracle):
+    """smoothing_kernels.jl:491-514, :550-574 evaluated directly (independent of the C code)."""
+    for nd in (2, 3):
+        for h in (0.3, 1.1):
+            for r in (0.0, 0.4 * h, 1.3 * h, 1.99 * h):
+                q = r / h
+                s4 = {2: 9 / (4 * np.pi), 3: 495 / (256 * np.pi)}[nd] / h ** nd
+                s6 = {2: 39 / (14 * np.pi), 3: 1365 / (512 * np.pi)}[nd] / h ** nd
+                w4 = s4 * (1 - q / 2) ** 6 * (35 * q * q / 12 + 3 * q + 1)
+                w6 = s6 * (1 - q / 2) ** 8 * (4 * q ** 3 + 25 * q * q / 4 + 4 * q + 1)
+                assert oracle.kernel(WC4, nd, r, h) == pytest.approx(w4, rel=1e-14, abs=1e-300)
+                assert oracle.kernel(WC6, nd, r, h) == pytest.approx(w6, rel=1e-14, abs=1e-300)
+                if r > 0:
+                    d4 = s4 * (-7 / 3) * (2 + 5 * q) * (1 - q / 2) ** 5 / h ** 2
+                    d6 = s6 * (-11 / 4) * (8 * q * q + 7 * q + 2) * (1 - q / 2) ** 7 / h ** 2
+                    assert oracle.kernel_deriv_div_r(WC4, nd, r, h) == pytest.approx(d4, rel=1e-13)
+                    assert oracle.kernel_deriv_div_r(WC6, nd, r, h) == pytest.approx(d6, rel=1e-13)
+
+
 # test/general/smoothing_kernels.jl:135-176: Float32 evaluation stays close to Float64
-@pytest.mark.parametrize("kernel", [WC2, CUBIC])
+@pytest.mark.parametrize("kernel", [WC2, CUBIC, WC4, WC6])
 def test_kernel_float32(oracle, kernel):
     for nd in (2, 3):
         for r in [0.1, 0.5, 1.3]:

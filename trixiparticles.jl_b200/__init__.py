@@ -10,7 +10,8 @@ from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
                     BoundaryModelDummyParticles, ContinuityDensity,
                     DensityDiffusionMolteniColagrossi, SchoenbergCubicSplineKernel,
                     SourceTermDamping, StateEquationCole, SummationDensity, WallBoundarySystem,
-                    WeaklyCompressibleSPHSystem, WendlandC2Kernel, compact_support)
+                    WeaklyCompressibleSPHSystem, WendlandC2Kernel, WendlandC4Kernel, WendlandC6Kernel,
+                    compact_support)
 from .semidiscretization import (B200Backend, DynamicalODEProblem, FullGridCellList,
                                  GridNeighborhoodSearch, Semidiscretization, drift_, kick_,
                                  semidiscretize)
@@ -21,7 +22,8 @@ __all__ = [
     "AdamiPressureExtrapolation", "ArtificialViscosityMonaghan", "BoundaryModelDummyParticles",
     "ContinuityDensity", "DensityDiffusionMolteniColagrossi", "SchoenbergCubicSplineKernel",
     "SourceTermDamping", "StateEquationCole", "SummationDensity", "WallBoundarySystem",
-    "WeaklyCompressibleSPHSystem", "WendlandC2Kernel", "compact_support", "B200Backend",
+    "WeaklyCompressibleSPHSystem", "WendlandC2Kernel", "WendlandC4Kernel", "WendlandC6Kernel",
+    "compact_support", "B200Backend",
     "DynamicalODEProblem", "FullGridCellList", "GridNeighborhoodSearch", "Semidiscretization",
     "drift_", "kick_", "semidiscretize", "InitialCondition", "RectangularShape",
     "RectangularTank", "union", "interpolate_line", "interpolate_points",

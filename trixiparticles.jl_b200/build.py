@@ -12,6 +12,8 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    # no -split-compile: it halves the build time (one translation unit, ~100 kernel
+    # instantiations) but costs 7.7 % in k_interact_tiles (0.942 vs 0.875 ms, measured on B200)
 ]
 
 

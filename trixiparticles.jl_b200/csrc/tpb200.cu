@@ -135,10 +135,21 @@ KernelConst<T> make_kernel_const(int kernel, int nd, double h_)
     k.h = (T)h_;
     k.h_inv = (T)1 / k.h;
     T sigma;
-    if (kernel == TPB_KERNEL_WENDLAND_C2)
+    k.c_d = (T)0;
+    k.order = 0;
+    if (kernel == TPB_KERNEL_WENDLAND_C2) {
         sigma = nd == 2 ? (T)(7.0 / (4.0 * pi)) : (T)(21.0 / (16.0 * pi));
-    else
+    } else if (kernel == TPB_KERNEL_WENDLAND_C4) {
+        sigma = nd == 2 ? (T)(9.0 / (pi * 4.0)) : (T)(495.0 / (pi * 256.0));
+        k.c_d = (T)(-7.0 / 3.0);
+        k.order = 4;
+    } else if (kernel == TPB_KERNEL_WENDLAND_C6) {
+        sigma = nd == 2 ? (T)(39.0 / (pi * 14.0)) : (T)(1365.0 / (pi * 512.0));
+        k.c_d = (T)(-11.0 / 4.0);
+        k.order = 6;
+    } else {
         sigma = nd == 2 ? (T)(10.0 / (pi * 7.0)) : (T)(1.0 / pi);
+    }
     k.nf = nd == 2 ? sigma * (k.h_inv * k.h_inv) : sigma * (k.h_inv * k.h_inv * k.h_inv);
     k.m5nf = (T)(-5) * k.nf;
     k.h_inv2 = k.h_inv * k.h_inv;
@@ -461,20 +472,25 @@ struct Ops {
                                             s.fp.background_pressure, s.fp.clip_negative_pressure);
         const bool summ = s.fp.density_calculator == TPB_DENSITY_SUMMATION;
         prof_mark(s, TPB_PHASE_DENSITY);
+        // kernel template value: 0 Wendland C2, 1 cubic spline, 2 Wendland C4 / C6
+        const int fk = std::min(s.fp.kernel, 2), wk = std::min(s.wp.kernel, 2);
         if (summ) {
-            if (s.fp.kernel == 0) launch_summation<0>(s, g, pc, eos);
-            else launch_summation<1>(s, g, pc, eos);
+            if (fk == 0) launch_summation<0>(s, g, pc, eos);
+            else if (fk == 1) launch_summation<1>(s, g, pc, eos);
+            else launch_summation<2>(s, g, pc, eos);
         }
         prof_mark(s, TPB_PHASE_BOUNDARY);
         if (s.n_w > 0) {
-            rc = s.wp.kernel == 0 ? launch_adami<0>(s, g) : launch_adami<1>(s, g);
+            rc = wk == 0 ? launch_adami<0>(s, g) : wk == 1 ? launch_adami<1>(s, g) : launch_adami<2>(s, g);
             if (rc) return rc;
         }
         prof_mark(s, TPB_PHASE_INTERACT);
-        if (s.fp.kernel == 0)
+        if (fk == 0)
             rc = summ ? launch_interact<0, 1>(s, g, pc, d_dv) : launch_interact<0, 0>(s, g, pc, d_dv);
-        else
+        else if (fk == 1)
             rc = summ ? launch_interact<1, 1>(s, g, pc, d_dv) : launch_interact<1, 0>(s, g, pc, d_dv);
+        else
+            rc = summ ? launch_interact<2, 1>(s, g, pc, d_dv) : launch_interact<2, 0>(s, g, pc, d_dv);
         if (rc) return rc;
         prof_mark(s, TPB_PHASE_END);
         if (s.prof_capacity > 0 && s.prof_kicks < s.prof_capacity) s.prof_kicks++;
@@ -775,7 +791,7 @@ int32_t tpb_add_fluid_system(tpb_semi_t semi, const tpb_fluid_params *p, int64_t
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "tpb_fluid_params.struct_size mismatch");
     if (s->fluid_index >= 0)
         return fail(s, TPB_ERR_UNSUPPORTED, "only one fluid system per semidiscretization is supported");
-    if (p->kernel != TPB_KERNEL_WENDLAND_C2 && p->kernel != TPB_KERNEL_SCHOENBERG_CUBIC)
+    if (p->kernel < TPB_KERNEL_WENDLAND_C2 || p->kernel > TPB_KERNEL_WENDLAND_C6)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown smoothing kernel");
     if (p->density_calculator != TPB_DENSITY_CONTINUITY && p->density_calculator != TPB_DENSITY_SUMMATION)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown density calculator");
@@ -804,7 +820,7 @@ int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *p, int64_t n
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "tpb_wall_params.struct_size mismatch");
     if (s->wall_index >= 0)
         return fail(s, TPB_ERR_UNSUPPORTED, "only one wall system per semidiscretization is supported");
-    if (p->kernel != TPB_KERNEL_WENDLAND_C2 && p->kernel != TPB_KERNEL_SCHOENBERG_CUBIC)
+    if (p->kernel < TPB_KERNEL_WENDLAND_C2 || p->kernel > TPB_KERNEL_WENDLAND_C6)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown smoothing kernel");
     if (!(p->smoothing_length > 0) || !(p->sound_speed > 0) || !(p->reference_density > 0) || p->exponent == 0)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "smoothing_length, sound_speed, reference_density must be positive");

@@ -70,6 +70,8 @@ struct KernelConst {
     T m5nf;     // -5 * nf                (Wendland C2 derivative)
     T h_inv2;   // h_inv * h_inv
     T support;  // compact_support = 2h
+    T c_d;      // Wendland C4 / C6: derivative prefactor (-7/3 or -11/4) in T
+    int order;  // Wendland C4 / C6 (SmoothingKernel<2>): 4 or 6
 };
 
 template <int KERNEL, typename T>
@@ -111,6 +113,39 @@ struct SmoothingKernel<1, T> {
         T three_lt = q < (T)1 ? (T)3 : (T)0;
         T result = (T)(-3) * (a * a) / (T)4 + three_lt * (b * b);
         return div_fast(k.nf * result * k.h_inv, r);
+    }
+};
+
+// WendlandC4Kernel / WendlandC6Kernel (smoothing_kernels.jl:489-514, :548-574), one template
+// value, the order is a warp-uniform run-time switch:
+//   C4: W = nf (1-q/2)^6 (35 q^2/12 + 3q + 1);        (dW/dr)/r = nf (-7/3)(2 + 5q)(1-q/2)^5 h^-2
+//   C6: W = nf (1-q/2)^8 (4q^3 + 25 q^2/4 + 4q + 1);  (dW/dr)/r = nf (-11/4)(8q^2 + 7q + 2)(1-q/2)^7 h^-2
+template <typename T>
+struct SmoothingKernel<2, T> {
+    static __device__ __forceinline__ T w_unsafe(const KernelConst<T> &k, T r)
+    {
+        T q = r * k.h_inv;
+        T t = (T)1 - q / (T)2;
+        T t2 = t * t;
+        if (k.order == 4) {
+            T t6 = t2 * t2 * t2;
+            return k.nf * (t6 * ((T)35 * (q * q) / (T)12 + (T)3 * q + (T)1));
+        }
+        T t4 = t2 * t2;
+        T t8 = t4 * t4;
+        return k.nf * (t8 * ((T)4 * (q * q * q) + (T)25 * (q * q) / (T)4 + (T)4 * q + (T)1));
+    }
+    static __device__ __forceinline__ T dw_div_r(const KernelConst<T> &k, T r)
+    {
+        T q = r * k.h_inv;
+        T t = (T)1 - q / (T)2;
+        T t2 = t * t;
+        if (k.order == 4) {
+            T t5 = t2 * t2 * t;
+            return k.nf * (k.c_d * ((T)2 + (T)5 * q) * t5 * k.h_inv2);
+        }
+        T t7 = t2 * t2 * t2 * t;
+        return k.nf * (k.c_d * ((T)8 * (q * q) + (T)7 * q + (T)2) * t7 * k.h_inv2);
     }
 };
 
@@ -243,6 +278,8 @@ struct FastConst {
     float r2, az2;         // search radius^2, almostzero^2
     float h_inv, nfh;      // 1/h; cubic spline: nf * h_inv
     float c_t, c_w;        // Wendland C2: t = 1 + c_t r, wdr = c_w t^3
+    float c_d;             // Wendland C4 / C6: nf * (-7/3 or -11/4) * h^-2
+    int order;             // Wendland C4 / C6
     float h, eps_h2;       // viscosity
     float ac2, b2;         // 2 alpha c, 2 beta
     float dhc2;            // 2 delta h c (0 without density diffusion)
@@ -257,6 +294,8 @@ __host__ __device__ inline FastConst make_fast_const(const PairConst<float> &k)
     f.nfh = k.kern.nf * k.kern.h_inv;
     f.c_t = -0.5f * k.kern.h_inv;
     f.c_w = k.kern.m5nf * k.kern.h_inv2;
+    f.c_d = k.kern.nf * k.kern.c_d * k.kern.h_inv2;
+    f.order = k.kern.order;
     f.h = k.kern.h;
     f.eps_h2 = k.eps_h2;
     f.ac2 = k.has_viscosity ? 2.0f * k.alpha * k.c : 0.0f;
@@ -272,6 +311,12 @@ __device__ __forceinline__ float fast_wdr(const FastConst &c, float dist, float 
     if (KERNEL == 0) {
         const float t = fmaf(dist, c.c_t, 1.0f);
         return c.c_w * (t * t * t);
+    } else if (KERNEL == 2) {
+        const float q = dist * c.h_inv;
+        const float t = fmaf(dist, c.c_t, 1.0f);
+        const float t2 = t * t;
+        if (c.order == 4) return c.c_d * fmaf(5.0f, q, 2.0f) * (t2 * t2 * t);
+        return c.c_d * fmaf(fmaf(8.0f, q, 7.0f), q, 2.0f) * (t2 * t2 * t2 * t);
     } else {
         const float q = dist * c.h_inv;
         const float a = 2.0f - q, b = 1.0f - q;

@@ -22,7 +22,7 @@ from __future__ import annotations
 import numpy as np
 
 from .model import (SchoenbergCubicSplineKernel, WallBoundarySystem, WeaklyCompressibleSPHSystem,
-                    WendlandC2Kernel, compact_support)
+                    WendlandC2Kernel, WendlandC4Kernel, WendlandC6Kernel, compact_support)
 
 
 def kernel(smoothing_kernel, r, h):
@@ -33,6 +33,12 @@ def kernel(smoothing_kernel, r, h):
     if isinstance(smoothing_kernel, WendlandC2Kernel):
         sigma = {2: 7 / (4 * np.pi), 3: 21 / (16 * np.pi)}[nd]
         w = sigma / h ** nd * (1 - q / 2) ** 4 * (2 * q + 1)
+    elif isinstance(smoothing_kernel, WendlandC4Kernel):
+        sigma = {2: 9 / (4 * np.pi), 3: 495 / (256 * np.pi)}[nd]
+        w = sigma / h ** nd * (1 - q / 2) ** 6 * (35 * q ** 2 / 12 + 3 * q + 1)
+    elif isinstance(smoothing_kernel, WendlandC6Kernel):
+        sigma = {2: 39 / (14 * np.pi), 3: 1365 / (512 * np.pi)}[nd]
+        w = sigma / h ** nd * (1 - q / 2) ** 8 * (4 * q ** 3 + 25 * q ** 2 / 4 + 4 * q + 1)
     elif isinstance(smoothing_kernel, SchoenbergCubicSplineKernel):
         sigma = {2: 10 / (7 * np.pi), 3: 1 / np.pi}[nd]
         w = sigma / h ** nd * ((2 - q) ** 3 / 4 - np.where(q < 1, (1 - q) ** 3, 0.0))

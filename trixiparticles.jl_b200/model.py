@@ -17,6 +17,8 @@ from .setups import InitialCondition
 # ids shared with include/tpb200.h
 KERNEL_WENDLAND_C2 = 0
 KERNEL_SCHOENBERG_CUBIC = 1
+KERNEL_WENDLAND_C4 = 2
+KERNEL_WENDLAND_C6 = 3
 DENSITY_CONTINUITY = 0
 DENSITY_SUMMATION = 1
 
@@ -31,6 +33,20 @@ class WendlandC2Kernel:
 class SchoenbergCubicSplineKernel:
     ndims: int
     kernel_id: int = KERNEL_SCHOENBERG_CUBIC
+
+
+@dataclass(frozen=True)
+class WendlandC4Kernel:
+    """smoothing_kernels.jl:489-514."""
+    ndims: int
+    kernel_id: int = KERNEL_WENDLAND_C4
+
+
+@dataclass(frozen=True)
+class WendlandC6Kernel:
+    """smoothing_kernels.jl:548-574."""
+    ndims: int
+    kernel_id: int = KERNEL_WENDLAND_C6
 
 
 def compact_support(kernel, h):
