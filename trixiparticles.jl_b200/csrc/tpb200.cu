@@ -229,9 +229,10 @@ int exclusive_scan(Semi &s, const int *d_in, int n, int *d_out)
 
 template <int ND, typename T, typename CT>
 struct Ops {
-    // threads per target particle in the tile sweeps (tpb_tiles.cuh): the Float32 kernels fit
-    // 2 x 384 threads into the register file; the Float64 ones keep one thread per target
-    static constexpr int KS = std::is_same<T, float>::value && std::is_same<CT, float>::value ? TPB_SPLIT : 1;
+    // threads per target particle in the tile sweeps (tpb_tiles.cuh): the Float32 kernels (with
+    // Float32 or Float64 coordinates) fit 2 x 384 threads into the register file; the Float64
+    // ones keep one thread per target
+    static constexpr int KS = std::is_same<T, float>::value ? TPB_SPLIT : 1;
     static constexpr int nv(const Semi &s) { return s.fp.density_calculator == TPB_DENSITY_SUMMATION ? ND : ND + 1; }
 
     // ---- counting sort of one point set into the shared grid: key/slot/count/scan/scatter

@@ -326,18 +326,21 @@ __device__ __forceinline__ float fast_wdr(const FastConst &c, float dist, float 
 }
 
 // Exact reference predicate + fast physics.  pa_term: DENS == 1 ? p_a / rho_a^2 : unused.
-template <int ND, int KERNEL, int DENS, bool SAME>
-__device__ __forceinline__ void interact_pair_fast(const FastConst &c, const V4<float> &xi,
-                                                   const V4<float> &xj, float rho_a, float p_a,
+// CT = double: the reference's default single-precision set-up (Float32 fields, Float64
+// coordinates, docs/src/gpu.md "Single precision simulations"): the difference is formed in
+// double and rounded to float exactly as `convert(T, x_i - y_j)` does.
+template <int ND, int KERNEL, int DENS, bool SAME, typename CT>
+__device__ __forceinline__ void interact_pair_fast(const FastConst &c, const V4<CT> &xi,
+                                                   const V4<CT> &xj, float rho_a, float p_a,
                                                    float pa_term, const float (&v_a)[3], float vbx,
                                                    float vby, float vbz, float rho_b, float p_b,
                                                    float (&dv)[3], float &drho)
 {
     float pd[3];
-    float d2 = pos_diff_d2<ND, float, float>(xi, xj, pd);  // exactly rounded, as the reference
+    float d2 = pos_diff_d2<ND, float, CT>(xi, xj, pd);  // exactly rounded, as the reference
     const bool ok = d2 <= c.r2 && d2 >= c.az2;
     d2 = ok ? d2 : c.r2;
-    const float mb = ok ? xj.w : 0.0f;
+    const float mb = ok ? (float)xj.w : 0.0f;
     const float rs = rsqrt_approx(d2);
     const float dist = d2 * rs;
     const float mw = mb * fast_wdr<KERNEL>(c, dist, rs);

@@ -769,7 +769,7 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     const T rho_a = bi.w;
     const T v_a[3] = {bi.x, bi.y, bi.z};
 
-    constexpr bool FAST = std::is_same<T, float>::value && std::is_same<CT, float>::value;
+    constexpr bool FAST = std::is_same<T, float>::value;  // Float32 fields; coordinates float or double
     FastConst fc = {};
     float pa_term = 0.f;
     if constexpr (FAST) {
