@@ -351,6 +351,12 @@ def run_single(args):
     # ---- e2e arm: host ODE vectors through the same API, copies inside the timed region
     e2e = run_e2e(tp, torch, fluid, wall, u, v, args)
 
+    # ---- the reference's default single-precision set-up: Float32 fields, Float64 coordinates
+    # (docs/src/gpu.md "Single precision simulations"; examples/fluid/dam_break_3d.jl:36-39)
+    variants = None
+    if args.eltype is None and args.coords is None and tsize == 4 and csize == 4 and not args.no_variants:
+        variants = {"f32_fields_f64_coordinates": run_variant(tp, torch, args, "f32", "f64")}
+
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample
     cpu = None
     if not args.no_cpu_baseline:
@@ -368,16 +374,48 @@ def run_single(args):
         "data": "synthetic",
         "config": {"workload": args.workload, "n_fluid": n_f, "n_wall": n_w, "n_wall_active": n_w_active,
                    "ndims": nd, "coords_dtype": "f32" if csize == 4 else "f64",
-                   "kernel": "WendlandC2" if fluid.smoothing_kernel.kernel_id == 0 else "SchoenbergCubicSpline",
+                   "kernel": type(fluid.smoothing_kernel).__name__,
                    "nhs": "rebuilt every kick", "l2": "flushed between steps (256 MiB write, untimed)",
                    "interact_variant": int(st1.interact_variant_used)},
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         "phases_ms": {**{k: phases[k] for k in _lib.PHASES}, "kick": float(ms_kick.mean()),
                       "drift": float(ms_drift.mean()), "step_min": float(ms_steps.min()),
                       "step_median": float(np.median(ms_steps)), "step_l2_warm": ms_warm},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "variants": variants,
     }
     print(json.dumps(line))
+
+
+def run_variant(tp, torch, args, eltype, coords, steps=10):
+    """Device-resident kick!+drift! of the same workload in another precision set-up."""
+    fluid, wall, u, v = make_workload(args.workload, eltype, coords)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(
+        device=0, ode_memory="device", interact_variant=args.variant))
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    dev = torch.device("cuda", 0)
+    u_d, v_d = torch.from_numpy(u.reshape(-1)).to(dev), torch.from_numpy(v.reshape(-1)).to(dev)
+    dv_d, du_d = torch.empty_like(v_d), torch.empty_like(u_d)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
+        ode.f2(du_d, v_d, u_d, ode.p, 0.0)
+    semi.set_profiling(steps)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k & 0xFF)
+        starts[k].record()
+        ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
+        ode.f2(du_d, v_d, u_d, ode.p, 0.0)
+        ends[k].record()
+    torch.cuda.synchronize()
+    semi.synchronize()
+    ms = float(np.mean([s.elapsed_time(e) for s, e in zip(starts, ends)]))
+    phases = semi.phase_times()
+    n_f = fluid.nparticles
+    semi.close()
+    return {"ms_per_step": ms, "value": n_f / (ms * 1e-3), "unit": UNIT, "steps": steps,
+            "dtype": eltype, "coords_dtype": coords, "phases_ms": {k: phases[k] for k in phases}}
 
 
 def run_e2e(tp, torch, fluid, wall, u, v, args):
@@ -423,6 +461,7 @@ def main():
     ap.add_argument("--eltype", default=None, choices=["f32", "f64"], help="eltype(system) (default: the example's)")
     ap.add_argument("--coords", default=None, choices=["f32", "f64"], help="coordinates_eltype (default: eltype)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the other precision set-ups")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
     ap.add_argument("--e2e-only", action="store_true", help="host-pointer (e2e) timing only (tuning runs)")
     args = ap.parse_args()
