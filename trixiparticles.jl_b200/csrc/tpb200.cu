@@ -24,9 +24,13 @@
 
 using namespace tpb;
 
-namespace {
+// The library is built from several translation units of THIS file (build.py): one per
+// (ndims, eltype, coordinates eltype) combination, compiled with -DTPB_TU_ND / _T / _CT / _TAG and
+// holding the kernels of that combination behind five entry functions, plus the main one with the
+// C ABI.  Everything shared lives in this named namespace with internal linkage per unit.
+namespace tpbhost {
 
-thread_local std::string g_create_error;
+static thread_local std::string g_create_error;
 
 struct Semi {
     tpb_config cfg{};
@@ -95,7 +99,7 @@ inline void *mapped_host_alias(const void *p)
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
-int fail(Semi *s, int code, const std::string &msg)
+static int fail(Semi *s, int code, const std::string &msg)
 {
     if (s) s->err = msg; else g_create_error = msg;
     return code;
@@ -217,7 +221,7 @@ GridConst<CT> make_grid_const(const Semi &s)
 }
 
 // ---------------------------------------------------------------------------------------
-int exclusive_scan(Semi &s, const int *d_in, int n, int *d_out)
+static int exclusive_scan(Semi &s, const int *d_in, int n, int *d_out)
 {
     int nblocks = cdiv(n, SCAN_TILE);
     if (nblocks > SCAN_TILE) return fail(&s, TPB_ERR_UNSUPPORTED, "cell grid too large for the scan");
@@ -671,37 +675,80 @@ struct Ops {
     }
 };
 
-#ifdef TPB_DEV_ONLY_3D_F32  // development builds: one instantiation, quick to compile
-#define DISPATCH(S, CALL)                                                                     \
-    do {                                                                                      \
-        const int nd_ = (S).cfg.ndims, t_ = (S).cfg.eltype, ct_ = (S).cfg.coords_eltype;      \
-        if (nd_ == 3 && t_ == TPB_F32 && ct_ == TPB_F32) return Ops<3, float, float>::CALL;   \
-        return fail(&(S), TPB_ERR_UNSUPPORTED, "development build: 3-D Float32 only");        \
-    } while (0)
-#else
-#define DISPATCH(S, CALL)                                                                     \
-    do {                                                                                      \
-        const int nd_ = (S).cfg.ndims, t_ = (S).cfg.eltype, ct_ = (S).cfg.coords_eltype;      \
-        if (nd_ == 2 && t_ == TPB_F32 && ct_ == TPB_F32) return Ops<2, float, float>::CALL;   \
-        if (nd_ == 3 && t_ == TPB_F32 && ct_ == TPB_F32) return Ops<3, float, float>::CALL;   \
-        if (nd_ == 2 && t_ == TPB_F32 && ct_ == TPB_F64) return Ops<2, float, double>::CALL;  \
-        if (nd_ == 3 && t_ == TPB_F32 && ct_ == TPB_F64) return Ops<3, float, double>::CALL;  \
-        if (nd_ == 2 && t_ == TPB_F64 && ct_ == TPB_F64) return Ops<2, double, double>::CALL; \
-        if (nd_ == 3 && t_ == TPB_F64 && ct_ == TPB_F64) return Ops<3, double, double>::CALL; \
-        return fail(&(S), TPB_ERR_UNSUPPORTED, "unsupported ndims / eltype combination");     \
-    } while (0)
+// ---- entry points of one (ND, T, CT) combination (external linkage: defined in that unit)
+#define TPB_CAT_(a, b) a##b
+#define TPB_CAT(a, b) TPB_CAT_(a, b)
+#define TPB_DECLARE_ENTRIES(TAG)                                                                         \
+    int TPB_CAT(init_wall_, TAG)(Semi &s);                                                               \
+    int TPB_CAT(kick_, TAG)(Semi &s, void *dv, const void *v, const void *u);                            \
+    int TPB_CAT(drift_, TAG)(Semi &s, void *du, const void *v, const void *u);                           \
+    int TPB_CAT(get_field_, TAG)(Semi &s, int sys, int field, void *out, int64_t n);                     \
+    int TPB_CAT(pairs_, TAG)(Semi &s, int sys, int nb, const void *u, int64_t cap, int32_t *oi, int32_t *oj, \
+                             int64_t *cnt);
+#define TPB_DEFINE_ENTRIES(TAG, ND, T, CT)                                                               \
+    int TPB_CAT(init_wall_, TAG)(Semi &s) { return Ops<ND, T, CT>::init_wall(s); }                       \
+    int TPB_CAT(kick_, TAG)(Semi &s, void *dv, const void *v, const void *u)                             \
+    {                                                                                                    \
+        return Ops<ND, T, CT>::kick(s, dv, v, u);                                                        \
+    }                                                                                                    \
+    int TPB_CAT(drift_, TAG)(Semi &s, void *du, const void *v, const void *u)                            \
+    {                                                                                                    \
+        return Ops<ND, T, CT>::drift(s, du, v, u);                                                       \
+    }                                                                                                    \
+    int TPB_CAT(get_field_, TAG)(Semi &s, int sys, int field, void *out, int64_t n)                      \
+    {                                                                                                    \
+        return Ops<ND, T, CT>::get_field(s, sys, field, out, n);                                         \
+    }                                                                                                    \
+    int TPB_CAT(pairs_, TAG)(Semi &s, int sys, int nb, const void *u, int64_t cap, int32_t *oi, int32_t *oj, \
+                             int64_t *cnt)                                                               \
+    {                                                                                                    \
+        return Ops<ND, T, CT>::neighbor_pairs(s, sys, nb, u, cap, oi, oj, cnt);                          \
+    }
+TPB_DECLARE_ENTRIES(2ff)
+TPB_DECLARE_ENTRIES(3ff)
+TPB_DECLARE_ENTRIES(2fd)
+TPB_DECLARE_ENTRIES(3fd)
+TPB_DECLARE_ENTRIES(2dd)
+TPB_DECLARE_ENTRIES(3dd)
+
+#if defined(TPB_TU_TAG)  // a kernel unit: -DTPB_TU_TAG=3ff -DTPB_TU_ND=3 -DTPB_TU_T=float -DTPB_TU_CT=float
+TPB_DEFINE_ENTRIES(TPB_TU_TAG, TPB_TU_ND, TPB_TU_T, TPB_TU_CT)
+#elif defined(TPB_SINGLE_TU)  // everything in one unit (slow to compile)
+TPB_DEFINE_ENTRIES(2ff, 2, float, float)
+TPB_DEFINE_ENTRIES(3ff, 3, float, float)
+TPB_DEFINE_ENTRIES(2fd, 2, float, double)
+TPB_DEFINE_ENTRIES(3fd, 3, float, double)
+TPB_DEFINE_ENTRIES(2dd, 2, double, double)
+TPB_DEFINE_ENTRIES(3dd, 3, double, double)
 #endif
 
-int dispatch_init_wall(Semi &s) { DISPATCH(s, init_wall(s)); }
-int dispatch_kick(Semi &s, void *dv, const void *v, const void *u) { DISPATCH(s, kick(s, dv, v, u)); }
-int dispatch_drift(Semi &s, void *du, const void *v, const void *u) { DISPATCH(s, drift(s, du, v, u)); }
-int dispatch_get_field(Semi &s, int sys, int field, void *out, int64_t n) { DISPATCH(s, get_field(s, sys, field, out, n)); }
-int dispatch_pairs(Semi &s, int sys, int nb, const void *u, int64_t cap, int32_t *oi, int32_t *oj, int64_t *cnt)
+#ifndef TPB_TU_TAG  // the main unit: dispatch + C ABI
+#define DISPATCH(S, NAME, ...)                                                                \
+    do {                                                                                      \
+        const int nd_ = (S).cfg.ndims, t_ = (S).cfg.eltype, ct_ = (S).cfg.coords_eltype;      \
+        if (nd_ == 2 && t_ == TPB_F32 && ct_ == TPB_F32) return NAME##2ff(__VA_ARGS__);       \
+        if (nd_ == 3 && t_ == TPB_F32 && ct_ == TPB_F32) return NAME##3ff(__VA_ARGS__);       \
+        if (nd_ == 2 && t_ == TPB_F32 && ct_ == TPB_F64) return NAME##2fd(__VA_ARGS__);       \
+        if (nd_ == 3 && t_ == TPB_F32 && ct_ == TPB_F64) return NAME##3fd(__VA_ARGS__);       \
+        if (nd_ == 2 && t_ == TPB_F64 && ct_ == TPB_F64) return NAME##2dd(__VA_ARGS__);       \
+        if (nd_ == 3 && t_ == TPB_F64 && ct_ == TPB_F64) return NAME##3dd(__VA_ARGS__);       \
+        return fail(&(S), TPB_ERR_UNSUPPORTED, "unsupported ndims / eltype combination");     \
+    } while (0)
+
+static int dispatch_init_wall(Semi &s) { DISPATCH(s, init_wall_, s); }
+static int dispatch_kick(Semi &s, void *dv, const void *v, const void *u) { DISPATCH(s, kick_, s, dv, v, u); }
+static int dispatch_drift(Semi &s, void *du, const void *v, const void *u) { DISPATCH(s, drift_, s, du, v, u); }
+static int dispatch_get_field(Semi &s, int sys, int field, void *out, int64_t n)
 {
-    DISPATCH(s, neighbor_pairs(s, sys, nb, u, cap, oi, oj, cnt));
+    DISPATCH(s, get_field_, s, sys, field, out, n);
+}
+static int dispatch_pairs(Semi &s, int sys, int nb, const void *u, int64_t cap, int32_t *oi, int32_t *oj,
+                          int64_t *cnt)
+{
+    DISPATCH(s, pairs_, s, sys, nb, u, cap, oi, oj, cnt);
 }
 
-void free_device(Semi &s)
+static void free_device(Semi &s)
 {
     void *ptrs[] = {s.d_mass_f, s.d_u, s.d_v, s.d_dv, s.d_du, s.d_key, s.d_slot, s.d_tmp_perm,
                     s.d_perm_f, s.d_count, s.d_fcell_start, s.d_wcell_start, s.d_block_sums,
@@ -716,12 +763,16 @@ void free_device(Semi &s)
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
 }
 
-double as_double(const unsigned char *p, int eltype, size_t i)
+static double as_double(const unsigned char *p, int eltype, size_t i)
 {
     return eltype == TPB_F64 ? ((const double *)p)[i] : (double)((const float *)p)[i];
 }
+#endif  // !TPB_TU_TAG
 
-}  // namespace
+}  // namespace tpbhost
+
+#ifndef TPB_TU_TAG
+using namespace tpbhost;
 
 // =========================================================================================
 // C ABI
@@ -1343,3 +1394,4 @@ int32_t tpb_host_unregister(void *ptr)
 }
 
 }  // extern "C"
+#endif  // !TPB_TU_TAG (main unit)

@@ -80,7 +80,7 @@ __device__ __forceinline__ int block_inclusive_scan(int v, int &total)
     return inc + offset;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS)
+static __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_block_sums(const int *__restrict__ in, int n, int *__restrict__ block_sums)
 {
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
@@ -94,7 +94,7 @@ k_scan_block_sums(const int *__restrict__ in, int n, int *__restrict__ block_sum
 }
 
 // single block: exclusive scan of up to SCAN_TILE block sums in place
-__global__ void __launch_bounds__(SCAN_THREADS)
+static __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_top(int *__restrict__ block_sums, int nblocks)
 {
     int base = threadIdx.x * SCAN_ITEMS;
@@ -116,7 +116,7 @@ k_scan_top(int *__restrict__ block_sums, int nblocks)
 }
 
 // out[i] = exclusive prefix of in; out[n] = total
-__global__ void __launch_bounds__(SCAN_THREADS)
+static __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_final(const int *__restrict__ in, int n, const int *__restrict__ block_offsets,
              int *__restrict__ out)
 {
@@ -140,7 +140,7 @@ k_scan_final(const int *__restrict__ in, int n, const int *__restrict__ block_of
 }
 
 // ------------------------------------------------------------------ scatter of indices
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_scatter(const int *__restrict__ key, const int *__restrict__ slot,
           const int *__restrict__ cell_start, int n, int *__restrict__ tmp_perm)
 {

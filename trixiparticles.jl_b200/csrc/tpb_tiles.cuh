@@ -94,7 +94,7 @@ __device__ __forceinline__ void fence_proxy_async()
 
 // ------------------------------------------------------------------ tile table
 // row_tiles[r] = number of tiles of cell row r (r = cy + n1 * cz)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_row_tiles(const int *__restrict__ cell_start, int n0, int nrows, int *__restrict__ row_tiles)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,7 +104,7 @@ k_row_tiles(const int *__restrict__ cell_start, int n0, int nrows, int *__restri
 }
 
 // tile descriptors: (first target, one past the last target, cell row, unused)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_fill_tiles(const int *__restrict__ cell_start, int n0, int nrows,
              const int *__restrict__ row_tile_start, int4 *__restrict__ desc)
 {
@@ -121,7 +121,7 @@ k_fill_tiles(const int *__restrict__ cell_start, int n0, int nrows,
 // Both steps and the scan between them in ONE block, for grids of up to TILE_TABLE_MAX_ROWS cell
 // rows (one launch instead of five on the per-kick path).
 constexpr int TILE_TABLE_MAX_ROWS = 16384;
-__global__ void __launch_bounds__(SCAN_THREADS)
+static __global__ void __launch_bounds__(SCAN_THREADS)
 k_row_tile_table(const int *__restrict__ cell_start, int n0, int nrows, int *__restrict__ row_tile_start,
                  int4 *__restrict__ desc)
 {
