@@ -73,13 +73,17 @@ def check_against_oracle(fluid, wall, u, v, tol_scale=1.0, **backend):
 
 
 # ------------------------------------------------------------------ neighbour sets
-@pytest.mark.parametrize("config", ["dam_break_2d", "hydrostatic_2d", "dam_break_3d"])
+@pytest.mark.parametrize("config", ["dam_break_2d", "hydrostatic_2d", "dam_break_3d", "dam_break_3d_f64_coordinates"])
 @pytest.mark.parametrize("jitter", [False, True])
 def test_neighbor_sets_bit_exact(oracle, config, jitter):
     if config == "dam_break_2d":
         fluid, wall, _ = examples.dam_break_2d(20)
     elif config == "hydrostatic_2d":
         fluid, wall, _ = examples.hydrostatic_water_column_2d()
+    elif config == "dam_break_3d_f64_coordinates":
+        # Float32 fields, Float64 coordinates: phase 1 filters on a Float32 copy of the positions
+        # with a padded radius, the predicate is evaluated on the Float64 difference
+        fluid, wall, _ = examples.dam_break_3d(0.125, coordinates_eltype=np.float64)
     else:
         fluid, wall, _ = examples.dam_break_3d(0.125)
     u = fluid.initial_condition.coordinates.copy()

@@ -66,6 +66,9 @@ struct Semi {
     void *d_Aw = nullptr, *d_Ww = nullptr, *d_volw = nullptr;
     int *d_perm_w = nullptr;
     void *d_scratch = nullptr;  // max(n_f, n_w) * sizeof(double): field unsort
+    void *d_Ff = nullptr, *d_Fw = nullptr;  // Float32 filter copies of the sorted positions (f32 / f64 coords)
+    double filter_ref[3] = {0, 0, 0};       // reference point of the copies (coordinate order)
+    float filter_pad = 0;                   // see FilterRef
     TileState tiles;
 
     tpb_stats stats{};
@@ -217,6 +220,8 @@ GridConst<CT> make_grid_const(const Semi &s)
     g.ncells = (int)s.ncells;
     g.sx = s.xsplit;
     g.ax = s.row_axis;
+    for (int d = 0; d < 3; ++d) g.fref.ref[d] = (CT)s.filter_ref[d];
+    g.fref.pad = s.filter_pad;
     return g;
 }
 
@@ -263,17 +268,18 @@ struct Ops {
         if (rc) return rc;
         EosConst<T> eos = make_eos_const<T>(s.fp.sound_speed, s.fp.exponent, s.fp.reference_density,
                                             s.fp.background_pressure, s.fp.clip_negative_pressure);
+        const GridConst<CT> g = make_grid_const<CT>(s);
         if (n > 0) {
             if (s.fp.density_calculator == TPB_DENSITY_CONTINUITY)
                 LAUNCH(s, (k_reorder_fluid<ND, T, CT, 0>), cdiv(n, 256), 256, 0, d_u, d_v,
                        (const T *)s.d_mass_f, s.d_key, s.d_fcell_start, s.d_tmp_perm, n,
                        s.d_fcell_start + s.ncells, s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
-                       s.d_perm_f);
+                       s.d_perm_f, g.fref, (V4<float> *)s.d_Ff);
             else
                 LAUNCH(s, (k_reorder_fluid<ND, T, CT, 1>), cdiv(n, 256), 256, 0, d_u, d_v,
                        (const T *)s.d_mass_f, s.d_key, s.d_fcell_start, s.d_tmp_perm, n,
                        s.d_fcell_start + s.ncells, s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
-                       s.d_perm_f);
+                       s.d_perm_f, g.fref, (V4<float> *)s.d_Ff);
         }
         if (use_tiles(s)) {
             rc = build_tile_table(s, s.d_fcell_start, s.tiles.d_frow_tile_start, s.tiles.d_ftile_desc);
@@ -306,7 +312,7 @@ struct Ops {
         if (n > 0)
             LAUNCH(s, (k_reorder_wall<ND, T, CT>), cdiv(n, 256), 256, 0, d_coords, d_mass, d_dens,
                    s.d_key, s.d_wcell_start, s.d_tmp_perm, n, (V4<CT> *)s.d_Aw, (V2<T> *)s.d_Ww,
-                   s.d_perm_w);
+                   s.d_perm_w, make_grid_const<CT>(s).fref, (V4<float> *)s.d_Fw);
         CUDA_TRY(&s, cudaMemsetAsync(s.d_volw, 0, sizeof(T) * (size_t)std::max(n, 1), s.stream));
         rc = build_tile_table(s, s.d_wcell_start, s.tiles.d_wrow_tile_start, s.tiles.d_wtile_desc, true);
         if (rc) return rc;
@@ -416,7 +422,8 @@ struct Ops {
                    s.tiles.d_n_wactive, s.tiles.d_wactive, s.tiles.d_wtile_desc, s.tiles.d_wtile_ext,
                    s.tiles.d_wtile_rng, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
                    s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
-                   s.interaction[1][0], k, (V2<T> *)s.d_Ww, (T *)s.d_volw, cap, list_len);
+                   s.interaction[1][0], k, (V2<T> *)s.d_Ww, (T *)s.d_volw, cap, list_len,
+                   (const V4<float> *)s.d_Ff);
             return TPB_OK;
         }
         LAUNCH(s, (k_adami<ND, T, CT, KERNEL>), cdiv(n, 128), 128, 0, n, g,
@@ -454,7 +461,7 @@ struct Ops {
                    s.tiles.d_ftile_rng, s.d_fcell_start, (const V4<CT> *)s.d_A,
                    (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f, s.interaction[0][0], has_wall,
                    s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv,
-                   (int)s.n_tgt, cap, list_len);
+                   (int)s.n_tgt, cap, list_len, (const V4<float> *)s.d_Ff, (const V4<float> *)s.d_Fw);
             return TPB_OK;
         }
         LAUNCH(s, (k_interact_pp<ND, T, CT, KERNEL, DENS>), cdiv(n, 128), 128, 0, n, g,
@@ -648,7 +655,8 @@ struct Ops {
                    (const V4<CT> *)(x_fluid ? s.d_A : s.d_Aw), x_fluid ? s.d_perm_f : s.d_perm_w,
                    y_fluid ? s.d_fcell_start : s.d_wcell_start,
                    (const V4<CT> *)(y_fluid ? s.d_A : s.d_Aw), y_fluid ? s.d_perm_f : s.d_perm_w, r2,
-                   (long long)capacity, d_oi, d_oj, d_counter, cap, list_len);
+                   (long long)capacity, d_oi, d_oj, d_counter, cap, list_len,
+                   (const V4<float> *)(y_fluid ? s.d_Ff : s.d_Fw));
         } else if (n_x > 0)
             LAUNCH(s, (k_pairs<ND, T, CT>), cdiv(n_x, 128), 128, 0, n_x,
                    (x_fluid ? s.d_fcell_start : s.d_wcell_start) + s.ncells, g,
@@ -753,7 +761,7 @@ static void free_device(Semi &s)
     void *ptrs[] = {s.d_mass_f, s.d_u, s.d_v, s.d_dv, s.d_du, s.d_key, s.d_slot, s.d_tmp_perm,
                     s.d_perm_f, s.d_count, s.d_fcell_start, s.d_wcell_start, s.d_block_sums,
                     s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_perm_w,
-                    s.d_scratch};
+                    s.d_scratch, s.d_Ff, s.d_Fw};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     tiles_free(s.tiles);
@@ -963,6 +971,16 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
         }
         s->ncells *= s->ncell[d];
     }
+    // Float32 filter copy of Float64 positions (FilterRef): reference point = lower corner of
+    // the bounding box, pad = 2 x the worst-case distance error 2 sqrt(3) 2^-24 L
+    {
+        double extent = 0;
+        for (int d = 0; d < nd; ++d) {
+            s->filter_ref[d] = lo[d];
+            extent = std::max(extent, hi[d] - lo[d]);
+        }
+        s->filter_pad = (float)(4.0 * std::sqrt(3.0) * std::ldexp(1.0, -24) * extent * 1.01);
+    }
     // Rows (the fastest cell index; one row = one contiguous run of sorted records, the unit the
     // tile sweeps stage and split into tiles) run along the longest side of the bounding box: long
     // rows give full tiles and little staging overhead, and a slab of a decomposed domain is
@@ -1030,6 +1048,10 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     CUDA_TRY(s, cudaMalloc(&s->d_Ww, 2 * ts * (nw + 8)));
     CUDA_TRY(s, cudaMalloc(&s->d_volw, ts * (nw + 8)));
     CUDA_TRY(s, cudaMalloc(&s->d_scratch, sizeof(double) * nmax));
+    if (s->cfg.eltype == TPB_F32 && s->cfg.coords_eltype == TPB_F64) {
+        CUDA_TRY(s, cudaMalloc(&s->d_Ff, sizeof(float) * 4 * nf));
+        CUDA_TRY(s, cudaMalloc(&s->d_Fw, sizeof(float) * 4 * nw));
+    }
     CUDA_TRY(s, cudaMemset(s->d_A, 0, 4 * cs * (nf + 8)));
     CUDA_TRY(s, cudaMemset(s->d_B, 0, 4 * ts * (nf + 8)));
     CUDA_TRY(s, cudaMemset(s->d_P, 0, ts * (nf + 8)));

@@ -376,6 +376,28 @@ __device__ __forceinline__ void interact_pair_fast(const FastConst &c, const V4<
 // linear with x fastest, so the 2 sx + 1 cells {cx - sx .. cx + sx} of one (y, z) row are one
 // contiguous run of sorted particles, and the finer x resolution lets a sweep clip that run to
 // the chord of the search sphere in that row (tpb_tiles.cuh).
+// Float32 fields with Float64 coordinates: the phase-1 filter of the tile sweeps works on a
+// Float32 copy of the positions relative to a fixed reference point (the lower corner of the
+// bounding box), F = fl32(x - ref).  |F - (x - ref)| <= 2^-24 L per coordinate (L = largest
+// extent of the box), so a distance computed from two F's is within 2 sqrt(3) 2^-24 L of the
+// true one; `pad` is twice that.  The exact predicate and the pair physics still use the
+// Float64 difference (phase 2).
+template <typename CT>
+struct FilterRef {
+    CT ref[3];   // reference point, coordinate order
+    float pad;   // added to the search radius of the filter
+};
+template <typename CT>
+__device__ __forceinline__ V4<float> filter_position(const FilterRef<CT> &r, const V4<CT> &x)
+{
+    V4<float> f;
+    f.x = (float)(x.x - r.ref[0]);
+    f.y = (float)(x.y - r.ref[1]);
+    f.z = (float)(x.z - r.ref[2]);
+    f.w = 0.0f;
+    return f;
+}
+
 template <typename CT>
 struct GridConst {
     CT origin[3];
@@ -387,6 +409,7 @@ struct GridConst {
     int n[3];
     int ncells;
     int sx;         // x-split factor
+    FilterRef<CT> fref;  // Float32 filter copy of Float64 positions (tile sweeps)
     int ax;         // coordinate axis of the rows (fastest cell index); every per-axis field above is
                     // stored with the entries 0 and ax swapped ("cell-axis order")
 };

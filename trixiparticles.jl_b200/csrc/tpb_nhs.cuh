@@ -168,7 +168,7 @@ k_reorder_fluid(const CT *__restrict__ u, const T *__restrict__ v, const T *__re
                 const int *__restrict__ key, const int *__restrict__ cell_start,
                 const int *__restrict__ tmp_perm, int n, const int *__restrict__ n_sorted,
                 int deterministic, EosConst<T> eos, V4<CT> *__restrict__ A, V4<T> *__restrict__ B,
-                T *__restrict__ P, int *__restrict__ perm)
+                T *__restrict__ P, int *__restrict__ perm, FilterRef<CT> fref, V4<float> *__restrict__ F)
 {
     constexpr int NV = DENS == 0 ? ND + 1 : ND;
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,6 +199,7 @@ k_reorder_fluid(const CT *__restrict__ u, const T *__restrict__ v, const T *__re
     A[dst] = ra;
     B[dst] = rb;
     perm[dst] = i;
+    if (F) F[dst] = filter_position<CT>(fref, ra);
 }
 
 // ------------------------------------------------------------------ wall reorder (once)
@@ -207,7 +208,8 @@ __global__ void __launch_bounds__(256)
 k_reorder_wall(const CT *__restrict__ coords, const T *__restrict__ mass,
                const T *__restrict__ density0, const int *__restrict__ key,
                const int *__restrict__ cell_start, const int *__restrict__ tmp_perm, int n,
-               V4<CT> *__restrict__ A, V2<T> *__restrict__ W, int *__restrict__ perm)
+               V4<CT> *__restrict__ A, V2<T> *__restrict__ W, int *__restrict__ perm, FilterRef<CT> fref,
+               V4<float> *__restrict__ F)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -221,6 +223,7 @@ k_reorder_wall(const CT *__restrict__ coords, const T *__restrict__ mass,
     ra.z = ND == 3 ? coords[(int64_t)i * ND + 2] : (CT)0;
     ra.w = (CT)mass[i];
     A[dst] = ra;
+    if (F) F[dst] = filter_position<CT>(fref, ra);
     V2<T> w;
     w.x = (T)0;          // pressure (initial_boundary_pressure: zero for Adami)
     w.y = density0[i];   // cache.density = copy(initial_density) (dummy_particles.jl:290-297)

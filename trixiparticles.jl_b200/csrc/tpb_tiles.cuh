@@ -261,6 +261,7 @@ struct TileSmem {
     V4<CT> *tA;            // [cap]
     unsigned char *tB;     // [cap] of V4<T> (fluid neighbours) or V2<T> (wall neighbours)
     T *tP;                 // [cap]
+    V4<float> *tF;         // [cap] Float32 filter positions (tile_has_filter_copy)
     int cap, list_len;
     __device__ TileSmem(unsigned char *base, int cap_, int list_len_, int nt) : cap(cap_), list_len(list_len_)
     {
@@ -273,19 +274,28 @@ struct TileSmem {
         tB = p;
         p += (size_t)cap * sizeof(V4<T>);
         tP = (T *)p;
+        p += (size_t)cap * sizeof(T);
+        tF = (V4<float> *)p;  // cap is a multiple of 4: 16-byte aligned
     }
 };
+// Float32 fields with Float64 coordinates: a Float32 copy of the positions for the phase-1 filter
+template <typename T, typename CT>
+__host__ __device__ constexpr bool tile_has_filter_copy()
+{
+    return std::is_same<T, float>::value && !std::is_same<CT, float>::value;
+}
 // bytes per staged record
 template <typename T, typename CT>
-constexpr size_t tile_record_bytes()
+__host__ __device__ constexpr size_t tile_record_bytes()
 {
-    return sizeof(V4<CT>) + sizeof(V4<T>) + sizeof(T);
+    return sizeof(V4<CT>) + sizeof(V4<T>) + sizeof(T) + (tile_has_filter_copy<T, CT>() ? sizeof(V4<float>) : 0);
 }
 template <typename T, typename CT>
 inline size_t tile_smem_bytes(int cap, int list_len, int ks = 1)
 {
+    // + 64: the last partial group of a candidate window reads up to three records past it
     return TILE_HDR_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short) +
-           (size_t)cap * tile_record_bytes<T, CT>();
+           (size_t)cap * tile_record_bytes<T, CT>() + 64;
 }
 
 // Load the tile descriptor of this block into hdr (thread 0).
@@ -378,6 +388,7 @@ struct NbSet {
     const V4<CT> *__restrict__ A;
     const R1 *__restrict__ B;
     const T *__restrict__ P;
+    const V4<float> *__restrict__ F;  // filter copy of A (tile_has_filter_copy), else unused
 };
 
 // Stage the neighbour rows of a sweep (warp 0 only, all 32 lanes; the staging area must be
@@ -390,7 +401,9 @@ __device__ __forceinline__ void tile_stage(TileSmem<T, CT> &sm, const NB &nb, co
 {
     using R1 = typename NB::R1;
     constexpr int NROWS = ND == 3 ? 9 : 3;
-    constexpr uint32_t REC_BYTES = sizeof(V4<CT>) + sizeof(R1) + (NB::HAS_P ? sizeof(T) : 0);
+    constexpr bool HAS_F = tile_has_filter_copy<T, CT>();
+    constexpr uint32_t REC_BYTES = sizeof(V4<CT>) + sizeof(R1) + (NB::HAS_P ? sizeof(T) : 0) +
+                                   (HAS_F ? sizeof(V4<float>) : 0);
     const int tid = threadIdx.x;
     TileHdr *hdr = sm.hdr;
     R1 *tB = (R1 *)sm.tB;
@@ -450,6 +463,7 @@ __device__ __forceinline__ void tile_stage(TileSmem<T, CT> &sm, const NB &nb, co
             bulk_g2s(sm.tA + used, nb.A + a, (uint32_t)(len * sizeof(V4<CT>)), sm.bar);
             bulk_g2s(tB + used, nb.B + a, (uint32_t)(len * sizeof(R1)), sm.bar);
             if constexpr (NB::HAS_P) bulk_g2s(sm.tP + used, nb.P + a, (uint32_t)(len * sizeof(T)), sm.bar);
+            if constexpr (HAS_F) bulk_g2s(sm.tF + used, nb.F + a, (uint32_t)(len * sizeof(V4<float>)), sm.bar);
         }
     } else if (tid == 0) {
         hdr->nseg = 0;
@@ -478,12 +492,27 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
     using R1 = typename NB::R1;
     constexpr int NROWS = ND == 3 ? 9 : 3;
     constexpr int NT = KS * TILE_TB;  // threads per block
-    constexpr uint32_t REC_BYTES = sizeof(V4<CT>) + sizeof(R1) + (NB::HAS_P ? sizeof(T) : 0);
+    constexpr bool HAS_F = tile_has_filter_copy<T, CT>();
+    constexpr uint32_t REC_BYTES = sizeof(V4<CT>) + sizeof(R1) + (NB::HAS_P ? sizeof(T) : 0) +
+                                   (HAS_F ? sizeof(V4<float>) : 0);
     const int tid = threadIdx.x;
     const int kg = KS > 1 ? tid / TILE_TB : 0;  // warp-uniform
     TileHdr *hdr = sm.hdr;
     R1 *tB = (R1 *)sm.tB;
     const Filter<ND, T, CT> filter(radius2);
+    // phase-1 records: the Float32 filter copy (padded radius) or the positions themselves
+    using FRec = typename std::conditional<HAS_F, V4<float>, V4<CT>>::type;
+    const FRec *const tFilt = HAS_F ? (const FRec *)sm.tF : (const FRec *)sm.tA;
+    const float rf = HAS_F ? sqrtf((float)radius2) + g.fref.pad : 0.0f;
+    const Filter<ND, float, float> ffilter(rf * rf);
+    V4<float> xf = {};
+    if constexpr (HAS_F) xf = filter_position<CT>(g.fref, xi);
+    auto pass = [&](const FRec &c) {
+        if constexpr (HAS_F)
+            return ffilter(xf, c);
+        else
+            return filter(xi, c);
+    };
     bool staged = hdr->nseg > 0;
     if (!staged && hdr->last) return;
     // chunked mode: thread 0 is about to rewrite the header every thread has just read
@@ -550,6 +579,8 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
                     bulk_g2s(sm.tA + used, nb.A + a, (uint32_t)(len * sizeof(V4<CT>)), sm.bar);
                     bulk_g2s(tB + used, nb.B + a, (uint32_t)(len * sizeof(R1)), sm.bar);
                     if constexpr (NB::HAS_P) bulk_g2s(sm.tP + used, nb.P + a, (uint32_t)(len * sizeof(T)), sm.bar);
+                    if constexpr (HAS_F)
+                        bulk_g2s(sm.tF + used, nb.F + a, (uint32_t)(len * sizeof(V4<float>)), sm.bar);
                     bytes += (uint32_t)len * REC_BYTES;
                     used += len;
                     ++nseg;
@@ -606,28 +637,27 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
             while (true) {
                 // phase 1: filter candidates into the private list
                 while (t + STEP + 4 <= t1 && room(8)) {
-                    V4<CT> xc[8];
+                    FRec xc[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) xc[u] = sm.tA[t + u];
+                    for (int u = 0; u < 4; ++u) xc[u] = tFilt[t + u];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) xc[4 + u] = sm.tA[t + STEP + u];
+                    for (int u = 0; u < 4; ++u) xc[4 + u] = tFilt[t + STEP + u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) lpa = list_append<ESTEP>(lpa, (uint32_t)(t + u), pass(xc[u]));
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + u), filter(xi, xc[u]));
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + STEP + u), filter(xi, xc[4 + u]));
+                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + STEP + u), pass(xc[4 + u]));
                     t += 2 * STEP;
                 }
                 while (t < t1 && room(4)) {
                     // one group, the last one possibly partial (records past t1 are staged
                     // neighbours of other lanes or padding: read, never appended)
-                    V4<CT> xc[4];
+                    FRec xc[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) xc[u] = sm.tA[t + u];
+                    for (int u = 0; u < 4; ++u) xc[u] = tFilt[t + u];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + u), t + u < t1 && filter(xi, xc[u]));
+                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + u), t + u < t1 && pass(xc[u]));
                     t += STEP;
                 }
                 if (!__any_sync(0xffffffffu, t < t1)) break;
@@ -719,7 +749,8 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
                  const int *__restrict__ perm, int ff_enabled, int has_wall,
                  const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
                  const V2<T> *__restrict__ Ww, PairConst<T> k, SourceConst<T> src,
-                 T *__restrict__ dv, int n_targets, int cap, int list_len)
+                 T *__restrict__ dv, int n_targets, int cap, int list_len,
+                 const V4<float> *__restrict__ Ff, const V4<float> *__restrict__ Fw)
 {
     constexpr int NV = DENS == 0 ? ND + 1 : ND;
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
@@ -727,7 +758,7 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     if (tile >= *n_tiles) return;
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
     const int2 *rng = tile_rng + (int64_t)tile * 18;
-    const NbSet<T, CT, V4<T>, true> nb_f{fcell_start, A, B, P};
+    const NbSet<T, CT, V4<T>, true> nb_f{fcell_start, A, B, P, Ff};
     // every thread reads the descriptor itself (one broadcast transaction) and starts loading its
     // own particle while warp 0 is staging; the barrier below also publishes the header
     const int4 desc = tile_desc[tile];
@@ -807,7 +838,7 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     T &drho_fw = acc[7];
     if (has_wall && any_fw) {
         const T zero3[3] = {0, 0, 0};
-        NbSet<T, CT, V2<T>, false> nb{wcell_start, Aw, Ww, nullptr};
+        NbSet<T, CT, V2<T>, false> nb{wcell_start, Aw, Ww, nullptr, Fw};
         tile_sweep<KS, ND, T, CT>(sm, g, nb, rng + 9, valid, cx, xi, k.radius2, parity,
                               [&](const V4<CT> &xj, const V2<T> &wj, T) {
                                   if constexpr (FAST) {
@@ -923,7 +954,8 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
               const int2 *__restrict__ tile_rng, const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
               const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
               const V4<T> *__restrict__ B, const T *__restrict__ P, int interaction_enabled,
-              AdamiConst<T> k, V2<T> *__restrict__ W, T *__restrict__ volume, int cap, int list_len)
+              AdamiConst<T> k, V2<T> *__restrict__ W, T *__restrict__ volume, int cap, int list_len,
+              const V4<float> *__restrict__ Ff)
 {
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     const int n_act = *n_active;
@@ -931,7 +963,7 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
     if (threadIdx.x == 0) mbar_init(sm.bar, 1);
     uint32_t parity = 0;
-    const NbSet<T, CT, V4<T>, true> nb{fcell_start, A, B, P};
+    const NbSet<T, CT, V4<T>, true> nb{fcell_start, A, B, P, Ff};
     for (int it = blockIdx.x; it < n_act; it += gridDim.x) {
         // the previous tile is done with the staged records, the header and the reduction slots
         __syncthreads();
@@ -1009,7 +1041,8 @@ k_pairs_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__re
               const V4<CT> *__restrict__ X, const int *__restrict__ perm_x,
               const int *__restrict__ ycell_start, const V4<CT> *__restrict__ Y,
               const int *__restrict__ perm_y, T radius2, long long capacity, int *__restrict__ out_i,
-              int *__restrict__ out_j, unsigned long long *__restrict__ counter, int cap, int list_len)
+              int *__restrict__ out_j, unsigned long long *__restrict__ counter, int cap, int list_len,
+              const V4<float> *__restrict__ Fy)
 {
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     const int tile = blockIdx.x;
@@ -1030,7 +1063,7 @@ k_pairs_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__re
         cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
     }
     uint32_t parity = 0;
-    NbSet<T, CT, int, false> nb{ycell_start, Y, perm_y, nullptr};
+    NbSet<T, CT, int, false> nb{ycell_start, Y, perm_y, nullptr, Fy};
     tile_sweep<KS, ND, T, CT>(sm, g, nb, tile_rng + (int64_t)tile * 9, valid, cx, xi, radius2, parity, [&](const V4<CT> &xj, const int &pj, T) {
         T pd[3];
         if (pos_diff_d2<ND, T, CT>(xi, xj, pd) <= radius2) {
@@ -1146,7 +1179,7 @@ inline void tiles_free(TileState &t)
 template <typename T, typename CT>
 inline int tile_capacity(int smem_budget, int list_len, int ks = 1)
 {
-    const size_t fixed = TILE_HDR_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short);
+    const size_t fixed = TILE_HDR_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short) + 64;
     const size_t rec = tile_record_bytes<T, CT>();
     int cap = (size_t)smem_budget > fixed ? (int)(((size_t)smem_budget - fixed) / rec) : 0;
     cap &= ~3;
