@@ -77,7 +77,7 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
-def make_workload(name, eltype=None, coords=None):
+def make_workload(name, eltype=None, coords=None, shuffle=False):
     from trixiparticles.jl_b200 import examples
     ex, arg = WORKLOADS[name]
     dt = {None: None, "f32": np.float32, "f64": np.float64}
@@ -91,6 +91,13 @@ def make_workload(name, eltype=None, coords=None):
     else:
         fluid, wall, _ = examples.dam_break_2d(arg, **kw)
     ic = fluid.initial_condition
+    if shuffle:
+        # random particle <-> ODE index map: what the reference's SortingCallback exists to undo
+        # (callbacks/sorting.jl:17-19 quotes a 3-4x penalty for unsorted particles on its GPU path)
+        perm = np.random.default_rng(1234).permutation(fluid.nparticles)
+        for name_ in ("coordinates", "velocity", "mass", "density", "pressure"):
+            setattr(ic, name_, np.ascontiguousarray(getattr(ic, name_)[perm]))
+        fluid.mass = np.ascontiguousarray(fluid.mass[perm])
     u = np.ascontiguousarray(ic.coordinates, dtype=fluid.coordinates_eltype)
     v = np.ascontiguousarray(np.concatenate([ic.velocity, ic.density[:, None]], axis=1), dtype=fluid.eltype)
     return fluid, wall, u, v
@@ -220,7 +227,7 @@ def run_single(args):
     _lib.load()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    fluid, wall, u, v = make_workload(args.workload, args.eltype, args.coords)
+    fluid, wall, u, v = make_workload(args.workload, args.eltype, args.coords, args.shuffle)
     nd, n_f, n_w = fluid.ndims, fluid.nparticles, wall.nparticles
     tsize, csize = np.dtype(fluid.eltype).itemsize, np.dtype(fluid.coordinates_eltype).itemsize
     if args.e2e_only:
@@ -462,6 +469,7 @@ def main():
     ap.add_argument("--coords", default=None, choices=["f32", "f64"], help="coordinates_eltype (default: eltype)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the other precision set-ups")
+    ap.add_argument("--shuffle", action="store_true", help="random particle order in the ODE vectors")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
     ap.add_argument("--e2e-only", action="store_true", help="host-pointer (e2e) timing only (tuning runs)")
     args = ap.parse_args()
