@@ -49,6 +49,10 @@ extern "C" {
 #define TPB_MEM_DEVICE 1
 
 /* smoothing kernels (src/general/smoothing_kernels.jl:191-227, :434-455) */
+#define TPB_VISCOSITY_NONE 0
+#define TPB_VISCOSITY_MONAGHAN 1
+#define TPB_VISCOSITY_MORRIS 2 /* viscosity.jl:134-205 */
+#define TPB_VISCOSITY_ADAMI 3  /* viscosity.jl:207-285 */
 #define TPB_KERNEL_WENDLAND_C2 0
 #define TPB_KERNEL_SCHOENBERG_CUBIC 1
 #define TPB_KERNEL_WENDLAND_C4 2 /* smoothing_kernels.jl:489-514 */
@@ -89,11 +93,13 @@ typedef struct {
     int32_t kernel;                 /* TPB_KERNEL_* */
     int32_t density_calculator;     /* TPB_DENSITY_* */
     int32_t clip_negative_pressure; /* StateEquationCole CLIP */
-    int32_t has_viscosity;          /* ArtificialViscosityMonaghan | nothing */
+    int32_t has_viscosity;          /* TPB_VISCOSITY_*: nothing | ArtificialViscosityMonaghan |
+                                     * ViscosityMorris | ViscosityAdami (viscosity.jl:68-279) */
     int32_t has_diffusion;          /* DensityDiffusionMolteniColagrossi | nothing */
     double smoothing_length;
     double sound_speed, exponent, reference_density, background_pressure; /* StateEquationCole */
-    double alpha, beta, epsilon;    /* viscosity.jl:68-76 */
+    double alpha, beta, epsilon;    /* Monaghan: alpha, beta, epsilon (viscosity.jl:68-76);
+                                     * Morris / Adami: alpha = kinematic viscosity nu, epsilon */
     double delta;                   /* density_diffusion.jl:41-47 */
     double acceleration[3];         /* system.acceleration */
     double damping_coefficient;     /* SourceTermDamping (semidiscretization.jl:795-807); 0 = none */

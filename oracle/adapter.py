@@ -17,7 +17,7 @@ def fluid_params(fluid) -> O.FluidParams:
     p.kernel = fluid.smoothing_kernel.kernel_id
     p.density_calculator = fluid.density_calculator.density_id
     p.clip_negative_pressure = int(se.clip_negative_pressure)
-    p.has_viscosity = int(fluid.viscosity is not None)
+    p.has_viscosity = 0 if fluid.viscosity is None else int(getattr(fluid.viscosity, "viscosity_id", 1))
     p.has_diffusion = int(fluid.density_diffusion is not None)
     p.smoothing_length = float(t(fluid.smoothing_length))
     p.sound_speed = float(t(se.sound_speed))
@@ -25,8 +25,12 @@ def fluid_params(fluid) -> O.FluidParams:
     p.reference_density = float(t(se.reference_density))
     p.background_pressure = float(t(se.background_pressure))
     if fluid.viscosity is not None:
-        p.alpha = float(t(fluid.viscosity.alpha))
-        p.beta = float(t(fluid.viscosity.beta))
+        if p.has_viscosity == 1:
+            p.alpha = float(t(fluid.viscosity.alpha))
+            p.beta = float(t(fluid.viscosity.beta))
+        else:
+            p.alpha = float(t(fluid.viscosity.nu))
+            p.beta = 0.0
         p.epsilon = float(t(fluid.viscosity.epsilon))
     if fluid.density_diffusion is not None:
         p.delta = float(t(fluid.density_diffusion.delta))

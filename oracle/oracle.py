@@ -88,6 +88,8 @@ def _declare(L):
         f = getattr(L, f"orc_inverse_eos_{s}"); f.restype = d; f.argtypes = [d, d, d, d, d]
         f = getattr(L, f"orc_viscosity_pair_{s}"); f.restype = None
         f.argtypes = [i, i, d, d, d, d, d, d, d, d, p, p, p]
+        f = getattr(L, f"orc_viscosity_pair_nu_{s}"); f.restype = None
+        f.argtypes = [i, i, i, d, d, d, d, d, d, d, p, p, p]
         f = getattr(L, f"orc_interact_pair_{s}"); f.restype = None
         f.argtypes = [C.POINTER(FluidParams), i, d, d, d, d, d, p, p, p, p, p]
         for name in ("orc_pairs_bruteforce", "orc_pairs_grid"):
@@ -143,6 +145,16 @@ def viscosity_pair(kernel_id, ndims, h, alpha, beta, epsilon, c, m_b, rho_a, rho
     getattr(lib(), f"orc_viscosity_pair_{suffix(dtype)}")(
         kernel_id, ndims, float(h), float(alpha), float(beta), float(epsilon), float(c),
         float(m_b), float(rho_a), float(rho_b), _ptr(vd), _ptr(pd), _ptr(out))
+    return out[:ndims]
+
+
+def viscosity_pair_nu(model, kernel_id, ndims, h, nu, epsilon, m_a, m_b, rho_a, rho_b, v_diff, pos_diff,
+                      dtype=np.float64):
+    """ViscosityMorris (model 2) / ViscosityAdami (model 3) functor on one pair."""
+    vd, pd, out = _vec3(v_diff), _vec3(pos_diff), np.zeros(3)
+    getattr(lib(), f"orc_viscosity_pair_nu_{suffix(dtype)}")(
+        int(model), kernel_id, ndims, float(h), float(nu), float(epsilon), float(m_a), float(m_b),
+        float(rho_a), float(rho_b), _ptr(vd), _ptr(pd), _ptr(out))
     return out[:ndims]
 
 

@@ -32,6 +32,8 @@
 extern "C" {
 #endif
 
+/* `has_viscosity` selects the model; Morris / Adami carry their kinematic viscosity nu in `alpha` */
+enum { ORC_VISCOSITY_NONE = 0, ORC_VISCOSITY_MONAGHAN = 1, ORC_VISCOSITY_MORRIS = 2, ORC_VISCOSITY_ADAMI = 3 };
 enum { ORC_KERNEL_WENDLAND_C2 = 0, ORC_KERNEL_SCHOENBERG_CUBIC = 1, ORC_KERNEL_WENDLAND_C4 = 2,
        ORC_KERNEL_WENDLAND_C6 = 3 };
 enum { ORC_DENSITY_CONTINUITY = 0, ORC_DENSITY_SUMMATION = 1 };
@@ -78,6 +80,10 @@ typedef struct {
                                   double m_b, double rho_a, double rho_b,                    \
                                   const double *v_diff, const double *pos_diff,              \
                                   double *dv_out);                                           \
+    void orc_viscosity_pair_nu_##SUF(int model, int kernel, int ndims, double h, double nu,  \
+                                     double epsilon, double m_a, double m_b, double rho_a,   \
+                                     double rho_b, const double *v_diff,                     \
+                                     const double *pos_diff, double *dv_out);                \
     void orc_interact_pair_##SUF(const orc_fluid_params *fp, int neighbor_is_wall,           \
                                  double m_b, double rho_a, double rho_b, double p_a,         \
                                  double p_b, const double *v_a, const double *v_b,           \

@@ -206,6 +206,31 @@ def test_kick_wendland_c4_c6(oracle, kernel_cls, config):
     check_against_oracle(fluid, wall, u, v)
 
 
+@pytest.mark.parametrize("viscosity_cls", ["ViscosityMorris", "ViscosityAdami"])
+@pytest.mark.parametrize("config", ["hydrostatic_2d_f32", "dam_break_2d_f64", "dam_break_3d_f32",
+                                    "dam_break_3d_f32_f64_coordinates"])
+def test_kick_viscosity_morris_adami(oracle, viscosity_cls, config):
+    """`ViscosityMorris` / `ViscosityAdami` between the fluid particles (viscosity.jl:134-285; the
+    "WCSPH with ViscosityAdami / ViscosityMorris" rows of test/examples/gpu.jl:349-362); the wall
+    model has no viscosity (free slip), as in those tests."""
+    if config == "hydrostatic_2d_f32":
+        fluid, wall, _ = examples.hydrostatic_water_column_2d()
+        nu = 0.0015                                    # gpu.jl: 0.02 * 10.0 * 1.2 * 0.05 / 8
+    elif config == "dam_break_2d_f64":
+        fluid, wall, _ = examples.dam_break_2d(20)
+        nu = 0.01
+    elif config == "dam_break_3d_f32":
+        fluid, wall, _ = examples.dam_break_3d(0.1)
+        nu = 0.01
+    else:
+        fluid, wall, _ = examples.dam_break_3d(0.1, coordinates_eltype=np.float64)
+        nu = 0.01
+    fluid.viscosity = getattr(tp, viscosity_cls)(nu=nu)
+    u, v = examples.perturbed_state(fluid)
+    check_against_oracle(fluid, wall, u, v)
+    check_against_oracle(fluid, wall, u, v, interact_variant=1)
+
+
 @pytest.mark.parametrize("example", ["dam_break_2d", "hydrostatic_2d"])
 def test_kick_summation_density(oracle, example):
     """SummationDensity variant (density_calculators.jl:26-50; dam_break_2d variant in

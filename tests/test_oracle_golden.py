@@ -20,6 +20,20 @@ def test_monaghan_viscosity_known_answer(oracle):
     assert dv[1] == pytest.approx(0.03073826434949052, abs=6e-15)
 
 
+# test/schemes/fluid/viscosity.jl:43-105: the same pair through ViscosityMorris / ViscosityAdami
+@pytest.mark.parametrize("model,expected", [
+    (2, (-1.0895602048035404e-5, 3.631867349345135e-5)),      # ViscosityMorris(nu=7e-3)
+    (3, (-1.089560204803541e-5, 3.6318673493451364e-5)),      # ViscosityAdami(nu=7e-3)
+])
+def test_morris_adami_viscosity_known_answers(oracle, model, expected):
+    particle_spacing = 0.2
+    h = 1.2 * particle_spacing
+    dv = oracle.viscosity_pair_nu(model, CUBIC, 2, h, 7e-3, 0.01, 0.01, 0.01, 1000.0, 1000.0,
+                                  [0.3, -1.0], [-0.25 * h, 0.375 * h])
+    assert dv[0] == pytest.approx(expected[0], abs=6e-15)
+    assert dv[1] == pytest.approx(expected[1], abs=6e-15)
+
+
 # test/schemes/fluid/weakly_compressible_sph/state_equation.jl:24-38, :85-98 (exact `==`)
 @pytest.mark.parametrize("gamma,expected", [
     (7.15, [998.34, 1002.8323123356663, 1019.8235062499685, 1038.8747989986027,

@@ -9,7 +9,8 @@ directory maps the dotted name onto this folder).
 from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
                     BoundaryModelDummyParticles, ContinuityDensity,
                     DensityDiffusionMolteniColagrossi, SchoenbergCubicSplineKernel,
-                    SourceTermDamping, StateEquationCole, SummationDensity, WallBoundarySystem,
+                    SourceTermDamping, StateEquationCole, SummationDensity, ViscosityAdami, ViscosityMorris,
+                    WallBoundarySystem,
                     WeaklyCompressibleSPHSystem, WendlandC2Kernel, WendlandC4Kernel, WendlandC6Kernel,
                     compact_support)
 from .semidiscretization import (B200Backend, DynamicalODEProblem, FullGridCellList,
@@ -21,7 +22,8 @@ from .setups import InitialCondition, RectangularShape, RectangularTank, union
 __all__ = [
     "AdamiPressureExtrapolation", "ArtificialViscosityMonaghan", "BoundaryModelDummyParticles",
     "ContinuityDensity", "DensityDiffusionMolteniColagrossi", "SchoenbergCubicSplineKernel",
-    "SourceTermDamping", "StateEquationCole", "SummationDensity", "WallBoundarySystem",
+    "SourceTermDamping", "StateEquationCole", "SummationDensity", "ViscosityAdami", "ViscosityMorris",
+    "WallBoundarySystem",
     "WeaklyCompressibleSPHSystem", "WendlandC2Kernel", "WendlandC4Kernel", "WendlandC6Kernel",
     "compact_support", "B200Backend",
     "DynamicalODEProblem", "FullGridCellList", "GridNeighborhoodSearch", "Semidiscretization",

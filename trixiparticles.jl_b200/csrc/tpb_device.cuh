@@ -189,12 +189,12 @@ template <typename T>
 struct PairConst {
     KernelConst<T> kern;
     T c;                  // sound speed
-    T alpha, beta, eps;   // ArtificialViscosityMonaghan
+    T alpha, beta, eps;   // ArtificialViscosityMonaghan; ViscosityMorris / ViscosityAdami: alpha = nu
     T eps_h2;             // epsilon * h^2
     T delta_h_c;          // delta * h_avg * c      (density_diffusion.jl:236-239)
     T almostzero;         // sqrt(eps(compact_support^2)) (rhs.jl:27-28)
     T radius2;            // search_radius^2
-    int has_viscosity, has_diffusion;
+    int has_viscosity, has_diffusion;  // has_viscosity: TPB_VISCOSITY_* (0 none, 1 Monaghan, 2 Morris, 3 Adami)
 };
 
 // SAME: particle_system === neighbor_system (fluid-fluid); otherwise the neighbour is a
@@ -203,7 +203,7 @@ template <int ND, typename T, int KERNEL, int DENS, bool SAME>
 __device__ __forceinline__ void interact_pair(const PairConst<T> &k, T m_b, T rho_a, T rho_b,
                                               T p_a, T p_b, const T (&v_a)[3],
                                               const T (&v_b)[3], const T (&pd)[3], T dist,
-                                              T (&dv)[3], T &drho)
+                                              T (&dv)[3], T &drho, T m_a = (T)0)
 {
     const T wdr = SmoothingKernel<KERNEL, T>::dw_div_r(k.kern, dist);
     T grad[3];
@@ -224,7 +224,28 @@ __device__ __forceinline__ void interact_pair(const PairConst<T> &k, T m_b, T rh
     for (int d = 0; d < ND; ++d) vd[d] = SAME ? v_a[d] - v_b[d] : v_a[d];
 
     // ArtificialViscosityMonaghan (viscosity.jl:89-132)
-    if (SAME && k.has_viscosity) {
+    if (SAME && k.has_viscosity >= 2) {
+        // ViscosityMorris (viscosity.jl:163-205) / ViscosityAdami (:222-279); nu_a = nu_b = nu
+        const T nu = k.alpha;
+        const T d2e = dist * dist + k.eps_h2;
+        T coef;
+        if (k.has_viscosity == 2) {
+            T pg = pd[0] * grad[0] + pd[1] * grad[1];
+            if (ND == 3) pg += pd[2] * grad[2];
+            const T mu_a = nu * rho_a, mu_b = nu * rho_b;
+            coef = div_fast(m_b * (mu_a + mu_b) * pg, rho_a * rho_b * d2e);
+        } else {
+            T gp = grad[0] * pd[0] + grad[1] * pd[1];
+            if (ND == 3) gp += grad[2] * pd[2];
+            const T eta_a = nu * rho_a, eta_b = nu * rho_b;
+            const T volume_a = div_fast(m_a, rho_a), volume_b = div_fast(m_b, rho_b);
+            const T tmp = div_fast((T)2 * eta_a * eta_b, (eta_a + eta_b) * d2e * m_a);
+            coef = (volume_a * volume_a + volume_b * volume_b) * gp * tmp;
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) dv[d] += coef * vd[d];
+    }
+    if (SAME && k.has_viscosity == 1) {
         T vr = vd[0] * pd[0] + vd[1] * pd[1];
         if (ND == 3) vr += vd[2] * pd[2];
         if (vr < (T)0) {
@@ -282,6 +303,8 @@ struct FastConst {
     int order;             // Wendland C4 / C6
     float h, eps_h2;       // viscosity
     float ac2, b2;         // 2 alpha c, 2 beta
+    float nu;              // ViscosityMorris / ViscosityAdami
+    int visc;              // TPB_VISCOSITY_*
     float dhc2;            // 2 delta h c (0 without density diffusion)
 };
 
@@ -298,8 +321,10 @@ __host__ __device__ inline FastConst make_fast_const(const PairConst<float> &k)
     f.order = k.kern.order;
     f.h = k.kern.h;
     f.eps_h2 = k.eps_h2;
-    f.ac2 = k.has_viscosity ? 2.0f * k.alpha * k.c : 0.0f;
-    f.b2 = k.has_viscosity ? 2.0f * k.beta : 0.0f;
+    f.ac2 = k.has_viscosity == 1 ? 2.0f * k.alpha * k.c : 0.0f;
+    f.b2 = k.has_viscosity == 1 ? 2.0f * k.beta : 0.0f;
+    f.nu = k.has_viscosity >= 2 ? k.alpha : 0.0f;
+    f.visc = k.has_viscosity;
     f.dhc2 = k.has_diffusion ? 2.0f * k.delta_h_c : 0.0f;
     return f;
 }
@@ -336,6 +361,7 @@ __device__ __forceinline__ void interact_pair_fast(const FastConst &c, const V4<
                                                    float vby, float vbz, float rho_b, float p_b,
                                                    float (&dv)[3], float &drho)
 {
+    // (the target's mass is xi.w)
     float pd[3];
     float d2 = pos_diff_d2<ND, float, CT>(xi, xj, pd);  // exactly rounded, as the reference
     const bool ok = d2 <= c.r2 && d2 >= c.az2;
@@ -343,7 +369,8 @@ __device__ __forceinline__ void interact_pair_fast(const FastConst &c, const V4<
     const float mb = ok ? (float)xj.w : 0.0f;
     const float rs = rsqrt_approx(d2);
     const float dist = d2 * rs;
-    const float mw = mb * fast_wdr<KERNEL>(c, dist, rs);
+    const float wdr = fast_wdr<KERNEL>(c, dist, rs);
+    const float mw = mb * wdr;
     const float rb = rcp_approx(rho_b);
     float f;
     if (DENS == 0)
@@ -357,6 +384,26 @@ __device__ __forceinline__ void interact_pair_fast(const FastConst &c, const V4<
     if (SAME && (c.ac2 != 0.0f || c.b2 != 0.0f)) {
         const float mu = (c.h * fminf(vr, 0.0f)) * rcp_approx(d2 + c.eps_h2);
         f = fmaf(fmaf(c.b2, mu, c.ac2) * mu, rcp_approx(rho_a + rho_b), f);
+    }
+    if (SAME && c.visc >= 2) {
+        // Morris: m_b nu (rho_a + rho_b) (pos_diff . grad W) / (rho_a rho_b (r^2 + eps h^2)),
+        // Adami:  (V_a^2 + V_b^2) (grad W . pos_diff) 2 nu rho_a rho_b / ((rho_a + rho_b)(r^2 + eps h^2) m_a);
+        // pos_diff . grad W = wdr r^2; a rejected pair has m_b = 0 (Morris) or wdr masked (Adami)
+        const float ra = rcp_approx(rho_a);
+        const float d2e = d2 + c.eps_h2;
+        float coef;
+        if (c.visc == 2) {
+            coef = (mw * d2) * (c.nu * (rho_a + rho_b)) * ((ra * rb) * rcp_approx(d2e));
+        } else {
+            const float m_a = (float)xi.w;
+            const float va = m_a * ra, vb = (float)xj.w * rb;
+            const float wm = ok ? wdr : 0.0f;
+            coef = fmaf(va, va, vb * vb) * (wm * d2) *
+                   ((2.0f * c.nu * rho_a * rho_b) * rcp_approx((rho_a + rho_b) * d2e * m_a));
+        }
+        dv[0] = fmaf(coef, vdx, dv[0]);
+        dv[1] = fmaf(coef, vdy, dv[1]);
+        if (ND == 3) dv[2] = fmaf(coef, vdz, dv[2]);
     }
     const float s = mw * f;
     dv[0] = fmaf(s, pd[0], dv[0]);

@@ -169,7 +169,7 @@ k_interact_pp(int n_f, GridConst<CT> g, const int *__restrict__ fcell_start,
                         const T v_b[3] = {bj.x, bj.y, bj.z};
                         interact_pair<ND, T, KERNEL, DENS, true>(k, (T)xj.w, rho_a, bj.w, p_a,
                                                                 P[j], v_a, v_b, pd, dist, dv_ff,
-                                                                drho_ff);
+                                                                drho_ff, (T)xi.w);
                     }
                 }
             }

@@ -829,7 +829,7 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
                                           const T v_b[3] = {bj.x, bj.y, bj.z};
                                           interact_pair<ND, T, KERNEL, DENS, true>(
                                               k, (T)xj.w, rho_a, bj.w, p_a, pj, v_a, v_b, pd, dist, dv_ff,
-                                              drho_ff);
+                                              drho_ff, (T)xi.w);
                                       }
                                   }
                               });

@@ -95,6 +95,22 @@ class ArtificialViscosityMonaghan:
 
 
 @dataclass(frozen=True)
+class ViscosityMorris:
+    """viscosity.jl:134-205 (kinematic viscosity `nu`)."""
+    nu: float
+    epsilon: float = 0.01
+    viscosity_id: int = 2
+
+
+@dataclass(frozen=True)
+class ViscosityAdami:
+    """viscosity.jl:207-285 (kinematic viscosity `nu`)."""
+    nu: float
+    epsilon: float = 0.01
+    viscosity_id: int = 3
+
+
+@dataclass(frozen=True)
 class DensityDiffusionMolteniColagrossi:
     delta: float
 

@@ -139,7 +139,7 @@ class Semidiscretization:
         p.kernel = f.smoothing_kernel.kernel_id
         p.density_calculator = f.density_calculator.density_id
         p.clip_negative_pressure = int(se.clip_negative_pressure)
-        p.has_viscosity = int(f.viscosity is not None)
+        p.has_viscosity = 0 if f.viscosity is None else int(getattr(f.viscosity, "viscosity_id", 1))
         p.has_diffusion = int(f.density_diffusion is not None)
         t = self.eltype.type
         p.smoothing_length = float(t(f.smoothing_length))
@@ -148,8 +148,11 @@ class Semidiscretization:
         p.reference_density = float(t(se.reference_density))
         p.background_pressure = float(t(se.background_pressure))
         if f.viscosity is not None:
-            p.alpha, p.beta, p.epsilon = (float(t(f.viscosity.alpha)), float(t(f.viscosity.beta)),
-                                          float(t(f.viscosity.epsilon)))
+            if p.has_viscosity == 1:
+                p.alpha, p.beta, p.epsilon = (float(t(f.viscosity.alpha)), float(t(f.viscosity.beta)),
+                                              float(t(f.viscosity.epsilon)))
+            else:  # ViscosityMorris / ViscosityAdami: the kinematic viscosity travels in `alpha`
+                p.alpha, p.beta, p.epsilon = float(t(f.viscosity.nu)), 0.0, float(t(f.viscosity.epsilon))
         if f.density_diffusion is not None:
             p.delta = float(t(f.density_diffusion.delta))
         for d in range(self.ndims):

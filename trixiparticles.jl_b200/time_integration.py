@@ -45,7 +45,10 @@ def calculate_dt(system: WeaklyCompressibleSPHSystem, cfl_number: float) -> floa
     c = float(system.state_equation.sound_speed)
     dt_viscosity = math.inf
     if system.viscosity is not None:
-        nu = float(system.viscosity.alpha) * h * c / (2 * system.ndims + 4)
+        if hasattr(system.viscosity, "nu"):   # ViscosityMorris / ViscosityAdami: kinematic_viscosity = nu
+            nu = float(system.viscosity.nu)
+        else:
+            nu = float(system.viscosity.alpha) * h * c / (2 * system.ndims + 4)
         dt_viscosity = 0.125 * h ** 2 / nu
     dt_acceleration = 0.25 * math.sqrt(h / float(np.linalg.norm(system.acceleration)))
     dt_sound_speed = cfl_number * h / c
