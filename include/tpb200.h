@@ -57,6 +57,8 @@ extern "C" {
 #define TPB_KERNEL_SCHOENBERG_CUBIC 1
 #define TPB_KERNEL_WENDLAND_C4 2 /* smoothing_kernels.jl:489-514 */
 #define TPB_KERNEL_WENDLAND_C6 3 /* smoothing_kernels.jl:548-574 */
+#define TPB_KERNEL_SCHOENBERG_QUARTIC 4 /* smoothing_kernels.jl:264-322, compact support 5/2 h */
+#define TPB_KERNEL_SCHOENBERG_QUINTIC 5 /* smoothing_kernels.jl:357-395, compact support 3 h */
 
 /* density calculators (src/general/density_calculators.jl) */
 #define TPB_DENSITY_CONTINUITY 0

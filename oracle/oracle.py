@@ -19,6 +19,8 @@ KERNEL_WENDLAND_C2 = 0
 KERNEL_SCHOENBERG_CUBIC = 1
 KERNEL_WENDLAND_C4 = 2
 KERNEL_WENDLAND_C6 = 3
+KERNEL_SCHOENBERG_QUARTIC = 4
+KERNEL_SCHOENBERG_QUINTIC = 5
 DENSITY_CONTINUITY = 0
 DENSITY_SUMMATION = 1
 

@@ -35,7 +35,7 @@ extern "C" {
 /* `has_viscosity` selects the model; Morris / Adami carry their kinematic viscosity nu in `alpha` */
 enum { ORC_VISCOSITY_NONE = 0, ORC_VISCOSITY_MONAGHAN = 1, ORC_VISCOSITY_MORRIS = 2, ORC_VISCOSITY_ADAMI = 3 };
 enum { ORC_KERNEL_WENDLAND_C2 = 0, ORC_KERNEL_SCHOENBERG_CUBIC = 1, ORC_KERNEL_WENDLAND_C4 = 2,
-       ORC_KERNEL_WENDLAND_C6 = 3 };
+       ORC_KERNEL_WENDLAND_C6 = 3, ORC_KERNEL_SCHOENBERG_QUARTIC = 4, ORC_KERNEL_SCHOENBERG_QUINTIC = 5 };
 enum { ORC_DENSITY_CONTINUITY = 0, ORC_DENSITY_SUMMATION = 1 };
 
 /* WeaklyCompressibleSPHSystem fields (wcsph/system.jl:65-86) that the RHS reads. */

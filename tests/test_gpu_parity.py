@@ -189,12 +189,13 @@ def test_chunked_staging_small_shared_memory(oracle, monkeypatch, smem, list_len
     semi.close()
 
 
-@pytest.mark.parametrize("kernel_cls", ["WendlandC4Kernel", "WendlandC6Kernel"])
+@pytest.mark.parametrize("kernel_cls", ["WendlandC4Kernel", "WendlandC6Kernel", "SchoenbergQuarticSplineKernel",
+                                        "SchoenbergQuinticSplineKernel"])
 @pytest.mark.parametrize("config", ["dam_break_2d_f64", "dam_break_3d_f32"])
-def test_kick_wendland_c4_c6(oracle, kernel_cls, config):
-    """The higher-order Wendland kernels of the reference's GPU test matrix
-    (test/examples/gpu.jl:349-394; smoothing_kernels.jl:489-574), fluid and wall model."""
-    import copy
+def test_kick_other_smoothing_kernels(oracle, kernel_cls, config):
+    """The other kernels of the reference's GPU test matrix (test/examples/gpu.jl:364-378;
+    smoothing_kernels.jl:264-395, :489-574), fluid and wall model; the quartic and quintic splines
+    have a compact support of 5/2 h and 3 h (smoothing length 1.1 dx as in that matrix)."""
     if config == "dam_break_2d_f64":
         fluid, wall, _ = examples.dam_break_2d(20)
     else:
@@ -202,8 +203,21 @@ def test_kick_wendland_c4_c6(oracle, kernel_cls, config):
     kernel = getattr(tp, kernel_cls)(fluid.ndims)
     fluid.smoothing_kernel = kernel
     wall.boundary_model.smoothing_kernel = kernel
+    if kernel_cls.startswith("Schoenberg"):
+        h = fluid.eltype.type(1.1 * fluid.initial_condition.particle_spacing)
+        fluid.smoothing_length = h
+        wall.boundary_model.smoothing_length = h
     u, v = examples.perturbed_state(fluid)
     check_against_oracle(fluid, wall, u, v)
+    # neighbour sets with the kernel's own search radius, bit-exact
+    semi, ode = make_semi(fluid, wall)
+    u_ode = np.ascontiguousarray(u).reshape(-1)
+    R_f = float(tp.compact_support(kernel, fluid.eltype.type(fluid.smoothing_length)))
+    for (a, b, xa, xb) in [(fluid, fluid, u, u), (fluid, wall, u, wall.coordinates), (wall, fluid, wall.coordinates, u)]:
+        gi, gj = semi.neighbor_pairs(a, b, u_ode)
+        oi, oj = oracle.neighbor_pairs(xa, xb, R_f, dtype=fluid.eltype, grid=True)
+        assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
+    semi.close()
 
 
 @pytest.mark.parametrize("viscosity_cls", ["ViscosityMorris", "ViscosityAdami"])

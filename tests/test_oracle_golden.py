@@ -6,7 +6,8 @@ import pytest
 import trixiparticles.jl_b200 as tp
 from oracle import adapter
 
-WC2, CUBIC, WC4, WC6 = 0, 1, 2, 3
+WC2, CUBIC, WC4, WC6, QUARTIC, QUINTIC = 0, 1, 2, 3, 4, 5
+SUPPORT = {WC2: 2.0, CUBIC: 2.0, WC4: 2.0, WC6: 2.0, QUARTIC: 2.5, QUINTIC: 3.0}   # compact_support / h
 
 
 # test/schemes/fluid/viscosity.jl:2-42
@@ -76,22 +77,23 @@ def test_cole_inverse_roundtrip(oracle):
 
 
 # test/general/smoothing_kernels.jl:61-73 (normalisation) and :99-132 (derivative)
-@pytest.mark.parametrize("kernel", [WC2, CUBIC, WC4, WC6])
+@pytest.mark.parametrize("kernel", [WC2, CUBIC, WC4, WC6, QUARTIC, QUINTIC])
 @pytest.mark.parametrize("nd", [2, 3])
 def test_kernel_normalisation_and_derivative(oracle, kernel, nd):
     from scipy.integrate import quad
+    sup = SUPPORT[kernel]
     for h in [0.1, 1.0, 1.7]:
         surf = (lambda r: 2 * np.pi * r) if nd == 2 else (lambda r: 4 * np.pi * r * r)
-        integral, _ = quad(lambda r: oracle.kernel(kernel, nd, r, h) * surf(r), 0, 2 * h,
-                           points=[h], epsabs=1e-13, epsrel=1e-12)
+        integral, _ = quad(lambda r: oracle.kernel(kernel, nd, r, h) * surf(r), 0, sup * h,
+                           points=[0.5 * h, h, 1.5 * h, 2 * h][: 4 if sup > 2 else 2], epsabs=1e-13, epsrel=1e-12)
         assert integral == pytest.approx(1.0, abs=1e-12)
-        for r in np.linspace(0.05, 1.95, 11) * h:
+        for r in np.linspace(0.05, sup - 0.05, 11) * h:
             d = 1e-6 * h
             fd = (oracle.kernel(kernel, nd, r + d, h) - oracle.kernel(kernel, nd, r - d, h)) / (2 * d)
             assert oracle.kernel_deriv_div_r(kernel, nd, r, h) * r == pytest.approx(fd, rel=2e-6, abs=1e-9)
         # compact support: strict `<` (smoothing_kernels.jl:30-34)
-        assert oracle.kernel(kernel, nd, 2 * h, h) == 0.0
-        assert oracle.kernel(kernel, nd, np.nextafter(2 * h, 0), h) >= 0.0
+        assert oracle.kernel(kernel, nd, sup * h, h) == 0.0
+        assert oracle.kernel(kernel, nd, np.nextafter(sup * h, 0), h) >= 0.0
 
 
 def test_wendland_c4_c6_closed_forms(oracle):
@@ -114,7 +116,7 @@ def test_wendland_c4_c6_closed_forms(oracle):
 
 
 # test/general/smoothing_kernels.jl:135-176: Float32 evaluation stays close to Float64
-@pytest.mark.parametrize("kernel", [WC2, CUBIC, WC4, WC6])
+@pytest.mark.parametrize("kernel", [WC2, CUBIC, WC4, WC6, QUARTIC, QUINTIC])
 def test_kernel_float32(oracle, kernel):
     for nd in (2, 3):
         for r in [0.1, 0.5, 1.3]:

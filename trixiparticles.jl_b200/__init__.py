@@ -9,6 +9,7 @@ directory maps the dotted name onto this folder).
 from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
                     BoundaryModelDummyParticles, ContinuityDensity,
                     DensityDiffusionMolteniColagrossi, SchoenbergCubicSplineKernel,
+                    SchoenbergQuarticSplineKernel, SchoenbergQuinticSplineKernel,
                     SourceTermDamping, StateEquationCole, SummationDensity, ViscosityAdami, ViscosityMorris,
                     WallBoundarySystem,
                     WeaklyCompressibleSPHSystem, WendlandC2Kernel, WendlandC4Kernel, WendlandC6Kernel,
@@ -22,6 +23,7 @@ from .setups import InitialCondition, RectangularShape, RectangularTank, union
 __all__ = [
     "AdamiPressureExtrapolation", "ArtificialViscosityMonaghan", "BoundaryModelDummyParticles",
     "ContinuityDensity", "DensityDiffusionMolteniColagrossi", "SchoenbergCubicSplineKernel",
+    "SchoenbergQuarticSplineKernel", "SchoenbergQuinticSplineKernel",
     "SourceTermDamping", "StateEquationCole", "SummationDensity", "ViscosityAdami", "ViscosityMorris",
     "WallBoundarySystem",
     "WeaklyCompressibleSPHSystem", "WendlandC2Kernel", "WendlandC4Kernel", "WendlandC6Kernel",

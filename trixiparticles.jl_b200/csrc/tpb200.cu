@@ -154,13 +154,22 @@ KernelConst<T> make_kernel_const(int kernel, int nd, double h_)
         sigma = nd == 2 ? (T)(39.0 / (pi * 14.0)) : (T)(1365.0 / (pi * 512.0));
         k.c_d = (T)(-11.0 / 4.0);
         k.order = 6;
+    } else if (kernel == TPB_KERNEL_SCHOENBERG_QUARTIC) {
+        sigma = nd == 2 ? (T)(96.0 / (pi * 1199.0)) : (T)(1.0 / (pi * 20.0));
+        k.order = 4;
+    } else if (kernel == TPB_KERNEL_SCHOENBERG_QUINTIC) {
+        sigma = nd == 2 ? (T)(7.0 / (pi * 478.0)) : (T)(1.0 / (pi * 120.0));
+        k.order = 5;
     } else {
         sigma = nd == 2 ? (T)(10.0 / (pi * 7.0)) : (T)(1.0 / pi);
     }
     k.nf = nd == 2 ? sigma * (k.h_inv * k.h_inv) : sigma * (k.h_inv * k.h_inv * k.h_inv);
     k.m5nf = (T)(-5) * k.nf;
     k.h_inv2 = k.h_inv * k.h_inv;
-    k.support = (T)2 * k.h;
+    // compact_support (smoothing_kernels.jl:215, :310, :383, :400)
+    k.support = kernel == TPB_KERNEL_SCHOENBERG_QUARTIC   ? (T)(5.0 / 2.0) * k.h
+                : kernel == TPB_KERNEL_SCHOENBERG_QUINTIC ? (T)3 * k.h
+                                                          : (T)2 * k.h;
     return k;
 }
 
@@ -191,7 +200,7 @@ PairConst<T> make_pair_const(const tpb_fluid_params &fp, int nd)
     k.eps_h2 = k.eps * (h * h);
     T h_avg = (h + h) / (T)2;
     k.delta_h_c = (T)fp.delta * h_avg * k.c;
-    T R = (T)2 * h;
+    T R = k.kern.support;
     k.radius2 = R * R;
     k.almostzero = std::sqrt(eps_of<T>(R * R));
     k.has_viscosity = fp.has_viscosity;
@@ -391,7 +400,7 @@ struct Ops {
         k.kern = make_kernel_const<T>(s.wp.kernel, ND, s.wp.smoothing_length);
         k.eos = make_eos_const<T>(s.wp.sound_speed, s.wp.exponent, s.wp.reference_density,
                                   s.wp.background_pressure, 0);
-        T R = (T)2 * k.kern.h;
+        T R = k.kern.support;
         k.radius2 = R * R;
         for (int d = 0; d < 3; ++d) k.acc[d] = (T)s.fp.acceleration[d];
         k.p_off = (T)s.wp.pressure_offset;
@@ -485,15 +494,20 @@ struct Ops {
         const bool summ = s.fp.density_calculator == TPB_DENSITY_SUMMATION;
         prof_mark(s, TPB_PHASE_DENSITY);
         // kernel template value: 0 Wendland C2, 1 cubic spline, 2 Wendland C4 / C6
-        const int fk = std::min(s.fp.kernel, 2), wk = std::min(s.wp.kernel, 2);
+        auto tk = [](int kernel) { return kernel <= 1 ? kernel : kernel <= TPB_KERNEL_WENDLAND_C6 ? 2 : 3; };
+        const int fk = tk(s.fp.kernel), wk = tk(s.wp.kernel);
         if (summ) {
             if (fk == 0) launch_summation<0>(s, g, pc, eos);
             else if (fk == 1) launch_summation<1>(s, g, pc, eos);
-            else launch_summation<2>(s, g, pc, eos);
+            else if (fk == 2) launch_summation<2>(s, g, pc, eos);
+            else launch_summation<3>(s, g, pc, eos);
         }
         prof_mark(s, TPB_PHASE_BOUNDARY);
         if (s.n_w > 0) {
-            rc = wk == 0 ? launch_adami<0>(s, g) : wk == 1 ? launch_adami<1>(s, g) : launch_adami<2>(s, g);
+            rc = wk == 0   ? launch_adami<0>(s, g)
+                 : wk == 1 ? launch_adami<1>(s, g)
+                 : wk == 2 ? launch_adami<2>(s, g)
+                           : launch_adami<3>(s, g);
             if (rc) return rc;
         }
         prof_mark(s, TPB_PHASE_INTERACT);
@@ -501,8 +515,10 @@ struct Ops {
             rc = summ ? launch_interact<0, 1>(s, g, pc, d_dv) : launch_interact<0, 0>(s, g, pc, d_dv);
         else if (fk == 1)
             rc = summ ? launch_interact<1, 1>(s, g, pc, d_dv) : launch_interact<1, 0>(s, g, pc, d_dv);
-        else
+        else if (fk == 2)
             rc = summ ? launch_interact<2, 1>(s, g, pc, d_dv) : launch_interact<2, 0>(s, g, pc, d_dv);
+        else
+            rc = summ ? launch_interact<3, 1>(s, g, pc, d_dv) : launch_interact<3, 0>(s, g, pc, d_dv);
         if (rc) return rc;
         prof_mark(s, TPB_PHASE_END);
         if (s.prof_capacity > 0 && s.prof_kicks < s.prof_capacity) s.prof_kicks++;
@@ -627,8 +643,8 @@ struct Ops {
         if ((!x_fluid && system != s.wall_index) || (!y_fluid && neighbor != s.wall_index))
             return fail(&s, TPB_ERR_INVALID_ARGUMENT, "unknown system index");
         // radius of the ordered pair: compact_support(system, neighbor)
-        T h = x_fluid ? (T)s.fp.smoothing_length : (T)s.wp.smoothing_length;
-        T R = (T)2 * h;
+        T R = make_kernel_const<T>(x_fluid ? s.fp.kernel : s.wp.kernel, ND,
+                                   x_fluid ? s.fp.smoothing_length : s.wp.smoothing_length).support;
         T r2 = R * R;
         int n_x = (int)(x_fluid ? s.n_act : s.n_w);
         int *d_oi = nullptr, *d_oj = nullptr;
@@ -851,7 +867,7 @@ int32_t tpb_add_fluid_system(tpb_semi_t semi, const tpb_fluid_params *p, int64_t
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "tpb_fluid_params.struct_size mismatch");
     if (s->fluid_index >= 0)
         return fail(s, TPB_ERR_UNSUPPORTED, "only one fluid system per semidiscretization is supported");
-    if (p->kernel < TPB_KERNEL_WENDLAND_C2 || p->kernel > TPB_KERNEL_WENDLAND_C6)
+    if (p->kernel < TPB_KERNEL_WENDLAND_C2 || p->kernel > TPB_KERNEL_SCHOENBERG_QUINTIC)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown smoothing kernel");
     if (p->density_calculator != TPB_DENSITY_CONTINUITY && p->density_calculator != TPB_DENSITY_SUMMATION)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown density calculator");
@@ -880,7 +896,7 @@ int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *p, int64_t n
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "tpb_wall_params.struct_size mismatch");
     if (s->wall_index >= 0)
         return fail(s, TPB_ERR_UNSUPPORTED, "only one wall system per semidiscretization is supported");
-    if (p->kernel < TPB_KERNEL_WENDLAND_C2 || p->kernel > TPB_KERNEL_WENDLAND_C6)
+    if (p->kernel < TPB_KERNEL_WENDLAND_C2 || p->kernel > TPB_KERNEL_SCHOENBERG_QUINTIC)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown smoothing kernel");
     if (!(p->smoothing_length > 0) || !(p->sound_speed > 0) || !(p->reference_density > 0) || p->exponent == 0)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "smoothing_length, sound_speed, reference_density must be positive");
@@ -918,12 +934,13 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     const int nd = s->cfg.ndims;
     const size_t ts = tsize(s->cfg.eltype), cs = tsize(s->cfg.coords_eltype);
 
-    // search radii in T: compact_support = 2h (smoothing_kernels.jl:215,400)
-    auto radius = [&](double h) {
-        return s->cfg.eltype == TPB_F64 ? 2.0 * h : (double)(2.0f * (float)h);
+    // search radii in T: compact_support (smoothing_kernels.jl:215, :310, :383, :400)
+    auto radius = [&](int kernel, double h) {
+        return s->cfg.eltype == TPB_F64 ? (double)make_kernel_const<double>(kernel, nd, h).support
+                                        : (double)make_kernel_const<float>(kernel, nd, h).support;
     };
-    double R = radius(s->fp.smoothing_length);
-    if (s->wall_index >= 0) R = std::max(R, radius(s->wp.smoothing_length));
+    double R = radius(s->fp.kernel, s->fp.smoothing_length);
+    if (s->wall_index >= 0) R = std::max(R, radius(s->wp.kernel, s->wp.smoothing_length));
 
     // bounding box
     double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};

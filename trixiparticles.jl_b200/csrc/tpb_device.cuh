@@ -69,9 +69,9 @@ struct KernelConst {
     T nf;       // normalization_factor(kernel, h_inv) = sigma * h_inv^ND
     T m5nf;     // -5 * nf                (Wendland C2 derivative)
     T h_inv2;   // h_inv * h_inv
-    T support;  // compact_support = 2h
+    T support;  // compact_support: 2h; quartic spline 5/2 h; quintic spline 3h
     T c_d;      // Wendland C4 / C6: derivative prefactor (-7/3 or -11/4) in T
-    int order;  // Wendland C4 / C6 (SmoothingKernel<2>): 4 or 6
+    int order;  // Wendland C4 / C6 (SmoothingKernel<2>): 4 or 6; Schoenberg quartic / quintic (<3>): 4 or 5
 };
 
 template <int KERNEL, typename T>
@@ -146,6 +146,44 @@ struct SmoothingKernel<2, T> {
         }
         T t7 = t2 * t2 * t2 * t;
         return k.nf * (k.c_d * ((T)8 * (q * q) + (T)7 * q + (T)2) * t7 * k.h_inv2);
+    }
+};
+
+// SchoenbergQuarticSplineKernel / SchoenbergQuinticSplineKernel (smoothing_kernels.jl:264-395), one
+// template value, the order is a warp-uniform run-time switch:
+//   quartic: W = nf [(5/2-q)^4 - 5 (q<3/2)(3/2-q)^4 + 10 (q<1/2)(1/2-q)^4]
+//   quintic: W = nf [(3-q)^5 - 6 (q<2)(2-q)^5 + 15 (q<1)(1-q)^5];   (dW/dr)/r = div_fast(nf W'(q) h^-1, r)
+template <typename T>
+struct SmoothingKernel<3, T> {
+    static __device__ __forceinline__ T w_unsafe(const KernelConst<T> &k, T r)
+    {
+        T q = r * k.h_inv;
+        if (k.order == 4) {
+            T a = (T)2.5 - q, b = (T)1.5 - q, c = (T)0.5 - q;
+            T a2 = a * a, b2 = b * b, c2 = c * c;
+            T lt15 = q < (T)1.5 ? (T)1 : (T)0, lt05 = q < (T)0.5 ? (T)1 : (T)0;
+            return k.nf * (a2 * a2 - (T)5 * lt15 * (b2 * b2) + (T)10 * lt05 * (c2 * c2));
+        }
+        T a = (T)3 - q, b = (T)2 - q, c = (T)1 - q;
+        T a2 = a * a, b2 = b * b, c2 = c * c;
+        T lt2 = q < (T)2 ? (T)1 : (T)0, lt1 = q < (T)1 ? (T)1 : (T)0;
+        return k.nf * (a2 * a2 * a - (T)6 * lt2 * (b2 * b2 * b) + (T)15 * lt1 * (c2 * c2 * c));
+    }
+    static __device__ __forceinline__ T dw_div_r(const KernelConst<T> &k, T r)
+    {
+        T q = r * k.h_inv;
+        T result;
+        if (k.order == 4) {
+            T a = (T)2.5 - q, b = (T)1.5 - q, c = (T)0.5 - q;
+            T lt15 = q < (T)1.5 ? (T)1 : (T)0, lt05 = q < (T)0.5 ? (T)1 : (T)0;
+            result = (T)(-4) * (a * a * a) + (T)20 * lt15 * (b * b * b) - (T)40 * lt05 * (c * c * c);
+        } else {
+            T a = (T)3 - q, b = (T)2 - q, c = (T)1 - q;
+            T a2 = a * a, b2 = b * b, c2 = c * c;
+            T lt2 = q < (T)2 ? (T)1 : (T)0, lt1 = q < (T)1 ? (T)1 : (T)0;
+            result = (T)(-5) * (a2 * a2) + (T)30 * lt2 * (b2 * b2) - (T)75 * lt1 * (c2 * c2);
+        }
+        return div_fast(k.nf * result * k.h_inv, r);
     }
 };
 
@@ -342,6 +380,20 @@ __device__ __forceinline__ float fast_wdr(const FastConst &c, float dist, float 
         const float t2 = t * t;
         if (c.order == 4) return c.c_d * fmaf(5.0f, q, 2.0f) * (t2 * t2 * t);
         return c.c_d * fmaf(fmaf(8.0f, q, 7.0f), q, 2.0f) * (t2 * t2 * t2 * t);
+    } else if (KERNEL == 3) {
+        const float q = dist * c.h_inv;
+        float result;
+        if (c.order == 4) {
+            const float a = 2.5f - q, b = 1.5f - q, d = 0.5f - q;
+            result = -4.0f * (a * a * a) + (q < 1.5f ? 20.0f * (b * b * b) : 0.0f) -
+                     (q < 0.5f ? 40.0f * (d * d * d) : 0.0f);
+        } else {
+            const float a = 3.0f - q, b = 2.0f - q, d = 1.0f - q;
+            const float a2 = a * a, b2 = b * b, d2_ = d * d;
+            result = -5.0f * (a2 * a2) + (q < 2.0f ? 30.0f * (b2 * b2) : 0.0f) -
+                     (q < 1.0f ? 75.0f * (d2_ * d2_) : 0.0f);
+        }
+        return c.nfh * result * rs;
     } else {
         const float q = dist * c.h_inv;
         const float a = 2.0f - q, b = 1.0f - q;

@@ -21,7 +21,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from .model import (SchoenbergCubicSplineKernel, WallBoundarySystem, WeaklyCompressibleSPHSystem,
+from .model import (SchoenbergCubicSplineKernel, SchoenbergQuarticSplineKernel,
+                    SchoenbergQuinticSplineKernel, WallBoundarySystem, WeaklyCompressibleSPHSystem,
                     WendlandC2Kernel, WendlandC4Kernel, WendlandC6Kernel, compact_support)
 
 
@@ -39,6 +40,14 @@ def kernel(smoothing_kernel, r, h):
     elif isinstance(smoothing_kernel, WendlandC6Kernel):
         sigma = {2: 39 / (14 * np.pi), 3: 1365 / (512 * np.pi)}[nd]
         w = sigma / h ** nd * (1 - q / 2) ** 8 * (4 * q ** 3 + 25 * q ** 2 / 4 + 4 * q + 1)
+    elif isinstance(smoothing_kernel, SchoenbergQuarticSplineKernel):
+        sigma = {2: 96 / (1199 * np.pi), 3: 1 / (20 * np.pi)}[nd]
+        w = sigma / h ** nd * ((2.5 - q) ** 4 - 5 * np.where(q < 1.5, (1.5 - q) ** 4, 0.0)
+                               + 10 * np.where(q < 0.5, (0.5 - q) ** 4, 0.0))
+    elif isinstance(smoothing_kernel, SchoenbergQuinticSplineKernel):
+        sigma = {2: 7 / (478 * np.pi), 3: 1 / (120 * np.pi)}[nd]
+        w = sigma / h ** nd * ((3 - q) ** 5 - 6 * np.where(q < 2, (2 - q) ** 5, 0.0)
+                               + 15 * np.where(q < 1, (1 - q) ** 5, 0.0))
     elif isinstance(smoothing_kernel, SchoenbergCubicSplineKernel):
         sigma = {2: 10 / (7 * np.pi), 3: 1 / np.pi}[nd]
         w = sigma / h ** nd * ((2 - q) ** 3 / 4 - np.where(q < 1, (1 - q) ** 3, 0.0))

@@ -19,6 +19,8 @@ KERNEL_WENDLAND_C2 = 0
 KERNEL_SCHOENBERG_CUBIC = 1
 KERNEL_WENDLAND_C4 = 2
 KERNEL_WENDLAND_C6 = 3
+KERNEL_SCHOENBERG_QUARTIC = 4
+KERNEL_SCHOENBERG_QUINTIC = 5
 DENSITY_CONTINUITY = 0
 DENSITY_SUMMATION = 1
 
@@ -49,8 +51,28 @@ class WendlandC6Kernel:
     kernel_id: int = KERNEL_WENDLAND_C6
 
 
+@dataclass(frozen=True)
+class SchoenbergQuarticSplineKernel:
+    """smoothing_kernels.jl:264-322 (compact support 5/2 h)."""
+    ndims: int
+    kernel_id: int = KERNEL_SCHOENBERG_QUARTIC
+
+
+@dataclass(frozen=True)
+class SchoenbergQuinticSplineKernel:
+    """smoothing_kernels.jl:357-395 (compact support 3 h)."""
+    ndims: int
+    kernel_id: int = KERNEL_SCHOENBERG_QUINTIC
+
+
 def compact_support(kernel, h):
-    """`compact_support(kernel, h) = 2h` for both kernels (smoothing_kernels.jl:215, :400)."""
+    """smoothing_kernels.jl:215, :400 (2h: cubic spline, Wendland), :310 (5/2 h), :383 (3h);
+    evaluated in the type of `h`."""
+    t = type(h) if isinstance(h, np.floating) else float
+    if kernel.kernel_id == KERNEL_SCHOENBERG_QUARTIC:
+        return t(5 / 2) * h
+    if kernel.kernel_id == KERNEL_SCHOENBERG_QUINTIC:
+        return 3 * h
     return 2 * h
 
 

@@ -541,8 +541,10 @@ class SlabSemidiscretization:
         self.rank, self.world = rank, world
         self.global_n_fluid = fluid.nparticles
         t = fluid.eltype.type
-        R_f = float(t(2) * fluid.smoothing_length)
-        R_w = float(t(2) * wall.boundary_model.smoothing_length) if wall is not None else R_f
+        from .model import compact_support
+        R_f = float(compact_support(fluid.smoothing_kernel, t(fluid.smoothing_length)))
+        R_w = (float(compact_support(wall.boundary_model.smoothing_kernel, t(wall.boundary_model.smoothing_length)))
+               if wall is not None else R_f)
         self._radii = (R_f, R_w)
         self._wall_global = wall
         self._device_index, self._interact_variant, self._transport_arg = device, interact_variant, transport
