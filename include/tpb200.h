@@ -105,6 +105,14 @@ typedef struct {
     double delta;                   /* density_diffusion.jl:41-47 */
     double acceleration[3];         /* system.acceleration */
     double damping_coefficient;     /* SourceTermDamping (semidiscretization.jl:795-807); 0 = none */
+    /* StateEquationAdaptiveCole (state_equations.jl:37-84; update_speed_of_sound!,
+     * wcsph/system.jl:307-321): every kick sets sound_speed = clamp(max|v| / mach_number_target,
+     * min_sound_speed, max_sound_speed) before the pressure update; `sound_speed` above is the
+     * initial value (min_sound_speed).  adaptive_params_f32: the state equation's fields are
+     * Float32 (its default literals) although eltype(system) may be Float64. */
+    int32_t adaptive_sound_speed;
+    int32_t adaptive_params_f32;
+    double mach_number_target, min_sound_speed, max_sound_speed;
 } tpb_fluid_params;
 
 /* `WallBoundarySystem(ic, BoundaryModelDummyParticles(density, mass,
@@ -114,7 +122,7 @@ typedef struct {
     int32_t struct_size;
     int32_t kernel;
     int32_t clip_negative_pressure; /* boundary model flag */
-    int32_t reserved;
+    int32_t sound_speed_from_fluid; /* 1: the boundary model shares the fluid's StateEquationAdaptiveCole */
     double smoothing_length;
     double sound_speed, exponent, reference_density, background_pressure;
     double pressure_offset;
@@ -192,6 +200,8 @@ int32_t tpb_synchronize(tpb_semi_t semi);
 /* `stream` is a cudaStream_t; NULL selects the handle's own stream */
 int32_t tpb_set_stream(tpb_semi_t semi, void *stream);
 int32_t tpb_get_stats(tpb_semi_t semi, tpb_stats *out);
+/* `system_sound_speed(fluid)` as of the last kick (StateEquationAdaptiveCole; else the constant) */
+int32_t tpb_get_sound_speed(tpb_semi_t semi, double *out);
 
 /* ---- device ODE-vector algebra ----------------------------------------------------------------
  * What a GPU-resident ODE-vector type binds for the integrator's broadcasts (the reference's

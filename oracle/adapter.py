@@ -58,11 +58,26 @@ def wall_params(wall) -> O.WallParams:
     return p
 
 
+def _f32_bits(x) -> int:
+    return int(np.array([x], dtype=np.float32).view(np.int32)[0])
+
+
 def kick(fluid, wall, u, v, use_grid=True, nthreads=0, fluid_wall_interaction=True):
     """Oracle `kick!` for Semidiscretization(fluid[, wall]); u (n, ND), v (n, nv)."""
+    se = fluid.state_equation
+    adaptive = hasattr(se, "update_speed_of_sound")
+    if adaptive:
+        # update_speed_of_sound! (wcsph/system.jl:307-321) comes first in the reference's kick!;
+        # the C oracle then sees a Cole equation with that speed of sound
+        se.update_speed_of_sound(np.asarray(v)[:, :fluid.ndims], fluid.eltype)
     fp = fluid_params(fluid)
+    mixed = adaptive and se.param_eltype == np.float32 and np.dtype(fluid.eltype) != np.float32
+    if mixed:   # B formed in Float32 by the state equation itself
+        fp.reserved0, fp.reserved1 = _f32_bits(se._B()), 1
     if wall is not None and fluid_wall_interaction:
         wp = wall_params(wall)
+        if mixed and wall.boundary_model.state_equation is se:
+            wp.reserved0 = _f32_bits(se._B())
         cw, mw = wall.coordinates, wall.boundary_model.hydrodynamic_mass
     else:
         wp, cw, mw = None, None, None

@@ -46,7 +46,7 @@ typedef struct {
     int32_t clip_negative_pressure; /* StateEquationCole{..., CLIP} */
     int32_t has_viscosity;          /* ArtificialViscosityMonaghan or nothing */
     int32_t has_diffusion;          /* DensityDiffusionMolteniColagrossi or nothing */
-    int32_t reserved0, reserved1;
+    int32_t reserved0, reserved1;   /* reserved1 != 0: reserved0 = bits of a Float32 B (see eos_B) */
     double smoothing_length;
     double sound_speed, exponent, reference_density, background_pressure;
     double alpha, beta, epsilon;    /* viscosity.jl:68-76 */

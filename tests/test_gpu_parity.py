@@ -245,6 +245,32 @@ def test_kick_viscosity_morris_adami(oracle, viscosity_cls, config):
     check_against_oracle(fluid, wall, u, v, interact_variant=1)
 
 
+@pytest.mark.parametrize("eltype,cdtype", [(np.float32, np.float32), (np.float32, np.float64),
+                                           (np.float64, np.float64)])
+def test_kick_adaptive_cole(oracle, eltype, cdtype):
+    """`StateEquationAdaptiveCole` shared by the fluid and the boundary model, as the shipped
+    examples/fluid/dam_break_3d.jl:33-39 does: every kick first sets the speed of sound from the
+    largest particle velocity (`update_speed_of_sound!`, wcsph/system.jl:307-321).  Its fields are
+    Float32 (the reference's default literals) in every precision set-up."""
+    fluid, wall, _ = examples.dam_break_3d(0.1, eltype=eltype, coordinates_eltype=cdtype,
+                                           adaptive_sound_speed=True)
+    se = fluid.state_equation
+    assert wall.boundary_model.state_equation is se and se.sound_speed == np.float32(10.0)
+    u, v = examples.perturbed_state(fluid)
+    for scale in (1.0, 40.0, 1e4):            # inside the band, and clamped at both ends
+        vs = v.copy()
+        vs[:, :3] *= eltype(scale * 3.0 / max(np.abs(v[:, :3]).max(), 1e-30) / 40.0)
+        semi, ode = make_semi(fluid, wall)
+        dv = np.full_like(vs.reshape(-1), np.nan)
+        tp.kick_(dv, vs.reshape(-1).copy(), np.ascontiguousarray(u).reshape(-1), ode.p, 0.0)
+        c_gpu = semi.sound_speed()
+        semi.close()
+        check_against_oracle(fluid, wall, u, vs)            # the oracle updates se.sound_speed
+        assert c_gpu == float(se.sound_speed), (scale, c_gpu, se.sound_speed)
+        assert 10.0 <= c_gpu <= 100.0
+    assert float(se.sound_speed) == 100.0
+
+
 @pytest.mark.parametrize("example", ["dam_break_2d", "hydrostatic_2d"])
 def test_kick_summation_density(oracle, example):
     """SummationDensity variant (density_calculators.jl:26-50; dam_break_2d variant in

@@ -10,7 +10,8 @@ from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
                     BoundaryModelDummyParticles, ContinuityDensity,
                     DensityDiffusionMolteniColagrossi, SchoenbergCubicSplineKernel,
                     SchoenbergQuarticSplineKernel, SchoenbergQuinticSplineKernel,
-                    SourceTermDamping, StateEquationCole, SummationDensity, ViscosityAdami, ViscosityMorris,
+                    SourceTermDamping, StateEquationAdaptiveCole, StateEquationCole, SummationDensity,
+                    ViscosityAdami, ViscosityMorris,
                     WallBoundarySystem,
                     WeaklyCompressibleSPHSystem, WendlandC2Kernel, WendlandC4Kernel, WendlandC6Kernel,
                     compact_support)
@@ -24,7 +25,8 @@ __all__ = [
     "AdamiPressureExtrapolation", "ArtificialViscosityMonaghan", "BoundaryModelDummyParticles",
     "ContinuityDensity", "DensityDiffusionMolteniColagrossi", "SchoenbergCubicSplineKernel",
     "SchoenbergQuarticSplineKernel", "SchoenbergQuinticSplineKernel",
-    "SourceTermDamping", "StateEquationCole", "SummationDensity", "ViscosityAdami", "ViscosityMorris",
+    "SourceTermDamping", "StateEquationAdaptiveCole", "StateEquationCole", "SummationDensity",
+    "ViscosityAdami", "ViscosityMorris",
     "WallBoundarySystem",
     "WeaklyCompressibleSPHSystem", "WendlandC2Kernel", "WendlandC4Kernel", "WendlandC6Kernel",
     "compact_support", "B200Backend",

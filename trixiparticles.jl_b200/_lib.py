@@ -20,7 +20,7 @@ EXPORTS = [
     "tpb_version", "tpb_last_error", "tpb_create", "tpb_destroy", "tpb_add_fluid_system",
     "tpb_add_wall_system", "tpb_set_interaction", "tpb_semidiscretize", "tpb_ode_sizes",
     "tpb_system_range", "tpb_kick", "tpb_drift", "tpb_get_system_field", "tpb_neighbor_pairs",
-    "tpb_synchronize", "tpb_set_stream", "tpb_get_stats", "tpb_host_register",
+    "tpb_synchronize", "tpb_set_stream", "tpb_get_stats", "tpb_get_sound_speed", "tpb_host_register",
     "tpb_host_unregister", "tpb_set_profiling", "tpb_get_phase_times",
     "tpb_set_fluid_count", "tpb_set_fluid_mass",
     "tpb_vec_axpby", "tpb_vec_rk2n_stage", "tpb_vec_fill", "tpb_vec_strided_max",
@@ -49,13 +49,15 @@ class FluidParams(C.Structure):
         ("background_pressure", C.c_double), ("alpha", C.c_double), ("beta", C.c_double),
         ("epsilon", C.c_double), ("delta", C.c_double), ("acceleration", C.c_double * 3),
         ("damping_coefficient", C.c_double),
+        ("adaptive_sound_speed", C.c_int32), ("adaptive_params_f32", C.c_int32),
+        ("mach_number_target", C.c_double), ("min_sound_speed", C.c_double), ("max_sound_speed", C.c_double),
     ]
 
 
 class WallParams(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("kernel", C.c_int32), ("clip_negative_pressure", C.c_int32),
-        ("reserved", C.c_int32), ("smoothing_length", C.c_double), ("sound_speed", C.c_double),
+        ("sound_speed_from_fluid", C.c_int32), ("smoothing_length", C.c_double), ("sound_speed", C.c_double),
         ("exponent", C.c_double), ("reference_density", C.c_double),
         ("background_pressure", C.c_double), ("pressure_offset", C.c_double),
     ]
@@ -112,6 +114,7 @@ def load():
     L.tpb_set_stream.restype = i32; L.tpb_set_stream.argtypes = [p, p]
     L.tpb_get_stats.restype = i32; L.tpb_get_stats.argtypes = [p, C.POINTER(Stats)]
     L.tpb_host_register.restype = i32; L.tpb_host_register.argtypes = [p, i64]
+    L.tpb_get_sound_speed.restype = i32; L.tpb_get_sound_speed.argtypes = [p, C.POINTER(d)]
     u32 = C.c_uint32
     L.tpb_peer_alloc.restype = i32; L.tpb_peer_alloc.argtypes = [i64, C.POINTER(p)]
     L.tpb_peer_free.restype = i32; L.tpb_peer_free.argtypes = [p]

@@ -66,6 +66,7 @@ struct Semi {
     void *d_Aw = nullptr, *d_Ww = nullptr, *d_volw = nullptr;
     int *d_perm_w = nullptr;
     void *d_scratch = nullptr;  // max(n_f, n_w) * sizeof(double): field unsort
+    unsigned long long *d_vmax2 = nullptr, *h_vmax2 = nullptr;  // StateEquationAdaptiveCole: max |v|^2 (bits)
     void *d_Ff = nullptr, *d_Fw = nullptr;  // Float32 filter copies of the sorted positions (f32 / f64 coords)
     double filter_ref[3] = {0, 0, 0};       // reference point of the copies (coordinate order)
     float filter_pad = 0;                   // see FilterRef
@@ -173,12 +174,15 @@ KernelConst<T> make_kernel_const(int kernel, int nd, double h_)
     return k;
 }
 
+// params_f32: the state equation's own fields are Float32 (StateEquationAdaptiveCole with its
+// default literals): B = reference_density * sound_speed^2 / exponent is then formed in Float32.
 template <typename T>
-EosConst<T> make_eos_const(double c_, double gamma_, double rho0_, double pbg_, int clip)
+EosConst<T> make_eos_const(double c_, double gamma_, double rho0_, double pbg_, int clip, int params_f32 = 0)
 {
     EosConst<T> e;
     T c = (T)c_, gamma = (T)gamma_, rho0 = (T)rho0_;
     e.B = rho0 * (c * c) / gamma;
+    if (params_f32) e.B = (T)((float)rho0_ * ((float)c_ * (float)c_) / (float)gamma_);
     e.gamma = gamma;
     e.inv_gamma = (T)1 / gamma;
     e.rho0 = rho0;
@@ -276,7 +280,8 @@ struct Ops {
         int rc = bin_points(s, d_u, n, (int)s.n_tgt, s.d_fcell_start);
         if (rc) return rc;
         EosConst<T> eos = make_eos_const<T>(s.fp.sound_speed, s.fp.exponent, s.fp.reference_density,
-                                            s.fp.background_pressure, s.fp.clip_negative_pressure);
+                                            s.fp.background_pressure, s.fp.clip_negative_pressure,
+                                            s.fp.adaptive_sound_speed && s.fp.adaptive_params_f32);
         const GridConst<CT> g = make_grid_const<CT>(s);
         if (n > 0) {
             if (s.fp.density_calculator == TPB_DENSITY_CONTINUITY)
@@ -399,7 +404,8 @@ struct Ops {
         AdamiConst<T> k;
         k.kern = make_kernel_const<T>(s.wp.kernel, ND, s.wp.smoothing_length);
         k.eos = make_eos_const<T>(s.wp.sound_speed, s.wp.exponent, s.wp.reference_density,
-                                  s.wp.background_pressure, 0);
+                                  s.wp.background_pressure, 0,
+                                  s.wp.sound_speed_from_fluid && s.fp.adaptive_params_f32);
         T R = k.kern.support;
         k.radius2 = R * R;
         for (int d = 0; d < 3; ++d) k.acc[d] = (T)s.fp.acceleration[d];
@@ -480,17 +486,58 @@ struct Ops {
         return TPB_OK;
     }
 
+    // ---- update_speed_of_sound! (wcsph/system.jl:307-321, StateEquationAdaptiveCole): one max
+    // reduction over the fluid velocities; like the reference (`maximum` returns a host scalar)
+    // the new sound speed is a host value, so this kick waits for the reduction.
+    static int update_sound_speed(Semi &s, const T *d_v)
+    {
+        const int64_t n = s.n_act;
+        CUDA_TRY(&s, cudaMemsetAsync(s.d_vmax2, 0, sizeof(unsigned long long), s.stream));
+        LAUNCH(s, (k_max_speed2<ND, T>), (int)std::min<int64_t>(cdiv(n, 256), 148 * 8), 256, 0, n, nv(s), d_v,
+               s.d_vmax2);
+        CUDA_TRY(&s, cudaMemcpyAsync(s.h_vmax2, s.d_vmax2, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                     s.stream));
+        CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
+        T v_max2;
+        if (sizeof(T) == 4) {
+            const uint32_t bits = (uint32_t)*s.h_vmax2;
+            std::memcpy(&v_max2, &bits, sizeof(T));
+        } else {
+            std::memcpy(&v_max2, s.h_vmax2, sizeof(T));
+        }
+        const T v_max = std::sqrt(v_max2);
+        double c;
+        if (s.fp.adaptive_params_f32 && sizeof(T) == 8) {
+            // Float64 velocities, Float32 parameters: the quotient and the clamps are evaluated in
+            // Float64 (promotion), the result is stored in the state equation's Float32 Ref
+            const double q = (double)v_max / (double)(float)s.fp.mach_number_target;
+            c = (double)(float)std::min((double)(float)s.fp.max_sound_speed,
+                                        std::max((double)(float)s.fp.min_sound_speed, q));
+        } else {
+            const T q = v_max / (T)s.fp.mach_number_target;
+            c = (double)std::min((T)s.fp.max_sound_speed, std::max((T)s.fp.min_sound_speed, q));
+        }
+        s.fp.sound_speed = c;
+        if (s.wp.sound_speed_from_fluid) s.wp.sound_speed = c;
+        return TPB_OK;
+    }
+
     // ---- kick! on device pointers
     static int kick_device(Semi &s, T *d_dv, const T *d_v, const CT *d_u)
     {
         if (s.n_act == 0) return TPB_OK;
+        if (s.fp.adaptive_sound_speed) {
+            int rc_c = update_sound_speed(s, d_v);
+            if (rc_c) return rc_c;
+        }
         prof_mark(s, TPB_PHASE_REBUILD);
         int rc = rebuild_fluid(s, d_u, d_v);
         if (rc) return rc;
         GridConst<CT> g = make_grid_const<CT>(s);
         PairConst<T> pc = make_pair_const<T>(s.fp, ND);
         EosConst<T> eos = make_eos_const<T>(s.fp.sound_speed, s.fp.exponent, s.fp.reference_density,
-                                            s.fp.background_pressure, s.fp.clip_negative_pressure);
+                                            s.fp.background_pressure, s.fp.clip_negative_pressure,
+                                            s.fp.adaptive_sound_speed && s.fp.adaptive_params_f32);
         const bool summ = s.fp.density_calculator == TPB_DENSITY_SUMMATION;
         prof_mark(s, TPB_PHASE_DENSITY);
         // kernel template value: 0 Wendland C2, 1 cubic spline, 2 Wendland C4 / C6
@@ -777,13 +824,14 @@ static void free_device(Semi &s)
     void *ptrs[] = {s.d_mass_f, s.d_u, s.d_v, s.d_dv, s.d_du, s.d_key, s.d_slot, s.d_tmp_perm,
                     s.d_perm_f, s.d_count, s.d_fcell_start, s.d_wcell_start, s.d_block_sums,
                     s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_perm_w,
-                    s.d_scratch, s.d_Ff, s.d_Fw};
+                    s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     tiles_free(s.tiles);
     for (cudaEvent_t e : s.prof_events) cudaEventDestroy(e);
     s.prof_events.clear();
     if (s.h_flags) cudaFreeHost(s.h_flags);
+    if (s.h_vmax2) cudaFreeHost(s.h_vmax2);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
 }
 
@@ -875,6 +923,10 @@ int32_t tpb_add_fluid_system(tpb_semi_t semi, const tpb_fluid_params *p, int64_t
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "smoothing_length, sound_speed, reference_density must be positive");
     if (p->has_diffusion && p->density_calculator == TPB_DENSITY_SUMMATION)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "density diffusion requires ContinuityDensity");
+    if (p->adaptive_sound_speed &&
+        (!(p->mach_number_target > 0) || !(p->min_sound_speed > 0) || !(p->max_sound_speed >= p->min_sound_speed)))
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "StateEquationAdaptiveCole: mach_number_target > 0 and "
+                                                 "0 < min_sound_speed <= max_sound_speed are required");
     if (n < 0 || n > 0x7fffffff / 4) return fail(s, TPB_ERR_INVALID_ARGUMENT, "particle count out of range");
     s->fp = *p;
     s->n_f = n; s->n_act = n; s->n_tgt = n;
@@ -1065,6 +1117,8 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     CUDA_TRY(s, cudaMalloc(&s->d_Ww, 2 * ts * (nw + 8)));
     CUDA_TRY(s, cudaMalloc(&s->d_volw, ts * (nw + 8)));
     CUDA_TRY(s, cudaMalloc(&s->d_scratch, sizeof(double) * nmax));
+    CUDA_TRY(s, cudaMalloc(&s->d_vmax2, sizeof(unsigned long long)));
+    CUDA_TRY(s, cudaHostAlloc(&s->h_vmax2, sizeof(unsigned long long), cudaHostAllocDefault));
     if (s->cfg.eltype == TPB_F32 && s->cfg.coords_eltype == TPB_F64) {
         CUDA_TRY(s, cudaMalloc(&s->d_Ff, sizeof(float) * 4 * nf));
         CUDA_TRY(s, cudaMalloc(&s->d_Fw, sizeof(float) * 4 * nw));
@@ -1183,6 +1237,15 @@ int32_t tpb_set_stream(tpb_semi_t semi, void *stream)
     return TPB_OK;
 }
 
+int32_t tpb_get_sound_speed(tpb_semi_t semi, double *out)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !out) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (s->fluid_index < 0) return fail(s, TPB_ERR_STATE, "no fluid system");
+    *out = s->fp.sound_speed;
+    return TPB_OK;
+}
+
 int32_t tpb_get_stats(tpb_semi_t semi, tpb_stats *out)
 {
     Semi *s = (Semi *)semi;
@@ -1199,6 +1262,8 @@ int32_t tpb_set_fluid_count(tpb_semi_t semi, int64_t n_active, int64_t n_targets
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "need 0 <= n_targets <= n_active <= capacity of the fluid system");
     if (n_targets < n_active && s->fp.density_calculator == TPB_DENSITY_SUMMATION)
         return fail(s, TPB_ERR_UNSUPPORTED, "ghost particles need ContinuityDensity (their density travels with them)");
+    if (n_targets < n_active && s->fp.adaptive_sound_speed)
+        return fail(s, TPB_ERR_UNSUPPORTED, "StateEquationAdaptiveCole needs the maximum velocity of all slabs");
     s->n_act = n_active;
     s->n_tgt = n_targets;
     return TPB_OK;

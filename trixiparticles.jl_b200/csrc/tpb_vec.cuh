@@ -73,4 +73,31 @@ k_vec_strided_max(int64_t count, int stride, int offset, const T *__restrict__ x
     }
 }
 
+// max_i |v_i|^2 over the first ND entries of every row of v (update_speed_of_sound!,
+// wcsph/system.jl:307-315): products and sums separately rounded, left to right; the maximum of
+// non-negative IEEE numbers is the maximum of their bit patterns.
+template <int ND, typename T>
+__global__ void __launch_bounds__(256)
+k_max_speed2(int64_t n, int nv, const T *__restrict__ v, unsigned long long *__restrict__ out_bits)
+{
+    unsigned long long best = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T *r = v + i * nv;
+        T s;
+        if constexpr (sizeof(T) == 4) {
+            s = __fadd_rn(__fmul_rn(r[0], r[0]), __fmul_rn(r[1], r[1]));
+            if (ND == 3) s = __fadd_rn(s, __fmul_rn(r[2], r[2]));
+            best = max(best, (unsigned long long)__float_as_uint(s));
+        } else {
+            s = __dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1]));
+            if (ND == 3) s = __dadd_rn(s, __dmul_rn(r[2], r[2]));
+            best = max(best, (unsigned long long)__double_as_longlong(s));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(out_bits, best);
+}
+
 }  // namespace tpb

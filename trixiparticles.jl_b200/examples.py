@@ -11,7 +11,7 @@ import numpy as np
 from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
                     BoundaryModelDummyParticles, ContinuityDensity,
                     DensityDiffusionMolteniColagrossi, SchoenbergCubicSplineKernel,
-                    StateEquationCole, SummationDensity, WallBoundarySystem,
+                    StateEquationAdaptiveCole, StateEquationCole, SummationDensity, WallBoundarySystem,
                     WeaklyCompressibleSPHSystem, WendlandC2Kernel)
 from .setups import RectangularTank
 
@@ -72,7 +72,7 @@ def hydrostatic_water_column_2d(fluid_particle_spacing=0.05, *, eltype=np.float3
 
 
 def dam_break_3d(fluid_particle_spacing=0.08, *, eltype=np.float32, coordinates_eltype=None,
-                 sound_speed=None, fluid_size=(2.0, 1.0, 1.0), tank_size=None):
+                 sound_speed=None, fluid_size=(2.0, 1.0, 1.0), tank_size=None, adaptive_sound_speed=False):
     """examples/fluid/dam_break_3d.jl:13-66 (BASELINE configs 3/4 at smaller spacings).
 
     As SURVEY.md section 8(d) M3 prescribes, the headline runs use a static
@@ -86,6 +86,9 @@ def dam_break_3d(fluid_particle_spacing=0.08, *, eltype=np.float32, coordinates_
     c = sound_speed if sound_speed is not None else 20 * np.sqrt(gravity * 1.0)
     state_equation = StateEquationCole(sound_speed=float(np.dtype(eltype).type(c)),
                                        reference_density=1000.0, exponent=7)
+    if adaptive_sound_speed:
+        # the script as shipped (dam_break_3d.jl:33-34): one object shared by fluid and boundary model
+        state_equation = StateEquationAdaptiveCole(reference_density=1000.0, exponent=7)
     tank = RectangularTank(dx, fluid_size, tank_size, 1000.0, n_layers=4, spacing_ratio=1,
                            acceleration=(0.0, -gravity, 0.0), state_equation=state_equation,
                            coordinates_eltype=coordinates_eltype, eltype=eltype)

@@ -109,6 +109,56 @@ class StateEquationCole:
         return r0 * t(np.float64(tmp) ** np.float64(t(1) / g))
 
 
+class StateEquationAdaptiveCole:
+    """state_equations.jl:37-84: Cole's equation whose speed of sound follows the largest particle
+    velocity, c = clamp(max|v| / mach_number_target, min_sound_speed, max_sound_speed), updated at
+    the start of every right-hand-side evaluation (`update_speed_of_sound!`,
+    wcsph/system.jl:307-321).  All fields are stored in ELTYPE = typeof(mach_number_target) --
+    Float32 with the reference's default literals, whatever eltype(system) is; `sound_speed` starts
+    at `min_sound_speed`.  One object may be shared by the fluid and the boundary model."""
+
+    def __init__(self, *, reference_density, exponent, mach_number_target=np.float32(0.1),
+                 min_sound_speed=np.float32(10.0), max_sound_speed=np.float32(100.0),
+                 background_pressure=np.float32(0.0), clip_negative_pressure=False):
+        t = type(mach_number_target) if isinstance(mach_number_target, np.floating) else np.float64
+        self.param_eltype = np.dtype(t)
+        self.mach_number_target = t(mach_number_target)
+        self.min_sound_speed = t(min_sound_speed)
+        self.max_sound_speed = t(max_sound_speed)
+        self.exponent = t(exponent)
+        self.reference_density = t(reference_density)
+        self.background_pressure = t(background_pressure)
+        self.clip_negative_pressure = bool(clip_negative_pressure)
+        self.sound_speed = t(min_sound_speed)
+
+    def update_speed_of_sound(self, velocity, eltype):
+        """`velocity`: (n, ND) array of eltype(system).  Sets and returns `sound_speed`."""
+        v = np.asarray(velocity, dtype=eltype)
+        if len(v) == 0:
+            return self.sound_speed
+        s = v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]
+        if v.shape[1] == 3:
+            s = s + v[:, 2] * v[:, 2]
+        v_max = np.sqrt(s.max())                       # eltype(system)
+        q = v_max / self.mach_number_target            # promoted
+        self.sound_speed = self.param_eltype.type(min(self.max_sound_speed, max(self.min_sound_speed, q)))
+        return self.sound_speed
+
+    def _B(self):
+        return self.reference_density * self.sound_speed ** 2 / self.exponent   # in ELTYPE
+
+    def __call__(self, density, dtype=np.float64):
+        t = np.dtype(dtype).type
+        x = t(density) / t(self.reference_density)
+        p = t(self._B()) * (t(np.float64(x) ** np.float64(self.exponent)) - t(1)) + t(self.background_pressure)
+        return max(t(0), p) if self.clip_negative_pressure else p
+
+    def inverse(self, pressure, dtype=np.float64):
+        t = np.dtype(dtype).type
+        tmp = (t(pressure) - t(self.background_pressure)) / t(self._B()) + t(1)
+        return t(self.reference_density) * t(np.float64(tmp) ** np.float64(t(1) / t(self.exponent)))
+
+
 @dataclass(frozen=True)
 class ArtificialViscosityMonaghan:
     alpha: float

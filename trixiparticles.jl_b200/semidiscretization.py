@@ -17,8 +17,8 @@ import numpy as np
 
 from . import _lib
 from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
-                    DensityDiffusionMolteniColagrossi, SourceTermDamping, SummationDensity,
-                    WallBoundarySystem, WeaklyCompressibleSPHSystem)
+                    DensityDiffusionMolteniColagrossi, SourceTermDamping, StateEquationAdaptiveCole,
+                    SummationDensity, WallBoundarySystem, WeaklyCompressibleSPHSystem)
 
 
 @dataclass
@@ -157,6 +157,14 @@ class Semidiscretization:
             p.delta = float(t(f.density_diffusion.delta))
         for d in range(self.ndims):
             p.acceleration[d] = float(f.acceleration[d])
+        if isinstance(se, StateEquationAdaptiveCole):
+            p.adaptive_sound_speed = 1
+            p.adaptive_params_f32 = int(se.param_eltype == np.float32)
+            if not (se.param_eltype == np.float32 or se.param_eltype == self.eltype):
+                raise ValueError("StateEquationAdaptiveCole: parameters must be Float32 or eltype(system)")
+            p.mach_number_target = float(se.mach_number_target)
+            p.min_sound_speed = float(se.min_sound_speed)
+            p.max_sound_speed = float(se.max_sound_speed)
         if isinstance(f.source_terms, SourceTermDamping):
             p.damping_coefficient = float(t(f.source_terms.damping_coefficient))
         return p
@@ -175,6 +183,11 @@ class Semidiscretization:
         p.reference_density = float(t(se.reference_density))
         p.background_pressure = float(t(se.background_pressure))
         p.pressure_offset = float(t(m.density_calculator.pressure_offset))
+        if isinstance(se, StateEquationAdaptiveCole):
+            if se is not self.fluid.state_equation:
+                raise ValueError("a boundary model with its own StateEquationAdaptiveCole is outside the "
+                                 "accelerated hot path (share the fluid's state equation object)")
+            p.sound_speed_from_fluid = 1
         return p
 
     def _create(self, u0_ode: np.ndarray):
@@ -263,6 +276,12 @@ class Semidiscretization:
 
     def synchronize(self):
         _lib.check(self._handle, _lib.load().tpb_synchronize(self._handle))
+
+    def sound_speed(self) -> float:
+        """`system_sound_speed(fluid)` as of the last kick (StateEquationAdaptiveCole), else the constant."""
+        out = C.c_double(0.0)
+        _lib.check(self._handle, _lib.load().tpb_get_sound_speed(self._handle, C.byref(out)))
+        return out.value
 
     def stats(self) -> _lib.Stats:
         st = _lib.Stats()

@@ -152,6 +152,8 @@ def solve(ode, alg: CarpenterKennedy2N54, *, dt: Optional[float] = None, save_ev
         dt = stepsize.dt(semi)
     if dt is None or not dt > 0:
         raise ValueError("a positive `dt` or a `StepsizeCallback` is required (fixed-step scheme)")
+    adaptive_eos = [s_.state_equation for s_ in semi.systems
+                    if isinstance(s_, WeaklyCompressibleSPHSystem) and hasattr(s_.state_equation, "update_speed_of_sound")]
     ops = _VecOps(semi)
     v = ode.v0.clone() if ops.device else ode.v0.copy()
     u = ode.u0.clone() if ops.device else ode.u0.copy()
@@ -176,6 +178,12 @@ def solve(ode, alg: CarpenterKennedy2N54, *, dt: Optional[float] = None, save_ev
             nf += 1
         t = stop if step != dt else t + step
         nsteps += 1
+        if stepsize is not None and adaptive_eos:
+            # StateEquationAdaptiveCole: the StepsizeCallback sees the speed of sound of the last
+            # right-hand-side evaluation (stepsize.jl:63-79, fluid.jl:199-239)
+            for se_ in adaptive_eos:
+                se_.sound_speed = se_.param_eltype.type(semi.sound_speed())
+            dt = stepsize.dt(semi)
         if save_everystep:
             dts.append(step)
         for i, p in enumerate(posts):
