@@ -6,7 +6,7 @@ its ctypes binding (_lib.py) and the host-side mirror of the reference interface
 Import it as `import trixiparticles.jl_b200` (the `trixiparticles/` shim next to this
 directory maps the dotted name onto this folder).
 """
-from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
+from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan, BernoulliPressureExtrapolation,
                     BoundaryModelDummyParticles, ContinuityDensity,
                     DensityDiffusionMolteniColagrossi, SchoenbergCubicSplineKernel,
                     SchoenbergQuarticSplineKernel, SchoenbergQuinticSplineKernel,
@@ -22,7 +22,8 @@ from .interpolation import interpolate_line, interpolate_points
 from .setups import InitialCondition, RectangularShape, RectangularTank, union
 
 __all__ = [
-    "AdamiPressureExtrapolation", "ArtificialViscosityMonaghan", "BoundaryModelDummyParticles",
+    "AdamiPressureExtrapolation", "ArtificialViscosityMonaghan", "BernoulliPressureExtrapolation",
+    "BoundaryModelDummyParticles",
     "ContinuityDensity", "DensityDiffusionMolteniColagrossi", "SchoenbergCubicSplineKernel",
     "SchoenbergQuarticSplineKernel", "SchoenbergQuinticSplineKernel",
     "SourceTermDamping", "StateEquationAdaptiveCole", "StateEquationCole", "SummationDensity",

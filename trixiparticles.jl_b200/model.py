@@ -198,6 +198,16 @@ class AdamiPressureExtrapolation:
     allow_loop_flipping: bool = True  # accepted for API parity; the GPU sweep is always wall-major
 
 
+@dataclass(frozen=True)
+class BernoulliPressureExtrapolation:
+    """dummy_particles.jl:150-187.  Its dynamic-pressure term applies to *moving* boundaries only
+    (`if system.ismoving[]`, dummy_particles.jl:680-694); for the static walls of the accelerated
+    path it is exactly `AdamiPressureExtrapolation` with the same `pressure_offset`."""
+    pressure_offset: float = 0.0
+    factor: float = 1.0
+    allow_loop_flipping: bool = True
+
+
 class WeaklyCompressibleSPHSystem:
     """wcsph/system.jl:65-225 -- only the options on the accelerated path are accepted;
     anything else raises `ValueError` (the reference throws `ArgumentError`)."""
@@ -256,8 +266,9 @@ class BoundaryModelDummyParticles:
     def __init__(self, initial_density, hydrodynamic_mass, density_calculator, smoothing_kernel,
                  smoothing_length, *, viscosity=None, state_equation=None, correction=None,
                  clip_negative_pressure=False, reference_particle_spacing=0.0):
-        if not isinstance(density_calculator, AdamiPressureExtrapolation):
-            raise ValueError("only `AdamiPressureExtrapolation` is on the accelerated path")
+        if not isinstance(density_calculator, (AdamiPressureExtrapolation, BernoulliPressureExtrapolation)):
+            raise ValueError("only `AdamiPressureExtrapolation` / `BernoulliPressureExtrapolation` are on "
+                             "the accelerated path")
         if viscosity is not None or correction is not None:
             raise ValueError("wall `viscosity`/`correction` are outside the accelerated hot path")
         if state_equation is None:
