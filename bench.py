@@ -77,7 +77,7 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
-def make_workload(name, eltype=None, coords=None, shuffle=False):
+def make_workload(name, eltype=None, coords=None, shuffle=False, adaptive=False):
     from trixiparticles.jl_b200 import examples
     ex, arg = WORKLOADS[name]
     dt = {None: None, "f32": np.float32, "f64": np.float64}
@@ -87,6 +87,8 @@ def make_workload(name, eltype=None, coords=None, shuffle=False):
     if dt[coords] is not None:
         kw["coordinates_eltype"] = dt[coords]
     if ex == "dam_break_3d":
+        if adaptive:
+            kw["adaptive_sound_speed"] = True
         fluid, wall, _ = examples.dam_break_3d(arg, **kw)
     else:
         fluid, wall, _ = examples.dam_break_2d(arg, **kw)
@@ -363,6 +365,11 @@ def run_single(args):
     variants = None
     if args.eltype is None and args.coords is None and tsize == 4 and csize == 4 and not args.no_variants:
         variants = {"f32_fields_f64_coordinates": run_variant(tp, torch, args, "f32", "f64")}
+        if WORKLOADS[args.workload][0] == "dam_break_3d":
+            # the script as shipped: Float64 coordinates + StateEquationAdaptiveCole (one max|v|
+            # reduction per kick, whose result is a host scalar as in the reference)
+            variants["as_shipped_f64_coordinates_adaptive_cole"] = run_variant(tp, torch, args, "f32", "f64",
+                                                                              adaptive=True)
 
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample
     cpu = None
@@ -393,9 +400,9 @@ def run_single(args):
     print(json.dumps(line))
 
 
-def run_variant(tp, torch, args, eltype, coords, steps=10):
+def run_variant(tp, torch, args, eltype, coords, steps=10, adaptive=False):
     """Device-resident kick!+drift! of the same workload in another precision set-up."""
-    fluid, wall, u, v = make_workload(args.workload, eltype, coords)
+    fluid, wall, u, v = make_workload(args.workload, eltype, coords, adaptive=adaptive)
     semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(
         device=0, ode_memory="device", interact_variant=args.variant))
     ode = tp.semidiscretize(semi, (0.0, 1.0))
