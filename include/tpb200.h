@@ -218,6 +218,12 @@ int32_t tpb_vec_fill(tpb_semi_t semi, int64_t n, int32_t eltype, double value, v
 int32_t tpb_vec_strided_max(tpb_semi_t semi, int64_t count, int32_t eltype, int32_t stride, int32_t offset,
                             const void *x, double *out_host);
 
+/* sqrt(mean_i (err_i / (abstol + reltol * max(|u_prev_i|, |u_i|)))^2) to the host (synchronises):
+ * the residual norm an adaptive integrator (RDPK3SpFSAL35 in the reference's examples) accepts or
+ * rejects a step on -- OrdinaryDiffEq `calculate_residuals` + `ODE_DEFAULT_NORM` */
+int32_t tpb_vec_wrms_norm(tpb_semi_t semi, int64_t n, int32_t eltype, const void *err, const void *u_prev,
+                          const void *u, double abstol, double reltol, double *out_host);
+
 /* Phase timing of `tpb_kick` with CUDA events on the handle's stream (the reference's
  * TimerOutputs sections "update systems and nhs" / "system interaction",
  * semidiscretization.jl:596-606).  `tpb_set_profiling(max_kicks)` arms recording for the next

@@ -59,6 +59,37 @@ def test_dam_break_2d_pressure_sensors_match_reference_traces():
         assert smooth.max() <= 0.1, (name, smooth.max())
 
 
+def test_device_vector_ops_match_numpy():
+    """`tpb_vec_*`: what a device-resident ODE-vector type binds (util.jl:183-303) -- axpby, fill, the
+    2N-storage stage, the strided maximum and the residual norm of an adaptive integrator."""
+    import ctypes as C
+    import torch
+    import trixiparticles.jl_b200 as tp
+    from trixiparticles.jl_b200 import _lib, examples
+    fluid, wall, _ = examples.dam_break_2d(20)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    tp.semidiscretize(semi, (0.0, 1.0))
+    L, h = _lib.load(), semi._handle
+    semi._bind_stream()
+    rng = np.random.default_rng(7)
+    for dt, eid, tol in ((torch.float64, _lib.F64, 1e-15), (torch.float32, _lib.F32, 1e-6)):
+        n = 100003
+        x, y, e = (torch.from_numpy(rng.standard_normal(n)).to("cuda", dt) for _ in range(3))
+        xn, yn, en = (t.cpu().numpy().astype(np.float64) for t in (x, y, e))
+        ptr = lambda t: C.c_void_p(t.data_ptr())
+        out = C.c_double(0.0)
+        _lib.check(h, L.tpb_vec_wrms_norm(h, n, eid, ptr(e), ptr(x), ptr(y), 1e-3, 1e-2, C.byref(out)))
+        ref = np.sqrt(np.mean((en / (1e-3 + 1e-2 * np.maximum(np.abs(xn), np.abs(yn)))) ** 2))
+        assert out.value == pytest.approx(ref, rel=1e-12 if eid == _lib.F64 else 1e-6)
+        _lib.check(h, L.tpb_vec_strided_max(h, n // 3, eid, 3, 1, ptr(x), C.byref(out)))
+        assert out.value == xn[1::3][: n // 3].max()
+        _lib.check(h, L.tpb_vec_axpby(h, n, eid, 0.5, ptr(x), -2.0, ptr(y)))
+        assert np.abs(y.cpu().numpy() - (0.5 * xn - 2.0 * yn)).max() <= tol * 10
+        _lib.check(h, L.tpb_vec_fill(h, n, eid, 1.25, ptr(x)))
+        assert bool((x == 1.25).all())
+    semi.close()
+
+
 def test_time_loop_host_and_device_memory_agree():
     """The same short run with host-resident (numpy) and device-resident (torch) ODE vectors."""
     import run_dam_break_validation as V

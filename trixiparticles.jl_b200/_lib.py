@@ -23,7 +23,7 @@ EXPORTS = [
     "tpb_synchronize", "tpb_set_stream", "tpb_get_stats", "tpb_get_sound_speed", "tpb_host_register",
     "tpb_host_unregister", "tpb_set_profiling", "tpb_get_phase_times",
     "tpb_set_fluid_count", "tpb_set_fluid_mass",
-    "tpb_vec_axpby", "tpb_vec_rk2n_stage", "tpb_vec_fill", "tpb_vec_strided_max",
+    "tpb_vec_axpby", "tpb_vec_rk2n_stage", "tpb_vec_fill", "tpb_vec_strided_max", "tpb_vec_wrms_norm",
     "tpb_peer_alloc", "tpb_peer_free", "tpb_peer_export", "tpb_peer_import", "tpb_peer_close",
     "tpb_halo_pack", "tpb_halo_install",
 ]
@@ -134,6 +134,8 @@ def load():
     L.tpb_vec_fill.restype = i32; L.tpb_vec_fill.argtypes = [p, i64, i32, d, p]
     L.tpb_vec_strided_max.restype = i32
     L.tpb_vec_strided_max.argtypes = [p, i64, i32, i32, i32, p, C.POINTER(d)]
+    L.tpb_vec_wrms_norm.restype = i32
+    L.tpb_vec_wrms_norm.argtypes = [p, i64, i32, p, p, p, d, d, C.POINTER(d)]
     L.tpb_set_fluid_count.restype = i32; L.tpb_set_fluid_count.argtypes = [p, i64, i64]
     L.tpb_set_fluid_mass.restype = i32; L.tpb_set_fluid_mass.argtypes = [p, i64, i64, p]
     _lib = L

@@ -1356,6 +1356,35 @@ int32_t tpb_vec_strided_max(tpb_semi_t semi, int64_t count, int32_t eltype, int3
     return TPB_OK;
 }
 
+int32_t tpb_vec_wrms_norm(tpb_semi_t semi, int64_t n, int32_t eltype, const void *err, const void *u_prev,
+                          const void *u, double abstol, double reltol, double *out_host)
+{
+    Semi *s = (Semi *)semi;
+    int rc = vec_check(s, n, eltype);
+    if (rc) return rc;
+    if (!out_host) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    *out_host = 0.0;
+    if (n == 0) return TPB_OK;
+    const int blocks = (int)std::min<int64_t>(vec_grid(n), 1024);
+    double *d_part = (double *)s->d_scratch;
+    if ((int64_t)blocks > std::max<int64_t>(std::max(s->n_f, s->n_w), 1))  // scratch holds max(n_f, n_w) doubles
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "vector too short for the reduction scratch space");
+    if (eltype == TPB_F32)
+        LAUNCH(*s, k_vec_wrms_partial<float>, blocks, 256, 0, n, (const float *)err, (const float *)u_prev,
+               (const float *)u, abstol, reltol, d_part);
+    else
+        LAUNCH(*s, k_vec_wrms_partial<double>, blocks, 256, 0, n, (const double *)err, (const double *)u_prev,
+               (const double *)u, abstol, reltol, d_part);
+    std::vector<double> part((size_t)blocks);
+    CUDA_TRY(s, cudaMemcpyAsync(part.data(), d_part, sizeof(double) * (size_t)blocks, cudaMemcpyDeviceToHost,
+                                s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    double sum = 0.0;
+    for (double p : part) sum += p;
+    *out_host = std::sqrt(sum / (double)n);
+    return TPB_OK;
+}
+
 int32_t tpb_set_profiling(tpb_semi_t semi, int32_t max_kicks)
 {
     Semi *s = (Semi *)semi;

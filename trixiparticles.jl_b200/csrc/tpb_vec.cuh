@@ -73,6 +73,31 @@ k_vec_strided_max(int64_t count, int stride, int offset, const T *__restrict__ x
     }
 }
 
+// partial[b] = sum over block b of (e_i / (abstol + reltol * max(|a_i|, |b_i|)))^2 in double: the
+// residual norm of an adaptive integrator (OrdinaryDiffEq `calculate_residuals` +
+// `ODE_DEFAULT_NORM`); the host adds the per-block partial sums in block order (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_vec_wrms_partial(int64_t n, const T *__restrict__ e, const T *__restrict__ a, const T *__restrict__ b,
+                   double abstol, double reltol, double *__restrict__ partial)
+{
+    double s = 0.0;
+    const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        const double r = (double)e[i] / (abstol + reltol * fmax(fabs((double)a[i]), fabs((double)b[i])));
+        s += r * r;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) s += ws[w];
+        partial[blockIdx.x] = s;
+    }
+}
+
 // max_i |v_i|^2 over the first ND entries of every row of v (update_speed_of_sound!,
 // wcsph/system.jl:307-315): products and sums separately rounded, left to right; the maximum of
 // non-negative IEEE numbers is the maximum of their bit patterns.
