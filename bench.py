@@ -247,6 +247,15 @@ def run_single(args):
     dv_d = torch.empty_like(v_d)
     du_d = torch.empty_like(u_d)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    if args.evolve > 0:
+        # the state after `--evolve` steps of the library's own time loop
+        # (CarpenterKennedy2N54, dt from StepsizeCallback(cfl = 0.9)): realistic disorder
+        from trixiparticles.jl_b200.time_integration import CarpenterKennedy2N54, StepsizeCallback, solve
+        dt_ = StepsizeCallback(cfl=0.9).dt(semi)
+        ode_e = tp.DynamicalODEProblem(ode.f1, ode.f2, v_d, u_d, (0.0, args.evolve * dt_), ode.p)
+        sol = solve(ode_e, CarpenterKennedy2N54(williamson_condition=False), dt=dt_)
+        u_d, v_d = sol.u.contiguous(), sol.v.contiguous()
+        semi.synchronize()
 
     def step():
         ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
@@ -477,6 +486,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the other precision set-ups")
     ap.add_argument("--shuffle", action="store_true", help="random particle order in the ODE vectors")
+    ap.add_argument("--evolve", type=int, default=0, help="time steps to run before measuring (evolved state)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
     ap.add_argument("--e2e-only", action="store_true", help="host-pointer (e2e) timing only (tuning runs)")
     args = ap.parse_args()
