@@ -29,7 +29,7 @@ def pressure_sensors(H, tank_right_wall_x):
     return out
 
 
-def run(t_end=None, eltype=np.float64, memory="device", sensors=False):
+def run(t_end=None, eltype=np.float64, memory="device", sensors=False, cuda_graph=False):
     fx = json.load(open(os.path.join(ROOT, "tests", "golden", "dam_break_2d_wcsph_40_trace.json")))
     H, g = 0.6, 9.81
     fluid, wall, tank = examples.dam_break_2d(40, alpha=fx["fluid"]["viscosity_model"]["alpha"],
@@ -45,7 +45,8 @@ def run(t_end=None, eltype=np.float64, memory="device", sensors=False):
         funcs.update(pressure_sensors(H, float(np.floor(5.366 * H / 0.015) * 0.015)))
     post = PostprocessCallback(dt=0.01 / np.sqrt(g / H), **funcs)
     t0 = time.perf_counter()
-    sol = solve(ode, CarpenterKennedy2N54(williamson_condition=False), callback=[step_cb, post])
+    sol = solve(ode, CarpenterKennedy2N54(williamson_condition=False), callback=[step_cb, post],
+                cuda_graph=cuda_graph)
     wall_s = time.perf_counter() - t0
     n = len(post.times)
     ref_t = np.array(fx["time"][:n])

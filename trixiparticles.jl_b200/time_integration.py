@@ -136,12 +136,15 @@ class _VecOps:
 
 
 def solve(ode, alg: CarpenterKennedy2N54, *, dt: Optional[float] = None, save_everystep: bool = False,
-          callback=(), maxiters: int = 10 ** 7) -> Solution:
+          callback=(), maxiters: int = 10 ** 7, cuda_graph: bool = False) -> Solution:
     """`solve(ode, CarpenterKennedy2N54(); dt, callback)` for the `DynamicalODEProblem` returned by
     `semidiscretize`: per stage dv = kick!(v, u), du = drift!(v, u), then the 2N-storage update of
     both partitions.  Fixed step from `dt` or a `StepsizeCallback`; `PostprocessCallback`s add
     tstops at multiples of their `dt`, which the step is shortened to hit (OrdinaryDiffEq's
-    `modify_dt_for_tstops!`)."""
+    `modify_dt_for_tstops!`).  `cuda_graph=True` (device-resident vectors): one full step of the
+    regular size -- all stages, about 15 kernel launches each -- is captured once into a CUDA graph
+    and replayed, so that small problems are not bound by launch latency; the shortened steps
+    before an output time run eagerly."""
     semi = ode.p.semi
     if callback is None:
         callback = ()
@@ -165,17 +168,36 @@ def solve(ode, alg: CarpenterKennedy2N54, *, dt: Optional[float] = None, save_ev
         p(t, v, u, semi)
     nsteps = nf = 0
     dts: List[float] = []
+    graph, warmed, graph_ok = None, False, bool(cuda_graph and ops.device)
+
+    def run_stages(step_):
+        for A, B, c in zip(alg.A, alg.B, alg.c):
+            ode.f1(dv, v, u, ode.p, t + c * step_)
+            ode.f2(du, v, u, ode.p, t + c * step_)
+            ops.rk2n_stage(A, B, step_, dv, tmp_v, v)
+            ops.rk2n_stage(A, B, step_, du, tmp_u, u)
+
     while t < t_end and nsteps < maxiters:
         stop = min([t_end] + next_stop)
         step = dt
         if stop - t <= step * (1 + 1e-10):
             step = stop - t
-        for A, B, c in zip(alg.A, alg.B, alg.c):
-            ode.f1(dv, v, u, ode.p, t + c * step)
-            ode.f2(du, v, u, ode.p, t + c * step)
-            ops.rk2n_stage(A, B, step, dv, tmp_v, v)
-            ops.rk2n_stage(A, B, step, du, tmp_u, u)
-            nf += 1
+        if graph_ok and step == dt and not adaptive_eos:
+            if graph is None:
+                if not warmed:
+                    run_stages(step)       # first regular step eagerly (one-time kernel attributes)
+                    warmed = True
+                else:
+                    import torch
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        run_stages(step)       # recorded, not executed
+                    graph.replay()
+            else:
+                graph.replay()
+        else:
+            run_stages(step)
+        nf += len(alg.A)
         t = stop if step != dt else t + step
         nsteps += 1
         if stepsize is not None and adaptive_eos:
