@@ -181,11 +181,15 @@ def run_reference(args):
         return
     from oracle import adapter, oracle as O
     O.build()
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    _kick = adapter.kick
+    adapter_kick = lambda *a, **k: _kick(*a, nthreads=nthreads, **k)
     name = args.workload
     fluid, wall, u, v = make_workload(name)
     nd = fluid.ndims
     t0 = time.perf_counter()
-    adapter.kick(fluid, wall, u, v)
+    adapter_kick(fluid, wall, u, v)
     t1 = time.perf_counter() - t0
     sample = f"full workload {name}: {fluid.nparticles} fluid + {wall.nparticles} wall particles per step"
     if (args.steps + args.warmup) * t1 > 240.0 and name != "dam_break_3d_250k":
@@ -194,15 +198,15 @@ def run_reference(args):
         sample = (f"reduced lattice {small} of the same geometry ({fluid.nparticles} fluid + "
                   f"{wall.nparticles} wall per step) because the full {name} would exceed the time bound")
     for _ in range(args.warmup):
-        adapter.kick(fluid, wall, u, v)
+        adapter_kick(fluid, wall, u, v)
         O.drift(v, nd, u.dtype)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        adapter.kick(fluid, wall, u, v)
+        adapter_kick(fluid, wall, u, v)
         O.drift(v, nd, u.dtype)
     dt = time.perf_counter() - t0
     value = fluid.nparticles * args.steps / dt
-    cores = O.max_threads()
+    cores = nthreads
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
