@@ -169,6 +169,7 @@ def test_chunked_staging_small_shared_memory(oracle, monkeypatch, smem, list_len
     monkeypatch.setenv("TPB_TILE_SMEM", str(smem))
     monkeypatch.setenv("TPB_TILE_LIST", str(list_len))
     monkeypatch.setenv("TPB_TILE_LIST_SPLIT", str(list_len))
+    monkeypatch.setenv("TPB_TILE_LIST_SPLIT2", str(list_len))
     fluid, wall, _ = examples.dam_break_3d(0.05)
     u, v = examples.perturbed_state(fluid)
     check_against_oracle(fluid, wall, u, v)

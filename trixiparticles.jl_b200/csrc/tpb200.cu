@@ -253,8 +253,8 @@ template <int ND, typename T, typename CT>
 struct Ops {
     // threads per target particle in the tile sweeps (tpb_tiles.cuh): the Float32 kernels (with
     // Float32 or Float64 coordinates) fit 2 x 384 threads into the register file; the Float64
-    // ones keep one thread per target
-    static constexpr int KS = std::is_same<T, float>::value ? TPB_SPLIT : 1;
+    // ones (106 registers) two
+    static constexpr int KS = std::is_same<T, float>::value ? TPB_SPLIT : 2;
     static constexpr int nv(const Semi &s) { return s.fp.density_calculator == TPB_DENSITY_SUMMATION ? ND : ND + 1; }
 
     // ---- counting sort of one point set into the shared grid: key/slot/count/scan/scatter
@@ -412,8 +412,9 @@ struct Ops {
         k.p_off = (T)s.wp.pressure_offset;
         k.clip = s.wp.clip_negative_pressure;
         if (use_tiles(s)) {
-            const int list_len = KS > 1 ? s.tiles.adami_list_len : s.tiles.list(KS);
-            const int budget = KS > 1 ? std::min(s.tiles.adami_smem_budget, s.tiles.smem_budget) : s.tiles.smem_budget;
+            constexpr bool SMALL = KS > 1 && sizeof(T) == 4;  // three blocks per SM (see k_adami_tiles)
+            const int list_len = SMALL ? s.tiles.adami_list_len : s.tiles.list(KS);
+            const int budget = SMALL ? std::min(s.tiles.adami_smem_budget, s.tiles.smem_budget) : s.tiles.smem_budget;
             const int cap = tile_capacity<T, CT>(budget, list_len, KS);
             const size_t smem = tile_smem_bytes<T, CT>(cap, list_len, KS);
             int grid = s.tiles.max_wtiles;  // one block per tile slot; surplus blocks exit at once

@@ -707,21 +707,21 @@ __device__ __forceinline__ void named_barrier(int id)
 // threadIdx.x < TILE_TB hold val = ((val_0 + val_1) + val_2) ...; the other threads are done.
 // Only the KS warps that share 32 targets meet (named barrier 1 + warp % 4): the writers
 // arrive and leave, the reader waits for them -- nobody waits for the slowest warp of the block.
-// Scratch space without extra shared memory: the 16-bit list slots of entry e of the threads
-// 2m and 2m + 1 form one aligned 32-bit word; thread 2m parks its values in the words of the
-// entries 0..3, thread 2m + 1 in those of the entries 4..7 -- slots only this pair of lanes
-// ever touches, so warps that are still sweeping are not disturbed.
+// Scratch space without extra shared memory: the 16-bit list slots of entry e of W = sizeof(T) / 2
+// neighbouring threads (a pair for Float32, four for Float64) form one aligned word of T; thread
+// j of such a group parks its values in the words of the entries j * 4 .. j * 4 + 3 -- slots
+// only this group of lanes ever touches, so warps that are still sweeping are not disturbed.
 template <int KS, int NVAL, typename T, typename CT>
 __device__ __forceinline__ void tile_reduce(TileSmem<T, CT> &sm, T (&val)[NVAL])
 {
     static_assert(NVAL <= TILE_RED_VALS, "tile_reduce: scratch space too small");
     if constexpr (KS > 1) {
-        static_assert(sizeof(T) == 4, "tile_reduce: 32-bit values only");
         constexpr int NT = KS * TILE_TB;
+        constexpr int W = (int)sizeof(T) / 2;  // 16-bit slots per value
         const int ti = threadIdx.x % TILE_TB, kg = threadIdx.x / TILE_TB;
         const int bar_id = 1 + ti / 32;
         auto slot = [&](int tid, int n) {
-            return reinterpret_cast<T *>(sm.list + (n + TILE_RED_VALS * (tid & 1)) * NT + (tid & ~1));
+            return reinterpret_cast<T *>(sm.list + (n + TILE_RED_VALS * (tid % W)) * NT + (tid - tid % W));
         };
         __syncwarp();  // both lanes of a pair have drained their lists
         if (kg > 0) {
@@ -948,7 +948,7 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
 // grid (0.100 vs 0.113 ms).
 constexpr int ADAMI_BLOCKS_PER_SM = 3;
 template <int KS, int ND, typename T, typename CT, int KERNEL>
-__global__ void __launch_bounds__(KS * TILE_TB, KS > 1 ? ADAMI_BLOCKS_PER_SM : 2)
+__global__ void __launch_bounds__(KS * TILE_TB, (KS > 1 && sizeof(T) == 4) ? ADAMI_BLOCKS_PER_SM : 2)
 k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__restrict__ active,
               const int4 *__restrict__ tile_desc, const int4 *__restrict__ tile_ext,
               const int2 *__restrict__ tile_rng, const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
@@ -1095,8 +1095,9 @@ struct TileState {
     int max_ftiles = 0, max_wtiles = 0;
     int smem_budget = 112 * 1024;  // bytes per block: two blocks per SM
     int list_len = 160;            // private list entries per thread (one flush per sweep in 3-D)
-    int list_len_split = 64;       // the same with TPB_SPLIT threads per target
-    int list(int ks) const { return ks > 1 ? list_len_split : list_len; }
+    int list_len_split = 64;       // the same with TPB_SPLIT (three) threads per target
+    int list_len_split2 = 96;      // two threads per target (Float64)
+    int list(int ks) const { return ks > 2 ? list_len_split : ks == 2 ? list_len_split2 : list_len; }
     // Adami sweep with TPB_SPLIT threads per target: three blocks per SM, short lists
     int adami_smem_budget = 74 * 1024, adami_list_len = 32;
 };
@@ -1112,6 +1113,8 @@ inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
     if (const char *e = getenv("TPB_ADAMI_LIST")) t.adami_list_len = atoi(e);
     t.list_len = std::max(t.list_len, 8);
     t.list_len_split = std::max(t.list_len_split, 8);
+    if (const char *e = getenv("TPB_TILE_LIST_SPLIT2")) t.list_len_split2 = atoi(e);
+    t.list_len_split2 = std::max(t.list_len_split2, 16);  // tile_reduce: 4 values x 4 threads per word
     t.adami_list_len = std::max(t.adami_list_len, 8);
     if (t.smem_budget > 227 * 1024) t.smem_budget = 227 * 1024;
     t.max_ftiles = (int)((n_f + TILE_TB - 1) / TILE_TB) + nrows;
