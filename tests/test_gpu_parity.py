@@ -301,6 +301,66 @@ def test_kick_fluid_only_and_source_damping(oracle):
     check_against_oracle(fluid, None, u, v)
 
 
+@pytest.mark.parametrize("nd,eltype,seed", [(2, np.float64, 1), (3, np.float32, 2), (3, np.float64, 3),
+                                            (2, np.float32, 4)])
+@pytest.mark.parametrize("smem", [None, 16 * 1024])
+def test_random_clustered_clouds(oracle, monkeypatch, nd, eltype, seed, smem):
+    """Irregular particle sets: a sparse random cloud plus dense clumps (cells with several hundred
+    particles: tiles inside one cell, rows longer than the staging area, lists that overflow), a
+    ragged wall, random masses / densities / velocities, a random kernel and viscosity model.
+    Parity and neighbour sets against the oracle, also with a 16 KB shared-memory budget (pieces
+    of oversized rows)."""
+    if smem is not None:
+        monkeypatch.setenv("TPB_TILE_SMEM", str(smem))
+        for name in ("TPB_TILE_LIST", "TPB_TILE_LIST_SPLIT", "TPB_TILE_LIST_SPLIT2"):
+            monkeypatch.setenv(name, "16")
+    rng = np.random.default_rng(seed)
+    dx = 0.02
+    h = 1.3 * dx
+    n_cloud, n_clump = (1500, 700) if nd == 3 else (700, 500)
+    box = np.array([1.0, 0.6, 0.4][:nd])
+    cloud = rng.uniform(0.0, 1.0, (n_cloud, nd)) * box
+    centres = rng.uniform(0.2, 0.8, (3, nd)) * box
+    clumps = np.concatenate([c + rng.normal(0.0, 0.6 * h, (n_clump, nd)) for c in centres])
+    x = np.concatenate([cloud, clumps]).astype(eltype)
+    n = len(x)
+    rho = (1000.0 * (1 + rng.uniform(-0.02, 0.02, n))).astype(eltype)
+    mass = (1000.0 * dx ** nd * (1 + rng.uniform(-0.3, 0.3, n))).astype(eltype)
+    vel = rng.uniform(-1.0, 1.0, (n, nd)).astype(eltype)
+    ic = tp.InitialCondition(coordinates=x, velocity=vel, mass=mass, density=rho,
+                             pressure=np.zeros(n, dtype=eltype), particle_spacing=dx)
+    kernel = [tp.WendlandC2Kernel, tp.SchoenbergCubicSplineKernel, tp.WendlandC6Kernel,
+              tp.SchoenbergQuinticSplineKernel][seed % 4](nd)
+    visc = [tp.ArtificialViscosityMonaghan(alpha=0.05, beta=0.1), tp.ViscosityAdami(nu=0.01),
+            tp.ViscosityMorris(nu=0.02), None][seed % 4]
+    se = tp.StateEquationCole(sound_speed=20.0, reference_density=1000.0, exponent=7)
+    fluid = tp.WeaklyCompressibleSPHSystem(ic, smoothing_kernel=kernel, smoothing_length=h,
+                                           density_calculator=tp.ContinuityDensity(), state_equation=se,
+                                           viscosity=visc,
+                                           density_diffusion=tp.DensityDiffusionMolteniColagrossi(delta=0.1),
+                                           acceleration=tuple([0.0] * (nd - 1) + [-9.81]))
+    # ragged wall: random points below the box, some far from any fluid
+    nw = 900
+    xw = (rng.uniform(-0.3, 1.3, (nw, nd)) * box).astype(eltype)
+    xw[:, -1] = rng.uniform(-3 * dx, 0.0, nw).astype(eltype)
+    icw = tp.InitialCondition(coordinates=xw, velocity=np.zeros((nw, nd), dtype=eltype),
+                              mass=np.full(nw, 1000.0 * dx ** nd, dtype=eltype),
+                              density=np.full(nw, 1000.0, dtype=eltype), pressure=np.zeros(nw, dtype=eltype),
+                              particle_spacing=dx)
+    model = tp.BoundaryModelDummyParticles(icw.density, icw.mass, tp.AdamiPressureExtrapolation(pressure_offset=5.0),
+                                           kernel, h, state_equation=se)
+    wall = tp.WallBoundarySystem(icw, model)
+    v = np.concatenate([vel, rho[:, None]], axis=1).astype(eltype)
+    check_against_oracle(fluid, wall, x, v, tol_scale=4.0)     # sums over several hundred neighbours
+    semi, ode = make_semi(fluid, wall)
+    R = float(tp.compact_support(kernel, eltype(h)))
+    for (a, b_, xa, xb) in [(fluid, fluid, x, x), (fluid, wall, x, xw), (wall, fluid, xw, x)]:
+        gi, gj = semi.neighbor_pairs(a, b_, x.reshape(-1).copy())
+        oi, oj = oracle.neighbor_pairs(xa, xb, R, dtype=eltype, grid=True)
+        assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
+    semi.close()
+
+
 def test_interaction_matrix_disables_wall(oracle):
     """interaction_matrix[fluid, wall] = false (semidiscretization.jl:157-187)."""
     fluid, wall, _ = examples.hydrostatic_water_column_2d(eltype=np.float64, coordinates_eltype=np.float64)
