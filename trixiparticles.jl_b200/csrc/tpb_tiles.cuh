@@ -44,7 +44,10 @@
 
 namespace tpb {
 
-constexpr int TILE_TB = 128;      // target particles per tile; a block has KS * TILE_TB threads
+#ifndef TPB_TILE_TB
+#define TPB_TILE_TB 128
+#endif
+constexpr int TILE_TB = TPB_TILE_TB;  // target particles per tile; a block has KS * TILE_TB threads
 constexpr int TILE_MAXSEG = 12;   // segments per staged chunk (>= 3^(ND-1))
 constexpr int TILE_TABW = 16;     // cell_start entries per neighbour row kept in shared memory
 
