@@ -59,6 +59,35 @@ def test_dam_break_2d_pressure_sensors_match_reference_traces():
         assert smooth.max() <= 0.1, (name, smooth.max())
 
 
+def test_hydrostatic_water_column_2d_float32_stays_at_rest():
+    """BASELINE config 2 (examples/fluid/hydrostatic_water_column_2d.jl in Float32, the case of
+    test/examples/gpu.jl:313-394 "WCSPH default"): 0.3 s of the time loop from the hydrostatic
+    initial condition.  The column must stay a column: the free surface within a third of a
+    particle spacing, velocities below 2 % of the speed of sound, the pressure at the bottom
+    within 20 % of rho g H, every particle inside the tank."""
+    import trixiparticles.jl_b200 as tp
+    from trixiparticles.jl_b200 import examples
+    from trixiparticles.jl_b200.time_integration import CarpenterKennedy2N54, StepsizeCallback, solve
+    fluid, wall, tank = examples.hydrostatic_water_column_2d()
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 0.3))
+    sol = solve(ode, CarpenterKennedy2N54(williamson_condition=False), callback=[StepsizeCallback(cfl=0.9)],
+                cuda_graph=True)
+    assert sol.retcode == "Success"
+    u = sol.u.cpu().numpy().reshape(-1, 2)
+    v = sol.v.cpu().numpy().reshape(-1, 3)
+    dx, H, c = 0.05, 0.9, 10.0
+    assert np.isfinite(u).all() and np.isfinite(v).all()
+    assert u[:, 0].min() > 0.0 and u[:, 0].max() < 1.0 and u[:, 1].min() > 0.0
+    assert abs(u[:, 1].max() - (H - dx / 2)) < dx / 3
+    assert np.abs(v[:, :2]).max() < 0.02 * c
+    p = semi.system_field(fluid, "pressure")
+    bottom = u[:, 1] < dx
+    # the undamped column rings acoustically around the hydrostatic value (+10 % at t = 0.3 s)
+    assert p[bottom].mean() == pytest.approx(1000.0 * 9.81 * (H - dx / 2), rel=0.2)
+    semi.close()
+
+
 def test_device_vector_ops_match_numpy():
     """`tpb_vec_*`: what a device-resident ODE-vector type binds (util.jl:183-303) -- axpby, fill, the
     2N-storage stage, the strided maximum and the residual norm of an adaptive integrator."""
