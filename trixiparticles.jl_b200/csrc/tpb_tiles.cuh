@@ -946,7 +946,7 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
 // the kernel is bound by the latency of getting a tile started: warp 0 issues the TMA copies
 // straight from the descriptors while the other warps load their particles, and the Float32
 // version keeps three blocks per SM resident (launch bounds cap it at 56 registers, shared memory
-// at 74 KB).  Blocks walk the active list with a grid stride; with the default grid (one block per
+// at 72 KB).  Blocks walk the active list with a grid stride; with the default grid (one block per
 // tile slot) the hardware scheduler balances the tiles, which measured better than a persistent
 // grid (0.100 vs 0.113 ms).
 constexpr int ADAMI_BLOCKS_PER_SM = 3;
@@ -1102,7 +1102,7 @@ struct TileState {
     int list_len_split2 = 96;      // two threads per target (Float64)
     int list(int ks) const { return ks > 2 ? list_len_split : ks == 2 ? list_len_split2 : list_len; }
     // Adami sweep with TPB_SPLIT threads per target: three blocks per SM, short lists
-    int adami_smem_budget = 74 * 1024, adami_list_len = 32;
+    int adami_smem_budget = 72 * 1024, adami_list_len = 32;  // 3 x (72 + 1) KB fit the 228 KB of an SM
 };
 
 inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
