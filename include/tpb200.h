@@ -68,6 +68,8 @@ extern "C" {
 #define TPB_FIELD_PRESSURE 0
 #define TPB_FIELD_DENSITY 1
 #define TPB_FIELD_VOLUME 2 /* wall: boundary_model.cache.volume */
+#define TPB_FIELD_WALL_VELOCITY 3 /* no-slip wall: boundary_model.cache.wall_velocity, ND x n values
+                                   * (dummy_particles.jl:299-307) */
 
 typedef struct tpb_semi_s *tpb_semi_t; /* opaque; mirrors `Semidiscretization` */
 
@@ -126,6 +128,14 @@ typedef struct {
     double smoothing_length;
     double sound_speed, exponent, reference_density, background_pressure;
     double pressure_offset;
+    /* `BoundaryModelDummyParticles(...; viscosity)` (dummy_particles.jl:52-77): TPB_VISCOSITY_NONE =
+     * free-slip wall; any model = no-slip wall: the wall velocity v_w = -sum_f v_f W / sum_f W
+     * (compute_wall_velocity!, dummy_particles.jl:710-758) enters the model's viscous term of the
+     * fluid (viscous_velocity, wall_boundary/system.jl:148-163).  Monaghan: alpha, beta, epsilon;
+     * Morris / Adami: alpha = kinematic viscosity nu, epsilon. */
+    int32_t has_viscosity;
+    int32_t reserved;
+    double alpha, beta, epsilon;
 } tpb_wall_params;
 
 /* launch/traffic accounting of the last kick (what bench.py reports as gpu_launches) */

@@ -55,6 +55,14 @@ def wall_params(wall) -> O.WallParams:
     p.reference_density = float(t(se.reference_density))
     p.background_pressure = float(t(se.background_pressure))
     p.pressure_offset = float(t(m.density_calculator.pressure_offset))
+    visc = getattr(m, "viscosity", None)
+    if visc is not None:   # no-slip wall
+        p.has_viscosity = int(getattr(visc, "viscosity_id", 1))
+        if p.has_viscosity == 1:
+            p.visc_alpha, p.visc_beta = float(t(visc.alpha)), float(t(visc.beta))
+        else:
+            p.visc_alpha = float(t(visc.nu))
+        p.visc_epsilon = float(t(visc.epsilon))
     return p
 
 

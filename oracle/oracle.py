@@ -45,6 +45,8 @@ class WallParams(C.Structure):
         ("smoothing_length", C.c_double), ("sound_speed", C.c_double),
         ("exponent", C.c_double), ("reference_density", C.c_double),
         ("background_pressure", C.c_double), ("pressure_offset", C.c_double),
+        ("has_viscosity", C.c_int32), ("reserved1", C.c_int32),
+        ("visc_alpha", C.c_double), ("visc_beta", C.c_double), ("visc_epsilon", C.c_double),
     ]
 
 
@@ -100,6 +102,9 @@ def _declare(L):
         f = getattr(L, f"orc_kick_{s}"); f.restype = i
         f.argtypes = [C.POINTER(FluidParams), C.POINTER(WallParams), i64, p, i64, p, p, p, p, p,
                       p, p, p, p, p, i, i]
+        f = getattr(L, f"orc_kick_noslip_{s}"); f.restype = i
+        f.argtypes = [C.POINTER(FluidParams), C.POINTER(WallParams), i64, p, i64, p, p, p, p, p,
+                      p, p, p, p, p, p, i, i]
         f = getattr(L, f"orc_drift_{s}"); f.restype = None
         f.argtypes = [i, i, i64, p, p]
     L.orc_max_threads.restype = i
@@ -223,12 +228,13 @@ def kick(fp: FluidParams, wp, mass_f, coords_w, mass_w, v_ode, u_ode, dtype, use
     out = dict(
         dv=np.zeros((n_f, nv), dtype=dtype), pressure=np.zeros(n_f, dtype=dtype),
         density=np.zeros(n_f, dtype=dtype), wall_pressure=np.zeros(n_w, dtype=dtype),
-        wall_density=np.zeros(n_w, dtype=dtype), wall_volume=np.zeros(n_w, dtype=dtype))
-    rc = getattr(lib(), f"orc_kick_{s}")(
+        wall_density=np.zeros(n_w, dtype=dtype), wall_volume=np.zeros(n_w, dtype=dtype),
+        wall_velocity=np.zeros((n_w, nd), dtype=dtype))
+    rc = getattr(lib(), f"orc_kick_noslip_{s}")(
         C.byref(fp), wpp, n_f, _ptr(mass_f), n_w, _ptr(coords_w), _ptr(mass_w), _ptr(v_ode),
         _ptr(u_ode), _ptr(out["dv"]), _ptr(out["pressure"]), _ptr(out["density"]),
         _ptr(out["wall_pressure"]), _ptr(out["wall_density"]), _ptr(out["wall_volume"]),
-        int(bool(use_grid)), int(nthreads))
+        _ptr(out["wall_velocity"]), int(bool(use_grid)), int(nthreads))
     if rc != 0:
         raise RuntimeError(f"orc_kick failed: {rc}")
     return out

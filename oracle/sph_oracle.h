@@ -65,6 +65,11 @@ typedef struct {
     double smoothing_length;
     double sound_speed, exponent, reference_density, background_pressure;
     double pressure_offset;
+    /* boundary_model.viscosity (dummy_particles.jl:52-77): nothing = free-slip; any model = no-slip
+     * wall (compute_wall_velocity!, :710-758).  Morris / Adami carry nu in `visc_alpha`. */
+    int32_t has_viscosity; /* ORC_VISCOSITY_* */
+    int32_t reserved1;
+    double visc_alpha, visc_beta, visc_epsilon;
 } orc_wall_params;
 
 #define ORC_DECLARE(SUF, T, CT)                                                              \
@@ -99,6 +104,12 @@ typedef struct {
                        const T *v_ode, const CT *u_ode, T *dv_ode, T *pressure_f,            \
                        T *density_f, T *pressure_w, T *density_w, T *volume_w,               \
                        int use_grid, int nthreads);                                          \
+    /* as orc_kick; wall_velocity_w (ND x n_w, may be NULL): boundary_model.cache.wall_velocity */ \
+    int orc_kick_noslip_##SUF(const orc_fluid_params *fp, const orc_wall_params *wp, int64_t n_f, \
+                       const T *mass_f, int64_t n_w, const CT *coords_w, const T *mass_w,    \
+                       const T *v_ode, const CT *u_ode, T *dv_ode, T *pressure_f,            \
+                       T *density_f, T *pressure_w, T *density_w, T *volume_w,               \
+                       T *wall_velocity_w, int use_grid, int nthreads);                      \
     void orc_drift_##SUF(int ndims, int nvars_v, int64_t n_f, const T *v_ode, CT *du_ode);
 
 ORC_DECLARE(f64, double, double)

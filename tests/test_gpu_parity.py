@@ -45,6 +45,8 @@ def run_kick(fluid, wall, u, v, **backend):
         out.update(wall_pressure=semi.system_field(wall, "pressure"),
                    wall_density=semi.system_field(wall, "density"),
                    wall_volume=semi.system_field(wall, "volume"))
+        if wall.boundary_model.viscosity is not None:
+            out["wall_velocity"] = semi.system_field(wall, "wall_velocity")
     semi.close()
     return out
 
@@ -63,6 +65,8 @@ def check_against_oracle(fluid, wall, u, v, tol_scale=1.0, **backend):
         errs["wall_pressure"] = rel_inf(got["wall_pressure"], ref["wall_pressure"])
         errs["wall_density"] = rel_inf(got["wall_density"], ref["wall_density"])
         errs["wall_volume"] = rel_inf(got["wall_volume"], ref["wall_volume"])
+        if "wall_velocity" in got:
+            errs["wall_velocity"] = rel_inf(got["wall_velocity"], ref["wall_velocity"])
     assert np.isfinite(got["dv"]).all()
     bad = {k: e for k, e in errs.items() if not e <= tol}
     assert not bad, f"parity above {tol:g}: {bad} (all: {errs})"
@@ -244,6 +248,88 @@ def test_kick_viscosity_morris_adami(oracle, viscosity_cls, config):
     u, v = examples.perturbed_state(fluid)
     check_against_oracle(fluid, wall, u, v)
     check_against_oracle(fluid, wall, u, v, interact_variant=1)
+
+
+@pytest.mark.parametrize("wall_viscosity", ["fluid", "ViscosityAdami", "ViscosityMorris", "Monaghan_beta"])
+@pytest.mark.parametrize("config", ["hydrostatic_2d_f32", "dam_break_2d_f64", "dam_break_3d_f32",
+                                    "dam_break_3d_f32_f64_coordinates", "dam_break_3d_f64"])
+def test_kick_no_slip_wall(oracle, wall_viscosity, config):
+    """No-slip wall: `BoundaryModelDummyParticles(...; viscosity=model)` (`viscosity_wall = viscosity_fluid`
+    in examples/fluid/dam_break_2d.jl:78-80).  Wall velocity (dummy_particles.jl:710-758, pinned in the
+    oracle to the reference's known answers) and the wall model's viscous term of the fluid
+    (viscosity.jl:9-40; wall_boundary/system.jl:148-163), tile sweep and per-particle sweep."""
+    if config == "hydrostatic_2d_f32":
+        fluid, wall, _ = examples.hydrostatic_water_column_2d()
+    elif config == "dam_break_2d_f64":
+        fluid, wall, _ = examples.dam_break_2d(20)
+    elif config == "dam_break_3d_f32":
+        fluid, wall, _ = examples.dam_break_3d(0.1)
+    elif config == "dam_break_3d_f32_f64_coordinates":
+        fluid, wall, _ = examples.dam_break_3d(0.1, coordinates_eltype=np.float64)
+    else:
+        fluid, wall, _ = examples.dam_break_3d(0.1, eltype=np.float64)
+    if wall_viscosity == "fluid":
+        wall.boundary_model.viscosity = fluid.viscosity          # ArtificialViscosityMonaghan(alpha)
+    elif wall_viscosity == "Monaghan_beta":
+        wall.boundary_model.viscosity = tp.ArtificialViscosityMonaghan(alpha=0.1, beta=0.5, epsilon=0.02)
+    else:
+        # nu_a from the fluid's Monaghan model (alpha h c / (2 ND + 4)), nu_b from the wall's
+        wall.boundary_model.viscosity = getattr(tp, wall_viscosity)(nu=0.01)
+    assert fluid.viscosity is not None
+    u, v = examples.perturbed_state(fluid)
+    errs = check_against_oracle(fluid, wall, u, v)
+    assert "wall_velocity" in errs
+    check_against_oracle(fluid, wall, u, v, interact_variant=1)
+    # the viscous wall term is really there: the free-slip result differs
+    free = run_kick(fluid, examples_free_slip(wall), u, v)
+    noslip = run_kick(fluid, wall, u, v)
+    assert rel_inf(noslip["dv"][:, :fluid.ndims], free["dv"][:, :fluid.ndims]) > 1e-4
+    assert np.array_equal(noslip["dv"][:, fluid.ndims:], free["dv"][:, fluid.ndims:])  # continuity untouched
+
+
+def examples_free_slip(wall):
+    import copy
+    w = copy.copy(wall)
+    w.boundary_model = copy.copy(wall.boundary_model)
+    w.boundary_model.viscosity = None
+    return w
+
+
+def test_no_slip_wall_known_answers():
+    """The reference's own wall-velocity test on the device (test/schemes/boundary/dummy_particles/
+    dummy_particles.jl:104-303): constant profile => v_wall = -v_fluid; staggered profile => the
+    explicit weights."""
+    dx, h = 0.1, 0.12
+    rows = [tp.RectangularShape(dx, (10, 1), (0.0, y), density=257.0) for y in (0.2, 0.1, 0.0)]
+    boundary = tp.union(*rows)
+    fluid_ic = tp.RectangularShape(dx, (16, 5), (-0.3, 0.3), density=257.0, loop_order="x_first")
+    se = tp.StateEquationCole(sound_speed=10.0, reference_density=257.0, exponent=7)
+    kernel = tp.SchoenbergCubicSplineKernel(2)
+    fluid = tp.WeaklyCompressibleSPHSystem(fluid_ic, smoothing_kernel=kernel, smoothing_length=h,
+                                           density_calculator=tp.ContinuityDensity(), state_equation=se,
+                                           viscosity=tp.ViscosityAdami(nu=1e-6))
+    model = tp.BoundaryModelDummyParticles(boundary.density, boundary.mass, tp.AdamiPressureExtrapolation(),
+                                           kernel, h, state_equation=se, viscosity=tp.ViscosityAdami(nu=1e-6))
+    wall = tp.WallBoundarySystem(boundary, model)
+    n = fluid_ic.nparticles
+    rho = np.full((n, 1), 257.0)
+    for variant in (0, 1):
+        for v_fluid in [(0.0, -1.0), (1.0, 1.0), (0.7, 0.2)]:
+            v = np.concatenate([np.tile(np.array(v_fluid), (n, 1)), rho], axis=1)
+            got = run_kick(fluid, wall, fluid_ic.coordinates, v, interact_variant=variant)["wall_velocity"]
+            expected = np.zeros((30, 2))
+            expected[:20] = -np.array(v_fluid)
+            np.testing.assert_allclose(got, expected, rtol=1e-8, atol=1e-14)
+        for scale in (1.0, 0.7, 67.5):
+            vel = np.where((np.arange(1, n + 1) % 2 == 1)[:, None], scale, 0.0) * np.ones((n, 2))
+            got = run_kick(fluid, wall, fluid_ic.coordinates, np.concatenate([vel, rho], axis=1),
+                           interact_variant=variant)["wall_velocity"]
+            expected = np.zeros((30, 2))
+            for i in range(1, 11):
+                expected[i - 1] = -(0.42040669416720744 if i % 2 == 1 else 0.5795933058327924) * scale
+            for i in range(11, 21):
+                expected[i - 1] = -(0.12101100073462243 if i % 2 == 1 else 0.8789889992653775) * scale
+            np.testing.assert_allclose(got, expected, rtol=1e-11, atol=1e-13)
 
 
 @pytest.mark.parametrize("eltype,cdtype", [(np.float32, np.float32), (np.float32, np.float64),

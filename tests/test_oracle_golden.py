@@ -174,6 +174,98 @@ def test_adami_weights_known_answers(oracle, scale):
         assert np.all(out["wall_volume"][:20] > 0.0)
 
 
+def _no_slip_fixture():
+    # test/schemes/boundary/dummy_particles/dummy_particles.jl:104-178: ViscosityAdami(nu=1e-6) wall
+    boundary, fluid_ic = _adami_wall_velocity_fixture()
+    h = 1.2 * 0.1
+    se = tp.StateEquationCole(sound_speed=10.0, reference_density=257.0, exponent=7)
+    kernel = tp.SchoenbergCubicSplineKernel(2)
+    fluid = tp.WeaklyCompressibleSPHSystem(fluid_ic, smoothing_kernel=kernel, smoothing_length=h,
+                                           density_calculator=tp.ContinuityDensity(),
+                                           state_equation=se, viscosity=tp.ViscosityAdami(nu=1e-6))
+    model = tp.BoundaryModelDummyParticles(boundary.density, boundary.mass,
+                                           tp.AdamiPressureExtrapolation(), kernel, h,
+                                           state_equation=se, viscosity=tp.ViscosityAdami(nu=1e-6))
+    return fluid_ic, fluid, tp.WallBoundarySystem(boundary, model)
+
+
+# dummy_particles.jl:180-233: constant fluid velocity => v_wall = -v_fluid inside the compact support
+@pytest.mark.parametrize("v_fluid", [(0.0, -1.0), (1.0, 1.0), (-1.0, 0.0), (0.7, 0.2), (0.3, 0.8)])
+def test_no_slip_wall_velocity_constant_profile(oracle, v_fluid):
+    fluid_ic, fluid, wall = _no_slip_fixture()
+    n = fluid_ic.nparticles
+    v = np.concatenate([np.tile(np.array(v_fluid), (n, 1)), np.full((n, 1), 257.0)], axis=1)
+    for use_grid in (False, True):
+        out = adapter.kick(fluid, wall, fluid_ic.coordinates, v, use_grid=use_grid)
+        expected = np.zeros((30, 2))
+        expected[:20] = -np.array(v_fluid)
+        np.testing.assert_allclose(out["wall_velocity"], expected, rtol=1e-8, atol=1e-14)  # isapprox
+
+
+# dummy_particles.jl:235-303: staggered profile, the reference's explicit numbers
+@pytest.mark.parametrize("scale", [1.0, 0.5, 0.7, 1.8, 67.5])
+def test_no_slip_wall_velocity_staggered_known_answers(oracle, scale):
+    fluid_ic, fluid, wall = _no_slip_fixture()
+    n = fluid_ic.nparticles
+    vel = np.where((np.arange(1, n + 1) % 2 == 1)[:, None], scale, 0.0) * np.ones((n, 2))
+    v = np.concatenate([vel, np.full((n, 1), 257.0)], axis=1)
+    out = adapter.kick(fluid, wall, fluid_ic.coordinates, v)
+    expected = np.zeros((30, 2))
+    for i in range(1, 11):
+        expected[i - 1] = -(0.42040669416720744 if i % 2 == 1 else 0.5795933058327924) * scale
+    for i in range(11, 21):
+        expected[i - 1] = -(0.12101100073462243 if i % 2 == 1 else 0.8789889992653775) * scale
+    np.testing.assert_allclose(out["wall_velocity"], expected, rtol=1e-11, atol=1e-13)
+
+
+def test_no_slip_wall_viscous_term_matches_pair_functions(oracle):
+    """The fluid<-wall viscous term of a no-slip wall is the wall model's pair formula (pinned above to
+    test/schemes/fluid/viscosity.jl) evaluated with v_b = wall_velocity: difference of two oracle
+    kicks (no-slip minus free-slip) against the sum over the wall neighbours."""
+    fluid_ic, fluid, wall = _no_slip_fixture()
+    n = fluid_ic.nparticles
+    rng = np.random.default_rng(5)
+    v = np.concatenate([rng.normal(size=(n, 2)), 257.0 * (1 + 0.01 * rng.normal(size=(n, 1)))], axis=1)
+    u = fluid_ic.coordinates
+    for visc in (tp.ViscosityAdami(nu=1e-3), tp.ViscosityMorris(nu=2e-3),
+                 tp.ArtificialViscosityMonaghan(alpha=0.05, beta=0.1)):
+        wall.boundary_model.viscosity = visc
+        ns = adapter.kick(fluid, wall, u, v)
+        wall.boundary_model.viscosity = None
+        fs = adapter.kick(fluid, wall, u, v)
+        diff = ns["dv"][:, :2] - fs["dv"][:, :2]
+        h, c = 0.12, 10.0
+        expected = np.zeros((n, 2))
+        xw, mw = wall.coordinates, wall.boundary_model.hydrodynamic_mass
+        for a in range(n):
+            for b in range(xw.shape[0]):
+                pd = u[a] - xw[b]
+                if pd @ pd > (2 * h) ** 2:
+                    continue
+                vd = v[a, :2] - ns["wall_velocity"][b]
+                if isinstance(visc, tp.ArtificialViscosityMonaghan):
+                    expected[a] += oracle.viscosity_pair(CUBIC, 2, h, visc.alpha, visc.beta, visc.epsilon, c,
+                                                         mw[b], v[a, 2], ns["wall_density"][b], vd, pd)
+                else:
+                    # nu_a (fluid: ViscosityAdami(1e-6)) != nu_b (wall): checked in numpy below
+                    nu_a, nu_b = 1e-6, visc.nu
+                    r2 = pd @ pd
+                    r = np.sqrt(r2)
+                    grad = oracle.kernel_deriv_div_r(CUBIC, 2, r, h) * pd
+                    rho_a, rho_b, m_a, m_b = v[a, 2], ns["wall_density"][b], fluid.mass[a], mw[b]
+                    d2e = r2 + visc.epsilon * h * h
+                    if isinstance(visc, tp.ViscosityMorris):
+                        coef = m_b * (nu_a * rho_a + nu_b * rho_b) * (pd @ grad) / (rho_a * rho_b * d2e)
+                    else:
+                        eta_a, eta_b = nu_a * rho_a, nu_b * rho_b
+                        tmp = 2 * eta_a * eta_b / ((eta_a + eta_b) * d2e * m_a)
+                        coef = ((m_a / rho_a) ** 2 + (m_b / rho_b) ** 2) * (grad @ pd) * tmp
+                    expected[a] += coef * vd
+        scale = np.abs(fs["dv"][:, :2]).max()
+        assert np.abs(expected).max() > 0
+        np.testing.assert_allclose(diff, expected, rtol=0, atol=1e-12 * scale)
+
+
 def _adami_tank(density, acceleration=None, eltype=np.float64):
     # dummy_particles.jl:305-328
     dx, n, n_layers = 0.1, 10, 2

@@ -14,7 +14,7 @@ TPB_OK = 0
 ERR_NAMES = {1: "INVALID_ARGUMENT", 2: "UNSUPPORTED", 3: "CUDA", 4: "OUT_OF_BOUNDS", 5: "STATE", 6: "CAPACITY"}
 F32, F64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
-FIELD_PRESSURE, FIELD_DENSITY, FIELD_VOLUME = 0, 1, 2
+FIELD_PRESSURE, FIELD_DENSITY, FIELD_VOLUME, FIELD_WALL_VELOCITY = 0, 1, 2, 3
 
 EXPORTS = [
     "tpb_version", "tpb_last_error", "tpb_create", "tpb_destroy", "tpb_add_fluid_system",
@@ -60,6 +60,8 @@ class WallParams(C.Structure):
         ("sound_speed_from_fluid", C.c_int32), ("smoothing_length", C.c_double), ("sound_speed", C.c_double),
         ("exponent", C.c_double), ("reference_density", C.c_double),
         ("background_pressure", C.c_double), ("pressure_offset", C.c_double),
+        ("has_viscosity", C.c_int32), ("reserved", C.c_int32),
+        ("alpha", C.c_double), ("beta", C.c_double), ("epsilon", C.c_double),
     ]
 
 

@@ -64,6 +64,7 @@ struct Semi {
     int *h_flags = nullptr;  // pinned
     void *d_A = nullptr, *d_B = nullptr, *d_P = nullptr;
     void *d_Aw = nullptr, *d_Ww = nullptr, *d_volw = nullptr;
+    void *d_Vw = nullptr;  // no-slip wall: cache.wall_velocity of the sorted wall particles (V4<T>)
     int *d_perm_w = nullptr;
     void *d_scratch = nullptr;  // max(n_f, n_w) * sizeof(double): field unsort
     unsigned long long *d_vmax2 = nullptr, *h_vmax2 = nullptr;  // StateEquationAdaptiveCole: max |v|^2 (bits)
@@ -449,6 +450,48 @@ struct Ops {
         return TPB_OK;
     }
 
+    // ---- no-slip wall (boundary_model.viscosity !== nothing): wall velocity after the Adami pass
+    template <int KERNEL>
+    static int launch_wall_velocity(Semi &s, const GridConst<CT> &g)
+    {
+        int n = (int)s.n_w;
+        KernelConst<T> kern = make_kernel_const<T>(s.wp.kernel, ND, s.wp.smoothing_length);
+        T R = kern.support;
+        LAUNCH(s, (k_wall_velocity<ND, T, CT, KERNEL>), cdiv(n, 128), 128, 0, n, g, (const V4<CT> *)s.d_Aw,
+               s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.interaction[1][0], kern,
+               (T)(R * R), (V4<T> *)s.d_Vw);
+        return TPB_OK;
+    }
+
+    // ---- ... and the wall model's viscous term of the fluid after interact!
+    template <int KERNEL, int DENS>
+    static int launch_wall_viscous(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc, T *d_dv)
+    {
+        constexpr int NV = DENS == 0 ? ND + 1 : ND;
+        int n = (int)s.n_act;
+        WallViscConst<T> k;
+        k.kern = pc.kern;
+        k.model = s.wp.has_viscosity;
+        k.alpha = (T)s.wp.alpha;
+        k.beta = (T)s.wp.beta;
+        const T h_f = pc.kern.h, h_w = (T)s.wp.smoothing_length;
+        // kinematic_viscosity (viscosity.jl:82-87, :154-157, :282-285)
+        auto kin = [&](int model, T alpha_or_nu, T h) {
+            return model == TPB_VISCOSITY_MONAGHAN ? alpha_or_nu * h * pc.c / (T)(2 * ND + 4) : alpha_or_nu;
+        };
+        k.nu_a = kin(s.fp.has_viscosity, (T)s.fp.alpha, h_f);
+        k.nu_b = kin(s.wp.has_viscosity, (T)s.wp.alpha, h_w);
+        k.h = (h_f + h_w) / (T)2;
+        k.eps_h2 = (T)s.wp.epsilon * (k.h * k.h);
+        k.c = pc.c;
+        k.radius2 = pc.radius2;
+        k.almostzero = pc.almostzero;
+        LAUNCH(s, (k_wall_viscous<ND, T, CT, KERNEL, NV>), cdiv(n, 128), 128, 0, n, g, s.d_fcell_start,
+               (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.d_perm_f, s.d_wcell_start,
+               (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, (const V4<T> *)s.d_Vw, k, d_dv, (int)s.n_tgt);
+        return TPB_OK;
+    }
+
     template <int KERNEL, int DENS>
     static int launch_interact(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc, T *d_dv)
     {
@@ -557,6 +600,13 @@ struct Ops {
                  : wk == 2 ? launch_adami<2>(s, g)
                            : launch_adami<3>(s, g);
             if (rc) return rc;
+            if (s.wp.has_viscosity) {
+                rc = wk == 0   ? launch_wall_velocity<0>(s, g)
+                     : wk == 1 ? launch_wall_velocity<1>(s, g)
+                     : wk == 2 ? launch_wall_velocity<2>(s, g)
+                               : launch_wall_velocity<3>(s, g);
+                if (rc) return rc;
+            }
         }
         prof_mark(s, TPB_PHASE_INTERACT);
         if (fk == 0)
@@ -568,6 +618,17 @@ struct Ops {
         else
             rc = summ ? launch_interact<3, 1>(s, g, pc, d_dv) : launch_interact<3, 0>(s, g, pc, d_dv);
         if (rc) return rc;
+        if (s.n_w > 0 && s.wp.has_viscosity && s.interaction[0][1]) {
+            if (fk == 0)
+                rc = summ ? launch_wall_viscous<0, 1>(s, g, pc, d_dv) : launch_wall_viscous<0, 0>(s, g, pc, d_dv);
+            else if (fk == 1)
+                rc = summ ? launch_wall_viscous<1, 1>(s, g, pc, d_dv) : launch_wall_viscous<1, 0>(s, g, pc, d_dv);
+            else if (fk == 2)
+                rc = summ ? launch_wall_viscous<2, 1>(s, g, pc, d_dv) : launch_wall_viscous<2, 0>(s, g, pc, d_dv);
+            else
+                rc = summ ? launch_wall_viscous<3, 1>(s, g, pc, d_dv) : launch_wall_viscous<3, 0>(s, g, pc, d_dv);
+            if (rc) return rc;
+        }
         prof_mark(s, TPB_PHASE_END);
         if (s.prof_capacity > 0 && s.prof_kicks < s.prof_capacity) s.prof_kicks++;
         CUDA_TRY(&s, cudaGetLastError());
@@ -639,6 +700,24 @@ struct Ops {
 
     static int get_field(Semi &s, int system, int field, void *out, int64_t n)
     {
+        if (field == TPB_FIELD_WALL_VELOCITY) {
+            // ND x n_w values; not on the hot path: a buffer of its own
+            if (system != s.wall_index || !s.d_Vw)
+                return fail(&s, TPB_ERR_INVALID_ARGUMENT, "wall_velocity: the system is not a wall with a viscosity model");
+            if (n != s.n_w) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
+            if (n == 0) return TPB_OK;
+            T *d_tmp = nullptr;
+            const size_t bytes = sizeof(T) * ND * (size_t)n;
+            CUDA_TRY(&s, cudaMalloc(&d_tmp, bytes));
+            cudaMemsetAsync(d_tmp, 0, bytes, s.stream);
+            LAUNCH(s, (k_unsort_vector<T>), cdiv(n, 256), 256, 0, (int)n, s.d_wcell_start + s.ncells, s.d_perm_w,
+                   (const V4<T> *)s.d_Vw, ND, d_tmp);
+            cudaError_t e = cudaMemcpyAsync(out, d_tmp, bytes, cudaMemcpyDeviceToHost, s.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+            cudaFree(d_tmp);
+            CUDA_TRY(&s, e);
+            return TPB_OK;
+        }
         T *scratch = (T *)s.d_scratch;
         CUDA_TRY(&s, cudaMemsetAsync(scratch, 0, sizeof(T) * (size_t)std::max<int64_t>(n, 1), s.stream));
         if (system == s.fluid_index) {
@@ -824,7 +903,7 @@ static void free_device(Semi &s)
 {
     void *ptrs[] = {s.d_mass_f, s.d_u, s.d_v, s.d_dv, s.d_du, s.d_key, s.d_slot, s.d_tmp_perm,
                     s.d_perm_f, s.d_count, s.d_fcell_start, s.d_wcell_start, s.d_block_sums,
-                    s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_perm_w,
+                    s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_Vw, s.d_perm_w,
                     s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -954,6 +1033,8 @@ int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *p, int64_t n
     if (!(p->smoothing_length > 0) || !(p->sound_speed > 0) || !(p->reference_density > 0) || p->exponent == 0)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "smoothing_length, sound_speed, reference_density must be positive");
     if (n < 0 || n > 0x7fffffff / 4) return fail(s, TPB_ERR_INVALID_ARGUMENT, "particle count out of range");
+    if (p->has_viscosity < TPB_VISCOSITY_NONE || p->has_viscosity > TPB_VISCOSITY_ADAMI)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown wall viscosity model");
     s->wp = *p;
     s->n_w = n;
     const size_t ts = tsize(s->cfg.eltype), cs = tsize(s->cfg.coords_eltype);
@@ -983,6 +1064,10 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
     if (s->ready) return fail(s, TPB_ERR_STATE, "tpb_semidiscretize was already called");
     if (s->fluid_index < 0) return fail(s, TPB_ERR_INVALID_ARGUMENT, "a fluid system is required");
+    if (s->wall_index >= 0 && s->wp.has_viscosity >= TPB_VISCOSITY_MORRIS && s->fp.has_viscosity == TPB_VISCOSITY_NONE)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT,
+                    "a ViscosityMorris / ViscosityAdami wall needs a fluid viscosity model: "
+                    "kinematic_viscosity(fluid, nothing, ...) has no method in the reference");
     CUDA_TRY(s, cudaSetDevice(s->cfg.device));
     const int nd = s->cfg.ndims;
     const size_t ts = tsize(s->cfg.eltype), cs = tsize(s->cfg.coords_eltype);
@@ -1117,6 +1202,10 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     CUDA_TRY(s, cudaMalloc(&s->d_Aw, 4 * cs * (nw + 8)));
     CUDA_TRY(s, cudaMalloc(&s->d_Ww, 2 * ts * (nw + 8)));
     CUDA_TRY(s, cudaMalloc(&s->d_volw, ts * (nw + 8)));
+    if (s->wp.has_viscosity) {
+        CUDA_TRY(s, cudaMalloc(&s->d_Vw, 4 * ts * (nw + 8)));
+        CUDA_TRY(s, cudaMemset(s->d_Vw, 0, 4 * ts * (nw + 8)));
+    }
     CUDA_TRY(s, cudaMalloc(&s->d_scratch, sizeof(double) * nmax));
     CUDA_TRY(s, cudaMalloc(&s->d_vmax2, sizeof(unsigned long long)));
     CUDA_TRY(s, cudaHostAlloc(&s->h_vmax2, sizeof(unsigned long long), cudaHostAllocDefault));

@@ -210,6 +210,153 @@ k_interact_pp(int n_f, GridConst<CT> g, const int *__restrict__ fcell_start,
     if (DENS == 0) dv[o + ND] = drho_ff + drho_fw;
 }
 
+// ------------------------------------------------------------------ no-slip wall
+// `BoundaryModelDummyParticles(...; viscosity=model)`: the wall carries a velocity
+//   v_w = 2 v_boundary - sum_f v_f W(r_wf) / sum_f W(r_wf)        (v_boundary = 0: static wall)
+// (interpolate_fluid_velocity! / compute_wall_velocity!, dummy_particles.jl:710-758) and the fluid
+// feels the wall through the wall's viscosity model with v_b = v_w (dv_viscosity!, viscosity.jl:9-40;
+// viscous_velocity, wall_boundary/system.jl:148-163).  Two sweeps of their own, launched after the
+// Adami pass and after interact!, so that the register budgets of k_adami_tiles / k_interact_tiles
+// (the free-slip hot path) stay untouched.
+template <int ND, typename T, typename CT, int KERNEL>
+__global__ void __launch_bounds__(128)
+k_wall_velocity(int n_w, GridConst<CT> g, const V4<CT> *__restrict__ Aw,
+                const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
+                const V4<T> *__restrict__ B, int interaction_enabled, KernelConst<T> kern, T radius2,
+                V4<T> *__restrict__ Vw)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_w) return;
+    const V4<CT> xi = Aw[w];
+    int cx, cy, cz;
+    cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    T wv[3] = {0, 0, 0}, vol = (T)0;
+    if (interaction_enabled) {
+        for_neighbor_rows<ND, CT>(g, fcell_start, cx, cy, cz, [&](int j0, int j1) {
+            for (int j = j0; j < j1; ++j) {
+                const V4<CT> xj = A[j];
+                T pd[3];
+                T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                if (d2 <= radius2) {
+                    T kw = kernel_safe<KERNEL, T>(kern, sqrt_rn(d2));
+                    const V4<T> bj = B[j];
+                    wv[0] += kw * bj.x;
+                    wv[1] += kw * bj.y;
+                    if (ND == 3) wv[2] += kw * bj.z;
+                    vol += kw;
+                }
+            }
+        });
+    }
+    if ((double)vol > 2.220446049250313e-16) {  // `volume > eps()` (dummy_particles.jl:554)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) wv[d] = (T)0 - wv[d] / vol;
+    }
+    V4<T> out;
+    out.x = wv[0];
+    out.y = wv[1];
+    out.z = ND == 3 ? wv[2] : (T)0;
+    out.w = (T)0;
+    Vw[w] = out;
+}
+
+template <typename T>
+struct WallViscConst {
+    KernelConst<T> kern;  // the fluid's kernel (gradient)
+    int model;            // TPB_VISCOSITY_* of the boundary model
+    T alpha, beta;        // ArtificialViscosityMonaghan of the wall
+    T nu_a, nu_b;         // Morris / Adami: kinematic_viscosity of the fluid / of the wall
+    T h;                  // (h_fluid + h_wall) / 2
+    T eps_h2;             // epsilon_wall * h^2
+    T c;                  // system_sound_speed(fluid)
+    T radius2, almostzero;
+};
+
+// One thread per sorted fluid particle: dv[1:ND, a] += sum_w viscous term (wall's model).
+template <int ND, typename T, typename CT, int KERNEL, int NV>
+__global__ void __launch_bounds__(128)
+k_wall_viscous(int n_f, GridConst<CT> g, const int *__restrict__ fcell_start,
+               const V4<CT> *__restrict__ A, const V4<T> *__restrict__ B,
+               const int *__restrict__ perm, const int *__restrict__ wcell_start,
+               const V4<CT> *__restrict__ Aw, const V2<T> *__restrict__ Ww,
+               const V4<T> *__restrict__ Vw, WallViscConst<T> k, T *__restrict__ dv, int n_targets)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_f || s >= fcell_start[g.ncells]) return;
+    if (perm[s] >= n_targets) return;  // slab ghost: neighbour only
+    const V4<CT> xi = A[s];
+    const V4<T> bi = B[s];
+    const T rho_a = bi.w, m_a = (T)xi.w;
+    int cx, cy, cz;
+    cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    T acc[3] = {0, 0, 0};
+    for_neighbor_rows<ND, CT>(g, wcell_start, cx, cy, cz, [&](int j0, int j1) {
+        for (int j = j0; j < j1; ++j) {
+            const V4<CT> xj = Aw[j];
+            T pd[3];
+            T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+            if (d2 > k.radius2) continue;
+            const T dist = sqrt_rn(d2);
+            if (dist < k.almostzero) continue;
+            const T wdr = SmoothingKernel<KERNEL, T>::dw_div_r(k.kern, dist);
+            const V4<T> vw = Vw[j];
+            const T rho_b = Ww[j].y, m_b = (T)xj.w;
+            T vd[3] = {bi.x - vw.x, bi.y - vw.y, ND == 3 ? bi.z - vw.z : (T)0};
+            T grad[3];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) grad[d] = wdr * pd[d];
+            const T d2e = dist * dist + k.eps_h2;
+            if (k.model == 1) {
+                // ArtificialViscosityMonaghan (viscosity.jl:89-132)
+                T vr = vd[0] * pd[0] + vd[1] * pd[1];
+                if (ND == 3) vr += vd[2] * pd[2];
+                if (vr < (T)0) {
+                    const T rho_mean = (rho_a + rho_b) / (T)2;
+                    const T mu = div_fast(k.h * vr, d2e);
+                    const T dvv = div_fast(m_b * k.alpha * k.c * mu + m_b * k.beta * (mu * mu), rho_mean);
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) acc[d] += dvv * grad[d];
+                }
+            } else {
+                T pg = pd[0] * grad[0] + pd[1] * grad[1];
+                if (ND == 3) pg += pd[2] * grad[2];
+                T coef;
+                if (k.model == 2) {
+                    // ViscosityMorris (viscosity.jl:163-205)
+                    const T mu_a = k.nu_a * rho_a, mu_b = k.nu_b * rho_b;
+                    coef = div_fast(m_b * (mu_a + mu_b) * pg, rho_a * rho_b * d2e);
+                } else {
+                    // ViscosityAdami (viscosity.jl:222-279)
+                    const T eta_a = k.nu_a * rho_a, eta_b = k.nu_b * rho_b;
+                    const T volume_a = div_fast(m_a, rho_a), volume_b = div_fast(m_b, rho_b);
+                    const T tmp = div_fast((T)2 * eta_a * eta_b, (eta_a + eta_b) * d2e * m_a);
+                    coef = (volume_a * volume_a + volume_b * volume_b) * pg * tmp;
+                }
+#pragma unroll
+                for (int d = 0; d < ND; ++d) acc[d] += coef * vd[d];
+            }
+        }
+    });
+    const int64_t o = (int64_t)perm[s] * NV;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) dv[o + d] += acc[d];
+}
+
+// scatter a sorted per-particle vector field (V4 records) back to the system's own particle order
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_unsort_vector(int n, const int *__restrict__ n_sorted, const int *__restrict__ perm,
+                const V4<T> *__restrict__ sorted, int nd, T *__restrict__ out)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n || s >= *n_sorted) return;
+    const V4<T> r = sorted[s];
+    T *o = out + (int64_t)perm[s] * nd;
+    o[0] = r.x;
+    o[1] = r.y;
+    if (nd == 3) o[2] = r.z;
+}
+
 // ------------------------------------------------------------------ drift!
 // du[1:ND, a] = v[1:ND, a]  (strided copy: v has NV rows, du has ND; T -> cT conversion)
 template <int ND, typename T, typename CT>

@@ -269,8 +269,12 @@ class BoundaryModelDummyParticles:
         if not isinstance(density_calculator, (AdamiPressureExtrapolation, BernoulliPressureExtrapolation)):
             raise ValueError("only `AdamiPressureExtrapolation` / `BernoulliPressureExtrapolation` are on "
                              "the accelerated path")
-        if viscosity is not None or correction is not None:
-            raise ValueError("wall `viscosity`/`correction` are outside the accelerated hot path")
+        if correction is not None:
+            raise ValueError("wall `correction` is outside the accelerated hot path")
+        if viscosity is not None and not isinstance(viscosity, (ArtificialViscosityMonaghan, ViscosityMorris,
+                                                                 ViscosityAdami)):
+            raise ValueError("wall `viscosity` must be ArtificialViscosityMonaghan, ViscosityMorris or "
+                             "ViscosityAdami on the accelerated path")
         if state_equation is None:
             raise ValueError("`AdamiPressureExtrapolation` needs a `state_equation`")
         self.initial_density = np.asarray(initial_density)
@@ -281,7 +285,7 @@ class BoundaryModelDummyParticles:
         self.eltype = self.hydrodynamic_mass.dtype
         self.smoothing_length = self.eltype.type(smoothing_length)
         self.state_equation = state_equation
-        self.viscosity = None
+        self.viscosity = viscosity   # None: free-slip; a model: no-slip wall (dummy_particles.jl:299-307)
         self.clip_negative_pressure = bool(clip_negative_pressure)
         n = self.hydrodynamic_mass.shape[0]
         self.pressure = np.zeros(n, dtype=self.eltype)

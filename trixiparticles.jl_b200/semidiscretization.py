@@ -183,6 +183,16 @@ class Semidiscretization:
         p.reference_density = float(t(se.reference_density))
         p.background_pressure = float(t(se.background_pressure))
         p.pressure_offset = float(t(m.density_calculator.pressure_offset))
+        if m.viscosity is not None:   # no-slip wall
+            p.has_viscosity = int(getattr(m.viscosity, "viscosity_id", 1))
+            if p.has_viscosity == 1:
+                p.alpha, p.beta = float(t(m.viscosity.alpha)), float(t(m.viscosity.beta))
+            else:
+                p.alpha = float(t(m.viscosity.nu))
+            p.epsilon = float(t(m.viscosity.epsilon))
+            if p.has_viscosity >= 2 and self.fluid.viscosity is None:
+                raise ValueError("a ViscosityMorris / ViscosityAdami wall needs a fluid viscosity model "
+                                 "(kinematic_viscosity(fluid, nothing, ...) has no method in the reference)")
         if isinstance(se, StateEquationAdaptiveCole):
             if se is not self.fluid.state_equation:
                 raise ValueError("a boundary model with its own StateEquationAdaptiveCole is outside the "
@@ -305,7 +315,12 @@ class Semidiscretization:
         """`system.pressure`, `cache.density`, `boundary_model.pressure/cache.density/cache.volume`
         after the last kick (fluid.jl:312-326, wall_boundary/system.jl:339-350)."""
         fid = {"pressure": _lib.FIELD_PRESSURE, "density": _lib.FIELD_DENSITY,
-               "volume": _lib.FIELD_VOLUME}[field]
+               "volume": _lib.FIELD_VOLUME, "wall_velocity": _lib.FIELD_WALL_VELOCITY}[field]
+        if field == "wall_velocity":   # boundary_model.cache.wall_velocity, (n, ND)
+            out = np.zeros((system.nparticles, self.ndims), dtype=self.eltype)
+            _lib.check(self._handle, _lib.load().tpb_get_system_field(
+                self._handle, self.system_index(system), fid, out.ctypes.data, system.nparticles))
+            return out
         out = np.zeros(system.nparticles, dtype=self.eltype)
         _lib.check(self._handle, _lib.load().tpb_get_system_field(
             self._handle, self.system_index(system), fid, out.ctypes.data, out.size))
