@@ -383,6 +383,12 @@ def run_single(args):
             # reduction per kick, whose result is a host scalar as in the reference)
             variants["as_shipped_f64_coordinates_adaptive_cole"] = run_variant(tp, torch, args, "f32", "f64",
                                                                               adaptive=True)
+        # no-slip wall (`viscosity_wall = viscosity_fluid`, examples/fluid/dam_break_2d.jl:78-80): the
+        # wall-velocity sweep and the wall's viscous term run as two extra per-particle kernels
+        # (both on the same synthetic velocity field, since the lattice itself is at rest)
+        variants["moving_fluid_free_slip_wall"] = run_variant(tp, torch, args, "f32", "f32", moving=True)
+        variants["moving_fluid_no_slip_wall"] = run_variant(tp, torch, args, "f32", "f32", moving=True,
+                                                            no_slip=True)
 
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample
     cpu = None
@@ -413,9 +419,15 @@ def run_single(args):
     print(json.dumps(line))
 
 
-def run_variant(tp, torch, args, eltype, coords, steps=10, adaptive=False):
+def run_variant(tp, torch, args, eltype, coords, steps=10, adaptive=False, no_slip=False, moving=False):
     """Device-resident kick!+drift! of the same workload in another precision set-up."""
     fluid, wall, u, v = make_workload(args.workload, eltype, coords, adaptive=adaptive)
+    if no_slip:
+        wall.boundary_model.viscosity = fluid.viscosity
+    if moving:
+        # the lattice is at rest; a velocity field exercises the viscous terms
+        v = v.copy()
+        v[:, :fluid.ndims] = (0.05 * np.sin(40.0 * u)).astype(v.dtype)
     semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(
         device=0, ode_memory="device", interact_variant=args.variant))
     ode = tp.semidiscretize(semi, (0.0, 1.0))
