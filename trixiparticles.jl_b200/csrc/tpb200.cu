@@ -64,7 +64,8 @@ struct Semi {
     int *h_flags = nullptr;  // pinned
     void *d_A = nullptr, *d_B = nullptr, *d_P = nullptr;
     void *d_Aw = nullptr, *d_Ww = nullptr, *d_volw = nullptr;
-    void *d_Vw = nullptr;  // no-slip wall: cache.wall_velocity of the sorted wall particles (V4<T>)
+    void *d_Vw = nullptr;  // no-slip wall: (cache.wall_velocity, rho_w) of the sorted wall particles (V4<T>)
+    bool wall_velocity_done = false;  // this kick's Adami sweep has written d_Vw already (fused tile version)
     int *d_perm_w = nullptr;
     void *d_scratch = nullptr;  // max(n_f, n_w) * sizeof(double): field unsort
     unsigned long long *d_vmax2 = nullptr, *h_vmax2 = nullptr;  // StateEquationAdaptiveCole: max |v|^2 (bits)
@@ -425,8 +426,14 @@ struct Ops {
             if (!attr_set) {
                 int rc = set_smem(s, k_adami_tiles<KS, ND, T, CT, KERNEL>, 227 * 1024);
                 if (rc) return rc;
+                rc = set_smem(s, k_adami_tiles<KS, ND, T, CT, KERNEL, true>, 227 * 1024);
+                if (rc) return rc;
                 attr_set = true;
             }
+            // no-slip wall: the wall velocity rides along in the same sweep when the lists leave room
+            // for the five reduction slots; otherwise k_wall_velocity follows (kick_device)
+            const bool fused = s.wp.has_viscosity && list_len >= ADAMI_NOSLIP_RED * (int)sizeof(T) / 2;
+            s.wall_velocity_done = fused;
             CUDA_TRY(&s, cudaMemsetAsync(s.tiles.d_n_wactive, 0, sizeof(int), s.stream));
             T p_empty = (T)0;  // empty sum, clipped or not: p = 0
             T rho_empty = k.eos.rho0 * (T)std::pow((double)((p_empty - k.eos.p_bg) / k.eos.B + (T)1),
@@ -434,7 +441,17 @@ struct Ops {
             LAUNCH(s, (k_wall_tile_prep<ND, T, CT>), cdiv((int64_t)s.tiles.max_wtiles * 32, 256), 256, 0, g,
                    s.tiles.d_wrow_tile_start + s.tiles.nrows, s.tiles.d_wtile_desc, (const V4<CT> *)s.d_Aw,
                    s.d_fcell_start, rho_empty, (V2<T> *)s.d_Ww, (T *)s.d_volw, s.tiles.d_wactive,
-                   s.tiles.d_n_wactive, s.tiles.d_wtile_rng, s.tiles.d_wtile_ext);
+                   s.tiles.d_n_wactive, s.tiles.d_wtile_rng, s.tiles.d_wtile_ext,
+                   fused ? (V4<T> *)s.d_Vw : (V4<T> *)nullptr);
+            if (fused) {
+                LAUNCH(s, (k_adami_tiles<KS, ND, T, CT, KERNEL, true>), grid, KS * TILE_TB, smem, g,
+                       s.tiles.d_n_wactive, s.tiles.d_wactive, s.tiles.d_wtile_desc, s.tiles.d_wtile_ext,
+                       s.tiles.d_wtile_rng, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
+                       s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
+                       s.interaction[1][0], k, (V2<T> *)s.d_Ww, (T *)s.d_volw, cap, list_len,
+                       (const V4<float> *)s.d_Ff, (V4<T> *)s.d_Vw);
+                return TPB_OK;
+            }
             LAUNCH(s, (k_adami_tiles<KS, ND, T, CT, KERNEL>), grid, KS * TILE_TB, smem, g,
                    s.tiles.d_n_wactive, s.tiles.d_wactive, s.tiles.d_wtile_desc, s.tiles.d_wtile_ext,
                    s.tiles.d_wtile_rng, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
@@ -443,6 +460,7 @@ struct Ops {
                    (const V4<float> *)s.d_Ff);
             return TPB_OK;
         }
+        s.wall_velocity_done = false;
         LAUNCH(s, (k_adami<ND, T, CT, KERNEL>), cdiv(n, 128), 128, 0, n, g,
                (const V4<CT> *)s.d_Aw, s.d_fcell_start, (const V4<CT> *)s.d_A,
                (const V4<T> *)s.d_B, (const T *)s.d_P, s.interaction[1][0], k,
@@ -459,7 +477,7 @@ struct Ops {
         T R = kern.support;
         LAUNCH(s, (k_wall_velocity<ND, T, CT, KERNEL>), cdiv(n, 128), 128, 0, n, g, (const V4<CT> *)s.d_Aw,
                s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.interaction[1][0], kern,
-               (T)(R * R), (V4<T> *)s.d_Vw);
+               (T)(R * R), (const V2<T> *)s.d_Ww, (V4<T> *)s.d_Vw);
         return TPB_OK;
     }
 
@@ -486,6 +504,23 @@ struct Ops {
         k.c = pc.c;
         k.radius2 = pc.radius2;
         k.almostzero = pc.almostzero;
+        if (use_tiles(s)) {
+            const int list_len = s.tiles.list(KS);
+            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, list_len, KS);
+            const size_t smem = tile_smem_bytes<T, CT>(cap, list_len, KS);
+            static bool attr_set = false;
+            if (!attr_set) {
+                int rc = set_smem(s, k_wall_viscous_tiles<KS, ND, T, CT, KERNEL, NV>, 227 * 1024);
+                if (rc) return rc;
+                attr_set = true;
+            }
+            LAUNCH(s, (k_wall_viscous_tiles<KS, ND, T, CT, KERNEL, NV>), s.tiles.max_ftiles, KS * TILE_TB, smem, g,
+                   s.tiles.d_frow_tile_start + s.tiles.nrows, s.tiles.d_ftile_desc, s.tiles.d_ftile_ext,
+                   s.tiles.d_ftile_rng, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.d_perm_f,
+                   s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V4<T> *)s.d_Vw, k, d_dv, (int)s.n_tgt, cap,
+                   list_len, (const V4<float> *)s.d_Fw);
+            return TPB_OK;
+        }
         LAUNCH(s, (k_wall_viscous<ND, T, CT, KERNEL, NV>), cdiv(n, 128), 128, 0, n, g, s.d_fcell_start,
                (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.d_perm_f, s.d_wcell_start,
                (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, (const V4<T> *)s.d_Vw, k, d_dv, (int)s.n_tgt);
@@ -600,7 +635,7 @@ struct Ops {
                  : wk == 2 ? launch_adami<2>(s, g)
                            : launch_adami<3>(s, g);
             if (rc) return rc;
-            if (s.wp.has_viscosity) {
+            if (s.wp.has_viscosity && !s.wall_velocity_done) {
                 rc = wk == 0   ? launch_wall_velocity<0>(s, g)
                      : wk == 1 ? launch_wall_velocity<1>(s, g)
                      : wk == 2 ? launch_wall_velocity<2>(s, g)

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(128)
 k_wall_velocity(int n_w, GridConst<CT> g, const V4<CT> *__restrict__ Aw,
                 const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
                 const V4<T> *__restrict__ B, int interaction_enabled, KernelConst<T> kern, T radius2,
-                V4<T> *__restrict__ Vw)
+                const V2<T> *__restrict__ Ww, V4<T> *__restrict__ Vw /* (v_w, rho_w) */)
 {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_w) return;
@@ -256,7 +256,7 @@ k_wall_velocity(int n_w, GridConst<CT> g, const V4<CT> *__restrict__ Aw,
     out.x = wv[0];
     out.y = wv[1];
     out.z = ND == 3 ? wv[2] : (T)0;
-    out.w = (T)0;
+    out.w = Ww[w].y;
     Vw[w] = out;
 }
 

@@ -33,6 +33,7 @@
 #include "tpb_device.cuh"
 #include "tpb_nhs.cuh"
 #include "tpb_sweeps.cuh"
+#include "tpb_sweeps.cuh"
 
 // tuning knobs (compile time)
 #ifndef TPB_P2_UNROLL
@@ -714,17 +715,18 @@ __device__ __forceinline__ void named_barrier(int id)
 // neighbouring threads (a pair for Float32, four for Float64) form one aligned word of T; thread
 // j of such a group parks its values in the words of the entries j * 4 .. j * 4 + 3 -- slots
 // only this group of lanes ever touches, so warps that are still sweeping are not disturbed.
-template <int KS, int NVAL, typename T, typename CT>
+// RED: slots per thread (the list must hold RED * sizeof(T) / 2 entries).
+template <int KS, int NVAL, typename T, typename CT, int RED = TILE_RED_VALS>
 __device__ __forceinline__ void tile_reduce(TileSmem<T, CT> &sm, T (&val)[NVAL])
 {
-    static_assert(NVAL <= TILE_RED_VALS, "tile_reduce: scratch space too small");
+    static_assert(NVAL <= RED, "tile_reduce: scratch space too small");
     if constexpr (KS > 1) {
         constexpr int NT = KS * TILE_TB;
         constexpr int W = (int)sizeof(T) / 2;  // 16-bit slots per value
         const int ti = threadIdx.x % TILE_TB, kg = threadIdx.x / TILE_TB;
         const int bar_id = 1 + ti / 32;
         auto slot = [&](int tid, int n) {
-            return reinterpret_cast<T *>(sm.list + (n + TILE_RED_VALS * (tid % W)) * NT + (tid - tid % W));
+            return reinterpret_cast<T *>(sm.list + (n + RED * (tid % W)) * NT + (tid - tid % W));
         };
         __syncwarp();  // both lanes of a pair have drained their lists
         if (kg > 0) {
@@ -891,6 +893,101 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     }
 }
 
+// ------------------------------------------------------------------ no-slip wall: viscous term (variant 2)
+// The wall model's viscous term of the fluid (dv_viscosity!, viscosity.jl:9-40, with v_b = v_w:
+// viscous_velocity, wall_boundary/system.jl:148-163) as a tile sweep of its own over the wall records
+// (x, m | v_w, rho_w), launched after k_interact_tiles: dv[1:ND, a] += sum_w.  Fluid tiles without a
+// wall particle in reach (most of them) exit at once; k_interact_tiles keeps its register budget.
+template <int KS, int ND, typename T, typename CT, int KERNEL, int NV>
+__global__ void __launch_bounds__(KS * TILE_TB, 2)
+k_wall_viscous_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
+                     const int4 *__restrict__ tile_ext, const int2 *__restrict__ tile_rng,
+                     const V4<CT> *__restrict__ A, const V4<T> *__restrict__ B, const int *__restrict__ perm,
+                     const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
+                     const V4<T> *__restrict__ Vw, WallViscConst<T> k, T *__restrict__ dv, int n_targets,
+                     int cap, int list_len, const V4<float> *__restrict__ Fw)
+{
+    extern __shared__ __align__(16) unsigned char tile_smem_raw[];
+    const int tile = blockIdx.x;
+    if (tile >= *n_tiles) return;
+    const int4 desc = tile_desc[tile];
+    const int4 ext = tile_ext[tile];
+    if (ext.w <= 0) return;  // no wall particle in reach of this tile
+    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
+    const int2 *rng = tile_rng + (int64_t)tile * 18;
+    if (threadIdx.x == 0) {
+        tile_locate(sm.hdr, g.n[1], desc, ext);
+        mbar_init(sm.bar, 1);
+    }
+    const int s = desc.x + threadIdx.x % TILE_TB;
+    const bool in_tile = s < desc.y;
+    V4<CT> xi = {};
+    V4<T> bi = {};
+    int orig = n_targets;
+    if (in_tile) {
+        orig = perm[s];
+        xi = A[s];
+        bi = B[s];
+    }
+    const bool valid = in_tile && orig < n_targets;  // slab ghosts are neighbours only
+    uint32_t parity = 0;
+    if (!__syncthreads_or(valid)) return;  // nothing staged yet
+    int cx = ext.x, cy, cz;
+    if (valid) cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    const T rho_a = bi.w, m_a = (T)xi.w;
+    T acc[3] = {0, 0, 0};
+    NbSet<T, CT, V4<T>, false> nb{wcell_start, Aw, Vw, nullptr, Fw};
+    tile_sweep<KS, ND, T, CT>(
+        sm, g, nb, rng + 9, valid, cx, xi, k.radius2, parity, [&](const V4<CT> &xj, const V4<T> &wj, T) {
+            T pd[3];
+            const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+            if (d2 > k.radius2) return;
+            const T dist = sqrt_rn(d2);
+            if (dist < k.almostzero) return;
+            const T wdr = SmoothingKernel<KERNEL, T>::dw_div_r(k.kern, dist);
+            const T rho_b = wj.w, m_b = (T)xj.w;
+            const T vd[3] = {bi.x - wj.x, bi.y - wj.y, ND == 3 ? bi.z - wj.z : (T)0};
+            T grad[3] = {0, 0, 0};
+#pragma unroll
+            for (int d = 0; d < ND; ++d) grad[d] = wdr * pd[d];
+            const T d2e = dist * dist + k.eps_h2;
+            if (k.model == 1) {
+                // ArtificialViscosityMonaghan (viscosity.jl:89-132)
+                T vr = vd[0] * pd[0] + vd[1] * pd[1];
+                if (ND == 3) vr += vd[2] * pd[2];
+                if (vr < (T)0) {
+                    const T rho_mean = (rho_a + rho_b) / (T)2;
+                    const T mu = div_fast(k.h * vr, d2e);
+                    const T dvv = div_fast(m_b * k.alpha * k.c * mu + m_b * k.beta * (mu * mu), rho_mean);
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) acc[d] += dvv * grad[d];
+                }
+            } else {
+                T pg = pd[0] * grad[0] + pd[1] * grad[1];
+                if (ND == 3) pg += pd[2] * grad[2];
+                T coef;
+                if (k.model == 2) {
+                    // ViscosityMorris (viscosity.jl:163-205)
+                    const T mu_a = k.nu_a * rho_a, mu_b = k.nu_b * rho_b;
+                    coef = div_fast(m_b * (mu_a + mu_b) * pg, rho_a * rho_b * d2e);
+                } else {
+                    // ViscosityAdami (viscosity.jl:222-279)
+                    const T eta_a = k.nu_a * rho_a, eta_b = k.nu_b * rho_b;
+                    const T volume_a = div_fast(m_a, rho_a), volume_b = div_fast(m_b, rho_b);
+                    const T tmp = div_fast((T)2 * eta_a * eta_b, (eta_a + eta_b) * d2e * m_a);
+                    coef = (volume_a * volume_a + volume_b * volume_b) * pg * tmp;
+                }
+#pragma unroll
+                for (int d = 0; d < ND; ++d) acc[d] += coef * vd[d];
+            }
+        });
+    tile_reduce<KS, 3>(sm, acc);
+    if (!valid || threadIdx.x >= TILE_TB) return;
+    const int64_t o = (int64_t)orig * NV;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) dv[o + d] += acc[d];
+}
+
 // ------------------------------------------------------------------ Adami (variant 2)
 // Most wall particles of a tank are far from any fluid.  One warp per wall tile checks whether
 // the tile's neighbour rows hold any fluid particle: if not, it writes the result of an empty
@@ -901,7 +998,8 @@ __global__ void __launch_bounds__(256)
 k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
                  const V4<CT> *__restrict__ Aw, const int *__restrict__ fcell_start, T rho_empty,
                  V2<T> *__restrict__ W, T *__restrict__ volume, int *__restrict__ active,
-                 int *__restrict__ n_active, int2 *__restrict__ rng, int4 *__restrict__ ext)
+                 int *__restrict__ n_active, int2 *__restrict__ rng, int4 *__restrict__ ext,
+                 V4<T> *__restrict__ Vw /* no-slip wall: (v_w, rho_w) records; else nullptr */)
 {
     constexpr int NROWS = ND == 3 ? 9 : 3;
     const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -935,9 +1033,13 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     V2<T> empty;
     empty.x = (T)0;
     empty.y = rho_empty;
+    V4<T> vempty;
+    vempty.x = vempty.y = vempty.z = (T)0;
+    vempty.w = rho_empty;
     for (int w = d.x + lane; w < d.y; w += 32) {
         W[w] = empty;
         volume[w] = (T)0;
+        if (Vw) Vw[w] = vempty;
     }
 }
 
@@ -949,16 +1051,21 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
 // at 72 KB).  Blocks walk the active list with a grid stride; with the default grid (one block per
 // tile slot) the hardware scheduler balances the tiles, which measured better than a persistent
 // grid (0.100 vs 0.113 ms).
+// NOSLIP (boundary_model.viscosity !== nothing): the same sweep also interpolates the fluid velocity,
+// v_w = -sum_f v_f W / sum_f W (interpolate_fluid_velocity! / compute_wall_velocity!,
+// dummy_particles.jl:710-758), and writes the records (v_w, rho_w) that k_wall_viscous_tiles stages;
+// three more accumulators, so two blocks per SM.  The free-slip instantiation is unchanged.
 constexpr int ADAMI_BLOCKS_PER_SM = 3;
-template <int KS, int ND, typename T, typename CT, int KERNEL>
-__global__ void __launch_bounds__(KS * TILE_TB, (KS > 1 && sizeof(T) == 4) ? ADAMI_BLOCKS_PER_SM : 2)
+constexpr int ADAMI_NOSLIP_RED = 6;  // tile_reduce slots of the no-slip version (5 values)
+template <int KS, int ND, typename T, typename CT, int KERNEL, bool NOSLIP = false>
+__global__ void __launch_bounds__(KS * TILE_TB, (KS > 1 && sizeof(T) == 4 && !NOSLIP) ? ADAMI_BLOCKS_PER_SM : 2)
 k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__restrict__ active,
               const int4 *__restrict__ tile_desc, const int4 *__restrict__ tile_ext,
               const int2 *__restrict__ tile_rng, const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
               const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
               const V4<T> *__restrict__ B, const T *__restrict__ P, int interaction_enabled,
               AdamiConst<T> k, V2<T> *__restrict__ W, T *__restrict__ volume, int cap, int list_len,
-              const V4<float> *__restrict__ Ff)
+              const V4<float> *__restrict__ Ff, V4<T> *__restrict__ Vw = nullptr)
 {
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     const int n_act = *n_active;
@@ -989,7 +1096,8 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
             cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
         }
         __syncthreads();
-        T acc[2] = {0, 0};
+        constexpr int NACC = NOSLIP ? 5 : 2;
+        T acc[NACC] = {};
         T &p = acc[0], &vol = acc[1];
         if (interaction_enabled) {
             tile_sweep_staged<KS, ND, T, CT>(
@@ -1006,6 +1114,11 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
                         const float kw = ok ? kernel_safe<KERNEL, float>(k.kern, dist) : 0.0f;
                         p = fmaf(k.p_off + pj + hyd, kw, p);
                         vol += kw;
+                        if constexpr (NOSLIP) {
+                            acc[2] = fmaf(kw, bj.x, acc[2]);
+                            acc[3] = fmaf(kw, bj.y, acc[3]);
+                            if (ND == 3) acc[4] = fmaf(kw, bj.z, acc[4]);
+                        }
                         return;
                     }
                     if (d2 <= k.radius2) {
@@ -1017,18 +1130,35 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
                         const T kw = kernel_safe<KERNEL, T>(k.kern, dist);
                         p += sum_p * kw;
                         vol += kw;
+                        if constexpr (NOSLIP) {
+                            acc[2] += kw * bj.x;
+                            acc[3] += kw * bj.y;
+                            if (ND == 3) acc[4] += kw * bj.z;
+                        }
                     }
                 });
         }
-        tile_reduce<KS, 2>(sm, acc);
+        if constexpr (NOSLIP)
+            tile_reduce<KS, NACC, T, CT, ADAMI_NOSLIP_RED>(sm, acc);
+        else
+            tile_reduce<KS, 2>(sm, acc);
         if (valid && threadIdx.x < TILE_TB) {
-            if ((double)vol > 2.220446049250313e-16) p = p / vol;  // `volume > eps()`: eps(Float64)
+            const bool has_fluid = (double)vol > 2.220446049250313e-16;  // `volume > eps()`: eps(Float64)
+            if (has_fluid) p = p / vol;
             if (k.clip) p = p > (T)0 ? p : (T)0;
             V2<T> out;
             out.x = p;
             out.y = eos_inverse(k.eos, p);
             W[w] = out;
             volume[w] = vol;
+            if constexpr (NOSLIP) {
+                V4<T> vw;
+                vw.x = has_fluid ? (T)0 - acc[2] / vol : acc[2];
+                vw.y = has_fluid ? (T)0 - acc[3] / vol : acc[3];
+                vw.z = ND == 3 ? (has_fluid ? (T)0 - acc[4] / vol : acc[4]) : (T)0;
+                vw.w = out.y;
+                Vw[w] = vw;
+            }
         }
     }
 }
