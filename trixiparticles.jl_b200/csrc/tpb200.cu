@@ -64,7 +64,9 @@ struct Semi {
     int *h_flags = nullptr;  // pinned
     void *d_A = nullptr, *d_B = nullptr, *d_P = nullptr;
     void *d_Aw = nullptr, *d_Ww = nullptr, *d_volw = nullptr;
+    void *d_Pw = nullptr;  // no-slip wall: p_w of the sorted wall particles as a scalar array
     void *d_Vw = nullptr;  // no-slip wall: (cache.wall_velocity, rho_w) of the sorted wall particles (V4<T>)
+    bool wall_viscous_done = false;   // this kick's interact! sweep carried the wall's viscous term
     bool wall_velocity_done = false;  // this kick's Adami sweep has written d_Vw already (fused tile version)
     int *d_perm_w = nullptr;
     void *d_scratch = nullptr;  // max(n_f, n_w) * sizeof(double): field unsort
@@ -442,14 +444,14 @@ struct Ops {
                    s.tiles.d_wrow_tile_start + s.tiles.nrows, s.tiles.d_wtile_desc, (const V4<CT> *)s.d_Aw,
                    s.d_fcell_start, rho_empty, (V2<T> *)s.d_Ww, (T *)s.d_volw, s.tiles.d_wactive,
                    s.tiles.d_n_wactive, s.tiles.d_wtile_rng, s.tiles.d_wtile_ext,
-                   fused ? (V4<T> *)s.d_Vw : (V4<T> *)nullptr);
+                   fused ? (V4<T> *)s.d_Vw : (V4<T> *)nullptr, (T *)s.d_Pw);
             if (fused) {
                 LAUNCH(s, (k_adami_tiles<KS, ND, T, CT, KERNEL, true>), grid, KS * TILE_TB, smem, g,
                        s.tiles.d_n_wactive, s.tiles.d_wactive, s.tiles.d_wtile_desc, s.tiles.d_wtile_ext,
                        s.tiles.d_wtile_rng, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
                        s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
                        s.interaction[1][0], k, (V2<T> *)s.d_Ww, (T *)s.d_volw, cap, list_len,
-                       (const V4<float> *)s.d_Ff, (V4<T> *)s.d_Vw);
+                       (const V4<float> *)s.d_Ff, (V4<T> *)s.d_Vw, (T *)s.d_Pw);
                 return TPB_OK;
             }
             LAUNCH(s, (k_adami_tiles<KS, ND, T, CT, KERNEL>), grid, KS * TILE_TB, smem, g,
@@ -477,16 +479,13 @@ struct Ops {
         T R = kern.support;
         LAUNCH(s, (k_wall_velocity<ND, T, CT, KERNEL>), cdiv(n, 128), 128, 0, n, g, (const V4<CT> *)s.d_Aw,
                s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.interaction[1][0], kern,
-               (T)(R * R), (const V2<T> *)s.d_Ww, (V4<T> *)s.d_Vw);
+               (T)(R * R), (const V2<T> *)s.d_Ww, (V4<T> *)s.d_Vw, (T *)s.d_Pw);
         return TPB_OK;
     }
 
     // ---- ... and the wall model's viscous term of the fluid after interact!
-    template <int KERNEL, int DENS>
-    static int launch_wall_viscous(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc, T *d_dv)
+    static WallViscConst<T> make_wall_visc_const(const Semi &s, const PairConst<T> &pc)
     {
-        constexpr int NV = DENS == 0 ? ND + 1 : ND;
-        int n = (int)s.n_act;
         WallViscConst<T> k;
         k.kern = pc.kern;
         k.model = s.wp.has_viscosity;
@@ -504,23 +503,16 @@ struct Ops {
         k.c = pc.c;
         k.radius2 = pc.radius2;
         k.almostzero = pc.almostzero;
-        if (use_tiles(s)) {
-            const int list_len = s.tiles.list(KS);
-            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, list_len, KS);
-            const size_t smem = tile_smem_bytes<T, CT>(cap, list_len, KS);
-            static bool attr_set = false;
-            if (!attr_set) {
-                int rc = set_smem(s, k_wall_viscous_tiles<KS, ND, T, CT, KERNEL, NV>, 227 * 1024);
-                if (rc) return rc;
-                attr_set = true;
-            }
-            LAUNCH(s, (k_wall_viscous_tiles<KS, ND, T, CT, KERNEL, NV>), s.tiles.max_ftiles, KS * TILE_TB, smem, g,
-                   s.tiles.d_frow_tile_start + s.tiles.nrows, s.tiles.d_ftile_desc, s.tiles.d_ftile_ext,
-                   s.tiles.d_ftile_rng, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.d_perm_f,
-                   s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V4<T> *)s.d_Vw, k, d_dv, (int)s.n_tgt, cap,
-                   list_len, (const V4<float> *)s.d_Fw);
-            return TPB_OK;
-        }
+        return k;
+    }
+
+    // (per-particle variant; the tile sweep has the term inside k_interact_tiles<NOSLIP>)
+    template <int KERNEL, int DENS>
+    static int launch_wall_viscous(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc, T *d_dv)
+    {
+        constexpr int NV = DENS == 0 ? ND + 1 : ND;
+        int n = (int)s.n_act;
+        const WallViscConst<T> k = make_wall_visc_const(s, pc);
         LAUNCH(s, (k_wall_viscous<ND, T, CT, KERNEL, NV>), cdiv(n, 128), 128, 0, n, g, s.d_fcell_start,
                (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.d_perm_f, s.d_wcell_start,
                (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, (const V4<T> *)s.d_Vw, k, d_dv, (int)s.n_tgt);
@@ -539,6 +531,7 @@ struct Ops {
         }
         src.damping = (T)s.fp.damping_coefficient;
         int has_wall = s.n_w > 0 && s.interaction[0][1];
+        s.wall_viscous_done = false;
         s.stats.interact_variant_used = use_tiles(s) ? 2 : 1;
         if (use_tiles(s)) {
             const int list_len = s.tiles.list(KS);
@@ -548,7 +541,21 @@ struct Ops {
             if (!attr_set) {
                 int rc = set_smem(s, k_interact_tiles<KS, ND, T, CT, KERNEL, DENS>, 227 * 1024);
                 if (rc) return rc;
+                rc = set_smem(s, k_interact_tiles<KS, ND, T, CT, KERNEL, DENS, true>, 227 * 1024);
+                if (rc) return rc;
                 attr_set = true;
+            }
+            if (has_wall && s.wp.has_viscosity) {
+                // no-slip wall: pressure and viscous term of the wall in one sweep
+                s.wall_viscous_done = true;
+                LAUNCH(s, (k_interact_tiles<KS, ND, T, CT, KERNEL, DENS, true>), s.tiles.max_ftiles, KS * TILE_TB,
+                       smem, g, s.tiles.d_frow_tile_start + s.tiles.nrows, s.tiles.d_ftile_desc,
+                       s.tiles.d_ftile_ext, s.tiles.d_ftile_rng, s.d_fcell_start, (const V4<CT> *)s.d_A,
+                       (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f, s.interaction[0][0], has_wall,
+                       s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv,
+                       (int)s.n_tgt, cap, list_len, (const V4<float> *)s.d_Ff, (const V4<float> *)s.d_Fw,
+                       (const V4<T> *)s.d_Vw, (const T *)s.d_Pw, make_wall_visc_const(s, pc));
+                return TPB_OK;
             }
             LAUNCH(s, (k_interact_tiles<KS, ND, T, CT, KERNEL, DENS>), s.tiles.max_ftiles, KS * TILE_TB, smem, g,
                    s.tiles.d_frow_tile_start + s.tiles.nrows, s.tiles.d_ftile_desc, s.tiles.d_ftile_ext,
@@ -653,7 +660,7 @@ struct Ops {
         else
             rc = summ ? launch_interact<3, 1>(s, g, pc, d_dv) : launch_interact<3, 0>(s, g, pc, d_dv);
         if (rc) return rc;
-        if (s.n_w > 0 && s.wp.has_viscosity && s.interaction[0][1]) {
+        if (s.n_w > 0 && s.wp.has_viscosity && s.interaction[0][1] && !s.wall_viscous_done) {
             if (fk == 0)
                 rc = summ ? launch_wall_viscous<0, 1>(s, g, pc, d_dv) : launch_wall_viscous<0, 0>(s, g, pc, d_dv);
             else if (fk == 1)
@@ -938,7 +945,7 @@ static void free_device(Semi &s)
 {
     void *ptrs[] = {s.d_mass_f, s.d_u, s.d_v, s.d_dv, s.d_du, s.d_key, s.d_slot, s.d_tmp_perm,
                     s.d_perm_f, s.d_count, s.d_fcell_start, s.d_wcell_start, s.d_block_sums,
-                    s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_Vw, s.d_perm_w,
+                    s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_Vw, s.d_Pw, s.d_perm_w,
                     s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1240,6 +1247,8 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     if (s->wp.has_viscosity) {
         CUDA_TRY(s, cudaMalloc(&s->d_Vw, 4 * ts * (nw + 8)));
         CUDA_TRY(s, cudaMemset(s->d_Vw, 0, 4 * ts * (nw + 8)));
+        CUDA_TRY(s, cudaMalloc(&s->d_Pw, ts * (nw + 8)));
+        CUDA_TRY(s, cudaMemset(s->d_Pw, 0, ts * (nw + 8)));
     }
     CUDA_TRY(s, cudaMalloc(&s->d_scratch, sizeof(double) * nmax));
     CUDA_TRY(s, cudaMalloc(&s->d_vmax2, sizeof(unsigned long long)));

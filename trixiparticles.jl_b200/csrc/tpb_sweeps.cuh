@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(128)
 k_wall_velocity(int n_w, GridConst<CT> g, const V4<CT> *__restrict__ Aw,
                 const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
                 const V4<T> *__restrict__ B, int interaction_enabled, KernelConst<T> kern, T radius2,
-                const V2<T> *__restrict__ Ww, V4<T> *__restrict__ Vw /* (v_w, rho_w) */)
+                const V2<T> *__restrict__ Ww, V4<T> *__restrict__ Vw /* (v_w, rho_w) */,
+                T *__restrict__ Pw /* p_w as a scalar array */)
 {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_w) return;
@@ -256,8 +257,10 @@ k_wall_velocity(int n_w, GridConst<CT> g, const V4<CT> *__restrict__ Aw,
     out.x = wv[0];
     out.y = wv[1];
     out.z = ND == 3 ? wv[2] : (T)0;
-    out.w = Ww[w].y;
+    const V2<T> pr = Ww[w];
+    out.w = pr.y;
     Vw[w] = out;
+    Pw[w] = pr.x;
 }
 
 template <typename T>
@@ -271,6 +274,51 @@ struct WallViscConst {
     T c;                  // system_sound_speed(fluid)
     T radius2, almostzero;
 };
+
+// The wall model's viscous term of one accepted pair (fluid particle a, wall particle b with the
+// record wj = (v_w, rho_w)); pd = x_a - x_b, dist >= almostzero.
+template <int ND, typename T, int KERNEL>
+__device__ __forceinline__ void wall_viscous_term(const WallViscConst<T> &k, T m_a, T rho_a, const T (&v_a)[3],
+                                                  T m_b, const V4<T> &wj, const T (&pd)[3], T dist,
+                                                  T (&acc)[3])
+{
+    const T wdr = SmoothingKernel<KERNEL, T>::dw_div_r(k.kern, dist);
+    const T rho_b = wj.w;
+    const T vd[3] = {v_a[0] - wj.x, v_a[1] - wj.y, ND == 3 ? v_a[2] - wj.z : (T)0};
+    T grad[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < ND; ++d) grad[d] = wdr * pd[d];
+    const T d2e = dist * dist + k.eps_h2;
+    if (k.model == 1) {
+        // ArtificialViscosityMonaghan (viscosity.jl:89-132)
+        T vr = vd[0] * pd[0] + vd[1] * pd[1];
+        if (ND == 3) vr += vd[2] * pd[2];
+        if (vr < (T)0) {
+            const T rho_mean = (rho_a + rho_b) / (T)2;
+            const T mu = div_fast(k.h * vr, d2e);
+            const T dvv = div_fast(m_b * k.alpha * k.c * mu + m_b * k.beta * (mu * mu), rho_mean);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) acc[d] += dvv * grad[d];
+        }
+    } else {
+        T pg = pd[0] * grad[0] + pd[1] * grad[1];
+        if (ND == 3) pg += pd[2] * grad[2];
+        T coef;
+        if (k.model == 2) {
+            // ViscosityMorris (viscosity.jl:163-205)
+            const T mu_a = k.nu_a * rho_a, mu_b = k.nu_b * rho_b;
+            coef = div_fast(m_b * (mu_a + mu_b) * pg, rho_a * rho_b * d2e);
+        } else {
+            // ViscosityAdami (viscosity.jl:222-279)
+            const T eta_a = k.nu_a * rho_a, eta_b = k.nu_b * rho_b;
+            const T volume_a = div_fast(m_a, rho_a), volume_b = div_fast(m_b, rho_b);
+            const T tmp = div_fast((T)2 * eta_a * eta_b, (eta_a + eta_b) * d2e * m_a);
+            coef = (volume_a * volume_a + volume_b * volume_b) * pg * tmp;
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) acc[d] += coef * vd[d];
+    }
+}
 
 // One thread per sorted fluid particle: dv[1:ND, a] += sum_w viscous term (wall's model).
 template <int ND, typename T, typename CT, int KERNEL, int NV>
@@ -287,6 +335,7 @@ k_wall_viscous(int n_f, GridConst<CT> g, const int *__restrict__ fcell_start,
     const V4<CT> xi = A[s];
     const V4<T> bi = B[s];
     const T rho_a = bi.w, m_a = (T)xi.w;
+    const T v_a[3] = {bi.x, bi.y, bi.z};
     int cx, cy, cz;
     cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
     T acc[3] = {0, 0, 0};
@@ -298,43 +347,7 @@ k_wall_viscous(int n_f, GridConst<CT> g, const int *__restrict__ fcell_start,
             if (d2 > k.radius2) continue;
             const T dist = sqrt_rn(d2);
             if (dist < k.almostzero) continue;
-            const T wdr = SmoothingKernel<KERNEL, T>::dw_div_r(k.kern, dist);
-            const V4<T> vw = Vw[j];
-            const T rho_b = Ww[j].y, m_b = (T)xj.w;
-            T vd[3] = {bi.x - vw.x, bi.y - vw.y, ND == 3 ? bi.z - vw.z : (T)0};
-            T grad[3];
-#pragma unroll
-            for (int d = 0; d < ND; ++d) grad[d] = wdr * pd[d];
-            const T d2e = dist * dist + k.eps_h2;
-            if (k.model == 1) {
-                // ArtificialViscosityMonaghan (viscosity.jl:89-132)
-                T vr = vd[0] * pd[0] + vd[1] * pd[1];
-                if (ND == 3) vr += vd[2] * pd[2];
-                if (vr < (T)0) {
-                    const T rho_mean = (rho_a + rho_b) / (T)2;
-                    const T mu = div_fast(k.h * vr, d2e);
-                    const T dvv = div_fast(m_b * k.alpha * k.c * mu + m_b * k.beta * (mu * mu), rho_mean);
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) acc[d] += dvv * grad[d];
-                }
-            } else {
-                T pg = pd[0] * grad[0] + pd[1] * grad[1];
-                if (ND == 3) pg += pd[2] * grad[2];
-                T coef;
-                if (k.model == 2) {
-                    // ViscosityMorris (viscosity.jl:163-205)
-                    const T mu_a = k.nu_a * rho_a, mu_b = k.nu_b * rho_b;
-                    coef = div_fast(m_b * (mu_a + mu_b) * pg, rho_a * rho_b * d2e);
-                } else {
-                    // ViscosityAdami (viscosity.jl:222-279)
-                    const T eta_a = k.nu_a * rho_a, eta_b = k.nu_b * rho_b;
-                    const T volume_a = div_fast(m_a, rho_a), volume_b = div_fast(m_b, rho_b);
-                    const T tmp = div_fast((T)2 * eta_a * eta_b, (eta_a + eta_b) * d2e * m_a);
-                    coef = (volume_a * volume_a + volume_b * volume_b) * pg * tmp;
-                }
-#pragma unroll
-                for (int d = 0; d < ND; ++d) acc[d] += coef * vd[d];
-            }
+            wall_viscous_term<ND, T, KERNEL>(k, m_a, rho_a, v_a, (T)xj.w, Vw[j], pd, dist, acc);
         }
     });
     const int64_t o = (int64_t)perm[s] * NV;

@@ -745,7 +745,11 @@ __device__ __forceinline__ void tile_reduce(TileSmem<T, CT> &sm, T (&val)[NVAL])
 }
 
 // ------------------------------------------------------------------ interact! (variant 2)
-template <int KS, int ND, typename T, typename CT, int KERNEL, int DENS>
+// NOSLIP (boundary_model.viscosity !== nothing): the wall records are (x, m | v_w, rho_w | p_w) -- the
+// shape of the fluid's -- and the wall sweep adds the wall model's viscous term with v_b = v_w
+// (dv_viscosity!, viscosity.jl:9-40; viscous_velocity, wall_boundary/system.jl:148-163) right after the
+// pressure term, as rhs.jl:85-96 does.  The free-slip instantiation is unchanged.
+template <int KS, int ND, typename T, typename CT, int KERNEL, int DENS, bool NOSLIP = false>
 __global__ void __launch_bounds__(KS * TILE_TB, 2)
 k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
                  const int4 *__restrict__ tile_ext, const int2 *__restrict__ tile_rng,
@@ -755,7 +759,9 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
                  const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
                  const V2<T> *__restrict__ Ww, PairConst<T> k, SourceConst<T> src,
                  T *__restrict__ dv, int n_targets, int cap, int list_len,
-                 const V4<float> *__restrict__ Ff, const V4<float> *__restrict__ Fw)
+                 const V4<float> *__restrict__ Ff, const V4<float> *__restrict__ Fw,
+                 const V4<T> *__restrict__ Vw = nullptr, const T *__restrict__ Pw = nullptr,
+                 WallViscConst<T> wk = WallViscConst<T>())
 {
     constexpr int NV = DENS == 0 ? ND + 1 : ND;
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
@@ -841,7 +847,32 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     }
     T(&dv_fw)[3] = *reinterpret_cast<T(*)[3]>(acc + 4);
     T &drho_fw = acc[7];
-    if (has_wall && any_fw) {
+    if constexpr (NOSLIP) {
+        if (has_wall && any_fw) {
+            const T zero3[3] = {0, 0, 0};
+            NbSet<T, CT, V4<T>, true> nb{wcell_start, Aw, Vw, Pw, Fw};
+            tile_sweep<KS, ND, T, CT>(sm, g, nb, rng + 9, valid, cx, xi, k.radius2, parity,
+                                  [&](const V4<CT> &xj, const V4<T> &wj, T pj) {
+                                      if constexpr (FAST)
+                                          interact_pair_fast<ND, KERNEL, DENS, false>(
+                                              fc, xi, xj, rho_a, p_a, pa_term, v_a, 0.f, 0.f, 0.f, wj.w, pj,
+                                              dv_fw, drho_fw);
+                                      T pd[3];
+                                      const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                                      if (d2 <= k.radius2) {
+                                          const T dist = sqrt_rn(d2);
+                                          if (dist >= k.almostzero) {
+                                              if constexpr (!FAST)
+                                                  interact_pair<ND, T, KERNEL, DENS, false>(
+                                                      k, (T)xj.w, rho_a, wj.w, p_a, pj, v_a, zero3, pd, dist,
+                                                      dv_fw, drho_fw);
+                                              wall_viscous_term<ND, T, KERNEL>(wk, (T)xi.w, rho_a, v_a, (T)xj.w,
+                                                                               wj, pd, dist, dv_fw);
+                                          }
+                                      }
+                                  });
+        }
+    } else if (has_wall && any_fw) {
         const T zero3[3] = {0, 0, 0};
         NbSet<T, CT, V2<T>, false> nb{wcell_start, Aw, Ww, nullptr, Fw};
         tile_sweep<KS, ND, T, CT>(sm, g, nb, rng + 9, valid, cx, xi, k.radius2, parity,
@@ -893,101 +924,6 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     }
 }
 
-// ------------------------------------------------------------------ no-slip wall: viscous term (variant 2)
-// The wall model's viscous term of the fluid (dv_viscosity!, viscosity.jl:9-40, with v_b = v_w:
-// viscous_velocity, wall_boundary/system.jl:148-163) as a tile sweep of its own over the wall records
-// (x, m | v_w, rho_w), launched after k_interact_tiles: dv[1:ND, a] += sum_w.  Fluid tiles without a
-// wall particle in reach (most of them) exit at once; k_interact_tiles keeps its register budget.
-template <int KS, int ND, typename T, typename CT, int KERNEL, int NV>
-__global__ void __launch_bounds__(KS * TILE_TB, 2)
-k_wall_viscous_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
-                     const int4 *__restrict__ tile_ext, const int2 *__restrict__ tile_rng,
-                     const V4<CT> *__restrict__ A, const V4<T> *__restrict__ B, const int *__restrict__ perm,
-                     const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
-                     const V4<T> *__restrict__ Vw, WallViscConst<T> k, T *__restrict__ dv, int n_targets,
-                     int cap, int list_len, const V4<float> *__restrict__ Fw)
-{
-    extern __shared__ __align__(16) unsigned char tile_smem_raw[];
-    const int tile = blockIdx.x;
-    if (tile >= *n_tiles) return;
-    const int4 desc = tile_desc[tile];
-    const int4 ext = tile_ext[tile];
-    if (ext.w <= 0) return;  // no wall particle in reach of this tile
-    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
-    const int2 *rng = tile_rng + (int64_t)tile * 18;
-    if (threadIdx.x == 0) {
-        tile_locate(sm.hdr, g.n[1], desc, ext);
-        mbar_init(sm.bar, 1);
-    }
-    const int s = desc.x + threadIdx.x % TILE_TB;
-    const bool in_tile = s < desc.y;
-    V4<CT> xi = {};
-    V4<T> bi = {};
-    int orig = n_targets;
-    if (in_tile) {
-        orig = perm[s];
-        xi = A[s];
-        bi = B[s];
-    }
-    const bool valid = in_tile && orig < n_targets;  // slab ghosts are neighbours only
-    uint32_t parity = 0;
-    if (!__syncthreads_or(valid)) return;  // nothing staged yet
-    int cx = ext.x, cy, cz;
-    if (valid) cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
-    const T rho_a = bi.w, m_a = (T)xi.w;
-    T acc[3] = {0, 0, 0};
-    NbSet<T, CT, V4<T>, false> nb{wcell_start, Aw, Vw, nullptr, Fw};
-    tile_sweep<KS, ND, T, CT>(
-        sm, g, nb, rng + 9, valid, cx, xi, k.radius2, parity, [&](const V4<CT> &xj, const V4<T> &wj, T) {
-            T pd[3];
-            const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
-            if (d2 > k.radius2) return;
-            const T dist = sqrt_rn(d2);
-            if (dist < k.almostzero) return;
-            const T wdr = SmoothingKernel<KERNEL, T>::dw_div_r(k.kern, dist);
-            const T rho_b = wj.w, m_b = (T)xj.w;
-            const T vd[3] = {bi.x - wj.x, bi.y - wj.y, ND == 3 ? bi.z - wj.z : (T)0};
-            T grad[3] = {0, 0, 0};
-#pragma unroll
-            for (int d = 0; d < ND; ++d) grad[d] = wdr * pd[d];
-            const T d2e = dist * dist + k.eps_h2;
-            if (k.model == 1) {
-                // ArtificialViscosityMonaghan (viscosity.jl:89-132)
-                T vr = vd[0] * pd[0] + vd[1] * pd[1];
-                if (ND == 3) vr += vd[2] * pd[2];
-                if (vr < (T)0) {
-                    const T rho_mean = (rho_a + rho_b) / (T)2;
-                    const T mu = div_fast(k.h * vr, d2e);
-                    const T dvv = div_fast(m_b * k.alpha * k.c * mu + m_b * k.beta * (mu * mu), rho_mean);
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) acc[d] += dvv * grad[d];
-                }
-            } else {
-                T pg = pd[0] * grad[0] + pd[1] * grad[1];
-                if (ND == 3) pg += pd[2] * grad[2];
-                T coef;
-                if (k.model == 2) {
-                    // ViscosityMorris (viscosity.jl:163-205)
-                    const T mu_a = k.nu_a * rho_a, mu_b = k.nu_b * rho_b;
-                    coef = div_fast(m_b * (mu_a + mu_b) * pg, rho_a * rho_b * d2e);
-                } else {
-                    // ViscosityAdami (viscosity.jl:222-279)
-                    const T eta_a = k.nu_a * rho_a, eta_b = k.nu_b * rho_b;
-                    const T volume_a = div_fast(m_a, rho_a), volume_b = div_fast(m_b, rho_b);
-                    const T tmp = div_fast((T)2 * eta_a * eta_b, (eta_a + eta_b) * d2e * m_a);
-                    coef = (volume_a * volume_a + volume_b * volume_b) * pg * tmp;
-                }
-#pragma unroll
-                for (int d = 0; d < ND; ++d) acc[d] += coef * vd[d];
-            }
-        });
-    tile_reduce<KS, 3>(sm, acc);
-    if (!valid || threadIdx.x >= TILE_TB) return;
-    const int64_t o = (int64_t)orig * NV;
-#pragma unroll
-    for (int d = 0; d < ND; ++d) dv[o + d] += acc[d];
-}
-
 // ------------------------------------------------------------------ Adami (variant 2)
 // Most wall particles of a tank are far from any fluid.  One warp per wall tile checks whether
 // the tile's neighbour rows hold any fluid particle: if not, it writes the result of an empty
@@ -999,7 +935,8 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
                  const V4<CT> *__restrict__ Aw, const int *__restrict__ fcell_start, T rho_empty,
                  V2<T> *__restrict__ W, T *__restrict__ volume, int *__restrict__ active,
                  int *__restrict__ n_active, int2 *__restrict__ rng, int4 *__restrict__ ext,
-                 V4<T> *__restrict__ Vw /* no-slip wall: (v_w, rho_w) records; else nullptr */)
+                 V4<T> *__restrict__ Vw /* no-slip wall: (v_w, rho_w) records; else nullptr */,
+                 T *__restrict__ Pw /* no-slip wall: p_w as a scalar array */)
 {
     constexpr int NROWS = ND == 3 ? 9 : 3;
     const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1039,7 +976,10 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
     for (int w = d.x + lane; w < d.y; w += 32) {
         W[w] = empty;
         volume[w] = (T)0;
-        if (Vw) Vw[w] = vempty;
+        if (Vw) {
+            Vw[w] = vempty;
+            Pw[w] = (T)0;
+        }
     }
 }
 
@@ -1053,7 +993,7 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
 // grid (0.100 vs 0.113 ms).
 // NOSLIP (boundary_model.viscosity !== nothing): the same sweep also interpolates the fluid velocity,
 // v_w = -sum_f v_f W / sum_f W (interpolate_fluid_velocity! / compute_wall_velocity!,
-// dummy_particles.jl:710-758), and writes the records (v_w, rho_w) that k_wall_viscous_tiles stages;
+// dummy_particles.jl:710-758), and writes the records (v_w, rho_w | p_w) that k_interact_tiles<NOSLIP> stages;
 // three more accumulators, so two blocks per SM.  The free-slip instantiation is unchanged.
 constexpr int ADAMI_BLOCKS_PER_SM = 3;
 constexpr int ADAMI_NOSLIP_RED = 6;  // tile_reduce slots of the no-slip version (5 values)
@@ -1065,7 +1005,7 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
               const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
               const V4<T> *__restrict__ B, const T *__restrict__ P, int interaction_enabled,
               AdamiConst<T> k, V2<T> *__restrict__ W, T *__restrict__ volume, int cap, int list_len,
-              const V4<float> *__restrict__ Ff, V4<T> *__restrict__ Vw = nullptr)
+              const V4<float> *__restrict__ Ff, V4<T> *__restrict__ Vw = nullptr, T *__restrict__ Pw = nullptr)
 {
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     const int n_act = *n_active;
@@ -1158,6 +1098,7 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
                 vw.z = ND == 3 ? (has_fluid ? (T)0 - acc[4] / vol : acc[4]) : (T)0;
                 vw.w = out.y;
                 Vw[w] = vw;
+                Pw[w] = p;
             }
         }
     }
