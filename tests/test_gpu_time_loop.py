@@ -150,3 +150,36 @@ def test_float32_run_tracks_float64_trace():
     r = V.run(t_end=0.3, eltype=np.float32)
     err = np.abs(r["got"] - r["ref"])
     assert err.max() <= 2e-3
+
+
+def test_no_slip_wall_time_loop_slows_the_surge_front():
+    """2-D dam break with `viscosity_wall = viscosity` (examples/fluid/dam_break_2d.jl:78-80: no-slip wall)
+    through the whole time loop: the CUDA-graph replay (k_adami_tiles<NOSLIP>, k_interact_tiles<NOSLIP>)
+    gives the bits of the eager loop, and a viscous no-slip floor holds the surge front back compared with
+    the free-slip wall."""
+    import trixiparticles.jl_b200 as tp
+    from trixiparticles.jl_b200 import examples
+    from trixiparticles.jl_b200.time_integration import CarpenterKennedy2N54, StepsizeCallback, solve
+
+    def front(wall_viscosity, cuda_graph):
+        fluid, wall, tank = examples.dam_break_2d(20)
+        wall.boundary_model.viscosity = wall_viscosity
+        semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+        ode = tp.semidiscretize(semi, (0.0, 0.35))
+        sol = solve(ode, CarpenterKennedy2N54(williamson_condition=False), callback=[StepsizeCallback(cfl=0.9)],
+                    cuda_graph=cuda_graph)
+        assert sol.retcode == "Success"
+        u = sol.u.cpu().numpy().reshape(-1, 2)
+        v = sol.v.cpu().numpy().reshape(-1, 3)
+        semi.close()
+        assert np.isfinite(u).all() and np.isfinite(v).all()
+        return u, v
+
+    u_free, _ = front(None, True)
+    u_ns, v_ns = front(tp.ViscosityAdami(nu=0.05), True)
+    u_ns_eager, v_ns_eager = front(tp.ViscosityAdami(nu=0.05), False)
+    assert np.array_equal(u_ns, u_ns_eager) and np.array_equal(v_ns, v_ns_eager)
+    x_free, x_ns = u_free[:, 0].max(), u_ns[:, 0].max()
+    print(f"surge front at t = 0.35 s: free-slip {x_free:.4f} m, no-slip {x_ns:.4f} m")
+    assert x_free > 1.3                      # the column (1.2 m wide) has started to run
+    assert x_ns < x_free - 1e-3              # the no-slip floor holds the front back
