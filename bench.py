@@ -234,6 +234,10 @@ def run_single(args):
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     fluid, wall, u, v = make_workload(args.workload, args.eltype, args.coords, args.shuffle)
+    if args.no_slip:
+        # no-slip wall (`viscosity_wall = viscosity_fluid`) on a synthetic velocity field; not the headline
+        wall.boundary_model.viscosity = fluid.viscosity
+        v[:, :fluid.ndims] = (0.05 * np.sin(40.0 * u)).astype(v.dtype)
     nd, n_f, n_w = fluid.ndims, fluid.nparticles, wall.nparticles
     tsize, csize = np.dtype(fluid.eltype).itemsize, np.dtype(fluid.coordinates_eltype).itemsize
     if args.e2e_only:
@@ -409,7 +413,9 @@ def run_single(args):
                    "ndims": nd, "coords_dtype": "f32" if csize == 4 else "f64",
                    "kernel": type(fluid.smoothing_kernel).__name__,
                    "nhs": "rebuilt every kick", "l2": "flushed between steps (256 MiB write, untimed)",
-                   "interact_variant": int(st1.interact_variant_used)},
+                   "interact_variant": int(st1.interact_variant_used),
+                   **({"wall": "no-slip (wall viscosity = fluid viscosity), synthetic velocity field"}
+                      if args.no_slip else {})},
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         "phases_ms": {**{k: phases[k] for k in _lib.PHASES}, "kick": float(ms_kick.mean()),
                       "drift": float(ms_drift.mean()), "step_min": float(ms_steps.min()),
@@ -502,6 +508,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the other precision set-ups")
     ap.add_argument("--shuffle", action="store_true", help="random particle order in the ODE vectors")
+    ap.add_argument("--no-slip", action="store_true", help="no-slip wall (wall viscosity = fluid viscosity) on a "
+                    "synthetic velocity field instead of the free-slip headline workload")
     ap.add_argument("--evolve", type=int, default=0, help="time steps to run before measuring (evolved state)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
     ap.add_argument("--e2e-only", action="store_true", help="host-pointer (e2e) timing only (tuning runs)")
