@@ -89,12 +89,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, no_slip=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import adapter
         fluid, wall, _ = examples.dam_break_2d(20)
+        if no_slip:   # the wall velocity needs the same fluid as the Adami pressure: no extra exchange
+            import trixiparticles.jl_b200 as tp
+            wall.boundary_model.viscosity = tp.ViscosityAdami(nu=0.01)
         R = _radius(fluid)
         layout = make_layout(fluid.initial_condition.coordinates[:, 0], world, R, R)
         u, v = examples.perturbed_state(fluid)
@@ -124,14 +127,16 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_gloo_two_rank_halo_exchange_reproduces_global_kick(oracle):
+@pytest.mark.parametrize("no_slip", [False, True])
+def test_gloo_two_rank_halo_exchange_reproduces_global_kick(oracle, no_slip):
     """world_size 2 over gloo: the oracle kick on (owned + received ghosts, local wall) equals
-    the global oracle kick on the owned rows to rounding (summation order differs)."""
+    the global oracle kick on the owned rows to rounding (summation order differs); also with a
+    no-slip wall, whose wall velocity is interpolated from the same two-radii ghost layer."""
     world = 2
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out, no_slip)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
