@@ -196,7 +196,8 @@ int32_t tpb_kick(tpb_semi_t semi, void *dv_ode, const void *v_ode, const void *u
 int32_t tpb_drift(tpb_semi_t semi, void *du_ode, const void *v_ode, const void *u_ode, double t);
 
 /* ---- outputs / diagnostics ----------------------------------------------------------------- */
-/* system data after the last kick, in the system's own particle order; `out`: host T[n] */
+/* system data after the last kick, in the system's own particle order; `out`: host T[n]
+ * (TPB_FIELD_WALL_VELOCITY: host T[ndims * n], particle-major; n stays the particle count) */
 int32_t tpb_get_system_field(tpb_semi_t semi, int32_t system, int32_t field, void *out, int64_t n);
 /* Test hook: rebuilds the grids for `u_ode` and writes every ordered neighbour pair
  * (i in `system`, j in `neighbor`, both 0-based) with |x_i - x_j|^2 <= R^2 for the radius of
