@@ -72,6 +72,17 @@ def test_constructor_validation():
         tp.WeaklyCompressibleSPHSystem(f.initial_condition, smoothing_kernel=tp.WendlandC2Kernel(2),
                                        smoothing_length=0.1, density_calculator=tp.ContinuityDensity(),
                                        state_equation=f.state_equation, acceleration=(0.0, 0.0, 1.0))
+    # wall viscosity (no-slip wall): the three models of the accelerated path, nothing else
+    m = w.boundary_model
+    for visc in (tp.ArtificialViscosityMonaghan(alpha=0.02), tp.ViscosityMorris(nu=1e-3), tp.ViscosityAdami(nu=1e-3)):
+        model = tp.BoundaryModelDummyParticles(m.initial_density, m.hydrodynamic_mass, m.density_calculator,
+                                               m.smoothing_kernel, m.smoothing_length,
+                                               state_equation=m.state_equation, viscosity=visc)
+        assert model.viscosity is visc
+    with pytest.raises(ValueError):
+        tp.BoundaryModelDummyParticles(m.initial_density, m.hydrodynamic_mass, m.density_calculator,
+                                       m.smoothing_kernel, m.smoothing_length, state_equation=m.state_equation,
+                                       viscosity="no-slip")
 
 
 def test_state_equation_host_mirror(oracle):
