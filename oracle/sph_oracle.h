@@ -8,7 +8,8 @@
  * links or calls anything in oracle/.
  *
  * Pinning: the oracle reproduces the reference's own known-answer tests
- * (tests/test_oracle_golden.py): Monaghan viscosity pair, Adami kernel weights,
+ * (tests/test_oracle_golden.py): Monaghan / Morris / Adami viscosity pairs, Adami kernel weights, the
+ * no-slip wall velocities (constant and staggered profiles, dummy_particles.jl test :104-303),
  * Cole EOS inverse values, kernel normalisation, conservation properties, and the first
  * samples of the dam-break surge-front trace.  The neighbour search itself lives in the
  * third-party PointNeighbors.jl (compat 0.6.6, not under /root/reference); its published
