@@ -19,10 +19,13 @@ Own arm (default): the CUDA library through the reference-facing API.
             timed on this box's host cores on the same workload.
 Reference arm (--impl reference): the CPU oracle port, all host threads, same workload.
 
-N > 1 (torchrun): the lattice is slab-decomposed along x, one slab per rank, ghost particles are
-exchanged every kick over peer memory (one pack-and-store kernel per neighbour; NCCL send/recv
-with TPB_HALO=nccl; see trixiparticles.jl_b200/slabs.py); "scaling" is "weak": every rank gets a
-slab of the N = 1 size.
+N > 1 (torchrun): BASELINE config 4.  The lattice is slab-decomposed along x, one slab per rank
+(generated locally by every rank), ghost particles are exchanged every kick over peer memory (one
+pack-and-store kernel per neighbour; NCCL send/recv with TPB_HALO=nccl; see
+trixiparticles.jl_b200/slabs.py and slabs_bench.py); "scaling" is "weak": every rank gets a slab of
+`--per-gpu` (12.5 M) fluid particles -- 100 M on 8 GPUs.  The run starts with an in-process parity
+check of the slab path against a single-GPU kick (`parity_check` in the JSON line; failure exits
+non-zero) and carries the 1 M-per-GPU and the 10 M strong-scaling runs as `variants`.
 """
 from __future__ import annotations
 
@@ -48,6 +51,7 @@ UNIT = "particle-RHS/s"
 WORKLOADS = {
     "dam_break_3d_1m": ("dam_break_3d", 0.0126),     # 992 319 fluid + 1 599 800 wall
     "dam_break_3d_10m": ("dam_break_3d", 0.00585),   # ~10 M fluid
+    "dam_break_3d_12m5": ("dam_break_3d", 0.00543),  # ~12.5 M fluid: the per-GPU size of the --gpus N run
     "dam_break_3d_250k": ("dam_break_3d", 0.02),     # reduced sample for slow CPU legs
     "dam_break_3d_small": ("dam_break_3d", 0.05),    # quick functional check
     "dam_break_2d": ("dam_break_2d", 40),            # config 1 (Float64)
@@ -164,10 +168,10 @@ def cpu_step_time(fluid, wall, u, v, reps, nthreads=0):
     from oracle import adapter, oracle as O
     O.build()
     nd = fluid.ndims
-    adapter.kick(fluid, wall, u, v, nthreads=nthreads)  # warm-up (page faults, thread pool)
+    adapter.kick(fluid, wall, u, v, nthreads=nthreads, use_grid=2)  # warm-up (page faults, thread pool, static wall grid)
     t0 = time.perf_counter()
     for _ in range(reps):
-        adapter.kick(fluid, wall, u, v, nthreads=nthreads)
+        adapter.kick(fluid, wall, u, v, nthreads=nthreads, use_grid=2)
         O.drift(v, nd, u.dtype)
     dt = (time.perf_counter() - t0) / reps
     return dt, (nthreads or O.max_threads())
@@ -184,7 +188,7 @@ def run_reference(args):
     # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
     nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     _kick = adapter.kick
-    adapter_kick = lambda *a, **k: _kick(*a, nthreads=nthreads, **k)
+    adapter_kick = lambda *a, **k: _kick(*a, nthreads=nthreads, use_grid=2, **k)   # static wall grid built once
     name = args.workload
     fluid, wall, u, v = make_workload(name)
     nd = fluid.ndims
@@ -315,6 +319,24 @@ def run_single(args):
                           "env": {k: v for k, v in os.environ.items() if k.startswith("TPB_")}}))
         return
 
+    # SURVEY 8(d) timing protocol: >= 200 timed kick!+drift! pairs, median and min (the driver picks
+    # --steps; when it is smaller, the same loop simply runs on)
+    proto = None
+    n_proto = max(200, args.steps)
+    if not args.no_variants:
+        ps = [torch.cuda.Event(enable_timing=True) for _ in range(n_proto)]
+        pe = [torch.cuda.Event(enable_timing=True) for _ in range(n_proto)]
+        for k in range(n_proto):
+            flush.fill_(k & 0xFF)
+            ps[k].record()
+            ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
+            ode.f2(du_d, v_d, u_d, ode.p, 0.0)
+            pe[k].record()
+        torch.cuda.synchronize()
+        pm = np.array([a.elapsed_time(b) for a, b in zip(ps, pe)])
+        proto = {"timed_evaluations": n_proto, "ms_median": float(np.median(pm)), "ms_min": float(pm.min()),
+                 "ms_mean": float(pm.mean()), "value_median": n_f / (float(np.median(pm)) * 1e-3)}
+
     # L2-warm variant (no flush), reported for information
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -355,8 +377,13 @@ def run_single(args):
             limiters = {k: rec[k] for k in ("shared_memory_pipe_pct_of_peak", "issue_slots_pct_of_peak",
                                             "fma_pipe_pct_of_peak", "alu_pipe_pct_of_peak", "l2_hit_rate_pct",
                                             "limiters_note") if k in rec}
+    fp32_tflops = flops / (ms_kick.mean() * 1e-3) / 1e12
     roofline = {
-        "bound": "hbm", "kernel": "interact! phase (fluid-fluid + fluid-wall pair sweep)",
+        "bound": "hbm", "bound_actual": "shared-memory pipe / issue slots: the pair sweep does about 270 flop "
+                                        "per compulsory byte, HBM cannot bound it (see limiters, fp32_frac)",
+        "fp32_frac": fp32_tflops / fp32_peak, "step_frac": step_achieved / peak_gbs,
+        "rebuild_frac": (n_f * 80 / (phases["rebuild"] * 1e-3) / 1e9 / peak_gbs) if phases["rebuild"] > 0 else None,
+        "kernel": "interact! phase (fluid-fluid + fluid-wall pair sweep)",
         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
         "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": k_bytes, "kernel_ms": k_ms,
@@ -393,6 +420,11 @@ def run_single(args):
         variants["moving_fluid_free_slip_wall"] = run_variant(tp, torch, args, "f32", "f32", moving=True)
         variants["moving_fluid_no_slip_wall"] = run_variant(tp, torch, args, "f32", "f32", moving=True,
                                                             no_slip=True)
+        if args.workload == DEFAULT_WORKLOAD:
+            # BASELINE config 4 on one GPU: the 10 M lattice (north_star's size) and the per-GPU size of
+            # the weak-scaling run of `--gpus N` (12.5 M: the denominator of its efficiency)
+            variants["dam_break_3d_10m"] = run_variant(tp, torch, args, "f32", "f32", workload="dam_break_3d_10m")
+            variants["dam_break_3d_12m5"] = run_variant(tp, torch, args, "f32", "f32", workload="dam_break_3d_12m5")
 
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample
     cpu = None
@@ -402,7 +434,8 @@ def run_single(args):
         dt, cores = cpu_step_time(fluid, wall, u, v, reps=reps)
         cpu = {"value": n_f / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{reps} kick!+drift! evaluations of the full workload ({n_f} fluid + {n_w} wall) "
-                         f"with the OpenMP CPU oracle, {1e3 * dt:.1f} ms each"}
+                         f"with the OpenMP CPU oracle (static wall cell list built once and reused, fluid cell list "
+                         f"rebuilt every kick), {1e3 * dt:.1f} ms each"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
@@ -420,14 +453,17 @@ def run_single(args):
         "phases_ms": {**{k: phases[k] for k in _lib.PHASES}, "kick": float(ms_kick.mean()),
                       "drift": float(ms_drift.mean()), "step_min": float(ms_steps.min()),
                       "step_median": float(np.median(ms_steps)), "step_l2_warm": ms_warm},
+        "protocol_200": proto,
         "cpu_baseline": cpu, "variants": variants,
     }
     print(json.dumps(line))
 
 
-def run_variant(tp, torch, args, eltype, coords, steps=10, adaptive=False, no_slip=False, moving=False):
-    """Device-resident kick!+drift! of the same workload in another precision set-up."""
-    fluid, wall, u, v = make_workload(args.workload, eltype, coords, adaptive=adaptive)
+def run_variant(tp, torch, args, eltype, coords, steps=10, adaptive=False, no_slip=False, moving=False,
+                workload=None):
+    """Device-resident kick!+drift! of the same workload in another precision set-up (or of
+    another lattice size: `workload`)."""
+    fluid, wall, u, v = make_workload(workload or args.workload, eltype, coords, adaptive=adaptive)
     if no_slip:
         wall.boundary_model.viscosity = fluid.viscosity
     if moving:
@@ -459,8 +495,17 @@ def run_variant(tp, torch, args, eltype, coords, steps=10, adaptive=False, no_sl
     phases = semi.phase_times()
     n_f = fluid.nparticles
     semi.close()
-    return {"ms_per_step": ms, "value": n_f / (ms * 1e-3), "unit": UNIT, "steps": steps,
-            "dtype": eltype, "coords_dtype": coords, "phases_ms": {k: phases[k] for k in phases}}
+    out = {"ms_per_step": ms, "value": n_f / (ms * 1e-3), "unit": UNIT, "steps": steps,
+           "dtype": eltype, "coords_dtype": coords, "phases_ms": {k: phases[k] for k in phases}}
+    if workload is not None:
+        peak_gbs, _, sm_max_mhz = load_peaks()
+        bpp = bytes_per_particle(fluid.ndims, 4 if eltype == "f32" else 8, 4 if coords == "f32" else 8)
+        out.update({"workload": workload, "n_fluid": n_f, "n_wall": wall.nparticles,
+                    "roofline_step_frac_fluid_bytes_only": n_f * bpp["step_fluid"] / (ms * 1e-3) / 1e9 / peak_gbs,
+                    "rebuild_gbs": n_f * 80 / (phases["rebuild"] * 1e-3) / 1e9 if phases.get("rebuild") else None})
+    del u_d, v_d, dv_d, du_d, flush
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_e2e(tp, torch, fluid, wall, u, v, args):
@@ -511,6 +556,8 @@ def main():
     ap.add_argument("--no-slip", action="store_true", help="no-slip wall (wall viscosity = fluid viscosity) on a "
                     "synthetic velocity field instead of the free-slip headline workload")
     ap.add_argument("--evolve", type=int, default=0, help="time steps to run before measuring (evolved state)")
+    ap.add_argument("--per-gpu", type=float, default=12.5e6, help="N > 1: fluid particles per GPU of the "
+                    "weak-scaling headline (BASELINE config 4: 12.5 M per GPU = 100 M on 8)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
     ap.add_argument("--e2e-only", action="store_true", help="host-pointer (e2e) timing only (tuning runs)")
     args = ap.parse_args()

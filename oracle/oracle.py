@@ -204,7 +204,9 @@ def neighbor_pairs(x, y, radius, dtype=None, grid=False):
 def kick(fp: FluidParams, wp, mass_f, coords_w, mass_w, v_ode, u_ode, dtype, use_grid=True,
          nthreads=0):
     """One `kick!` of Semidiscretization(fluid[, wall]).  Arrays are particle-major:
-    u_ode (n_f, ND) coordinate dtype; v_ode (n_f, nv) dtype.  Returns a dict."""
+    u_ode (n_f, ND) coordinate dtype; v_ode (n_f, nv) dtype.  Returns a dict.
+    use_grid: False = all pairs, True = cell lists built per call, 2 = timing mode: the static
+    wall's cell list is built once and reused across calls (as the reference does)."""
     dtype = np.dtype(dtype)
     u_ode = np.ascontiguousarray(u_ode)
     cdt = u_ode.dtype
@@ -234,7 +236,7 @@ def kick(fp: FluidParams, wp, mass_f, coords_w, mass_w, v_ode, u_ode, dtype, use
         C.byref(fp), wpp, n_f, _ptr(mass_f), n_w, _ptr(coords_w), _ptr(mass_w), _ptr(v_ode),
         _ptr(u_ode), _ptr(out["dv"]), _ptr(out["pressure"]), _ptr(out["density"]),
         _ptr(out["wall_pressure"]), _ptr(out["wall_density"]), _ptr(out["wall_volume"]),
-        _ptr(out["wall_velocity"]), int(bool(use_grid)), int(nthreads))
+        _ptr(out["wall_velocity"]), (2 if use_grid == 2 else int(bool(use_grid))), int(nthreads))
     if rc != 0:
         raise RuntimeError(f"orc_kick failed: {rc}")
     return out

@@ -77,6 +77,7 @@ struct Semi {
     TileState tiles;
 
     tpb_stats stats{};
+    unsigned smem_opt_in = 0;  // dynamic shared-memory opt-ins done for this handle (kernel templates are fixed per handle)
     int launches_this_call = 0;
     int deferred_status = TPB_OK;
     bool host_zero_copy = true;  // TPB_MEM_HOST: use mapped page-locked ODE vectors in place (TPB_HOST_ZEROCOPY=0 disables)
@@ -424,13 +425,13 @@ struct Ops {
             int grid = s.tiles.max_wtiles;  // one block per tile slot; surplus blocks exit at once
             if (const char *e = getenv("TPB_ADAMI_GRID"))  // tuning: fewer blocks, each walking several tiles
                 if (atoi(e) > 0) grid = std::min(grid, atoi(e));
-            static bool attr_set = false;
-            if (!attr_set) {
+            // the opt-in is per device (a handle on another device of the same process needs its own)
+            if (!(s.smem_opt_in & 1)) {
                 int rc = set_smem(s, k_adami_tiles<KS, ND, T, CT, KERNEL>, 227 * 1024);
                 if (rc) return rc;
                 rc = set_smem(s, k_adami_tiles<KS, ND, T, CT, KERNEL, true>, 227 * 1024);
                 if (rc) return rc;
-                attr_set = true;
+                s.smem_opt_in |= 1;
             }
             // no-slip wall: the wall velocity rides along in the same sweep when the lists leave room
             // for the five reduction slots; otherwise k_wall_velocity follows (kick_device)
@@ -537,13 +538,12 @@ struct Ops {
             const int list_len = s.tiles.list(KS);
             const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, list_len, KS);
             const size_t smem = tile_smem_bytes<T, CT>(cap, list_len, KS);
-            static bool attr_set = false;
-            if (!attr_set) {
+            if (!(s.smem_opt_in & 2)) {
                 int rc = set_smem(s, k_interact_tiles<KS, ND, T, CT, KERNEL, DENS>, 227 * 1024);
                 if (rc) return rc;
                 rc = set_smem(s, k_interact_tiles<KS, ND, T, CT, KERNEL, DENS, true>, 227 * 1024);
                 if (rc) return rc;
-                attr_set = true;
+                s.smem_opt_in |= 2;
             }
             if (has_wall && s.wp.has_viscosity) {
                 // no-slip wall: pressure and viscous term of the wall in one sweep

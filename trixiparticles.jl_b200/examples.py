@@ -72,7 +72,8 @@ def hydrostatic_water_column_2d(fluid_particle_spacing=0.05, *, eltype=np.float3
 
 
 def dam_break_3d(fluid_particle_spacing=0.08, *, eltype=np.float32, coordinates_eltype=None,
-                 sound_speed=None, fluid_size=(2.0, 1.0, 1.0), tank_size=None, adaptive_sound_speed=False):
+                 sound_speed=None, fluid_size=(2.0, 1.0, 1.0), tank_size=None, adaptive_sound_speed=False,
+                 x_window=None, boundary_x_window=None):
     """examples/fluid/dam_break_3d.jl:13-66 (BASELINE configs 3/4 at smaller spacings).
 
     As SURVEY.md section 8(d) M3 prescribes, the headline runs use a static
@@ -91,7 +92,8 @@ def dam_break_3d(fluid_particle_spacing=0.08, *, eltype=np.float32, coordinates_
         state_equation = StateEquationAdaptiveCole(reference_density=1000.0, exponent=7)
     tank = RectangularTank(dx, fluid_size, tank_size, 1000.0, n_layers=4, spacing_ratio=1,
                            acceleration=(0.0, -gravity, 0.0), state_equation=state_equation,
-                           coordinates_eltype=coordinates_eltype, eltype=eltype)
+                           coordinates_eltype=coordinates_eltype, eltype=eltype, x_window=x_window,
+                           boundary_x_window=boundary_x_window)
     h = 1.5 * dx
     kernel = WendlandC2Kernel(3)
     fluid = WeaklyCompressibleSPHSystem(

@@ -219,6 +219,9 @@ class Semidiscretization:
             for d in range(self.ndims):
                 cfg.min_corner[d] = float(nhs.cell_list.min_corner[d])
                 cfg.max_corner[d] = float(nhs.cell_list.max_corner[d])
+        elif be.ghost_capacity:
+            # without a box the library derives one from u0, which only holds the owned rows
+            raise ValueError("B200Backend.ghost_capacity needs a FullGridCellList bounding box")
         h = C.c_void_p()
         _lib.check(None, L.tpb_create(C.byref(cfg), C.byref(h)))
         self._handle = h
@@ -282,9 +285,12 @@ class Semidiscretization:
             stream = torch.cuda.current_stream(self.parallelization_backend.device).cuda_stream
             # torch's default stream has the handle 0, which tpb_set_stream reads as "use the
             # handle's own stream": pass cudaStreamLegacy (0x1) for it instead
-            _lib.load().tpb_set_stream(self._handle, C.c_void_p(stream if stream else 1))
+            _lib.check(self._handle, _lib.load().tpb_set_stream(self._handle, C.c_void_p(stream if stream else 1)))
 
     def synchronize(self):
+        # the handle may still be bound to another stream (e.g. the side stream of a CUDA-graph
+        # capture): wait on torch's current stream, where the caller's work was queued
+        self._bind_stream()
         _lib.check(self._handle, _lib.load().tpb_synchronize(self._handle))
 
     def sound_speed(self) -> float:

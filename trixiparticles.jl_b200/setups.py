@@ -72,28 +72,45 @@ def _loop_permutation(loop_order, ndims):
     raise ValueError(f"{loop_order} is not a valid loop order")
 
 
-def _permuted_indices(n_per_dim, loop_order):
+def _permuted_indices(n_per_dim, loop_order, x_range=None):
     """1-based Cartesian index of every particle in storage order.
 
     `permutedims(CartesianIndices(n), perm)` iterated column-major: the dimension
-    perm[0] runs fastest (rectangular_shape.jl:205-207)."""
+    perm[0] runs fastest (rectangular_shape.jl:205-207).  `x_range = (i0, i1)`: only the particles
+    whose 0-based index along the first coordinate lies in [i0, i1), in the same relative order
+    (a slab of the lattice)."""
     ndims = len(n_per_dim)
     perm = _loop_permutation(loop_order, ndims)
-    shape = [n_per_dim[p] for p in perm]
+    i0, i1 = (0, n_per_dim[0]) if x_range is None else x_range
+    sizes = list(n_per_dim)
+    sizes[0] = max(i1 - i0, 0)
+    shape = [sizes[p] for p in perm]
     # column-major iteration over `shape`
     grids = np.meshgrid(*[np.arange(1, s + 1) for s in shape], indexing="ij")
     flat = [g.ravel(order="F") for g in grids]
     idx = np.empty((flat[0].size, ndims), dtype=np.int64)
     for k, p in enumerate(perm):
-        idx[:, p] = flat[k]
+        idx[:, p] = flat[k] + (i0 if p == 0 else 0)
     return idx
 
 
+def _x_index_range(particle_spacing, n0, min0, shift0, x_window, coordinates_eltype):
+    """0-based index range [i0, i1) along x of the lattice columns whose final x coordinate
+    (`coordinates_eltype`, after the tank's `min_coordinates` shift) lies in x_window = [lo, hi)."""
+    ct = np.dtype(coordinates_eltype).type
+    xs = np.float64(min0) + np.float64(ct(particle_spacing)) * (np.arange(1, n0 + 1, dtype=np.float64) - 0.5)
+    xs = (xs.astype(ct) + ct(shift0)).astype(ct)
+    keep = np.nonzero((xs >= x_window[0]) & (xs < x_window[1]))[0]
+    if keep.size == 0:
+        return 0, 0
+    return int(keep[0]), int(keep[-1]) + 1
+
+
 def rectangular_shape_coords(particle_spacing, n_particles_per_dimension, min_coordinates,
-                             loop_order=None, coordinates_eltype=np.float64):
+                             loop_order=None, coordinates_eltype=np.float64, x_range=None):
     """rectangular_shape.jl:189-224: min_coordinates + spacing * (index - 0.5)."""
     ct = np.dtype(coordinates_eltype).type
-    idx = _permuted_indices(tuple(n_particles_per_dimension), loop_order)
+    idx = _permuted_indices(tuple(n_particles_per_dimension), loop_order, x_range)
     spacing = ct(particle_spacing)
     mins = np.asarray(min_coordinates, dtype=np.float64)
     # Julia: min_coordinates (Float64 tuple) .+ particle_spacing .* (index .- 0.5)
@@ -104,7 +121,7 @@ def rectangular_shape_coords(particle_spacing, n_particles_per_dimension, min_co
     return coords
 
 
-def _initialize_pressure(n_per_dim, particle_spacing, acceleration, density_fun, loop_order):
+def _initialize_pressure(n_per_dim, particle_spacing, acceleration, density_fun, loop_order, x_range=None):
     """rectangular_shape.jl:226-267: 1-D explicit-Euler hydrostatic column (Float64)."""
     eps = np.finfo(np.float64).eps
     acc = np.asarray(acceleration, dtype=np.float64)
@@ -112,7 +129,8 @@ def _initialize_pressure(n_per_dim, particle_spacing, acceleration, density_fun,
     if active.size > 1:
         raise ValueError("hydrostatic pressure calculation is not supported with diagonal acceleration")
     if active.size == 0:
-        return np.zeros(int(np.prod(n_per_dim)))
+        n0 = n_per_dim[0] if x_range is None else max(x_range[1] - x_range[0], 0)
+        return np.zeros(int(np.prod(n_per_dim[1:])) * n0)
     accel_dim = int(active[0])
     factor = float(particle_spacing) * abs(acc[accel_dim])
     n = n_per_dim[accel_dim]
@@ -122,21 +140,23 @@ def _initialize_pressure(n_per_dim, particle_spacing, acceleration, density_fun,
         p1d[i + 1] = p1d[i] + factor * density_fun(p1d[i])
     if acc[accel_dim] < 0:
         p1d = p1d[::-1].copy()
-    idx = _permuted_indices(tuple(n_per_dim), loop_order)
+    idx = _permuted_indices(tuple(n_per_dim), loop_order, x_range)
     return p1d[idx[:, accel_dim] - 1]
 
 
 def RectangularShape(particle_spacing, n_particles_per_dimension, min_coordinates, *,
                      velocity=None, mass=None, density=None, pressure=0.0, acceleration=None,
                      state_equation=None, coordinates_eltype=np.float64, loop_order=None,
-                     eltype=np.float64) -> InitialCondition:
-    """rectangular_shape.jl:79-151.  `eltype` plays the role of `eltype(particle_spacing)`."""
+                     eltype=np.float64, x_range=None) -> InitialCondition:
+    """rectangular_shape.jl:79-151.  `eltype` plays the role of `eltype(particle_spacing)`.
+    `x_range`: only the lattice columns [i0, i1) along x (see `_permuted_indices`)."""
     t = np.dtype(eltype)
     n_per_dim = tuple(int(n) for n in n_particles_per_dimension)
     ndims = len(n_per_dim)
-    n = int(np.prod(n_per_dim))
     coords = rectangular_shape_coords(particle_spacing, n_per_dim, min_coordinates,
-                                      loop_order=loop_order, coordinates_eltype=coordinates_eltype)
+                                      loop_order=loop_order, coordinates_eltype=coordinates_eltype,
+                                      x_range=x_range)
+    n = coords.shape[0]
     if acceleration is not None:
         if state_equation is None:
             if density is None:
@@ -147,10 +167,12 @@ def RectangularShape(particle_spacing, n_particles_per_dimension, min_coordinate
             if density is not None:
                 raise ValueError("`density` cannot be used together with `acceleration` and `state_equation`")
             density_fun = lambda p: state_equation.inverse(p, dtype=np.float64)
-        press = _initialize_pressure(n_per_dim, particle_spacing, acceleration, density_fun, loop_order)
+        press = _initialize_pressure(n_per_dim, particle_spacing, acceleration, density_fun, loop_order, x_range)
         press = press.astype(t)  # Vector{ELTYPE}
         if state_equation is not None:
-            densities = np.array([state_equation.inverse(p, dtype=t) for p in press], dtype=t)
+            # one inverse per distinct pressure (one per lattice layer), not per particle
+            levels, inv = np.unique(press, return_inverse=True)
+            densities = np.array([state_equation.inverse(p, dtype=t) for p in levels], dtype=t)[inv]
         else:
             densities = np.full(n, density, dtype=t)
     else:
@@ -249,8 +271,11 @@ def RectangularTank(particle_spacing, fluid_size: Sequence[float], tank_size: Se
                     fluid_density, *, velocity=None, pressure=0.0, acceleration=None,
                     state_equation=None, boundary_density=None, n_layers=1, spacing_ratio=1,
                     min_coordinates=None, faces=None, coordinates_eltype=np.float64,
-                    eltype=np.float64) -> RectangularTankResult:
-    """rectangular_tank.jl:99-200."""
+                    eltype=np.float64, x_window=None, boundary_x_window=None) -> RectangularTankResult:
+    """rectangular_tank.jl:99-200.  `x_window = (lo, hi)` (not in the reference): only the particles
+    with lo <= x < hi are generated -- exactly the rows of the full tank with that property, in the
+    same relative order -- so that a rank of a slab-decomposed run never builds the whole lattice
+    (`boundary_x_window`: a different window for the boundary particles; default: `x_window`)."""
     t = np.dtype(eltype)
     ndims = len(fluid_size)
     if faces is None:
@@ -279,8 +304,12 @@ def RectangularTank(particle_spacing, fluid_size: Sequence[float], tank_size: Se
         tank_size_[d] = new
 
     blocks = _tank_boundary_blocks(ndims, b_spacing, tank_size_, n_b, n_layers, faces)
-    parts = [rectangular_shape_coords(b_spacing, npd, mc, loop_order=lo,
-                                      coordinates_eltype=coordinates_eltype)
+    shift0 = float(np.asarray(min_coordinates, dtype=np.float64)[0])
+    xr = lambda sp, n0, mc0, win=x_window: (None if win is None else
+                                            _x_index_range(sp, n0, mc0, shift0, win, coordinates_eltype))
+    b_win = x_window if boundary_x_window is None else boundary_x_window
+    parts = [rectangular_shape_coords(b_spacing, npd, mc, loop_order=lo, coordinates_eltype=coordinates_eltype,
+                                      x_range=xr(b_spacing, npd[0], mc[0], b_win))
              for npd, mc, lo in blocks if int(np.prod(npd)) > 0]
     if parts:
         b_coords = np.concatenate(parts)
@@ -304,12 +333,14 @@ def RectangularTank(particle_spacing, fluid_size: Sequence[float], tank_size: Se
             fluid = RectangularShape(spacing, n_f, np.zeros(ndims), velocity=velocity,
                                      pressure=pressure, acceleration=acceleration,
                                      state_equation=state_equation,
-                                     coordinates_eltype=coordinates_eltype, eltype=t)
+                                     coordinates_eltype=coordinates_eltype, eltype=t,
+                                     x_range=xr(spacing, n_f[0], 0.0))
         else:
             fluid = RectangularShape(spacing, n_f, np.zeros(ndims), density=fluid_density,
                                      velocity=velocity, pressure=pressure,
                                      acceleration=acceleration,
-                                     coordinates_eltype=coordinates_eltype, eltype=t)
+                                     coordinates_eltype=coordinates_eltype, eltype=t,
+                                     x_range=xr(spacing, n_f[0], 0.0))
         fluid.coordinates = (fluid.coordinates + np.asarray(min_coordinates, dtype=fluid.coordinates.dtype)[None, :]).astype(coordinates_eltype)
     else:
         fluid = InitialCondition(np.zeros((0, ndims), dtype=coordinates_eltype),

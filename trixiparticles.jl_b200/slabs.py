@@ -60,7 +60,7 @@ class SlabLayout:
 
 
 def make_layout(x_fluid: np.ndarray, world: int, radius_fluid: float, radius_wall: float,
-                skin: Optional[float] = None) -> SlabLayout:
+                skin: Optional[float] = None, per_column: Optional[int] = None) -> SlabLayout:
     """Faces between lattice columns such that every slab holds the same number of fluid
     particles (+-1 column): the dam-break column fills only part of the tank, equal-width slabs
     would leave most GPUs idle."""
@@ -68,6 +68,14 @@ def make_layout(x_fluid: np.ndarray, world: int, radius_fluid: float, radius_wal
     xs = np.sort(np.asarray(x_fluid, dtype=np.float64))
     planes = [-np.inf]
     for k in range(1, world):
+        if per_column is not None:
+            # x_fluid = the distinct column coordinates of a lattice with `per_column` particles
+            # each: the same faces as from the full coordinate array, without building it
+            n = len(xs) * per_column
+            i = min(max(int(round(n * k / world)), 1), n - 1)
+            c = min(max(-(-i // per_column), 1), len(xs) - 1)
+            planes.append(0.5 * (xs[c - 1] + xs[c]))
+            continue
         i = int(round(len(xs) * k / world))
         i = min(max(i, 1), len(xs) - 1)
         # move to a column boundary: first index whose x differs from its predecessor
@@ -78,7 +86,8 @@ def make_layout(x_fluid: np.ndarray, world: int, radius_fluid: float, radius_wal
     planes = np.asarray(planes)
     halo = float(radius_fluid) + float(radius_wall) + skin
     widths = np.diff(planes[1:-1]) if world > 2 else np.array([np.inf])
-    if world > 1 and (np.any(np.diff(planes) <= 0) or np.any(widths < halo)):
+    # an owner from rank k+2 may sit `skin` inside slab k+1 before the next rebalance
+    if world > 1 and (np.any(np.diff(planes) <= 0) or np.any(widths < halo + skin)):
         raise ValueError("slabs are thinner than the ghost layer: use fewer ranks or a larger problem")
     return SlabLayout(planes=planes, halo=halo, wall_reach=float(radius_fluid) + skin, skin=skin,
                       direct=float(radius_fluid) + skin, near_wall=float(radius_wall))
@@ -152,6 +161,38 @@ def local_wall(wall, layout: SlabLayout, rank: int):
     model.cache = dict(density=model.initial_density.copy(), volume=np.zeros(len(widx), dtype=wall.eltype))
     wall_k.boundary_model = model
     return wall_k, widx
+
+
+def dam_break_3d_slab(dx: float, rank: int, world: int, skin: Optional[float] = None, **kw):
+    """Slab `rank` of `examples.dam_break_3d(dx)` cut into `world` slabs of equal fluid count,
+    generated locally: the rank builds only its own fluid columns and the wall particles within
+    reach of them (RectangularTank(x_window=...)); the rows are exactly those of the global lattice,
+    in the same relative order.  Returns `(fluid_k, wall_k, local)` for
+    `SlabSemidiscretization(fluid_k, wall_k, ..., local=local)` (BASELINE config 4: 10 M - 100 M
+    particles)."""
+    from . import examples
+    from .model import compact_support
+    # geometry only: an empty window generates no particles
+    fluid0, wall0, tank0 = examples.dam_break_3d(dx, x_window=(0.0, 0.0), **kw)
+    t = fluid0.eltype.type
+    ct = np.dtype(fluid0.coordinates_eltype).type
+    n_f = tank0.n_particles_per_dimension
+    spacing = float(t(dx))
+    # x coordinate of every fluid column, exactly as rectangular_shape_coords computes it
+    xs = (np.float64(ct(spacing)) * (np.arange(1, n_f[0] + 1, dtype=np.float64) - 0.5)).astype(ct)
+    R_f = float(compact_support(fluid0.smoothing_kernel, t(fluid0.smoothing_length)))
+    R_w = float(compact_support(wall0.boundary_model.smoothing_kernel, t(wall0.boundary_model.smoothing_length)))
+    layout = make_layout(xs, world, R_f, R_w, skin, per_column=int(np.prod(n_f[1:])))
+    lo, hi = layout.planes[rank], layout.planes[rank + 1]
+    reach = layout.wall_reach
+    fluid_k, wall_k, _ = examples.dam_break_3d(
+        dx, x_window=(lo, hi), boundary_x_window=(lo - reach, np.nextafter(hi + reach, np.inf)), **kw)
+    fluid_k.pressure = np.zeros(fluid_k.nparticles, dtype=fluid_k.eltype)
+    L = tank0.n_layers
+    gmin = np.full(3, -(L - 0.5) * spacing)
+    gmax = np.asarray(tank0.tank_size, dtype=np.float64) + (L - 0.5) * spacing
+    local = dict(layout=layout, bounding_box=(gmin, gmax), n_fluid=int(np.prod(n_f)))
+    return fluid_k, wall_k, local
 
 
 # ------------------------------------------------------------------ rebalance: planes + migration
@@ -383,18 +424,21 @@ class HaloExchange:
             out.append(rows)
         return out
 
-    def check_drift(self, u) -> bool:
-        """True while every owned particle is within `skin` of its slab and, once the candidate
-        lists are fixed, has moved less than `skin` since then (else: rebalance)."""
+    def check_drift(self, u, margin: float = 0.0) -> bool:
+        """True while every owned particle is within `skin - margin` of its slab and, once the
+        candidate lists are fixed, has moved less than `skin - margin` since then (else: rebalance).
+        `margin` = how far a particle may still travel until the next check (the caller's
+        `steps between checks * dt * max|v|`), so that the budget is never exceeded in between."""
         x = u[:, 0]
         ok = True
+        skin = max(self.layout.skin - float(margin), 0.0)
         if self.ready:
             moved2 = ((u - self.u_setup) ** 2).sum(dim=1).max() if len(u) else 0.0
-            ok = ok and float(moved2) < self.layout.skin ** 2
+            ok = ok and float(moved2) < skin ** 2
         if self.has_left:
-            ok = ok and bool((x >= self.lo - self.layout.skin).all())
+            ok = ok and bool((x >= self.lo - skin).all())
         if self.has_right:
-            ok = ok and bool((x < self.hi + self.layout.skin).all())
+            ok = ok and bool((x < self.hi + skin).all())
         return ok
 
     def exchange(self, u, v):
@@ -533,22 +577,53 @@ class SlabSemidiscretization:
 
     def __init__(self, fluid, wall, *, rank: int, world: int, device: int = 0, transport=None,
                  skin: Optional[float] = None, ghost_capacity: Optional[int] = None,
-                 interact_variant: int = 0):
+                 interact_variant: int = 0, local: Optional[dict] = None):
+        """`fluid`, `wall`: the GLOBAL systems (every rank builds the whole lattice and keeps its
+        slab), or -- `local=dict(layout=SlabLayout, bounding_box=(min, max), n_fluid=N)` -- the rank's
+        OWN systems already (fluid particles of slab `rank`, wall particles within `wall_reach` of
+        it; see `dam_break_3d_slab`): nothing of global size is ever built, the ghost-slot counts
+        come from the neighbours (one all_gather)."""
         import torch
         from . import _lib
         from .semidiscretization import (B200Backend, FullGridCellList, GridNeighborhoodSearch,
                                          Semidiscretization)
         self.rank, self.world = rank, world
-        self.global_n_fluid = fluid.nparticles
         t = fluid.eltype.type
         from .model import compact_support
         R_f = float(compact_support(fluid.smoothing_kernel, t(fluid.smoothing_length)))
         R_w = (float(compact_support(wall.boundary_model.smoothing_kernel, t(wall.boundary_model.smoothing_length)))
                if wall is not None else R_f)
         self._radii = (R_f, R_w)
-        self._wall_global = wall
         self._device_index, self._interact_variant, self._transport_arg = device, interact_variant, transport
         self._lib = _lib
+        if local is not None:
+            self.global_n_fluid = int(local["n_fluid"])
+            self._wall_global = None            # rebalance needs the global wall: not available
+            self.layout = local["layout"]
+            self.fluid, self.wall, self.owned_index, self.wall_index = fluid, wall, None, None
+            lo, hi = self.layout.planes[rank], self.layout.planes[rank + 1]
+            # the wall particles that can matter for the candidate selection: near the two faces
+            tree = None
+            if wall is not None and world > 1:
+                xw = wall.coordinates[:, 0].astype(np.float64)
+                reach = self.layout.halo + 2 * self.layout.skin + R_w
+                near = np.zeros(len(xw), dtype=bool)
+                for face in (lo, hi):
+                    if np.isfinite(face):
+                        near |= np.abs(xw - face) <= reach
+                tree = wall_tree(wall.coordinates[near])
+            self._tree = tree
+            gmin, gmax = local["bounding_box"]
+            self._gbox = (np.asarray(gmin, dtype=np.float64) - 2 * max(R_f, R_w),
+                          np.asarray(gmax, dtype=np.float64) + 2 * max(R_f, R_w))
+            n_slots = ghost_capacity
+            if n_slots is None:
+                n_slots = self._slots_from_neighbours(fluid.initial_condition.coordinates, self.layout,
+                                                      torch.device("cuda", device) if transport is None else None)
+            self._build(int(n_slots))
+            return
+        self.global_n_fluid = fluid.nparticles
+        self._wall_global = wall
         self.layout = make_layout(fluid.initial_condition.coordinates[:, 0], world, R_f, R_w, skin)
         self.fluid, self.wall, self.owned_index, self.wall_index = local_systems(fluid, wall, self.layout, rank)
         # ghost slots = the neighbours' candidate counts (particles within halo + skin of the
@@ -569,6 +644,28 @@ class SlabSemidiscretization:
         self._gbox = (allc.min(axis=0) - 2 * max(R_f, R_w), allc.max(axis=0) + 2 * max(R_f, R_w))
         self._tree = tree
         self._build(int(ghost_capacity if ghost_capacity is not None else n_slots))
+
+    def _slots_from_neighbours(self, coords, layout, device=None, group=None) -> int:
+        """Ghost slots of this rank = what its neighbours will send: every rank counts its own
+        candidates per face, one all_gather distributes the counts."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return 0
+        lo, hi = float(layout.planes[self.rank]), float(layout.planes[self.rank + 1])
+        mine = torch.zeros(2, dtype=torch.int64, device=device)
+        if self.rank > 0:
+            mine[0] = int(candidate_mask(coords, lo, -1, layout, self._tree).sum())
+        if self.rank < self.world - 1:
+            mine[1] = int(candidate_mask(coords, hi, +1, layout, self._tree).sum())
+        allc = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allc, mine, group=group)
+        n_slots = 0
+        if self.rank > 0:
+            n_slots += int(allc[self.rank - 1][1])
+        if self.rank < self.world - 1:
+            n_slots += int(allc[self.rank + 1][0])
+        return n_slots
 
     def _build(self, n_slots: int):
         """Everything that depends on the partition: the rank's Semidiscretization (bounding box =
@@ -709,8 +806,14 @@ class SlabSemidiscretization:
                                        C.c_void_p(u_ode.data_ptr()), float(t)))
         return du_ode
 
-    def needs_rebalance(self, u_ode) -> bool:
-        return not self.halo.check_drift(u_ode.view(self.n_owned, self.nd))
+    def needs_rebalance(self, u_ode, v_ode=None, lookahead: float = 0.0) -> bool:
+        """`lookahead` = time until the next check: with `v_ode` given, the motion `lookahead *
+        max|v|` still to come is taken off the skin."""
+        margin = 0.0
+        if v_ode is not None and lookahead > 0.0 and self.n_owned:
+            vel = v_ode.view(self.n_owned, self.nv)[:, : self.nd]
+            margin = float(lookahead) * float((vel.double() ** 2).sum(dim=1).max().sqrt())
+        return not self.halo.check_drift(u_ode.view(self.n_owned, self.nd), margin)
 
     # -- rebalance: new partition by position, particles migrate to their new owners ----------
     def rebalance(self, tspan=None):
@@ -726,6 +829,8 @@ class SlabSemidiscretization:
         from .model import ContinuityDensity
         if self.nv != self.nd + 1:
             raise ValueError("rebalance needs ContinuityDensity (the density travels in v_ode)")
+        if self._wall_global is None and self.wall is not None:
+            raise ValueError("rebalance needs the global wall system (this slab was built from local systems)")
         group = getattr(self.transport, "group", None)
         n0, nd = self.n_owned, self.nd
         u, v = self.u_ext[:n0], self.v_ext[:n0]
@@ -733,7 +838,7 @@ class SlabSemidiscretization:
         old = self.layout
         layout = SlabLayout(planes=planes, halo=old.halo, wall_reach=old.wall_reach, skin=old.skin,
                             direct=old.direct, near_wall=old.near_wall)
-        if self.world > 2 and np.any(np.diff(planes[1:-1]) < layout.halo):
+        if self.world > 2 and np.any(np.diff(planes[1:-1]) < layout.halo + layout.skin):
             raise ValueError("slabs are thinner than the ghost layer: use fewer ranks or a larger problem")
         dest = torch.bucketize(u[:, 0].to(torch.float64).contiguous(),
                                torch.as_tensor(planes[1:-1], dtype=torch.float64, device=u.device), right=True)
@@ -755,20 +860,7 @@ class SlabSemidiscretization:
         fluid_k.pressure = np.zeros(len(un), dtype=template.eltype)
         wall_k, widx = local_wall(self._wall_global, layout, self.rank)
         # ghost slots: the neighbours' candidate counts under the new partition
-        n_slots = 0
-        if self.world > 1:
-            lo, hi = float(planes[self.rank]), float(planes[self.rank + 1])
-            mine = torch.zeros(2, dtype=torch.int64, device=u.device)
-            if self.rank > 0:
-                mine[0] = int(candidate_mask(un, lo, -1, layout, self._tree).sum())
-            if self.rank < self.world - 1:
-                mine[1] = int(candidate_mask(un, hi, +1, layout, self._tree).sum())
-            allc = [torch.empty_like(mine) for _ in range(self.world)]
-            dist.all_gather(allc, mine, group=group)
-            if self.rank > 0:
-                n_slots += int(allc[self.rank - 1][1])
-            if self.rank < self.world - 1:
-                n_slots += int(allc[self.rank + 1][0])
+        n_slots = self._slots_from_neighbours(un, layout, u.device, group)
         # swap the handle
         self.close()
         self.fluid, self.wall, self.wall_index = fluid_k, wall_k, widx
@@ -807,7 +899,8 @@ class SlabSemidiscretization:
         t = float(t0)
         for step in range(int(n_steps)):
             if self.world > 1 and step % check_every == 0:
-                flag = torch.tensor([1 if self.needs_rebalance(u) else 0], dtype=torch.int32, device=u.device)
+                flag = torch.tensor([1 if self.needs_rebalance(u, v, check_every * dt) else 0],
+                                    dtype=torch.int32, device=u.device)
                 dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
                 if int(flag):
                     self.rebalance()

@@ -50,7 +50,9 @@ def calculate_dt(system: WeaklyCompressibleSPHSystem, cfl_number: float) -> floa
         else:
             nu = float(system.viscosity.alpha) * h * c / (2 * system.ndims + 4)
         dt_viscosity = 0.125 * h ** 2 / nu
-    dt_acceleration = 0.25 * math.sqrt(h / float(np.linalg.norm(system.acceleration)))
+    # sqrt(h / 0) = Inf in the reference: without gravity the other two limits decide
+    a = float(np.linalg.norm(system.acceleration))
+    dt_acceleration = math.inf if a == 0.0 else 0.25 * math.sqrt(h / a)
     dt_sound_speed = cfl_number * h / c
     return min(dt_viscosity, dt_acceleration, dt_sound_speed)
 
@@ -74,6 +76,7 @@ def max_x_coord(system, v_ode, u_ode, semi, t) -> float:
     out = C.c_double(0.0)
     eltype = _lib.F32 if semi.coordinates_eltype == np.float32 else _lib.F64
     ptr = u_ode.data_ptr() + a * u_ode.element_size()
+    semi._bind_stream()
     _lib.check(semi._handle, _lib.load().tpb_vec_strided_max(
         semi._handle, (b - a) // nd, eltype, nd, 0, C.c_void_p(ptr), C.byref(out)))
     return out.value
@@ -192,6 +195,7 @@ def solve(ode, alg: CarpenterKennedy2N54, *, dt: Optional[float] = None, save_ev
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
                         run_stages(step)       # recorded, not executed
+                    semi._bind_stream()        # back from the capture's side stream
                     graph.replay()
             else:
                 graph.replay()
