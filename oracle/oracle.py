@@ -52,7 +52,7 @@ class WallParams(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
-    srcs = [os.path.join(_HERE, f) for f in ("sph_oracle.c", "sph_oracle_impl.inc", "sph_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("sph_oracle.c", "sph_oracle_impl.inc", "tlsph_oracle_impl.inc", "sph_oracle.h")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B", "liboracle_sph.so"], check=True,
@@ -75,6 +75,20 @@ def lib():
 
 _SUFFIX = {("float64", "float64"): "f64", ("float32", "float32"): "f32",
            ("float32", "float64"): "f32c64"}
+
+
+BOUNDARY_NONE = 0
+BOUNDARY_MONAGHAN_KAJTAR = 1
+
+
+class TlsphParams(C.Structure):
+    _fields_ = [
+        ("ndims", C.c_int32), ("kernel", C.c_int32), ("has_penalty", C.c_int32),
+        ("boundary_model", C.c_int32), ("smoothing_length", C.c_double),
+        ("young_modulus", C.c_double), ("poisson_ratio", C.c_double), ("penalty_alpha", C.c_double),
+        ("acceleration", C.c_double * 3), ("mk_K", C.c_double), ("mk_beta", C.c_double),
+        ("mk_spacing", C.c_double),
+    ]
 
 
 def suffix(dtype, coords_dtype=None) -> str:
@@ -107,6 +121,16 @@ def _declare(L):
                       p, p, p, p, p, p, i, i]
         f = getattr(L, f"orc_drift_{s}"); f.restype = None
         f.argtypes = [i, i, i64, p, p]
+        TP = C.POINTER(TlsphParams)
+        f = getattr(L, f"orc_tlsph_correction_matrix_{s}"); f.restype = i
+        f.argtypes = [TP, i64, p, p, p, p]
+        f = getattr(L, f"orc_tlsph_update_{s}"); f.restype = i
+        f.argtypes = [TP, i64, p, p, p, p, p, p, p]
+        f = getattr(L, f"orc_tlsph_interact_{s}"); f.restype = i
+        f.argtypes = [TP, i64, i64, p, p, p, p, p, p, p]
+        f = getattr(L, f"orc_kick_fsi_{s}"); f.restype = i
+        f.argtypes = [C.POINTER(FluidParams), C.POINTER(WallParams), TP, i64, p, i64, p, p, i64, i64,
+                      p, p, p, p, p, p, p, p, p, p, i]
     L.orc_max_threads.restype = i
     L.orc_max_threads.argtypes = []
 
@@ -252,3 +276,84 @@ def drift(v_ode, ndims, coords_dtype):
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+# ---------------------------------------------------------------- TLSPH structure + FSI
+
+def tlsph_correction_matrix(sp: TlsphParams, x0, mass, rho, dtype):
+    """`initialize!` of a TotalLagrangianSPHSystem: (n, ND, ND) correction matrices, [p, j, i] =
+    Julia's L[i, j, p] (the memory layout of the reference's ND x ND x n array)."""
+    dtype = np.dtype(dtype)
+    x0 = np.ascontiguousarray(x0)
+    s = suffix(dtype, x0.dtype)
+    n, nd = x0.shape
+    mass, rho = np.ascontiguousarray(mass, dtype=dtype), np.ascontiguousarray(rho, dtype=dtype)
+    L = np.zeros((n, nd, nd), dtype=dtype)
+    rc = getattr(lib(), f"orc_tlsph_correction_matrix_{s}")(C.byref(sp), n, _ptr(x0), _ptr(mass), _ptr(rho), _ptr(L))
+    assert rc == 0
+    return L
+
+
+def tlsph_update(sp: TlsphParams, x0, x_cur, mass, rho, L, dtype):
+    """Deformation gradient and PK1 / rho^2 of every particle: two (n, ND, ND) arrays in the
+    reference's memory layout ([p, j, i] = M[i, j, p])."""
+    dtype = np.dtype(dtype)
+    x0, x_cur = np.ascontiguousarray(x0), np.ascontiguousarray(x_cur, dtype=np.asarray(x0).dtype)
+    s = suffix(dtype, x0.dtype)
+    n, nd = x0.shape
+    mass, rho = np.ascontiguousarray(mass, dtype=dtype), np.ascontiguousarray(rho, dtype=dtype)
+    L = np.ascontiguousarray(L, dtype=dtype)
+    F, P = np.zeros((n, nd, nd), dtype=dtype), np.zeros((n, nd, nd), dtype=dtype)
+    rc = getattr(lib(), f"orc_tlsph_update_{s}")(C.byref(sp), n, _ptr(x0), _ptr(x_cur), _ptr(mass), _ptr(rho),
+                                                  _ptr(L), _ptr(F), _ptr(P))
+    assert rc == 0
+    return F, P
+
+
+def tlsph_interact(sp: TlsphParams, n_int, x0, x_cur, mass, rho, F, pk1_rho2, dtype):
+    """`interact_structure_structure!`: dv (n_int, ND) of the integrated particles."""
+    dtype = np.dtype(dtype)
+    x0, x_cur = np.ascontiguousarray(x0), np.ascontiguousarray(x_cur, dtype=np.asarray(x0).dtype)
+    s = suffix(dtype, x0.dtype)
+    n, nd = x0.shape
+    mass, rho = np.ascontiguousarray(mass, dtype=dtype), np.ascontiguousarray(rho, dtype=dtype)
+    F, P = np.ascontiguousarray(F, dtype=dtype), np.ascontiguousarray(pk1_rho2, dtype=dtype)
+    dv = np.zeros((n_int, nd), dtype=dtype)
+    rc = getattr(lib(), f"orc_tlsph_interact_{s}")(C.byref(sp), n, n_int, _ptr(x0), _ptr(x_cur), _ptr(mass),
+                                                    _ptr(rho), _ptr(F), _ptr(P), _ptr(dv))
+    assert rc == 0
+    return dv
+
+
+def kick_fsi(fp: FluidParams, wp, sp: TlsphParams, mass_f, coords_w, mass_w, n_s_int, x0_s, mass_s, rho_s,
+             hydro_mass_s, L, v_ode, u_ode, dtype, nthreads=0):
+    """One `kick!` of Semidiscretization(fluid, wall, structure) on flat ODE vectors [fluid | structure]
+    (see orc_kick_fsi).  Returns dict(dv=flat dv_ode, F=..., pk1_rho2=...)."""
+    dtype = np.dtype(dtype)
+    u_ode = np.ascontiguousarray(u_ode)
+    cdt = u_ode.dtype
+    s = suffix(dtype, cdt)
+    v_ode = np.ascontiguousarray(v_ode, dtype=dtype)
+    mass_f = np.ascontiguousarray(mass_f, dtype=dtype)
+    n_f, nd = mass_f.size, fp.ndims
+    x0_s = np.ascontiguousarray(x0_s, dtype=cdt)
+    n_s = x0_s.shape[0]
+    assert u_ode.size == nd * (n_f + n_s_int) and v_ode.size == (nd + 1) * n_f + nd * n_s_int
+    if wp is not None and coords_w is not None and len(coords_w) > 0:
+        coords_w = np.ascontiguousarray(coords_w, dtype=cdt)
+        mass_w = np.ascontiguousarray(mass_w, dtype=dtype)
+        n_w, wpp = coords_w.shape[0], C.byref(wp)
+    else:
+        coords_w, mass_w, n_w, wpp = np.zeros((0, nd), dtype=cdt), np.zeros(0, dtype=dtype), 0, None
+    mass_s, rho_s = np.ascontiguousarray(mass_s, dtype=dtype), np.ascontiguousarray(rho_s, dtype=dtype)
+    hydro = np.ascontiguousarray(hydro_mass_s, dtype=dtype)
+    L = np.ascontiguousarray(L, dtype=dtype)
+    dv = np.zeros_like(v_ode)
+    F, P = np.zeros((n_s, nd, nd), dtype=dtype), np.zeros((n_s, nd, nd), dtype=dtype)
+    rc = getattr(lib(), f"orc_kick_fsi_{s}")(C.byref(fp), wpp, C.byref(sp), n_f, _ptr(mass_f), n_w, _ptr(coords_w),
+                                              _ptr(mass_w), n_s, n_s_int, _ptr(x0_s), _ptr(mass_s), _ptr(rho_s),
+                                              _ptr(hydro), _ptr(L), _ptr(v_ode), _ptr(u_ode), _ptr(dv), _ptr(F),
+                                              _ptr(P), int(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"orc_kick_fsi failed: {rc}")
+    return dict(dv=dv, F=F, pk1_rho2=P)

@@ -15,6 +15,7 @@
 #define CT double
 #define SUF f64
 #include "sph_oracle_impl.inc"
+#include "tlsph_oracle_impl.inc"
 #undef T
 #undef CT
 #undef SUF
@@ -23,6 +24,7 @@
 #define CT float
 #define SUF f32
 #include "sph_oracle_impl.inc"
+#include "tlsph_oracle_impl.inc"
 #undef T
 #undef CT
 #undef SUF
@@ -31,6 +33,7 @@
 #define CT double
 #define SUF f32c64
 #include "sph_oracle_impl.inc"
+#include "tlsph_oracle_impl.inc"
 #undef T
 #undef CT
 #undef SUF

@@ -73,6 +73,21 @@ typedef struct {
     double visc_alpha, visc_beta, visc_epsilon;
 } orc_wall_params;
 
+/* TotalLagrangianSPHSystem (structure/total_lagrangian_sph/system.jl:76-106) with scalar material
+ * constants, PenaltyForceGanzenmueller (penalty_force.jl) and, for the coupling with a fluid, a
+ * BoundaryModelMonaghanKajtar (wall_boundary/monaghan_kajtar.jl:18-34). */
+enum { ORC_BOUNDARY_NONE = 0, ORC_BOUNDARY_MONAGHAN_KAJTAR = 1 };
+typedef struct {
+    int32_t ndims, kernel;
+    int32_t has_penalty;      /* PenaltyForceGanzenmueller or nothing */
+    int32_t boundary_model;   /* ORC_BOUNDARY_* */
+    double smoothing_length;
+    double young_modulus, poisson_ratio;
+    double penalty_alpha;
+    double acceleration[3];
+    double mk_K, mk_beta, mk_spacing; /* BoundaryModelMonaghanKajtar(K, beta, boundary_particle_spacing, ...) */
+} orc_tlsph_params;
+
 #define ORC_DECLARE(SUF, T, CT)                                                              \
     double orc_kernel_##SUF(int kernel, int ndims, double r, double h);                      \
     double orc_kernel_unsafe_##SUF(int kernel, int ndims, double r, double h);               \
@@ -111,7 +126,21 @@ typedef struct {
                        const T *v_ode, const CT *u_ode, T *dv_ode, T *pressure_f,            \
                        T *density_f, T *pressure_w, T *density_w, T *volume_w,               \
                        T *wall_velocity_w, int use_grid, int nthreads);                      \
-    void orc_drift_##SUF(int ndims, int nvars_v, int64_t n_f, const T *v_ode, CT *du_ode);
+    void orc_drift_##SUF(int ndims, int nvars_v, int64_t n_f, const T *v_ode, CT *du_ode);    \
+    int orc_tlsph_correction_matrix_##SUF(const orc_tlsph_params *sp, int64_t n, const CT *x0, \
+                                          const T *mass, const T *rho, T *L);                \
+    int orc_tlsph_update_##SUF(const orc_tlsph_params *sp, int64_t n, const CT *x0,          \
+                               const CT *x_cur, const T *mass, const T *rho, const T *L,     \
+                               T *F_out, T *pk1_rho2);                                       \
+    int orc_tlsph_interact_##SUF(const orc_tlsph_params *sp, int64_t n, int64_t n_int,       \
+                                 const CT *x0, const CT *x_cur, const T *mass, const T *rho, \
+                                 const T *F, const T *pk1_rho2, T *dv);                      \
+    int orc_kick_fsi_##SUF(const orc_fluid_params *fp, const orc_wall_params *wp,            \
+                           const orc_tlsph_params *sp, int64_t n_f, const T *mass_f,         \
+                           int64_t n_w, const CT *coords_w, const T *mass_w, int64_t n_s,    \
+                           int64_t n_s_int, const CT *x0_s, const T *mass_s, const T *rho_s, \
+                           const T *hydro_mass_s, const T *L, const T *v_ode,                \
+                           const CT *u_ode, T *dv_ode, T *F_out, T *pk1_out, int nthreads);
 
 ORC_DECLARE(f64, double, double)
 ORC_DECLARE(f32, float, float)
