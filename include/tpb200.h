@@ -71,6 +71,12 @@ extern "C" {
 #define TPB_FIELD_WALL_VELOCITY 3 /* no-slip wall: boundary_model.cache.wall_velocity, ND x n values
                                    * (dummy_particles.jl:299-307) */
 
+/* structure system (n = particle count; ND x ND matrices in the reference's memory layout,
+ * entry (i, j) of particle p at [i + ND * j + ND * ND * p]: `out` holds ND * ND * n values) */
+#define TPB_FIELD_DEFORMATION_GRADIENT 4 /* system.deformation_grad after the last kick */
+#define TPB_FIELD_PK1_RHO2 5             /* system.pk1_rho2 (corrected PK1 / rho^2) */
+#define TPB_FIELD_CORRECTION_MATRIX 6    /* system.correction_matrix (initialize!) */
+
 typedef struct tpb_semi_s *tpb_semi_t; /* opaque; mirrors `Semidiscretization` */
 
 /* `Semidiscretization(systems...; neighborhood_search=GridNeighborhoodSearch{ND}(cell_list=
@@ -138,6 +144,28 @@ typedef struct {
     double alpha, beta, epsilon;
 } tpb_wall_params;
 
+/* `TotalLagrangianSPHSystem(ic; smoothing_kernel, smoothing_length, young_modulus, poisson_ratio,
+ * clamped_particles, acceleration, penalty_force=PenaltyForceGanzenmueller(alpha), boundary_model=
+ * BoundaryModelMonaghanKajtar(K, beta, boundary_particle_spacing, hydrodynamic_mass))`
+ * (structure/total_lagrangian_sph/system.jl:76-184, penalty_force.jl:11-16,
+ * wall_boundary/monaghan_kajtar.jl:18-34) -- BASELINE config 5 (examples/fsi/dam_break_plate_2d.jl).
+ * Scalar material constants; the clamped particles are the LAST n - n_integrated particles (the
+ * reference's constructor moves them there, system.jl:131-147) and are fixed
+ * (clamped_particles_motion = nothing). */
+#define TPB_BOUNDARY_NONE 0            /* boundary_model = nothing: no coupling with the fluid */
+#define TPB_BOUNDARY_MONAGHAN_KAJTAR 1
+typedef struct {
+    int32_t struct_size;
+    int32_t kernel;            /* TPB_KERNEL_* */
+    int32_t has_penalty_force; /* PenaltyForceGanzenmueller | nothing */
+    int32_t boundary_model;    /* TPB_BOUNDARY_* */
+    double smoothing_length;
+    double young_modulus, poisson_ratio;
+    double penalty_alpha;
+    double acceleration[3];
+    double mk_K, mk_beta, mk_spacing; /* BoundaryModelMonaghanKajtar */
+} tpb_structure_params;
+
 /* launch/traffic accounting of the last kick (what bench.py reports as gpu_launches) */
 typedef struct {
     int64_t kernel_launches_total; /* since create */
@@ -165,6 +193,14 @@ int32_t tpb_add_fluid_system(tpb_semi_t semi, const tpb_fluid_params *params, in
 int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *params, int64_t n,
                             const void *coords, const void *hydrodynamic_mass,
                             const void *initial_density, int32_t *system_index);
+/* `initial_coords`: cT[ND x n] (integrated particles first); `mass`, `material_density`: T[n];
+ * `hydrodynamic_mass`: T[n] (boundary_model.hydrodynamic_mass; may be NULL with TPB_BOUNDARY_NONE).
+ * The system contributes ND x n_integrated entries to u_ode and to v_ode
+ * (system.jl:277-289).  At most one structure system; not combined with slab ghosts. */
+int32_t tpb_add_structure_system(tpb_semi_t semi, const tpb_structure_params *params, int64_t n,
+                                 int64_t n_integrated, const void *initial_coords, const void *mass,
+                                 const void *material_density, const void *hydrodynamic_mass,
+                                 int32_t *system_index);
 /* `interaction_matrix[system, neighbor]` (semidiscretization.jl:157-187); default all true */
 int32_t tpb_set_interaction(tpb_semi_t semi, int32_t system, int32_t neighbor, int32_t enabled);
 

@@ -91,3 +91,39 @@ def kick(fluid, wall, u, v, use_grid=True, nthreads=0, fluid_wall_interaction=Tr
         wp, cw, mw = None, None, None
     return O.kick(fp, wp, fluid.mass, cw, mw, v, u, fluid.eltype, use_grid=use_grid,
                   nthreads=nthreads)
+
+
+def structure_params(st) -> O.TlsphParams:
+    t = np.dtype(st.eltype).type
+    p = O.TlsphParams()
+    p.ndims = st.ndims
+    p.kernel = st.smoothing_kernel.kernel_id
+    p.smoothing_length = float(t(st.smoothing_length))
+    p.young_modulus, p.poisson_ratio = float(t(st.young_modulus)), float(t(st.poisson_ratio))
+    if st.penalty_force is not None:
+        p.has_penalty, p.penalty_alpha = 1, float(t(st.penalty_force.alpha))
+    for d in range(st.ndims):
+        p.acceleration[d] = float(st.acceleration[d])
+    m = st.boundary_model
+    if m is not None:
+        p.boundary_model = O.BOUNDARY_MONAGHAN_KAJTAR
+        p.mk_K, p.mk_beta, p.mk_spacing = float(t(m.K)), float(t(m.beta)), float(t(m.boundary_particle_spacing))
+    return p
+
+
+def kick_fsi(fluid, wall, structure, u_ode, v_ode, nthreads=0):
+    """Oracle `kick!` of Semidiscretization(fluid, wall, structure) on flat ODE vectors laid out
+    [fluid | structure].  Returns dict(dv, F, pk1_rho2, L)."""
+    fp = fluid_params(fluid)
+    wp = wall_params(wall) if wall is not None else None
+    sp = structure_params(structure)
+    hyd = (structure.boundary_model.hydrodynamic_mass if structure.boundary_model is not None
+           else np.zeros(structure.nparticles, dtype=structure.eltype))
+    L = O.tlsph_correction_matrix(sp, structure.initial_coordinates, structure.mass, structure.material_density,
+                                  structure.eltype)
+    out = O.kick_fsi(fp, wp, sp, fluid.mass, wall.coordinates if wall is not None else None,
+                     wall.boundary_model.hydrodynamic_mass if wall is not None else None,
+                     structure.n_integrated_particles, structure.initial_coordinates, structure.mass,
+                     structure.material_density, hyd, L, v_ode, u_ode, fluid.eltype, nthreads=nthreads)
+    out["L"] = L
+    return out

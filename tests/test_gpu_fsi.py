@@ -1,0 +1,121 @@
+"""BASELINE config 5 on the GPU: WCSPH fluid + dummy-particle tank + TotalLagrangianSPHSystem plate
+(examples/fsi/dam_break_plate_2d.jl with the dimensions of the reference's GPU tests,
+test/examples/gpu.jl:664-726) through the C ABI against the CPU oracle.  `-m gpu` only."""
+import numpy as np
+import pytest
+
+import trixiparticles.jl_b200 as tp
+from trixiparticles.jl_b200 import examples
+from oracle import adapter
+
+pytestmark = pytest.mark.gpu
+
+
+def fsi_state(fluid, structure, seed=7, deform=0.05):
+    """ODE vectors [fluid | structure]: the fluid as `perturbed_state`, the plate bent and moving."""
+    u_f, v_f = examples.perturbed_state(fluid, seed=seed, position_jitter=0.05)
+    rng = np.random.default_rng(seed + 1)
+    n_int = structure.n_integrated_particles
+    x0 = structure.initial_coordinates[:n_int].astype(np.float64)
+    ds = structure.initial_condition.particle_spacing
+    height = x0[:, 1] - x0[:, 1].min()
+    u_s = x0.copy()
+    u_s[:, 0] += 0.5 * height ** 2 / max(height.max(), 1e-12)           # bending
+    u_s += rng.uniform(-deform * ds, deform * ds, u_s.shape)              # + noise (non-affine)
+    v_s = rng.uniform(-0.5, 0.5, u_s.shape)
+    u = np.concatenate([u_f.reshape(-1), u_s.astype(structure.coordinates_eltype).reshape(-1)])
+    v = np.concatenate([v_f.reshape(-1), v_s.astype(structure.eltype).reshape(-1)])
+    return np.ascontiguousarray(u), np.ascontiguousarray(v)
+
+
+@pytest.mark.parametrize("eltype,coords,tol", [(np.float64, np.float64, 1e-11), (np.float32, np.float32, 2e-5),
+                                                (np.float32, np.float64, 2e-5)])
+@pytest.mark.parametrize("memory", ["host", "device"])
+def test_fsi_kick_matches_oracle(eltype, coords, tol, memory):
+    # the plate next to the water column, so that the Monaghan-Kajtar coupling is active
+    fluid, wall, structure, _ = examples.dam_break_plate_2d(
+        0.01, eltype=eltype, coordinates_eltype=coords, initial_fluid_size=(0.15, 0.29), plate_position=(0.165, 0.0))
+    u, v = fsi_state(fluid, structure)
+    ref = adapter.kick_fsi(fluid, wall, structure, u, v)
+    semi = tp.Semidiscretization(fluid, wall, structure,
+                                 parallelization_backend=tp.B200Backend(device=0, ode_memory=memory))
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    assert semi.ranges_u[-1][1] == u.size and semi.ranges_v[-1][1] == v.size
+    if memory == "device":
+        import torch
+        dev = ode.u0.device
+        u_d, v_d = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev)
+        dv_d, du_d = torch.full_like(v_d, float("nan")), torch.full_like(u_d, float("nan"))
+        ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
+        ode.f2(du_d, v_d, u_d, ode.p, 0.0)
+        semi.synchronize()
+        dv, du = dv_d.cpu().numpy(), du_d.cpu().numpy()
+    else:
+        dv, du = np.full_like(v, np.nan), np.full_like(u, np.nan)
+        ode.f1(dv, v, u, ode.p, 0.0)
+        ode.f2(du, v, u, ode.p, 0.0)
+    nd, n_f, n_int = 2, fluid.nparticles, structure.n_integrated_particles
+    # correction matrix, deformation gradient, PK1 / rho^2
+    for name, key in (("correction_matrix", "L"), ("deformation_grad", "F"), ("pk1_rho2", "pk1_rho2")):
+        got = semi.system_field(structure, name)
+        scale = np.abs(ref[key]).max()
+        assert np.abs(got - ref[key]).max() <= tol * scale, (name, np.abs(got - ref[key]).max() / scale)
+    dv_f, ref_f = dv[: 3 * n_f].reshape(n_f, 3), ref["dv"][: 3 * n_f].reshape(n_f, 3)
+    dv_s, ref_s = dv[3 * n_f:].reshape(n_int, 2), ref["dv"][3 * n_f:].reshape(n_int, 2)
+    assert np.isfinite(dv).all()
+    # the coupling is active on both sides
+    no_plate = adapter.kick(fluid, wall, u[: 2 * n_f].reshape(n_f, 2), v[: 3 * n_f].reshape(n_f, 3))["dv"]
+    assert np.abs(ref_f - no_plate).max() > 1.0
+    for name, a, b in (("fluid acceleration", dv_f[:, :2], ref_f[:, :2]), ("fluid drho", dv_f[:, 2], ref_f[:, 2]),
+                       ("structure acceleration", dv_s, ref_s)):
+        err = np.abs(a - b).max() / np.abs(b).max()
+        assert err <= tol, (name, err)
+    # drift!: du = v for both systems
+    assert np.array_equal(du[: 2 * n_f].reshape(n_f, 2), v[: 3 * n_f].reshape(n_f, 3)[:, :2].astype(u.dtype))
+    assert np.array_equal(du[2 * n_f:], v[3 * n_f:].astype(u.dtype))
+    semi.close()
+
+
+def test_fsi_structure_first_ordering():
+    """Semidiscretization(structure, fluid, wall) -- the order of examples/fsi/hydrostatic_water_column_2d.jl:
+    the ODE vectors are laid out [structure | fluid]; same physics."""
+    fluid, wall, structure, _ = examples.dam_break_plate_2d(
+        0.01, initial_fluid_size=(0.15, 0.29), plate_position=(0.165, 0.0))
+    u, v = fsi_state(fluid, structure)
+    ref = adapter.kick_fsi(fluid, wall, structure, u, v)["dv"]
+    n_f, n_int = fluid.nparticles, structure.n_integrated_particles
+    u2 = np.concatenate([u[2 * n_f:], u[: 2 * n_f]])
+    v2 = np.concatenate([v[3 * n_f:], v[: 3 * n_f]])
+    semi = tp.Semidiscretization(structure, fluid, wall, parallelization_backend=tp.B200Backend(device=0))
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    assert semi.ranges_u == ((0, 2 * n_int), (2 * n_int, 2 * n_int + 2 * n_f), (2 * n_int + 2 * n_f,) * 2)
+    dv = np.full_like(v2, np.nan)
+    ode.f1(dv, v2, u2, ode.p, 0.0)
+    got = np.concatenate([dv[2 * n_int:], dv[: 2 * n_int]])
+    assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max()
+    semi.close()
+
+
+def test_dam_break_plate_2d_time_loop():
+    """test/examples/gpu.jl:696-726: Float32, initial_fluid_size = (0.15, 0.29), CarpenterKennedy2N54 with
+    StepsizeCallback(cfl = 1.2) to t = 0.05: the run completes, nothing leaves the tank, the clamped
+    base holds the plate and the plate has not moved by more than a fraction of its thickness before
+    the water arrives."""
+    from trixiparticles.jl_b200.time_integration import CarpenterKennedy2N54, StepsizeCallback, solve
+    fluid, wall, structure, _ = examples.dam_break_plate_2d(
+        0.01, eltype=np.float32, coordinates_eltype=np.float32, initial_fluid_size=(0.15, 0.29))
+    semi = tp.Semidiscretization(fluid, wall, structure,
+                                 parallelization_backend=tp.B200Backend(device=0, ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 0.05))
+    cb = StepsizeCallback(cfl=1.2)
+    sol = solve(ode, CarpenterKennedy2N54(williamson_condition=False), dt=cb.dt(semi), callback=cb)
+    assert sol.retcode == "Success"
+    u, v = sol.u.cpu().numpy(), sol.v.cpu().numpy()
+    assert np.isfinite(u).all() and np.isfinite(v).all()
+    n_f, n_int = fluid.nparticles, structure.n_integrated_particles
+    u_s = u[2 * n_f:].reshape(n_int, 2)
+    disp = np.abs(u_s - structure.initial_coordinates[:n_int]).max()
+    assert disp < 0.012, disp          # plate thickness
+    u_f = u[: 2 * n_f].reshape(n_f, 2)
+    assert u_f[:, 0].max() > 0.16       # the column has started to collapse
+    semi.close()

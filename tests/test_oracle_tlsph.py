@@ -1,0 +1,110 @@
+"""The TLSPH / FSI part of the CPU oracle against the known answers the reference's own tests hold
+(SURVEY.md section 8(c) / 8(f) rank 3).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ROT = np.array([[np.cos(0.3), -np.sin(0.3)], [np.sin(0.3), np.cos(0.3)]])
+STRETCH = np.array([[2.0, 0.0], [0.0, 3.0]])
+
+
+def grid_9x9(x_fastest=True):
+    r = np.arange(1, 10) * 0.1
+    if x_fastest:    # Iterators.product(range, range): the first index runs fastest
+        return np.array([[x, y] for y in r for x in r])
+    return np.array([[x, y] for x in r for y in r])    # particle = (x - 1) * 9 + y
+
+
+def params(h, E=1.0, nu=1.0, kernel=O.KERNEL_SCHOENBERG_CUBIC):
+    sp = O.TlsphParams()
+    sp.ndims, sp.kernel, sp.smoothing_length = 2, kernel, h
+    sp.young_modulus, sp.poisson_ratio = E, nu
+    return sp
+
+
+@pytest.mark.parametrize("name,deform,expected", [
+    ("Stretch x", lambda x: np.array([[2.0, 0.0], [0.0, 1.0]]) @ x, np.array([[2.0, 0.0], [0.0, 1.0]])),
+    ("Stretch Both", lambda x: STRETCH @ x, STRETCH),
+    ("Rotation", lambda x: ROT @ x, ROT),
+    ("Nonlinear Stretching", lambda x: np.array([x[0] ** 2, x[1]]), np.eye(2)),
+])
+def test_deformation_gradient_of_deformation_functions(name, deform, expected):
+    """test/systems/tlsph_system.jl:194-247: 9 x 9 grid, spacing 0.1, cubic spline h = 0.12; the
+    deformation gradient of the middle particle (41) equals the deformation matrix."""
+    x0 = grid_9x9()
+    mass, rho = np.full(81, 10.0), np.full(81, 1000.0)
+    sp = params(0.12)
+    L = O.tlsph_correction_matrix(sp, x0, mass, rho, np.float64)
+    cur = np.array([deform(c) for c in x0])
+    F, _ = O.tlsph_update(sp, x0, cur, mass, rho, L, np.float64)
+    assert np.allclose(F[40].T, expected, rtol=1.5e-8, atol=1e-14)
+
+
+@pytest.mark.parametrize("J,pk2,pk1", [
+    (ROT, np.zeros((2, 2)), np.zeros((2, 2))),
+    (STRETCH, np.array([[8.5, 0.0], [0.0, 13.5]]), np.array([[17.0, 0.0], [0.0, 40.5]])),
+    (ROT @ STRETCH, np.array([[8.5, 0.0], [0.0, 13.5]]), ROT @ STRETCH @ np.array([[8.5, 0.0], [0.0, 13.5]])),
+])
+def test_stress_tensors(J, pk2, pk1):
+    """test/systems/tlsph_system.jl:250-303: lambda = mu = 1 (E = 2.5, nu = 0.25); PK1 = F S.  The
+    deformation is applied to the grid, where the corrected gradient reproduces F = J exactly; the
+    oracle returns PK1 L / rho^2, so PK1 = rho^2 (PK1 L / rho^2) L^-1."""
+    x0 = grid_9x9()
+    mass, rho = np.full(81, 10.0), np.full(81, 1000.0)
+    sp = params(0.12, E=2.5, nu=0.25)
+    L = O.tlsph_correction_matrix(sp, x0, mass, rho, np.float64)
+    cur = x0 @ J.T
+    F, P = O.tlsph_update(sp, x0, cur, mass, rho, L, np.float64)
+    assert np.allclose(F[40].T, J, atol=1e-13)
+    got = 1000.0 ** 2 * P[40].T @ np.linalg.inv(L[40].T)
+    assert np.allclose(got, pk1, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("deform,expected", [
+    (lambda x: ROT @ x, [0.0, 0.0]),
+    (lambda x: STRETCH @ x, [0.0, 0.0]),
+    (lambda x: ROT @ STRETCH @ x, [0.0, 0.0]),
+    (lambda x: np.array([x[0] ** 2, x[1]]), [10 / 1000 ** 2 * 1.5400218087591082 * 324.67072684047224 * 1.224, 0.0]),
+])
+def test_structure_interact_with_deformation_function(deform, expected):
+    """test/schemes/structure/total_lagrangian_sph/rhs.jl:118-203: `kick!` of a 9 x 9 TLSPH grid
+    (cubic spline h = 0.07, E = 2.5, nu = 0.25, no penalty force, no gravity): acceleration of the
+    middle particle; tolerance sqrt(eps) as in the reference."""
+    x0 = grid_9x9(x_fastest=False)
+    mass, rho = np.full(81, 10.0), np.full(81, 1000.0)
+    sp = params(0.07, E=2.5, nu=0.25)
+    L = O.tlsph_correction_matrix(sp, x0, mass, rho, np.float64)
+    cur = np.array([deform(c) for c in x0])
+    F, P = O.tlsph_update(sp, x0, cur, mass, rho, L, np.float64)
+    dv = O.tlsph_interact(sp, 81, x0, cur, mass, rho, F, P, np.float64)
+    tol = np.sqrt(np.finfo(np.float64).eps)
+    assert np.allclose(dv[40], expected, rtol=tol, atol=tol)
+
+
+def test_monaghan_kajtar_rhs():
+    """test/schemes/boundary/monaghan_kajtar/monaghan_kajtar.jl:11-67: 3 x 3 fluid particles left of a
+    1 x 3 wall of repulsive particles (here: three clamped structure particles carrying the same
+    BoundaryModelMonaghanKajtar(K = 1, beta = 0.5, spacing 0.2)); the reference's numbers for the
+    middle column, zero for the left one, < -300 for the right one."""
+    dx = 0.1
+    xs = np.array([-0.1, 0.0, 0.1]) - 1.5 * dx
+    ys = np.array([-0.1, 0.0, 0.1])
+    fluid = np.array([[x, y] for y in ys for x in xs])
+    wall = np.array([[0.0, y] for y in (-0.2, 0.0, 0.2)])
+    fp = O.FluidParams()
+    fp.ndims, fp.kernel, fp.density_calculator = 2, O.KERNEL_SCHOENBERG_CUBIC, O.DENSITY_CONTINUITY
+    fp.smoothing_length, fp.sound_speed, fp.exponent, fp.reference_density = 1.2 * dx, 0.0, 1.0, 1000.0
+    sp = params(1.2 * dx)
+    sp.boundary_model, sp.mk_K, sp.mk_beta, sp.mk_spacing = O.BOUNDARY_MONAGHAN_KAJTAR, 1.0, 0.5, 2 * dx
+    mass_f = np.full(9, 1000.0 * dx ** 2)
+    mass_s = np.full(3, 1000.0 * (2 * dx) ** 2)
+    v = np.concatenate([np.zeros((9, 2)), np.full((9, 1), 1000.0)], axis=1)
+    L = np.tile(np.eye(2), (3, 1, 1))
+    out = O.kick_fsi(fp, None, sp, mass_f, None, None, 0, wall, mass_s, np.full(3, 1000.0), mass_s, L,
+                     v.reshape(-1), fluid.reshape(-1), np.float64)
+    dv = out["dv"].reshape(9, 3)
+    assert np.abs(dv[:, 1]).max() <= 1e-14
+    assert np.all(dv[[0, 3, 6], :2] == 0)
+    assert np.all(dv[[2, 5, 8], 0] < -300)
+    assert np.allclose(dv[[1, 4, 7], 0], [-26.052449, -95.162888, -26.052449], rtol=1.5e-8)

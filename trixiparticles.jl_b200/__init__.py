@@ -12,7 +12,8 @@ from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan, Ber
                     SchoenbergQuarticSplineKernel, SchoenbergQuinticSplineKernel,
                     SourceTermDamping, StateEquationAdaptiveCole, StateEquationCole, SummationDensity,
                     ViscosityAdami, ViscosityMorris,
-                    WallBoundarySystem,
+                    WallBoundarySystem, TotalLagrangianSPHSystem, BoundaryModelMonaghanKajtar,
+                    PenaltyForceGanzenmueller,
                     WeaklyCompressibleSPHSystem, WendlandC2Kernel, WendlandC4Kernel, WendlandC6Kernel,
                     compact_support)
 from .semidiscretization import (B200Backend, DynamicalODEProblem, FullGridCellList,
@@ -28,7 +29,8 @@ __all__ = [
     "SchoenbergQuarticSplineKernel", "SchoenbergQuinticSplineKernel",
     "SourceTermDamping", "StateEquationAdaptiveCole", "StateEquationCole", "SummationDensity",
     "ViscosityAdami", "ViscosityMorris",
-    "WallBoundarySystem",
+    "WallBoundarySystem", "TotalLagrangianSPHSystem", "BoundaryModelMonaghanKajtar",
+    "PenaltyForceGanzenmueller",
     "WeaklyCompressibleSPHSystem", "WendlandC2Kernel", "WendlandC4Kernel", "WendlandC6Kernel",
     "compact_support", "B200Backend",
     "DynamicalODEProblem", "FullGridCellList", "GridNeighborhoodSearch", "Semidiscretization",

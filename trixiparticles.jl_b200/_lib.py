@@ -15,10 +15,12 @@ ERR_NAMES = {1: "INVALID_ARGUMENT", 2: "UNSUPPORTED", 3: "CUDA", 4: "OUT_OF_BOUN
 F32, F64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 FIELD_PRESSURE, FIELD_DENSITY, FIELD_VOLUME, FIELD_WALL_VELOCITY = 0, 1, 2, 3
+FIELD_DEFORMATION_GRADIENT, FIELD_PK1_RHO2, FIELD_CORRECTION_MATRIX = 4, 5, 6
+BOUNDARY_NONE, BOUNDARY_MONAGHAN_KAJTAR = 0, 1
 
 EXPORTS = [
     "tpb_version", "tpb_last_error", "tpb_create", "tpb_destroy", "tpb_add_fluid_system",
-    "tpb_add_wall_system", "tpb_set_interaction", "tpb_semidiscretize", "tpb_ode_sizes",
+    "tpb_add_wall_system", "tpb_add_structure_system", "tpb_set_interaction", "tpb_semidiscretize", "tpb_ode_sizes",
     "tpb_system_range", "tpb_kick", "tpb_drift", "tpb_get_system_field", "tpb_neighbor_pairs",
     "tpb_synchronize", "tpb_set_stream", "tpb_get_stats", "tpb_get_sound_speed", "tpb_host_register",
     "tpb_host_unregister", "tpb_set_profiling", "tpb_get_phase_times",
@@ -65,6 +67,15 @@ class WallParams(C.Structure):
     ]
 
 
+class StructureParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("kernel", C.c_int32), ("has_penalty_force", C.c_int32),
+        ("boundary_model", C.c_int32), ("smoothing_length", C.c_double), ("young_modulus", C.c_double),
+        ("poisson_ratio", C.c_double), ("penalty_alpha", C.c_double), ("acceleration", C.c_double * 3),
+        ("mk_K", C.c_double), ("mk_beta", C.c_double), ("mk_spacing", C.c_double),
+    ]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("kernel_launches_total", C.c_int64), ("kicks", C.c_int64), ("drifts", C.c_int64),
@@ -102,6 +113,8 @@ def load():
     L.tpb_add_fluid_system.argtypes = [p, C.POINTER(FluidParams), i64, p, C.POINTER(i32)]
     L.tpb_add_wall_system.restype = i32
     L.tpb_add_wall_system.argtypes = [p, C.POINTER(WallParams), i64, p, p, p, C.POINTER(i32)]
+    L.tpb_add_structure_system.restype = i32
+    L.tpb_add_structure_system.argtypes = [p, C.POINTER(StructureParams), i64, i64, p, p, p, p, C.POINTER(i32)]
     L.tpb_set_interaction.restype = i32; L.tpb_set_interaction.argtypes = [p, i32, i32, i32]
     L.tpb_semidiscretize.restype = i32; L.tpb_semidiscretize.argtypes = [p, p]
     L.tpb_ode_sizes.restype = i32; L.tpb_ode_sizes.argtypes = [p, C.POINTER(i64), C.POINTER(i64)]

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,7 @@
 #include "tpb_nhs.cuh"
 #include "tpb_sweeps.cuh"
 #include "tpb_tiles.cuh"
+#include "tpb_structure.cuh"
 #include "tpb_vec.cuh"
 #include "tpb_halo.cuh"
 
@@ -45,6 +47,17 @@ struct Semi {
     std::vector<unsigned char> h_mass_f, h_coords_w, h_mass_w, h_dens_w;
     int interaction[2][2] = {{1, 1}, {1, 1}};
     bool ready = false;
+
+    // structure (TotalLagrangianSPHSystem), at most one; clamped particles are the last n_s - n_s_int
+    int struct_index = -1;
+    tpb_structure_params sp{};
+    int64_t n_s = 0, n_s_int = 0;
+    int struct_fluid[2] = {1, 1};  // interaction_matrix[structure, fluid], [fluid, structure]
+    int struct_self = 1;           // interaction_matrix[structure, structure]
+    std::vector<unsigned char> h_x0_s, h_mass_s, h_rho_s, h_hydro_s;
+    void *d_x0_s = nullptr, *d_xcur_s = nullptr, *d_mass_s = nullptr, *d_rho_s = nullptr, *d_hydro_s = nullptr;
+    void *d_L_s = nullptr, *d_F_s = nullptr, *d_pk1_s = nullptr, *d_As = nullptr, *d_Bs = nullptr;
+    int *d_nbr_start = nullptr, *d_nbr = nullptr, *d_scell_start = nullptr;
 
     // geometry of the shared cell grid (double; typed copies are built per call)
     double cell_size = 0, origin[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
@@ -95,6 +108,30 @@ inline void prof_mark(Semi &s, int ph)
 }
 
 inline size_t tsize(int eltype) { return eltype == TPB_F64 ? 8 : 4; }
+
+// ODE layout (`ranges_u` / `ranges_v`, semidiscretization.jl:128-135): systems in call order; the
+// fluid holds ND (u) and NV (v) entries per active particle, the wall none, the structure ND each
+// per integrated particle.  Offsets / totals in elements.
+struct OdeLayout {
+    int64_t off_u_f = 0, off_v_f = 0, off_u_s = 0, off_v_s = 0, tot_u = 0, tot_v = 0;
+};
+inline OdeLayout ode_layout(const Semi &s)
+{
+    const int nd = s.cfg.ndims;
+    const int nvars = s.fp.density_calculator == TPB_DENSITY_SUMMATION ? nd : nd + 1;
+    OdeLayout L;
+    const int64_t fu = s.n_act * nd, fv = s.n_act * nvars, su = s.n_s_int * nd;
+    if (s.struct_index >= 0 && s.struct_index < s.fluid_index) {
+        L.off_u_f = su;
+        L.off_v_f = su;
+    } else {
+        L.off_u_s = fu;
+        L.off_v_s = fv;
+    }
+    L.tot_u = fu + (s.struct_index >= 0 ? su : 0);
+    L.tot_v = fv + (s.struct_index >= 0 ? su : 0);
+    return L;
+}
 
 // Device-side alias of a page-locked, mapped host pointer (cudaHostAlloc / cudaHostRegister,
 // e.g. through tpb_host_register); nullptr for pageable memory.
@@ -339,6 +376,190 @@ struct Ops {
         cudaFree(d_coords);
         cudaFree(d_mass);
         cudaFree(d_dens);
+        return TPB_OK;
+    }
+
+    // ---- TotalLagrangianSPHSystem -------------------------------------------------------------
+    static StructConst<T> make_struct_const(const Semi &s)
+    {
+        StructConst<T> k;
+        k.kern = make_kernel_const<T>(s.sp.kernel, ND, s.sp.smoothing_length);
+        const T h = k.kern.h;
+        k.almostzero = std::sqrt(eps_of<T>(h * h));
+        const T E = (T)s.sp.young_modulus, nu = (T)s.sp.poisson_ratio;
+        // system.jl:158-161
+        k.lambda = E * nu / (((T)1 + nu) * ((T)1 - (T)2 * nu));
+        k.mu = (E / (T)2) / ((T)1 + nu);
+        k.young = E;
+        k.half_alpha = (T)s.sp.penalty_alpha / (T)2;
+        k.has_penalty = s.sp.has_penalty_force;
+        for (int d = 0; d < 3; ++d) k.acc[d] = (T)s.sp.acceleration[d];
+        return k;
+    }
+    static MKConst<T> make_mk_const(const Semi &s, const PairConst<T> &pc)
+    {
+        MKConst<T> k;
+        const T K = (T)s.sp.mk_K, beta = (T)s.sp.mk_beta, spacing = (T)s.sp.mk_spacing;
+        k.K_bpow = K / (ND == 2 ? beta : beta * beta);
+        k.spacing = spacing;
+        k.min_dfs = spacing / (T)100;
+        k.h_fluid = pc.kern.h;
+        k.vol = ND == 2 ? spacing * spacing : spacing * spacing * spacing;
+        k.radius2 = pc.radius2;
+        k.almostzero_fs = pc.almostzero;
+        k.almostzero_sf = std::sqrt(eps_of<T>(pc.kern.h * pc.kern.h));
+        return k;
+    }
+    static int struct_kernel_id(const Semi &s)
+    {
+        const int kernel = s.sp.kernel;
+        return kernel <= 1 ? kernel : kernel <= TPB_KERNEL_WENDLAND_C6 ? 2 : 3;
+    }
+
+    // once: neighbour list over the initial configuration (exact predicate, ascending neighbour
+    // index) + gradient correction matrices (initialize!, system.jl:391-401)
+    static int init_structure(Semi &s)
+    {
+        const int n = (int)s.n_s;
+        const CT *x0 = (const CT *)s.h_x0_s.data();
+        const T R = make_kernel_const<T>(s.sp.kernel, ND, s.sp.smoothing_length).support;
+        const T R2 = R * R;
+        std::vector<int> start((size_t)n + 1, 0), nbr;
+        {
+            // cells of size R over the structure's own bounding box
+            double lo[3] = {0, 0, 0}, cell = (double)R * (1.0 + 1e-6);
+            for (int d = 0; d < ND; ++d) {
+                lo[d] = (double)x0[d];
+                for (int i = 1; i < n; ++i) lo[d] = std::min(lo[d], (double)x0[(size_t)i * ND + d]);
+            }
+            auto cell_of = [&](int i, int d) { return (int64_t)std::floor(((double)x0[(size_t)i * ND + d] - lo[d]) / cell); };
+            std::vector<std::pair<std::array<int64_t, 3>, int>> keyed((size_t)n);
+            for (int i = 0; i < n; ++i) {
+                std::array<int64_t, 3> c = {0, 0, 0};
+                for (int d = 0; d < ND; ++d) c[d] = cell_of(i, d);
+                keyed[(size_t)i] = {c, i};
+            }
+            std::sort(keyed.begin(), keyed.end());
+            auto lower = [&](const std::array<int64_t, 3> &c) {
+                return std::lower_bound(keyed.begin(), keyed.end(), std::make_pair(c, -1)) - keyed.begin();
+            };
+            std::vector<int> cand;
+            for (int a = 0; a < n; ++a) {
+                cand.clear();
+                std::array<int64_t, 3> ca = {0, 0, 0};
+                for (int d = 0; d < ND; ++d) ca[d] = cell_of(a, d);
+                for (int64_t dz = (ND == 3 ? -1 : 0); dz <= (ND == 3 ? 1 : 0); ++dz)
+                    for (int64_t dy = -1; dy <= 1; ++dy)
+                        for (int64_t dx = -1; dx <= 1; ++dx) {
+                            const std::array<int64_t, 3> c = {ca[0] + dx, ca[1] + dy, ca[2] + dz};
+                            for (size_t q = (size_t)lower(c); q < keyed.size() && keyed[q].first == c; ++q) {
+                                const int b = keyed[q].second;
+                                // pos_diff = convert.(T, x_a - x_b); d2 = dot (left to right); d2 <= R^2
+                                T d2 = 0;
+                                for (int d = 0; d < ND; ++d) {
+                                    const T pd = (T)(x0[(size_t)a * ND + d] - x0[(size_t)b * ND + d]);
+                                    const T sq = pd * pd;
+                                    d2 = d == 0 ? sq : d2 + sq;
+                                }
+                                if (d2 <= R2) cand.push_back(b);
+                            }
+                        }
+                std::sort(cand.begin(), cand.end());
+                start[(size_t)a + 1] = start[(size_t)a] + (int)cand.size();
+                nbr.insert(nbr.end(), cand.begin(), cand.end());
+            }
+        }
+        const size_t nn = std::max<size_t>(nbr.size(), 1);
+        CUDA_TRY(&s, cudaMalloc(&s.d_nbr_start, sizeof(int) * ((size_t)n + 1)));
+        CUDA_TRY(&s, cudaMalloc(&s.d_nbr, sizeof(int) * nn));
+        CUDA_TRY(&s, cudaMemcpy(s.d_nbr_start, start.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice));
+        if (!nbr.empty())
+            CUDA_TRY(&s, cudaMemcpy(s.d_nbr, nbr.data(), sizeof(int) * nbr.size(), cudaMemcpyHostToDevice));
+        const size_t nz = (size_t)std::max(n, 1);
+        CUDA_TRY(&s, cudaMemcpy(s.d_x0_s, s.h_x0_s.data(), sizeof(CT) * ND * (size_t)n, cudaMemcpyHostToDevice));
+        CUDA_TRY(&s, cudaMemcpy(s.d_xcur_s, s.h_x0_s.data(), sizeof(CT) * ND * (size_t)n, cudaMemcpyHostToDevice));
+        CUDA_TRY(&s, cudaMemcpy(s.d_mass_s, s.h_mass_s.data(), sizeof(T) * (size_t)n, cudaMemcpyHostToDevice));
+        CUDA_TRY(&s, cudaMemcpy(s.d_rho_s, s.h_rho_s.data(), sizeof(T) * (size_t)n, cudaMemcpyHostToDevice));
+        if (!s.h_hydro_s.empty())
+            CUDA_TRY(&s, cudaMemcpy(s.d_hydro_s, s.h_hydro_s.data(), sizeof(T) * (size_t)n, cudaMemcpyHostToDevice));
+        else
+            CUDA_TRY(&s, cudaMemset(s.d_hydro_s, 0, sizeof(T) * nz));
+        if (n > 0) {
+            const StructConst<T> k = make_struct_const(s);
+            const T eps_h2 = eps_of<T>(k.kern.h * k.kern.h);
+            switch (struct_kernel_id(s)) {
+#define TPB_CORR(KID)                                                                                              \
+    case KID:                                                                                                      \
+        LAUNCH(s, (k_struct_correction_matrix<ND, T, CT, KID>), cdiv(n, 128), 128, 0, n, k, eps_h2, s.d_nbr_start,  \
+               s.d_nbr, (const CT *)s.d_x0_s, (const T *)s.d_mass_s, (const T *)s.d_rho_s, (T *)s.d_L_s);         \
+        break;
+                TPB_CORR(0) TPB_CORR(1) TPB_CORR(2) TPB_CORR(3)
+#undef TPB_CORR
+            }
+            CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
+        }
+        return TPB_OK;
+    }
+
+    // per kick, after the fluid rebuild: current coordinates, the structure binned into the shared
+    // grid (neighbour of the fluid), deformation gradient + PK1
+    static int update_structure(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc, const CT *d_u_s,
+                                const T *d_v_s)
+    {
+        const int n = (int)s.n_s, n_int = (int)s.n_s_int;
+        if (n == 0) return TPB_OK;
+        LAUNCH(s, (k_struct_positions<ND, CT>), cdiv((int64_t)n * ND, 256), 256, 0, n, n_int, d_u_s,
+               (const CT *)s.d_x0_s, (CT *)s.d_xcur_s);
+        if (s.sp.boundary_model != TPB_BOUNDARY_NONE) {
+            int rc = bin_points(s, (const CT *)s.d_xcur_s, n, n, s.d_scell_start);
+            if (rc) return rc;
+            const MKConst<T> mk = make_mk_const(s, pc);
+            LAUNCH(s, (k_reorder_struct<ND, T, CT>), cdiv(n, 256), 256, 0, (const CT *)s.d_xcur_s, d_v_s,
+                   (const T *)s.d_hydro_s, s.d_key, s.d_scell_start, s.d_tmp_perm, n, n_int, mk.vol,
+                   (V4<CT> *)s.d_As, (V4<T> *)s.d_Bs);
+        }
+        const StructConst<T> k = make_struct_const(s);
+        switch (struct_kernel_id(s)) {
+#define TPB_DEFGRAD(KID)                                                                                          \
+    case KID:                                                                                                     \
+        LAUNCH(s, (k_struct_defgrad_pk1<ND, T, CT, KID>), cdiv(n, 128), 128, 0, n, k, s.d_nbr_start, s.d_nbr,      \
+               (const CT *)s.d_x0_s, (const CT *)s.d_xcur_s, (const T *)s.d_mass_s, (const T *)s.d_rho_s,         \
+               (const T *)s.d_L_s, (T *)s.d_F_s, (T *)s.d_pk1_s);                                                 \
+        break;
+            TPB_DEFGRAD(0) TPB_DEFGRAD(1) TPB_DEFGRAD(2) TPB_DEFGRAD(3)
+#undef TPB_DEFGRAD
+        }
+        return TPB_OK;
+    }
+
+    // per kick, after interact!: fluid <- structure, structure <- fluid, structure <- structure + gravity
+    template <int FK, int DENS>
+    static int interact_structure(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc, T *d_dv_f, T *d_dv_s)
+    {
+        constexpr int NV = DENS == 0 ? ND + 1 : ND;
+        const int n = (int)s.n_s, n_int = (int)s.n_s_int;
+        if (n == 0) return TPB_OK;
+        const bool coupled = s.sp.boundary_model == TPB_BOUNDARY_MONAGHAN_KAJTAR;
+        const MKConst<T> mk = make_mk_const(s, pc);
+        if (coupled && s.struct_fluid[1] && s.n_act > 0)
+            LAUNCH(s, (k_fluid_from_struct<ND, T, CT, FK, NV>), cdiv(s.n_act, 128), 128, 0, (int)s.n_act, g,
+                   s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.d_perm_f, s.d_scell_start,
+                   (const V4<CT> *)s.d_As, (const V4<T> *)s.d_Bs, pc.kern, mk, d_dv_f, (int)s.n_tgt);
+        if (n_int == 0) return TPB_OK;
+        LAUNCH(s, (k_struct_from_fluid<ND, T, CT>), cdiv(n_int, 128), 128, 0, n_int, g, (const CT *)s.d_xcur_s,
+               (const T *)s.d_mass_s, s.d_fcell_start, (const V4<CT> *)s.d_A,
+               (int)(coupled && s.struct_fluid[0] && s.n_act > 0), mk, d_dv_s, s.d_flags);
+        StructConst<T> k = make_struct_const(s);
+        switch (struct_kernel_id(s)) {
+#define TPB_SINTERACT(KID)                                                                                       \
+    case KID:                                                                                                    \
+        LAUNCH(s, (k_struct_interact<ND, T, CT, KID>), cdiv(n_int, 128), 128, 0, n_int, k,                        \
+               s.d_nbr_start, s.d_nbr,                                      (const CT *)s.d_x0_s, (const CT *)s.d_xcur_s,   \
+               (const T *)s.d_mass_s, (const T *)s.d_rho_s, (const T *)s.d_F_s, (const T *)s.d_pk1_s, d_dv_s);   \
+        break;
+            TPB_SINTERACT(0) TPB_SINTERACT(1) TPB_SINTERACT(2) TPB_SINTERACT(3)
+#undef TPB_SINTERACT
+        }
         return TPB_OK;
     }
 
@@ -609,9 +830,13 @@ struct Ops {
     }
 
     // ---- kick! on device pointers
-    static int kick_device(Semi &s, T *d_dv, const T *d_v, const CT *d_u)
+    static int kick_device(Semi &s, T *d_dv_ode, const T *d_v_ode, const CT *d_u_ode)
     {
-        if (s.n_act == 0) return TPB_OK;
+        const OdeLayout lay = ode_layout(s);
+        T *d_dv = d_dv_ode + lay.off_v_f;
+        const T *d_v = d_v_ode + lay.off_v_f;
+        const CT *d_u = d_u_ode + lay.off_u_f;
+        if (s.n_act == 0 && s.n_s == 0) return TPB_OK;
         if (s.fp.adaptive_sound_speed) {
             int rc_c = update_sound_speed(s, d_v);
             if (rc_c) return rc_c;
@@ -625,6 +850,10 @@ struct Ops {
                                             s.fp.background_pressure, s.fp.clip_negative_pressure,
                                             s.fp.adaptive_sound_speed && s.fp.adaptive_params_f32);
         const bool summ = s.fp.density_calculator == TPB_DENSITY_SUMMATION;
+        if (s.struct_index >= 0) {
+            rc = update_structure(s, g, pc, d_u_ode + lay.off_u_s, d_v_ode + lay.off_v_s);
+            if (rc) return rc;
+        }
         prof_mark(s, TPB_PHASE_DENSITY);
         // kernel template value: 0 Wendland C2, 1 cubic spline, 2 Wendland C4 / C6
         auto tk = [](int kernel) { return kernel <= 1 ? kernel : kernel <= TPB_KERNEL_WENDLAND_C6 ? 2 : 3; };
@@ -671,6 +900,18 @@ struct Ops {
                 rc = summ ? launch_wall_viscous<3, 1>(s, g, pc, d_dv) : launch_wall_viscous<3, 0>(s, g, pc, d_dv);
             if (rc) return rc;
         }
+        if (s.struct_index >= 0) {
+            T *d_dv_s = d_dv_ode + lay.off_v_s;
+            if (fk == 0)
+                rc = summ ? interact_structure<0, 1>(s, g, pc, d_dv, d_dv_s) : interact_structure<0, 0>(s, g, pc, d_dv, d_dv_s);
+            else if (fk == 1)
+                rc = summ ? interact_structure<1, 1>(s, g, pc, d_dv, d_dv_s) : interact_structure<1, 0>(s, g, pc, d_dv, d_dv_s);
+            else if (fk == 2)
+                rc = summ ? interact_structure<2, 1>(s, g, pc, d_dv, d_dv_s) : interact_structure<2, 0>(s, g, pc, d_dv, d_dv_s);
+            else
+                rc = summ ? interact_structure<3, 1>(s, g, pc, d_dv, d_dv_s) : interact_structure<3, 0>(s, g, pc, d_dv, d_dv_s);
+            if (rc) return rc;
+        }
         prof_mark(s, TPB_PHASE_END);
         if (s.prof_capacity > 0 && s.prof_kicks < s.prof_capacity) s.prof_kicks++;
         CUDA_TRY(&s, cudaGetLastError());
@@ -679,7 +920,8 @@ struct Ops {
 
     static int kick(Semi &s, void *dv, const void *v, const void *u)
     {
-        const size_t nu = sizeof(CT) * ND * (size_t)s.n_act, nvb = sizeof(T) * nv(s) * (size_t)s.n_act;
+        const OdeLayout lay = ode_layout(s);
+        const size_t nu = sizeof(CT) * (size_t)lay.tot_u, nvb = sizeof(T) * (size_t)lay.tot_v;
         s.launches_this_call = 0;
         int rc;
         if (s.cfg.ode_memory == TPB_MEM_HOST) {
@@ -711,28 +953,36 @@ struct Ops {
     static int drift(Semi &s, void *du, const void *v, const void *u)
     {
         (void)u;
-        const size_t nu = sizeof(CT) * ND * (size_t)s.n_tgt, nvb = sizeof(T) * nv(s) * (size_t)s.n_tgt;
+        // (slab handles drift their owned rows only: n_tgt, not n_act)
+        OdeLayout lay = ode_layout(s);
+        const int64_t total_f = s.n_tgt * ND, total_s = s.struct_index >= 0 ? s.n_s_int * ND : 0;
+        if (s.struct_index < 0) lay.tot_u = total_f, lay.tot_v = s.n_tgt * nv(s);
+        const size_t nu = sizeof(CT) * (size_t)lay.tot_u, nvb = sizeof(T) * (size_t)lay.tot_v;
         s.launches_this_call = 0;
-        int64_t total = s.n_tgt * ND;
-        if (total == 0) return TPB_OK;
+        if (total_f + total_s == 0) return TPB_OK;
+        auto launch = [&](const T *v_base, CT *du_base) {
+            if (total_f > 0)
+                LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total_f, 256), 256, 0, total_f, nv(s), v_base + lay.off_v_f,
+                       du_base + lay.off_u_f);
+            if (total_s > 0)  // structure: v holds ND entries per integrated particle, du = v
+                LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total_s, 256), 256, 0, total_s, ND, v_base + lay.off_v_s,
+                       du_base + lay.off_u_s);
+        };
         if (s.cfg.ode_memory == TPB_MEM_HOST) {
             // Page-locked v and du: one kernel streams v in and du out over PCIe at the same
             // time (full duplex) instead of copy -> kernel -> copy.
             const void *v_alias = s.host_zero_copy ? mapped_host_alias(v) : nullptr;
             void *du_alias = s.host_zero_copy ? mapped_host_alias(du) : nullptr;
             if (v_alias && du_alias) {
-                LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total, 256), 256, 0, total, nv(s), (const T *)v_alias,
-                       (CT *)du_alias);
+                launch((const T *)v_alias, (CT *)du_alias);
             } else {
                 CUDA_TRY(&s, cudaMemcpyAsync(s.d_v, v, nvb, cudaMemcpyHostToDevice, s.stream));
-                LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total, 256), 256, 0, total, nv(s), (const T *)s.d_v,
-                       (CT *)s.d_du);
+                launch((const T *)s.d_v, (CT *)s.d_du);
                 CUDA_TRY(&s, cudaMemcpyAsync(du, s.d_du, nu, cudaMemcpyDeviceToHost, s.stream));
             }
             CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
         } else {
-            LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total, 256), 256, 0, total, nv(s), (const T *)v,
-                   (CT *)du);
+            launch((const T *)v, (CT *)du);
             CUDA_TRY(&s, cudaGetLastError());
         }
         s.stats.drifts++;
@@ -758,6 +1008,17 @@ struct Ops {
             if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
             cudaFree(d_tmp);
             CUDA_TRY(&s, e);
+            return TPB_OK;
+        }
+        if (field == TPB_FIELD_DEFORMATION_GRADIENT || field == TPB_FIELD_PK1_RHO2 || field == TPB_FIELD_CORRECTION_MATRIX) {
+            if (system != s.struct_index) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "the system is not the structure system");
+            if (n != s.n_s) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
+            if (n == 0) return TPB_OK;
+            const void *src = field == TPB_FIELD_DEFORMATION_GRADIENT ? s.d_F_s
+                              : field == TPB_FIELD_PK1_RHO2           ? s.d_pk1_s
+                                                                      : s.d_L_s;
+            CUDA_TRY(&s, cudaMemcpyAsync(out, src, sizeof(T) * ND * ND * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
             return TPB_OK;
         }
         T *scratch = (T *)s.d_scratch;
@@ -795,6 +1056,7 @@ struct Ops {
     {
         // rebuild the fluid grid for the given coordinates (velocities are irrelevant here)
         const size_t nu = sizeof(CT) * ND * (size_t)s.n_act, nvb = sizeof(T) * nv(s) * (size_t)s.n_act;
+        u_ode = (const CT *)u_ode + ode_layout(s).off_u_f;  // the fluid's part of u_ode
         const CT *d_u = (const CT *)u_ode;
         T *d_vzero = nullptr;
         CUDA_TRY(&s, cudaMalloc(&d_vzero, std::max(nvb, (size_t)16)));
@@ -873,6 +1135,7 @@ struct Ops {
 #define TPB_CAT(a, b) TPB_CAT_(a, b)
 #define TPB_DECLARE_ENTRIES(TAG)                                                                         \
     int TPB_CAT(init_wall_, TAG)(Semi &s);                                                               \
+    int TPB_CAT(init_structure_, TAG)(Semi &s);                                                          \
     int TPB_CAT(kick_, TAG)(Semi &s, void *dv, const void *v, const void *u);                            \
     int TPB_CAT(drift_, TAG)(Semi &s, void *du, const void *v, const void *u);                           \
     int TPB_CAT(get_field_, TAG)(Semi &s, int sys, int field, void *out, int64_t n);                     \
@@ -880,6 +1143,7 @@ struct Ops {
                              int64_t *cnt);
 #define TPB_DEFINE_ENTRIES(TAG, ND, T, CT)                                                               \
     int TPB_CAT(init_wall_, TAG)(Semi &s) { return Ops<ND, T, CT>::init_wall(s); }                       \
+    int TPB_CAT(init_structure_, TAG)(Semi &s) { return Ops<ND, T, CT>::init_structure(s); }             \
     int TPB_CAT(kick_, TAG)(Semi &s, void *dv, const void *v, const void *u)                             \
     {                                                                                                    \
         return Ops<ND, T, CT>::kick(s, dv, v, u);                                                        \
@@ -929,6 +1193,7 @@ TPB_DEFINE_ENTRIES(3dd, 3, double, double)
     } while (0)
 
 static int dispatch_init_wall(Semi &s) { DISPATCH(s, init_wall_, s); }
+static int dispatch_init_structure(Semi &s) { DISPATCH(s, init_structure_, s); }
 static int dispatch_kick(Semi &s, void *dv, const void *v, const void *u) { DISPATCH(s, kick_, s, dv, v, u); }
 static int dispatch_drift(Semi &s, void *du, const void *v, const void *u) { DISPATCH(s, drift_, s, du, v, u); }
 static int dispatch_get_field(Semi &s, int sys, int field, void *out, int64_t n)
@@ -946,7 +1211,8 @@ static void free_device(Semi &s)
     void *ptrs[] = {s.d_mass_f, s.d_u, s.d_v, s.d_dv, s.d_du, s.d_key, s.d_slot, s.d_tmp_perm,
                     s.d_perm_f, s.d_count, s.d_fcell_start, s.d_wcell_start, s.d_block_sums,
                     s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_Vw, s.d_Pw, s.d_perm_w,
-                    s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2};
+                    s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2, s.d_x0_s, s.d_xcur_s, s.d_mass_s, s.d_rho_s, s.d_hydro_s,
+                    s.d_L_s, s.d_F_s, s.d_pk1_s, s.d_As, s.d_Bs, s.d_nbr_start, s.d_nbr, s.d_scell_start};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     tiles_free(s.tiles);
@@ -1088,12 +1354,57 @@ int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *p, int64_t n
     return TPB_OK;
 }
 
+int32_t tpb_add_structure_system(tpb_semi_t semi, const tpb_structure_params *p, int64_t n, int64_t n_integrated,
+                                 const void *initial_coords, const void *mass, const void *material_density,
+                                 const void *hydrodynamic_mass, int32_t *system_index)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !p || (n > 0 && (!initial_coords || !mass || !material_density)))
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (s->ready) return fail(s, TPB_ERR_STATE, "systems must be added before tpb_semidiscretize");
+    if (p->struct_size != (int32_t)sizeof(tpb_structure_params))
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "tpb_structure_params.struct_size mismatch");
+    if (s->struct_index >= 0)
+        return fail(s, TPB_ERR_UNSUPPORTED, "only one structure system per semidiscretization is supported");
+    if (p->kernel < TPB_KERNEL_WENDLAND_C2 || p->kernel > TPB_KERNEL_SCHOENBERG_QUINTIC)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown smoothing kernel");
+    if (!(p->smoothing_length > 0) || !(p->young_modulus > 0))
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "smoothing_length and young_modulus must be positive");
+    if (p->boundary_model != TPB_BOUNDARY_NONE && p->boundary_model != TPB_BOUNDARY_MONAGHAN_KAJTAR)
+        return fail(s, TPB_ERR_UNSUPPORTED, "structure boundary model: only BoundaryModelMonaghanKajtar (or none)");
+    if (p->boundary_model == TPB_BOUNDARY_MONAGHAN_KAJTAR &&
+        (!hydrodynamic_mass || !(p->mk_K > 0) || !(p->mk_beta > 0) || !(p->mk_spacing > 0)))
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "BoundaryModelMonaghanKajtar needs K, beta, spacing > 0 and the hydrodynamic masses");
+    if (n < 0 || n > 0x7fffffff / 16 || n_integrated < 0 || n_integrated > n)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "particle count out of range");
+    s->sp = *p;
+    s->n_s = n;
+    s->n_s_int = n_integrated;
+    const size_t ts = tsize(s->cfg.eltype), cs = tsize(s->cfg.coords_eltype);
+    auto bytes = [](const void *q, size_t len) { return std::vector<unsigned char>((const unsigned char *)q, (const unsigned char *)q + len); };
+    s->h_x0_s = bytes(initial_coords, cs * s->cfg.ndims * (size_t)n);
+    s->h_mass_s = bytes(mass, ts * (size_t)n);
+    s->h_rho_s = bytes(material_density, ts * (size_t)n);
+    if (hydrodynamic_mass) s->h_hydro_s = bytes(hydrodynamic_mass, ts * (size_t)n);
+    s->struct_index = s->n_systems++;
+    if (system_index) *system_index = s->struct_index;
+    return TPB_OK;
+}
+
 int32_t tpb_set_interaction(tpb_semi_t semi, int32_t system, int32_t neighbor, int32_t enabled)
 {
     Semi *s = (Semi *)semi;
     if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
     if (system < 0 || system >= s->n_systems || neighbor < 0 || neighbor >= s->n_systems)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "system index out of range");
+    if (system == s->struct_index || neighbor == s->struct_index) {
+        // structure <-> wall pairs never interact (rhs.jl:111-119); the rest is switchable
+        if (system == s->struct_index && neighbor == s->struct_index) {
+            if (!enabled) return fail(s, TPB_ERR_UNSUPPORTED, "the structure's self-interaction cannot be switched off");
+        } else if (system == s->struct_index && neighbor == s->fluid_index) s->struct_fluid[0] = enabled ? 1 : 0;
+        else if (system == s->fluid_index && neighbor == s->struct_index) s->struct_fluid[1] = enabled ? 1 : 0;
+        return TPB_OK;
+    }
     // internal matrix is indexed [fluid=0|wall=1]
     int a = system == s->fluid_index ? 0 : 1, b = neighbor == s->fluid_index ? 0 : 1;
     s->interaction[a][b] = enabled ? 1 : 0;
@@ -1141,8 +1452,10 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
                     hi[d] = std::max(hi[d], v);
                 }
         };
-        if (u0_ode && s->n_f > 0) extend((const unsigned char *)u0_ode, s->n_f);
+        if (u0_ode && s->n_f > 0)
+            extend((const unsigned char *)u0_ode + cs * (size_t)ode_layout(*s).off_u_f, s->n_f);
         if (s->n_w > 0) extend(s->h_coords_w.data(), s->n_w);
+        if (s->n_s > 0) extend(s->h_x0_s.data(), s->n_s);
         if (first) return fail(s, TPB_ERR_INVALID_ARGUMENT, "no coordinates to derive the bounding box from");
         for (int d = 0; d < nd; ++d) { lo[d] -= 2 * R; hi[d] += 2 * R; }
     }
@@ -1213,15 +1526,34 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
 
     // device buffers
     const size_t nf = (size_t)std::max<int64_t>(s->n_f, 1), nw = (size_t)std::max<int64_t>(s->n_w, 1);
-    const size_t nmax = std::max(nf, nw);
+    const size_t ns = (size_t)std::max<int64_t>(s->n_s, 1);
+    const size_t nmax = std::max(std::max(nf, nw), ns);
     const int nvars = s->fp.density_calculator == TPB_DENSITY_SUMMATION ? nd : nd + 1;
     CUDA_TRY(s, cudaMalloc(&s->d_mass_f, ts * nf));
     CUDA_TRY(s, cudaMemcpy(s->d_mass_f, s->h_mass_f.data(), ts * (size_t)s->n_f, cudaMemcpyHostToDevice));
     if (s->cfg.ode_memory == TPB_MEM_HOST) {
-        CUDA_TRY(s, cudaMalloc(&s->d_u, cs * nd * nf));
-        CUDA_TRY(s, cudaMalloc(&s->d_v, ts * nvars * nf));
-        CUDA_TRY(s, cudaMalloc(&s->d_dv, ts * nvars * nf));
-        CUDA_TRY(s, cudaMalloc(&s->d_du, cs * nd * nf));
+        // staging copies of the whole ODE vectors (fluid + structure entries)
+        const size_t extra = s->struct_index >= 0 ? (size_t)nd * (size_t)s->n_s_int : 0;
+        CUDA_TRY(s, cudaMalloc(&s->d_u, cs * (nd * nf + extra)));
+        CUDA_TRY(s, cudaMalloc(&s->d_v, ts * (nvars * nf + extra)));
+        CUDA_TRY(s, cudaMalloc(&s->d_dv, ts * (nvars * nf + extra)));
+        CUDA_TRY(s, cudaMalloc(&s->d_du, cs * (nd * nf + extra)));
+    }
+    if (s->struct_index >= 0) {
+        CUDA_TRY(s, cudaMalloc(&s->d_x0_s, cs * nd * ns));
+        CUDA_TRY(s, cudaMalloc(&s->d_xcur_s, cs * nd * ns));
+        CUDA_TRY(s, cudaMalloc(&s->d_mass_s, ts * ns));
+        CUDA_TRY(s, cudaMalloc(&s->d_rho_s, ts * ns));
+        CUDA_TRY(s, cudaMalloc(&s->d_hydro_s, ts * ns));
+        CUDA_TRY(s, cudaMalloc(&s->d_L_s, ts * nd * nd * ns));
+        CUDA_TRY(s, cudaMalloc(&s->d_F_s, ts * nd * nd * ns));
+        CUDA_TRY(s, cudaMalloc(&s->d_pk1_s, ts * nd * nd * ns));
+        CUDA_TRY(s, cudaMemset(s->d_F_s, 0, ts * nd * nd * ns));
+        CUDA_TRY(s, cudaMemset(s->d_pk1_s, 0, ts * nd * nd * ns));
+        CUDA_TRY(s, cudaMalloc(&s->d_As, 4 * cs * (ns + 8)));
+        CUDA_TRY(s, cudaMalloc(&s->d_Bs, 4 * ts * (ns + 8)));
+        CUDA_TRY(s, cudaMalloc(&s->d_scell_start, sizeof(int) * (size_t)(s->ncells + 4)));
+        CUDA_TRY(s, cudaMemset(s->d_scell_start, 0, sizeof(int) * (size_t)(s->ncells + 4)));
     }
     CUDA_TRY(s, cudaMalloc(&s->d_key, sizeof(int) * nmax));
     CUDA_TRY(s, cudaMalloc(&s->d_slot, sizeof(int) * nmax));
@@ -1273,6 +1605,10 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
         if (*s->h_flags & 1)
             return fail(s, TPB_ERR_OUT_OF_BOUNDS, "wall particles outside the bounding box");
     }
+    if (s->struct_index >= 0) {
+        rc = dispatch_init_structure(*s);
+        if (rc) return rc;
+    }
     s->h_mass_f.clear(); s->h_mass_f.shrink_to_fit();
     s->h_mass_w.clear(); s->h_mass_w.shrink_to_fit();
     s->h_dens_w.clear(); s->h_dens_w.shrink_to_fit();
@@ -1284,10 +1620,9 @@ int32_t tpb_ode_sizes(tpb_semi_t semi, int64_t *n_u, int64_t *n_v)
 {
     Semi *s = (Semi *)semi;
     if (!s || s->fluid_index < 0) return fail(s, TPB_ERR_STATE, "no fluid system");
-    const int nd = s->cfg.ndims;
-    const int nvars = s->fp.density_calculator == TPB_DENSITY_SUMMATION ? nd : nd + 1;
-    if (n_u) *n_u = s->n_act * nd;
-    if (n_v) *n_v = s->n_act * nvars;
+    const OdeLayout lay = ode_layout(*s);
+    if (n_u) *n_u = lay.tot_u;
+    if (n_v) *n_v = lay.tot_v;
     return TPB_OK;
 }
 
@@ -1296,15 +1631,25 @@ int32_t tpb_system_range(tpb_semi_t semi, int32_t system, int64_t *u_first, int6
 {
     Semi *s = (Semi *)semi;
     if (!s || system < 0 || system >= s->n_systems) return fail(s, TPB_ERR_INVALID_ARGUMENT, "system index out of range");
-    int64_t nu = 0, nv = 0;
-    tpb_ode_sizes(semi, &nu, &nv);
-    const bool is_fluid = system == s->fluid_index;
-    // the wall has no integrated particles: zero-length range placed after/before the fluid
-    const bool wall_first = s->wall_index >= 0 && s->wall_index < s->fluid_index;
-    if (u_first) *u_first = is_fluid ? 0 : (wall_first ? 0 : nu);
-    if (u_len) *u_len = is_fluid ? nu : 0;
-    if (v_first) *v_first = is_fluid ? 0 : (wall_first ? 0 : nv);
-    if (v_len) *v_len = is_fluid ? nv : 0;
+    const OdeLayout lay = ode_layout(*s);
+    const int nd = s->cfg.ndims;
+    const int nvars = s->fp.density_calculator == TPB_DENSITY_SUMMATION ? nd : nd + 1;
+    int64_t uf = 0, ul = 0, vf = 0, vl = 0;
+    if (system == s->fluid_index) {
+        uf = lay.off_u_f, ul = s->n_act * nd, vf = lay.off_v_f, vl = s->n_act * nvars;
+    } else if (system == s->struct_index) {
+        uf = lay.off_u_s, ul = s->n_s_int * nd, vf = lay.off_v_s, vl = s->n_s_int * nd;
+    } else {
+        // the wall has no integrated particles: a zero-length range where its entries would start
+        for (int other = 0; other < system; ++other) {
+            if (other == s->fluid_index) uf += s->n_act * nd, vf += s->n_act * nvars;
+            if (other == s->struct_index) uf += s->n_s_int * nd, vf += s->n_s_int * nd;
+        }
+    }
+    if (u_first) *u_first = uf;
+    if (u_len) *u_len = ul;
+    if (v_first) *v_first = vf;
+    if (v_len) *v_len = vl;
     return TPB_OK;
 }
 
@@ -1396,6 +1741,8 @@ int32_t tpb_set_fluid_count(tpb_semi_t semi, int64_t n_active, int64_t n_targets
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "need 0 <= n_targets <= n_active <= capacity of the fluid system");
     if (n_targets < n_active && s->fp.density_calculator == TPB_DENSITY_SUMMATION)
         return fail(s, TPB_ERR_UNSUPPORTED, "ghost particles need ContinuityDensity (their density travels with them)");
+    if (s->struct_index >= 0 && (n_active != s->n_f || n_targets != s->n_f))
+        return fail(s, TPB_ERR_UNSUPPORTED, "slab ghosts are not combined with a structure system");
     if (n_targets < n_active && s->fp.adaptive_sound_speed)
         return fail(s, TPB_ERR_UNSUPPORTED, "StateEquationAdaptiveCole needs the maximum velocity of all slabs");
     s->n_act = n_active;

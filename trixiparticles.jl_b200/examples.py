@@ -12,8 +12,9 @@ from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
                     BoundaryModelDummyParticles, ContinuityDensity,
                     DensityDiffusionMolteniColagrossi, SchoenbergCubicSplineKernel,
                     StateEquationAdaptiveCole, StateEquationCole, SummationDensity, WallBoundarySystem,
-                    WeaklyCompressibleSPHSystem, WendlandC2Kernel)
-from .setups import RectangularTank
+                    WeaklyCompressibleSPHSystem, WendlandC2Kernel, BoundaryModelMonaghanKajtar,
+                    PenaltyForceGanzenmueller, TotalLagrangianSPHSystem)
+from .setups import RectangularShape, RectangularTank, union
 
 
 def dam_break_2d(particles_per_height=40, *, eltype=np.float64, coordinates_eltype=np.float64,
@@ -128,3 +129,54 @@ def perturbed_state(fluid, seed=1234, position_jitter=0.1, velocity_scale=0.05,
     else:
         v = vel.astype(fluid.eltype)
     return np.ascontiguousarray(u), np.ascontiguousarray(v)
+
+
+def dam_break_plate_2d(fluid_particle_spacing=0.01, *, n_particles_x=5, eltype=np.float64,
+                       coordinates_eltype=None, initial_fluid_size=(0.146, 2 * 0.146), plate_position=None,
+                       E=1e6, nu=0.0):
+    """examples/fsi/dam_break_plate_2d.jl:19-134 (BASELINE config 5): dam break against an elastic
+    plate clamped at its base; WCSPH fluid, dummy-particle tank, TLSPH plate with a
+    BoundaryModelMonaghanKajtar towards the fluid and a PenaltyForceGanzenmueller.  The reference's
+    GPU tests run it with `initial_fluid_size = (0.15, 0.29)` in Float32 (test/examples/gpu.jl:664-726).
+    Returns (fluid_system, boundary_system, structure_system, tank)."""
+    t = np.dtype(eltype).type
+    coordinates_eltype = coordinates_eltype or np.float64
+    gravity = 9.81
+    dx = fluid_particle_spacing
+    tank_size = tuple(4 * s for s in initial_fluid_size)
+    fluid_density = 1000.0
+    sound_speed = 20 * np.sqrt(gravity * initial_fluid_size[1])
+    state_equation = StateEquationCole(sound_speed=float(t(sound_speed)), reference_density=fluid_density,
+                                       exponent=1)
+    tank = RectangularTank(dx, initial_fluid_size, tank_size, fluid_density, n_layers=4, spacing_ratio=1,
+                           acceleration=(0.0, -gravity), state_equation=state_equation,
+                           coordinates_eltype=coordinates_eltype, eltype=eltype)
+    length_beam, thickness, structure_density = 0.08, 0.012, 2500
+    ds = thickness / (n_particles_x - 1)
+    n_particles_y = int(np.rint(length_beam / ds)) + 1
+    if plate_position is None:
+        plate_position = (2 * initial_fluid_size[0], 0.0)
+    non_fixed_position = (plate_position[0], plate_position[1] + ds)
+    plate = RectangularShape(ds, (n_particles_x, n_particles_y - 1), non_fixed_position, density=structure_density,
+                             place_on_shell=True, coordinates_eltype=coordinates_eltype, eltype=eltype)
+    clamped = RectangularShape(ds, (n_particles_x, 1), plate_position, density=structure_density,
+                               place_on_shell=True, coordinates_eltype=coordinates_eltype, eltype=eltype)
+    structure = union(clamped, plate)
+    h = 1.75 * dx
+    kernel = WendlandC2Kernel(2)
+    fluid = WeaklyCompressibleSPHSystem(
+        tank.fluid, smoothing_kernel=kernel, smoothing_length=h, density_calculator=ContinuityDensity(),
+        state_equation=state_equation, viscosity=ArtificialViscosityMonaghan(alpha=0.02, beta=0.0),
+        acceleration=(0.0, -gravity))
+    model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass, AdamiPressureExtrapolation(),
+                                        kernel, h, state_equation=state_equation, clip_negative_pressure=True)
+    wall = WallBoundarySystem(tank.boundary, model)
+    hydrodynamic_densities = t(fluid_density) * np.ones(structure.nparticles, dtype=eltype)
+    hydrodynamic_masses = (hydrodynamic_densities * t(ds) ** 2).astype(eltype)
+    k_structure = gravity * initial_fluid_size[1]
+    model_structure = BoundaryModelMonaghanKajtar(k_structure, dx / ds, ds, hydrodynamic_masses)
+    structure_system = TotalLagrangianSPHSystem(
+        structure, smoothing_kernel=WendlandC2Kernel(2), smoothing_length=np.sqrt(2) * ds, young_modulus=E,
+        poisson_ratio=nu, boundary_model=model_structure, clamped_particles=range(clamped.nparticles),
+        acceleration=(0.0, -gravity), penalty_force=PenaltyForceGanzenmueller(alpha=0.01))
+    return fluid, wall, structure_system, tank

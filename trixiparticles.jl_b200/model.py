@@ -310,3 +310,89 @@ class WallBoundarySystem:
     n_integrated_particles = property(lambda self: 0)  # wall_boundary/system.jl:78-90
     u_nvariables = property(lambda self: 0)
     v_nvariables = property(lambda self: 1)
+
+
+@dataclass(frozen=True)
+class PenaltyForceGanzenmueller:
+    """structure/total_lagrangian_sph/penalty_force.jl:1-16."""
+    alpha: float = 0.1
+
+
+class BoundaryModelMonaghanKajtar:
+    """wall_boundary/monaghan_kajtar.jl:1-34: repulsive boundary particles
+    `BoundaryModelMonaghanKajtar(K, beta, boundary_particle_spacing, mass; viscosity=nothing)`."""
+
+    def __init__(self, K, beta, boundary_particle_spacing, mass, *, viscosity=None):
+        if viscosity is not None:
+            raise ValueError("a viscous Monaghan-Kajtar boundary is outside the accelerated hot path")
+        self.hydrodynamic_mass = np.asarray(mass)
+        self.eltype = self.hydrodynamic_mass.dtype
+        self.K = self.eltype.type(K)
+        self.beta = self.eltype.type(beta)
+        self.boundary_particle_spacing = self.eltype.type(boundary_particle_spacing)
+        self.viscosity = None
+
+
+class TotalLagrangianSPHSystem:
+    """structure/total_lagrangian_sph/system.jl:76-184 on the accelerated path (BASELINE config 5):
+    scalar `young_modulus` / `poisson_ratio`, fixed clamped particles, optional
+    `PenaltyForceGanzenmueller`, `boundary_model` = `BoundaryModelMonaghanKajtar` or None.
+    As in the reference, the clamped particles are moved to the end of the particle list
+    (`move_particles_to_end!`); `clamped_particles` are 0-based indices here."""
+
+    def __init__(self, initial_condition: InitialCondition, *, smoothing_kernel, smoothing_length,
+                 young_modulus, poisson_ratio, clamped_particles=(), clamped_particles_motion=None,
+                 acceleration: Optional[Sequence[float]] = None, penalty_force=None, viscosity=None,
+                 source_terms=None, boundary_model=None, self_interaction_nhs="default",
+                 velocity_averaging=None):
+        nd = initial_condition.ndims
+        if smoothing_kernel.ndims != nd:
+            raise ValueError(f"smoothing kernel dimensionality must be {nd} for a {nd}D problem")
+        if acceleration is None:
+            acceleration = (0.0,) * nd
+        if len(acceleration) != nd:
+            raise ValueError(f"`acceleration` must be of length {nd} for a {nd}D problem")
+        for name, val in (("clamped_particles_motion", clamped_particles_motion), ("viscosity", viscosity),
+                          ("source_terms", source_terms), ("velocity_averaging", velocity_averaging)):
+            if val is not None:
+                raise ValueError(f"`{name}` is outside the accelerated hot path (see DESIGN.md)")
+        if not (np.isscalar(young_modulus) and np.isscalar(poisson_ratio)):
+            raise ValueError("per-particle material constants are outside the accelerated hot path")
+        if penalty_force is not None and not isinstance(penalty_force, PenaltyForceGanzenmueller):
+            raise ValueError("`penalty_force` must be a PenaltyForceGanzenmueller")
+        if boundary_model is not None and not isinstance(boundary_model, BoundaryModelMonaghanKajtar):
+            raise ValueError("structure `boundary_model`: only BoundaryModelMonaghanKajtar is on the accelerated path")
+        clamped = np.asarray(list(clamped_particles), dtype=np.int64)
+        n = initial_condition.nparticles
+        if len(np.unique(clamped)) != len(clamped):
+            raise ValueError("`clamped_particles` contains duplicate particle indices")
+        order = np.concatenate([np.setdiff1d(np.arange(n), clamped, assume_unique=False), clamped])
+        ic = initial_condition
+        self.initial_condition = InitialCondition(
+            coordinates=np.ascontiguousarray(ic.coordinates[order]), velocity=np.ascontiguousarray(ic.velocity[order]),
+            mass=np.ascontiguousarray(ic.mass[order]), density=np.ascontiguousarray(ic.density[order]),
+            pressure=np.ascontiguousarray(ic.pressure[order]), particle_spacing=ic.particle_spacing)
+        if boundary_model is not None and len(clamped):
+            boundary_model = BoundaryModelMonaghanKajtar(boundary_model.K, boundary_model.beta,
+                                                         boundary_model.boundary_particle_spacing,
+                                                         boundary_model.hydrodynamic_mass[order])
+        self.particle_order = order
+        self.n_clamped_particles = len(clamped)
+        self.smoothing_kernel = smoothing_kernel
+        self.eltype = ic.eltype
+        self.coordinates_eltype = ic.coordinates_eltype
+        self.smoothing_length = self.eltype.type(smoothing_length)
+        self.young_modulus = self.eltype.type(young_modulus)
+        self.poisson_ratio = self.eltype.type(poisson_ratio)
+        self.acceleration = np.asarray(acceleration, dtype=self.eltype)
+        self.penalty_force = penalty_force
+        self.boundary_model = boundary_model
+        self.initial_coordinates = self.initial_condition.coordinates
+        self.mass = self.initial_condition.mass
+        self.material_density = self.initial_condition.density
+
+    ndims = property(lambda self: self.initial_condition.ndims)
+    nparticles = property(lambda self: self.initial_condition.nparticles)
+    n_integrated_particles = property(lambda self: self.initial_condition.nparticles - self.n_clamped_particles)
+    u_nvariables = property(lambda self: self.ndims)
+    v_nvariables = property(lambda self: self.ndims)   # system.jl:277-279

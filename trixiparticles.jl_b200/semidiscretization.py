@@ -18,7 +18,8 @@ import numpy as np
 from . import _lib
 from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
                     DensityDiffusionMolteniColagrossi, SourceTermDamping, StateEquationAdaptiveCole,
-                    SummationDensity, WallBoundarySystem, WeaklyCompressibleSPHSystem)
+                    SummationDensity, TotalLagrangianSPHSystem, WallBoundarySystem,
+                    WeaklyCompressibleSPHSystem)
 
 
 @dataclass
@@ -67,10 +68,13 @@ class Semidiscretization:
             raise ValueError("at least one system is required")
         fluids = [s for s in systems if isinstance(s, WeaklyCompressibleSPHSystem)]
         walls = [s for s in systems if isinstance(s, WallBoundarySystem)]
-        if len(fluids) + len(walls) != len(systems):
-            raise ValueError("only WeaklyCompressibleSPHSystem and WallBoundarySystem are on the accelerated path")
-        if len(fluids) != 1 or len(walls) > 1:
-            raise ValueError("the accelerated path takes exactly one fluid system and at most one wall system")
+        structures = [s for s in systems if isinstance(s, TotalLagrangianSPHSystem)]
+        if len(fluids) + len(walls) + len(structures) != len(systems):
+            raise ValueError("only WeaklyCompressibleSPHSystem, WallBoundarySystem and TotalLagrangianSPHSystem "
+                             "are on the accelerated path")
+        if len(fluids) != 1 or len(walls) > 1 or len(structures) > 1:
+            raise ValueError("the accelerated path takes exactly one fluid system, at most one wall system and "
+                             "at most one structure system")
         nd = {s.ndims for s in systems}
         if len(nd) != 1:
             raise ValueError("all systems must have the same number of dimensions")
@@ -108,6 +112,10 @@ class Semidiscretization:
     @property
     def wall(self) -> Optional[WallBoundarySystem]:
         return next((s for s in self.systems if isinstance(s, WallBoundarySystem)), None)
+
+    @property
+    def structure(self) -> Optional[TotalLagrangianSPHSystem]:
+        return next((s for s in self.systems if isinstance(s, TotalLagrangianSPHSystem)), None)
 
     def system_index(self, system) -> int:
         return next(i for i, s in enumerate(self.systems) if s is system)
@@ -200,6 +208,25 @@ class Semidiscretization:
             p.sound_speed_from_fluid = 1
         return p
 
+    def _structure_params(self, st: TotalLagrangianSPHSystem) -> _lib.StructureParams:
+        t = self.eltype.type
+        p = _lib.StructureParams()
+        p.struct_size = C.sizeof(_lib.StructureParams)
+        p.kernel = st.smoothing_kernel.kernel_id
+        p.smoothing_length = float(t(st.smoothing_length))
+        p.young_modulus = float(t(st.young_modulus))
+        p.poisson_ratio = float(t(st.poisson_ratio))
+        if st.penalty_force is not None:
+            p.has_penalty_force = 1
+            p.penalty_alpha = float(t(st.penalty_force.alpha))
+        for d in range(self.ndims):
+            p.acceleration[d] = float(st.acceleration[d])
+        m = st.boundary_model
+        if m is not None:
+            p.boundary_model = _lib.BOUNDARY_MONAGHAN_KAJTAR
+            p.mk_K, p.mk_beta, p.mk_spacing = float(t(m.K)), float(t(m.beta)), float(t(m.boundary_particle_spacing))
+        return p
+
     def _create(self, u0_ode: np.ndarray):
         L = _lib.load()
         be = self.parallelization_backend
@@ -235,6 +262,19 @@ class Semidiscretization:
                     fp = self._fluid_params(s)
                     _lib.check(h, L.tpb_add_fluid_system(h, C.byref(fp), mass.size,
                                                          mass.ctypes.data, C.byref(idx)))
+                elif isinstance(s, TotalLagrangianSPHSystem):
+                    if be.ghost_capacity:
+                        raise ValueError("slab ghosts are not combined with a structure system")
+                    x0 = np.ascontiguousarray(s.initial_coordinates, dtype=self.coordinates_eltype)
+                    mass = np.ascontiguousarray(s.mass, dtype=self.eltype)
+                    rho = np.ascontiguousarray(s.material_density, dtype=self.eltype)
+                    hyd = (np.ascontiguousarray(s.boundary_model.hydrodynamic_mass, dtype=self.eltype)
+                           if s.boundary_model is not None else None)
+                    sp = self._structure_params(s)
+                    _lib.check(h, L.tpb_add_structure_system(h, C.byref(sp), s.nparticles, s.n_integrated_particles,
+                                                             x0.ctypes.data, mass.ctypes.data, rho.ctypes.data,
+                                                             hyd.ctypes.data if hyd is not None else None,
+                                                             C.byref(idx)))
                 else:
                     coords = np.ascontiguousarray(s.coordinates, dtype=self.coordinates_eltype)
                     mass = np.ascontiguousarray(s.boundary_model.hydrodynamic_mass, dtype=self.eltype)
@@ -321,7 +361,15 @@ class Semidiscretization:
         """`system.pressure`, `cache.density`, `boundary_model.pressure/cache.density/cache.volume`
         after the last kick (fluid.jl:312-326, wall_boundary/system.jl:339-350)."""
         fid = {"pressure": _lib.FIELD_PRESSURE, "density": _lib.FIELD_DENSITY,
-               "volume": _lib.FIELD_VOLUME, "wall_velocity": _lib.FIELD_WALL_VELOCITY}[field]
+               "volume": _lib.FIELD_VOLUME, "wall_velocity": _lib.FIELD_WALL_VELOCITY,
+               "deformation_grad": _lib.FIELD_DEFORMATION_GRADIENT, "pk1_rho2": _lib.FIELD_PK1_RHO2,
+               "correction_matrix": _lib.FIELD_CORRECTION_MATRIX}[field]
+        if fid >= _lib.FIELD_DEFORMATION_GRADIENT:
+            # structure: (n, ND, ND) with [p, j, i] = M[i, j, p] (the reference's ND x ND x n memory layout)
+            out = np.zeros((system.nparticles, self.ndims, self.ndims), dtype=self.eltype)
+            _lib.check(self._handle, _lib.load().tpb_get_system_field(
+                self._handle, self.system_index(system), fid, out.ctypes.data, system.nparticles))
+            return out
         if field == "wall_velocity":   # boundary_model.cache.wall_velocity, (n, ND)
             out = np.zeros((system.nparticles, self.ndims), dtype=self.eltype)
             _lib.check(self._handle, _lib.load().tpb_get_system_field(
@@ -391,6 +439,12 @@ def semidiscretize(semi: Semidiscretization, tspan) -> DynamicalODEProblem:
             continue
         u = semi.wrap_u(u0, s)
         v = semi.wrap_v(v0, s)
+        if isinstance(s, TotalLagrangianSPHSystem):
+            # write_u0! / write_v0! (total_lagrangian_sph/system.jl:588-612): integrated particles only
+            n_int = s.n_integrated_particles
+            u[:] = s.initial_condition.coordinates[:n_int]
+            v[:] = s.initial_condition.velocity[:n_int]
+            continue
         u[:] = s.initial_condition.coordinates
         v[:, : s.ndims] = s.initial_condition.velocity
         if not isinstance(s.density_calculator, SummationDensity):

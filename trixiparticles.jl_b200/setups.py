@@ -107,12 +107,16 @@ def _x_index_range(particle_spacing, n0, min0, shift0, x_window, coordinates_elt
 
 
 def rectangular_shape_coords(particle_spacing, n_particles_per_dimension, min_coordinates,
-                             loop_order=None, coordinates_eltype=np.float64, x_range=None):
-    """rectangular_shape.jl:189-224: min_coordinates + spacing * (index - 0.5)."""
+                             loop_order=None, coordinates_eltype=np.float64, x_range=None,
+                             place_on_shell=False):
+    """rectangular_shape.jl:189-224: min_coordinates + spacing * (index - 0.5); `place_on_shell`:
+    the first particle sits AT min_coordinates (structures; rectangular_shape.jl:205-209)."""
     ct = np.dtype(coordinates_eltype).type
     idx = _permuted_indices(tuple(n_particles_per_dimension), loop_order, x_range)
     spacing = ct(particle_spacing)
     mins = np.asarray(min_coordinates, dtype=np.float64)
+    if place_on_shell:
+        mins = mins - 0.5 * np.float64(spacing)
     # Julia: min_coordinates (Float64 tuple) .+ particle_spacing .* (index .- 0.5)
     coords = mins[None, :] + np.float64(spacing) * (idx.astype(np.float64) - 0.5)
     if ct is np.float32:
@@ -147,7 +151,7 @@ def _initialize_pressure(n_per_dim, particle_spacing, acceleration, density_fun,
 def RectangularShape(particle_spacing, n_particles_per_dimension, min_coordinates, *,
                      velocity=None, mass=None, density=None, pressure=0.0, acceleration=None,
                      state_equation=None, coordinates_eltype=np.float64, loop_order=None,
-                     eltype=np.float64, x_range=None) -> InitialCondition:
+                     eltype=np.float64, x_range=None, place_on_shell=False) -> InitialCondition:
     """rectangular_shape.jl:79-151.  `eltype` plays the role of `eltype(particle_spacing)`.
     `x_range`: only the lattice columns [i0, i1) along x (see `_permuted_indices`)."""
     t = np.dtype(eltype)
@@ -155,7 +159,7 @@ def RectangularShape(particle_spacing, n_particles_per_dimension, min_coordinate
     ndims = len(n_per_dim)
     coords = rectangular_shape_coords(particle_spacing, n_per_dim, min_coordinates,
                                       loop_order=loop_order, coordinates_eltype=coordinates_eltype,
-                                      x_range=x_range)
+                                      x_range=x_range, place_on_shell=place_on_shell)
     n = coords.shape[0]
     if acceleration is not None:
         if state_equation is None:

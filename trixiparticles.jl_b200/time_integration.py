@@ -57,12 +57,25 @@ def calculate_dt(system: WeaklyCompressibleSPHSystem, cfl_number: float) -> floa
     return min(dt_viscosity, dt_acceleration, dt_sound_speed)
 
 
+def calculate_dt_structure(system, cfl_number: float) -> float:
+    """total_lagrangian_sph/system.jl:701-717: cfl h / sqrt(K / rho_min), bulk modulus
+    K = E / (ND (1 - 2 nu))."""
+    E, nu = float(system.young_modulus), float(system.poisson_ratio)
+    K = E / (system.ndims * (1 - 2 * nu))
+    sound_speed = math.sqrt(K / float(np.min(system.material_density)))
+    return cfl_number * float(system.smoothing_length) / sound_speed
+
+
 @dataclass
 class StepsizeCallback:
     cfl: float
 
     def dt(self, semi) -> float:
-        return min(calculate_dt(s, self.cfl) for s in semi.systems if isinstance(s, WeaklyCompressibleSPHSystem))
+        # minimum over all systems (stepsize.jl:63-79); walls contribute Inf
+        from .model import TotalLagrangianSPHSystem
+        dts = [calculate_dt(s, self.cfl) for s in semi.systems if isinstance(s, WeaklyCompressibleSPHSystem)]
+        dts += [calculate_dt_structure(s, self.cfl) for s in semi.systems if isinstance(s, TotalLagrangianSPHSystem)]
+        return min(dts)
 
 
 def max_x_coord(system, v_ode, u_ode, semi, t) -> float:
