@@ -260,6 +260,19 @@ int32_t tpb_vec_axpby(tpb_semi_t semi, int64_t n, int32_t eltype, double a, cons
 int32_t tpb_vec_rk2n_stage(tpb_semi_t semi, int64_t n, int32_t eltype, double A, double B, double dt,
                            const void *rhs, void *tmp, void *state);
 int32_t tpb_vec_fill(tpb_semi_t semi, int64_t n, int32_t eltype, double value, void *x);
+/* y = a0 x0 + a1 x1 + a2 x2 + a3 x3; a NULL x skips its term, any x may alias y.  The register
+ * updates of a 3S*+ low-storage stage (RDPK3SpFSAL35, the integrator of examples/fluid/dam_break_3d.jl:85:
+ * u = gamma1 u + gamma2 tmp + gamma3 uprev + beta dt k) in one pass. */
+int32_t tpb_vec_lincomb4(tpb_semi_t semi, int64_t n, int32_t eltype, double a0, const void *x0, double a1,
+                         const void *x1, double a2, const void *x2, double a3, const void *x3, void *y);
+/* `SymplecticPositionVerlet` velocity / density update of one WCSPH system
+ * (ext/TrixiParticlesOrdinaryDiffEqSymplecticRKExt.jl:137-171) on its rows of v_ode: `nvars` entries
+ * per particle (ndims velocities [+ density]); `du` holds the half-step state on entry. */
+int32_t tpb_vec_verlet_update(tpb_semi_t semi, int64_t n_particles, int32_t ndims, int32_t nvars, int32_t eltype,
+                              double dt, const void *kdu, const void *duprev, void *du);
+/* test hook: out[i] = div_fast(x, y[i]) with the library's fast division (util.jl:3-5,
+ * ext/TrixiParticlesCUDAExt.jl:12-33; reference test: test/examples/gpu.jl:30-78) */
+int32_t tpb_vec_div_fast(tpb_semi_t semi, int64_t n, int32_t eltype, double x, const void *y, void *out);
 /* max_k x[offset + k * stride], k < count, to the host (synchronises); `max_x_coord` of
  * general/custom_quantities.jl is (count = nparticles, stride = ND, offset = 0) on u_ode */
 int32_t tpb_vec_strided_max(tpb_semi_t semi, int64_t count, int32_t eltype, int32_t stride, int32_t offset,

@@ -223,6 +223,19 @@ def neighbor_pairs(x, y, radius, dtype=None, grid=False):
         cap = int(n)
 
 
+def neighbor_pair_count(x, y, radius, dtype=None) -> int:
+    """Number of (i, j) with |x_i - y_j|^2 <= R^2 (cell-list search; nothing is stored)."""
+    x = np.ascontiguousarray(x)
+    y = np.ascontiguousarray(y, dtype=x.dtype)
+    dtype = np.dtype(dtype) if dtype is not None else x.dtype
+    f = getattr(lib(), f"orc_pairs_grid_{suffix(dtype, x.dtype)}")
+    dummy = np.empty(1, dtype=np.int32)
+    n = f(x.shape[1], x.shape[0], _ptr(x), y.shape[0], _ptr(y), float(radius), 0, _ptr(dummy), _ptr(dummy))
+    if n < 0:
+        raise MemoryError("oracle grid allocation failed")
+    return int(n)
+
+
 # ---------------------------------------------------------------- kick! / drift!
 
 def kick(fp: FluidParams, wp, mass_f, coords_w, mass_w, v_ode, u_ode, dtype, use_grid=True,

@@ -579,3 +579,81 @@ def test_empty_fluid():
     tp.kick_(np.zeros(0), np.zeros(0), np.zeros(0), ode.p, 0.0)
     tp.drift_(np.zeros(0), np.zeros(0), np.zeros(0), ode.p, 0.0)
     semi.close()
+
+
+# ------------------------------------------------------------------ the bench workload itself
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("coords", [np.float32, np.float64])
+def test_bench_workload_matches_oracle(oracle, coords):
+    """BASELINE config 3 at the size bench.py times (dx = 0.0126: 992 319 fluid + 1 599 800 wall
+    particles, Float32 fields; Float32 and Float64 coordinates): dv of the lattice state bench.py
+    uses and of the perturbed state, and the accepted-pair COUNTS of all three ordered system pairs
+    (bench.py reports 101 034 113 fluid-fluid pairs) against the CPU oracle."""
+    import torch
+    fluid, wall, _ = examples.dam_break_3d(0.0126, coordinates_eltype=coords)
+    assert (fluid.nparticles, wall.nparticles) == (992319, 1599800)
+    ic = fluid.initial_condition
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    dev = ode.u0.device
+    states = [(np.ascontiguousarray(ic.coordinates),
+               np.ascontiguousarray(np.concatenate([ic.velocity, ic.density[:, None]], axis=1))),
+              examples.perturbed_state(fluid)]
+    for k, (u, v) in enumerate(states):
+        u_d, v_d = torch.from_numpy(u.reshape(-1)).to(dev), torch.from_numpy(v.reshape(-1)).to(dev)
+        dv_d = torch.full_like(v_d, float("nan"))
+        ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
+        semi.synchronize()
+        got = dv_d.cpu().numpy().reshape(v.shape)
+        ref = adapter.kick(fluid, wall, u, v)["dv"]
+        assert np.isfinite(got).all()
+        errs = (rel_inf(got[:, :3], ref[:, :3]), rel_inf(got[:, 3], ref[:, 3]))
+        assert max(errs) <= 1e-5, (k, errs)
+        if k == 0:
+            R = float(np.float32(2) * fluid.smoothing_length)
+            counts = {}
+            for name, a, b, xa, xb in (("fluid_fluid", fluid, fluid, u, u), ("fluid_wall", fluid, wall, u, wall.coordinates),
+                                       ("wall_fluid", wall, fluid, wall.coordinates, u)):
+                counts[name] = (semi.count_neighbor_pairs(a, b, u_d),
+                                oracle.neighbor_pair_count(xa, xb, R, dtype=np.float32))
+            assert all(g == o for g, o in counts.values()), counts
+            if coords == np.float32:
+                assert counts["fluid_fluid"][0] == 101034113
+    semi.close()
+
+
+@pytest.mark.timeout(900)
+def test_neighbor_sets_3d_bruteforce_definition(oracle):
+    """3-D sets against the O(N^2) definition itself: 21 296 fluid particles of the dam-break lattice
+    (dx = 0.045, exact ties at d = R) and their wall neighbours, Float32, lattice and perturbed."""
+    fluid, wall, _ = examples.dam_break_3d(0.045)
+    assert fluid.nparticles >= 20000
+    semi, ode = make_semi(fluid, wall)
+    R = float(np.float32(2) * fluid.smoothing_length)
+    for jitter in (False, True):
+        u = examples.perturbed_state(fluid)[0] if jitter else fluid.initial_condition.coordinates
+        u_ode = np.ascontiguousarray(u).reshape(-1)
+        gi, gj = semi.neighbor_pairs(fluid, fluid, u_ode)
+        oi, oj = oracle.neighbor_pairs(u, u, R, dtype=np.float32, grid=False)
+        assert len(gi) == len(oi) and np.array_equal(gi, oi) and np.array_equal(gj, oj)
+        if not jitter:
+            # ties: lattice pairs at exactly 3 dx are neighbours (d^2 <= R^2)
+            d2 = ((u[gi].astype(np.float32) - u[gj].astype(np.float32)) ** 2).sum(axis=1)
+            assert (np.abs(np.sqrt(d2) - R) < 1e-6).sum() > 1000
+        # the wall particles near the column only (the brute-force oracle is O(N_f N_w))
+        near = np.nonzero((wall.coordinates[:, 0] < 2.2))[0]
+        gi, gj = semi.neighbor_pairs(fluid, wall, u_ode)
+        oi, oj = oracle.neighbor_pairs(u, wall.coordinates[near], R, dtype=np.float32, grid=False)
+        assert len(gi) == len(oi) and np.array_equal(gi, oi) and np.array_equal(gj, near[oj])
+    semi.close()
+
+
+@pytest.mark.parametrize("eltype,variant", [(np.float32, 0), (np.float64, 0), (np.float32, 1)])
+def test_kick_summation_density_3d(oracle, eltype, variant):
+    """SummationDensity in 3-D (density_calculators.jl:26-50) on the dam-break geometry, dx = 0.1 and
+    Float32 at dx = 0.05 (16 000 fluid particles)."""
+    for dx in ((0.1, 0.05) if eltype == np.float32 and variant == 0 else (0.1,)):
+        fluid, wall, _ = examples.dam_break_3d(dx, eltype=eltype, density_calculator=tp.SummationDensity())
+        u, v = examples.perturbed_state(fluid)
+        assert v.shape[1] == 3
+        check_against_oracle(fluid, wall, u, v, interact_variant=variant)

@@ -25,7 +25,8 @@ EXPORTS = [
     "tpb_synchronize", "tpb_set_stream", "tpb_get_stats", "tpb_get_sound_speed", "tpb_host_register",
     "tpb_host_unregister", "tpb_set_profiling", "tpb_get_phase_times",
     "tpb_set_fluid_count", "tpb_set_fluid_mass",
-    "tpb_vec_axpby", "tpb_vec_rk2n_stage", "tpb_vec_fill", "tpb_vec_strided_max", "tpb_vec_wrms_norm",
+    "tpb_vec_axpby", "tpb_vec_rk2n_stage", "tpb_vec_fill", "tpb_vec_lincomb4", "tpb_vec_verlet_update",
+    "tpb_vec_div_fast", "tpb_vec_strided_max", "tpb_vec_wrms_norm",
     "tpb_peer_alloc", "tpb_peer_free", "tpb_peer_export", "tpb_peer_import", "tpb_peer_close",
     "tpb_halo_pack", "tpb_halo_install",
 ]
@@ -147,6 +148,9 @@ def load():
     L.tpb_vec_axpby.restype = i32; L.tpb_vec_axpby.argtypes = [p, i64, i32, d, p, d, p]
     L.tpb_vec_rk2n_stage.restype = i32; L.tpb_vec_rk2n_stage.argtypes = [p, i64, i32, d, d, d, p, p, p]
     L.tpb_vec_fill.restype = i32; L.tpb_vec_fill.argtypes = [p, i64, i32, d, p]
+    L.tpb_vec_lincomb4.restype = i32; L.tpb_vec_lincomb4.argtypes = [p, i64, i32, d, p, d, p, d, p, d, p, p]
+    L.tpb_vec_verlet_update.restype = i32; L.tpb_vec_verlet_update.argtypes = [p, i64, i32, i32, i32, d, p, p, p]
+    L.tpb_vec_div_fast.restype = i32; L.tpb_vec_div_fast.argtypes = [p, i64, i32, d, p, p]
     L.tpb_vec_strided_max.restype = i32
     L.tpb_vec_strided_max.argtypes = [p, i64, i32, i32, i32, p, C.POINTER(d)]
     L.tpb_vec_wrms_norm.restype = i32

@@ -1818,6 +1818,55 @@ int32_t tpb_vec_fill(tpb_semi_t semi, int64_t n, int32_t eltype, double value, v
     return TPB_OK;
 }
 
+int32_t tpb_vec_lincomb4(tpb_semi_t semi, int64_t n, int32_t eltype, double a0, const void *x0, double a1,
+                         const void *x1, double a2, const void *x2, double a3, const void *x3, void *y)
+{
+    Semi *s = (Semi *)semi;
+    int rc = vec_check(s, n, eltype);
+    if (rc || n == 0) return rc;
+    if (!y) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (eltype == TPB_F32)
+        LAUNCH(*s, k_vec_lincomb4<float>, vec_grid(n), 256, 0, n, a0, (const float *)x0, a1, (const float *)x1, a2,
+               (const float *)x2, a3, (const float *)x3, (float *)y);
+    else
+        LAUNCH(*s, k_vec_lincomb4<double>, vec_grid(n), 256, 0, n, a0, (const double *)x0, a1, (const double *)x1,
+               a2, (const double *)x2, a3, (const double *)x3, (double *)y);
+    CUDA_TRY(s, cudaGetLastError());
+    return TPB_OK;
+}
+
+int32_t tpb_vec_verlet_update(tpb_semi_t semi, int64_t n_particles, int32_t ndims, int32_t nvars, int32_t eltype,
+                              double dt, const void *kdu, const void *duprev, void *du)
+{
+    Semi *s = (Semi *)semi;
+    int rc = vec_check(s, n_particles, eltype);
+    if (rc || n_particles == 0) return rc;
+    if (!kdu || !duprev || !du || ndims < 1 || nvars < ndims || nvars > ndims + 1)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "invalid argument");
+    if (eltype == TPB_F32)
+        LAUNCH(*s, k_vec_verlet_update<float>, vec_grid(n_particles), 256, 0, n_particles, ndims, nvars, (float)dt,
+               (const float *)kdu, (const float *)duprev, (float *)du);
+    else
+        LAUNCH(*s, k_vec_verlet_update<double>, vec_grid(n_particles), 256, 0, n_particles, ndims, nvars, dt,
+               (const double *)kdu, (const double *)duprev, (double *)du);
+    CUDA_TRY(s, cudaGetLastError());
+    return TPB_OK;
+}
+
+int32_t tpb_vec_div_fast(tpb_semi_t semi, int64_t n, int32_t eltype, double x, const void *y, void *out)
+{
+    Semi *s = (Semi *)semi;
+    int rc = vec_check(s, n, eltype);
+    if (rc || n == 0) return rc;
+    if (!y || !out) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (eltype == TPB_F32)
+        LAUNCH(*s, k_div_fast<float>, cdiv(n, 256), 256, 0, n, (float)x, (const float *)y, (float *)out);
+    else
+        LAUNCH(*s, k_div_fast<double>, cdiv(n, 256), 256, 0, n, x, (const double *)y, (double *)out);
+    CUDA_TRY(s, cudaGetLastError());
+    return TPB_OK;
+}
+
 int32_t tpb_vec_strided_max(tpb_semi_t semi, int64_t count, int32_t eltype, int32_t stride, int32_t offset,
                             const void *x, double *out_host)
 {

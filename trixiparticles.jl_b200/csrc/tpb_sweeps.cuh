@@ -383,6 +383,15 @@ k_drift(int64_t n_total /* n_f * ND */, int nv, const T *__restrict__ v, CT *__r
     du[q] = (CT)v[a * nv + d];
 }
 
+// test hook behind tpb_vec_div_fast: out[i] = div_fast(x, y[i]) (test/examples/gpu.jl:30-78)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_div_fast(int64_t n, T x, const T *__restrict__ y, T *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = div_fast(x, y[i]);
+}
+
 // ------------------------------------------------------------------ neighbour pair dump
 // Test hook behind tpb_neighbor_pairs: appends (orig_i, orig_j) for every accepted pair.
 template <int ND, typename T, typename CT>

@@ -33,6 +33,46 @@ k_vec_rk2n_stage(int64_t n, double A, double B, double dt, const T *__restrict__
     }
 }
 
+// y = a0 x0 + a1 x1 + a2 x2 + a3 x3 (terms with a null pointer are skipped; any x may alias y): the
+// register updates of a low-storage 3S*+ Runge-Kutta stage (RDPK3SpFSAL35) in one pass
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_vec_lincomb4(int64_t n, double a0, const T *x0, double a1, const T *x1, double a2, const T *x2, double a3,
+               const T *x3, T *y)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double s = 0.0;
+        if (x0) s += a0 * (double)x0[i];
+        if (x1) s += a1 * (double)x1[i];
+        if (x2) s += a2 * (double)x2[i];
+        if (x3) s += a3 * (double)x3[i];
+        y[i] = (T)s;
+    }
+}
+
+// SymplecticPositionVerlet, velocity / density update of one WCSPH system
+// (ext/TrixiParticlesOrdinaryDiffEqSymplecticRKExt.jl:137-171): rows of NV entries per particle;
+// du[0:ND] = duprev + dt * kdu; with the density as last entry (NV == ND + 1):
+//   epsilon = -kdu[end] / du[end] * dt;  du[end] = duprev[end] * (2 - epsilon) / (2 + epsilon)
+// (du holds the half-step state on entry).  Arithmetic in T, as the reference's broadcast.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_vec_verlet_update(int64_t n_particles, int nd, int nv, T dt, const T *__restrict__ kdu,
+                    const T *__restrict__ duprev, T *__restrict__ du)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_particles; p += stride) {
+        const int64_t o = p * nv;
+        for (int d = 0; d < nd; ++d) du[o + d] = duprev[o + d] + dt * kdu[o + d];
+        if (nv > nd) {
+            const T density_prev = duprev[o + nd], density_half = du[o + nd];
+            const T epsilon = -kdu[o + nd] / density_half * dt;
+            du[o + nd] = density_prev * ((T)2 - epsilon) / ((T)2 + epsilon);
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_vec_fill(int64_t n, double value, T *__restrict__ x)

@@ -74,7 +74,7 @@ def hydrostatic_water_column_2d(fluid_particle_spacing=0.05, *, eltype=np.float3
 
 def dam_break_3d(fluid_particle_spacing=0.08, *, eltype=np.float32, coordinates_eltype=None,
                  sound_speed=None, fluid_size=(2.0, 1.0, 1.0), tank_size=None, adaptive_sound_speed=False,
-                 x_window=None, boundary_x_window=None):
+                 x_window=None, boundary_x_window=None, density_calculator=None):
     """examples/fluid/dam_break_3d.jl:13-66 (BASELINE configs 3/4 at smaller spacings).
 
     As SURVEY.md section 8(d) M3 prescribes, the headline runs use a static
@@ -97,11 +97,13 @@ def dam_break_3d(fluid_particle_spacing=0.08, *, eltype=np.float32, coordinates_
                            boundary_x_window=boundary_x_window)
     h = 1.5 * dx
     kernel = WendlandC2Kernel(3)
+    dc = density_calculator or ContinuityDensity()
     fluid = WeaklyCompressibleSPHSystem(
         tank.fluid, smoothing_kernel=kernel, smoothing_length=h,
-        density_calculator=ContinuityDensity(), state_equation=state_equation,
+        density_calculator=dc, state_equation=state_equation,
         viscosity=ArtificialViscosityMonaghan(alpha=0.02, beta=0.0),
-        density_diffusion=DensityDiffusionMolteniColagrossi(delta=0.1),
+        density_diffusion=(None if isinstance(dc, SummationDensity)
+                           else DensityDiffusionMolteniColagrossi(delta=0.1)),
         acceleration=(0.0, -gravity, 0.0))
     model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass,
                                         AdamiPressureExtrapolation(), kernel, h,

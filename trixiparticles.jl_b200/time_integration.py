@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import sys
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional
 
@@ -37,6 +38,79 @@ class CarpenterKennedy2N54:
          3134564353537 / 4481467310338, 2277821191437 / 14882151754819)
     c = (0.0, 1432997174477 / 9575080441755, 2526269341429 / 6820363962896,
          2006345519317 / 3224310063776, 2802321613138 / 2924317926251)
+
+
+def _rdpk3spfsal35_embedded_weights(c_stages, b_main):
+    """Embedded (second-order) weights of RDPK3SpFSAL35 over its five stages and the FSAL stage.
+
+    The scheme lives in OrdinaryDiffEqLowStorageRK.jl (third-party, not under /root/reference; no
+    network here).  The main method's coefficients below are verified: they reproduce the abscissae
+    c_i and satisfy all four third-order conditions to 1e-16 (tests/test_host_logic.py).  The
+    embedded weights could not be verified the same way -- the values on record violate
+    sum(bhat) = 1 and sum(bhat c) = 1/2 in the fourth digit -- so the weights used here are the
+    closest ones (least squares) that satisfy both second-order conditions exactly.  The step-size
+    sequence therefore follows the published controller on a second-order error estimate of the same
+    family, not bit for bit OrdinaryDiffEq's."""
+    recorded = np.array([1.046363371354093758897668305991705199e-01, 9.520431574956758809511173383346476348e-02,
+                         4.482446645568668405072421350300379357e-01, 2.449030295461310135957132640369862245e-01,
+                         7.962176910593929356839751650674380730e-02, 2.718753614680220546367613932962426040e-02])
+    c_all = np.append(np.asarray(c_stages, dtype=np.float64), 1.0)
+    M = np.stack([np.ones(6), c_all])
+    bhat = recorded - M.T @ np.linalg.solve(M @ M.T, M @ recorded - np.array([1.0, 0.5]))
+    return tuple(np.append(np.asarray(b_main, dtype=np.float64), 0.0) - bhat)   # error weights b - bhat
+
+
+@dataclass(frozen=True)
+class RDPK3SpFSAL35:
+    """Ranocha, Dalcin, Parsani, Ketcheson (2021): five-stage third-order 3S*+ low-storage scheme with
+    FSAL and an embedded second-order error estimate -- the integrator of the reference's shipped
+    examples (examples/fluid/dam_break_3d.jl:85, hydrostatic_water_column_2d.jl:86).  Per stage
+        tmp += delta_i u;  u = gamma1_i u + gamma2_i tmp + gamma3_i uprev + beta_i dt f(u)
+    Step-size control: PID controller (0.70, -0.23, 0.00) with the limiter 1 + atan(x - 1) and the
+    accept threshold 0.81, as OrdinaryDiffEq selects for this scheme."""
+    gamma1 = (0.0, 2.587771979725733308135192812685323706e-01, -1.324380360140723382965420909764953437e-01,
+              5.056033948190826045833606441415585735e-02, 5.670532000739313812633197158607642990e-01)
+    gamma2 = (1.0, 5.528354909301389892439698870483746541e-01, 6.731871608203061824849561782794643600e-01,
+              2.803103963297672407841316576323901761e-01, 5.521525447020610386070346724931300367e-01)
+    gamma3 = (0.0, 0.0, 0.0, 2.752563273304676380891217287572780582e-01, -8.950526174674033822276061734289327568e-01)
+    delta = (1.0, 3.407655879334525365094815965895763636e-01, 3.414382655003386206551709871126405331e-01,
+             7.229275366787987419692007421895451953e-01, 0.0)
+    beta = (2.300298624518076223899418286314123354e-01, 3.021434166948288809034402119555380003e-01,
+            8.025606185416310937583009085873554681e-01, 4.362158943603440930655148245148766471e-01,
+            1.129272530455059129782111662594436580e-01)
+    c = (0.0, 2.300298624518076223899418286314123354e-01, 4.050046072094990912268498160116125481e-01,
+         8.947822893693433545220710894560512805e-01, 7.235136928826589010272834603680114769e-01)
+    pid = (0.70, -0.23, 0.00)
+    order = 3
+    adaptive_order = 2
+
+    @classmethod
+    def butcher(cls):
+        """Effective Butcher tableau (A, b) of the low-storage recurrence."""
+        S = 5
+        up = np.zeros(S + 1); up[0] = 1.0
+        u, tmp = up.copy(), up.copy()
+        u[1] += cls.beta[0]
+        rows = [up.copy()]
+        for i in range(1, S):
+            rows.append(u.copy())
+            tmp = tmp + cls.delta[i] * u
+            u = cls.gamma1[i] * u + cls.gamma2[i] * tmp + cls.gamma3[i] * up
+            u[i + 1] += cls.beta[i]
+        return np.array([r[1:] for r in rows]), u[1:].copy()
+
+    @classmethod
+    def error_weights(cls):
+        A, b = cls.butcher()
+        return _rdpk3spfsal35_embedded_weights(A.sum(axis=1), b)
+
+
+@dataclass(frozen=True)
+class SymplecticPositionVerlet:
+    """DualSPHysics' symplectic position Verlet scheme as the reference defines it
+    (ext/TrixiParticlesOrdinaryDiffEqSymplecticRKExt.jl:89-171): drift half, kick half, kick at the
+    half step, then v = v_prev + dt dv except for an integrated density, which is advanced by
+    rho = rho_prev (2 - eps) / (2 + eps), eps = -(drho / rho_half) dt; drift half."""
 
 
 def calculate_dt(system: WeaklyCompressibleSPHSystem, cfl_number: float) -> float:
@@ -134,6 +208,64 @@ class _VecOps:
             return torch.zeros_like(x)
         return np.zeros_like(x)
 
+    def _eltype(self, x):
+        import torch
+        return _lib.F32 if x.dtype == torch.float32 else _lib.F64
+
+    def lincomb(self, y, *terms):
+        """y = sum_k a_k x_k for up to four (a, x) terms (an x may be y itself)."""
+        terms = [(float(a), x) for a, x in terms if x is not None]
+        assert 1 <= len(terms) <= 4
+        if not self.device:
+            acc = sum(a * x.astype(np.float64) for a, x in terms)
+            y[:] = acc.astype(y.dtype)
+            return
+        terms += [(0.0, None)] * (4 - len(terms))
+        self.semi._bind_stream()
+        args = []
+        for a, x in terms:
+            args += [a, C.c_void_p(x.data_ptr()) if x is not None else None]
+        _lib.check(self.semi._handle, _lib.load().tpb_vec_lincomb4(
+            self.semi._handle, y.numel(), self._eltype(y), *args, C.c_void_p(y.data_ptr())))
+
+    def wrms_sumsq(self, err, a, b, abstol, reltol):
+        """sum_i (err_i / (abstol + reltol max(|a_i|, |b_i|)))^2 and the number of entries."""
+        if not self.device:
+            e = err.astype(np.float64) / (abstol + reltol * np.maximum(np.abs(a), np.abs(b)).astype(np.float64))
+            return float((e * e).sum()), err.size
+        n = err.numel()
+        if n == 0:
+            return 0.0, 0
+        out = C.c_double(0.0)
+        self.semi._bind_stream()
+        _lib.check(self.semi._handle, _lib.load().tpb_vec_wrms_norm(
+            self.semi._handle, n, self._eltype(err), C.c_void_p(err.data_ptr()), C.c_void_p(a.data_ptr()),
+            C.c_void_p(b.data_ptr()), float(abstol), float(reltol), C.byref(out)))
+        return out.value ** 2 * n, n
+
+    def verlet_update(self, system, semi, dt, kdu, duprev, du):
+        """update_velocity! / update_density! of one system on its rows of the v vectors."""
+        a, b = semi.ranges_v[semi.system_index(system)]
+        if b == a:
+            return
+        nd, nv = system.ndims, system.v_nvariables
+        n = (b - a) // nv
+        if not self.device:
+            k, p, d = (x[a:b].reshape(n, nv) for x in (kdu, duprev, du))
+            t = d.dtype.type
+            if nv > nd:
+                eps = -k[:, nd] / d[:, nd] * t(dt)
+                rho = p[:, nd] * (t(2) - eps) / (t(2) + eps)
+            d[:, :nd] = p[:, :nd] + t(dt) * k[:, :nd]
+            if nv > nd:
+                d[:, nd] = rho
+            return
+        self.semi._bind_stream()
+        off = a * du.element_size()
+        _lib.check(self.semi._handle, _lib.load().tpb_vec_verlet_update(
+            self.semi._handle, n, nd, nv, self._eltype(du), float(dt), C.c_void_p(kdu.data_ptr() + off),
+            C.c_void_p(duprev.data_ptr() + off), C.c_void_p(du.data_ptr() + off)))
+
     def rk2n_stage(self, A, B, dt, rhs, tmp, state):
         if not self.device:
             if A == 0.0:
@@ -151,8 +283,9 @@ class _VecOps:
             C.c_void_p(rhs.data_ptr()), C.c_void_p(tmp.data_ptr()), C.c_void_p(state.data_ptr())))
 
 
-def solve(ode, alg: CarpenterKennedy2N54, *, dt: Optional[float] = None, save_everystep: bool = False,
-          callback=(), maxiters: int = 10 ** 7, cuda_graph: bool = False) -> Solution:
+def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
+          callback=(), maxiters: int = 10 ** 7, cuda_graph: bool = False, abstol: float = 1e-6,
+          reltol: float = 1e-3, dtmax: Optional[float] = None) -> Solution:
     """`solve(ode, CarpenterKennedy2N54(); dt, callback)` for the `DynamicalODEProblem` returned by
     `semidiscretize`: per stage dv = kick!(v, u), du = drift!(v, u), then the 2N-storage update of
     both partitions.  Fixed step from `dt` or a `StepsizeCallback`; `PostprocessCallback`s add
@@ -165,6 +298,11 @@ def solve(ode, alg: CarpenterKennedy2N54, *, dt: Optional[float] = None, save_ev
     if callback is None:
         callback = ()
     callbacks = list(callback) if isinstance(callback, (list, tuple)) else [callback]
+    if isinstance(alg, RDPK3SpFSAL35):
+        return _solve_rdpk3(ode, alg, callbacks, dt=dt, abstol=abstol, reltol=reltol, dtmax=dtmax,
+                            maxiters=maxiters, save_everystep=save_everystep)
+    if isinstance(alg, SymplecticPositionVerlet):
+        return _solve_verlet(ode, callbacks, dt=dt, maxiters=maxiters, save_everystep=save_everystep)
     stepsize = next((c for c in callbacks if isinstance(c, StepsizeCallback)), None)
     posts = [c for c in callbacks if isinstance(c, PostprocessCallback)]
     if stepsize is not None:
@@ -233,3 +371,171 @@ def solve(ode, alg: CarpenterKennedy2N54, *, dt: Optional[float] = None, save_ev
         semi.synchronize()   # surfaces a deferred out-of-bounds error of an asynchronous kick
     return Solution(t=t, v=v, u=u, nsteps=nsteps, nf=nf, dts=dts,
                     retcode="Success" if t >= t_end else "MaxIters")
+
+
+# ------------------------------------------------------------------ adaptive low-storage scheme
+def _rhs(ode, dv, du, v, u, t):
+    ode.f1(dv, v, u, ode.p, t)
+    ode.f2(du, v, u, ode.p, t)
+
+
+def _solve_rdpk3(ode, alg: RDPK3SpFSAL35, callbacks, *, dt, abstol, reltol, dtmax, maxiters, save_everystep):
+    """`solve(ode, RDPK3SpFSAL35(); abstol, reltol, dtmax)` on the (v, u) partition of the
+    `DynamicalODEProblem`: OrdinaryDiffEq's 3S*+ FSAL step (`LowStorageRK3SpFSAL`), its automatic
+    initial step (Hairer & Wanner) and its PID step-size controller; the error norm is the RMS of
+    err / (abstol + reltol max(|u_prev|, |u|)) over both partitions (`ODE_DEFAULT_NORM`)."""
+    semi = ode.p.semi
+    ops = _VecOps(semi)
+    posts = [c for c in callbacks if isinstance(c, PostprocessCallback)]
+    t, t_end = float(ode.tspan[0]), float(ode.tspan[1])
+    dtmax = float(dtmax) if dtmax is not None else t_end - t
+    v = ode.v0.clone() if ops.device else ode.v0.copy()
+    u = ode.u0.clone() if ops.device else ode.u0.copy()
+    Z = ops.zeros_like
+    kv, ku, k0v, k0u = Z(v), Z(u), Z(v), Z(u)           # stage rhs / FSAL rhs
+    tv, tu, pv, pu, ev, eu = Z(v), Z(u), Z(v), Z(u), Z(v), Z(u)   # tmp register, uprev, error estimate
+    ew = alg.error_weights()
+    nf = 0
+
+    def norm(ev_, eu_, av, au, bv, bu):
+        s1, n1 = ops.wrms_sumsq(ev_, av, bv, abstol, reltol)
+        s2, n2 = ops.wrms_sumsq(eu_, au, bu, abstol, reltol)
+        return math.sqrt((s1 + s2) / max(n1 + n2, 1))
+
+    _rhs(ode, k0v, k0u, v, u, t)
+    nf += 1
+    if dt is None or not dt > 0:
+        # ode_determine_initdt (Hairer, Norsett, Wanner I, II.4): d0 = |u0|, d1 = |f0|, an explicit Euler
+        # probe for the second derivative
+        zv, zu = Z(v), Z(u)
+        d0 = norm(v, u, v, u, v, u)
+        d1 = norm(k0v, k0u, v, u, v, u)
+        dt0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+        dt0 = min(dt0, dtmax)
+        ops.lincomb(tv, (1.0, v), (dt0, k0v))
+        ops.lincomb(tu, (1.0, u), (dt0, k0u))
+        _rhs(ode, kv, ku, tv, tu, t + dt0)
+        nf += 1
+        ops.lincomb(zv, (1.0, kv), (-1.0, k0v))
+        ops.lincomb(zu, (1.0, ku), (-1.0, k0u))
+        d2 = norm(zv, zu, v, u, v, u) / dt0
+        dmax = max(d1, d2)
+        dt1 = max(1e-6, dt0 * 1e-3) if dmax <= 1e-15 else 10.0 ** (-(2.0 + math.log10(dmax)) / (alg.order + 1))
+        dt = min(100 * dt0, dt1, dtmax)
+        del zv, zu
+    dt = min(float(dt), dtmax)
+    err_hist = [1.0, 1.0, 1.0]
+    kexp = min(alg.order, alg.adaptive_order) + 1
+    nsteps = nrejected = 0
+    dts: List[float] = []
+    next_stop = [t + p.dt for p in posts]
+    for p in posts:
+        p(t, v, u, semi)
+    retcode = "Success"
+    while t < t_end:
+        if nsteps >= maxiters:
+            retcode = "MaxIters"
+            break
+        stop = min([t_end] + next_stop)
+        step = min(dt, stop - t)
+        ops.lincomb(pv, (1.0, v))
+        ops.lincomb(pu, (1.0, u))
+        ops.lincomb(tv, (1.0, v))
+        ops.lincomb(tu, (1.0, u))
+        ops.lincomb(v, (1.0, tv), (alg.beta[0] * step, k0v))
+        ops.lincomb(u, (1.0, tu), (alg.beta[0] * step, k0u))
+        ops.lincomb(ev, (ew[0] * step, k0v))
+        ops.lincomb(eu, (ew[0] * step, k0u))
+        for i in range(1, 5):
+            _rhs(ode, kv, ku, v, u, t + alg.c[i] * step)
+            ops.lincomb(tv, (1.0, tv), (alg.delta[i], v))
+            ops.lincomb(tu, (1.0, tu), (alg.delta[i], u))
+            ops.lincomb(v, (alg.gamma1[i], v), (alg.gamma2[i], tv), (alg.gamma3[i], pv), (alg.beta[i] * step, kv))
+            ops.lincomb(u, (alg.gamma1[i], u), (alg.gamma2[i], tu), (alg.gamma3[i], pu), (alg.beta[i] * step, ku))
+            ops.lincomb(ev, (1.0, ev), (ew[i] * step, kv))
+            ops.lincomb(eu, (1.0, eu), (ew[i] * step, ku))
+        _rhs(ode, kv, ku, v, u, t + step)       # FSAL evaluation
+        nf += 5
+        ops.lincomb(ev, (1.0, ev), (ew[5] * step, kv))
+        ops.lincomb(eu, (1.0, eu), (ew[5] * step, ku))
+        est = norm(ev, eu, pv, pu, v, u)
+        # PIDController (Soederlind; OrdinaryDiffEqCore controllers)
+        est = max(est, 1.0 / sys.float_info.max) if est == est else float("inf")
+        err_hist = [1.0 / est, err_hist[0], err_hist[1]]
+        factor = (err_hist[0] ** (alg.pid[0] / kexp) * err_hist[1] ** (alg.pid[1] / kexp)
+                  * err_hist[2] ** (alg.pid[2] / kexp))
+        factor = 1.0 + math.atan(factor - 1.0)
+        if factor >= 0.81:
+            t = stop if step != dt else t + step
+            nsteps += 1
+            k0v, kv = kv, k0v
+            k0u, ku = ku, k0u
+            if save_everystep:
+                dts.append(step)
+            if step == dt:                       # a step shortened for an output time keeps the controller's dt
+                dt = min(dt * factor, dtmax)
+            for i, p in enumerate(posts):
+                if t >= next_stop[i] - 1e-12 * max(1.0, abs(t)):
+                    p(t, v, u, semi)
+                    next_stop[i] = len(p.times) * p.dt + float(ode.tspan[0])
+        else:
+            nrejected += 1
+            ops.lincomb(v, (1.0, pv))
+            ops.lincomb(u, (1.0, pu))
+            dt = step * factor
+            if not dt > 1e-14 * max(1.0, abs(t)):
+                retcode = "DtLessThanMin"
+                break
+    if ops.device:
+        semi.synchronize()
+    sol = Solution(t=t, v=v, u=u, nsteps=nsteps, nf=nf, dts=dts, retcode=retcode)
+    sol.nrejected = nrejected
+    return sol
+
+
+def _solve_verlet(ode, callbacks, *, dt, maxiters, save_everystep):
+    """`solve(ode, SymplecticPositionVerlet(); dt, callback=StepsizeCallback(cfl))`."""
+    semi = ode.p.semi
+    ops = _VecOps(semi)
+    stepsize = next((c for c in callbacks if isinstance(c, StepsizeCallback)), None)
+    posts = [c for c in callbacks if isinstance(c, PostprocessCallback)]
+    if stepsize is not None:
+        dt = stepsize.dt(semi)
+    if dt is None or not dt > 0:
+        raise ValueError("a positive `dt` or a `StepsizeCallback` is required (fixed-step scheme)")
+    v = ode.v0.clone() if ops.device else ode.v0.copy()
+    u = ode.u0.clone() if ops.device else ode.u0.copy()
+    Z = ops.zeros_like
+    pv, pu, kdu, ku = Z(v), Z(u), Z(v), Z(u)
+    t, t_end = float(ode.tspan[0]), float(ode.tspan[1])
+    next_stop = [t + p.dt for p in posts]
+    for p in posts:
+        p(t, v, u, semi)
+    nsteps = nf = 0
+    dts: List[float] = []
+    while t < t_end and nsteps < maxiters:
+        stop = min([t_end] + next_stop)
+        step = dt if stop - t > dt * (1 + 1e-10) else stop - t
+        ops.lincomb(pv, (1.0, v))
+        ops.lincomb(pu, (1.0, u))
+        ode.f2(ku, pv, pu, ode.p, t)                       # position half step
+        ops.lincomb(u, (1.0, pu), (0.5 * step, ku))
+        ode.f1(kdu, pv, pu, ode.p, t)                      # velocity half step
+        ops.lincomb(v, (1.0, pv), (0.5 * step, kdu))
+        ode.f1(kdu, v, u, ode.p, t + 0.5 * step)           # full kick from the half-step state
+        for system in semi.systems:
+            ops.verlet_update(system, semi, step, kdu, pv, v)
+        ode.f2(ku, v, u, ode.p, t + step)                  # second position half step
+        ops.lincomb(u, (1.0, u), (0.5 * step, ku))
+        nf += 2
+        t = stop if step != dt else t + step
+        nsteps += 1
+        if save_everystep:
+            dts.append(step)
+        for i, p in enumerate(posts):
+            if t >= next_stop[i] - 1e-12 * max(1.0, abs(t)):
+                p(t, v, u, semi)
+                next_stop[i] = len(p.times) * p.dt + float(ode.tspan[0])
+    if ops.device:
+        semi.synchronize()
+    return Solution(t=t, v=v, u=u, nsteps=nsteps, nf=nf, dts=dts, retcode="Success" if t >= t_end else "MaxIters")
