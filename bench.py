@@ -81,7 +81,7 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
-def make_workload(name, eltype=None, coords=None, shuffle=False, adaptive=False):
+def make_workload(name, eltype=None, coords=None, shuffle=False, adaptive=False, summation=False):
     from trixiparticles.jl_b200 import examples
     ex, arg = WORKLOADS[name]
     dt = {None: None, "f32": np.float32, "f64": np.float64}
@@ -93,6 +93,9 @@ def make_workload(name, eltype=None, coords=None, shuffle=False, adaptive=False)
     if ex == "dam_break_3d":
         if adaptive:
             kw["adaptive_sound_speed"] = True
+        if summation:
+            import trixiparticles.jl_b200 as tp_
+            kw["density_calculator"] = tp_.SummationDensity()
         fluid, wall, _ = examples.dam_break_3d(arg, **kw)
     else:
         fluid, wall, _ = examples.dam_break_2d(arg, **kw)
@@ -105,7 +108,8 @@ def make_workload(name, eltype=None, coords=None, shuffle=False, adaptive=False)
             setattr(ic, name_, np.ascontiguousarray(getattr(ic, name_)[perm]))
         fluid.mass = np.ascontiguousarray(fluid.mass[perm])
     u = np.ascontiguousarray(ic.coordinates, dtype=fluid.coordinates_eltype)
-    v = np.ascontiguousarray(np.concatenate([ic.velocity, ic.density[:, None]], axis=1), dtype=fluid.eltype)
+    cols = [ic.velocity] if summation else [ic.velocity, ic.density[:, None]]
+    v = np.ascontiguousarray(np.concatenate(cols, axis=1), dtype=fluid.eltype)
     return fluid, wall, u, v
 
 
@@ -237,7 +241,7 @@ def run_single(args):
     _lib.load()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    fluid, wall, u, v = make_workload(args.workload, args.eltype, args.coords, args.shuffle)
+    fluid, wall, u, v = make_workload(args.workload, args.eltype, args.coords, args.shuffle, summation=args.summation)
     if args.no_slip:
         # no-slip wall (`viscosity_wall = viscosity_fluid`) on a synthetic velocity field; not the headline
         wall.boundary_model.viscosity = fluid.viscosity
@@ -420,6 +424,8 @@ def run_single(args):
         variants["moving_fluid_free_slip_wall"] = run_variant(tp, torch, args, "f32", "f32", moving=True)
         variants["moving_fluid_no_slip_wall"] = run_variant(tp, torch, args, "f32", "f32", moving=True,
                                                             no_slip=True)
+        # SummationDensity (density_calculators.jl:26-50): one more tile sweep (W only) before interact!
+        variants["summation_density"] = run_variant(tp, torch, args, "f32", "f32", summation=True)
         if args.workload == DEFAULT_WORKLOAD:
             # BASELINE config 4 on one GPU: the 10 M lattice (north_star's size) and the per-GPU size of
             # the weak-scaling run of `--gpus N` (12.5 M: the denominator of its efficiency)
@@ -460,10 +466,11 @@ def run_single(args):
 
 
 def run_variant(tp, torch, args, eltype, coords, steps=10, adaptive=False, no_slip=False, moving=False,
-                workload=None):
+                workload=None, summation=False):
     """Device-resident kick!+drift! of the same workload in another precision set-up (or of
     another lattice size: `workload`)."""
-    fluid, wall, u, v = make_workload(workload or args.workload, eltype, coords, adaptive=adaptive)
+    fluid, wall, u, v = make_workload(workload or args.workload, eltype, coords, adaptive=adaptive,
+                                      summation=summation)
     if no_slip:
         wall.boundary_model.viscosity = fluid.viscosity
     if moving:
@@ -558,6 +565,7 @@ def main():
     ap.add_argument("--evolve", type=int, default=0, help="time steps to run before measuring (evolved state)")
     ap.add_argument("--per-gpu", type=float, default=12.5e6, help="N > 1: fluid particles per GPU of the "
                     "weak-scaling headline (BASELINE config 4: 12.5 M per GPU = 100 M on 8)")
+    ap.add_argument("--summation", action="store_true", help="SummationDensity instead of ContinuityDensity (with --quick)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning runs)")
     ap.add_argument("--e2e-only", action="store_true", help="host-pointer (e2e) timing only (tuning runs)")
     args = ap.parse_args()

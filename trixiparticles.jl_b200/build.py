@@ -9,7 +9,6 @@ from __future__ import annotations
 
 import os
 import subprocess
-import tempfile
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -38,39 +37,64 @@ def is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def _source_stamp() -> str:
+    import hashlib
+    h = hashlib.sha1()
+    for src in sources():
+        with open(src, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def build(force: bool = False, verbose: bool = False, out: str = SO, unit_flags=None) -> str:
+    """Compile the translation units (objects cached under build/obj by source hash + flags, so a
+    tuning variant that only adds -D flags to one unit recompiles that unit alone) and link them.
+    `unit_flags`: {unit tag: [extra nvcc flags]} for variant builds (tools/build_variant.py)."""
+    if not force and out == SO and not unit_flags and not is_stale():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("TPB_NVCC_EXTRA", "").split()
     src = os.path.join(CSRC, "tpb200.cu")
-    with tempfile.TemporaryDirectory(prefix="tpb200_build_") as tmp:
+    cache = os.path.join(os.path.dirname(HERE), "build", "obj")
+    os.makedirs(cache, exist_ok=True)
+    stamp = _source_stamp()
+    unit_flags = unit_flags or {}
 
-        def compile_unit(unit):
-            name = "main" if unit is None else unit[0]
-            obj = os.path.join(tmp, f"tpb200_{name}.o")
-            cmd = [nvcc, *NVCC_FLAGS, *extra]
-            if unit is not None:
-                tag, nd, t, ct = unit
-                cmd += [f"-DTPB_TU_TAG={tag}", f"-DTPB_TU_ND={nd}", f"-DTPB_TU_T={t}", f"-DTPB_TU_CT={ct}"]
-            if verbose:
-                cmd += ["-Xptxas", "-v"]
-            cmd += ["-c", "-o", obj, src]
-            res = subprocess.run(cmd, capture_output=True, text=True)
-            if res.returncode != 0:
-                raise RuntimeError(f"nvcc failed ({name}):\n" + res.stdout + res.stderr)
-            return obj, res.stderr
-
-        with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as pool:
-            results = list(pool.map(compile_unit, UNITS))
+    def compile_unit(unit):
+        import hashlib
+        name = "main" if unit is None else unit[0]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *unit_flags.get(name, [])]
+        if unit is not None:
+            tag, nd, t, ct = unit
+            cmd += [f"-DTPB_TU_TAG={tag}", f"-DTPB_TU_ND={nd}", f"-DTPB_TU_T={t}", f"-DTPB_TU_CT={ct}"]
         if verbose:
-            for _, log in results:
-                print(log)
-        link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + [o for o, _ in results]
-        res = subprocess.run(link, capture_output=True, text=True)
+            cmd += ["-Xptxas", "-v"]
+        key = hashlib.sha1((stamp + " ".join(cmd)).encode()).hexdigest()[:16]
+        obj = os.path.join(cache, f"tpb200_{name}_{key}.o")
+        if os.path.exists(obj) and not verbose and not (force and not unit_flags):
+            return obj, ""
+        tmp_obj = obj + f".{os.getpid()}.tmp"
+        res = subprocess.run(cmd + ["-c", "-o", tmp_obj, src], capture_output=True, text=True)
         if res.returncode != 0:
-            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
-    return SO
+            raise RuntimeError(f"nvcc failed ({name}):\n" + res.stdout + res.stderr)
+        os.replace(tmp_obj, obj)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_unit, UNITS))
+    if verbose:
+        for _, log in results:
+            print(log)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + [o for o, _ in results]
+    res = subprocess.run(link, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    # keep the cache small: drop objects of other source states
+    for f in os.listdir(cache):
+        path = os.path.join(cache, f)
+        if f.endswith(".o") and path not in {o for o, _ in results} and os.path.getmtime(path) < os.path.getmtime(out) - 6 * 3600:
+            os.unlink(path)
+    return out
 
 
 if __name__ == "__main__":

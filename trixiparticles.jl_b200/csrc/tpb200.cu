@@ -568,6 +568,23 @@ struct Ops {
                                  const EosConst<T> &eos)
     {
         int n = (int)s.n_act;
+        if (use_tiles(s) && !getenv("TPB_SUMMATION_PP")) {
+            // the tile sweep of interact! with a W-only body (the fluid's tile table is ready)
+            const int list_len = s.tiles.list(KS);
+            const int cap = tile_capacity<T, CT>(s.tiles.smem_budget, list_len, KS);
+            const size_t smem = tile_smem_bytes<T, CT>(cap, list_len, KS);
+            if (!(s.smem_opt_in & 4)) {
+                if (set_smem(s, k_summation_tiles<KS, ND, T, CT, KERNEL>, 227 * 1024)) return;
+                s.smem_opt_in |= 4;
+            }
+            LAUNCH(s, (k_summation_tiles<KS, ND, T, CT, KERNEL>), s.tiles.max_ftiles, KS * TILE_TB, smem, g,
+                   s.tiles.d_frow_tile_start + s.tiles.nrows, s.tiles.d_ftile_desc, s.tiles.d_ftile_ext,
+                   s.tiles.d_ftile_rng, s.d_fcell_start, (const V4<CT> *)s.d_A, s.d_perm_f,
+                   (int)(s.n_w > 0 && s.interaction[0][1]), s.d_wcell_start, (const V4<CT> *)s.d_Aw, s.d_perm_w,
+                   pc.kern, pc.radius2, eos, (V4<T> *)s.d_B, (T *)s.d_P, cap, list_len,
+                   (const V4<float> *)s.d_Ff, (const V4<float> *)s.d_Fw);
+            return;
+        }
         LAUNCH(s, (k_summation_density<ND, T, CT, KERNEL>), cdiv(n, 128), 128, 0, n, g,
                s.d_fcell_start, (const V4<CT> *)s.d_A, (int)(s.n_w > 0), s.d_wcell_start,
                (const V4<CT> *)s.d_Aw, s.interaction[0][1], pc.kern, pc.radius2, eos,

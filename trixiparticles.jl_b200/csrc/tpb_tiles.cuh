@@ -42,6 +42,9 @@
 #ifndef TPB_SPLIT
 #define TPB_SPLIT 3  // threads per target particle in the Float32 sweeps
 #endif
+#ifndef TPB_INTERLEAVE
+#define TPB_INTERLEAVE 1  // 1: the KS threads of a target take every KS-th candidate; 0: every KS-th group of four
+#endif
 
 namespace tpb {
 
@@ -297,9 +300,9 @@ __host__ __device__ constexpr size_t tile_record_bytes()
 template <typename T, typename CT>
 inline size_t tile_smem_bytes(int cap, int list_len, int ks = 1)
 {
-    // + 64: the last partial group of a candidate window reads up to three records past it
+    // + 256: the last partial group of a candidate window reads up to 3 * KS records past it
     return TILE_HDR_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short) +
-           (size_t)cap * tile_record_bytes<T, CT>() + 64;
+           (size_t)cap * tile_record_bytes<T, CT>() + 256;
 }
 
 // Load the tile descriptor of this block into hdr (thread 0).
@@ -635,22 +638,27 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
             const int base = hdr->seg_base[si];
             const int t0 = base + j;      // tile index of the first candidate
             const int t1 = base + j1;     // one past the last
-            // groups of four candidates counted from the lane's own first candidate
-            int t = t0 + 4 * kg;
-            constexpr int STEP = 4 * KS;
+            // The KS threads of a target share its candidates.  TPB_INTERLEAVE: thread kg takes the
+            // candidates kg, kg + KS, ... counted from the lane's own first candidate, so the accepted
+            // pairs -- concentrated in the middle of every row -- are dealt out evenly and the three
+            // lists of a target (and with them the lanes of a warp in phase 2) end up equally long;
+            // otherwise groups of four consecutive candidates are dealt out.
+            constexpr int CS = TPB_INTERLEAVE ? KS : 1;   // distance between the candidates of one group
+            constexpr int STEP = 4 * KS;                  // distance between two groups of one thread
+            int t = t0 + (TPB_INTERLEAVE ? kg : 4 * kg);
             while (true) {
                 // phase 1: filter candidates into the private list
-                while (t + STEP + 4 <= t1 && room(8)) {
+                while (t + STEP + 3 * CS < t1 && room(8)) {
                     FRec xc[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) xc[u] = tFilt[t + u];
+                    for (int u = 0; u < 4; ++u) xc[u] = tFilt[t + u * CS];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) xc[4 + u] = tFilt[t + STEP + u];
+                    for (int u = 0; u < 4; ++u) xc[4 + u] = tFilt[t + STEP + u * CS];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) lpa = list_append<ESTEP>(lpa, (uint32_t)(t + u), pass(xc[u]));
+                    for (int u = 0; u < 4; ++u) lpa = list_append<ESTEP>(lpa, (uint32_t)(t + u * CS), pass(xc[u]));
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + STEP + u), pass(xc[4 + u]));
+                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + STEP + u * CS), pass(xc[4 + u]));
                     t += 2 * STEP;
                 }
                 while (t < t1 && room(4)) {
@@ -658,10 +666,10 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
                     // neighbours of other lanes or padding: read, never appended)
                     FRec xc[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) xc[u] = tFilt[t + u];
+                    for (int u = 0; u < 4; ++u) xc[u] = tFilt[t + u * CS];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + u), t + u < t1 && pass(xc[u]));
+                        lpa = list_append<ESTEP>(lpa, (uint32_t)(t + u * CS), t + u * CS < t1 && pass(xc[u]));
                     t += STEP;
                 }
                 if (!__any_sync(0xffffffffu, t < t1)) break;
@@ -1104,6 +1112,72 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
     }
 }
 
+// ------------------------------------------------------------------ summation density (variant 2)
+// summation_density! (general/density_calculators.jl:26-50): rho_a = sum_b m_b W(r_ab) over the fluid
+// itself and the wall, then the equation of state.  The same tile sweep as interact! with a W-only
+// body: only the position / mass records are staged (the permutation rides in the second slot).
+template <int KS, int ND, typename T, typename CT, int KERNEL>
+__global__ void __launch_bounds__(KS * TILE_TB, 2)
+k_summation_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
+                  const int4 *__restrict__ tile_ext, const int2 *__restrict__ tile_rng,
+                  const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A, const int *__restrict__ perm_f,
+                  int has_wall, const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw,
+                  const int *__restrict__ perm_w, KernelConst<T> kern, T radius2, EosConst<T> eos,
+                  V4<T> *__restrict__ B, T *__restrict__ P, int cap, int list_len,
+                  const V4<float> *__restrict__ Ff, const V4<float> *__restrict__ Fw)
+{
+    extern __shared__ __align__(16) unsigned char tile_smem_raw[];
+    const int tile = blockIdx.x;
+    if (tile >= *n_tiles) return;
+    TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
+    const int2 *rng = tile_rng + (int64_t)tile * 18;
+    const NbSet<T, CT, int, false> nb_f{fcell_start, A, perm_f, nullptr, Ff};
+    const int4 desc = tile_desc[tile];
+    const int4 ext = tile_ext[tile];
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
+            tile_locate(sm.hdr, g.n[1], desc, ext);
+            mbar_init(sm.bar, 1);
+        }
+        __syncwarp();
+        tile_stage<ND, T, CT>(sm, nb_f, rng, ext.x, ext.y, desc.z % g.n[1], desc.z / g.n[1], g.sx, g.n[0], g.n[1]);
+    }
+    const int s = desc.x + threadIdx.x % TILE_TB;
+    const bool valid = s < desc.y;
+    V4<CT> xi = {};
+    int cx = ext.x, cy, cz;
+    if (valid) {
+        xi = A[s];
+        cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    T rho[1] = {(T)0};
+    auto body = [&](const V4<CT> &xj, const int &, T) {
+        T pd[3];
+        const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+        if constexpr (std::is_same<T, float>::value) {
+            // exact square root: the equation of state amplifies a density error by gamma rho0 / (rho - rho0)
+            const bool ok = d2 <= radius2;
+            const float dist = sqrt_rn(ok ? d2 : 0.0f);
+            rho[0] = fmaf(ok ? (float)xj.w : 0.0f, kernel_safe<KERNEL, float>(kern, dist), rho[0]);
+        } else {
+            if (d2 <= radius2) rho[0] += (T)xj.w * kernel_safe<KERNEL, T>(kern, sqrt_rn(d2));
+        }
+    };
+    tile_sweep_staged<KS, ND, T, CT>(sm, g, nb_f, valid, cx, xi, radius2, parity, body);
+    if (has_wall && ext.w > 0) {
+        const NbSet<T, CT, int, false> nb_w{wcell_start, Aw, perm_w, nullptr, Fw};
+        tile_sweep<KS, ND, T, CT>(sm, g, nb_w, rng + 9, valid, cx, xi, radius2, parity, body);
+    }
+    tile_reduce<KS, 1>(sm, rho);
+    if (!valid || threadIdx.x >= TILE_TB) return;
+    V4<T> b = B[s];
+    b.w = rho[0];
+    B[s] = b;
+    P[s] = eos_pressure(eos, rho[0]);
+}
+
 // ------------------------------------------------------------------ neighbour pair dump
 // Test hook behind tpb_neighbor_pairs (variant 2): the same tile sweep, filter and window
 // clipping as interact!, with a body that records (orig_i, orig_j) of every pair accepted by
@@ -1256,7 +1330,7 @@ inline void tiles_free(TileState &t)
 template <typename T, typename CT>
 inline int tile_capacity(int smem_budget, int list_len, int ks = 1)
 {
-    const size_t fixed = TILE_HDR_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short) + 64;
+    const size_t fixed = TILE_HDR_BYTES + (size_t)list_len * ks * TILE_TB * sizeof(unsigned short) + 256;
     const size_t rec = tile_record_bytes<T, CT>();
     int cap = (size_t)smem_budget > fixed ? (int)(((size_t)smem_budget - fixed) / rec) : 0;
     cap &= ~3;
