@@ -74,6 +74,12 @@ struct Semi {
     int *d_key = nullptr, *d_slot = nullptr, *d_tmp_perm = nullptr, *d_perm_f = nullptr;
     int *d_count = nullptr, *d_fcell_start = nullptr, *d_wcell_start = nullptr;
     int *d_block_sums = nullptr, *d_flags = nullptr;
+    // one-pass cell scan + tile table (k_scan_cells_tiles): look-back status words, block tickets
+    unsigned long long *d_scan_status = nullptr;
+    unsigned long long *d_scan_ticket = nullptr;
+    int scan_blocks = 0, scan_rows_per_block = 0;  // 0 blocks: grid shape not supported, three-kernel scan instead
+    bool count_clean = false;      // the cell histogram is all zero (left so by k_scan_cells_tiles)
+    bool wall_prep_done = false;   // this kick's rebuild launch has sorted the wall tiles into empty / active
     int *h_flags = nullptr;  // pinned
     void *d_A = nullptr, *d_B = nullptr, *d_P = nullptr;
     void *d_Aw = nullptr, *d_Ww = nullptr, *d_volw = nullptr;
@@ -304,6 +310,7 @@ struct Ops {
     {
         GridConst<CT> g = make_grid_const<CT>(s);
         CUDA_TRY(&s, cudaMemsetAsync(s.d_count, 0, sizeof(int) * (size_t)s.ncells, s.stream));
+        s.count_clean = false;
         if (n > 0)
             LAUNCH(s, (k_cell_count<ND, CT>), cdiv(n, 256), 256, 0, d_coords, n, n_targets, g, s.d_key,
                    s.d_slot, s.d_count, s.d_flags);
@@ -316,10 +323,72 @@ struct Ops {
     }
 
     // ---- NHS rebuild of the fluid + EOS (update_nhs!, update_pressure!)
+    // wall tiles: empty / active (k_wall_tile_prep); the no-slip records ride along when the Adami sweep
+    // carries the wall velocity (launch_adami)
+    static bool adami_fused_noslip(const Semi &s)
+    {
+        constexpr bool SMALL = KS > 1 && sizeof(T) == 4;
+        const int list_len = SMALL ? s.tiles.adami_list_len : s.tiles.list(KS);
+        return s.wp.has_viscosity && list_len >= ADAMI_NOSLIP_RED * (int)sizeof(T) / 2;
+    }
+    static WallPrepArgs<T, CT> wall_prep_args(const Semi &s)
+    {
+        const EosConst<T> weos = make_eos_const<T>(s.wp.sound_speed, s.wp.exponent, s.wp.reference_density,
+                                                   s.wp.background_pressure, 0,
+                                                   s.wp.sound_speed_from_fluid && s.fp.adaptive_params_f32);
+        const bool fused = adami_fused_noslip(s);
+        WallPrepArgs<T, CT> a;
+        a.n_tiles = s.tiles.d_wrow_tile_start + s.tiles.nrows;
+        a.tile_desc = s.tiles.d_wtile_desc;
+        a.Aw = (const V4<CT> *)s.d_Aw;
+        const T p_empty = (T)0;  // empty sum, clipped or not: p = 0
+        a.rho_empty = weos.rho0 * (T)std::pow((double)((p_empty - weos.p_bg) / weos.B + (T)1), (double)weos.inv_gamma);
+        a.W = (V2<T> *)s.d_Ww;
+        a.volume = (T *)s.d_volw;
+        a.active = s.tiles.d_wactive;
+        a.n_active = s.tiles.d_n_wactive;
+        a.rng = s.tiles.d_wtile_rng;
+        a.ext = s.tiles.d_wtile_ext;
+        a.Vw = fused ? (V4<T> *)s.d_Vw : (V4<T> *)nullptr;
+        a.Pw = (T *)s.d_Pw;
+        return a;
+    }
+
+    // ---- the per-kick rebuild in four launches: histogram -> one-pass scan + tile table -> scatter +
+    // candidate ranges + wall-tile sorting -> gather into sorted records (+ EOS)
+    static int rebuild_fluid_fused(Semi &s, const CT *d_u, const T *d_v)
+    {
+        const int n = (int)s.n_act;
+        const GridConst<CT> g = make_grid_const<CT>(s);
+        if (!s.count_clean) {
+            CUDA_TRY(&s, cudaMemsetAsync(s.d_count, 0, sizeof(int) * (size_t)s.ncells, s.stream));
+            s.count_clean = true;
+        }
+        if (n > 0)
+            LAUNCH(s, (k_cell_count<ND, CT>), cdiv(n, 256), 256, 0, d_u, n, (int)s.n_tgt, g, s.d_key, s.d_slot,
+                   s.d_count, s.d_flags);
+        const bool wall = s.n_w > 0;
+        LAUNCH(s, k_scan_cells_tiles, s.scan_blocks, SCAN_THREADS, 0, s.d_count, s.ncell[0], s.tiles.nrows,
+               s.scan_rows_per_block, s.d_scan_ticket, s.d_scan_status, s.d_fcell_start,
+               s.tiles.d_frow_tile_start, s.tiles.d_ftile_desc, wall ? s.tiles.d_n_wactive : (int *)nullptr);
+        const int nb_scatter = cdiv(n, 256), nb_ranges = cdiv((int64_t)s.tiles.max_ftiles * 32, 256);
+        const int nb_wprep = wall ? cdiv((int64_t)s.tiles.max_wtiles * 32, 256) : 0;
+        WallPrepArgs<T, CT> wpa{};
+        if (wall) wpa = wall_prep_args(s);
+        LAUNCH(s, (k_post_scan<ND, T, CT>), nb_scatter + nb_ranges + nb_wprep, 256, 0, nb_scatter, nb_ranges, s.d_key,
+               s.d_slot, s.d_fcell_start, n, s.d_tmp_perm, g, s.tiles.d_frow_tile_start + s.tiles.nrows,
+               s.tiles.d_ftile_desc, wall ? s.d_wcell_start : (const int *)nullptr, s.tiles.d_ftile_rng,
+               s.tiles.d_ftile_ext, wpa);
+        s.wall_prep_done = wall;
+        return TPB_OK;
+    }
+
     static int rebuild_fluid(Semi &s, const CT *d_u, const T *d_v)
     {
         int n = (int)s.n_act;
-        int rc = bin_points(s, d_u, n, (int)s.n_tgt, s.d_fcell_start);
+        const bool fused = use_tiles(s) && s.scan_blocks > 0;
+        s.wall_prep_done = false;
+        int rc = fused ? rebuild_fluid_fused(s, d_u, d_v) : bin_points(s, d_u, n, (int)s.n_tgt, s.d_fcell_start);
         if (rc) return rc;
         EosConst<T> eos = make_eos_const<T>(s.fp.sound_speed, s.fp.exponent, s.fp.reference_density,
                                             s.fp.background_pressure, s.fp.clip_negative_pressure,
@@ -337,7 +406,7 @@ struct Ops {
                        s.d_fcell_start + s.ncells, s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
                        s.d_perm_f, g.fref, (V4<float> *)s.d_Ff);
         }
-        if (use_tiles(s)) {
+        if (use_tiles(s) && !fused) {
             rc = build_tile_table(s, s.d_fcell_start, s.tiles.d_frow_tile_start, s.tiles.d_ftile_desc);
             if (rc) return rc;
             LAUNCH(s, (k_tile_ranges<ND>), cdiv((int64_t)s.tiles.max_ftiles * 32, 256), 256, 0, s.ncell[0],
@@ -673,17 +742,15 @@ struct Ops {
             }
             // no-slip wall: the wall velocity rides along in the same sweep when the lists leave room
             // for the five reduction slots; otherwise k_wall_velocity follows (kick_device)
-            const bool fused = s.wp.has_viscosity && list_len >= ADAMI_NOSLIP_RED * (int)sizeof(T) / 2;
+            const bool fused = adami_fused_noslip(s);
             s.wall_velocity_done = fused;
-            CUDA_TRY(&s, cudaMemsetAsync(s.tiles.d_n_wactive, 0, sizeof(int), s.stream));
-            T p_empty = (T)0;  // empty sum, clipped or not: p = 0
-            T rho_empty = k.eos.rho0 * (T)std::pow((double)((p_empty - k.eos.p_bg) / k.eos.B + (T)1),
-                                                   (double)k.eos.inv_gamma);
-            LAUNCH(s, (k_wall_tile_prep<ND, T, CT>), cdiv((int64_t)s.tiles.max_wtiles * 32, 256), 256, 0, g,
-                   s.tiles.d_wrow_tile_start + s.tiles.nrows, s.tiles.d_wtile_desc, (const V4<CT> *)s.d_Aw,
-                   s.d_fcell_start, rho_empty, (V2<T> *)s.d_Ww, (T *)s.d_volw, s.tiles.d_wactive,
-                   s.tiles.d_n_wactive, s.tiles.d_wtile_rng, s.tiles.d_wtile_ext,
-                   fused ? (V4<T> *)s.d_Vw : (V4<T> *)nullptr, (T *)s.d_Pw);
+            if (!s.wall_prep_done) {  // (the fused rebuild launch has done it already)
+                CUDA_TRY(&s, cudaMemsetAsync(s.tiles.d_n_wactive, 0, sizeof(int), s.stream));
+                const WallPrepArgs<T, CT> a = wall_prep_args(s);
+                LAUNCH(s, (k_wall_tile_prep<ND, T, CT>), cdiv((int64_t)s.tiles.max_wtiles * 32, 256), 256, 0, g,
+                       a.n_tiles, a.tile_desc, a.Aw, s.d_fcell_start, a.rho_empty, a.W, a.volume, a.active,
+                       a.n_active, a.rng, a.ext, a.Vw, a.Pw);
+            }
             if (fused) {
                 LAUNCH(s, (k_adami_tiles<KS, ND, T, CT, KERNEL, true>), grid, KS * TILE_TB, smem, g,
                        s.tiles.d_n_wactive, s.tiles.d_wactive, s.tiles.d_wtile_desc, s.tiles.d_wtile_ext,
@@ -1226,7 +1293,8 @@ static int dispatch_pairs(Semi &s, int sys, int nb, const void *u, int64_t cap, 
 static void free_device(Semi &s)
 {
     void *ptrs[] = {s.d_mass_f, s.d_u, s.d_v, s.d_dv, s.d_du, s.d_key, s.d_slot, s.d_tmp_perm,
-                    s.d_perm_f, s.d_count, s.d_fcell_start, s.d_wcell_start, s.d_block_sums,
+                    s.d_perm_f, s.d_count, s.d_fcell_start, s.d_wcell_start, s.d_block_sums, s.d_scan_status,
+                    s.d_scan_ticket,
                     s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_Vw, s.d_Pw, s.d_perm_w,
                     s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2, s.d_x0_s, s.d_xcur_s, s.d_mass_s, s.d_rho_s, s.d_hydro_s,
                     s.d_L_s, s.d_F_s, s.d_pk1_s, s.d_As, s.d_Bs, s.d_nbr_start, s.d_nbr, s.d_scell_start};
@@ -1582,6 +1650,18 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     CUDA_TRY(s, cudaMalloc(&s->d_wcell_start, sizeof(int) * (size_t)(s->ncells + 4)));
     CUDA_TRY(s, cudaMemset(s->d_wcell_start, 0, sizeof(int) * (size_t)(s->ncells + 4)));
     CUDA_TRY(s, cudaMalloc(&s->d_block_sums, sizeof(int) * (size_t)SCAN_TILE));
+    {
+        // k_scan_cells_tiles: whole cell rows per block
+        const int n0 = s->ncell[0], nrows = s->ncell[1] * s->ncell[2];
+        if (n0 <= SCAN_TILE && !getenv("TPB_SCAN3")) {
+            s->scan_rows_per_block = std::max(1, std::min(SCAN_TILE / n0, CSCAN_MAX_ROWS));
+            s->scan_blocks = cdiv(nrows, s->scan_rows_per_block);
+            CUDA_TRY(s, cudaMalloc(&s->d_scan_status, sizeof(unsigned long long) * 2 * (size_t)s->scan_blocks));
+            CUDA_TRY(s, cudaMemset(s->d_scan_status, 0, sizeof(unsigned long long) * 2 * (size_t)s->scan_blocks));
+            CUDA_TRY(s, cudaMalloc(&s->d_scan_ticket, sizeof(unsigned long long) * 2));
+            CUDA_TRY(s, cudaMemset(s->d_scan_ticket, 0, sizeof(unsigned long long) * 2));
+        }
+    }
     CUDA_TRY(s, cudaMalloc(&s->d_flags, sizeof(int) * 4));
     CUDA_TRY(s, cudaMemset(s->d_flags, 0, sizeof(int) * 4));
     CUDA_TRY(s, cudaHostAlloc(&s->h_flags, sizeof(int) * 4, cudaHostAllocDefault));

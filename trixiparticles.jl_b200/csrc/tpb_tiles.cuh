@@ -154,6 +154,139 @@ k_row_tile_table(const int *__restrict__ cell_start, int n0, int nrows, int *__r
     if (threadIdx.x == 0) row_tile_start[nrows] = carry;
 }
 
+// ------------------------------------------------------------------ one-pass cell scan + tile table
+// cell_start = exclusive_scan(count) AND the tile table of the sorted point set in ONE launch (the
+// per-kick path; replaces memset + three scan kernels + k_row_tile_table): every block owns a whole
+// number of cell rows, scans its cells locally, and chains both running totals -- particles and
+// tiles -- through a decoupled look-back (status words carry the number of the launch, so nothing has
+// to be reset between launches; blocks take a ticket, so a block only ever waits for blocks that
+// have already started).  The histogram is cleared on the way out for the next rebuild.
+//   status[2 b + w]: bits 63..34 epoch, 33..32 flag (1: aggregate of block b, 2: inclusive prefix), 31..0 value
+constexpr int CSCAN_MAX_ROWS = 2 * SCAN_THREADS;  // rows per block (two per thread)
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+static __global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_cells_tiles(int *__restrict__ count, int n0, int nrows, int rows_per_block,
+                   unsigned long long *__restrict__ ticket, unsigned long long *__restrict__ status,
+                   int *__restrict__ cell_start, int *__restrict__ row_tile_start, int4 *__restrict__ desc,
+                   int *__restrict__ zero_word)
+{
+    __shared__ int s_bid, s_off[2];
+    __shared__ unsigned s_epoch;
+    __shared__ int row_pref[CSCAN_MAX_ROWS + 1];
+    if (threadIdx.x == 0) {
+        // launch number and block number from one monotonic 64-bit ticket: nothing depends on host-side
+        // counters, so the launch can be replayed from a CUDA graph
+        const unsigned long long t = atomicAdd(ticket, 1ull);
+        const unsigned long long launch = t / gridDim.x;
+        s_bid = (int)(t - launch * gridDim.x);
+        s_epoch = 1u + (unsigned)(launch % 0x3FFFFFFEull);
+    }
+    __syncthreads();
+    const int bid = s_bid;
+    const unsigned epoch = s_epoch;
+    const int r0 = bid * rows_per_block;
+    const int rows_here = min(rows_per_block, nrows - r0);
+    const int cells_here = rows_here * n0;
+    int *const cnt_blk = count + (int64_t)r0 * n0;
+    const int base = threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = base + k < cells_here ? cnt_blk[base + k] : 0;
+        sum += v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < cells_here) cnt_blk[base + k] = 0;
+    int total_c;
+    const int run0 = block_inclusive_scan(sum, total_c) - sum;  // local exclusive prefix of cell `base`
+    {
+        int r = (base + n0 - 1) / n0;  // first row starting at or after cell `base`
+        int run = run0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (base + k < cells_here && base + k == r * n0) row_pref[r++] = run;
+            run += v[k];
+        }
+        if (threadIdx.x == 0) row_pref[rows_here] = total_c;
+    }
+    __syncthreads();
+    int nt[2], cnt[2], tsum = 0;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int r = threadIdx.x * 2 + e;
+        cnt[e] = r < rows_here ? row_pref[r + 1] - row_pref[r] : 0;
+        nt[e] = (cnt[e] + TILE_TB - 1) / TILE_TB;
+        tsum += nt[e];
+    }
+    int total_t;
+    const int trun0 = block_inclusive_scan(tsum, total_t) - tsum;
+    if (threadIdx.x == 0) {
+        const unsigned long long ep = (unsigned long long)epoch << 34;
+        const int total[2] = {total_c, total_t};
+        int off[2] = {0, 0};
+        if (bid > 0) {
+            st_release_u64(&status[2 * bid], ep | (1ull << 32) | (unsigned)total_c);
+            st_release_u64(&status[2 * bid + 1], ep | (1ull << 32) | (unsigned)total_t);
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                for (int p = bid - 1;; --p) {
+                    unsigned long long sw;
+                    do {
+                        sw = ld_acquire_u64(&status[2 * p + w]);
+                    } while ((unsigned)(sw >> 34) != epoch || ((sw >> 32) & 3ull) == 0);
+                    off[w] += (int)(unsigned)sw;
+                    if (((sw >> 32) & 3ull) == 2) break;
+                }
+            }
+        }
+        st_release_u64(&status[2 * bid], ep | (2ull << 32) | (unsigned)(off[0] + total[0]));
+        st_release_u64(&status[2 * bid + 1], ep | (2ull << 32) | (unsigned)(off[1] + total[1]));
+        s_off[0] = off[0];
+        s_off[1] = off[1];
+        if (bid == 0 && zero_word) *zero_word = 0;
+    }
+    __syncthreads();
+    const int off_c = s_off[0], off_t = s_off[1];
+    {
+        int *const cs_blk = cell_start + (int64_t)r0 * n0;
+        int run = off_c + run0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (base + k < cells_here) cs_blk[base + k] = run;
+            run += v[k];
+        }
+    }
+    const bool last_block = r0 + rows_here == nrows;
+    if (last_block && threadIdx.x == 0) {
+        cell_start[(int64_t)nrows * n0] = off_c + total_c;
+        row_tile_start[nrows] = off_t + total_t;
+    }
+    int first = off_t + trun0;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int r = threadIdx.x * 2 + e;
+        if (r < rows_here) {
+            row_tile_start[r0 + r] = first;
+            const int rs = off_c + row_pref[r];
+            for (int k = 0; k < nt[e]; ++k)
+                desc[first + k] = make_int4(rs + (int)((long long)cnt[e] * k / nt[e]),
+                                            rs + (int)((long long)cnt[e] * (k + 1) / nt[e]), r0 + r, 0);
+        }
+        first += nt[e];
+    }
+}
+
 // The same two steps for a static point set (the wall, built once): a row is first cut into
 // segments wherever `gap` or more consecutive cells are empty, then every segment is split into
 // balanced tiles.  Without the cut, the one tile of a tank-wall row that holds both its left and
@@ -200,14 +333,14 @@ k_row_tiles_gaps(const int *__restrict__ cell_start, int n0, int nrows, int gap,
 // that the sweeps start their TMA copies without a dependent chain of global loads.
 //   rng[tile * stride + 9 * set + q] = (g0, g1);   ext[tile] = (cxmin, cxmax, total set 0, total set 1)
 template <int ND>
-__global__ void __launch_bounds__(256)
-k_tile_ranges(int n0, int n1, int sx, const int *__restrict__ n_tiles, const int4 *__restrict__ desc,
-              const int *__restrict__ xcell_start, const int *__restrict__ nb0_cell_start,
-              const int *__restrict__ nb1_cell_start, int2 *__restrict__ rng, int stride,
-              int4 *__restrict__ ext)
+__device__ __forceinline__ void
+tile_ranges_body(int vblock, int n0, int n1, int sx, const int *__restrict__ n_tiles, const int4 *__restrict__ desc,
+                 const int *__restrict__ xcell_start, const int *__restrict__ nb0_cell_start,
+                 const int *__restrict__ nb1_cell_start, int2 *__restrict__ rng, int stride,
+                 int4 *__restrict__ ext)
 {
     constexpr int NROWS = ND == 3 ? 9 : 3;
-    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int tile = (vblock * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (tile >= *n_tiles) return;
     const int4 d = desc[tile];
@@ -242,6 +375,16 @@ k_tile_ranges(int n0, int n1, int sx, const int *__restrict__ n_tiles, const int
         cnt1 += __shfl_xor_sync(0xffffffffu, cnt1, o);
     }
     if (lane == 0) ext[tile] = make_int4(cx[0], cx[1], cnt0, cnt1);
+}
+template <int ND>
+__global__ void __launch_bounds__(256)
+k_tile_ranges(int n0, int n1, int sx, const int *__restrict__ n_tiles, const int4 *__restrict__ desc,
+              const int *__restrict__ xcell_start, const int *__restrict__ nb0_cell_start,
+              const int *__restrict__ nb1_cell_start, int2 *__restrict__ rng, int stride,
+              int4 *__restrict__ ext)
+{
+    tile_ranges_body<ND>(blockIdx.x, n0, n1, sx, n_tiles, desc, xcell_start, nb0_cell_start, nb1_cell_start, rng,
+                         stride, ext);
 }
 
 struct TileHdr {
@@ -937,17 +1080,30 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
 // the tile's neighbour rows hold any fluid particle: if not, it writes the result of an empty
 // sum (p = 0, rho = EOS^-1(0), volume = 0) directly; otherwise the tile is appended to the
 // active list that k_adami_tiles runs over.
+template <typename T, typename CT>
+struct WallPrepArgs {
+    const int *n_tiles;
+    const int4 *tile_desc;
+    const V4<CT> *Aw;
+    T rho_empty;
+    V2<T> *W;
+    T *volume;
+    int *active, *n_active;
+    int2 *rng;
+    int4 *ext;
+    V4<T> *Vw;  // no-slip wall: (v_w, rho_w) records; else nullptr
+    T *Pw;      // no-slip wall: p_w as a scalar array
+};
 template <int ND, typename T, typename CT>
-__global__ void __launch_bounds__(256)
-k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
-                 const V4<CT> *__restrict__ Aw, const int *__restrict__ fcell_start, T rho_empty,
-                 V2<T> *__restrict__ W, T *__restrict__ volume, int *__restrict__ active,
-                 int *__restrict__ n_active, int2 *__restrict__ rng, int4 *__restrict__ ext,
-                 V4<T> *__restrict__ Vw /* no-slip wall: (v_w, rho_w) records; else nullptr */,
-                 T *__restrict__ Pw /* no-slip wall: p_w as a scalar array */)
+__device__ __forceinline__ void
+wall_tile_prep_body(int vblock, const GridConst<CT> &g, const int *__restrict__ n_tiles,
+                    const int4 *__restrict__ tile_desc, const V4<CT> *__restrict__ Aw,
+                    const int *__restrict__ fcell_start, T rho_empty, V2<T> *__restrict__ W,
+                    T *__restrict__ volume, int *__restrict__ active, int *__restrict__ n_active,
+                    int2 *__restrict__ rng, int4 *__restrict__ ext, V4<T> *__restrict__ Vw, T *__restrict__ Pw)
 {
     constexpr int NROWS = ND == 3 ? 9 : 3;
-    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int tile = (vblock * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (tile >= *n_tiles) return;
     const int4 d = tile_desc[tile];
@@ -989,6 +1145,48 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
             Pw[w] = (T)0;
         }
     }
+}
+template <int ND, typename T, typename CT>
+__global__ void __launch_bounds__(256)
+k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *__restrict__ tile_desc,
+                 const V4<CT> *__restrict__ Aw, const int *__restrict__ fcell_start, T rho_empty,
+                 V2<T> *__restrict__ W, T *__restrict__ volume, int *__restrict__ active,
+                 int *__restrict__ n_active, int2 *__restrict__ rng, int4 *__restrict__ ext,
+                 V4<T> *__restrict__ Vw /* no-slip wall: (v_w, rho_w) records; else nullptr */,
+                 T *__restrict__ Pw /* no-slip wall: p_w as a scalar array */)
+{
+    wall_tile_prep_body<ND, T, CT>(blockIdx.x, g, n_tiles, tile_desc, Aw, fcell_start, rho_empty, W, volume, active,
+                                   n_active, rng, ext, Vw, Pw);
+}
+
+// One launch for the three independent steps that follow the cell scan: blocks [0, nb_scatter) scatter the
+// particle indices (k_scatter), the next nb_ranges blocks compute the candidate ranges of the fluid tiles
+// (k_tile_ranges), the rest sort the wall tiles into empty / active (k_wall_tile_prep).  At a million
+// particles each of them runs for a few microseconds: as separate launches their start-up and drain
+// dominate.
+template <int ND, typename T, typename CT>
+__global__ void __launch_bounds__(256)
+k_post_scan(int nb_scatter, int nb_ranges, const int *__restrict__ key, const int *__restrict__ slot,
+            const int *__restrict__ fcell_start, int n, int *__restrict__ tmp_perm, GridConst<CT> g,
+            const int *__restrict__ n_ftiles, const int4 *__restrict__ fdesc,
+            const int *__restrict__ wcell_start, int2 *__restrict__ frng, int4 *__restrict__ fext,
+            WallPrepArgs<T, CT> wp)
+{
+    int vb = blockIdx.x;
+    if (vb < nb_scatter) {
+        const int i = vb * blockDim.x + threadIdx.x;
+        if (i < n && key[i] >= 0) tmp_perm[fcell_start[key[i]] + slot[i]] = i;
+        return;
+    }
+    vb -= nb_scatter;
+    if (vb < nb_ranges) {
+        tile_ranges_body<ND>(vb, g.n[0], g.n[1], g.sx, n_ftiles, fdesc, fcell_start, fcell_start, wcell_start, frng,
+                             18, fext);
+        return;
+    }
+    vb -= nb_ranges;
+    wall_tile_prep_body<ND, T, CT>(vb, g, wp.n_tiles, wp.tile_desc, wp.Aw, fcell_start, wp.rho_empty, wp.W,
+                                   wp.volume, wp.active, wp.n_active, wp.rng, wp.ext, wp.Vw, wp.Pw);
 }
 
 // Targets: wall particles (active tiles over the wall's sorted order); neighbours: fluid.
