@@ -331,7 +331,7 @@ struct Ops {
         const int list_len = SMALL ? s.tiles.adami_list_len : s.tiles.list(KS);
         return s.wp.has_viscosity && list_len >= ADAMI_NOSLIP_RED * (int)sizeof(T) / 2;
     }
-    static WallPrepArgs<T, CT> wall_prep_args(const Semi &s)
+    static WallPrepArgs<T, CT> wall_prep_args(Semi &s)
     {
         const EosConst<T> weos = make_eos_const<T>(s.wp.sound_speed, s.wp.exponent, s.wp.reference_density,
                                                    s.wp.background_pressure, 0,
@@ -351,6 +351,9 @@ struct Ops {
         a.ext = s.tiles.d_wtile_ext;
         a.Vw = fused ? (V4<T> *)s.d_Vw : (V4<T> *)nullptr;
         a.Pw = (T *)s.d_Pw;
+        a.state = s.tiles.d_wtile_state;
+        a.rewrite = (double)a.rho_empty != s.tiles.wall_rho_empty;
+        s.tiles.wall_rho_empty = (double)a.rho_empty;
         return a;
     }
 
@@ -749,7 +752,7 @@ struct Ops {
                 const WallPrepArgs<T, CT> a = wall_prep_args(s);
                 LAUNCH(s, (k_wall_tile_prep<ND, T, CT>), cdiv((int64_t)s.tiles.max_wtiles * 32, 256), 256, 0, g,
                        a.n_tiles, a.tile_desc, a.Aw, s.d_fcell_start, a.rho_empty, a.W, a.volume, a.active,
-                       a.n_active, a.rng, a.ext, a.Vw, a.Pw);
+                       a.n_active, a.rng, a.ext, a.Vw, a.Pw, a.state, a.rewrite);
             }
             if (fused) {
                 LAUNCH(s, (k_adami_tiles<KS, ND, T, CT, KERNEL, true>), grid, KS * TILE_TB, smem, g,

@@ -216,6 +216,18 @@ struct EosConst {
     int clip;
 };
 
+// StateEquationAdaptiveCole: what follows the speed of sound, written on the device by k_adaptive_consts
+// (tpb_vec.cuh) before the kick's kernels run -- the kick does not wait for the host
+template <typename T>
+struct AdaptConsts {
+    T c;            // system_sound_speed(fluid)
+    T B_f, B_w;     // rho0 c^2 / gamma of the fluid's / the boundary model's state equation
+    T delta_h_c;    // density diffusion
+    T nu_a, nu_b;   // kinematic viscosities seen by the wall's viscous term
+    T rho_empty_w;  // wall density of an empty Adami sum
+    T pad;
+};
+
 template <typename T>
 __device__ __forceinline__ T eos_pressure(const EosConst<T> &e, T density)
 {

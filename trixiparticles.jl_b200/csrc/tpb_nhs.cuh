@@ -168,11 +168,13 @@ k_reorder_fluid(const CT *__restrict__ u, const T *__restrict__ v, const T *__re
                 const int *__restrict__ key, const int *__restrict__ cell_start,
                 const int *__restrict__ tmp_perm, int n, const int *__restrict__ n_sorted,
                 int deterministic, EosConst<T> eos, V4<CT> *__restrict__ A, V4<T> *__restrict__ B,
-                T *__restrict__ P, int *__restrict__ perm, FilterRef<CT> fref, V4<float> *__restrict__ F)
+                T *__restrict__ P, int *__restrict__ perm, FilterRef<CT> fref, V4<float> *__restrict__ F,
+                const AdaptConsts<T> *__restrict__ ad = nullptr)
 {
     constexpr int NV = DENS == 0 ? ND + 1 : ND;
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n || s >= *n_sorted) return;  // n_sorted < n when ghost slots are empty
+    if (ad) eos.B = ad->B_f;  // StateEquationAdaptiveCole: this kick's speed of sound (k_adaptive_consts)
     int i = tmp_perm[s];
     int dst = s;
     if (deterministic) {

@@ -231,30 +231,42 @@ k_scan_cells_tiles(int *__restrict__ count, int n0, int nrows, int rows_per_bloc
     }
     int total_t;
     const int trun0 = block_inclusive_scan(tsum, total_t) - tsum;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // warp 0: publish the block's aggregates, then look back 32 predecessors at a time
         const unsigned long long ep = (unsigned long long)epoch << 34;
-        const int total[2] = {total_c, total_t};
+        const int lane = threadIdx.x;
         int off[2] = {0, 0};
         if (bid > 0) {
-            st_release_u64(&status[2 * bid], ep | (1ull << 32) | (unsigned)total_c);
-            st_release_u64(&status[2 * bid + 1], ep | (1ull << 32) | (unsigned)total_t);
+            if (lane < 2) st_release_u64(&status[2 * bid + lane], ep | (1ull << 32) | (unsigned)(lane == 0 ? total_c : total_t));
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
-                for (int p = bid - 1;; --p) {
-                    unsigned long long sw;
-                    do {
-                        sw = ld_acquire_u64(&status[2 * p + w]);
-                    } while ((unsigned)(sw >> 34) != epoch || ((sw >> 32) & 3ull) == 0);
-                    off[w] += (int)(unsigned)sw;
-                    if (((sw >> 32) & 3ull) == 2) break;
+                for (int p0 = bid - 1; p0 >= 0; p0 -= 32) {
+                    const int p = p0 - lane;
+                    unsigned long long sw = 2ull << 32;  // blocks before the first one: an empty inclusive prefix
+                    if (p >= 0) {
+                        do {
+                            sw = ld_acquire_u64(&status[2 * p + w]);
+                        } while ((unsigned)(sw >> 34) != epoch || ((sw >> 32) & 3ull) == 0);
+                    }
+                    // lanes up to (and including) the nearest block that already knows its inclusive prefix
+                    const unsigned incl = __ballot_sync(0xffffffffu, ((sw >> 32) & 3ull) == 2);
+                    const int stop = incl ? __ffs(incl) - 1 : 31;
+                    int val = lane <= stop ? (int)(unsigned)sw : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                    off[w] += val;
+                    if (incl) break;
                 }
             }
         }
-        st_release_u64(&status[2 * bid], ep | (2ull << 32) | (unsigned)(off[0] + total[0]));
-        st_release_u64(&status[2 * bid + 1], ep | (2ull << 32) | (unsigned)(off[1] + total[1]));
-        s_off[0] = off[0];
-        s_off[1] = off[1];
-        if (bid == 0 && zero_word) *zero_word = 0;
+        if (lane < 2)
+            st_release_u64(&status[2 * bid + lane],
+                           ep | (2ull << 32) | (unsigned)(lane == 0 ? off[0] + total_c : off[1] + total_t));
+        if (lane == 0) {
+            s_off[0] = off[0];
+            s_off[1] = off[1];
+            if (bid == 0 && zero_word) *zero_word = 0;
+        }
     }
     __syncthreads();
     const int off_c = s_off[0], off_t = s_off[1];
@@ -912,12 +924,21 @@ k_interact_tiles(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
                  T *__restrict__ dv, int n_targets, int cap, int list_len,
                  const V4<float> *__restrict__ Ff, const V4<float> *__restrict__ Fw,
                  const V4<T> *__restrict__ Vw = nullptr, const T *__restrict__ Pw = nullptr,
-                 WallViscConst<T> wk = WallViscConst<T>())
+                 WallViscConst<T> wk = WallViscConst<T>(), const AdaptConsts<T> *__restrict__ ad = nullptr)
 {
     constexpr int NV = DENS == 0 ? ND + 1 : ND;
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     const int tile = blockIdx.x;
     if (tile >= *n_tiles) return;
+    if (ad) {  // StateEquationAdaptiveCole: this kick's speed of sound (k_adaptive_consts)
+        k.c = ad->c;
+        k.delta_h_c = ad->delta_h_c;
+        if constexpr (NOSLIP) {
+            wk.c = ad->c;
+            wk.nu_a = ad->nu_a;
+            wk.nu_b = ad->nu_b;
+        }
+    }
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
     const int2 *rng = tile_rng + (int64_t)tile * 18;
     const NbSet<T, CT, V4<T>, true> nb_f{fcell_start, A, B, P, Ff};
@@ -1093,6 +1114,9 @@ struct WallPrepArgs {
     int4 *ext;
     V4<T> *Vw;  // no-slip wall: (v_w, rho_w) records; else nullptr
     T *Pw;      // no-slip wall: p_w as a scalar array
+    unsigned char *state;  // per tile: 1 = the empty-sum values are in place since an earlier kick
+    int rewrite;           // the empty-sum values have changed (adaptive sound speed): write them again
+    const AdaptConsts<T> *ad;  // StateEquationAdaptiveCole shared with the fluid: rho_empty comes from there
 };
 template <int ND, typename T, typename CT>
 __device__ __forceinline__ void
@@ -1100,7 +1124,8 @@ wall_tile_prep_body(int vblock, const GridConst<CT> &g, const int *__restrict__ 
                     const int4 *__restrict__ tile_desc, const V4<CT> *__restrict__ Aw,
                     const int *__restrict__ fcell_start, T rho_empty, V2<T> *__restrict__ W,
                     T *__restrict__ volume, int *__restrict__ active, int *__restrict__ n_active,
-                    int2 *__restrict__ rng, int4 *__restrict__ ext, V4<T> *__restrict__ Vw, T *__restrict__ Pw)
+                    int2 *__restrict__ rng, int4 *__restrict__ ext, V4<T> *__restrict__ Vw, T *__restrict__ Pw,
+                    unsigned char *__restrict__ state = nullptr, int rewrite = 1)
 {
     constexpr int NROWS = ND == 3 ? 9 : 3;
     const int tile = (vblock * blockDim.x + threadIdx.x) >> 5;
@@ -1128,8 +1153,17 @@ wall_tile_prep_body(int vblock, const GridConst<CT> &g, const int *__restrict__ 
         if (lane == 0) {
             ext[tile] = make_int4(cxmin, cxmax, total, 0);
             active[atomicAdd(n_active, 1)] = tile;
+            if (state) state[tile] = 0;
         }
         return;
+    }
+    // Most wall tiles of a tank never see fluid: their empty-sum values are written once, not every kick
+    // (at 10 M fluid particles the 7.3 M wall particles would cost 88 MB of stores per kick).
+    if (state) {
+        const bool in_place = state[tile] == 1 && !rewrite;
+        __syncwarp();
+        if (in_place) return;
+        if (lane == 0) state[tile] = 1;
     }
     V2<T> empty;
     empty.x = (T)0;
@@ -1153,10 +1187,11 @@ k_wall_tile_prep(GridConst<CT> g, const int *__restrict__ n_tiles, const int4 *_
                  V2<T> *__restrict__ W, T *__restrict__ volume, int *__restrict__ active,
                  int *__restrict__ n_active, int2 *__restrict__ rng, int4 *__restrict__ ext,
                  V4<T> *__restrict__ Vw /* no-slip wall: (v_w, rho_w) records; else nullptr */,
-                 T *__restrict__ Pw /* no-slip wall: p_w as a scalar array */)
+                 T *__restrict__ Pw /* no-slip wall: p_w as a scalar array */,
+                 unsigned char *__restrict__ state, int rewrite)
 {
     wall_tile_prep_body<ND, T, CT>(blockIdx.x, g, n_tiles, tile_desc, Aw, fcell_start, rho_empty, W, volume, active,
-                                   n_active, rng, ext, Vw, Pw);
+                                   n_active, rng, ext, Vw, Pw, state, rewrite);
 }
 
 // One launch for the three independent steps that follow the cell scan: blocks [0, nb_scatter) scatter the
@@ -1185,8 +1220,9 @@ k_post_scan(int nb_scatter, int nb_ranges, const int *__restrict__ key, const in
         return;
     }
     vb -= nb_ranges;
-    wall_tile_prep_body<ND, T, CT>(vb, g, wp.n_tiles, wp.tile_desc, wp.Aw, fcell_start, wp.rho_empty, wp.W,
-                                   wp.volume, wp.active, wp.n_active, wp.rng, wp.ext, wp.Vw, wp.Pw);
+    wall_tile_prep_body<ND, T, CT>(vb, g, wp.n_tiles, wp.tile_desc, wp.Aw, fcell_start,
+                                   wp.ad ? wp.ad->rho_empty_w : wp.rho_empty, wp.W, wp.volume, wp.active,
+                                   wp.n_active, wp.rng, wp.ext, wp.Vw, wp.Pw, wp.state, wp.rewrite);
 }
 
 // Targets: wall particles (active tiles over the wall's sorted order); neighbours: fluid.
@@ -1211,11 +1247,13 @@ k_adami_tiles(GridConst<CT> g, const int *__restrict__ n_active, const int *__re
               const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
               const V4<T> *__restrict__ B, const T *__restrict__ P, int interaction_enabled,
               AdamiConst<T> k, V2<T> *__restrict__ W, T *__restrict__ volume, int cap, int list_len,
-              const V4<float> *__restrict__ Ff, V4<T> *__restrict__ Vw = nullptr, T *__restrict__ Pw = nullptr)
+              const V4<float> *__restrict__ Ff, V4<T> *__restrict__ Vw = nullptr, T *__restrict__ Pw = nullptr,
+              const AdaptConsts<T> *__restrict__ ad = nullptr)
 {
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     const int n_act = *n_active;
     if ((int)blockIdx.x >= n_act) return;
+    if (ad) k.eos.B = ad->B_w;  // the boundary model shares the fluid's StateEquationAdaptiveCole
     TileSmem<T, CT> sm(tile_smem_raw, cap, list_len, KS * TILE_TB);
     if (threadIdx.x == 0) mbar_init(sm.bar, 1);
     uint32_t parity = 0;
@@ -1437,6 +1475,8 @@ struct TileState {
     int2 *d_ptile_rng = nullptr;
     int *d_wactive = nullptr;          // [max_wtiles] wall tiles with fluid in reach (per kick)
     int *d_n_wactive = nullptr;        // [1]
+    unsigned char *d_wtile_state = nullptr;  // [max_wtiles] 1: tile without fluid in reach, empty-sum values in place
+    double wall_rho_empty = -1;        // the value those tiles hold
     int nrows = 0;
     int max_ftiles = 0, max_wtiles = 0;
     int smem_budget = 112 * 1024;  // bytes per block: two blocks per SM
@@ -1479,6 +1519,8 @@ inline int tiles_alloc(TileState &t, int nrows, int64_t n_f, int64_t n_w)
     if (cudaMalloc(&t.d_ptile_rng, sizeof(int2) * 9 * max_tiles) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_wactive, sizeof(int) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_n_wactive, sizeof(int) * 4) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_wtile_state, (size_t)t.max_wtiles + 4) != cudaSuccess) return 1;
+    cudaMemset(t.d_wtile_state, 0, (size_t)t.max_wtiles + 4);
     cudaMemset(t.d_frow_tile_start, 0, sizeof(int) * (size_t)(nrows + 4));
     cudaMemset(t.d_wrow_tile_start, 0, sizeof(int) * (size_t)(nrows + 4));
     return 0;
@@ -1492,11 +1534,15 @@ inline int tiles_reserve_wall(TileState &t, int n_tiles)
     cudaFree(t.d_wtile_ext);
     cudaFree(t.d_wtile_rng);
     cudaFree(t.d_wactive);
+    cudaFree(t.d_wtile_state);
     t.d_wtile_desc = nullptr, t.d_wtile_ext = nullptr, t.d_wtile_rng = nullptr, t.d_wactive = nullptr;
+    t.d_wtile_state = nullptr;
     if (cudaMalloc(&t.d_wtile_desc, sizeof(int4) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_wtile_ext, sizeof(int4) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_wtile_rng, sizeof(int2) * 9 * (size_t)t.max_wtiles) != cudaSuccess) return 1;
     if (cudaMalloc(&t.d_wactive, sizeof(int) * (size_t)t.max_wtiles) != cudaSuccess) return 1;
+    if (cudaMalloc(&t.d_wtile_state, (size_t)t.max_wtiles + 4) != cudaSuccess) return 1;
+    cudaMemset(t.d_wtile_state, 0, (size_t)t.max_wtiles + 4);
     if (t.max_wtiles > t.max_ftiles) {
         cudaFree(t.d_ptile_ext);
         cudaFree(t.d_ptile_rng);
@@ -1521,6 +1567,7 @@ inline void tiles_free(TileState &t)
     if (t.d_ptile_rng) cudaFree(t.d_ptile_rng);
     if (t.d_wactive) cudaFree(t.d_wactive);
     if (t.d_n_wactive) cudaFree(t.d_n_wactive);
+    if (t.d_wtile_state) cudaFree(t.d_wtile_state);
     t = TileState();
 }
 

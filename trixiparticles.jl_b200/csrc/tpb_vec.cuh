@@ -165,4 +165,73 @@ k_max_speed2(int64_t n, int nv, const T *__restrict__ v, unsigned long long *__r
     if ((threadIdx.x & 31) == 0 && best) atomicMax(out_bits, best);
 }
 
+// ------------------------------------------------------------------ StateEquationAdaptiveCole on the device
+// update_speed_of_sound! (wcsph/system.jl:307-321, state_equations.jl:37-84) without a host round trip:
+// one thread turns max|v|^2 into the new speed of sound and into every constant of the kick that follows
+// it, with the operations (and roundings) of the host path (update_sound_speed / make_eos_const /
+// make_pair_const / make_wall_visc_const in tpb200.cu).  The tile kernels read the struct when they are
+// handed its address.
+template <typename T>
+struct AdaptParams {
+    T mach, c_min, c_max;
+    float mach_f, c_min_f, c_max_f;  // the state equation's own Float32 fields (params_f32)
+    int params_f32;
+    T gamma_f, rho0_f;
+    float gamma_f32, rho0_f32;
+    int wall_follows;  // the boundary model shares the fluid's state equation
+    T gamma_w, rho0_w, pbg_w, inv_gamma_w;
+    float gamma_w32, rho0_w32;
+    T delta_h;         // delta * (h + h) / 2
+    int visc_f, visc_w, nd;
+    T alpha_f, alpha_w, h_f, h_w;
+};
+template <typename T>
+__global__ void k_adaptive_consts(const unsigned long long *__restrict__ vmax2_bits, AdaptParams<T> p,
+                                  AdaptConsts<T> *__restrict__ out, double *__restrict__ c_out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    T v_max2;
+    if constexpr (sizeof(T) == 4)
+        v_max2 = __uint_as_float((unsigned)*vmax2_bits);
+    else
+        v_max2 = __longlong_as_double((long long)*vmax2_bits);
+    double c;  // the value tpb_get_sound_speed reports (the state equation's Ref)
+    if constexpr (sizeof(T) == 4) {
+        const float q = __fdiv_rn(__fsqrt_rn(v_max2), p.mach);
+        c = (double)fminf(p.c_max, fmaxf(p.c_min, q));
+    } else if (p.params_f32) {
+        const double q = __ddiv_rn(__dsqrt_rn(v_max2), (double)p.mach_f);
+        c = (double)(float)fmin((double)p.c_max_f, fmax((double)p.c_min_f, q));
+    } else {
+        const double q = __ddiv_rn(__dsqrt_rn(v_max2), p.mach);
+        c = fmin(p.c_max, fmax(p.c_min, q));
+    }
+    const T ct = (T)c;
+    auto bulk = [&](T rho0, T gamma, float rho0_32, float gamma_32) -> T {
+        if (p.params_f32) return (T)__fdiv_rn(__fmul_rn(rho0_32, __fmul_rn((float)c, (float)c)), gamma_32);
+        if constexpr (sizeof(T) == 4)
+            return __fdiv_rn(__fmul_rn(rho0, __fmul_rn(ct, ct)), gamma);
+        else
+            return __ddiv_rn(__dmul_rn(rho0, __dmul_rn(ct, ct)), gamma);
+    };
+    AdaptConsts<T> a;
+    a.c = ct;
+    a.B_f = bulk(p.rho0_f, p.gamma_f, p.rho0_f32, p.gamma_f32);
+    a.B_w = p.wall_follows ? bulk(p.rho0_w, p.gamma_w, p.rho0_w32, p.gamma_w32) : (T)0;
+    a.delta_h_c = p.delta_h * ct;
+    // kinematic_viscosity of ArtificialViscosityMonaghan: alpha h c / (2 ND + 4) (viscosity.jl:82-87)
+    auto kin = [&](int model, T alpha_or_nu, T h) {
+        return model == 1 ? alpha_or_nu * h * ct / (T)(2 * p.nd + 4) : alpha_or_nu;
+    };
+    a.nu_a = kin(p.visc_f, p.alpha_f, p.h_f);
+    a.nu_b = kin(p.visc_w, p.alpha_w, p.h_w);
+    // density of a wall particle without fluid in reach: inverse state equation of p = 0
+    a.rho_empty_w = p.wall_follows
+                        ? p.rho0_w * (T)pow((double)(((T)0 - p.pbg_w) / a.B_w + (T)1), (double)p.inv_gamma_w)
+                        : (T)0;
+    a.pad = (T)0;
+    *out = a;
+    *c_out = c;
+}
+
 }  // namespace tpb
