@@ -249,6 +249,16 @@ int32_t tpb_set_stream(tpb_semi_t semi, void *stream);
 int32_t tpb_get_stats(tpb_semi_t semi, tpb_stats *out);
 /* `system_sound_speed(fluid)` as of the last kick (StateEquationAdaptiveCole; else the constant) */
 int32_t tpb_get_sound_speed(tpb_semi_t semi, double *out);
+/* StateEquationAdaptiveCole on several slabs (update_speed_of_sound!, wcsph/system.jl:307-321, takes the
+ * maximum over ALL fluid particles): `tpb_max_speed2` reduces max |v|^2 over the handle's owned rows of
+ * the device vector `v_ode` into the 8-byte device word `out_bits` (the IEEE bit pattern of the value,
+ * zero-extended: the maximum of non-negative numbers is the maximum of their bit patterns, so an
+ * integer MAX all-reduce over the ranks finishes the job); `tpb_set_max_speed2` hands the reduced word
+ * (device memory) to the next tpb_kick, which then skips its own reduction.  Both are stream-ordered;
+ * a kick of a handle with ghost particles and an adaptive state equation fails with TPB_ERR_STATE
+ * unless tpb_set_max_speed2 preceded it. */
+int32_t tpb_max_speed2(tpb_semi_t semi, const void *v_ode, void *out_bits);
+int32_t tpb_set_max_speed2(tpb_semi_t semi, const void *bits);
 
 /* ---- device ODE-vector algebra ----------------------------------------------------------------
  * What a GPU-resident ODE-vector type binds for the integrator's broadcasts (the reference's

@@ -358,6 +358,42 @@ def test_kick_adaptive_cole(oracle, eltype, cdtype):
     assert float(se.sound_speed) == 100.0
 
 
+def test_adaptive_cole_device_path_equals_host_path(monkeypatch):
+    """The speed of sound stays on the device (k_max_speed2 -> k_adaptive_consts -> the kernels read
+    AdaptConsts; no host round trip, so the kick can be captured in a CUDA graph); TPB_ADAPTIVE_HOST
+    selects the host-scalar path the reference's `maximum` corresponds to.  Same value, same dv, bit for
+    bit, also with a no-slip wall whose kinematic viscosities follow the speed of sound."""
+    import torch
+    for no_slip in (False, True):
+        fluid, wall, _ = examples.dam_break_3d(0.1, eltype=np.float32, coordinates_eltype=np.float32,
+                                               adaptive_sound_speed=True)
+        if no_slip:
+            wall.boundary_model.viscosity = tp.ArtificialViscosityMonaghan(alpha=0.1, beta=0.0)
+        u, v = examples.perturbed_state(fluid)
+        v[:, :3] *= np.float32(20.0)
+        res = {}
+        for mode in ("device", "host"):
+            if mode == "host":
+                monkeypatch.setenv("TPB_ADAPTIVE_HOST", "1")
+            else:
+                monkeypatch.delenv("TPB_ADAPTIVE_HOST", raising=False)
+            semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+            ode = tp.semidiscretize(semi, (0.0, 1.0))
+            dev = ode.u0.device
+            u_d, v_d = torch.from_numpy(u.reshape(-1)).to(dev), torch.from_numpy(v.reshape(-1)).to(dev)
+            dv_d = torch.full_like(v_d, float("nan"))
+            ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
+            ode.f1(dv_d, v_d * 0.5, u_d, ode.p, 0.0)      # a second kick: the constants follow
+            c = semi.sound_speed()
+            semi.synchronize()
+            res[mode] = (c, dv_d.cpu().numpy(), semi.system_field(wall, "pressure"))
+            semi.close()
+        monkeypatch.delenv("TPB_ADAPTIVE_HOST", raising=False)
+        assert res["device"][0] == res["host"][0] and 10.0 < res["device"][0] < 100.0
+        np.testing.assert_array_equal(res["device"][1], res["host"][1])
+        np.testing.assert_array_equal(res["device"][2], res["host"][2])
+
+
 @pytest.mark.parametrize("example", ["dam_break_2d", "hydrostatic_2d"])
 def test_kick_summation_density(oracle, example):
     """SummationDensity variant (density_calculators.jl:26-50; dam_break_2d variant in

@@ -74,6 +74,57 @@ def test_slab_ranks_reproduce_single_gpu_kick(config, world):
         s.close()
 
 
+def test_adaptive_cole_across_slab_ranks():
+    """StateEquationAdaptiveCole on several slabs: `update_speed_of_sound!` (wcsph/system.jl:307-321)
+    takes the maximum over ALL fluid particles, so every rank reduces its own max |v|^2 on the device,
+    the words are combined (an integer MAX all-reduce between processes, the in-process mailbox here)
+    and handed to the kick with tpb_set_max_speed2.  The fastest particle sits in ONE slab; all slabs
+    must arrive at the single-handle speed of sound and dv."""
+    import torch
+    fluid, wall, _ = examples.dam_break_3d(0.05, adaptive_sound_speed=True)
+    nd = fluid.ndims
+    u, v = examples.perturbed_state(fluid)
+    fastest = int(np.argmax(u[:, 0]))                  # a particle of the last slab
+    v[fastest, :nd] = np.float32(4.0)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    dev = ode.u0.device
+    dv_ref = torch.full((v.size,), float("nan"), dtype=torch.float32, device=dev)
+    ode.f1(dv_ref, torch.from_numpy(v.reshape(-1)).to(dev), torch.from_numpy(u.reshape(-1)).to(dev), ode.p, 0.0)
+    c_ref = semi.sound_speed()
+    ref = dv_ref.cpu().numpy().reshape(v.shape)
+    semi.close()
+    assert 10.0 < c_ref < 100.0
+    world = 3
+    mb = LocalMailbox(world)
+    slabs = [SlabSemidiscretization(fluid, wall, rank=r, world=world, device=0, transport=mb.transport(r))
+             for r in range(world)]
+    odes = [s.semidiscretize((0.0, 1.0), finish=False) for s in slabs]
+    for s in slabs:
+        s.setup_finish()
+    us = [torch.from_numpy(u[s.owned_index].reshape(-1)).to(dev) for s in slabs]
+    vs = [torch.from_numpy(v[s.owned_index].reshape(-1)).to(dev) for s in slabs]
+    dvs = [torch.full_like(x, float("nan")) for x in vs]
+    for s, uu, vv in zip(slabs, us, vs):
+        s.kick_post(vv, uu)
+    for s, dv in zip(slabs, dvs):
+        s.kick_finish(dv)
+    got = np.full_like(ref, np.nan)
+    for s, dv in zip(slabs, dvs):
+        assert s.semi.sound_speed() == c_ref, (s.rank, s.semi.sound_speed(), c_ref)
+        got[s.owned_index] = dv.cpu().numpy().reshape(-1, v.shape[1])
+    for block in (slice(0, nd), slice(nd, nd + 1)):
+        err = np.abs(got[:, block] - ref[:, block]).max() / np.abs(ref[:, block]).max()
+        assert err <= 1e-5, (block, err)
+    # without the reduced maximum a handle with ghosts refuses to guess
+    s0 = slabs[0]
+    with pytest.raises(Exception):
+        s0._lib.check(s0.semi._handle, s0._lib.load().tpb_kick(
+            s0.semi._handle, dvs[0].data_ptr(), s0.v_ext.data_ptr(), s0.u_ext.data_ptr(), 0.0))
+    for s in slabs:
+        s.close()
+
+
 # ------------------------------------------------------------------ one process per GPU
 def _peer_worker(rank, world, port, out):
     import os

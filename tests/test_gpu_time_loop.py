@@ -145,6 +145,36 @@ def test_cuda_graph_replay_is_bit_identical_and_faster():
     print(f"eager {a['wall_s']:.2f} s, graph {b['wall_s']:.2f} s for {a['sol'].nsteps} steps")
 
 
+def test_adaptive_cole_time_loop_replays_from_a_cuda_graph():
+    """examples/fluid/dam_break_3d.jl as shipped (StateEquationAdaptiveCole shared by fluid and wall) with
+    a fixed time step: the speed of sound is updated on the device inside every kick, so the whole
+    Runge-Kutta step is captured and replayed -- same bits as the eager loop, and the speed of sound has
+    followed the accelerating column."""
+    import trixiparticles.jl_b200 as tp
+    from trixiparticles.jl_b200 import examples
+    from trixiparticles.jl_b200.time_integration import CarpenterKennedy2N54, solve
+
+    def run(cuda_graph):
+        fluid, wall, _ = examples.dam_break_3d(0.1, adaptive_sound_speed=True)
+        semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+        assert semi.adaptive_sound_speed_on_device()
+        ode = tp.semidiscretize(semi, (0.0, 0.06))
+        sol = solve(ode, CarpenterKennedy2N54(williamson_condition=False), dt=5e-4, cuda_graph=cuda_graph)
+        c = semi.sound_speed()
+        out = sol.u.cpu().numpy(), sol.v.cpu().numpy(), c, sol.nsteps
+        semi.close()
+        return out
+
+    u_e, v_e, c_e, n_e = run(False)
+    u_g, v_g, c_g, n_g = run(True)
+    assert n_e == n_g == 120
+    assert np.isfinite(v_e).all()
+    assert np.array_equal(u_e, u_g) and np.array_equal(v_e, v_g) and c_e == c_g
+    assert 10.0 <= c_e <= 100.0
+    vmax = np.sqrt((v_e.reshape(-1, 4)[:, :3].astype(np.float64) ** 2).sum(axis=1).max())
+    assert c_e == pytest.approx(min(100.0, max(10.0, vmax / 0.1)), rel=0.2)   # Mach-number target 0.1, last kick's state
+
+
 def test_float32_run_tracks_float64_trace():
     import run_dam_break_validation as V
     r = V.run(t_end=0.3, eltype=np.float32)

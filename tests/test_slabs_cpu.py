@@ -149,6 +149,43 @@ def test_gloo_two_rank_halo_exchange_reproduces_global_kick(oracle, no_slip):
         assert n_owned > 0 and n_ghost > 0
 
 
+def _vmax_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)
+        res = []
+        for dtype, itype in ((np.float32, np.uint32), (np.float64, np.uint64)):
+            v = rng.normal(size=(1000, 3)).astype(dtype)              # the same global state on every rank
+            v[123] *= 7                                               # the fastest particle lives on rank 0
+            mine = v[rank::world]
+            s2 = (mine[:, 0] * mine[:, 0] + mine[:, 1] * mine[:, 1]) + mine[:, 2] * mine[:, 2]
+            word = torch.tensor([int(s2.max().view(itype))], dtype=torch.int64)   # what tpb_max_speed2 writes
+            dist.all_reduce(word, op=dist.ReduceOp.MAX)
+            g2 = (v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2]
+            res.append(int(word) == int(g2.max().view(itype)))
+        out.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_max_speed_word_all_reduce():
+    """StateEquationAdaptiveCole across slabs: max |v|^2 travels as the zero-extended IEEE bit pattern and
+    is combined with an integer MAX all-reduce (non-negative floats order like their bit patterns)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_vmax_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, res in sorted(out.get() for _ in range(world)):
+        assert res == [True, True], (rank, res)
+
+
 def _rebalance_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2j_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2j_pytest_gpu.log; tail -25 gpurun_out/r2j_pytest_gpu.log
+for w in dam_break_3d_1m; do
+    echo "== $w"; timeout 200 python bench.py --steps 20 --warmup 3 --quick --workload $w 2>&1 | tail -1 | cut -c1-420
+done

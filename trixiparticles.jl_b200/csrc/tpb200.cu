@@ -90,6 +90,10 @@ struct Semi {
     int *d_perm_w = nullptr;
     void *d_scratch = nullptr;  // max(n_f, n_w) * sizeof(double): field unsort
     unsigned long long *d_vmax2 = nullptr, *h_vmax2 = nullptr;  // StateEquationAdaptiveCole: max |v|^2 (bits)
+    void *d_adapt = nullptr;       // AdaptConsts<T> + the speed of sound as a double behind it (k_adaptive_consts)
+    const void *ad_kick = nullptr; // this kick's kernels read their sound-speed constants from d_adapt
+    bool vmax2_ready = false;      // d_vmax2 already holds this kick's maximum (tpb_set_max_speed2: all slabs)
+    bool c_on_device = false;      // the current speed of sound lives in d_adapt, fp.sound_speed is stale
     void *d_Ff = nullptr, *d_Fw = nullptr;  // Float32 filter copies of the sorted positions (f32 / f64 coords)
     double filter_ref[3] = {0, 0, 0};       // reference point of the copies (coordinate order)
     float filter_pad = 0;                   // see FilterRef
@@ -352,8 +356,15 @@ struct Ops {
         a.Vw = fused ? (V4<T> *)s.d_Vw : (V4<T> *)nullptr;
         a.Pw = (T *)s.d_Pw;
         a.state = s.tiles.d_wtile_state;
-        a.rewrite = (double)a.rho_empty != s.tiles.wall_rho_empty;
-        s.tiles.wall_rho_empty = (double)a.rho_empty;
+        a.ad = s.ad_kick && s.wp.sound_speed_from_fluid ? (const AdaptConsts<T> *)s.ad_kick : nullptr;
+        if (a.ad) {
+            // the value lives on the device: it only moves with the speed of sound when p_background != 0
+            a.rewrite = s.wp.background_pressure != 0 || s.tiles.wall_rho_empty != -2;
+            s.tiles.wall_rho_empty = -2;
+        } else {
+            a.rewrite = (double)a.rho_empty != s.tiles.wall_rho_empty;
+            s.tiles.wall_rho_empty = (double)a.rho_empty;
+        }
         return a;
     }
 
@@ -402,7 +413,7 @@ struct Ops {
                 LAUNCH(s, (k_reorder_fluid<ND, T, CT, 0>), cdiv(n, 256), 256, 0, d_u, d_v,
                        (const T *)s.d_mass_f, s.d_key, s.d_fcell_start, s.d_tmp_perm, n,
                        s.d_fcell_start + s.ncells, s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
-                       s.d_perm_f, g.fref, (V4<float> *)s.d_Ff);
+                       s.d_perm_f, g.fref, (V4<float> *)s.d_Ff, (const AdaptConsts<T> *)s.ad_kick);
             else
                 LAUNCH(s, (k_reorder_fluid<ND, T, CT, 1>), cdiv(n, 256), 256, 0, d_u, d_v,
                        (const T *)s.d_mass_f, s.d_key, s.d_fcell_start, s.d_tmp_perm, n,
@@ -747,6 +758,8 @@ struct Ops {
             // for the five reduction slots; otherwise k_wall_velocity follows (kick_device)
             const bool fused = adami_fused_noslip(s);
             s.wall_velocity_done = fused;
+            const AdaptConsts<T> *wall_ad =
+                s.ad_kick && s.wp.sound_speed_from_fluid ? (const AdaptConsts<T> *)s.ad_kick : nullptr;
             if (!s.wall_prep_done) {  // (the fused rebuild launch has done it already)
                 CUDA_TRY(&s, cudaMemsetAsync(s.tiles.d_n_wactive, 0, sizeof(int), s.stream));
                 const WallPrepArgs<T, CT> a = wall_prep_args(s);
@@ -760,7 +773,7 @@ struct Ops {
                        s.tiles.d_wtile_rng, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
                        s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
                        s.interaction[1][0], k, (V2<T> *)s.d_Ww, (T *)s.d_volw, cap, list_len,
-                       (const V4<float> *)s.d_Ff, (V4<T> *)s.d_Vw, (T *)s.d_Pw);
+                       (const V4<float> *)s.d_Ff, (V4<T> *)s.d_Vw, (T *)s.d_Pw, wall_ad);
                 return TPB_OK;
             }
             LAUNCH(s, (k_adami_tiles<KS, ND, T, CT, KERNEL>), grid, KS * TILE_TB, smem, g,
@@ -768,7 +781,7 @@ struct Ops {
                    s.tiles.d_wtile_rng, s.d_wcell_start, (const V4<CT> *)s.d_Aw,
                    s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P,
                    s.interaction[1][0], k, (V2<T> *)s.d_Ww, (T *)s.d_volw, cap, list_len,
-                   (const V4<float> *)s.d_Ff);
+                   (const V4<float> *)s.d_Ff, (V4<T> *)nullptr, (T *)nullptr, wall_ad);
             return TPB_OK;
         }
         s.wall_velocity_done = false;
@@ -862,7 +875,8 @@ struct Ops {
                        (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f, s.interaction[0][0], has_wall,
                        s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv,
                        (int)s.n_tgt, cap, list_len, (const V4<float> *)s.d_Ff, (const V4<float> *)s.d_Fw,
-                       (const V4<T> *)s.d_Vw, (const T *)s.d_Pw, make_wall_visc_const(s, pc));
+                       (const V4<T> *)s.d_Vw, (const T *)s.d_Pw, make_wall_visc_const(s, pc),
+                       (const AdaptConsts<T> *)s.ad_kick);
                 return TPB_OK;
             }
             LAUNCH(s, (k_interact_tiles<KS, ND, T, CT, KERNEL, DENS>), s.tiles.max_ftiles, KS * TILE_TB, smem, g,
@@ -870,7 +884,8 @@ struct Ops {
                    s.tiles.d_ftile_rng, s.d_fcell_start, (const V4<CT> *)s.d_A,
                    (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f, s.interaction[0][0], has_wall,
                    s.d_wcell_start, (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc, src, d_dv,
-                   (int)s.n_tgt, cap, list_len, (const V4<float> *)s.d_Ff, (const V4<float> *)s.d_Fw);
+                   (int)s.n_tgt, cap, list_len, (const V4<float> *)s.d_Ff, (const V4<float> *)s.d_Fw,
+                   (const V4<T> *)nullptr, (const T *)nullptr, WallViscConst<T>(), (const AdaptConsts<T> *)s.ad_kick);
             return TPB_OK;
         }
         LAUNCH(s, (k_interact_pp<ND, T, CT, KERNEL, DENS>), cdiv(n, 128), 128, 0, n, g,
@@ -913,6 +928,55 @@ struct Ops {
         }
         s.fp.sound_speed = c;
         if (s.wp.sound_speed_from_fluid) s.wp.sound_speed = c;
+        s.c_on_device = false;
+        return TPB_OK;
+    }
+
+    // ---- the same without the host: k_max_speed2 -> k_adaptive_consts -> the kick's kernels read
+    // AdaptConsts.  Stream-ordered (no synchronisation, CUDA-graph capturable); the maximum may come from
+    // outside (tpb_set_max_speed2: reduced over all slabs).  Tile path with ContinuityDensity only.
+    static bool adaptive_on_device(const Semi &s)
+    {
+        const bool off = getenv("TPB_ADAPTIVE_HOST") != nullptr;
+        return !off && (s.cfg.interact_variant == 0 || s.cfg.interact_variant == 2) &&
+               s.fp.density_calculator == TPB_DENSITY_CONTINUITY && s.struct_index < 0;
+    }
+    static int max_speed2(Semi &s, const T *d_v, int64_t n, unsigned long long *d_out)
+    {
+        CUDA_TRY(&s, cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), s.stream));
+        if (n > 0)
+            LAUNCH(s, (k_max_speed2<ND, T>), (int)std::min<int64_t>(cdiv(n, 256), 148 * 8), 256, 0, n, nv(s), d_v,
+                   d_out);
+        return TPB_OK;
+    }
+    static int update_sound_speed_device(Semi &s, const T *d_v)
+    {
+        if (!s.d_adapt) CUDA_TRY(&s, cudaMalloc(&s.d_adapt, sizeof(AdaptConsts<T>) + 16));
+        if (!s.vmax2_ready) {
+            int rc = max_speed2(s, d_v, s.n_act, s.d_vmax2);
+            if (rc) return rc;
+        }
+        s.vmax2_ready = false;
+        AdaptParams<T> p{};
+        p.mach = (T)s.fp.mach_number_target, p.c_min = (T)s.fp.min_sound_speed, p.c_max = (T)s.fp.max_sound_speed;
+        p.mach_f = (float)s.fp.mach_number_target, p.c_min_f = (float)s.fp.min_sound_speed;
+        p.c_max_f = (float)s.fp.max_sound_speed;
+        p.params_f32 = s.fp.adaptive_params_f32;
+        p.gamma_f = (T)s.fp.exponent, p.rho0_f = (T)s.fp.reference_density;
+        p.gamma_f32 = (float)s.fp.exponent, p.rho0_f32 = (float)s.fp.reference_density;
+        p.wall_follows = s.n_w > 0 && s.wp.sound_speed_from_fluid;
+        p.gamma_w = (T)s.wp.exponent, p.rho0_w = (T)s.wp.reference_density, p.pbg_w = (T)s.wp.background_pressure;
+        p.inv_gamma_w = (T)1 / p.gamma_w;
+        p.gamma_w32 = (float)s.wp.exponent, p.rho0_w32 = (float)s.wp.reference_density;
+        const KernelConst<T> kern = make_kernel_const<T>(s.fp.kernel, ND, s.fp.smoothing_length);
+        p.delta_h = (T)s.fp.delta * ((kern.h + kern.h) / (T)2);
+        p.visc_f = s.fp.has_viscosity, p.visc_w = s.wp.has_viscosity, p.nd = ND;
+        p.alpha_f = (T)s.fp.alpha, p.alpha_w = (T)s.wp.alpha;
+        p.h_f = kern.h, p.h_w = (T)s.wp.smoothing_length;
+        LAUNCH(s, (k_adaptive_consts<T>), 1, 32, 0, s.d_vmax2, p, (AdaptConsts<T> *)s.d_adapt,
+               (double *)((unsigned char *)s.d_adapt + sizeof(AdaptConsts<T>)));
+        s.ad_kick = s.d_adapt;
+        s.c_on_device = true;
         return TPB_OK;
     }
 
@@ -924,8 +988,15 @@ struct Ops {
         const T *d_v = d_v_ode + lay.off_v_f;
         const CT *d_u = d_u_ode + lay.off_u_f;
         if (s.n_act == 0 && s.n_s == 0) return TPB_OK;
+        s.ad_kick = nullptr;
         if (s.fp.adaptive_sound_speed) {
-            int rc_c = update_sound_speed(s, d_v);
+            if (!adaptive_on_device(s) && s.n_tgt < s.n_act)
+                return fail(&s, TPB_ERR_UNSUPPORTED,
+                            "StateEquationAdaptiveCole across slabs needs the device path (tile sweeps, ContinuityDensity)");
+            if (adaptive_on_device(s) && s.n_tgt < s.n_act && !s.vmax2_ready)
+                return fail(&s, TPB_ERR_STATE,
+                            "StateEquationAdaptiveCole across slabs: call tpb_set_max_speed2 (maximum over all slabs) before every kick");
+            int rc_c = adaptive_on_device(s) ? update_sound_speed_device(s, d_v) : update_sound_speed(s, d_v);
             if (rc_c) return rc_c;
         }
         prof_mark(s, TPB_PHASE_REBUILD);
@@ -1227,7 +1298,8 @@ struct Ops {
     int TPB_CAT(drift_, TAG)(Semi &s, void *du, const void *v, const void *u);                           \
     int TPB_CAT(get_field_, TAG)(Semi &s, int sys, int field, void *out, int64_t n);                     \
     int TPB_CAT(pairs_, TAG)(Semi &s, int sys, int nb, const void *u, int64_t cap, int32_t *oi, int32_t *oj, \
-                             int64_t *cnt);
+                             int64_t *cnt);                                                              \
+    int TPB_CAT(max_speed2_, TAG)(Semi &s, const void *v, void *out_bits);
 #define TPB_DEFINE_ENTRIES(TAG, ND, T, CT)                                                               \
     int TPB_CAT(init_wall_, TAG)(Semi &s) { return Ops<ND, T, CT>::init_wall(s); }                       \
     int TPB_CAT(init_structure_, TAG)(Semi &s) { return Ops<ND, T, CT>::init_structure(s); }             \
@@ -1247,6 +1319,11 @@ struct Ops {
                              int64_t *cnt)                                                               \
     {                                                                                                    \
         return Ops<ND, T, CT>::neighbor_pairs(s, sys, nb, u, cap, oi, oj, cnt);                          \
+    }                                                                                                    \
+    int TPB_CAT(max_speed2_, TAG)(Semi &s, const void *v, void *out_bits)                                \
+    {                                                                                                    \
+        return Ops<ND, T, CT>::max_speed2(s, (const T *)v + ode_layout(s).off_v_f, s.n_tgt,              \
+                                          (unsigned long long *)out_bits);                               \
     }
 TPB_DECLARE_ENTRIES(2ff)
 TPB_DECLARE_ENTRIES(3ff)
@@ -1292,6 +1369,7 @@ static int dispatch_pairs(Semi &s, int sys, int nb, const void *u, int64_t cap, 
 {
     DISPATCH(s, pairs_, s, sys, nb, u, cap, oi, oj, cnt);
 }
+static int dispatch_max_speed2(Semi &s, const void *v, void *out_bits) { DISPATCH(s, max_speed2_, s, v, out_bits); }
 
 static void free_device(Semi &s)
 {
@@ -1299,7 +1377,7 @@ static void free_device(Semi &s)
                     s.d_perm_f, s.d_count, s.d_fcell_start, s.d_wcell_start, s.d_block_sums, s.d_scan_status,
                     s.d_scan_ticket,
                     s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_Vw, s.d_Pw, s.d_perm_w,
-                    s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2, s.d_x0_s, s.d_xcur_s, s.d_mass_s, s.d_rho_s, s.d_hydro_s,
+                    s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2, s.d_adapt, s.d_x0_s, s.d_xcur_s, s.d_mass_s, s.d_rho_s, s.d_hydro_s,
                     s.d_L_s, s.d_F_s, s.d_pk1_s, s.d_As, s.d_Bs, s.d_nbr_start, s.d_nbr, s.d_scell_start};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1821,7 +1899,39 @@ int32_t tpb_get_sound_speed(tpb_semi_t semi, double *out)
     Semi *s = (Semi *)semi;
     if (!s || !out) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
     if (s->fluid_index < 0) return fail(s, TPB_ERR_STATE, "no fluid system");
+    if (s->c_on_device && s->d_adapt) {
+        // the kick left the value on the device (k_adaptive_consts): fetch it, stream-ordered
+        const size_t off = s->cfg.eltype == TPB_F64 ? sizeof(tpb::AdaptConsts<double>) : sizeof(tpb::AdaptConsts<float>);
+        double c = 0;
+        CUDA_TRY(s, cudaMemcpyAsync(&c, (const unsigned char *)s->d_adapt + off, sizeof(double), cudaMemcpyDeviceToHost,
+                                    s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        s->fp.sound_speed = c;
+        if (s->wp.sound_speed_from_fluid) s->wp.sound_speed = c;
+        s->c_on_device = false;
+    }
     *out = s->fp.sound_speed;
+    return TPB_OK;
+}
+
+int32_t tpb_max_speed2(tpb_semi_t semi, const void *v_ode, void *out_bits)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !v_ode || !out_bits) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->ready || s->fluid_index < 0) return fail(s, TPB_ERR_STATE, "call tpb_semidiscretize first");
+    if (s->cfg.ode_memory != TPB_MEM_DEVICE) return fail(s, TPB_ERR_UNSUPPORTED, "device ODE vectors only");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    return dispatch_max_speed2(*s, v_ode, out_bits);
+}
+
+int32_t tpb_set_max_speed2(tpb_semi_t semi, const void *bits)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !bits) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->fp.adaptive_sound_speed) return fail(s, TPB_ERR_STATE, "the fluid has no StateEquationAdaptiveCole");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_vmax2, bits, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s->stream));
+    s->vmax2_ready = true;
     return TPB_OK;
 }
 
@@ -1843,8 +1953,6 @@ int32_t tpb_set_fluid_count(tpb_semi_t semi, int64_t n_active, int64_t n_targets
         return fail(s, TPB_ERR_UNSUPPORTED, "ghost particles need ContinuityDensity (their density travels with them)");
     if (s->struct_index >= 0 && (n_active != s->n_f || n_targets != s->n_f))
         return fail(s, TPB_ERR_UNSUPPORTED, "slab ghosts are not combined with a structure system");
-    if (n_targets < n_active && s->fp.adaptive_sound_speed)
-        return fail(s, TPB_ERR_UNSUPPORTED, "StateEquationAdaptiveCole needs the maximum velocity of all slabs");
     s->n_act = n_active;
     s->n_tgt = n_targets;
     return TPB_OK;

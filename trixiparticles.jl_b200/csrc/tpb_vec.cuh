@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "tpb_device.cuh"
+
 namespace tpb {
 
 template <typename T>

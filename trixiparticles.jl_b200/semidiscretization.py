@@ -339,6 +339,17 @@ class Semidiscretization:
         _lib.check(self._handle, _lib.load().tpb_get_sound_speed(self._handle, C.byref(out)))
         return out.value
 
+    def adaptive_sound_speed_on_device(self) -> bool:
+        """StateEquationAdaptiveCole without a host round trip (tile sweeps, ContinuityDensity, no structure
+        system; `TPB_ADAPTIVE_HOST` selects the host-scalar path): such a kick is stream-ordered and can
+        be captured in a CUDA graph."""
+        import os
+        from .model import ContinuityDensity, TotalLagrangianSPHSystem
+        fluids = [s_ for s_ in self.systems if isinstance(s_, WeaklyCompressibleSPHSystem)]
+        return ("TPB_ADAPTIVE_HOST" not in os.environ and self.parallelization_backend.interact_variant in (0, 2)
+                and all(isinstance(f.density_calculator, ContinuityDensity) for f in fluids)
+                and not any(isinstance(s_, TotalLagrangianSPHSystem) for s_ in self.systems))
+
     def stats(self) -> _lib.Stats:
         st = _lib.Stats()
         _lib.check(self._handle, _lib.load().tpb_get_stats(self._handle, C.byref(st)))

@@ -693,6 +693,9 @@ class SlabSemidiscretization:
         systems = (self.fluid,) if self.wall is None else (self.fluid, self.wall)
         self.semi = Semidiscretization(*systems, neighborhood_search=nhs, parallelization_backend=backend)
         self.device = torch.device("cuda", device)
+        from .model import StateEquationAdaptiveCole
+        self.adaptive_sound_speed = isinstance(self.fluid.state_equation, StateEquationAdaptiveCole)
+        self._vmax_bits = None
         self.peer = None
         self.transport = self._transport_arg if self._transport_arg is not None else DistTransport(rank, world)
         self.halo = HaloExchange(self.layout, rank, self.transport, tree)
@@ -772,9 +775,39 @@ class SlabSemidiscretization:
             self.u_ext[n0:n0 + n_g] = u_g
             self.v_ext[n0:n0 + n_g] = v_g
 
+    def _local_max_speed(self):
+        import torch
+        L, h = self._lib.load(), self.semi._handle
+        if getattr(self, "_vmax_bits", None) is None:
+            self._vmax_bits = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.semi._bind_stream()
+        self._lib.check(h, L.tpb_max_speed2(h, C.c_void_p(self.v_ext.data_ptr()), C.c_void_p(self._vmax_bits.data_ptr())))
+        return self._vmax_bits
+
+    def _reduce_max_speed(self):
+        """StateEquationAdaptiveCole: `update_speed_of_sound!` (wcsph/system.jl:307-321) takes the maximum
+        over ALL fluid particles -- the rank's max |v|^2 over its owned rows (one kernel), an integer MAX
+        all-reduce of the 8-byte bit pattern on the same stream, and the result is handed to the kick;
+        nothing waits for the host."""
+        import torch
+        import torch.distributed as dist
+        L, h = self._lib.load(), self.semi._handle
+        if isinstance(self.transport, LocalTransport) and self.world > 1:
+            # in-process ranks (two-phase kick): every rank has posted its word in kick_post
+            words = [self.transport.mb.box[("vmax", r)] for r in range(self.world)]
+            bits = torch.stack(words).max(dim=0).values
+        else:
+            bits = self._local_max_speed()
+            if self.world > 1:
+                dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=self.transport.group)
+        self._lib.check(h, L.tpb_set_max_speed2(h, C.c_void_p(bits.data_ptr())))
+        self._vmax_last = bits
+
     def _compute(self, dv_ode, t):
         L, h = self._lib.load(), self.semi._handle
         self.semi._bind_stream()
+        if self.adaptive_sound_speed:
+            self._reduce_max_speed()
         self._lib.check(h, L.tpb_kick(h, C.c_void_p(dv_ode.data_ptr()), C.c_void_p(self.v_ext.data_ptr()),
                                       C.c_void_p(self.u_ext.data_ptr()), float(t)))
 
@@ -793,6 +826,8 @@ class SlabSemidiscretization:
     def kick_post(self, v_ode, u_ode):
         self._stage_owned(v_ode, u_ode)
         self.halo.post(self.u_ext[: self.n_owned], self.v_ext[: self.n_owned])
+        if self.adaptive_sound_speed:
+            self.transport.mb.box[("vmax", self.rank)] = self._local_max_speed().clone()
 
     def kick_finish(self, dv_ode, t=0.0):
         self._install_ghosts(self.halo.collect(self.u_ext[: self.n_owned], self.v_ext[: self.n_owned]))

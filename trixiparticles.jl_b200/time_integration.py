@@ -336,7 +336,9 @@ def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
         step = dt
         if stop - t <= step * (1 + 1e-10):
             step = stop - t
-        if graph_ok and step == dt and not adaptive_eos:
+        # StateEquationAdaptiveCole: replayable when the speed of sound stays on the device and dt is fixed
+        if graph_ok and step == dt and (not adaptive_eos or
+                                        (stepsize is None and semi.adaptive_sound_speed_on_device())):
             if graph is None:
                 if not warmed:
                     run_stages(step)       # first regular step eagerly (one-time kernel attributes)
