@@ -140,9 +140,21 @@ typedef struct {
      * fluid (viscous_velocity, wall_boundary/system.jl:148-163).  Monaghan: alpha, beta, epsilon;
      * Morris / Adami: alpha = kinematic viscosity nu, epsilon. */
     int32_t has_viscosity;
-    int32_t reserved;
+    /* the boundary model's density calculator: TPB_WALL_DENSITY_ADAMI = AdamiPressureExtrapolation (and
+     * BernoulliPressureExtrapolation, the same thing for a static wall); TPB_WALL_DENSITY_CONTINUITY =
+     * ContinuityDensity (wall_boundary/rhs.jl:11-59, system.jl:78-90, :243-252; dummy_particles.jl:364-368,
+     * :458-478): the wall density is integrated -- the system contributes ONE entry per wall particle to
+     * v_ode / dv_ode (none to u_ode), pressure = state_equation(density) with the state equation's own
+     * clip flag (eos_clip_negative_pressure) and then the boundary model's, and kick! fills the wall rows
+     * of dv_ode with the continuity equation over the fluid neighbours.  Free-slip only; not combined
+     * with slab ghosts. */
+    int32_t density_calculator;
     double alpha, beta, epsilon;
+    int32_t eos_clip_negative_pressure; /* StateEquationCole{..., CLIP} of the boundary model (ContinuityDensity) */
+    int32_t reserved;
 } tpb_wall_params;
+#define TPB_WALL_DENSITY_ADAMI 0
+#define TPB_WALL_DENSITY_CONTINUITY 1
 
 /* `TotalLagrangianSPHSystem(ic; smoothing_kernel, smoothing_length, young_modulus, poisson_ratio,
  * clamped_particles, acceleration, penalty_force=PenaltyForceGanzenmueller(alpha), boundary_model=

@@ -54,7 +54,11 @@ def wall_params(wall) -> O.WallParams:
     p.exponent = float(t(se.exponent))
     p.reference_density = float(t(se.reference_density))
     p.background_pressure = float(t(se.background_pressure))
-    p.pressure_offset = float(t(m.density_calculator.pressure_offset))
+    p.eos_clip_negative_pressure = int(getattr(se, "clip_negative_pressure", False))
+    if type(m.density_calculator).__name__ == "ContinuityDensity":
+        p.density_calculator = O.WALL_CONTINUITY
+    else:
+        p.pressure_offset = float(t(m.density_calculator.pressure_offset))
     visc = getattr(m, "viscosity", None)
     if visc is not None:   # no-slip wall
         p.has_viscosity = int(getattr(visc, "viscosity_id", 1))
@@ -89,8 +93,17 @@ def kick(fluid, wall, u, v, use_grid=True, nthreads=0, fluid_wall_interaction=Tr
         cw, mw = wall.coordinates, wall.boundary_model.hydrodynamic_mass
     else:
         wp, cw, mw = None, None, None
+    v_wall = None
+    if wp is not None and wp.density_calculator == O.WALL_CONTINUITY:
+        v = np.asarray(v)
+        nv = fluid.v_nvariables
+        if v.ndim == 1:      # the flat ODE vector [fluid | wall] (semidiscretization.jl:128-135)
+            v_wall = v[fluid.nparticles * nv:]
+            v = v[: fluid.nparticles * nv].reshape(-1, nv)
+        else:                # fluid rows only: the wall at its initial density
+            v_wall = np.asarray(wall.boundary_model.initial_density, dtype=fluid.eltype)
     return O.kick(fp, wp, fluid.mass, cw, mw, v, u, fluid.eltype, use_grid=use_grid,
-                  nthreads=nthreads)
+                  nthreads=nthreads, v_wall=v_wall)
 
 
 def structure_params(st) -> O.TlsphParams:

@@ -45,9 +45,12 @@ class WallParams(C.Structure):
         ("smoothing_length", C.c_double), ("sound_speed", C.c_double),
         ("exponent", C.c_double), ("reference_density", C.c_double),
         ("background_pressure", C.c_double), ("pressure_offset", C.c_double),
-        ("has_viscosity", C.c_int32), ("reserved1", C.c_int32),
+        ("has_viscosity", C.c_int32), ("density_calculator", C.c_int32),
         ("visc_alpha", C.c_double), ("visc_beta", C.c_double), ("visc_epsilon", C.c_double),
     ]
+
+
+WALL_ADAMI, WALL_CONTINUITY = 0, 1
 
 
 def build(force: bool = False) -> str:
@@ -239,7 +242,7 @@ def neighbor_pair_count(x, y, radius, dtype=None) -> int:
 # ---------------------------------------------------------------- kick! / drift!
 
 def kick(fp: FluidParams, wp, mass_f, coords_w, mass_w, v_ode, u_ode, dtype, use_grid=True,
-         nthreads=0):
+         nthreads=0, v_wall=None):
     """One `kick!` of Semidiscretization(fluid[, wall]).  Arrays are particle-major:
     u_ode (n_f, ND) coordinate dtype; v_ode (n_f, nv) dtype.  Returns a dict.
     use_grid: False = all pairs, True = cell lists built per call, 2 = timing mode: the static
@@ -264,18 +267,30 @@ def kick(fp: FluidParams, wp, mass_f, coords_w, mass_w, v_ode, u_ode, dtype, use
         mass_w = np.zeros(0, dtype=dtype)
         n_w = 0
         wpp = None
+    # BoundaryModelDummyParticles{ContinuityDensity}: the wall's density rows sit behind the fluid's rows
+    # (`v_wall`, n_w values); the result gains `dv_wall`
+    wall_cont = wpp is not None and wp.density_calculator == WALL_CONTINUITY
+    v_in, dv_flat = v_ode, None
+    if wall_cont:
+        v_wall = np.ascontiguousarray(v_wall, dtype=dtype)
+        assert v_wall.shape == (n_w,)
+        v_in = np.concatenate([v_ode.reshape(-1), v_wall])
+        dv_flat = np.full(v_in.shape, np.nan, dtype=dtype)
     out = dict(
         dv=np.zeros((n_f, nv), dtype=dtype), pressure=np.zeros(n_f, dtype=dtype),
         density=np.zeros(n_f, dtype=dtype), wall_pressure=np.zeros(n_w, dtype=dtype),
         wall_density=np.zeros(n_w, dtype=dtype), wall_volume=np.zeros(n_w, dtype=dtype),
         wall_velocity=np.zeros((n_w, nd), dtype=dtype))
     rc = getattr(lib(), f"orc_kick_noslip_{s}")(
-        C.byref(fp), wpp, n_f, _ptr(mass_f), n_w, _ptr(coords_w), _ptr(mass_w), _ptr(v_ode),
-        _ptr(u_ode), _ptr(out["dv"]), _ptr(out["pressure"]), _ptr(out["density"]),
+        C.byref(fp), wpp, n_f, _ptr(mass_f), n_w, _ptr(coords_w), _ptr(mass_w), _ptr(v_in),
+        _ptr(u_ode), _ptr(dv_flat if wall_cont else out["dv"]), _ptr(out["pressure"]), _ptr(out["density"]),
         _ptr(out["wall_pressure"]), _ptr(out["wall_density"]), _ptr(out["wall_volume"]),
         _ptr(out["wall_velocity"]), (2 if use_grid == 2 else int(bool(use_grid))), int(nthreads))
     if rc != 0:
         raise RuntimeError(f"orc_kick failed: {rc}")
+    if wall_cont:
+        out["dv"] = dv_flat[: n_f * nv].reshape(n_f, nv)
+        out["dv_wall"] = dv_flat[n_f * nv:]
     return out
 
 

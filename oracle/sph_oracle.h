@@ -69,9 +69,14 @@ typedef struct {
     /* boundary_model.viscosity (dummy_particles.jl:52-77): nothing = free-slip; any model = no-slip
      * wall (compute_wall_velocity!, :710-758).  Morris / Adami carry nu in `visc_alpha`. */
     int32_t has_viscosity; /* ORC_VISCOSITY_* */
-    int32_t reserved1;
+    /* boundary model's density calculator: 0 = AdamiPressureExtrapolation; ORC_WALL_CONTINUITY =
+     * ContinuityDensity (wall_boundary/rhs.jl:11-59): the wall density is integrated, v_ode / dv_ode
+     * carry one row per wall particle BEHIND the fluid's rows (systems in the order fluid, wall),
+     * pressure = state_equation(density) (dummy_particles.jl:458-478) */
+    int32_t density_calculator;
     double visc_alpha, visc_beta, visc_epsilon;
 } orc_wall_params;
+enum { ORC_WALL_ADAMI = 0, ORC_WALL_CONTINUITY = 1 };
 
 /* TotalLagrangianSPHSystem (structure/total_lagrangian_sph/system.jl:76-106) with scalar material
  * constants, PenaltyForceGanzenmueller (penalty_force.jl) and, for the coupling with a fluid, a

@@ -358,6 +358,65 @@ def test_kick_adaptive_cole(oracle, eltype, cdtype):
     assert float(se.sound_speed) == 100.0
 
 
+@pytest.mark.parametrize("config", ["dam_break_2d_f64", "dam_break_3d_f32", "dam_break_3d_f32_f64coords",
+                                    "dam_break_2d_f64_summation", "dam_break_2d_f64_host"])
+def test_kick_continuity_density_wall(oracle, config):
+    """`BoundaryModelDummyParticles(..., ContinuityDensity(), ...)` (wall_boundary/rhs.jl:11-59,
+    system.jl:78-90): the wall density is integrated.  The ODE vectors carry one row per wall particle
+    behind the fluid's rows; kick! takes the wall density from there, sets pressure = state_equation(density)
+    and fills the wall's rows of dv with the continuity equation over the fluid neighbours."""
+    host = config.endswith("_host")
+    if config.startswith("dam_break_2d"):
+        dc = tp.SummationDensity() if "summation" in config else tp.ContinuityDensity()
+        fluid, wall0, _ = examples.dam_break_2d(20, density_calculator=dc)
+    else:
+        cdt = np.float64 if "f64coords" in config else np.float32
+        fluid, wall0, _ = examples.dam_break_3d(0.1, eltype=np.float32, coordinates_eltype=cdt)
+    m0 = wall0.boundary_model
+    model = tp.BoundaryModelDummyParticles(m0.initial_density, m0.hydrodynamic_mass, tp.ContinuityDensity(),
+                                           m0.smoothing_kernel, m0.smoothing_length, state_equation=m0.state_equation,
+                                           clip_negative_pressure=True)
+    wall = tp.WallBoundarySystem(wall0.initial_condition, model)
+    nd, n_f, n_w = fluid.ndims, fluid.nparticles, wall.nparticles
+    u, v = examples.perturbed_state(fluid)
+    rng = np.random.default_rng(5)
+    rho_w = (model.initial_density * (1 + rng.uniform(-0.01, 0.01, n_w))).astype(fluid.eltype)
+    v_ode = np.concatenate([v.reshape(-1), rho_w])
+    ref = adapter.kick(fluid, wall, u, v_ode)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(
+        ode_memory="host" if host else "device"))
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    assert semi.ranges_v == ((0, v.size), (v.size, v.size + n_w)) and semi.ranges_u[1] == (u.size, u.size)
+    v0 = ode.v0 if host else ode.v0.cpu().numpy()
+    np.testing.assert_array_equal(v0[v.size:], model.initial_density)           # write_v0! (system.jl:243-252)
+    if host:
+        dv = np.full_like(v_ode, np.nan)
+        du = np.full(u.size, np.nan, dtype=u.dtype)
+        tp.kick_(dv, v_ode, np.ascontiguousarray(u).reshape(-1), ode.p, 0.0)
+        tp.drift_(du, v_ode, np.ascontiguousarray(u).reshape(-1), ode.p, 0.0)
+    else:
+        import torch
+        dev = ode.u0.device
+        v_d, u_d = torch.from_numpy(v_ode).to(dev), torch.from_numpy(u.reshape(-1)).to(dev)
+        dv_d, du_d = torch.full_like(v_d, float("nan")), torch.full_like(u_d, float("nan"))
+        ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
+        ode.f2(du_d, v_d, u_d, ode.p, 0.0)
+        semi.synchronize()
+        dv, du = dv_d.cpu().numpy(), du_d.cpu().numpy()
+    tol = TOL[np.dtype(fluid.eltype)]
+    got_f, got_w = dv[: v.size].reshape(v.shape), dv[v.size:]
+    assert np.isfinite(dv).all()
+    assert rel_inf(got_f[:, :nd], ref["dv"][:, :nd]) <= tol
+    if v.shape[1] > nd:
+        assert rel_inf(got_f[:, nd], ref["dv"][:, nd]) <= tol
+    assert np.abs(ref["dv_wall"]).max() > 0
+    assert rel_inf(got_w, ref["dv_wall"]) <= tol
+    np.testing.assert_array_equal(du.reshape(u.shape), v[:, :nd].astype(u.dtype))
+    np.testing.assert_array_equal(semi.system_field(wall, "density"), rho_w)
+    assert rel_inf(semi.system_field(wall, "pressure"), ref["wall_pressure"]) <= tol
+    semi.close()
+
+
 def test_adaptive_cole_device_path_equals_host_path(monkeypatch):
     """The speed of sound stays on the device (k_max_speed2 -> k_adaptive_consts -> the kernels read
     AdaptConsts; no host round trip, so the kick can be captured in a CUDA graph); TPB_ADAPTIVE_HOST

@@ -193,6 +193,75 @@ def test_peer_memory_halo_matches_nccl_and_single_gpu():
         assert err <= 1e-5, (block, err)
 
 
+def _adaptive_worker(rank, world, port, out):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        fluid, wall, _ = examples.dam_break_3d(0.05, adaptive_sound_speed=True)
+        u, v = examples.perturbed_state(fluid)
+        v[int(np.argmax(u[:, 0])), :3] = np.float32(4.0)      # the fastest particle lives on the last rank
+        slab = SlabSemidiscretization(fluid, wall, rank=rank, world=world, device=rank)
+        ode = slab.semidiscretize((0.0, 1.0))
+        dev = ode.u0.device
+        ode.u0.copy_(torch.from_numpy(u[slab.owned_index].reshape(-1)).to(dev))
+        ode.v0.copy_(torch.from_numpy(v[slab.owned_index].reshape(-1)).to(dev))
+        dv = torch.full_like(ode.v0, float("nan"))
+        for _ in range(2):
+            ode.f1(dv, ode.v0, ode.u0, ode.p, 0.0)
+        c = slab.semi.sound_speed()
+        out.put((rank, dv.cpu().numpy().reshape(-1, v.shape[1]), slab.owned_index.copy(), c))
+        dist.barrier()
+        slab.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(400)
+def test_two_gpu_adaptive_cole_matches_single_gpu():
+    """StateEquationAdaptiveCole on two GPUs: max |v|^2 of every rank, an NCCL integer MAX all-reduce on
+    the compute stream, tpb_set_max_speed2 -- both ranks arrive at the single-GPU speed of sound."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    fluid, wall, _ = examples.dam_break_3d(0.05, adaptive_sound_speed=True)
+    u, v = examples.perturbed_state(fluid)
+    v[int(np.argmax(u[:, 0])), :3] = np.float32(4.0)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    dev = ode.u0.device
+    dv_d = torch.full((v.size,), float("nan"), dtype=torch.float32, device=dev)
+    ode.f1(dv_d, torch.from_numpy(v.reshape(-1)).to(dev), torch.from_numpy(u.reshape(-1)).to(dev), ode.p, 0.0)
+    c_ref = semi.sound_speed()
+    ref = dv_d.cpu().numpy().reshape(v.shape)
+    semi.close()
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_adaptive_worker, args=(r, world, port, out), daemon=True) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = np.full_like(ref, np.nan)
+    for _ in range(world):
+        rank, dv, owned, c = out.get(timeout=240)
+        assert c == c_ref, (rank, c, c_ref)
+        got[owned] = dv
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for block in (slice(0, 3), slice(3, 4)):
+        err = np.abs(got[:, block] - ref[:, block]).max() / np.abs(ref[:, block]).max()
+        assert err <= 1e-5, (block, err)
+
+
 def _loop_worker(rank, world, port, out, n_steps, dt):
     import os
     import torch

@@ -105,7 +105,7 @@ def test_abi_library_exports_header_symbols():
     # struct sizes agree between the ctypes mirror and the header (compile-time check in C)
     assert ctypes.sizeof(_lib.Config) == 4 * 10 + 8 * 6
     assert ctypes.sizeof(_lib.FluidParams) == 4 * 6 + 8 * 13 + 4 * 2 + 8 * 3   # + StateEquationAdaptiveCole fields
-    assert ctypes.sizeof(_lib.WallParams) == 4 * 4 + 8 * 6 + 4 * 2 + 8 * 3   # + wall viscosity (no-slip)
+    assert ctypes.sizeof(_lib.WallParams) == 4 * 4 + 8 * 6 + 4 * 2 + 8 * 3 + 4 * 2   # + wall viscosity (no-slip), + ContinuityDensity
 
 
 def test_abi_argument_errors_without_gpu():

@@ -404,6 +404,83 @@ def test_interact_conservation(oracle, seed, density_calculator):
     np.testing.assert_allclose(out_grid["dv"], out["dv"], rtol=1e-12, atol=1e-12 * np.abs(out["dv"]).max())
 
 
+def _continuity_wall_case(rng, density_calculator, eltype=np.float64):
+    """A perturbed 5 x 5 patch split at the centre particle into a fluid and a dummy-particle wall with
+    ContinuityDensity, as test/schemes/boundary/dummy_particles/rhs.jl:126-150 splits its 3 x 3 patch."""
+    dx = 0.1
+    ic = tp.RectangularShape(dx, (5, 5), (-2.5 * dx, -2.5 * dx), density=1000.0)
+    ic.coordinates += rng.uniform(-0.3 * dx, 0.3 * dx, ic.coordinates.shape)
+    ic.mass += rng.uniform(-0.1, 0.1, ic.nparticles) * ic.mass[0]
+    ic.density += rng.uniform(-0.1, 0.1, ic.nparticles) * 1000.0
+    ic.velocity += rng.uniform(-1.0, 1.0, ic.velocity.shape)
+    c = int(np.ceil(ic.nparticles / 2))
+    part = lambda sl: tp.InitialCondition(coordinates=ic.coordinates[sl].astype(eltype),
+                                          velocity=ic.velocity[sl].astype(eltype), mass=ic.mass[sl].astype(eltype),
+                                          density=ic.density[sl].astype(eltype),
+                                          pressure=np.zeros(len(ic.mass[sl]), dtype=eltype), particle_spacing=dx)
+    f_ic, w_ic = part(slice(0, c)), part(slice(c, None))
+    se = tp.StateEquationCole(sound_speed=10.0, reference_density=1000.0, exponent=7)
+    kernel, h = tp.SchoenbergCubicSplineKernel(2), 1.2 * dx
+    fluid = tp.WeaklyCompressibleSPHSystem(f_ic, smoothing_kernel=kernel, smoothing_length=h,
+                                           density_calculator=density_calculator, state_equation=se)
+    model = tp.BoundaryModelDummyParticles(w_ic.density, w_ic.mass, tp.ContinuityDensity(), kernel, h,
+                                           state_equation=se)
+    wall = tp.WallBoundarySystem(w_ic, model)
+    cont = isinstance(density_calculator, tp.ContinuityDensity)
+    v_f = np.concatenate([f_ic.velocity, f_ic.density[:, None]], axis=1) if cont else f_ic.velocity.copy()
+    rho_w = (w_ic.density * (1 + rng.uniform(-0.02, 0.02, w_ic.nparticles))).astype(eltype)   # the integrated density has moved
+    return fluid, wall, f_ic, w_ic, v_f, rho_w
+
+
+# test/schemes/boundary/dummy_particles/rhs.jl:13-308, "Fluid-BoundaryDummyContinuityDensity": with the
+# continuity equation solved for the dummy particles too, fluid + wall conserve the total energy
+#   sum_a m_a (v_a . dv_a + p_a / rho_a^2 drho_a) = 0
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_continuity_density_wall_conserves_total_energy(oracle, seed):
+    rng = np.random.default_rng(seed)
+    fluid, wall, f_ic, w_ic, v_f, rho_w = _continuity_wall_case(rng, tp.ContinuityDensity())
+    v_ode = np.concatenate([v_f.reshape(-1), rho_w])
+    out = adapter.kick(fluid, wall, f_ic.coordinates, v_ode, use_grid=False)
+    assert wall.n_integrated_particles == wall.nparticles and wall.v_nvariables == 1 and wall.u_nvariables == 0
+    np.testing.assert_array_equal(out["wall_density"], rho_w)          # current_density = the wall's rows of v
+    se = wall.boundary_model.state_equation
+    np.testing.assert_allclose(out["wall_pressure"], [se(r) for r in rho_w], rtol=1e-14)
+    dv, drho_f, drho_w = out["dv"][:, :2], out["dv"][:, 2], out["dv_wall"]
+    assert np.abs(drho_w).max() > 0
+    e_f = f_ic.mass * ((f_ic.velocity * dv).sum(axis=1) + out["pressure"] / out["density"] ** 2 * drho_f)
+    e_w = w_ic.mass * (out["wall_pressure"] / rho_w ** 2 * drho_w)      # v_wall = 0: no kinetic part
+    scale = max(np.abs(e_f).max(), np.abs(e_w).max())
+    assert abs(e_f.sum() + e_w.sum()) <= 1e-13 * scale
+    # the cell-list search gives the same sums up to their order
+    out_grid = adapter.kick(fluid, wall, f_ic.coordinates, v_ode, use_grid=True)
+    np.testing.assert_allclose(out_grid["dv_wall"], drho_w, rtol=1e-12, atol=1e-12 * np.abs(drho_w).max())
+
+
+@pytest.mark.parametrize("density_calculator", [tp.ContinuityDensity(), tp.SummationDensity()])
+def test_continuity_density_wall_rhs_matches_pair_formula(oracle, density_calculator):
+    """wall_boundary/rhs.jl:11-79 restated pair by pair in numpy: drho_a = sum_b [rho_a / rho_b] m_b
+    (0 - v_b) . grad W(x_a - x_b) with the boundary model's kernel; the bracket only for a fluid with
+    ContinuityDensity (rhs.jl:63-79)."""
+    rng = np.random.default_rng(11)
+    fluid, wall, f_ic, w_ic, v_f, rho_w = _continuity_wall_case(rng, density_calculator)
+    cont = isinstance(density_calculator, tp.ContinuityDensity)
+    v_ode = np.concatenate([v_f.reshape(-1), rho_w])
+    out = adapter.kick(fluid, wall, f_ic.coordinates, v_ode, use_grid=False)
+    h = float(wall.boundary_model.smoothing_length)
+    R = 2 * h
+    expected = np.zeros(w_ic.nparticles)
+    for a in range(w_ic.nparticles):
+        for b in range(f_ic.nparticles):
+            pd = w_ic.coordinates[a] - f_ic.coordinates[b]
+            r = np.sqrt(pd @ pd)
+            if pd @ pd > R * R or r < np.sqrt(np.spacing(h * h)):
+                continue
+            grad = oracle.kernel_deriv_div_r(1, 2, r, h) * pd
+            term = f_ic.mass[b] * ((0.0 - f_ic.velocity[b]) @ grad)
+            expected[a] += (rho_w[a] / out["density"][b]) * term if cont else term
+    np.testing.assert_allclose(out["dv_wall"], expected, rtol=1e-12, atol=1e-12 * np.abs(expected).max())
+
+
 # test/general/density_calculator.jl:30-31: lone particle, rho === m W(0)
 def test_summation_density_lone_particle(oracle):
     ic = tp.RectangularShape(0.1, (1, 1), (0.0, 0.0), density=1000.0)

@@ -64,9 +64,13 @@ class WallParams(C.Structure):
         ("sound_speed_from_fluid", C.c_int32), ("smoothing_length", C.c_double), ("sound_speed", C.c_double),
         ("exponent", C.c_double), ("reference_density", C.c_double),
         ("background_pressure", C.c_double), ("pressure_offset", C.c_double),
-        ("has_viscosity", C.c_int32), ("reserved", C.c_int32),
+        ("has_viscosity", C.c_int32), ("density_calculator", C.c_int32),
         ("alpha", C.c_double), ("beta", C.c_double), ("epsilon", C.c_double),
+        ("eos_clip_negative_pressure", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+WALL_DENSITY_ADAMI, WALL_DENSITY_CONTINUITY = 0, 1
 
 
 class StructureParams(C.Structure):

@@ -120,26 +120,34 @@ inline void prof_mark(Semi &s, int ph)
 inline size_t tsize(int eltype) { return eltype == TPB_F64 ? 8 : 4; }
 
 // ODE layout (`ranges_u` / `ranges_v`, semidiscretization.jl:128-135): systems in call order; the
-// fluid holds ND (u) and NV (v) entries per active particle, the wall none, the structure ND each
-// per integrated particle.  Offsets / totals in elements.
+// fluid holds ND (u) and NV (v) entries per active particle, the structure ND each per integrated
+// particle, the wall none -- except dummy particles with ContinuityDensity, whose density is integrated
+// (one v entry per wall particle, wall_boundary/system.jl:78-90).  Offsets / totals in elements.
 struct OdeLayout {
-    int64_t off_u_f = 0, off_v_f = 0, off_u_s = 0, off_v_s = 0, tot_u = 0, tot_v = 0;
+    int64_t off_u_f = 0, off_v_f = 0, off_u_s = 0, off_v_s = 0, off_v_w = 0, len_v_w = 0, tot_u = 0, tot_v = 0;
 };
+inline bool wall_integrates_density(const Semi &s)
+{
+    return s.wall_index >= 0 && s.wp.density_calculator == TPB_WALL_DENSITY_CONTINUITY;
+}
 inline OdeLayout ode_layout(const Semi &s)
 {
     const int nd = s.cfg.ndims;
     const int nvars = s.fp.density_calculator == TPB_DENSITY_SUMMATION ? nd : nd + 1;
     OdeLayout L;
-    const int64_t fu = s.n_act * nd, fv = s.n_act * nvars, su = s.n_s_int * nd;
-    if (s.struct_index >= 0 && s.struct_index < s.fluid_index) {
-        L.off_u_f = su;
-        L.off_v_f = su;
-    } else {
-        L.off_u_s = fu;
-        L.off_v_s = fv;
+    L.len_v_w = wall_integrates_density(s) ? s.n_w : 0;
+    for (int sys = 0; sys < s.n_systems; ++sys) {
+        if (sys == s.fluid_index) {
+            L.off_u_f = L.tot_u, L.off_v_f = L.tot_v;
+            L.tot_u += s.n_act * nd, L.tot_v += s.n_act * nvars;
+        } else if (sys == s.struct_index) {
+            L.off_u_s = L.tot_u, L.off_v_s = L.tot_v;
+            L.tot_u += s.n_s_int * nd, L.tot_v += s.n_s_int * nd;
+        } else if (sys == s.wall_index) {
+            L.off_v_w = L.tot_v;
+            L.tot_v += L.len_v_w;
+        }
     }
-    L.tot_u = fu + (s.struct_index >= 0 ? su : 0);
-    L.tot_v = fv + (s.struct_index >= 0 ? su : 0);
     return L;
 }
 
@@ -381,7 +389,8 @@ struct Ops {
         if (n > 0)
             LAUNCH(s, (k_cell_count<ND, CT>), cdiv(n, 256), 256, 0, d_u, n, (int)s.n_tgt, g, s.d_key, s.d_slot,
                    s.d_count, s.d_flags);
-        const bool wall = s.n_w > 0;
+        const bool has_wall = s.n_w > 0;                           // a second neighbour set for the fluid tiles
+        const bool wall = has_wall && !wall_integrates_density(s);  // Adami walls: sort the wall tiles as well
         LAUNCH(s, k_scan_cells_tiles, s.scan_blocks, SCAN_THREADS, 0, s.d_count, s.ncell[0], s.tiles.nrows,
                s.scan_rows_per_block, s.d_scan_ticket, s.d_scan_status, s.d_fcell_start,
                s.tiles.d_frow_tile_start, s.tiles.d_ftile_desc, wall ? s.tiles.d_n_wactive : (int *)nullptr);
@@ -391,7 +400,7 @@ struct Ops {
         if (wall) wpa = wall_prep_args(s);
         LAUNCH(s, (k_post_scan<ND, T, CT>), nb_scatter + nb_ranges + nb_wprep, 256, 0, nb_scatter, nb_ranges, s.d_key,
                s.d_slot, s.d_fcell_start, n, s.d_tmp_perm, g, s.tiles.d_frow_tile_start + s.tiles.nrows,
-               s.tiles.d_ftile_desc, wall ? s.d_wcell_start : (const int *)nullptr, s.tiles.d_ftile_rng,
+               s.tiles.d_ftile_desc, has_wall ? s.d_wcell_start : (const int *)nullptr, s.tiles.d_ftile_rng,
                s.tiles.d_ftile_ext, wpa);
         s.wall_prep_done = wall;
         return TPB_OK;
@@ -1023,7 +1032,16 @@ struct Ops {
             else launch_summation<3>(s, g, pc, eos);
         }
         prof_mark(s, TPB_PHASE_BOUNDARY);
-        if (s.n_w > 0) {
+        if (s.n_w > 0 && wall_integrates_density(s)) {
+            // BoundaryModelDummyParticles{ContinuityDensity}: density = the wall's rows of v_ode,
+            // pressure = state_equation(density) (dummy_particles.jl:364-368, :458-478)
+            EosConst<T> weos = make_eos_const<T>(s.wp.sound_speed, s.wp.exponent, s.wp.reference_density,
+                                                 s.wp.background_pressure, s.wp.eos_clip_negative_pressure,
+                                                 s.wp.sound_speed_from_fluid && s.fp.adaptive_params_f32);
+            LAUNCH(s, (k_wall_density_eos<T>), cdiv(s.n_w, 256), 256, 0, (int)s.n_w, d_v_ode + lay.off_v_w, s.d_perm_w,
+                   weos, s.wp.clip_negative_pressure, (V2<T> *)s.d_Ww, (T *)s.d_volw,
+                   s.wp.sound_speed_from_fluid ? (const AdaptConsts<T> *)s.ad_kick : (const AdaptConsts<T> *)nullptr);
+        } else if (s.n_w > 0) {
             rc = wk == 0   ? launch_adami<0>(s, g)
                  : wk == 1 ? launch_adami<1>(s, g)
                  : wk == 2 ? launch_adami<2>(s, g)
@@ -1070,6 +1088,24 @@ struct Ops {
                 rc = summ ? interact_structure<3, 1>(s, g, pc, d_dv, d_dv_s) : interact_structure<3, 0>(s, g, pc, d_dv, d_dv_s);
             if (rc) return rc;
         }
+        if (s.n_w > 0 && wall_integrates_density(s)) {
+            // interact!(wall, fluid): the continuity equation of the dummy particles (wall_boundary/rhs.jl:11-59)
+            KernelConst<T> wkern = make_kernel_const<T>(s.wp.kernel, ND, s.wp.smoothing_length);
+            const T Rw = wkern.support;
+            const T az = (T)std::sqrt(eps_of<T>(wkern.h * wkern.h));
+            T *d_dv_w = d_dv_ode + lay.off_v_w;
+            auto go = [&](auto kernel_tag) {
+                constexpr int K = decltype(kernel_tag)::value;
+                LAUNCH(s, (k_wall_continuity<ND, T, CT, K>), cdiv(s.n_w, 128), 128, 0, (int)s.n_w, g,
+                       (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, s.d_perm_w, s.d_fcell_start,
+                       (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.interaction[1][0], wkern, (T)(Rw * Rw), az,
+                       (int)summ, d_dv_w);
+            };
+            if (wk == 0) go(std::integral_constant<int, 0>());
+            else if (wk == 1) go(std::integral_constant<int, 1>());
+            else if (wk == 2) go(std::integral_constant<int, 2>());
+            else go(std::integral_constant<int, 3>());
+        }
         prof_mark(s, TPB_PHASE_END);
         if (s.prof_capacity > 0 && s.prof_kicks < s.prof_capacity) s.prof_kicks++;
         CUDA_TRY(&s, cudaGetLastError());
@@ -1114,7 +1150,7 @@ struct Ops {
         // (slab handles drift their owned rows only: n_tgt, not n_act)
         OdeLayout lay = ode_layout(s);
         const int64_t total_f = s.n_tgt * ND, total_s = s.struct_index >= 0 ? s.n_s_int * ND : 0;
-        if (s.struct_index < 0) lay.tot_u = total_f, lay.tot_v = s.n_tgt * nv(s);
+        if (s.struct_index < 0 && lay.len_v_w == 0) lay.tot_u = total_f, lay.tot_v = s.n_tgt * nv(s);
         const size_t nu = sizeof(CT) * (size_t)lay.tot_u, nvb = sizeof(T) * (size_t)lay.tot_v;
         s.launches_this_call = 0;
         if (total_f + total_s == 0) return TPB_OK;
@@ -1509,6 +1545,10 @@ int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *p, int64_t n
     if (n < 0 || n > 0x7fffffff / 4) return fail(s, TPB_ERR_INVALID_ARGUMENT, "particle count out of range");
     if (p->has_viscosity < TPB_VISCOSITY_NONE || p->has_viscosity > TPB_VISCOSITY_ADAMI)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown wall viscosity model");
+    if (p->density_calculator != TPB_WALL_DENSITY_ADAMI && p->density_calculator != TPB_WALL_DENSITY_CONTINUITY)
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown wall density calculator");
+    if (p->density_calculator == TPB_WALL_DENSITY_CONTINUITY && p->has_viscosity != TPB_VISCOSITY_NONE)
+        return fail(s, TPB_ERR_UNSUPPORTED, "a no-slip wall with ContinuityDensity is not supported");
     s->wp = *p;
     s->n_w = n;
     const size_t ts = tsize(s->cfg.eltype), cs = tsize(s->cfg.coords_eltype);
@@ -1700,9 +1740,10 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     if (s->cfg.ode_memory == TPB_MEM_HOST) {
         // staging copies of the whole ODE vectors (fluid + structure entries)
         const size_t extra = s->struct_index >= 0 ? (size_t)nd * (size_t)s->n_s_int : 0;
+        const size_t extra_w = wall_integrates_density(*s) ? (size_t)s->n_w : 0;  // the wall's density rows
         CUDA_TRY(s, cudaMalloc(&s->d_u, cs * (nd * nf + extra)));
-        CUDA_TRY(s, cudaMalloc(&s->d_v, ts * (nvars * nf + extra)));
-        CUDA_TRY(s, cudaMalloc(&s->d_dv, ts * (nvars * nf + extra)));
+        CUDA_TRY(s, cudaMalloc(&s->d_v, ts * (nvars * nf + extra + extra_w)));
+        CUDA_TRY(s, cudaMalloc(&s->d_dv, ts * (nvars * nf + extra + extra_w)));
         CUDA_TRY(s, cudaMalloc(&s->d_du, cs * (nd * nf + extra)));
     }
     if (s->struct_index >= 0) {
@@ -1736,7 +1777,12 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
         const int n0 = s->ncell[0], nrows = s->ncell[1] * s->ncell[2];
         if (n0 <= SCAN_TILE && !getenv("TPB_SCAN3")) {
             s->scan_rows_per_block = std::max(1, std::min(SCAN_TILE / n0, CSCAN_MAX_ROWS));
+            if (s->scan_rows_per_block >= 4) s->scan_rows_per_block &= ~3;  // 16-byte aligned block starts
             s->scan_blocks = cdiv(nrows, s->scan_rows_per_block);
+            // (both running totals share one status word: 29 bits of particles, 24 bits of tiles)
+            if ((int64_t)(s->n_f + 127) / 128 + nrows >= (1 << 24)) s->scan_blocks = 0;
+        }
+        if (s->scan_blocks > 0) {
             CUDA_TRY(s, cudaMalloc(&s->d_scan_status, sizeof(unsigned long long) * 2 * (size_t)s->scan_blocks));
             CUDA_TRY(s, cudaMemset(s->d_scan_status, 0, sizeof(unsigned long long) * 2 * (size_t)s->scan_blocks));
             CUDA_TRY(s, cudaMalloc(&s->d_scan_ticket, sizeof(unsigned long long) * 2));
@@ -1818,11 +1864,13 @@ int32_t tpb_system_range(tpb_semi_t semi, int32_t system, int64_t *u_first, int6
     } else if (system == s->struct_index) {
         uf = lay.off_u_s, ul = s->n_s_int * nd, vf = lay.off_v_s, vl = s->n_s_int * nd;
     } else {
-        // the wall has no integrated particles: a zero-length range where its entries would start
+        // the wall: no u entries (a zero-length range where they would start); v entries only with
+        // ContinuityDensity dummy particles
         for (int other = 0; other < system; ++other) {
-            if (other == s->fluid_index) uf += s->n_act * nd, vf += s->n_act * nvars;
-            if (other == s->struct_index) uf += s->n_s_int * nd, vf += s->n_s_int * nd;
+            if (other == s->fluid_index) uf += s->n_act * nd;
+            if (other == s->struct_index) uf += s->n_s_int * nd;
         }
+        vf = lay.off_v_w, vl = lay.len_v_w;
     }
     if (u_first) *u_first = uf;
     if (u_len) *u_len = ul;
@@ -1951,6 +1999,8 @@ int32_t tpb_set_fluid_count(tpb_semi_t semi, int64_t n_active, int64_t n_targets
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "need 0 <= n_targets <= n_active <= capacity of the fluid system");
     if (n_targets < n_active && s->fp.density_calculator == TPB_DENSITY_SUMMATION)
         return fail(s, TPB_ERR_UNSUPPORTED, "ghost particles need ContinuityDensity (their density travels with them)");
+    if (n_targets < n_active && wall_integrates_density(*s))
+        return fail(s, TPB_ERR_UNSUPPORTED, "slab ghosts are not combined with a ContinuityDensity wall");
     if (s->struct_index >= 0 && (n_active != s->n_f || n_targets != s->n_f))
         return fail(s, TPB_ERR_UNSUPPORTED, "slab ghosts are not combined with a structure system");
     s->n_act = n_active;

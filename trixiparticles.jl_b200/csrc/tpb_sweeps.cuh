@@ -126,6 +126,69 @@ k_adami(int n_w, GridConst<CT> g, const V4<CT> *__restrict__ Aw,
     volume[w] = vol;
 }
 
+// ------------------------------------------------------------------ dummy particles with ContinuityDensity
+// The wall density is integrated (wall_boundary/system.jl:78-90): it arrives in the wall's rows of v_ode
+// (ODE order), pressure = state_equation(density), clipped by the boundary model's own flag
+// (compute_pressure!, apply_state_equation!, dummy_particles.jl:458-478).  Fills the sorted wall records
+// (p, rho) the fluid's sweep reads.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_wall_density_eos(int n_w, const T *__restrict__ v_wall, const int *__restrict__ perm_w, EosConst<T> eos,
+                   int clip, V2<T> *__restrict__ W, T *__restrict__ volume, const AdaptConsts<T> *__restrict__ ad)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_w) return;
+    if (ad) eos.B = ad->B_w;
+    const T rho = v_wall[perm_w[w]];
+    T p = eos_pressure(eos, rho);
+    if (clip) p = p > (T)0 ? p : (T)0;
+    V2<T> out;
+    out.x = p;
+    out.y = rho;
+    W[w] = out;
+    volume[w] = (T)0;
+}
+
+// interact!(wall, fluid) of such a wall (wall_boundary/rhs.jl:11-59): the continuity equation of every wall
+// particle over its fluid neighbours with the WALL's kernel and smoothing length, v_a = 0 (static wall),
+// almostzero = sqrt(eps(h_wall^2)); the fluid's density calculator picks the form (rhs.jl:63-79).  One
+// thread per sorted wall particle; dv_wall is in ODE order and written exactly once (set_zero! included).
+template <int ND, typename T, typename CT, int KERNEL>
+__global__ void __launch_bounds__(128)
+k_wall_continuity(int n_w, GridConst<CT> g, const V4<CT> *__restrict__ Aw, const V2<T> *__restrict__ Ww,
+                  const int *__restrict__ perm_w, const int *__restrict__ fcell_start,
+                  const V4<CT> *__restrict__ A, const V4<T> *__restrict__ B, int interaction_enabled,
+                  KernelConst<T> kern, T radius2, T almostzero, int fluid_summation, T *__restrict__ dv_wall)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_w) return;
+    const V4<CT> xi = Aw[w];
+    const T rho_a = Ww[w].y;
+    int cx, cy, cz;
+    cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    T drho = (T)0;
+    if (interaction_enabled) {
+        for_neighbor_rows<ND, CT>(g, fcell_start, cx, cy, cz, [&](int j0, int j1) {
+            for (int j = j0; j < j1; ++j) {
+                const V4<CT> xj = A[j];
+                T pd[3];
+                const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                if (d2 > radius2) continue;
+                const T dist = sqrt_rn(d2);
+                if (dist < almostzero) continue;
+                const T wdr = SmoothingKernel<KERNEL, T>::dw_div_r(kern, dist);
+                const V4<T> bj = B[j];
+                // dot(v_a - v_b, grad_kernel), v_a = 0, grad_kernel = wdr * pos_diff
+                T vg = ((T)0 - bj.x) * (wdr * pd[0]) + ((T)0 - bj.y) * (wdr * pd[1]);
+                if (ND == 3) vg += ((T)0 - bj.z) * (wdr * pd[2]);
+                const T m_b = (T)xj.w;
+                drho += fluid_summation ? m_b * vg : rho_a / bj.w * m_b * vg;
+            }
+        });
+    }
+    dv_wall[perm_w[w]] = drho;
+}
+
 // ------------------------------------------------------------------ interact! (variant 1)
 template <typename T>
 struct SourceConst {

@@ -161,7 +161,8 @@ k_row_tile_table(const int *__restrict__ cell_start, int n0, int nrows, int *__r
 // tiles -- through a decoupled look-back (status words carry the number of the launch, so nothing has
 // to be reset between launches; blocks take a ticket, so a block only ever waits for blocks that
 // have already started).  The histogram is cleared on the way out for the next rebuild.
-//   status[2 b + w]: bits 63..34 epoch, 33..32 flag (1: aggregate of block b, 2: inclusive prefix), 31..0 value
+//   status[b]: bits 63..55 launch number, 54..53 flag (1: aggregate of block b, 2: inclusive prefix),
+//              52..24 particles, 23..0 tiles
 constexpr int CSCAN_MAX_ROWS = 2 * SCAN_THREADS;  // rows per block (two per thread)
 __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v)
 {
@@ -188,7 +189,7 @@ k_scan_cells_tiles(int *__restrict__ count, int n0, int nrows, int rows_per_bloc
         const unsigned long long t = atomicAdd(ticket, 1ull);
         const unsigned long long launch = t / gridDim.x;
         s_bid = (int)(t - launch * gridDim.x);
-        s_epoch = 1u + (unsigned)(launch % 0x3FFFFFFEull);
+        s_epoch = 1u + (unsigned)(launch % 510ull);  // 9 bits; a stale word always carries the previous launch
     }
     __syncthreads();
     const int bid = s_bid;
@@ -198,16 +199,31 @@ k_scan_cells_tiles(int *__restrict__ count, int n0, int nrows, int rows_per_bloc
     const int cells_here = rows_here * n0;
     int *const cnt_blk = count + (int64_t)r0 * n0;
     const int base = threadIdx.x * SCAN_ITEMS;
+    static_assert(SCAN_ITEMS == 8, "two int4 per thread");
+    // 16-byte accesses where the block's first cell allows it (rows_per_block is a multiple of four whenever
+    // it can be): a warp then touches whole sectors -- with 4-byte accesses at a stride of 32 bytes every
+    // store is a partial-sector write, and a 29 M-cell grid (the end slab of the 8-GPU run) took 0.39 ms
+    const bool vec = ((((int64_t)r0 * n0) & 3) == 0) && base + SCAN_ITEMS <= cells_here;
     int v[SCAN_ITEMS];
     int sum = 0;
+    if (vec) {
+        const int4 a = reinterpret_cast<const int4 *>(cnt_blk + base)[0];
+        const int4 b = reinterpret_cast<const int4 *>(cnt_blk + base)[1];
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        v[k] = base + k < cells_here ? cnt_blk[base + k] : 0;
-        sum += v[k];
+        for (int k = 0; k < SCAN_ITEMS; ++k) sum += v[k];
+        reinterpret_cast<int4 *>(cnt_blk + base)[0] = make_int4(0, 0, 0, 0);
+        reinterpret_cast<int4 *>(cnt_blk + base)[1] = make_int4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            v[k] = base + k < cells_here ? cnt_blk[base + k] : 0;
+            sum += v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (base + k < cells_here) cnt_blk[base + k] = 0;
     }
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k)
-        if (base + k < cells_here) cnt_blk[base + k] = 0;
     int total_c;
     const int run0 = block_inclusive_scan(sum, total_c) - sum;  // local exclusive prefix of cell `base`
     {
@@ -231,40 +247,50 @@ k_scan_cells_tiles(int *__restrict__ count, int n0, int nrows, int rows_per_bloc
     }
     int total_t;
     const int trun0 = block_inclusive_scan(tsum, total_t) - tsum;
-    if (threadIdx.x < 32) {
-        // warp 0: publish the block's aggregates, then look back 32 predecessors at a time
-        const unsigned long long ep = (unsigned long long)epoch << 34;
-        const int lane = threadIdx.x;
-        int off[2] = {0, 0};
-        if (bid > 0) {
-            if (lane < 2) st_release_u64(&status[2 * bid + lane], ep | (1ull << 32) | (unsigned)(lane == 0 ? total_c : total_t));
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                for (int p0 = bid - 1; p0 >= 0; p0 -= 32) {
-                    const int p = p0 - lane;
-                    unsigned long long sw = 2ull << 32;  // blocks before the first one: an empty inclusive prefix
-                    if (p >= 0) {
-                        do {
-                            sw = ld_acquire_u64(&status[2 * p + w]);
-                        } while ((unsigned)(sw >> 34) != epoch || ((sw >> 32) & 3ull) == 0);
-                    }
-                    // lanes up to (and including) the nearest block that already knows its inclusive prefix
-                    const unsigned incl = __ballot_sync(0xffffffffu, ((sw >> 32) & 3ull) == 2);
-                    const int stop = incl ? __ffs(incl) - 1 : 31;
-                    int val = lane <= stop ? (int)(unsigned)sw : 0;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-                    off[w] += val;
-                    if (incl) break;
-                }
+    {
+        // Publish the block's aggregate, then look back with the WHOLE block: thread t reads the status of
+        // predecessor bid - 1 - t, so the window covers every block that can be resident at once and the
+        // look-back is one round trip (with one warp looking back 32 at a time a block spent most of its
+        // life here: 0.39 ms for the 29 M cells of the end slab of the 8-GPU run).  Both totals travel in
+        // one word: [63:55] launch number, [54:53] flag, [52:24] particles, [23:0] tiles.
+        __shared__ unsigned long long w_sum[32];
+        __shared__ int w_incl[32];
+        const unsigned long long FIELD = (1ull << 53) - 1;
+        const unsigned long long ep = (unsigned long long)epoch << 55;
+        const unsigned long long mine = ((unsigned long long)(unsigned)total_c << 24) | (unsigned)total_t;
+        if (threadIdx.x == 0 && bid > 0) st_release_u64(&status[bid], ep | (1ull << 53) | mine);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        unsigned long long off = 0;
+        bool found = false;
+        for (int p0 = bid - 1; !found; p0 -= SCAN_THREADS) {
+            const int p = p0 - (int)threadIdx.x;
+            unsigned long long sw = 2ull << 53;  // before the first block: an empty inclusive prefix
+            if (p >= 0) {
+                do {
+                    sw = ld_acquire_u64(&status[p]);
+                } while ((unsigned)(sw >> 55) != epoch || ((sw >> 53) & 3ull) == 0);
             }
+            const unsigned incl = __ballot_sync(0xffffffffu, ((sw >> 53) & 3ull) == 2);
+            const int stop = incl ? __ffs(incl) - 1 : 31;
+            unsigned long long val = lane <= stop ? (sw & FIELD) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            if (lane == 0) {
+                w_sum[wid] = val;
+                w_incl[wid] = incl != 0;
+            }
+            __syncthreads();
+            // every thread walks the 32 warp results (nearest predecessors first) -- uniform, no broadcast
+            for (int w = 0; w < SCAN_THREADS / 32 && !found; ++w) {
+                off += w_sum[w];
+                found = w_incl[w] != 0;
+            }
+            __syncthreads();
         }
-        if (lane < 2)
-            st_release_u64(&status[2 * bid + lane],
-                           ep | (2ull << 32) | (unsigned)(lane == 0 ? off[0] + total_c : off[1] + total_t));
-        if (lane == 0) {
-            s_off[0] = off[0];
-            s_off[1] = off[1];
+        if (threadIdx.x == 0) {
+            st_release_u64(&status[bid], ep | (2ull << 53) | (off + mine));
+            s_off[0] = (int)(off >> 24);
+            s_off[1] = (int)(off & 0xFFFFFFull);
             if (bid == 0 && zero_word) *zero_word = 0;
         }
     }
@@ -273,10 +299,21 @@ k_scan_cells_tiles(int *__restrict__ count, int n0, int nrows, int rows_per_bloc
     {
         int *const cs_blk = cell_start + (int64_t)r0 * n0;
         int run = off_c + run0;
+        if (vec) {
+            int e[SCAN_ITEMS];
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) {
-            if (base + k < cells_here) cs_blk[base + k] = run;
-            run += v[k];
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                e[k] = run;
+                run += v[k];
+            }
+            reinterpret_cast<int4 *>(cs_blk + base)[0] = make_int4(e[0], e[1], e[2], e[3]);
+            reinterpret_cast<int4 *>(cs_blk + base)[1] = make_int4(e[4], e[5], e[6], e[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                if (base + k < cells_here) cs_blk[base + k] = run;
+                run += v[k];
+            }
         }
     }
     const bool last_block = r0 + rows_here == nrows;

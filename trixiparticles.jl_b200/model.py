@@ -261,14 +261,19 @@ class WeaklyCompressibleSPHSystem:
 
 
 class BoundaryModelDummyParticles:
-    """dummy_particles.jl:52-113 with `AdamiPressureExtrapolation`."""
+    """dummy_particles.jl:52-113 with `AdamiPressureExtrapolation` (`BernoulliPressureExtrapolation` is the
+    same thing for a static wall) or `ContinuityDensity` (the wall density is integrated: one row of the
+    ODE vector per wall particle, wall_boundary/rhs.jl:11-59, system.jl:78-90)."""
 
     def __init__(self, initial_density, hydrodynamic_mass, density_calculator, smoothing_kernel,
                  smoothing_length, *, viscosity=None, state_equation=None, correction=None,
                  clip_negative_pressure=False, reference_particle_spacing=0.0):
-        if not isinstance(density_calculator, (AdamiPressureExtrapolation, BernoulliPressureExtrapolation)):
-            raise ValueError("only `AdamiPressureExtrapolation` / `BernoulliPressureExtrapolation` are on "
-                             "the accelerated path")
+        if not isinstance(density_calculator, (AdamiPressureExtrapolation, BernoulliPressureExtrapolation,
+                                               ContinuityDensity)):
+            raise ValueError("only `AdamiPressureExtrapolation` / `BernoulliPressureExtrapolation` / "
+                             "`ContinuityDensity` are on the accelerated path")
+        if isinstance(density_calculator, ContinuityDensity) and viscosity is not None:
+            raise ValueError("a no-slip wall with `ContinuityDensity` is outside the accelerated path")
         if correction is not None:
             raise ValueError("wall `correction` is outside the accelerated hot path")
         if viscosity is not None and not isinstance(viscosity, (ArtificialViscosityMonaghan, ViscosityMorris,
@@ -276,7 +281,7 @@ class BoundaryModelDummyParticles:
             raise ValueError("wall `viscosity` must be ArtificialViscosityMonaghan, ViscosityMorris or "
                              "ViscosityAdami on the accelerated path")
         if state_equation is None:
-            raise ValueError("`AdamiPressureExtrapolation` needs a `state_equation`")
+            raise ValueError("the boundary model needs a `state_equation`")
         self.initial_density = np.asarray(initial_density)
         self.hydrodynamic_mass = np.asarray(hydrodynamic_mass)
         assert self.initial_density.shape == self.hydrodynamic_mass.shape
@@ -307,7 +312,10 @@ class WallBoundarySystem:
 
     ndims = property(lambda self: self.initial_condition.ndims)
     nparticles = property(lambda self: self.initial_condition.nparticles)
-    n_integrated_particles = property(lambda self: 0)  # wall_boundary/system.jl:78-90
+    # wall_boundary/system.jl:78-90: nothing is integrated, except the density of dummy particles with
+    # `ContinuityDensity` (one v variable per particle, no u variable)
+    integrates_density = property(lambda self: isinstance(self.boundary_model.density_calculator, ContinuityDensity))
+    n_integrated_particles = property(lambda self: self.nparticles if self.integrates_density else 0)
     u_nvariables = property(lambda self: 0)
     v_nvariables = property(lambda self: 1)
 

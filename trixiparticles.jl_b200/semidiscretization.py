@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan,
+from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan, ContinuityDensity,
                     DensityDiffusionMolteniColagrossi, SourceTermDamping, StateEquationAdaptiveCole,
                     SummationDensity, TotalLagrangianSPHSystem, WallBoundarySystem,
                     WeaklyCompressibleSPHSystem)
@@ -190,7 +190,11 @@ class Semidiscretization:
         p.exponent = float(t(se.exponent))
         p.reference_density = float(t(se.reference_density))
         p.background_pressure = float(t(se.background_pressure))
-        p.pressure_offset = float(t(m.density_calculator.pressure_offset))
+        if isinstance(m.density_calculator, ContinuityDensity):
+            p.density_calculator = _lib.WALL_DENSITY_CONTINUITY
+            p.eos_clip_negative_pressure = int(getattr(se, "clip_negative_pressure", False))
+        else:
+            p.pressure_offset = float(t(m.density_calculator.pressure_offset))
         if m.viscosity is not None:   # no-slip wall
             p.has_viscosity = int(getattr(m.viscosity, "viscosity_id", 1))
             if p.has_viscosity == 1:
@@ -450,6 +454,10 @@ def semidiscretize(semi: Semidiscretization, tspan) -> DynamicalODEProblem:
             continue
         u = semi.wrap_u(u0, s)
         v = semi.wrap_v(v0, s)
+        if isinstance(s, WallBoundarySystem):
+            # write_v0! of dummy particles with ContinuityDensity (wall_boundary/system.jl:243-252)
+            v[:, 0] = s.boundary_model.initial_density
+            continue
         if isinstance(s, TotalLagrangianSPHSystem):
             # write_u0! / write_v0! (total_lagrangian_sph/system.jl:588-612): integrated particles only
             n_int = s.n_integrated_particles

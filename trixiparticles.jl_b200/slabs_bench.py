@@ -343,7 +343,8 @@ def run(args):
             "parity_check": parity,
             "clocks": main["clocks"], "e2e": main["e2e"],
             "gpu_launches": main["launches_per_rank"] * world,
-            "roofline": {"bound": "hbm", "bound_actual": "shared-memory pipe / issue slots (pair sweep)",
+            "roofline": {"bound": "hbm", "bound_measured": "smem_pipe",
+                         "bound_actual": "shared-memory pipe / issue slots (pair sweep)",
                          "kernel": "interact! phase, slowest rank", "achieved": achieved,
                          "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "peak_source": peak_src,
                          "traffic": None, "kernel_ms": k_ms,
