@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python tools/profile_end_slab.py 8 0.00271442 10 2>&1 | tail -3
+
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r2l_endslab.csv python tools/profile_end_slab.py 8 0.00271442 3 > gpurun_out/ncu_r2l.log 2>&1; echo "ncu rc=$?"
 python - <<'PY'
 import csv,collections

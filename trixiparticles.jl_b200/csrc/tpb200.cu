@@ -391,7 +391,7 @@ struct Ops {
                    s.d_count, s.d_flags);
         const bool has_wall = s.n_w > 0;                           // a second neighbour set for the fluid tiles
         const bool wall = has_wall && !wall_integrates_density(s);  // Adami walls: sort the wall tiles as well
-        LAUNCH(s, k_scan_cells_tiles, s.scan_blocks, SCAN_THREADS, 0, s.d_count, s.ncell[0], s.tiles.nrows,
+        LAUNCH(s, k_scan_cells_tiles, s.scan_blocks, CSCAN_THREADS, 0, s.d_count, s.ncell[0], s.tiles.nrows,
                s.scan_rows_per_block, s.d_scan_ticket, s.d_scan_status, s.d_fcell_start,
                s.tiles.d_frow_tile_start, s.tiles.d_ftile_desc, wall ? s.tiles.d_n_wactive : (int *)nullptr);
         const int nb_scatter = cdiv(n, 256), nb_ranges = cdiv((int64_t)s.tiles.max_ftiles * 32, 256);
@@ -1775,12 +1775,18 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     {
         // k_scan_cells_tiles: whole cell rows per block
         const int n0 = s->ncell[0], nrows = s->ncell[1] * s->ncell[2];
-        if (n0 <= SCAN_TILE && !getenv("TPB_SCAN3")) {
-            s->scan_rows_per_block = std::max(1, std::min(SCAN_TILE / n0, CSCAN_MAX_ROWS));
+        if (n0 <= CSCAN_TILE && !getenv("TPB_SCAN3")) {
+            s->scan_rows_per_block = std::max(1, std::min(CSCAN_TILE / n0, CSCAN_MAX_ROWS));
             if (s->scan_rows_per_block >= 4) s->scan_rows_per_block &= ~3;  // 16-byte aligned block starts
             s->scan_blocks = cdiv(nrows, s->scan_rows_per_block);
             // (both running totals share one status word: 29 bits of particles, 24 bits of tiles)
             if ((int64_t)(s->n_f + 127) / 128 + nrows >= (1 << 24)) s->scan_blocks = 0;
+            // Large, mostly empty grids (the end slab of the 8-GPU config-4 run: 29 M cells for 12.5 M
+            // particles) are faster through the separate kernels: there the one-pass kernel takes 0.39 ms
+            // against 0.20 ms for the three-kernel scan (measured, profiles/r2_p_end_slab.txt), while at
+            // 4.5 M cells (10 M particles) it wins.
+            const char *lim = getenv("TPB_SCAN_FUSED_MAX_CELLS");
+            if (s->ncells > (lim ? atoll(lim) : 12000000ll)) s->scan_blocks = 0;
         }
         if (s->scan_blocks > 0) {
             CUDA_TRY(s, cudaMalloc(&s->d_scan_status, sizeof(unsigned long long) * 2 * (size_t)s->scan_blocks));

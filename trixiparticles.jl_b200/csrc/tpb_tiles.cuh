@@ -163,18 +163,26 @@ k_row_tile_table(const int *__restrict__ cell_start, int n0, int nrows, int *__r
 // have already started).  The histogram is cleared on the way out for the next rebuild.
 //   status[b]: bits 63..55 launch number, 54..53 flag (1: aggregate of block b, 2: inclusive prefix),
 //              52..24 particles, 23..0 tiles
-constexpr int CSCAN_MAX_ROWS = 2 * SCAN_THREADS;  // rows per block (two per thread)
-__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v)
+#ifndef TPB_CSCAN_THREADS
+#define TPB_CSCAN_THREADS 1024  // measured: 1024 > 512 > 256 (fewer, larger blocks)
+#endif
+constexpr int CSCAN_THREADS = TPB_CSCAN_THREADS;
+constexpr int CSCAN_TILE = CSCAN_THREADS * SCAN_ITEMS;
+constexpr int CSCAN_MAX_ROWS = 2 * CSCAN_THREADS;  // rows per block (two per thread)
+// The status word IS the message (no other data is handed over through it), so relaxed device-scope
+// accesses are enough: `ld.acquire.gpu` in the polling loop costs a CCTL.IVALL (L1 invalidation) per
+// poll -- 31 % of the kernel's stall samples in the first version -- and `st.release.gpu` a MEMBAR.
+__device__ __forceinline__ void st_status_u64(unsigned long long *p, unsigned long long v)
 {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+__device__ __forceinline__ unsigned long long ld_status_u64(const unsigned long long *p)
 {
     unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-static __global__ void __launch_bounds__(SCAN_THREADS)
+static __global__ void __launch_bounds__(CSCAN_THREADS)
 k_scan_cells_tiles(int *__restrict__ count, int n0, int nrows, int rows_per_block,
                    unsigned long long *__restrict__ ticket, unsigned long long *__restrict__ status,
                    int *__restrict__ cell_start, int *__restrict__ row_tile_start, int4 *__restrict__ desc,
@@ -258,16 +266,16 @@ k_scan_cells_tiles(int *__restrict__ count, int n0, int nrows, int rows_per_bloc
         const unsigned long long FIELD = (1ull << 53) - 1;
         const unsigned long long ep = (unsigned long long)epoch << 55;
         const unsigned long long mine = ((unsigned long long)(unsigned)total_c << 24) | (unsigned)total_t;
-        if (threadIdx.x == 0 && bid > 0) st_release_u64(&status[bid], ep | (1ull << 53) | mine);
+        if (threadIdx.x == 0 && bid > 0) st_status_u64(&status[bid], ep | (1ull << 53) | mine);
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         unsigned long long off = 0;
         bool found = false;
-        for (int p0 = bid - 1; !found; p0 -= SCAN_THREADS) {
+        for (int p0 = bid - 1; !found; p0 -= CSCAN_THREADS) {
             const int p = p0 - (int)threadIdx.x;
             unsigned long long sw = 2ull << 53;  // before the first block: an empty inclusive prefix
             if (p >= 0) {
                 do {
-                    sw = ld_acquire_u64(&status[p]);
+                    sw = ld_status_u64(&status[p]);
                 } while ((unsigned)(sw >> 55) != epoch || ((sw >> 53) & 3ull) == 0);
             }
             const unsigned incl = __ballot_sync(0xffffffffu, ((sw >> 53) & 3ull) == 2);
@@ -281,14 +289,14 @@ k_scan_cells_tiles(int *__restrict__ count, int n0, int nrows, int rows_per_bloc
             }
             __syncthreads();
             // every thread walks the 32 warp results (nearest predecessors first) -- uniform, no broadcast
-            for (int w = 0; w < SCAN_THREADS / 32 && !found; ++w) {
+            for (int w = 0; w < CSCAN_THREADS / 32 && !found; ++w) {
                 off += w_sum[w];
                 found = w_incl[w] != 0;
             }
             __syncthreads();
         }
         if (threadIdx.x == 0) {
-            st_release_u64(&status[bid], ep | (2ull << 53) | (off + mine));
+            st_status_u64(&status[bid], ep | (2ull << 53) | (off + mine));
             s_off[0] = (int)(off >> 24);
             s_off[1] = (int)(off & 0xFFFFFFull);
             if (bid == 0 && zero_word) *zero_word = 0;
