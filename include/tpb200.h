@@ -201,7 +201,12 @@ int32_t tpb_destroy(tpb_semi_t semi);
  * (semidiscretization.jl:128-135).  `mass`: T[n].  Arrays are host pointers, copied. */
 int32_t tpb_add_fluid_system(tpb_semi_t semi, const tpb_fluid_params *params, int64_t n,
                              const void *mass, int32_t *system_index);
-/* `coords`: cT[ND x n]; `hydrodynamic_mass`, `initial_density`: T[n]. */
+/* `coords`: cT[ND x n]; `hydrodynamic_mass`, `initial_density`: T[n].  Several wall systems may be added
+ * (e.g. tank and obstacle as separate `WallBoundarySystem`s, semidiscretization.jl:813-829 loops over all
+ * ordered pairs) as long as their boundary models are the same (all tpb_wall_params fields equal; not with
+ * ContinuityDensity): inside the library they form one static wall set, every system keeps its own index
+ * for tpb_get_system_field / tpb_system_range / tpb_set_interaction (whose switches towards the fluid must
+ * agree between the walls).  Different boundary models: TPB_ERR_UNSUPPORTED. */
 int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *params, int64_t n,
                             const void *coords, const void *hydrodynamic_mass,
                             const void *initial_density, int32_t *system_index);

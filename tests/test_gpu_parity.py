@@ -417,6 +417,54 @@ def test_kick_continuity_density_wall(oracle, config):
     semi.close()
 
 
+def _split_wall(wall, mask):
+    """The particles `mask` of a WallBoundarySystem as a system of their own (same boundary model)."""
+    ic, m = wall.initial_condition, wall.boundary_model
+    part = tp.InitialCondition(coordinates=ic.coordinates[mask], velocity=ic.velocity[mask], mass=ic.mass[mask],
+                               density=ic.density[mask], pressure=ic.pressure[mask],
+                               particle_spacing=ic.particle_spacing)
+    model = tp.BoundaryModelDummyParticles(m.initial_density[mask], m.hydrodynamic_mass[mask], m.density_calculator,
+                                           m.smoothing_kernel, m.smoothing_length, state_equation=m.state_equation,
+                                           viscosity=m.viscosity, clip_negative_pressure=m.clip_negative_pressure)
+    return tp.WallBoundarySystem(part, model)
+
+
+@pytest.mark.parametrize("no_slip", [False, True])
+def test_kick_several_wall_systems(oracle, no_slip):
+    """`Semidiscretization(fluid, floor, side_walls)`: the reference loops over all ordered pairs of systems
+    (semidiscretization.jl:813-829), wall <-> wall never interact (wall_boundary/rhs.jl:2-8), so two
+    WallBoundarySystems with the same boundary model give the fluid exactly the sums one system holding all
+    their particles gives; every system reports its own fields."""
+    fluid, wall, _ = examples.dam_break_3d(0.1)
+    if no_slip:
+        wall.boundary_model.viscosity = tp.ViscosityAdami(nu=0.01)
+    floor = wall.coordinates[:, 2] < 0
+    w_floor, w_sides = _split_wall(wall, floor), _split_wall(wall, ~floor)
+    assert w_floor.nparticles > 0 and w_sides.nparticles > 0
+    u, v = examples.perturbed_state(fluid)
+    ref = adapter.kick(fluid, wall, u, v)
+    semi = tp.Semidiscretization(w_floor, fluid, w_sides, parallelization_backend=tp.B200Backend())
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    assert semi.ranges_v == ((0, 0), (0, v.size), (v.size, v.size))
+    dv = np.full(v.size, np.nan, dtype=v.dtype)
+    tp.kick_(dv, v.reshape(-1).copy(), np.ascontiguousarray(u).reshape(-1), ode.p, 0.0)
+    dv = dv.reshape(v.shape)
+    tol = TOL[np.dtype(fluid.eltype)]
+    assert rel_inf(dv[:, :3], ref["dv"][:, :3]) <= tol and rel_inf(dv[:, 3], ref["dv"][:, 3]) <= tol
+    for part, mask in ((w_floor, floor), (w_sides, ~floor)):
+        assert rel_inf(semi.system_field(part, "pressure"), ref["wall_pressure"][mask]) <= 10 * tol
+        assert rel_inf(semi.system_field(part, "density"), ref["wall_density"][mask]) <= tol
+        if no_slip:
+            assert rel_inf(semi.system_field(part, "wall_velocity"), ref["wall_velocity"][mask]) <= 10 * tol
+    semi.close()
+    # different boundary models are refused, not silently merged
+    other = _split_wall(wall, ~floor)
+    other.boundary_model.smoothing_length = other.boundary_model.smoothing_length * np.float32(1.1)
+    with pytest.raises(Exception, match="different boundary models"):
+        tp.semidiscretize(tp.Semidiscretization(fluid, w_floor, other, parallelization_backend=tp.B200Backend()),
+                          (0.0, 1.0))
+
+
 def test_adaptive_cole_device_path_equals_host_path(monkeypatch):
     """The speed of sound stays on the device (k_max_speed2 -> k_adaptive_consts -> the kernels read
     AdaptConsts; no host round trip, so the kick can be captured in a CUDA graph); TPB_ADAPTIVE_HOST

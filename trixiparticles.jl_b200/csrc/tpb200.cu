@@ -40,6 +40,21 @@ struct Semi {
     // systems (one fluid, at most one wall; numbered in call order)
     int n_systems = 0;
     int fluid_index = -1, wall_index = -1;
+    // several WallBoundarySystems with the same boundary model are ONE static wall set inside the library
+    // (the fluid sums over all wall particles alike; wall <-> wall never interact): `wall_index` is the
+    // first one, every system keeps its own index, particle range and interaction switches
+    struct WallPart {
+        int index;
+        int64_t first, n;
+        int fluid_from_wall = 1, wall_from_fluid = 1;
+    };
+    std::vector<WallPart> wall_parts;
+    const WallPart *wall_part(int system) const
+    {
+        for (const WallPart &w : wall_parts)
+            if (w.index == system) return &w;
+        return nullptr;
+    }
     tpb_fluid_params fp{};
     tpb_wall_params wp{};
     int64_t n_f = 0, n_w = 0;   // n_f: capacity of the fluid system (particles allocated)
@@ -1188,17 +1203,19 @@ struct Ops {
     {
         if (field == TPB_FIELD_WALL_VELOCITY) {
             // ND x n_w values; not on the hot path: a buffer of its own
-            if (system != s.wall_index || !s.d_Vw)
+            const Semi::WallPart *part = s.wall_part(system);
+            if (!part || !s.d_Vw)
                 return fail(&s, TPB_ERR_INVALID_ARGUMENT, "wall_velocity: the system is not a wall with a viscosity model");
-            if (n != s.n_w) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
+            if (n != part->n) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
             if (n == 0) return TPB_OK;
             T *d_tmp = nullptr;
-            const size_t bytes = sizeof(T) * ND * (size_t)n;
+            const size_t bytes = sizeof(T) * ND * (size_t)s.n_w;
             CUDA_TRY(&s, cudaMalloc(&d_tmp, bytes));
             cudaMemsetAsync(d_tmp, 0, bytes, s.stream);
-            LAUNCH(s, (k_unsort_vector<T>), cdiv(n, 256), 256, 0, (int)n, s.d_wcell_start + s.ncells, s.d_perm_w,
+            LAUNCH(s, (k_unsort_vector<T>), cdiv(s.n_w, 256), 256, 0, (int)s.n_w, s.d_wcell_start + s.ncells, s.d_perm_w,
                    (const V4<T> *)s.d_Vw, ND, d_tmp);
-            cudaError_t e = cudaMemcpyAsync(out, d_tmp, bytes, cudaMemcpyDeviceToHost, s.stream);
+            cudaError_t e = cudaMemcpyAsync(out, d_tmp + ND * part->first, sizeof(T) * ND * (size_t)n,
+                                            cudaMemcpyDeviceToHost, s.stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
             cudaFree(d_tmp);
             CUDA_TRY(&s, e);
@@ -1226,17 +1243,21 @@ struct Ops {
                 LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_fcell_start + s.ncells, s.d_perm_f, (const T *)s.d_B, 4, 3, scratch);
             else
                 return fail(&s, TPB_ERR_INVALID_ARGUMENT, "unknown fluid field");
-        } else if (system == s.wall_index) {
-            if (n != s.n_w) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
+        } else if (const Semi::WallPart *part = s.wall_part(system)) {
+            // the wall set is unsorted as a whole, the system's own particles are a slice of it
+            if (n != part->n) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
             if (n == 0) return TPB_OK;
+            const int nw = (int)s.n_w;
+            CUDA_TRY(&s, cudaMemsetAsync(scratch, 0, sizeof(T) * (size_t)nw, s.stream));
             if (field == TPB_FIELD_PRESSURE)
-                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_wcell_start + s.ncells, s.d_perm_w, (const T *)s.d_Ww, 2, 0, scratch);
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(nw, 256), 256, 0, nw, s.d_wcell_start + s.ncells, s.d_perm_w, (const T *)s.d_Ww, 2, 0, scratch);
             else if (field == TPB_FIELD_DENSITY)
-                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_wcell_start + s.ncells, s.d_perm_w, (const T *)s.d_Ww, 2, 1, scratch);
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(nw, 256), 256, 0, nw, s.d_wcell_start + s.ncells, s.d_perm_w, (const T *)s.d_Ww, 2, 1, scratch);
             else if (field == TPB_FIELD_VOLUME)
-                LAUNCH(s, (k_unsort_scalar<T>), cdiv(n, 256), 256, 0, (int)n, s.d_wcell_start + s.ncells, s.d_perm_w, (const T *)s.d_volw, 1, 0, scratch);
+                LAUNCH(s, (k_unsort_scalar<T>), cdiv(nw, 256), 256, 0, nw, s.d_wcell_start + s.ncells, s.d_perm_w, (const T *)s.d_volw, 1, 0, scratch);
             else
                 return fail(&s, TPB_ERR_INVALID_ARGUMENT, "unknown wall field");
+            scratch += part->first;
         } else {
             return fail(&s, TPB_ERR_INVALID_ARGUMENT, "unknown system index");
         }
@@ -1265,6 +1286,8 @@ struct Ops {
         if (rc) return rc;
         GridConst<CT> g = make_grid_const<CT>(s);
         const bool x_fluid = system == s.fluid_index, y_fluid = neighbor == s.fluid_index;
+        if (s.wall_parts.size() > 1 && (!x_fluid || !y_fluid))
+            return fail(&s, TPB_ERR_UNSUPPORTED, "tpb_neighbor_pairs with several wall systems: fluid-fluid pairs only");
         if ((!x_fluid && system != s.wall_index) || (!y_fluid && neighbor != s.wall_index))
             return fail(&s, TPB_ERR_INVALID_ARGUMENT, "unknown system index");
         // radius of the ordered pair: compact_support(system, neighbor)
@@ -1536,8 +1559,22 @@ int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *p, int64_t n
     if (s->ready) return fail(s, TPB_ERR_STATE, "systems must be added before tpb_semidiscretize");
     if (p->struct_size != (int32_t)sizeof(tpb_wall_params))
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "tpb_wall_params.struct_size mismatch");
-    if (s->wall_index >= 0)
-        return fail(s, TPB_ERR_UNSUPPORTED, "only one wall system per semidiscretization is supported");
+    if (s->wall_index >= 0) {
+        // a further WallBoundarySystem joins the wall set if its boundary model is the same
+        const tpb_wall_params &a = s->wp, &b = *p;
+        const bool same = a.kernel == b.kernel && a.clip_negative_pressure == b.clip_negative_pressure &&
+                          a.sound_speed_from_fluid == b.sound_speed_from_fluid && a.smoothing_length == b.smoothing_length &&
+                          a.sound_speed == b.sound_speed && a.exponent == b.exponent &&
+                          a.reference_density == b.reference_density && a.background_pressure == b.background_pressure &&
+                          a.pressure_offset == b.pressure_offset && a.has_viscosity == b.has_viscosity &&
+                          a.density_calculator == b.density_calculator && a.alpha == b.alpha && a.beta == b.beta &&
+                          a.epsilon == b.epsilon && a.eos_clip_negative_pressure == b.eos_clip_negative_pressure;
+        if (!same)
+            return fail(s, TPB_ERR_UNSUPPORTED, "wall systems with different boundary models are not supported "
+                                                "(kernel, smoothing length, state equation, viscosity, density calculator)");
+        if (a.density_calculator == TPB_WALL_DENSITY_CONTINUITY)
+            return fail(s, TPB_ERR_UNSUPPORTED, "only one wall system with ContinuityDensity is supported");
+    }
     if (p->kernel < TPB_KERNEL_WENDLAND_C2 || p->kernel > TPB_KERNEL_SCHOENBERG_QUINTIC)
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown smoothing kernel");
     if (!(p->smoothing_length > 0) || !(p->sound_speed > 0) || !(p->reference_density > 0) || p->exponent == 0)
@@ -1549,14 +1586,23 @@ int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *p, int64_t n
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown wall density calculator");
     if (p->density_calculator == TPB_WALL_DENSITY_CONTINUITY && p->has_viscosity != TPB_VISCOSITY_NONE)
         return fail(s, TPB_ERR_UNSUPPORTED, "a no-slip wall with ContinuityDensity is not supported");
+    if (s->n_w + n > 0x7fffffff / 4) return fail(s, TPB_ERR_INVALID_ARGUMENT, "particle count out of range");
     s->wp = *p;
-    s->n_w = n;
     const size_t ts = tsize(s->cfg.eltype), cs = tsize(s->cfg.coords_eltype);
-    s->h_coords_w.assign((const unsigned char *)coords, (const unsigned char *)coords + cs * s->cfg.ndims * (size_t)n);
-    s->h_mass_w.assign((const unsigned char *)hydrodynamic_mass, (const unsigned char *)hydrodynamic_mass + ts * (size_t)n);
-    s->h_dens_w.assign((const unsigned char *)initial_density, (const unsigned char *)initial_density + ts * (size_t)n);
-    s->wall_index = s->n_systems++;
-    if (system_index) *system_index = s->wall_index;
+    auto append = [](std::vector<unsigned char> &v, const void *src, size_t bytes) {
+        v.insert(v.end(), (const unsigned char *)src, (const unsigned char *)src + bytes);
+    };
+    append(s->h_coords_w, coords, cs * s->cfg.ndims * (size_t)n);
+    append(s->h_mass_w, hydrodynamic_mass, ts * (size_t)n);
+    append(s->h_dens_w, initial_density, ts * (size_t)n);
+    Semi::WallPart part;
+    part.index = s->n_systems++;
+    part.first = s->n_w;
+    part.n = n;
+    s->wall_parts.push_back(part);
+    s->n_w += n;
+    if (s->wall_index < 0) s->wall_index = part.index;
+    if (system_index) *system_index = part.index;
     return TPB_OK;
 }
 
@@ -1611,9 +1657,14 @@ int32_t tpb_set_interaction(tpb_semi_t semi, int32_t system, int32_t neighbor, i
         else if (system == s->fluid_index && neighbor == s->struct_index) s->struct_fluid[1] = enabled ? 1 : 0;
         return TPB_OK;
     }
-    // internal matrix is indexed [fluid=0|wall=1]
+    // internal matrix is indexed [fluid=0|wall=1]; the walls of the set must agree (tpb_semidiscretize)
     int a = system == s->fluid_index ? 0 : 1, b = neighbor == s->fluid_index ? 0 : 1;
-    s->interaction[a][b] = enabled ? 1 : 0;
+    if (a == 1 && b == 1) return TPB_OK;  // wall <-> wall: never interact (wall_boundary/rhs.jl:2-8)
+    for (Semi::WallPart &w : s->wall_parts) {
+        if (a == 0 && b == 1 && w.index == neighbor) w.fluid_from_wall = enabled ? 1 : 0;
+        if (a == 1 && b == 0 && w.index == system) w.wall_from_fluid = enabled ? 1 : 0;
+    }
+    if (a == 0 && b == 0) s->interaction[0][0] = enabled ? 1 : 0;
     return TPB_OK;
 }
 
@@ -1623,6 +1674,14 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
     if (s->ready) return fail(s, TPB_ERR_STATE, "tpb_semidiscretize was already called");
     if (s->fluid_index < 0) return fail(s, TPB_ERR_INVALID_ARGUMENT, "a fluid system is required");
+    for (const Semi::WallPart &w : s->wall_parts) {
+        const Semi::WallPart &w0 = s->wall_parts.front();
+        if (w.fluid_from_wall != w0.fluid_from_wall || w.wall_from_fluid != w0.wall_from_fluid)
+            return fail(s, TPB_ERR_UNSUPPORTED, "the wall systems of one semidiscretization must share their "
+                                                "interaction switches with the fluid");
+        s->interaction[0][1] = w0.fluid_from_wall;
+        s->interaction[1][0] = w0.wall_from_fluid;
+    }
     if (s->wall_index >= 0 && s->wp.has_viscosity >= TPB_VISCOSITY_MORRIS && s->fp.has_viscosity == TPB_VISCOSITY_NONE)
         return fail(s, TPB_ERR_INVALID_ARGUMENT,
                     "a ViscosityMorris / ViscosityAdami wall needs a fluid viscosity model: "
@@ -1873,10 +1932,10 @@ int32_t tpb_system_range(tpb_semi_t semi, int32_t system, int64_t *u_first, int6
         // the wall: no u entries (a zero-length range where they would start); v entries only with
         // ContinuityDensity dummy particles
         for (int other = 0; other < system; ++other) {
-            if (other == s->fluid_index) uf += s->n_act * nd;
-            if (other == s->struct_index) uf += s->n_s_int * nd;
+            if (other == s->fluid_index) uf += s->n_act * nd, vf += s->n_act * nvars;
+            if (other == s->struct_index) uf += s->n_s_int * nd, vf += s->n_s_int * nd;
         }
-        vf = lay.off_v_w, vl = lay.len_v_w;
+        if (lay.len_v_w > 0) vf = lay.off_v_w, vl = lay.len_v_w;
     }
     if (u_first) *u_first = uf;
     if (u_len) *u_len = ul;

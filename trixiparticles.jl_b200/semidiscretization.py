@@ -72,9 +72,9 @@ class Semidiscretization:
         if len(fluids) + len(walls) + len(structures) != len(systems):
             raise ValueError("only WeaklyCompressibleSPHSystem, WallBoundarySystem and TotalLagrangianSPHSystem "
                              "are on the accelerated path")
-        if len(fluids) != 1 or len(walls) > 1 or len(structures) > 1:
-            raise ValueError("the accelerated path takes exactly one fluid system, at most one wall system and "
-                             "at most one structure system")
+        if len(fluids) != 1 or len(structures) > 1:
+            raise ValueError("the accelerated path takes exactly one fluid system, any number of wall systems "
+                             "with the same boundary model and at most one structure system")
         nd = {s.ndims for s in systems}
         if len(nd) != 1:
             raise ValueError("all systems must have the same number of dimensions")
