@@ -166,6 +166,8 @@ typedef struct {
  * (clamped_particles_motion = nothing). */
 #define TPB_BOUNDARY_NONE 0            /* boundary_model = nothing: no coupling with the fluid */
 #define TPB_BOUNDARY_MONAGHAN_KAJTAR 1
+#define TPB_BOUNDARY_DUMMY_PARTICLES 2 /* BoundaryModelDummyParticles{AdamiPressureExtrapolation} on the structure
+                                        * (examples/fsi/hydrostatic_water_column_2d.jl:109-124): bm_* below */
 typedef struct {
     int32_t struct_size;
     int32_t kernel;            /* TPB_KERNEL_* */
@@ -176,6 +178,12 @@ typedef struct {
     double penalty_alpha;
     double acceleration[3];
     double mk_K, mk_beta, mk_spacing; /* BoundaryModelMonaghanKajtar */
+    /* TPB_BOUNDARY_DUMMY_PARTICLES: the boundary model's kernel, smoothing length, state equation, pressure
+     * offset and clip flag (dummy_particles.jl:52-77); free-slip (no viscosity) */
+    int32_t bm_kernel, bm_clip_negative_pressure;
+    double bm_smoothing_length;
+    double bm_sound_speed, bm_exponent, bm_reference_density, bm_background_pressure;
+    double bm_pressure_offset;
 } tpb_structure_params;
 
 /* launch/traffic accounting of the last kick (what bench.py reports as gpu_launches) */

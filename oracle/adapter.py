@@ -118,7 +118,17 @@ def structure_params(st) -> O.TlsphParams:
     for d in range(st.ndims):
         p.acceleration[d] = float(st.acceleration[d])
     m = st.boundary_model
-    if m is not None:
+    if m is not None and type(m).__name__ == "BoundaryModelDummyParticles":
+        se = m.state_equation
+        p.boundary_model = O.BOUNDARY_DUMMY_PARTICLES
+        p.bm_kernel = m.smoothing_kernel.kernel_id
+        p.bm_clip_negative_pressure = int(m.clip_negative_pressure)
+        p.bm_smoothing_length = float(t(m.smoothing_length))
+        p.bm_sound_speed, p.bm_exponent = float(t(se.sound_speed)), float(t(se.exponent))
+        p.bm_reference_density = float(t(se.reference_density))
+        p.bm_background_pressure = float(t(se.background_pressure))
+        p.bm_pressure_offset = float(t(m.density_calculator.pressure_offset))
+    elif m is not None:
         p.boundary_model = O.BOUNDARY_MONAGHAN_KAJTAR
         p.mk_K, p.mk_beta, p.mk_spacing = float(t(m.K)), float(t(m.beta)), float(t(m.boundary_particle_spacing))
     return p

@@ -82,6 +82,7 @@ _SUFFIX = {("float64", "float64"): "f64", ("float32", "float32"): "f32",
 
 BOUNDARY_NONE = 0
 BOUNDARY_MONAGHAN_KAJTAR = 1
+BOUNDARY_DUMMY_PARTICLES = 2
 
 
 class TlsphParams(C.Structure):
@@ -91,6 +92,10 @@ class TlsphParams(C.Structure):
         ("young_modulus", C.c_double), ("poisson_ratio", C.c_double), ("penalty_alpha", C.c_double),
         ("acceleration", C.c_double * 3), ("mk_K", C.c_double), ("mk_beta", C.c_double),
         ("mk_spacing", C.c_double),
+        ("bm_kernel", C.c_int32), ("bm_clip_negative_pressure", C.c_int32),
+        ("bm_smoothing_length", C.c_double), ("bm_sound_speed", C.c_double), ("bm_exponent", C.c_double),
+        ("bm_reference_density", C.c_double), ("bm_background_pressure", C.c_double),
+        ("bm_pressure_offset", C.c_double),
     ]
 
 
@@ -134,6 +139,9 @@ def _declare(L):
         f = getattr(L, f"orc_kick_fsi_{s}"); f.restype = i
         f.argtypes = [C.POINTER(FluidParams), C.POINTER(WallParams), TP, i64, p, i64, p, p, i64, i64,
                       p, p, p, p, p, p, p, p, p, p, i]
+        f = getattr(L, f"orc_kick_fsi2_{s}"); f.restype = i
+        f.argtypes = [C.POINTER(FluidParams), C.POINTER(WallParams), TP, i64, p, i64, p, p, i64, i64,
+                      p, p, p, p, p, p, p, p, p, p, p, p, i]
     L.orc_max_threads.restype = i
     L.orc_max_threads.argtypes = []
 
@@ -378,10 +386,11 @@ def kick_fsi(fp: FluidParams, wp, sp: TlsphParams, mass_f, coords_w, mass_w, n_s
     L = np.ascontiguousarray(L, dtype=dtype)
     dv = np.zeros_like(v_ode)
     F, P = np.zeros((n_s, nd, nd), dtype=dtype), np.zeros((n_s, nd, nd), dtype=dtype)
-    rc = getattr(lib(), f"orc_kick_fsi_{s}")(C.byref(fp), wpp, C.byref(sp), n_f, _ptr(mass_f), n_w, _ptr(coords_w),
-                                              _ptr(mass_w), n_s, n_s_int, _ptr(x0_s), _ptr(mass_s), _ptr(rho_s),
-                                              _ptr(hydro), _ptr(L), _ptr(v_ode), _ptr(u_ode), _ptr(dv), _ptr(F),
-                                              _ptr(P), int(nthreads))
+    ps, ds = np.zeros(n_s, dtype=dtype), np.zeros(n_s, dtype=dtype)
+    rc = getattr(lib(), f"orc_kick_fsi2_{s}")(C.byref(fp), wpp, C.byref(sp), n_f, _ptr(mass_f), n_w, _ptr(coords_w),
+                                               _ptr(mass_w), n_s, n_s_int, _ptr(x0_s), _ptr(mass_s), _ptr(rho_s),
+                                               _ptr(hydro), _ptr(L), _ptr(v_ode), _ptr(u_ode), _ptr(dv), _ptr(F),
+                                               _ptr(P), _ptr(ps), _ptr(ds), int(nthreads))
     if rc != 0:
         raise RuntimeError(f"orc_kick_fsi failed: {rc}")
-    return dict(dv=dv, F=F, pk1_rho2=P)
+    return dict(dv=dv, F=F, pk1_rho2=P, structure_pressure=ps, structure_density=ds)

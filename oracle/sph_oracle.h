@@ -81,7 +81,7 @@ enum { ORC_WALL_ADAMI = 0, ORC_WALL_CONTINUITY = 1 };
 /* TotalLagrangianSPHSystem (structure/total_lagrangian_sph/system.jl:76-106) with scalar material
  * constants, PenaltyForceGanzenmueller (penalty_force.jl) and, for the coupling with a fluid, a
  * BoundaryModelMonaghanKajtar (wall_boundary/monaghan_kajtar.jl:18-34). */
-enum { ORC_BOUNDARY_NONE = 0, ORC_BOUNDARY_MONAGHAN_KAJTAR = 1 };
+enum { ORC_BOUNDARY_NONE = 0, ORC_BOUNDARY_MONAGHAN_KAJTAR = 1, ORC_BOUNDARY_DUMMY_PARTICLES = 2 };
 typedef struct {
     int32_t ndims, kernel;
     int32_t has_penalty;      /* PenaltyForceGanzenmueller or nothing */
@@ -91,6 +91,13 @@ typedef struct {
     double penalty_alpha;
     double acceleration[3];
     double mk_K, mk_beta, mk_spacing; /* BoundaryModelMonaghanKajtar(K, beta, boundary_particle_spacing, ...) */
+    /* ORC_BOUNDARY_DUMMY_PARTICLES: BoundaryModelDummyParticles(hydrodynamic_density, hydrodynamic_mass,
+     * AdamiPressureExtrapolation(pressure_offset), kernel, smoothing_length; state_equation) on the structure
+     * (examples/fsi/hydrostatic_water_column_2d.jl:109-124) */
+    int32_t bm_kernel, bm_clip_negative_pressure;
+    double bm_smoothing_length;
+    double bm_sound_speed, bm_exponent, bm_reference_density, bm_background_pressure;
+    double bm_pressure_offset;
 } orc_tlsph_params;
 
 #define ORC_DECLARE(SUF, T, CT)                                                              \
@@ -145,7 +152,16 @@ typedef struct {
                            int64_t n_w, const CT *coords_w, const T *mass_w, int64_t n_s,    \
                            int64_t n_s_int, const CT *x0_s, const T *mass_s, const T *rho_s, \
                            const T *hydro_mass_s, const T *L, const T *v_ode,                \
-                           const CT *u_ode, T *dv_ode, T *F_out, T *pk1_out, int nthreads);
+                           const CT *u_ode, T *dv_ode, T *F_out, T *pk1_out, int nthreads);  \
+    /* as orc_kick_fsi; pressure_s / density_s (n_s, may be NULL): the structure's boundary-model    \
+     * pressure and density (dummy particles: Adami extrapolation) */                                \
+    int orc_kick_fsi2_##SUF(const orc_fluid_params *fp, const orc_wall_params *wp,           \
+                           const orc_tlsph_params *sp, int64_t n_f, const T *mass_f,         \
+                           int64_t n_w, const CT *coords_w, const T *mass_w, int64_t n_s,    \
+                           int64_t n_s_int, const CT *x0_s, const T *mass_s, const T *rho_s, \
+                           const T *hydro_mass_s, const T *L, const T *v_ode,                \
+                           const CT *u_ode, T *dv_ode, T *F_out, T *pk1_out, T *pressure_s,  \
+                           T *density_s, int nthreads);
 
 ORC_DECLARE(f64, double, double)
 ORC_DECLARE(f32, float, float)

@@ -31,10 +31,14 @@ def fsi_state(fluid, structure, seed=7, deform=0.05):
 @pytest.mark.parametrize("eltype,coords,tol", [(np.float64, np.float64, 1e-11), (np.float32, np.float32, 2e-5),
                                                 (np.float32, np.float64, 2e-5)])
 @pytest.mark.parametrize("memory", ["host", "device"])
-def test_fsi_kick_matches_oracle(eltype, coords, tol, memory):
-    # the plate next to the water column, so that the Monaghan-Kajtar coupling is active
+@pytest.mark.parametrize("boundary_model", ["monaghan_kajtar", "dummy_particles"])
+def test_fsi_kick_matches_oracle(eltype, coords, tol, memory, boundary_model):
+    """`boundary_model`: BoundaryModelMonaghanKajtar as the example ships it, or the BoundaryModelDummyParticles
+    (Adami) alternative of dam_break_plate_2d.jl:120-133 / hydrostatic_water_column_2d.jl:109-124."""
+    # the plate next to the water column, so that the coupling is active
     fluid, wall, structure, _ = examples.dam_break_plate_2d(
-        0.01, eltype=eltype, coordinates_eltype=coords, initial_fluid_size=(0.15, 0.29), plate_position=(0.165, 0.0))
+        0.01, eltype=eltype, coordinates_eltype=coords, initial_fluid_size=(0.15, 0.29), plate_position=(0.165, 0.0),
+        structure_boundary_model=boundary_model)
     u, v = fsi_state(fluid, structure)
     ref = adapter.kick_fsi(fluid, wall, structure, u, v)
     semi = tp.Semidiscretization(fluid, wall, structure,
@@ -66,6 +70,10 @@ def test_fsi_kick_matches_oracle(eltype, coords, tol, memory):
     # the coupling is active on both sides
     no_plate = adapter.kick(fluid, wall, u[: 2 * n_f].reshape(n_f, 2), v[: 3 * n_f].reshape(n_f, 3))["dv"]
     assert np.abs(ref_f - no_plate).max() > 1.0
+    if boundary_model == "dummy_particles":
+        for name, key in (("pressure", "structure_pressure"), ("density", "structure_density")):
+            got = semi.system_field(structure, name)
+            assert np.abs(got - ref[key]).max() <= 10 * tol * np.abs(ref[key]).max(), name
     for name, a, b in (("fluid acceleration", dv_f[:, :2], ref_f[:, :2]), ("fluid drho", dv_f[:, 2], ref_f[:, 2]),
                        ("structure acceleration", dv_s, ref_s)):
         err = np.abs(a - b).max() / np.abs(b).max()

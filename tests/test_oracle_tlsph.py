@@ -108,3 +108,67 @@ def test_monaghan_kajtar_rhs():
     assert np.all(dv[[0, 3, 6], :2] == 0)
     assert np.all(dv[[2, 5, 8], 0] < -300)
     assert np.allclose(dv[[1, 4, 7], 0], [-26.052449, -95.162888, -26.052449], rtol=1.5e-8)
+
+
+def _dummy_structure_case(seed=3):
+    """A block of structure particles under a block of fluid, the structure carrying
+    BoundaryModelDummyParticles{AdamiPressureExtrapolation} (examples/fsi/hydrostatic_water_column_2d.jl:109-124)."""
+    import trixiparticles.jl_b200 as tp
+    rng = np.random.default_rng(seed)
+    dx = 0.05
+    se = tp.StateEquationCole(sound_speed=10.0, reference_density=1000.0, exponent=7)
+    kernel, h = tp.WendlandC2Kernel(2), np.sqrt(2) * dx
+    f_ic = tp.RectangularShape(dx, (8, 6), (0.0, 0.0), density=1000.0)
+    s_ic = tp.RectangularShape(dx, (8, 3), (0.0, -3 * dx), density=2700.0)
+    fluid = tp.WeaklyCompressibleSPHSystem(f_ic, smoothing_kernel=kernel, smoothing_length=h,
+                                           density_calculator=tp.ContinuityDensity(), state_equation=se,
+                                           acceleration=(0.0, 0.0))
+    hyd_rho = np.full(s_ic.nparticles, 1000.0)
+    model = tp.BoundaryModelDummyParticles(hyd_rho, hyd_rho * dx ** 2, tp.AdamiPressureExtrapolation(), kernel, h,
+                                           state_equation=se)
+    st = tp.TotalLagrangianSPHSystem(s_ic, smoothing_kernel=kernel, smoothing_length=h, young_modulus=1e6,
+                                     poisson_ratio=0.3, boundary_model=model, acceleration=(0.0, 0.0))
+    u_f = f_ic.coordinates + rng.uniform(-0.1 * dx, 0.1 * dx, f_ic.coordinates.shape)
+    v_f = np.concatenate([rng.uniform(-0.5, 0.5, (f_ic.nparticles, 2)),
+                          1000.0 * (1 + rng.uniform(-0.01, 0.01, (f_ic.nparticles, 1)))], axis=1)
+    return tp, fluid, st, model, u_f, v_f
+
+
+def test_dummy_particle_structure_at_rest_acts_like_a_wall():
+    """A structure at rest with BoundaryModelDummyParticles gives the fluid exactly what a WallBoundarySystem of
+    the same particles with the same boundary model gives it (wcsph/rhs.jl treats both alike; the Adami pass
+    of dummy_particles.jl:489-672 does not care which system carries the model)."""
+    from oracle import adapter
+    tp, fluid, st, model, u_f, v_f = _dummy_structure_case()
+    wall = tp.WallBoundarySystem(st.initial_condition, model)
+    ref = adapter.kick(fluid, wall, u_f, v_f, use_grid=False)
+    u_ode = np.concatenate([u_f.reshape(-1), st.initial_coordinates.reshape(-1)])
+    v_ode = np.concatenate([v_f.reshape(-1), np.zeros(st.nparticles * 2)])
+    out = adapter.kick_fsi(fluid, None, st, u_ode, v_ode)
+    dv_f = out["dv"][: v_f.size].reshape(v_f.shape)
+    np.testing.assert_allclose(dv_f, ref["dv"], rtol=1e-12, atol=1e-12 * np.abs(ref["dv"]).max())
+    np.testing.assert_allclose(out["structure_pressure"], ref["wall_pressure"], rtol=1e-13, atol=1e-9)
+    np.testing.assert_allclose(out["structure_density"], ref["wall_density"], rtol=1e-13)
+
+
+def test_dummy_particle_structure_conserves_momentum_with_the_fluid():
+    """structure.jl:60-95: the structure receives "the exact same pair force" the fluid feels, with flipped
+    sign -- without gravity and with an undeformed structure the total momentum of fluid + structure is
+    conserved: sum_f m_f dv_f + sum_s m_s dv_s = 0 (material masses on the structure side)."""
+    from oracle import adapter
+    tp, fluid, st, model, u_f, v_f = _dummy_structure_case(seed=5)
+    rng = np.random.default_rng(9)
+    v_s = rng.uniform(-0.2, 0.2, (st.nparticles, 2))        # a moving (still undeformed) structure
+    u_ode = np.concatenate([u_f.reshape(-1), st.initial_coordinates.reshape(-1)])
+    v_ode = np.concatenate([v_f.reshape(-1), v_s.reshape(-1)])
+    out = adapter.kick_fsi(fluid, None, st, u_ode, v_ode)
+    dv_f = out["dv"][: v_f.size].reshape(v_f.shape)[:, :2]
+    dv_s = out["dv"][v_f.size:].reshape(-1, 2)
+    assert np.abs(dv_s).max() > 0
+    mom = (fluid.mass[:, None] * dv_f).sum(axis=0) + (st.mass[:, None] * dv_s).sum(axis=0)
+    scale = np.abs(st.mass[:, None] * dv_s).sum()
+    assert np.abs(mom).max() <= 1e-12 * scale
+    # the structure's velocity enters the fluid's continuity equation (a wall's would be zero)
+    still = adapter.kick_fsi(fluid, None, st, u_ode, np.concatenate([v_f.reshape(-1), 0 * v_s.reshape(-1)]))
+    drho = out["dv"][: v_f.size].reshape(v_f.shape)[:, 2]
+    assert np.abs(drho - still["dv"][: v_f.size].reshape(v_f.shape)[:, 2]).max() > 0

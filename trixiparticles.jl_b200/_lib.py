@@ -16,7 +16,7 @@ F32, F64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 FIELD_PRESSURE, FIELD_DENSITY, FIELD_VOLUME, FIELD_WALL_VELOCITY = 0, 1, 2, 3
 FIELD_DEFORMATION_GRADIENT, FIELD_PK1_RHO2, FIELD_CORRECTION_MATRIX = 4, 5, 6
-BOUNDARY_NONE, BOUNDARY_MONAGHAN_KAJTAR = 0, 1
+BOUNDARY_NONE, BOUNDARY_MONAGHAN_KAJTAR, BOUNDARY_DUMMY_PARTICLES = 0, 1, 2
 
 EXPORTS = [
     "tpb_version", "tpb_last_error", "tpb_create", "tpb_destroy", "tpb_add_fluid_system",
@@ -79,6 +79,9 @@ class StructureParams(C.Structure):
         ("boundary_model", C.c_int32), ("smoothing_length", C.c_double), ("young_modulus", C.c_double),
         ("poisson_ratio", C.c_double), ("penalty_alpha", C.c_double), ("acceleration", C.c_double * 3),
         ("mk_K", C.c_double), ("mk_beta", C.c_double), ("mk_spacing", C.c_double),
+        ("bm_kernel", C.c_int32), ("bm_clip_negative_pressure", C.c_int32), ("bm_smoothing_length", C.c_double),
+        ("bm_sound_speed", C.c_double), ("bm_exponent", C.c_double), ("bm_reference_density", C.c_double),
+        ("bm_background_pressure", C.c_double), ("bm_pressure_offset", C.c_double),
     ]
 
 

@@ -73,6 +73,9 @@ struct Semi {
     void *d_x0_s = nullptr, *d_xcur_s = nullptr, *d_mass_s = nullptr, *d_rho_s = nullptr, *d_hydro_s = nullptr;
     void *d_L_s = nullptr, *d_F_s = nullptr, *d_pk1_s = nullptr, *d_As = nullptr, *d_Bs = nullptr;
     int *d_nbr_start = nullptr, *d_nbr = nullptr, *d_scell_start = nullptr;
+    // structure with BoundaryModelDummyParticles: sorted -> own index, Adami pressure (sorted / own order), density
+    int *d_sperm = nullptr;
+    void *d_Ps = nullptr, *d_p_s = nullptr, *d_rhoh_s = nullptr;
 
     // geometry of the shared cell grid (double; typed copies are built per call)
     double cell_size = 0, origin[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
@@ -517,6 +520,23 @@ struct Ops {
         k.almostzero_sf = std::sqrt(eps_of<T>(pc.kern.h * pc.kern.h));
         return k;
     }
+    static DummyConst<T> make_dummy_const(const Semi &s, const PairConst<T> &pc)
+    {
+        DummyConst<T> k;
+        k.kern = make_kernel_const<T>(s.sp.bm_kernel, ND, s.sp.bm_smoothing_length);
+        k.eos = make_eos_const<T>(s.sp.bm_sound_speed, s.sp.bm_exponent, s.sp.bm_reference_density,
+                                  s.sp.bm_background_pressure, 0);
+        const T Rb = k.kern.support;
+        k.radius2_b = Rb * Rb;
+        k.radius2_f = pc.radius2;
+        for (int d = 0; d < 3; ++d) k.acc[d] = (T)s.fp.acceleration[d];
+        k.p_off = (T)s.sp.bm_pressure_offset;
+        k.clip = s.sp.bm_clip_negative_pressure;
+        k.almostzero_fs = pc.almostzero;
+        k.almostzero_sf = std::sqrt(eps_of<T>(pc.kern.h * pc.kern.h));
+        return k;
+    }
+    static int kernel_template_id(int kernel) { return kernel <= 1 ? kernel : kernel <= TPB_KERNEL_WENDLAND_C6 ? 2 : 3; }
     static int struct_kernel_id(const Semi &s)
     {
         const int kernel = s.sp.kernel;
@@ -620,10 +640,30 @@ struct Ops {
         if (s.sp.boundary_model != TPB_BOUNDARY_NONE) {
             int rc = bin_points(s, (const CT *)s.d_xcur_s, n, n, s.d_scell_start);
             if (rc) return rc;
-            const MKConst<T> mk = make_mk_const(s, pc);
-            LAUNCH(s, (k_reorder_struct<ND, T, CT>), cdiv(n, 256), 256, 0, (const CT *)s.d_xcur_s, d_v_s,
-                   (const T *)s.d_hydro_s, s.d_key, s.d_scell_start, s.d_tmp_perm, n, n_int, mk.vol,
-                   (V4<CT> *)s.d_As, (V4<T> *)s.d_Bs);
+            if (s.sp.boundary_model == TPB_BOUNDARY_DUMMY_PARTICLES) {
+                // dummy particles: sorted records first, then the Adami pass over the fluid's sorted records
+                // (rebuild_fluid has run: positions, density and pressure of the fluid are in place)
+                LAUNCH(s, (k_reorder_struct<ND, T, CT>), cdiv(n, 256), 256, 0, (const CT *)s.d_xcur_s, d_v_s,
+                       (const T *)s.d_hydro_s, s.d_key, s.d_scell_start, s.d_tmp_perm, n, n_int, (T)1,
+                       (V4<CT> *)s.d_As, (V4<T> *)s.d_Bs, s.d_sperm);
+                const DummyConst<T> dk = make_dummy_const(s, pc);
+                const int enabled = s.struct_fluid[0] && s.n_act > 0;
+                switch (kernel_template_id(s.sp.bm_kernel)) {
+#define TPB_SADAMI(KID)                                                                                           \
+    case KID:                                                                                                     \
+        LAUNCH(s, (k_struct_adami<ND, T, CT, KID>), cdiv(n, 128), 128, 0, n, g, (const V4<CT> *)s.d_As, s.d_sperm, \
+               s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P, enabled, dk,        \
+               (V4<T> *)s.d_Bs, (T *)s.d_Ps, (T *)s.d_p_s, (T *)s.d_rhoh_s, s.d_flags);                            \
+        break;
+                    TPB_SADAMI(0) TPB_SADAMI(1) TPB_SADAMI(2) TPB_SADAMI(3)
+#undef TPB_SADAMI
+                }
+            } else {
+                const MKConst<T> mk = make_mk_const(s, pc);
+                LAUNCH(s, (k_reorder_struct<ND, T, CT>), cdiv(n, 256), 256, 0, (const CT *)s.d_xcur_s, d_v_s,
+                       (const T *)s.d_hydro_s, s.d_key, s.d_scell_start, s.d_tmp_perm, n, n_int, mk.vol,
+                       (V4<CT> *)s.d_As, (V4<T> *)s.d_Bs);
+            }
         }
         const StructConst<T> k = make_struct_const(s);
         switch (struct_kernel_id(s)) {
@@ -646,6 +686,20 @@ struct Ops {
         constexpr int NV = DENS == 0 ? ND + 1 : ND;
         const int n = (int)s.n_s, n_int = (int)s.n_s_int;
         if (n == 0) return TPB_OK;
+        if (s.sp.boundary_model == TPB_BOUNDARY_DUMMY_PARTICLES) {
+            const DummyConst<T> dk = make_dummy_const(s, pc);
+            if (s.struct_fluid[1] && s.n_act > 0)
+                LAUNCH(s, (k_fluid_from_struct_dummy<ND, T, CT, FK, DENS>), cdiv(s.n_act, 128), 128, 0, (int)s.n_act, g,
+                       s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f,
+                       s.d_scell_start, (const V4<CT> *)s.d_As, (const V4<T> *)s.d_Bs, (const T *)s.d_Ps, pc.kern, dk,
+                       d_dv_f, (int)s.n_tgt);
+            if (n_int == 0) return TPB_OK;
+            LAUNCH(s, (k_struct_from_fluid_dummy<ND, T, CT, FK, DENS>), cdiv(n_int, 128), 128, 0, n_int, g,
+                   (const CT *)s.d_xcur_s, (const T *)s.d_mass_s, (const T *)s.d_hydro_s, (const T *)s.d_p_s,
+                   (const T *)s.d_rhoh_s, s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B,
+                   (const T *)s.d_P, (int)(s.struct_fluid[0] && s.n_act > 0), pc.kern, dk, d_dv_s, s.d_flags);
+            return interact_structure_self(s, d_dv_s);
+        }
         const bool coupled = s.sp.boundary_model == TPB_BOUNDARY_MONAGHAN_KAJTAR;
         const MKConst<T> mk = make_mk_const(s, pc);
         if (coupled && s.struct_fluid[1] && s.n_act > 0)
@@ -656,6 +710,13 @@ struct Ops {
         LAUNCH(s, (k_struct_from_fluid<ND, T, CT>), cdiv(n_int, 128), 128, 0, n_int, g, (const CT *)s.d_xcur_s,
                (const T *)s.d_mass_s, s.d_fcell_start, (const V4<CT> *)s.d_A,
                (int)(coupled && s.struct_fluid[0] && s.n_act > 0), mk, d_dv_s, s.d_flags);
+        return interact_structure_self(s, d_dv_s);
+    }
+
+    // structure <- structure + gravity (adds to what the fluid has left in dv_s)
+    static int interact_structure_self(Semi &s, T *d_dv_s)
+    {
+        const int n_int = (int)s.n_s_int;
         StructConst<T> k = make_struct_const(s);
         switch (struct_kernel_id(s)) {
 #define TPB_SINTERACT(KID)                                                                                       \
@@ -1232,6 +1293,17 @@ struct Ops {
             CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
             return TPB_OK;
         }
+        if (system == s.struct_index && s.struct_index >= 0) {
+            // boundary-model pressure / density of a structure with dummy particles (own particle order)
+            if (s.sp.boundary_model != TPB_BOUNDARY_DUMMY_PARTICLES || (field != TPB_FIELD_PRESSURE && field != TPB_FIELD_DENSITY))
+                return fail(&s, TPB_ERR_INVALID_ARGUMENT, "structure field: pressure / density exist with BoundaryModelDummyParticles only");
+            if (n != s.n_s) return fail(&s, TPB_ERR_INVALID_ARGUMENT, "field length mismatch");
+            if (n == 0) return TPB_OK;
+            CUDA_TRY(&s, cudaMemcpyAsync(out, field == TPB_FIELD_PRESSURE ? s.d_p_s : s.d_rhoh_s, sizeof(T) * (size_t)n,
+                                         cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
+            return TPB_OK;
+        }
         T *scratch = (T *)s.d_scratch;
         CUDA_TRY(&s, cudaMemsetAsync(scratch, 0, sizeof(T) * (size_t)std::max<int64_t>(n, 1), s.stream));
         if (system == s.fluid_index) {
@@ -1437,7 +1509,8 @@ static void free_device(Semi &s)
                     s.d_scan_ticket,
                     s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_Vw, s.d_Pw, s.d_perm_w,
                     s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2, s.d_adapt, s.d_x0_s, s.d_xcur_s, s.d_mass_s, s.d_rho_s, s.d_hydro_s,
-                    s.d_L_s, s.d_F_s, s.d_pk1_s, s.d_As, s.d_Bs, s.d_nbr_start, s.d_nbr, s.d_scell_start};
+                    s.d_L_s, s.d_F_s, s.d_pk1_s, s.d_As, s.d_Bs, s.d_nbr_start, s.d_nbr, s.d_scell_start, s.d_sperm,
+                    s.d_Ps, s.d_p_s, s.d_rhoh_s};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     tiles_free(s.tiles);
@@ -1622,8 +1695,16 @@ int32_t tpb_add_structure_system(tpb_semi_t semi, const tpb_structure_params *p,
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "unknown smoothing kernel");
     if (!(p->smoothing_length > 0) || !(p->young_modulus > 0))
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "smoothing_length and young_modulus must be positive");
-    if (p->boundary_model != TPB_BOUNDARY_NONE && p->boundary_model != TPB_BOUNDARY_MONAGHAN_KAJTAR)
-        return fail(s, TPB_ERR_UNSUPPORTED, "structure boundary model: only BoundaryModelMonaghanKajtar (or none)");
+    if (p->boundary_model != TPB_BOUNDARY_NONE && p->boundary_model != TPB_BOUNDARY_MONAGHAN_KAJTAR &&
+        p->boundary_model != TPB_BOUNDARY_DUMMY_PARTICLES)
+        return fail(s, TPB_ERR_UNSUPPORTED, "structure boundary model: BoundaryModelMonaghanKajtar, "
+                                            "BoundaryModelDummyParticles (Adami) or none");
+    if (p->boundary_model == TPB_BOUNDARY_DUMMY_PARTICLES &&
+        (!hydrodynamic_mass || !(p->bm_smoothing_length > 0) || !(p->bm_sound_speed > 0) ||
+         !(p->bm_reference_density > 0) || p->bm_exponent == 0 || p->bm_kernel < TPB_KERNEL_WENDLAND_C2 ||
+         p->bm_kernel > TPB_KERNEL_SCHOENBERG_QUINTIC))
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "BoundaryModelDummyParticles on the structure needs kernel, smoothing "
+                                                 "length, state equation and the hydrodynamic masses");
     if (p->boundary_model == TPB_BOUNDARY_MONAGHAN_KAJTAR &&
         (!hydrodynamic_mass || !(p->mk_K > 0) || !(p->mk_beta > 0) || !(p->mk_spacing > 0)))
         return fail(s, TPB_ERR_INVALID_ARGUMENT, "BoundaryModelMonaghanKajtar needs K, beta, spacing > 0 and the hydrodynamic masses");
@@ -1697,6 +1778,8 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     };
     double R = radius(s->fp.kernel, s->fp.smoothing_length);
     if (s->wall_index >= 0) R = std::max(R, radius(s->wp.kernel, s->wp.smoothing_length));
+    if (s->struct_index >= 0 && s->sp.boundary_model == TPB_BOUNDARY_DUMMY_PARTICLES)
+        R = std::max(R, radius(s->sp.bm_kernel, s->sp.bm_smoothing_length));
 
     // bounding box
     double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
@@ -1818,6 +1901,14 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
         CUDA_TRY(s, cudaMemset(s->d_pk1_s, 0, ts * nd * nd * ns));
         CUDA_TRY(s, cudaMalloc(&s->d_As, 4 * cs * (ns + 8)));
         CUDA_TRY(s, cudaMalloc(&s->d_Bs, 4 * ts * (ns + 8)));
+        if (s->sp.boundary_model == TPB_BOUNDARY_DUMMY_PARTICLES) {
+            CUDA_TRY(s, cudaMalloc(&s->d_sperm, sizeof(int) * (ns + 8)));
+            CUDA_TRY(s, cudaMalloc(&s->d_Ps, ts * (ns + 8)));
+            CUDA_TRY(s, cudaMalloc(&s->d_p_s, ts * (ns + 8)));
+            CUDA_TRY(s, cudaMalloc(&s->d_rhoh_s, ts * (ns + 8)));
+            CUDA_TRY(s, cudaMemset(s->d_p_s, 0, ts * (ns + 8)));
+            CUDA_TRY(s, cudaMemset(s->d_rhoh_s, 0, ts * (ns + 8)));
+        }
         CUDA_TRY(s, cudaMalloc(&s->d_scell_start, sizeof(int) * (size_t)(s->ncells + 4)));
         CUDA_TRY(s, cudaMemset(s->d_scell_start, 0, sizeof(int) * (size_t)(s->ncells + 4)));
     }

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256)
 k_reorder_struct(const CT *__restrict__ x_cur, const T *__restrict__ v_s, const T *__restrict__ hydro_mass,
                  const int *__restrict__ key, const int *__restrict__ cell_start,
                  const int *__restrict__ tmp_perm, int n, int n_int, T mk_vol, V4<CT> *__restrict__ A,
-                 V4<T> *__restrict__ B)
+                 V4<T> *__restrict__ B, int *__restrict__ sperm = nullptr)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -110,6 +110,7 @@ k_reorder_struct(const CT *__restrict__ x_cur, const T *__restrict__ v_s, const 
     rb.w = hydro_mass[i] / mk_vol;
     A[dst] = ra;
     B[dst] = rb;
+    if (sperm) sperm[dst] = i;
 }
 
 template <int ND, typename T, typename CT>
@@ -405,6 +406,170 @@ k_fluid_from_struct(int n_f, GridConst<CT> g, const int *__restrict__ fcell_star
 #pragma unroll
                     for (int d = 0; d < ND; ++d) acc[d] += dvp[d];
                     drho += div_fast(bi.w, bj.w) * (T)xj.w * vg;
+                }
+            }
+        }
+    });
+    const int64_t o = (int64_t)orig * NV;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) dv[o + d] += acc[d];
+    if (NV == ND + 1) dv[o + ND] += drho;
+}
+
+// ------------------------------------------------------------------ BoundaryModelDummyParticles on the structure
+// examples/fsi/hydrostatic_water_column_2d.jl:109-124 (and the alternative dam_break_plate_2d.jl:120-133 keeps in
+// a comment): the structure particles are dummy particles with AdamiPressureExtrapolation.
+template <typename T>
+struct DummyConst {
+    KernelConst<T> kern;   // boundary model's kernel / smoothing length
+    EosConst<T> eos;       // boundary model's state equation
+    T radius2_b;           // compact_support(structure, fluid)^2 = the MODEL's (neighborhood_search.jl:134-140)
+    T radius2_f;           // compact_support(fluid, structure)^2 = the fluid's
+    T acc[3];              // acceleration_source(fluid) - current_acceleration(structure) (= 0, abstract_system.jl:121)
+    T p_off;
+    int clip;
+    T almostzero_fs;       // fluid <- structure: sqrt(eps(compact_support_fluid^2))
+    T almostzero_sf;       // structure <- fluid: sqrt(eps(h_fluid^2))
+};
+
+// update_boundary_interpolation! for the structure's particles at their CURRENT positions (dummy_particles.jl:
+// 489-569, :637-672): one thread per sorted structure particle walks the fluid's sorted records.  Writes the
+// density into the sorted record (Bs.w) and pressure / density in the structure's own particle order.
+template <int ND, typename T, typename CT, int KERNEL>
+__global__ void __launch_bounds__(128)
+k_struct_adami(int n_s, GridConst<CT> g, const V4<CT> *__restrict__ As, const int *__restrict__ sperm,
+               const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A, const V4<T> *__restrict__ B,
+               const T *__restrict__ P, int enabled, DummyConst<T> k, V4<T> *__restrict__ Bs, T *__restrict__ Ps,
+               T *__restrict__ p_orig, T *__restrict__ rho_orig, int *__restrict__ flags)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_s) return;
+    const V4<CT> xi = As[w];
+    int cx, cy, cz;
+    T p = (T)0, vol = (T)0;
+    if (!cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz)) atomicOr(flags, 1);
+    else if (enabled) {
+        for_neighbor_rows<ND, CT>(g, fcell_start, cx, cy, cz, [&](int j0, int j1) {
+            for (int j = j0; j < j1; ++j) {
+                const V4<CT> xj = A[j];
+                T pd[3];
+                const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                if (d2 <= k.radius2_b) {
+                    const T dist = sqrt_rn(d2);
+                    const T rho_f = B[j].w;
+                    T hyd = k.acc[0] * (rho_f * pd[0]) + k.acc[1] * (rho_f * pd[1]);
+                    if (ND == 3) hyd += k.acc[2] * (rho_f * pd[2]);
+                    const T sum_p = k.p_off + P[j] + hyd;
+                    const T kw = kernel_safe<KERNEL, T>(k.kern, dist);
+                    p += sum_p * kw;
+                    vol += kw;
+                }
+            }
+        });
+    }
+    if ((double)vol > 2.220446049250313e-16) p = p / vol;  // `volume > eps()`: eps(Float64)
+    if (k.clip) p = p > (T)0 ? p : (T)0;
+    const T rho = eos_inverse(k.eos, p);
+    Bs[w].w = rho;
+    Ps[w] = p;
+    const int i = sperm[w];
+    p_orig[i] = p;
+    rho_orig[i] = rho;
+}
+
+// structure <- fluid with dummy particles (interact_structure_fluid!, structure.jl:20-102): pairs within the
+// model's compact support, the FLUID's kernel gradient and pressure-acceleration formulation with the roles
+// switched: dv_boundary = -m_a^hydro (p_b + p_a) / (rho_b rho_a) grad W;  dv_s = sum dv_boundary m_b / m_a^material
+template <int ND, typename T, typename CT, int FKERNEL, int DENS>
+__global__ void __launch_bounds__(128)
+k_struct_from_fluid_dummy(int n_int, GridConst<CT> g, const CT *__restrict__ x_cur, const T *__restrict__ mass_s,
+                          const T *__restrict__ hydro_s, const T *__restrict__ p_s, const T *__restrict__ rho_s,
+                          const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
+                          const V4<T> *__restrict__ B, const T *__restrict__ P, int enabled, KernelConst<T> fkern,
+                          DummyConst<T> k, T *__restrict__ dv_s, int *__restrict__ flags)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_int) return;
+    V4<CT> xi;
+    xi.x = x_cur[(int64_t)a * ND], xi.y = x_cur[(int64_t)a * ND + 1];
+    xi.z = ND == 3 ? x_cur[(int64_t)a * ND + 2] : (CT)0;
+    xi.w = (CT)0;
+    T acc[3] = {0, 0, 0};
+    int cx, cy, cz;
+    if (!cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz)) atomicOr(flags, 1);
+    else if (enabled) {
+        const T m_a = mass_s[a], mh_a = hydro_s[a], p_a = p_s[a], rho_a = rho_s[a];
+        for_neighbor_rows<ND, CT>(g, fcell_start, cx, cy, cz, [&](int j0, int j1) {
+            for (int j = j0; j < j1; ++j) {
+                const V4<CT> xj = A[j];
+                T pd[3];
+                const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                if (d2 <= k.radius2_b) {
+                    const T dist = sqrt_rn(d2);
+                    if (dist >= k.almostzero_sf) {
+                        const T wdr = SmoothingKernel<FKERNEL, T>::dw_div_r(fkern, dist);
+                        const T rho_b = B[j].w, p_b = P[j], m_b = (T)xj.w;
+                        T f;
+                        if (DENS == 0)
+                            f = -mh_a * div_fast(p_b + p_a, rho_b * rho_a);
+                        else
+                            f = -mh_a * (div_fast(p_b, rho_b * rho_b) + div_fast(p_a, rho_a * rho_a));
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) acc[d] += (f * (wdr * pd[d])) * m_b / m_a;
+                    }
+                }
+            }
+        });
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) dv_s[(int64_t)a * ND + d] = acc[d];
+}
+
+// fluid <- structure with dummy particles (wcsph/rhs.jl:5-127): like a wall particle, but with the structure's
+// velocity in the continuity equation; no viscous term, no density diffusion.  dv_f += S_fs
+template <int ND, typename T, typename CT, int KERNEL, int DENS>
+__global__ void __launch_bounds__(128)
+k_fluid_from_struct_dummy(int n_f, GridConst<CT> g, const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
+                          const V4<T> *__restrict__ B, const T *__restrict__ P, const int *__restrict__ perm,
+                          const int *__restrict__ scell_start, const V4<CT> *__restrict__ As,
+                          const V4<T> *__restrict__ Bs, const T *__restrict__ Ps, KernelConst<T> kern,
+                          DummyConst<T> k, T *__restrict__ dv, int n_targets)
+{
+    constexpr int NV = DENS == 0 ? ND + 1 : ND;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_f || s >= fcell_start[g.ncells]) return;
+    const int orig = perm[s];
+    if (orig >= n_targets) return;
+    const V4<CT> xi = A[s];
+    int cx, cy, cz;
+    cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    bool any = false;
+    for_neighbor_rows<ND, CT>(g, scell_start, cx, cy, cz, [&](int j0, int j1) { any = any || j1 > j0; });
+    if (!any) return;
+    const V4<T> bi = B[s];
+    const T p_a = P[s], rho_a = bi.w;
+    T acc[3] = {0, 0, 0}, drho = (T)0;
+    for_neighbor_rows<ND, CT>(g, scell_start, cx, cy, cz, [&](int j0, int j1) {
+        for (int j = j0; j < j1; ++j) {
+            const V4<CT> xj = As[j];
+            T pd[3];
+            const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+            if (d2 <= k.radius2_f) {
+                const T dist = sqrt_rn(d2);
+                if (dist >= k.almostzero_fs) {
+                    const V4<T> bj = Bs[j];
+                    const T p_b = Ps[j], rho_b = bj.w, m_b = (T)xj.w;
+                    const T wdr = SmoothingKernel<KERNEL, T>::dw_div_r(kern, dist);
+                    T f;
+                    if (DENS == 0)
+                        f = -m_b * div_fast(p_a + p_b, rho_a * rho_b);
+                    else
+                        f = -m_b * (div_fast(p_a, rho_a * rho_a) + div_fast(p_b, rho_b * rho_b));
+                    T vg = (bi.x - bj.x) * (wdr * pd[0]) + (bi.y - bj.y) * (wdr * pd[1]);
+                    if (ND == 3) vg += (bi.z - bj.z) * (wdr * pd[2]);
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) acc[d] += f * (wdr * pd[d]);
+                    if (DENS == 0) drho += div_fast(rho_a, rho_b) * m_b * vg;
                 }
             }
         }

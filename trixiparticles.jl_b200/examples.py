@@ -135,7 +135,7 @@ def perturbed_state(fluid, seed=1234, position_jitter=0.1, velocity_scale=0.05,
 
 def dam_break_plate_2d(fluid_particle_spacing=0.01, *, n_particles_x=5, eltype=np.float64,
                        coordinates_eltype=None, initial_fluid_size=(0.146, 2 * 0.146), plate_position=None,
-                       E=1e6, nu=0.0):
+                       E=1e6, nu=0.0, structure_boundary_model="monaghan_kajtar"):
     """examples/fsi/dam_break_plate_2d.jl:19-134 (BASELINE config 5): dam break against an elastic
     plate clamped at its base; WCSPH fluid, dummy-particle tank, TLSPH plate with a
     BoundaryModelMonaghanKajtar towards the fluid and a PenaltyForceGanzenmueller.  The reference's
@@ -176,7 +176,14 @@ def dam_break_plate_2d(fluid_particle_spacing=0.01, *, n_particles_x=5, eltype=n
     hydrodynamic_densities = t(fluid_density) * np.ones(structure.nparticles, dtype=eltype)
     hydrodynamic_masses = (hydrodynamic_densities * t(ds) ** 2).astype(eltype)
     k_structure = gravity * initial_fluid_size[1]
-    model_structure = BoundaryModelMonaghanKajtar(k_structure, dx / ds, ds, hydrodynamic_masses)
+    if structure_boundary_model == "dummy_particles":
+        # the alternative the example keeps in a comment (dam_break_plate_2d.jl:120-133) and
+        # examples/fsi/hydrostatic_water_column_2d.jl:109-124 uses
+        model_structure = BoundaryModelDummyParticles(hydrodynamic_densities, hydrodynamic_masses,
+                                                      AdamiPressureExtrapolation(), kernel, h,
+                                                      state_equation=state_equation)
+    else:
+        model_structure = BoundaryModelMonaghanKajtar(k_structure, dx / ds, ds, hydrodynamic_masses)
     structure_system = TotalLagrangianSPHSystem(
         structure, smoothing_kernel=WendlandC2Kernel(2), smoothing_length=np.sqrt(2) * ds, young_modulus=E,
         poisson_ratio=nu, boundary_model=model_structure, clamped_particles=range(clamped.nparticles),

@@ -368,8 +368,12 @@ class TotalLagrangianSPHSystem:
             raise ValueError("per-particle material constants are outside the accelerated hot path")
         if penalty_force is not None and not isinstance(penalty_force, PenaltyForceGanzenmueller):
             raise ValueError("`penalty_force` must be a PenaltyForceGanzenmueller")
-        if boundary_model is not None and not isinstance(boundary_model, BoundaryModelMonaghanKajtar):
-            raise ValueError("structure `boundary_model`: only BoundaryModelMonaghanKajtar is on the accelerated path")
+        dummy = isinstance(boundary_model, BoundaryModelDummyParticles)
+        if boundary_model is not None and not dummy and not isinstance(boundary_model, BoundaryModelMonaghanKajtar):
+            raise ValueError("structure `boundary_model`: BoundaryModelMonaghanKajtar or BoundaryModelDummyParticles")
+        if dummy and (isinstance(boundary_model.density_calculator, ContinuityDensity) or boundary_model.viscosity is not None):
+            raise ValueError("structure `BoundaryModelDummyParticles`: Adami / Bernoulli pressure extrapolation without "
+                             "viscosity are on the accelerated path")
         clamped = np.asarray(list(clamped_particles), dtype=np.int64)
         n = initial_condition.nparticles
         if len(np.unique(clamped)) != len(clamped):
@@ -380,7 +384,14 @@ class TotalLagrangianSPHSystem:
             coordinates=np.ascontiguousarray(ic.coordinates[order]), velocity=np.ascontiguousarray(ic.velocity[order]),
             mass=np.ascontiguousarray(ic.mass[order]), density=np.ascontiguousarray(ic.density[order]),
             pressure=np.ascontiguousarray(ic.pressure[order]), particle_spacing=ic.particle_spacing)
-        if boundary_model is not None and len(clamped):
+        if dummy and len(clamped):
+            # the constructor moves the clamped particles to the end (system.jl:131-147): so do the model's arrays
+            boundary_model = BoundaryModelDummyParticles(
+                boundary_model.initial_density[order], boundary_model.hydrodynamic_mass[order],
+                boundary_model.density_calculator, boundary_model.smoothing_kernel, boundary_model.smoothing_length,
+                state_equation=boundary_model.state_equation,
+                clip_negative_pressure=boundary_model.clip_negative_pressure)
+        elif boundary_model is not None and len(clamped):
             boundary_model = BoundaryModelMonaghanKajtar(boundary_model.K, boundary_model.beta,
                                                          boundary_model.boundary_particle_spacing,
                                                          boundary_model.hydrodynamic_mass[order])
