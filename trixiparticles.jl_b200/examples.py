@@ -189,3 +189,61 @@ def dam_break_plate_2d(fluid_particle_spacing=0.01, *, n_particles_x=5, eltype=n
         poisson_ratio=nu, boundary_model=model_structure, clamped_particles=range(clamped.nparticles),
         acceleration=(0.0, -gravity), penalty_force=PenaltyForceGanzenmueller(alpha=0.01))
     return fluid, wall, structure_system, tank
+
+
+def hydrostatic_water_column_fsi_2d(n_particles_plate_y=3, *, eltype=np.float64, coordinates_eltype=None,
+                                    initial_fluid_size=(1.0, 2.0), plate_size=(1.0, 0.05), E=67.5e9, nu=0.3,
+                                    sound_speed=50.0, damping_coefficient=0.05):
+    """examples/fsi/hydrostatic_water_column_2d.jl:13-177 with `use_edac = false`: a water column resting on an
+    elastic aluminium plate clamped at both ends.  WCSPH fluid (ContinuityDensity, Molteni-Colagrossi diffusion,
+    SourceTermDamping), tank with side walls only, TLSPH plate whose particles are dummy particles with
+    AdamiPressureExtrapolation towards the fluid.  The validation run of the reference
+    (validation/hydrostatic_water_column_2d/validation.jl, test/validation/validation.jl:95-109) compares the
+    mid-plate deflection with `analytical_value`.
+    Returns (structure_system, fluid_system, boundary_system, info) -- the system order of the example."""
+    from .model import DensityDiffusionMolteniColagrossi, SourceTermDamping
+    t = np.dtype(eltype).type
+    coordinates_eltype = coordinates_eltype or np.float64
+    gravity, boundary_layers, spacing_ratio = 9.81, 3, 1
+    fluid_density, structure_density = 1000.0, 2700.0
+    ds = plate_size[1] / (n_particles_plate_y - 1)                    # structure = fluid particle spacing
+    dx = ds
+    D = E * plate_size[1] ** 3 / (12 * (1 - nu ** 2))
+    analytical_value = -0.0026 * gravity * (fluid_density * initial_fluid_size[1] +
+                                            structure_density * plate_size[1]) / D
+    n_plate_x = int(np.rint(plate_size[0] / ds + 1))
+    shape = lambda n, mc: RectangularShape(ds, n, mc, density=structure_density, place_on_shell=True,
+                                           coordinates_eltype=coordinates_eltype, eltype=eltype)
+    plate = shape((n_plate_x, n_particles_plate_y), (0.0, -plate_size[1]))
+    left_wall = shape((3, n_particles_plate_y), (-3 * ds, -plate_size[1]))
+    right_wall = shape((3, n_particles_plate_y), (plate_size[0] + ds, -plate_size[1]))
+    fixed = union(left_wall, right_wall)
+    geometry = union(fixed, plate)
+    kernel = WendlandC2Kernel(2)
+    h_s = h_f = np.sqrt(2) * ds
+    state_equation = StateEquationCole(sound_speed=float(t(sound_speed)), reference_density=fluid_density, exponent=7,
+                                       clip_negative_pressure=False)
+    tank = RectangularTank(dx, initial_fluid_size, (plate_size[0], 3.0), fluid_density,
+                           min_coordinates=(0.0, dx / 2), n_layers=boundary_layers, spacing_ratio=spacing_ratio,
+                           faces=(True, True, False, False), acceleration=(0.0, -gravity),
+                           state_equation=state_equation, coordinates_eltype=coordinates_eltype, eltype=eltype)
+    fluid = WeaklyCompressibleSPHSystem(
+        tank.fluid, smoothing_kernel=kernel, smoothing_length=h_f, density_calculator=ContinuityDensity(),
+        state_equation=state_equation, density_diffusion=DensityDiffusionMolteniColagrossi(delta=0.1),
+        acceleration=(0.0, -gravity), source_terms=SourceTermDamping(damping_coefficient=damping_coefficient))
+    model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass, AdamiPressureExtrapolation(),
+                                        kernel, h_f, state_equation=state_equation)
+    wall = WallBoundarySystem(tank.boundary, model)
+    hyd_rho = t(fluid_density) * np.ones(geometry.nparticles, dtype=eltype)
+    hyd_mass = (hyd_rho * t(ds) ** 2).astype(eltype)
+    model_structure = BoundaryModelDummyParticles(hyd_rho, hyd_mass, AdamiPressureExtrapolation(), kernel, h_s,
+                                                  state_equation=state_equation)
+    structure = TotalLagrangianSPHSystem(
+        geometry, smoothing_kernel=kernel, smoothing_length=h_s, young_modulus=E, poisson_ratio=nu,
+        boundary_model=model_structure, clamped_particles=range(fixed.nparticles), acceleration=(0.0, -gravity))
+    # validation.jl:15-21: the particle in the middle of the plate (1-based, in the system's own order: the
+    # clamped particles are moved behind the plate's)
+    mid = int(n_plate_x * (n_particles_plate_y + 1) / 2 - (n_plate_x + 1) / 2 + 1)
+    info = dict(analytical_value=analytical_value, mid_particle=mid - 1, plate_size=plate_size, tank=tank,
+                n_particles_plate=(n_plate_x, n_particles_plate_y))
+    return structure, fluid, wall, info
