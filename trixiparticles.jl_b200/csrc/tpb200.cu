@@ -1966,8 +1966,12 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     CUDA_TRY(s, cudaMalloc(&s->d_vmax2, sizeof(unsigned long long)));
     CUDA_TRY(s, cudaHostAlloc(&s->h_vmax2, sizeof(unsigned long long), cudaHostAllocDefault));
     if (s->cfg.eltype == TPB_F32 && s->cfg.coords_eltype == TPB_F64) {
-        CUDA_TRY(s, cudaMalloc(&s->d_Ff, sizeof(float) * 4 * nf));
-        CUDA_TRY(s, cudaMalloc(&s->d_Fw, sizeof(float) * 4 * nw));
+        // (+8 records of slack like the other sorted arrays: the bulk copies of a tile round their runs up
+        // to four records -- compute-sanitizer found the last run of a small system one record over)
+        CUDA_TRY(s, cudaMalloc(&s->d_Ff, sizeof(float) * 4 * (nf + 8)));
+        CUDA_TRY(s, cudaMalloc(&s->d_Fw, sizeof(float) * 4 * (nw + 8)));
+        CUDA_TRY(s, cudaMemset(s->d_Ff, 0, sizeof(float) * 4 * (nf + 8)));
+        CUDA_TRY(s, cudaMemset(s->d_Fw, 0, sizeof(float) * 4 * (nw + 8)));
     }
     CUDA_TRY(s, cudaMemset(s->d_A, 0, 4 * cs * (nf + 8)));
     CUDA_TRY(s, cudaMemset(s->d_B, 0, 4 * ts * (nf + 8)));

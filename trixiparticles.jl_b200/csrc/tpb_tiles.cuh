@@ -45,6 +45,13 @@
 #ifndef TPB_INTERLEAVE
 #define TPB_INTERLEAVE 1  // 1: the KS threads of a target take every KS-th candidate; 0: every KS-th group of four
 #endif
+#ifndef TPB_LIST_MASKS
+// 1: list entries are (first candidate, 8-bit accept mask) per group of eight candidates -- phase 1 shrinks from 91
+// to 64 instructions per eight candidates (one funnel shift per verdict, one store per group), but phase 2 then has
+// to find its pairs with CLZ in a per-lane loop: measured 0.880 ms (one pair at a time) / 0.908 ms (four decoded
+// ahead) against 0.852 ms for 0: one 16-bit index per accepted candidate.  Kept as an experiment.
+#define TPB_LIST_MASKS 0
+#endif
 
 namespace tpb {
 
@@ -556,6 +563,22 @@ struct Filter<ND, float, float> {
         }
         return d2 <= r2;
     }
+    // d^2 - r2 with -r2 folded into the packed square (FFMA2): the SIGN BIT is the filter's verdict, so that a
+    // funnel shift can collect it (the radius carries the margin: a true neighbour is strictly inside)
+    __device__ __forceinline__ float margin(const V4<float> &xi, const V4<float> &xj) const
+    {
+        unsigned long long dxy, sq;
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dxy) : "l"(pack_f32x2(xi.x, xi.y)), "l"(pack_f32x2(xj.x, xj.y)));
+        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(sq) : "l"(dxy), "l"(pack_f32x2(-r2, 0.0f)));
+        float sx, sy;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(sx), "=f"(sy) : "l"(sq));
+        float s = sx + sy;
+        if (ND == 3) {
+            float dz = xi.z - xj.z;
+            s = fmaf(dz, dz, s);
+        }
+        return s;
+    }
 };
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
 {
@@ -582,6 +605,24 @@ __device__ __forceinline__ uint32_t list_append(uint32_t lpa, uint32_t idx, bool
                  "}"
                  : "=r"(next)
                  : "r"(lpa), "r"((uint32_t)pass), "r"(idx), "n"(ESTEP)
+                 : "memory");
+    return next;
+}
+// The same for a 32-bit entry (TPB_LIST_MASKS): (first candidate of a group << 8) | accept mask of the group.
+template <int ESTEP>
+__device__ __forceinline__ uint32_t entry_append(uint32_t lpa, uint32_t entry, bool nonempty)
+{
+    uint32_t next;
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 ".reg .b32 t;\n"
+                 "setp.ne.u32 p, %2, 0;\n"
+                 "@p st.shared.u32 [%1], %3;\n"
+                 "add.u32 t, %1, %4;\n"
+                 "selp.u32 %0, t, %1, p;\n"
+                 "}"
+                 : "=r"(next)
+                 : "r"(lpa), "r"((uint32_t)nonempty), "r"(entry), "n"(ESTEP)
                  : "memory");
     return next;
 }
@@ -725,6 +766,61 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
     // chunked mode: thread 0 is about to rewrite the header every thread has just read
     if (!staged) __syncthreads();
 
+    auto visit = [&](int idx) {
+        if constexpr (NB::HAS_P)
+            body(sm.tA[idx], tB[idx], sm.tP[idx]);
+        else
+            body(sm.tA[idx], tB[idx], (T)0);
+    };
+    constexpr int CS = TPB_INTERLEAVE ? KS : 1;   // distance between the candidates of one group
+    constexpr int STEP = 4 * KS;                  // distance between two groups of one thread
+#if TPB_LIST_MASKS
+    // private list of 32-bit entries, entry e of thread t at list32[e * NT + t] (conflict-free): a group of
+    // eight candidates (t + u CS, u = 0..3, and t + STEP + u CS) and the filter's verdicts as a bit mask,
+    // candidate u at bit 7 - u.  Against one 16-bit index per accepted candidate this costs one funnel shift
+    // per candidate instead of a compare, a predicated store and two address updates, and one store per
+    // group: 91 -> 64 instructions per eight candidates in phase 1; phase 2 finds its pairs with CLZ.
+    uint32_t *const my_list = reinterpret_cast<uint32_t *>(sm.list) + tid;
+    const uint32_t list_a = smem_u32(my_list);
+    const uint32_t list_end_a = list_a + (uint32_t)(sm.list_len / 2) * NT * 4u;
+    constexpr uint32_t ESTEP = NT * 4u;  // bytes between consecutive entries of one thread
+    uint32_t lpa = list_a;               // append position (shared-memory address)
+    auto room = [&](int n) { return lpa + n * ESTEP <= list_end_a; };
+    auto push_verdict = [&](uint32_t m, const FRec &c) -> uint32_t {
+        if constexpr (HAS_F)
+            return __funnelshift_l(__float_as_uint(ffilter.margin(xf, c)), m, 1);
+        else if constexpr (std::is_same<T, float>::value && std::is_same<CT, float>::value)
+            return __funnelshift_l(__float_as_uint(filter.margin(xi, c)), m, 1);
+        else
+            return (m << 1) | (uint32_t)pass(c);
+    };
+    auto flush = [&]() {
+        const uint32_t *e = my_list;
+        const uint32_t *const lp = my_list + (size_t)((lpa - list_a) / ESTEP) * NT;
+        uint32_t cur = 0;
+        constexpr int PF = TPB_P2_UNROLL;  // pairs in flight: decode PF candidates first, then run their bodies
+        for (;;) {
+            int idx[PF];
+#pragma unroll
+            for (int q = 0; q < PF; ++q) {
+                if ((cur & 0xFFu) == 0 && e < lp) {  // (stored entries never have an empty mask)
+                    cur = *e;
+                    e += NT;
+                }
+                const uint32_t m = cur & 0xFFu;
+                const int b = 31 - __clz((int)m);      // m == 0: b = -1
+                const int u = 7 - b;
+                idx[q] = m ? (int)(cur >> 8) + (u < 4 ? u * CS : STEP + (u - 4) * CS) : -1;
+                cur &= ~((m ? 1u : 0u) << (b & 31));
+            }
+            if (idx[0] < 0) break;  // the list is consumed in order: no first pair, nothing left
+#pragma unroll
+            for (int q = 0; q < PF; ++q)
+                if (idx[q] >= 0) visit(idx[q]);
+        }
+        lpa = list_a;
+    };
+#else
     // private list: entry e of thread t lives at list[e * NT + t] (conflict-free)
     unsigned short *const my_list = sm.list + tid;
     const uint32_t list_a = smem_u32(my_list);
@@ -732,12 +828,6 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
     constexpr uint32_t ESTEP = NT * 2u;  // bytes between consecutive entries of one thread
     uint32_t lpa = list_a;               // append position (shared-memory address)
     auto room = [&](int n) { return lpa + n * ESTEP <= list_end_a; };
-    auto visit = [&](int idx) {
-        if constexpr (NB::HAS_P)
-            body(sm.tA[idx], tB[idx], sm.tP[idx]);
-        else
-            body(sm.tA[idx], tB[idx], (T)0);
-    };
     auto flush = [&]() {
         const unsigned short *e = my_list;
         const unsigned short *const lp = my_list + (lpa - list_a) / 2u;
@@ -752,6 +842,7 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
         for (; e < lp; e += NT) visit(e[0]);
         lpa = list_a;
     };
+#endif
 
     while (true) {
         // ---- oversized neighbourhood: thread 0 stages the next chunk of whole rows (or one
@@ -843,11 +934,40 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
             // pairs -- concentrated in the middle of every row -- are dealt out evenly and the three
             // lists of a target (and with them the lanes of a warp in phase 2) end up equally long;
             // otherwise groups of four consecutive candidates are dealt out.
-            constexpr int CS = TPB_INTERLEAVE ? KS : 1;   // distance between the candidates of one group
-            constexpr int STEP = 4 * KS;                  // distance between two groups of one thread
             int t = t0 + (TPB_INTERLEAVE ? kg : 4 * kg);
             while (true) {
                 // phase 1: filter candidates into the private list
+#if TPB_LIST_MASKS
+                while (t + STEP + 3 * CS < t1 && room(1)) {
+                    FRec xc[8];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) xc[u] = tFilt[t + u * CS];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) xc[4 + u] = tFilt[t + STEP + u * CS];
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) m = push_verdict(m, xc[u]);
+                    m &= 0xFFu;
+                    lpa = entry_append<ESTEP>(lpa, ((uint32_t)t << 8) | m, m != 0);
+                    t += 2 * STEP;
+                }
+                while (t < t1 && room(1)) {
+                    // one group of four, the last one possibly partial (records past t1 are staged
+                    // neighbours of other lanes or padding: read, never accepted)
+                    FRec xc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) xc[u] = tFilt[t + u * CS];
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        m = push_verdict(m, xc[u]);
+                        if (t + u * CS >= t1) m &= ~1u;
+                    }
+                    m = (m & 0xFu) << 4;  // candidates 0..3 of the group: bits 7..4
+                    lpa = entry_append<ESTEP>(lpa, ((uint32_t)t << 8) | m, m != 0);
+                    t += STEP;
+                }
+#else
                 while (t + STEP + 3 * CS < t1 && room(8)) {
                     FRec xc[8];
 #pragma unroll
@@ -872,6 +992,7 @@ __device__ __forceinline__ void tile_sweep_staged(TileSmem<T, CT> &sm, const Gri
                         lpa = list_append<ESTEP>(lpa, (uint32_t)(t + u * CS), t + u * CS < t1 && pass(xc[u]));
                     t += STEP;
                 }
+#endif
                 if (!__any_sync(0xffffffffu, t < t1)) break;
                 flush();  // phase 2 (some list of the warp is full)
             }
@@ -933,6 +1054,43 @@ __device__ __forceinline__ void tile_reduce(TileSmem<T, CT> &sm, T (&val)[NVAL])
         constexpr int W = (int)sizeof(T) / 2;  // 16-bit slots per value
         const int ti = threadIdx.x % TILE_TB, kg = threadIdx.x / TILE_TB;
         const int bar_id = 1 + ti / 32;
+#if TPB_LIST_MASKS
+        // 32-bit list entries: entry e of thread t is the word list32[e * NT + t], so a thread parks value n
+        // in its OWN entries n * W32 .. (private: warps that are still sweeping are not disturbed)
+        constexpr int W32 = (int)sizeof(T) / 4;
+        uint32_t *const l32 = reinterpret_cast<uint32_t *>(sm.list);
+        auto put = [&](int tid, int n, T v) {
+            if constexpr (W32 == 1) {
+                l32[n * NT + tid] = __float_as_uint((float)v);
+            } else {
+                const unsigned long long b = (unsigned long long)__double_as_longlong((double)v);
+                l32[(2 * n) * NT + tid] = (uint32_t)b;
+                l32[(2 * n + 1) * NT + tid] = (uint32_t)(b >> 32);
+            }
+        };
+        auto get = [&](int tid, int n) -> T {
+            if constexpr (W32 == 1) {
+                return (T)__uint_as_float(l32[n * NT + tid]);
+            } else {
+                const unsigned long long b = (unsigned long long)l32[(2 * n) * NT + tid] |
+                                             ((unsigned long long)l32[(2 * n + 1) * NT + tid] << 32);
+                return (T)__longlong_as_double((long long)b);
+            }
+        };
+        (void)W;
+        if (kg > 0) {
+#pragma unroll
+            for (int n = 0; n < NVAL; ++n) put(threadIdx.x, n, val[n]);
+            __threadfence_block();
+            named_barrier<false, 32 * KS>(bar_id);
+        } else {
+            named_barrier<true, 32 * KS>(bar_id);
+#pragma unroll
+            for (int k = 1; k < KS; ++k)
+#pragma unroll
+                for (int n = 0; n < NVAL; ++n) val[n] += get(k * TILE_TB + ti, n);
+        }
+#else
         auto slot = [&](int tid, int n) {
             return reinterpret_cast<T *>(sm.list + (n + RED * (tid % W)) * NT + (tid - tid % W));
         };
@@ -949,6 +1107,7 @@ __device__ __forceinline__ void tile_reduce(TileSmem<T, CT> &sm, T (&val)[NVAL])
 #pragma unroll
                 for (int n = 0; n < NVAL; ++n) val[n] += *slot(k * TILE_TB + ti, n);
         }
+#endif
     }
 }
 
