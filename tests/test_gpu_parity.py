@@ -465,6 +465,33 @@ def test_kick_several_wall_systems(oracle, no_slip):
                           (0.0, 1.0))
 
 
+def test_kick_monaghan_kajtar_wall(oracle):
+    """`WallBoundarySystem(tank.boundary, BoundaryModelMonaghanKajtar(0.5, spacing_ratio, spacing, mass))` -- the
+    "dam_break_2d_gpu.jl Float32 BoundaryModelMonaghanKajtar" case of the reference's GPU tests
+    (test/examples/gpu.jl:219-253; boundary_layers = 1, spacing_ratio = 3): repulsive wall particles
+    (monaghan_kajtar.jl:48-111).  The oracle side is the FSI oracle with the wall as an all-clamped structure."""
+    from trixiparticles.jl_b200.model import BoundaryModelMonaghanKajtar
+    for eltype, tol in ((np.float64, 1e-11), (np.float32, 2e-5)):
+        fluid, wall, _ = examples.dam_break_2d(20, eltype=eltype, coordinates_eltype=eltype,
+                                               boundary_model="monaghan_kajtar", boundary_layers=1, spacing_ratio=3)
+        assert isinstance(wall.boundary_model, BoundaryModelMonaghanKajtar) and wall.n_integrated_particles == 0
+        u, v = examples.perturbed_state(fluid)
+        st = tp.TotalLagrangianSPHSystem(wall.initial_condition, smoothing_kernel=fluid.smoothing_kernel,
+                                         smoothing_length=fluid.smoothing_length, young_modulus=1.0, poisson_ratio=0.0,
+                                         boundary_model=wall.boundary_model, clamped_particles=range(wall.nparticles))
+        ref = adapter.kick_fsi(fluid, None, st, u.reshape(-1), v.reshape(-1))["dv"].reshape(v.shape)
+        free = adapter.kick(fluid, None, u, v)["dv"]
+        assert np.abs(ref - free).max() > 1.0          # the wall pushes back
+        semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend())
+        ode = tp.semidiscretize(semi, (0.0, 1.0))
+        assert semi.ranges_v[-1] == (v.size, v.size)
+        dv = np.full(v.size, np.nan, dtype=v.dtype)
+        tp.kick_(dv, v.reshape(-1).copy(), np.ascontiguousarray(u).reshape(-1), ode.p, 0.0)
+        dv = dv.reshape(v.shape)
+        assert rel_inf(dv[:, :2], ref[:, :2]) <= tol and rel_inf(dv[:, 2], ref[:, 2]) <= tol
+        semi.close()
+
+
 def test_adaptive_cole_device_path_equals_host_path(monkeypatch):
     """The speed of sound stays on the device (k_max_speed2 -> k_adaptive_consts -> the kernels read
     AdaptConsts; no host round trip, so the kick can be captured in a CUDA graph); TPB_ADAPTIVE_HOST

@@ -175,6 +175,36 @@ def test_adaptive_cole_time_loop_replays_from_a_cuda_graph():
     assert c_e == pytest.approx(min(100.0, max(10.0, vmax / 0.1)), rel=0.2)   # Mach-number target 0.1, last kick's state
 
 
+@pytest.mark.parametrize("variant", ["continuity_density_boundary", "monaghan_kajtar_boundary"])
+def test_dam_break_2d_boundary_model_variants_of_the_gpu_matrix(variant):
+    """test/examples/gpu.jl:198-253: dam_break_2d_gpu.jl in Float32 to t = 0.1 with
+    `boundary_density_calculator = ContinuityDensity()` (the wall density is integrated along) and with
+    `BoundaryModelMonaghanKajtar(0.5, spacing_ratio, spacing, mass)` on one layer of wall particles
+    (boundary_layers = 1, spacing_ratio = 3); the reference asks for `retcode == Success`."""
+    import trixiparticles.jl_b200 as tp
+    from trixiparticles.jl_b200 import examples
+    from trixiparticles.jl_b200.time_integration import CarpenterKennedy2N54, StepsizeCallback, solve
+    kw = (dict(boundary_density_calculator=tp.ContinuityDensity()) if variant == "continuity_density_boundary"
+          else dict(boundary_model="monaghan_kajtar", boundary_layers=1, spacing_ratio=3))
+    fluid, wall, tank = examples.dam_break_2d(40, eltype=np.float32, coordinates_eltype=np.float32, **kw)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 0.1))
+    sol = solve(ode, CarpenterKennedy2N54(williamson_condition=False), callback=[StepsizeCallback(cfl=0.9)])
+    assert sol.retcode == "Success"
+    u, v = sol.u.cpu().numpy(), sol.v.cpu().numpy()
+    assert np.isfinite(u).all() and np.isfinite(v).all()
+    n_f = fluid.nparticles
+    x = u[: 2 * n_f].reshape(n_f, 2)
+    assert x[:, 0].max() > 1.2 + 0.01                      # the column has started to run
+    assert x[:, 1].min() > -0.05 and x[:, 0].min() > -0.05  # nothing went through the wall
+    if variant == "continuity_density_boundary":
+        rho_w = v[3 * n_f:]
+        assert rho_w.size == wall.nparticles
+        assert np.abs(rho_w / 1000.0 - 1.0).max() < 0.2     # integrated wall density stays physical
+        assert np.abs(rho_w - wall.boundary_model.initial_density).max() > 0   # ... and has moved
+    semi.close()
+
+
 def test_float32_run_tracks_float64_trace():
     import run_dam_break_validation as V
     r = V.run(t_end=0.3, eltype=np.float32)

@@ -18,8 +18,12 @@ from .setups import RectangularShape, RectangularTank, union
 
 
 def dam_break_2d(particles_per_height=40, *, eltype=np.float64, coordinates_eltype=np.float64,
-                 density_calculator=None, alpha=0.02, delta=0.1, sound_speed_factor=20.0):
-    """examples/fluid/dam_break_2d.jl:19-97 (BASELINE config 1 at particles_per_height=40)."""
+                 density_calculator=None, alpha=0.02, delta=0.1, sound_speed_factor=20.0,
+                 boundary_density_calculator=None, boundary_model=None, boundary_layers=4, spacing_ratio=1):
+    """examples/fluid/dam_break_2d.jl:19-97 (BASELINE config 1 at particles_per_height=40).
+    `boundary_density_calculator=ContinuityDensity()` and `boundary_model="monaghan_kajtar"` (with
+    `boundary_layers=1, spacing_ratio=3`) are the variants of the reference's GPU tests
+    (test/examples/gpu.jl:198-253)."""
     t = np.dtype(eltype).type
     H = 0.6
     W = 2 * H
@@ -29,7 +33,7 @@ def dam_break_2d(particles_per_height=40, *, eltype=np.float64, coordinates_elty
     sound_speed = sound_speed_factor * np.sqrt(gravity * H)
     state_equation = StateEquationCole(sound_speed=float(t(sound_speed)), reference_density=1000.0,
                                        exponent=1, clip_negative_pressure=False)
-    tank = RectangularTank(dx, (W, H), tank_size, 1000.0, n_layers=4, spacing_ratio=1,
+    tank = RectangularTank(dx, (W, H), tank_size, 1000.0, n_layers=boundary_layers, spacing_ratio=spacing_ratio,
                            acceleration=(0.0, -gravity), state_equation=state_equation,
                            coordinates_eltype=coordinates_eltype, eltype=eltype)
     h = 2 * dx
@@ -41,9 +45,13 @@ def dam_break_2d(particles_per_height=40, *, eltype=np.float64, coordinates_elty
         density_diffusion=(None if isinstance(dc, SummationDensity)
                            else DensityDiffusionMolteniColagrossi(delta=delta)),
         acceleration=(0.0, -gravity))
-    model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass,
-                                        AdamiPressureExtrapolation(), kernel, h,
-                                        state_equation=state_equation, clip_negative_pressure=True)
+    if boundary_model == "monaghan_kajtar":
+        from .model import BoundaryModelMonaghanKajtar
+        model = BoundaryModelMonaghanKajtar(0.5, spacing_ratio, dx / spacing_ratio, tank.boundary.mass)
+    else:
+        model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass,
+                                            boundary_density_calculator or AdamiPressureExtrapolation(), kernel, h,
+                                            state_equation=state_equation, clip_negative_pressure=True)
     wall = WallBoundarySystem(tank.boundary, model)
     return fluid, wall, tank
 

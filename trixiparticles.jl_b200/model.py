@@ -314,7 +314,8 @@ class WallBoundarySystem:
     nparticles = property(lambda self: self.initial_condition.nparticles)
     # wall_boundary/system.jl:78-90: nothing is integrated, except the density of dummy particles with
     # `ContinuityDensity` (one v variable per particle, no u variable)
-    integrates_density = property(lambda self: isinstance(self.boundary_model.density_calculator, ContinuityDensity))
+    integrates_density = property(lambda self: isinstance(getattr(self.boundary_model, "density_calculator", None),
+                                                          ContinuityDensity))
     n_integrated_particles = property(lambda self: self.nparticles if self.integrates_density else 0)
     u_nvariables = property(lambda self: 0)
     v_nvariables = property(lambda self: 1)

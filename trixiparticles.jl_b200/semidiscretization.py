@@ -17,6 +17,7 @@ import numpy as np
 
 from . import _lib
 from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan, BoundaryModelDummyParticles,
+                    BoundaryModelMonaghanKajtar,
                     ContinuityDensity,
                     DensityDiffusionMolteniColagrossi, SourceTermDamping, StateEquationAdaptiveCole,
                     SummationDensity, TotalLagrangianSPHSystem, WallBoundarySystem,
@@ -289,6 +290,28 @@ class Semidiscretization:
                     _lib.check(h, L.tpb_add_structure_system(h, C.byref(sp), s.nparticles, s.n_integrated_particles,
                                                              x0.ctypes.data, mass.ctypes.data, rho.ctypes.data,
                                                              hyd.ctypes.data if hyd is not None else None,
+                                                             C.byref(idx)))
+                elif isinstance(s.boundary_model, BoundaryModelMonaghanKajtar):
+                    # a wall of repulsive particles (test/examples/gpu.jl:219-253): inside the library the
+                    # Monaghan-Kajtar coupling belongs to the structure path, and a static wall is a structure
+                    # without integrated particles (all clamped) -- no entries in the ODE vectors, like a wall
+                    if self.structure is not None:
+                        raise ValueError("a Monaghan-Kajtar wall and a structure system in one semidiscretization "
+                                         "are outside the accelerated path")
+                    m = s.boundary_model
+                    t = self.eltype.type
+                    sp = _lib.StructureParams()
+                    sp.struct_size = C.sizeof(_lib.StructureParams)
+                    sp.kernel = self.fluid.smoothing_kernel.kernel_id
+                    sp.smoothing_length = float(t(self.fluid.smoothing_length))
+                    sp.young_modulus, sp.poisson_ratio = 1.0, 0.0
+                    sp.boundary_model = _lib.BOUNDARY_MONAGHAN_KAJTAR
+                    sp.mk_K, sp.mk_beta, sp.mk_spacing = float(t(m.K)), float(t(m.beta)), float(t(m.boundary_particle_spacing))
+                    x0 = np.ascontiguousarray(s.coordinates, dtype=self.coordinates_eltype)
+                    hyd = np.ascontiguousarray(m.hydrodynamic_mass, dtype=self.eltype)
+                    rho = np.ones(s.nparticles, dtype=self.eltype)
+                    _lib.check(h, L.tpb_add_structure_system(h, C.byref(sp), s.nparticles, 0, x0.ctypes.data,
+                                                             hyd.ctypes.data, rho.ctypes.data, hyd.ctypes.data,
                                                              C.byref(idx)))
                 else:
                     coords = np.ascontiguousarray(s.coordinates, dtype=self.coordinates_eltype)
