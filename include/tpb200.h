@@ -283,6 +283,18 @@ int32_t tpb_get_sound_speed(tpb_semi_t semi, double *out);
  * a kick of a handle with ghost particles and an adaptive state equation fails with TPB_ERR_STATE
  * unless tpb_set_max_speed2 preceded it. */
 int32_t tpb_max_speed2(tpb_semi_t semi, const void *v_ode, void *out_bits);
+/* ---- SplitIntegrationCallback (callbacks/split_integration.jl): the structure is integrated by its own
+ * sub-integrator with smaller steps.  `tpb_set_integrate_structure(h, 0)` = `semi.integrate_tlsph[] = false`
+ * (semidiscretization.jl:149, :868-880, :545-552): tpb_kick / tpb_drift leave the structure's rows of dv / du
+ * zero, the fluid still feels the structure.  `tpb_structure_fluid_force` = update_systems_and_nhs +
+ * other_interaction_split! (:232-234, :444-470): the force of the fluid on the integrated structure particles
+ * for the state (v_ode, u_ode), ND x n_integrated values.  `tpb_kick_structure` = kick_split! (:352-371) on the
+ * structure's own vectors (ND x n_integrated each): structure <- structure + `dv_const` (may be NULL) +
+ * gravity.  Device vectors only; stream-ordered. */
+int32_t tpb_set_integrate_structure(tpb_semi_t semi, int32_t enabled);
+int32_t tpb_structure_fluid_force(tpb_semi_t semi, void *dv_split, const void *v_ode, const void *u_ode);
+int32_t tpb_kick_structure(tpb_semi_t semi, void *dv_split, const void *v_split, const void *u_split,
+                           const void *dv_const);
 int32_t tpb_set_max_speed2(tpb_semi_t semi, const void *bits);
 
 /* ---- device ODE-vector algebra ----------------------------------------------------------------

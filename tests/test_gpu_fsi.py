@@ -155,3 +155,85 @@ def test_hydrostatic_water_column_fsi_validation_trace():
     assert r["rel_error"] <= 0.045               # the reference's own bar
     ref_avg = ry[rt >= 0.25 - 1e-12].mean()
     assert abs(r["avg"] - ref_avg) <= 1e-3 * a
+
+
+def test_split_integration_pieces_match_oracle():
+    """The three entry points of the SplitIntegrationCallback (callbacks/split_integration.jl): with
+    `integrate_tlsph = false` kick! / drift! leave the structure's rows zero while the fluid still feels the plate;
+    `tpb_structure_fluid_force` (other_interaction_split!) + `tpb_kick_structure` (kick_split!) together give the
+    structure rows of the full oracle kick."""
+    import ctypes as C
+    import torch
+    from trixiparticles.jl_b200 import _lib
+    for bm in ("monaghan_kajtar", "dummy_particles"):
+        fluid, wall, structure, _ = examples.dam_break_plate_2d(
+            0.01, initial_fluid_size=(0.15, 0.29), plate_position=(0.165, 0.0), structure_boundary_model=bm)
+        u, v = fsi_state(fluid, structure)
+        ref = adapter.kick_fsi(fluid, wall, structure, u, v)["dv"]
+        semi = tp.Semidiscretization(fluid, wall, structure,
+                                     parallelization_backend=tp.B200Backend(device=0, ode_memory="device"))
+        ode = tp.semidiscretize(semi, (0.0, 1.0))
+        dev = ode.u0.device
+        u_d, v_d = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev)
+        n_f, n_int = fluid.nparticles, structure.n_integrated_particles
+        semi.set_integrate_structure(False)
+        dv_d, du_d = torch.full_like(v_d, float("nan")), torch.full_like(u_d, float("nan"))
+        ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
+        ode.f2(du_d, v_d, u_d, ode.p, 0.0)
+        semi.synchronize()
+        dv, du = dv_d.cpu().numpy(), du_d.cpu().numpy()
+        assert np.all(dv[3 * n_f:] == 0) and np.all(du[2 * n_f:] == 0)
+        assert np.abs(dv[: 3 * n_f] - ref[: 3 * n_f]).max() <= 1e-11 * np.abs(ref[: 3 * n_f]).max()
+        L, h = _lib.load(), semi._handle
+        force = torch.full((2 * n_int,), float("nan"), dtype=v_d.dtype, device=dev)
+        dv_s = torch.full_like(force, float("nan"))
+        _lib.check(h, L.tpb_structure_fluid_force(h, C.c_void_p(force.data_ptr()), C.c_void_p(v_d.data_ptr()),
+                                                  C.c_void_p(u_d.data_ptr())))
+        v_s, u_s = v_d[3 * n_f:].clone(), u_d[2 * n_f:].clone()
+        _lib.check(h, L.tpb_kick_structure(h, C.c_void_p(dv_s.data_ptr()), C.c_void_p(v_s.data_ptr()),
+                                           C.c_void_p(u_s.data_ptr()), C.c_void_p(force.data_ptr())))
+        semi.synchronize()
+        got, want = dv_s.cpu().numpy(), ref[3 * n_f:]
+        assert np.abs(force.cpu().numpy()).max() > 0
+        assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max(), bm
+        semi.close()
+
+
+def test_dam_break_plate_2d_split_integration():
+    """test/examples/gpu.jl:662-705: `fsi/dam_break_plate_2d.jl` with a SplitIntegrationCallback (CarpenterKennedy2N54
+    sub-integrator, dt = 5e-5, stage_coupling = true) in Float32, stiffer plate (E = 1e7) moved next to the water
+    column, tspan = (0, 0.2): the reference verifies that fewer than 400 iterations of the main integrator are
+    needed (its step is set by the fluid alone).  Here also: the plate's tip follows the monolithic run, which
+    integrates everything with the plate's step."""
+    from trixiparticles.jl_b200.time_integration import (CarpenterKennedy2N54, SplitIntegrationCallback,
+                                                         StepsizeCallback, solve)
+
+    def run(split):
+        fluid, wall, structure, _ = examples.dam_break_plate_2d(
+            0.01, eltype=np.float32, coordinates_eltype=np.float32, initial_fluid_size=(0.15, 0.29),
+            plate_position=(0.2, 0.0), E=1e7)
+        semi = tp.Semidiscretization(fluid, wall, structure,
+                                     parallelization_backend=tp.B200Backend(device=0, ode_memory="device"))
+        ode = tp.semidiscretize(semi, (0.0, 0.2))
+        cbs = [StepsizeCallback(cfl=1.2)]
+        if split:
+            cbs.append(SplitIntegrationCallback(CarpenterKennedy2N54(williamson_condition=False), stage_coupling=True,
+                                                dt=5e-5))
+        sol = solve(ode, CarpenterKennedy2N54(williamson_condition=False), callback=cbs,
+                    maxiters=400 if split else 10 ** 6, cuda_graph=not split)
+        u = sol.u.cpu().numpy()
+        n_f, n_int = fluid.nparticles, structure.n_integrated_particles
+        tip = u[2 * n_f:].reshape(n_int, 2)[-1] - structure.initial_coordinates[n_int - 1]
+        out = dict(nsteps=sol.nsteps, t=sol.t, tip=tip, finite=bool(np.isfinite(u).all()),
+                   substeps=cbs[-1].n_substeps if split else 0)
+        semi.close()
+        return out
+
+    a = run(split=True)
+    assert a["finite"] and abs(a["t"] - 0.2) < 1e-9 and a["nsteps"] < 400, a
+    b = run(split=False)
+    assert b["nsteps"] > 3 * a["nsteps"]                  # the plate's CFL step is far smaller than the fluid's
+    print(f"split: {a['nsteps']} steps + {a['substeps']} sub-steps, tip displacement {a['tip']}; "
+          f"monolithic: {b['nsteps']} steps, tip displacement {b['tip']}")
+    assert a["tip"][0] > 1e-4 and b["tip"][0] > 1e-4     # the water has bent the plate
+    assert abs(a["tip"][0] - b["tip"][0]) <= 0.25 * abs(b["tip"][0]) + 2e-4

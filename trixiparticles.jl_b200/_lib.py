@@ -23,7 +23,8 @@ EXPORTS = [
     "tpb_add_wall_system", "tpb_add_structure_system", "tpb_set_interaction", "tpb_semidiscretize", "tpb_ode_sizes",
     "tpb_system_range", "tpb_kick", "tpb_drift", "tpb_get_system_field", "tpb_neighbor_pairs",
     "tpb_synchronize", "tpb_set_stream", "tpb_get_stats", "tpb_get_sound_speed", "tpb_max_speed2",
-    "tpb_set_max_speed2", "tpb_host_register",
+    "tpb_set_max_speed2", "tpb_set_integrate_structure", "tpb_structure_fluid_force", "tpb_kick_structure",
+    "tpb_host_register",
     "tpb_host_unregister", "tpb_set_profiling", "tpb_get_phase_times",
     "tpb_set_fluid_count", "tpb_set_fluid_mass",
     "tpb_vec_axpby", "tpb_vec_rk2n_stage", "tpb_vec_fill", "tpb_vec_lincomb4", "tpb_vec_verlet_update",
@@ -141,6 +142,9 @@ def load():
     L.tpb_get_sound_speed.restype = i32; L.tpb_get_sound_speed.argtypes = [p, C.POINTER(d)]
     L.tpb_max_speed2.restype = i32; L.tpb_max_speed2.argtypes = [p, p, p]
     L.tpb_set_max_speed2.restype = i32; L.tpb_set_max_speed2.argtypes = [p, p]
+    L.tpb_set_integrate_structure.restype = i32; L.tpb_set_integrate_structure.argtypes = [p, i32]
+    L.tpb_structure_fluid_force.restype = i32; L.tpb_structure_fluid_force.argtypes = [p, p, p, p]
+    L.tpb_kick_structure.restype = i32; L.tpb_kick_structure.argtypes = [p, p, p, p, p]
     u32 = C.c_uint32
     L.tpb_peer_alloc.restype = i32; L.tpb_peer_alloc.argtypes = [i64, C.POINTER(p)]
     L.tpb_peer_free.restype = i32; L.tpb_peer_free.argtypes = [p]

@@ -69,6 +69,7 @@ struct Semi {
     int64_t n_s = 0, n_s_int = 0;
     int struct_fluid[2] = {1, 1};  // interaction_matrix[structure, fluid], [fluid, structure]
     int struct_self = 1;           // interaction_matrix[structure, structure]
+    int integrate_structure = 1;   // semi.integrate_tlsph[] (semidiscretization.jl:149): 0 with a SplitIntegrationCallback
     std::vector<unsigned char> h_x0_s, h_mass_s, h_rho_s, h_hydro_s;
     void *d_x0_s = nullptr, *d_xcur_s = nullptr, *d_mass_s = nullptr, *d_rho_s = nullptr, *d_hydro_s = nullptr;
     void *d_L_s = nullptr, *d_F_s = nullptr, *d_pk1_s = nullptr, *d_As = nullptr, *d_Bs = nullptr;
@@ -665,6 +666,13 @@ struct Ops {
                        (V4<CT> *)s.d_As, (V4<T> *)s.d_Bs);
             }
         }
+        return structure_deformation(s);
+    }
+
+    // deformation gradient + PK1 of every structure particle from the current positions
+    static int structure_deformation(Semi &s)
+    {
+        const int n = (int)s.n_s;
         const StructConst<T> k = make_struct_const(s);
         switch (struct_kernel_id(s)) {
 #define TPB_DEFGRAD(KID)                                                                                          \
@@ -680,37 +688,97 @@ struct Ops {
     }
 
     // per kick, after interact!: fluid <- structure, structure <- fluid, structure <- structure + gravity
+    // mode 0: everything; 1: the structure is not integrated by this kick (split integration,
+    // apply_system_interaction!, semidiscretization.jl:868-880): fluid <- structure only, dv_s = 0;
+    // 2: only structure <- fluid into d_dv_s (other_interaction_split!, split_integration.jl:444-470)
     template <int FK, int DENS>
-    static int interact_structure(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc, T *d_dv_f, T *d_dv_s)
+    static int interact_structure(Semi &s, const GridConst<CT> &g, const PairConst<T> &pc, T *d_dv_f, T *d_dv_s,
+                                  int mode = 0)
     {
         constexpr int NV = DENS == 0 ? ND + 1 : ND;
         const int n = (int)s.n_s, n_int = (int)s.n_s_int;
         if (n == 0) return TPB_OK;
+        const bool fluid_side = mode != 2, structure_side = mode != 1;
+        if (!structure_side && n_int > 0)
+            CUDA_TRY(&s, cudaMemsetAsync(d_dv_s, 0, sizeof(T) * ND * (size_t)n_int, s.stream));
         if (s.sp.boundary_model == TPB_BOUNDARY_DUMMY_PARTICLES) {
             const DummyConst<T> dk = make_dummy_const(s, pc);
-            if (s.struct_fluid[1] && s.n_act > 0)
+            if (fluid_side && s.struct_fluid[1] && s.n_act > 0)
                 LAUNCH(s, (k_fluid_from_struct_dummy<ND, T, CT, FK, DENS>), cdiv(s.n_act, 128), 128, 0, (int)s.n_act, g,
                        s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P, s.d_perm_f,
                        s.d_scell_start, (const V4<CT> *)s.d_As, (const V4<T> *)s.d_Bs, (const T *)s.d_Ps, pc.kern, dk,
                        d_dv_f, (int)s.n_tgt);
-            if (n_int == 0) return TPB_OK;
+            if (n_int == 0 || !structure_side) return TPB_OK;
             LAUNCH(s, (k_struct_from_fluid_dummy<ND, T, CT, FK, DENS>), cdiv(n_int, 128), 128, 0, n_int, g,
                    (const CT *)s.d_xcur_s, (const T *)s.d_mass_s, (const T *)s.d_hydro_s, (const T *)s.d_p_s,
                    (const T *)s.d_rhoh_s, s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B,
                    (const T *)s.d_P, (int)(s.struct_fluid[0] && s.n_act > 0), pc.kern, dk, d_dv_s, s.d_flags);
-            return interact_structure_self(s, d_dv_s);
+            return mode == 2 ? TPB_OK : interact_structure_self(s, d_dv_s);
         }
         const bool coupled = s.sp.boundary_model == TPB_BOUNDARY_MONAGHAN_KAJTAR;
         const MKConst<T> mk = make_mk_const(s, pc);
-        if (coupled && s.struct_fluid[1] && s.n_act > 0)
+        if (fluid_side && coupled && s.struct_fluid[1] && s.n_act > 0)
             LAUNCH(s, (k_fluid_from_struct<ND, T, CT, FK, NV>), cdiv(s.n_act, 128), 128, 0, (int)s.n_act, g,
                    s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.d_perm_f, s.d_scell_start,
                    (const V4<CT> *)s.d_As, (const V4<T> *)s.d_Bs, pc.kern, mk, d_dv_f, (int)s.n_tgt);
-        if (n_int == 0) return TPB_OK;
+        if (n_int == 0 || !structure_side) return TPB_OK;
         LAUNCH(s, (k_struct_from_fluid<ND, T, CT>), cdiv(n_int, 128), 128, 0, n_int, g, (const CT *)s.d_xcur_s,
                (const T *)s.d_mass_s, s.d_fcell_start, (const V4<CT> *)s.d_A,
                (int)(coupled && s.struct_fluid[0] && s.n_act > 0), mk, d_dv_s, s.d_flags);
-        return interact_structure_self(s, d_dv_s);
+        return mode == 2 ? TPB_OK : interact_structure_self(s, d_dv_s);
+    }
+
+    // ---- SplitIntegrationCallback (callbacks/split_integration.jl): the force of the fluid on the structure for
+    // the state (v_ode, u_ode), kept constant during one sub-integration (other_interaction_split!, :444-470,
+    // after update_systems_and_nhs, :232-234): rebuild, structure kinematics + binning + boundary model, then
+    // structure <- fluid alone into `d_out` (ND x n_integrated).  Device vectors.
+    static int structure_fluid_force(Semi &s, void *out, const void *v_ode, const void *u_ode)
+    {
+        if (s.struct_index < 0) return fail(&s, TPB_ERR_STATE, "no structure system");
+        const OdeLayout lay = ode_layout(s);
+        const T *d_v_ode = (const T *)v_ode;
+        const CT *d_u_ode = (const CT *)u_ode;
+        s.ad_kick = nullptr;
+        int rc = rebuild_fluid(s, d_u_ode + lay.off_u_f, d_v_ode + lay.off_v_f);
+        if (rc) return rc;
+        const GridConst<CT> g = make_grid_const<CT>(s);
+        const PairConst<T> pc = make_pair_const<T>(s.fp, ND);
+        rc = update_structure(s, g, pc, d_u_ode + lay.off_u_s, d_v_ode + lay.off_v_s);
+        if (rc) return rc;
+        auto tk = [](int kernel) { return kernel <= 1 ? kernel : kernel <= TPB_KERNEL_WENDLAND_C6 ? 2 : 3; };
+        const int fk = tk(s.fp.kernel);
+        const bool summ = s.fp.density_calculator == TPB_DENSITY_SUMMATION;
+        if (summ) return fail(&s, TPB_ERR_UNSUPPORTED, "split integration: ContinuityDensity fluid only");
+        T *d_out = (T *)out;
+        if (fk == 0) rc = interact_structure<0, 0>(s, g, pc, nullptr, d_out, 2);
+        else if (fk == 1) rc = interact_structure<1, 0>(s, g, pc, nullptr, d_out, 2);
+        else if (fk == 2) rc = interact_structure<2, 0>(s, g, pc, nullptr, d_out, 2);
+        else rc = interact_structure<3, 0>(s, g, pc, nullptr, d_out, 2);
+        if (rc) return rc;
+        CUDA_TRY(&s, cudaGetLastError());
+        return TPB_OK;
+    }
+
+    // kick_split! (split_integration.jl:352-371): the structure alone -- positions from u_split, deformation
+    // gradient and PK1, structure <- structure, + the constant force of the other systems, + gravity
+    static int kick_structure(Semi &s, void *dv_split, const void *v_split, const void *u_split, const void *dv_const)
+    {
+        (void)v_split;  // (no velocity-dependent term: penalty force and stress depend on positions only)
+        if (s.struct_index < 0) return fail(&s, TPB_ERR_STATE, "no structure system");
+        const int n = (int)s.n_s, n_int = (int)s.n_s_int;
+        if (n_int == 0) return TPB_OK;
+        LAUNCH(s, (k_struct_positions<ND, CT>), cdiv((int64_t)n * ND, 256), 256, 0, n, n_int, (const CT *)u_split,
+               (const CT *)s.d_x0_s, (CT *)s.d_xcur_s);
+        int rc = structure_deformation(s);
+        if (rc) return rc;
+        if (dv_const)
+            CUDA_TRY(&s, cudaMemcpyAsync(dv_split, dv_const, sizeof(T) * ND * (size_t)n_int, cudaMemcpyDeviceToDevice, s.stream));
+        else
+            CUDA_TRY(&s, cudaMemsetAsync(dv_split, 0, sizeof(T) * ND * (size_t)n_int, s.stream));
+        rc = interact_structure_self(s, (T *)dv_split);
+        if (rc) return rc;
+        CUDA_TRY(&s, cudaGetLastError());
+        return TPB_OK;
     }
 
     // structure <- structure + gravity (adds to what the fluid has left in dv_s)
@@ -1154,14 +1222,15 @@ struct Ops {
         }
         if (s.struct_index >= 0) {
             T *d_dv_s = d_dv_ode + lay.off_v_s;
+            const int sm = s.integrate_structure ? 0 : 1;
             if (fk == 0)
-                rc = summ ? interact_structure<0, 1>(s, g, pc, d_dv, d_dv_s) : interact_structure<0, 0>(s, g, pc, d_dv, d_dv_s);
+                rc = summ ? interact_structure<0, 1>(s, g, pc, d_dv, d_dv_s, sm) : interact_structure<0, 0>(s, g, pc, d_dv, d_dv_s, sm);
             else if (fk == 1)
-                rc = summ ? interact_structure<1, 1>(s, g, pc, d_dv, d_dv_s) : interact_structure<1, 0>(s, g, pc, d_dv, d_dv_s);
+                rc = summ ? interact_structure<1, 1>(s, g, pc, d_dv, d_dv_s, sm) : interact_structure<1, 0>(s, g, pc, d_dv, d_dv_s, sm);
             else if (fk == 2)
-                rc = summ ? interact_structure<2, 1>(s, g, pc, d_dv, d_dv_s) : interact_structure<2, 0>(s, g, pc, d_dv, d_dv_s);
+                rc = summ ? interact_structure<2, 1>(s, g, pc, d_dv, d_dv_s, sm) : interact_structure<2, 0>(s, g, pc, d_dv, d_dv_s, sm);
             else
-                rc = summ ? interact_structure<3, 1>(s, g, pc, d_dv, d_dv_s) : interact_structure<3, 0>(s, g, pc, d_dv, d_dv_s);
+                rc = summ ? interact_structure<3, 1>(s, g, pc, d_dv, d_dv_s, sm) : interact_structure<3, 0>(s, g, pc, d_dv, d_dv_s, sm);
             if (rc) return rc;
         }
         if (s.n_w > 0 && wall_integrates_density(s)) {
@@ -1234,9 +1303,11 @@ struct Ops {
             if (total_f > 0)
                 LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total_f, 256), 256, 0, total_f, nv(s), v_base + lay.off_v_f,
                        du_base + lay.off_u_f);
-            if (total_s > 0)  // structure: v holds ND entries per integrated particle, du = v
+            if (total_s > 0 && s.integrate_structure)  // structure: v holds ND entries per integrated particle, du = v
                 LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total_s, 256), 256, 0, total_s, ND, v_base + lay.off_v_s,
                        du_base + lay.off_u_s);
+            else if (total_s > 0)  // set_velocity!(..., ::TotalLagrangianSPHSystem) without integrate_tlsph: du = 0
+                cudaMemsetAsync(du_base + lay.off_u_s, 0, sizeof(CT) * (size_t)total_s, s.stream);
         };
         if (s.cfg.ode_memory == TPB_MEM_HOST) {
             // Page-locked v and du: one kernel streams v in and du out over PCIe at the same
@@ -1430,7 +1501,9 @@ struct Ops {
     int TPB_CAT(get_field_, TAG)(Semi &s, int sys, int field, void *out, int64_t n);                     \
     int TPB_CAT(pairs_, TAG)(Semi &s, int sys, int nb, const void *u, int64_t cap, int32_t *oi, int32_t *oj, \
                              int64_t *cnt);                                                              \
-    int TPB_CAT(max_speed2_, TAG)(Semi &s, const void *v, void *out_bits);
+    int TPB_CAT(max_speed2_, TAG)(Semi &s, const void *v, void *out_bits);                               \
+    int TPB_CAT(struct_force_, TAG)(Semi &s, void *out, const void *v, const void *u);                   \
+    int TPB_CAT(kick_struct_, TAG)(Semi &s, void *dv, const void *v, const void *u, const void *dv_const);
 #define TPB_DEFINE_ENTRIES(TAG, ND, T, CT)                                                               \
     int TPB_CAT(init_wall_, TAG)(Semi &s) { return Ops<ND, T, CT>::init_wall(s); }                       \
     int TPB_CAT(init_structure_, TAG)(Semi &s) { return Ops<ND, T, CT>::init_structure(s); }             \
@@ -1455,6 +1528,14 @@ struct Ops {
     {                                                                                                    \
         return Ops<ND, T, CT>::max_speed2(s, (const T *)v + ode_layout(s).off_v_f, s.n_tgt,              \
                                           (unsigned long long *)out_bits);                               \
+    }                                                                                                    \
+    int TPB_CAT(struct_force_, TAG)(Semi &s, void *out, const void *v, const void *u)                    \
+    {                                                                                                    \
+        return Ops<ND, T, CT>::structure_fluid_force(s, out, v, u);                                      \
+    }                                                                                                    \
+    int TPB_CAT(kick_struct_, TAG)(Semi &s, void *dv, const void *v, const void *u, const void *dv_const) \
+    {                                                                                                    \
+        return Ops<ND, T, CT>::kick_structure(s, dv, v, u, dv_const);                                    \
     }
 TPB_DECLARE_ENTRIES(2ff)
 TPB_DECLARE_ENTRIES(3ff)
@@ -1501,6 +1582,11 @@ static int dispatch_pairs(Semi &s, int sys, int nb, const void *u, int64_t cap, 
     DISPATCH(s, pairs_, s, sys, nb, u, cap, oi, oj, cnt);
 }
 static int dispatch_max_speed2(Semi &s, const void *v, void *out_bits) { DISPATCH(s, max_speed2_, s, v, out_bits); }
+static int dispatch_struct_force(Semi &s, void *out, const void *v, const void *u) { DISPATCH(s, struct_force_, s, out, v, u); }
+static int dispatch_kick_struct(Semi &s, void *dv, const void *v, const void *u, const void *c)
+{
+    DISPATCH(s, kick_struct_, s, dv, v, u, c);
+}
 
 static void free_device(Semi &s)
 {
@@ -2130,6 +2216,42 @@ int32_t tpb_max_speed2(tpb_semi_t semi, const void *v_ode, void *out_bits)
     if (s->cfg.ode_memory != TPB_MEM_DEVICE) return fail(s, TPB_ERR_UNSUPPORTED, "device ODE vectors only");
     CUDA_TRY(s, cudaSetDevice(s->cfg.device));
     return dispatch_max_speed2(*s, v_ode, out_bits);
+}
+
+int32_t tpb_set_integrate_structure(tpb_semi_t semi, int32_t enabled)
+{
+    Semi *s = (Semi *)semi;
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    if (s->struct_index < 0) return fail(s, TPB_ERR_STATE, "no structure system");
+    s->integrate_structure = enabled ? 1 : 0;
+    return TPB_OK;
+}
+
+static int split_ready(Semi *s)
+{
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    if (!s->ready || s->struct_index < 0) return fail(s, TPB_ERR_STATE, "needs a semidiscretized handle with a structure system");
+    if (s->cfg.ode_memory != TPB_MEM_DEVICE) return fail(s, TPB_ERR_UNSUPPORTED, "split integration: device ODE vectors only");
+    return TPB_OK;
+}
+
+int32_t tpb_structure_fluid_force(tpb_semi_t semi, void *dv_split, const void *v_ode, const void *u_ode)
+{
+    Semi *s = (Semi *)semi;
+    if (int rc = split_ready(s)) return rc;
+    if (!dv_split || !v_ode || !u_ode) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    return dispatch_struct_force(*s, dv_split, v_ode, u_ode);
+}
+
+int32_t tpb_kick_structure(tpb_semi_t semi, void *dv_split, const void *v_split, const void *u_split,
+                           const void *dv_const)
+{
+    Semi *s = (Semi *)semi;
+    if (int rc = split_ready(s)) return rc;
+    if (!dv_split || !u_split) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    return dispatch_kick_struct(*s, dv_split, v_split, u_split, dv_const);
 }
 
 int32_t tpb_set_max_speed2(tpb_semi_t semi, const void *bits)

@@ -377,6 +377,12 @@ class Semidiscretization:
         _lib.check(self._handle, _lib.load().tpb_get_sound_speed(self._handle, C.byref(out)))
         return out.value
 
+    def set_integrate_structure(self, enabled: bool):
+        """`semi.integrate_tlsph[] = enabled` (semidiscretization.jl:149): with a SplitIntegrationCallback kick! /
+        drift! leave the structure's rows zero."""
+        _lib.check(self._handle, _lib.load().tpb_set_integrate_structure(self._handle, int(bool(enabled))))
+        self.integrate_tlsph = bool(enabled)
+
     def adaptive_sound_speed_on_device(self) -> bool:
         """StateEquationAdaptiveCole without a host round trip (tile sweeps, ContinuityDensity, no structure
         system; `TPB_ADAPTIVE_HOST` selects the host-scalar path): such a kick is stream-ordered and can

@@ -148,8 +148,90 @@ class StepsizeCallback:
         # minimum over all systems (stepsize.jl:63-79); walls contribute Inf
         from .model import TotalLagrangianSPHSystem
         dts = [calculate_dt(s, self.cfl) for s in semi.systems if isinstance(s, WeaklyCompressibleSPHSystem)]
-        dts += [calculate_dt_structure(s, self.cfl) for s in semi.systems if isinstance(s, TotalLagrangianSPHSystem)]
+        if getattr(semi, "integrate_tlsph", True):   # calculate_dt skips TLSPH systems that are not integrated (:514-517)
+            dts += [calculate_dt_structure(s, self.cfl) for s in semi.systems if isinstance(s, TotalLagrangianSPHSystem)]
         return min(dts)
+
+
+class SplitIntegrationCallback:
+    """`SplitIntegrationCallback(alg; stage_coupling=false, predict_positions=true, dt, callback=StepsizeCallback(...))`
+    (callbacks/split_integration.jl:1-110): the `TotalLagrangianSPHSystem` is taken out of the main integrator
+    (`semi.integrate_tlsph[] = false`) and advanced by its own CarpenterKennedy2N54 sub-integrator with smaller
+    steps -- after every step of the main integrator, or to every stage time with `stage_coupling=true`.  During
+    one sub-integration the force of the fluid on the structure is constant; it is computed for the new fluid
+    state and the structure positions predicted by an Euler step (`predict_positions`).  Device-resident vectors."""
+
+    def __init__(self, alg, *, stage_coupling: bool = False, predict_positions: bool = True, dt: float = None,
+                 callback=None):
+        if not isinstance(alg, CarpenterKennedy2N54):
+            raise ValueError("SplitIntegrationCallback: CarpenterKennedy2N54 is the sub-integrator on this path")
+        self.alg, self.stage_coupling, self.predict_positions = alg, bool(stage_coupling), bool(predict_positions)
+        self.dt_sub, self.stepsize = dt, callback
+        self.n_substeps = self.n_calls = 0
+
+    # initialize_split_integration! (split_integration.jl:112-170)
+    def initialize(self, semi, v_ode, u_ode, t):
+        from .model import TotalLagrangianSPHSystem
+        st = next((s_ for s_ in semi.systems if isinstance(s_, TotalLagrangianSPHSystem)), None)
+        if st is None:
+            raise ValueError("`SplitIntegrationCallback` must be used with a `TotalLagrangianSPHSystem`")
+        if semi.parallelization_backend.ode_memory != "device":
+            raise ValueError("SplitIntegrationCallback needs B200Backend(ode_memory='device')")
+        self.semi, self.system = semi, st
+        i = semi.system_index(st)
+        self.rv, self.ru = semi.ranges_v[i], semi.ranges_u[i]
+        semi.set_integrate_structure(False)
+        if isinstance(self.stepsize, StepsizeCallback):
+            self.dt_sub = calculate_dt_structure(st, self.stepsize.cfl)
+        if self.dt_sub is None or not self.dt_sub > 0:
+            raise ValueError("SplitIntegrationCallback: `dt` or `callback=StepsizeCallback(...)` is required")
+        # copy_to_split!
+        self.v = v_ode[self.rv[0]:self.rv[1]].clone()
+        self.u = u_ode[self.ru[0]:self.ru[1]].clone()
+        self.dv, self.du = self.v.clone(), self.u.clone()
+        self.tmp_v, self.tmp_u = self.v.clone(), self.u.clone()
+        self.force = self.v.clone()
+        self.t = float(t)
+        self.ops = _VecOps(semi)
+
+    def _copy_from_split(self, v_ode, u_ode, dt_predict):
+        # copy_from_split! (split_integration.jl:490-510): u += v (t_new - t_previous) with PREDICT
+        v_ode[self.rv[0]:self.rv[1]].copy_(self.v)
+        us = u_ode[self.ru[0]:self.ru[1]]
+        us.copy_(self.u)
+        if dt_predict != 0.0:
+            us.add_(self.v.to(us.dtype), alpha=dt_predict)
+
+    # split_integrate! (split_integration.jl:237-350)
+    def integrate_to(self, v_ode, u_ode, t_new):
+        t_prev = self.t
+        if t_new < t_prev - 1e-12 * max(1.0, abs(t_prev)):
+            raise ValueError("stage-level coupling with `SplitIntegrationCallback` requires monotonically increasing "
+                             "stage times")
+        span = t_new - t_prev
+        self._copy_from_split(v_ode, u_ode, span if self.predict_positions else 0.0)
+        if abs(span) <= 1e-14 * max(1.0, abs(t_new)):
+            return
+        semi, L, h = self.semi, _lib.load(), self.semi._handle
+        semi._bind_stream()
+        # update_systems_and_nhs + other_interaction_split!: the fluid's force for this sub-integration
+        _lib.check(h, L.tpb_structure_fluid_force(h, C.c_void_p(self.force.data_ptr()), C.c_void_p(v_ode.data_ptr()),
+                                                  C.c_void_p(u_ode.data_ptr())))
+        n = max(1, int(math.ceil(span / self.dt_sub - 1e-9)))
+        dt = span / n
+        alg = self.alg
+        for _ in range(n):
+            for A, B, c in zip(alg.A, alg.B, alg.c):
+                _lib.check(h, L.tpb_kick_structure(h, C.c_void_p(self.dv.data_ptr()), C.c_void_p(self.v.data_ptr()),
+                                                   C.c_void_p(self.u.data_ptr()), C.c_void_p(self.force.data_ptr())))
+                # drift_split!: du = v; both partitions are updated from the state of the stage's start
+                self.du.copy_(self.v.to(self.du.dtype))
+                self.ops.rk2n_stage(A, B, dt, self.dv, self.tmp_v, self.v)
+                self.ops.rk2n_stage(A, B, dt, self.du, self.tmp_u, self.u)
+        self.n_substeps += n
+        self.n_calls += 1
+        self.t = float(t_new)
+        self._copy_from_split(v_ode, u_ode, 0.0)
 
 
 def max_x_coord(system, v_ode, u_ode, semi, t) -> float:
@@ -305,6 +387,10 @@ def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
         return _solve_verlet(ode, callbacks, dt=dt, maxiters=maxiters, save_everystep=save_everystep)
     stepsize = next((c for c in callbacks if isinstance(c, StepsizeCallback)), None)
     posts = [c for c in callbacks if isinstance(c, PostprocessCallback)]
+    split = next((c for c in callbacks if isinstance(c, SplitIntegrationCallback)), None)
+    if split is not None:
+        split.initialize(semi, ode.v0, ode.u0, ode.tspan[0])   # (also: the StepsizeCallback skips the structure)
+        cuda_graph = False                                      # the number of sub-steps varies from stage to stage
     if stepsize is not None:
         dt = stepsize.dt(semi)
     if dt is None or not dt > 0:
@@ -326,6 +412,8 @@ def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
 
     def run_stages(step_):
         for A, B, c in zip(alg.A, alg.B, alg.c):
+            if split is not None and split.stage_coupling:
+                split.integrate_to(v, u, t + c * step_)    # split_integrate_stage! (semidiscretization.jl:594)
             ode.f1(dv, v, u, ode.p, t + c * step_)
             ode.f2(du, v, u, ode.p, t + c * step_)
             ops.rk2n_stage(A, B, step_, dv, tmp_v, v)
@@ -357,6 +445,8 @@ def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
         nf += len(alg.A)
         t = stop if step != dt else t + step
         nsteps += 1
+        if split is not None:
+            split.integrate_to(v, u, t)                    # the callback's affect! at the end of every step
         if stepsize is not None and adaptive_eos:
             # StateEquationAdaptiveCole: the StepsizeCallback sees the speed of sound of the last
             # right-hand-side evaluation (stepsize.jl:63-79, fluid.jl:199-239)
