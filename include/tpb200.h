@@ -184,6 +184,14 @@ typedef struct {
     double bm_smoothing_length;
     double bm_sound_speed, bm_exponent, bm_reference_density, bm_background_pressure;
     double bm_pressure_offset;
+    /* bm_wall_semantics != 0: the system is a moving `WallBoundarySystem(ic, model; prescribed_motion)` registered
+     * with n_integrated = 0 -- the Adami hydrostatic term subtracts each particle's prescribed acceleration
+     * (current_acceleration, wall_boundary/system.jl:129-142; dummy_particles.jl:652-654) and the Bernoulli term
+     * exists only while the wall moves (dummy_particles.jl:680-694).  0: TotalLagrangianSPHSystem
+     * (current_acceleration = 0, general/abstract_system.jl:121; Bernoulli term always, :696-707).
+     * bm_bernoulli_factor: BernoulliPressureExtrapolation(factor); 0 = AdamiPressureExtrapolation */
+    int32_t bm_wall_semantics, bm_reserved;
+    double bm_bernoulli_factor;
 } tpb_structure_params;
 
 /* launch/traffic accounting of the last kick (what bench.py reports as gpu_launches) */
@@ -296,6 +304,16 @@ int32_t tpb_structure_fluid_force(tpb_semi_t semi, void *dv_split, const void *v
 int32_t tpb_kick_structure(tpb_semi_t semi, void *dv_split, const void *v_split, const void *u_split,
                            const void *dv_const);
 int32_t tpb_set_max_speed2(tpb_semi_t semi, const void *bits);
+/* ---- PrescribedMotion (schemes/boundary/prescribed_motion.jl:95-121; apply_prescribed_motion!,
+ * wall_boundary/system.jl:199-205 and total_lagrangian_sph/system.jl:436-447).  The movement function is the
+ * caller's: before a kick it hands over where the clamped particles of the structure system (all particles of
+ * a moving wall registered with n_integrated = 0) are now and how they move.  `coords`: cT[ND x n_clamped],
+ * `velocity`, `acceleration`: T[ND x n_clamped], HOST pointers, copied; `coords` may be NULL (particles stay
+ * where the last call put them).  `is_moving` = the motion's is_moving(t): 0 = velocity and acceleration count
+ * as zero (and may be NULL), the particles rest at their last position.  Takes effect with the next tpb_kick;
+ * a captured CUDA graph of kicks does not see it. */
+int32_t tpb_set_clamped_motion(tpb_semi_t semi, const void *coords, const void *velocity,
+                               const void *acceleration, int32_t is_moving);
 
 /* ---- device ODE-vector algebra ----------------------------------------------------------------
  * What a GPU-resident ODE-vector type binds for the integrator's broadcasts (the reference's

@@ -128,6 +128,7 @@ def structure_params(st) -> O.TlsphParams:
         p.bm_reference_density = float(t(se.reference_density))
         p.bm_background_pressure = float(t(se.background_pressure))
         p.bm_pressure_offset = float(t(m.density_calculator.pressure_offset))
+        p.bm_bernoulli_factor = float(t(getattr(m.density_calculator, "factor", 0.0)))
     elif m is not None:
         p.boundary_model = O.BOUNDARY_MONAGHAN_KAJTAR
         p.mk_K, p.mk_beta, p.mk_spacing = float(t(m.K)), float(t(m.beta)), float(t(m.boundary_particle_spacing))
@@ -147,6 +148,52 @@ def kick_fsi(fluid, wall, structure, u_ode, v_ode, nthreads=0):
     out = O.kick_fsi(fp, wp, sp, fluid.mass, wall.coordinates if wall is not None else None,
                      wall.boundary_model.hydrodynamic_mass if wall is not None else None,
                      structure.n_integrated_particles, structure.initial_coordinates, structure.mass,
-                     structure.material_density, hyd, L, v_ode, u_ode, fluid.eltype, nthreads=nthreads)
+                     structure.material_density, hyd, L, v_ode, u_ode, fluid.eltype, nthreads=nthreads,
+                     **_clamped_state(structure))
     out["L"] = L
     return out
+
+
+def _clamped_state(system):
+    """The prescribed state of a system's clamped particles as left by its last apply_prescribed_motion(t)."""
+    if getattr(system, "prescribed_motion", None) is None:
+        return {}
+    moving = bool(system.ismoving)
+    return dict(clamped_coords=system.clamped_coordinates,
+                clamped_velocity=system.clamped_velocity if moving else None,
+                clamped_acceleration=system.clamped_acceleration if moving else None)
+
+
+def kick_moving_wall(fluid, wall, u, v, static_wall=None, nthreads=0):
+    """Oracle `kick!` of Semidiscretization(fluid, [static_wall,] wall) where `wall` is a
+    `WallBoundarySystem(...; prescribed_motion)` in the state of its last apply_prescribed_motion(t): the FSI
+    oracle with the wall as an all-clamped system of dummy particles with wall semantics (orc_kick_fsi3).
+    Returns dict(dv (n_f, nv), pressure_wall, density_wall)."""
+    t = np.dtype(fluid.eltype).type
+    nd, n = fluid.ndims, wall.nparticles
+    m, se = wall.boundary_model, wall.boundary_model.state_equation
+    sp = O.TlsphParams()
+    sp.ndims = nd
+    sp.kernel = fluid.smoothing_kernel.kernel_id
+    sp.smoothing_length = float(t(fluid.smoothing_length))
+    sp.young_modulus, sp.poisson_ratio = 1.0, 0.0
+    sp.boundary_model = O.BOUNDARY_DUMMY_PARTICLES
+    sp.bm_kernel = m.smoothing_kernel.kernel_id
+    sp.bm_clip_negative_pressure = int(m.clip_negative_pressure)
+    sp.bm_smoothing_length = float(t(m.smoothing_length))
+    sp.bm_sound_speed, sp.bm_exponent = float(t(se.sound_speed)), float(t(se.exponent))
+    sp.bm_reference_density = float(t(se.reference_density))
+    sp.bm_background_pressure = float(t(se.background_pressure))
+    sp.bm_pressure_offset = float(t(m.density_calculator.pressure_offset))
+    sp.bm_wall_semantics = 1
+    sp.bm_bernoulli_factor = float(t(getattr(m.density_calculator, "factor", 0.0)))
+    L = np.tile(np.eye(nd, dtype=fluid.eltype), (n, 1, 1))
+    x0 = np.asarray(wall.initial_condition.coordinates)
+    out = O.kick_fsi(fluid_params(fluid), wall_params(static_wall) if static_wall is not None else None, sp, fluid.mass,
+                     static_wall.coordinates if static_wall is not None else None,
+                     static_wall.boundary_model.hydrodynamic_mass if static_wall is not None else None,
+                     0, x0, m.hydrodynamic_mass, np.ones(n, dtype=fluid.eltype), m.hydrodynamic_mass, L,
+                     np.ascontiguousarray(v).reshape(-1), np.ascontiguousarray(u).reshape(-1), fluid.eltype,
+                     nthreads=nthreads, **_clamped_state(wall))
+    return dict(dv=out["dv"].reshape(np.asarray(v).shape), pressure_wall=out["structure_pressure"],
+                density_wall=out["structure_density"])

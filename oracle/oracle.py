@@ -96,6 +96,8 @@ class TlsphParams(C.Structure):
         ("bm_smoothing_length", C.c_double), ("bm_sound_speed", C.c_double), ("bm_exponent", C.c_double),
         ("bm_reference_density", C.c_double), ("bm_background_pressure", C.c_double),
         ("bm_pressure_offset", C.c_double),
+        ("bm_wall_semantics", C.c_int32), ("bm_reserved", C.c_int32),
+        ("bm_bernoulli_factor", C.c_double),
     ]
 
 
@@ -142,6 +144,9 @@ def _declare(L):
         f = getattr(L, f"orc_kick_fsi2_{s}"); f.restype = i
         f.argtypes = [C.POINTER(FluidParams), C.POINTER(WallParams), TP, i64, p, i64, p, p, i64, i64,
                       p, p, p, p, p, p, p, p, p, p, p, p, i]
+        f = getattr(L, f"orc_kick_fsi3_{s}"); f.restype = i
+        f.argtypes = [C.POINTER(FluidParams), C.POINTER(WallParams), TP, i64, p, i64, p, p, i64, i64,
+                      p, p, p, p, p, p, p, p, p, p, p, p, p, p, p, i]
     L.orc_max_threads.restype = i
     L.orc_max_threads.argtypes = []
 
@@ -362,9 +367,11 @@ def tlsph_interact(sp: TlsphParams, n_int, x0, x_cur, mass, rho, F, pk1_rho2, dt
 
 
 def kick_fsi(fp: FluidParams, wp, sp: TlsphParams, mass_f, coords_w, mass_w, n_s_int, x0_s, mass_s, rho_s,
-             hydro_mass_s, L, v_ode, u_ode, dtype, nthreads=0):
+             hydro_mass_s, L, v_ode, u_ode, dtype, nthreads=0, clamped_coords=None, clamped_velocity=None,
+             clamped_acceleration=None):
     """One `kick!` of Semidiscretization(fluid, wall, structure) on flat ODE vectors [fluid | structure]
-    (see orc_kick_fsi).  Returns dict(dv=flat dv_ode, F=..., pk1_rho2=...)."""
+    (see orc_kick_fsi).  Returns dict(dv=flat dv_ode, F=..., pk1_rho2=...).  clamped_*: the prescribed
+    motion of the clamped particles (orc_kick_fsi3), (n_s - n_s_int, ND) each or None."""
     dtype = np.dtype(dtype)
     u_ode = np.ascontiguousarray(u_ode)
     cdt = u_ode.dtype
@@ -387,10 +394,16 @@ def kick_fsi(fp: FluidParams, wp, sp: TlsphParams, mass_f, coords_w, mass_w, n_s
     dv = np.zeros_like(v_ode)
     F, P = np.zeros((n_s, nd, nd), dtype=dtype), np.zeros((n_s, nd, nd), dtype=dtype)
     ps, ds = np.zeros(n_s, dtype=dtype), np.zeros(n_s, dtype=dtype)
-    rc = getattr(lib(), f"orc_kick_fsi2_{s}")(C.byref(fp), wpp, C.byref(sp), n_f, _ptr(mass_f), n_w, _ptr(coords_w),
+    n_cl = n_s - n_s_int
+    xc = None if clamped_coords is None else np.ascontiguousarray(clamped_coords, dtype=cdt).reshape(n_cl, nd)
+    vc = None if clamped_velocity is None else np.ascontiguousarray(clamped_velocity, dtype=dtype).reshape(n_cl, nd)
+    ac = None if clamped_acceleration is None else \
+        np.ascontiguousarray(clamped_acceleration, dtype=dtype).reshape(n_cl, nd)
+    rc = getattr(lib(), f"orc_kick_fsi3_{s}")(C.byref(fp), wpp, C.byref(sp), n_f, _ptr(mass_f), n_w, _ptr(coords_w),
                                                _ptr(mass_w), n_s, n_s_int, _ptr(x0_s), _ptr(mass_s), _ptr(rho_s),
                                                _ptr(hydro), _ptr(L), _ptr(v_ode), _ptr(u_ode), _ptr(dv), _ptr(F),
-                                               _ptr(P), _ptr(ps), _ptr(ds), int(nthreads))
+                                               _ptr(P), _ptr(ps), _ptr(ds), _ptr(xc), _ptr(vc), _ptr(ac),
+                                               int(nthreads))
     if rc != 0:
         raise RuntimeError(f"orc_kick_fsi failed: {rc}")
     return dict(dv=dv, F=F, pk1_rho2=P, structure_pressure=ps, structure_density=ds)

@@ -98,6 +98,14 @@ typedef struct {
     double bm_smoothing_length;
     double bm_sound_speed, bm_exponent, bm_reference_density, bm_background_pressure;
     double bm_pressure_offset;
+    /* prescribed motion of the clamped particles (boundary/prescribed_motion.jl:95-121).  bm_wall_semantics:
+     * the particles are a moving WallBoundarySystem -- the Adami hydrostatic term subtracts the particle's
+     * prescribed acceleration (wall_boundary/system.jl:133-142, dummy_particles.jl:652-654) and the Bernoulli
+     * term exists only while the wall moves (dummy_particles.jl:680-694); 0 = TotalLagrangianSPHSystem
+     * (current_acceleration = 0, abstract_system.jl:121; Bernoulli term always, dummy_particles.jl:696-707).
+     * bm_bernoulli_factor: BernoulliPressureExtrapolation's factor, 0 = AdamiPressureExtrapolation */
+    int32_t bm_wall_semantics, bm_reserved;
+    double bm_bernoulli_factor;
 } orc_tlsph_params;
 
 #define ORC_DECLARE(SUF, T, CT)                                                              \
@@ -161,7 +169,18 @@ typedef struct {
                            int64_t n_s_int, const CT *x0_s, const T *mass_s, const T *rho_s, \
                            const T *hydro_mass_s, const T *L, const T *v_ode,                \
                            const CT *u_ode, T *dv_ode, T *F_out, T *pk1_out, T *pressure_s,  \
-                           T *density_s, int nthreads);
+                           T *density_s, int nthreads);                                      \
+    /* as orc_kick_fsi2 with prescribed motion of the clamped particles: x_clamped (current positions), \
+     * v_clamped, a_clamped: (n_s - n_s_int) x ND, each may be NULL (positions: the initial ones;        \
+     * velocity NULL = not moving now, velocity and acceleration count as zero) */                       \
+    int orc_kick_fsi3_##SUF(const orc_fluid_params *fp, const orc_wall_params *wp,           \
+                           const orc_tlsph_params *sp, int64_t n_f, const T *mass_f,         \
+                           int64_t n_w, const CT *coords_w, const T *mass_w, int64_t n_s,    \
+                           int64_t n_s_int, const CT *x0_s, const T *mass_s, const T *rho_s, \
+                           const T *hydro_mass_s, const T *L, const T *v_ode,                \
+                           const CT *u_ode, T *dv_ode, T *F_out, T *pk1_out, T *pressure_s,  \
+                           T *density_s, const CT *x_clamped, const T *v_clamped,            \
+                           const T *a_clamped, int nthreads);
 
 ORC_DECLARE(f64, double, double)
 ORC_DECLARE(f32, float, float)

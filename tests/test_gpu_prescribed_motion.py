@@ -1,0 +1,144 @@
+"""PrescribedMotion on the GPU: moving walls of dummy particles (examples/fluid/moving_wall_2d.jl,
+accelerated_tank_2d.jl) and moving clamped particles of a TotalLagrangianSPHSystem, through the C ABI
+(tpb_set_clamped_motion + tpb_kick) against the CPU oracle.  `-m gpu` only."""
+import numpy as np
+import pytest
+
+import trixiparticles.jl_b200 as tp
+from trixiparticles.jl_b200 import examples
+from oracle import adapter
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_inf(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def gpu_kick(semi, ode, u, v, t):
+    dv = np.full(v.size, np.nan, dtype=v.dtype)
+    tp.kick_(dv, np.ascontiguousarray(v).reshape(-1).copy(), np.ascontiguousarray(u).reshape(-1), ode.p, t)
+    assert np.isfinite(dv).all()
+    return dv.reshape(v.shape)
+
+
+BOX = tp.GridNeighborhoodSearch(2, cell_list=tp.FullGridCellList((-1.0, -1.0), (5.0, 3.0)))
+
+
+@pytest.mark.parametrize("eltype,tol", [(np.float64, 1e-11), (np.float32, 3e-5)])
+def test_accelerated_tank_kick(eltype, tol):
+    """accelerated_tank_2d.jl at t = 0.37: GPU == oracle, and == the hydrostatic tank seen from the tank's frame
+    (dv + g e_y), the property test_oracle_prescribed_motion.py establishes for the oracle."""
+    g, t = 9.81, 0.37
+    fluid, wall, _ = examples.accelerated_tank_2d(0.05, eltype=eltype, coordinates_eltype=eltype)
+    fluid_h, wall_h, _ = examples.hydrostatic_water_column_2d(0.05, eltype=eltype, coordinates_eltype=eltype)
+    u0, v0 = examples.perturbed_state(fluid_h)
+    shift, vel = np.array([0.0, 0.5 * g * t * t]), np.array([0.0, g * t])
+    u, v = (u0 + shift).astype(eltype), v0.copy()
+    v[:, :2] += vel.astype(eltype)
+    semi = tp.Semidiscretization(fluid, wall, neighborhood_search=BOX, parallelization_backend=tp.B200Backend())
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    dv = gpu_kick(semi, ode, u, v, t)
+    ref = adapter.kick_moving_wall(fluid, wall, u, v)      # the wall object is in the state of the kick at t
+    assert np.allclose(wall.coordinates, wall_h.coordinates + shift, atol=1e-6)
+    assert rel_inf(dv[:, :2], ref["dv"][:, :2]) <= tol and rel_inf(dv[:, 2], ref["dv"][:, 2]) <= tol
+    for name, key in (("pressure", "pressure_wall"), ("density", "density_wall")):
+        assert rel_inf(semi.system_field(wall, name), ref[key]) <= 10 * tol, name
+    semi.close()
+    if eltype == np.float64:
+        semi_h = tp.Semidiscretization(fluid_h, wall_h, parallelization_backend=tp.B200Backend())
+        ode_h = tp.semidiscretize(semi_h, (0.0, 1.0))
+        want = gpu_kick(semi_h, ode_h, u0, v0, 0.0)
+        want[:, 1] += g
+        assert rel_inf(dv, want) <= 1e-9
+        semi_h.close()
+
+
+@pytest.mark.parametrize("eltype,tol", [(np.float64, 1e-11), (np.float32, 3e-5)])
+@pytest.mark.parametrize("extrapolation", ["adami", "bernoulli"])
+def test_moving_wall_kick(eltype, tol, extrapolation):
+    """moving_wall_2d.jl: only the right wall's face block moves (x + t^2/2 while t < 1.5).  Kicks while it moves
+    (t = 0.3: velocity 0.3, acceleration 1 enter the continuity equation and the Adami / Bernoulli extrapolation),
+    and after it stopped (t = 1.6 following a kick at t = 1.4: rests at its last position, velocity 0)."""
+    fluid, wall, tank = examples.moving_wall_2d(0.05, eltype=eltype, coordinates_eltype=eltype)
+    if extrapolation == "bernoulli":
+        m = wall.boundary_model
+        wall = tp.WallBoundarySystem(wall.initial_condition, tp.BoundaryModelDummyParticles(
+            m.initial_density, m.hydrodynamic_mass, tp.BernoulliPressureExtrapolation(factor=0.8), m.smoothing_kernel,
+            m.smoothing_length, state_equation=m.state_equation), prescribed_motion=wall.prescribed_motion)
+    u, v = examples.perturbed_state(fluid)
+    semi = tp.Semidiscretization(fluid, wall, neighborhood_search=BOX, parallelization_backend=tp.B200Backend())
+    ode = tp.semidiscretize(semi, (0.0, 2.0))
+    static = None
+    for t in (0.3, 1.4, 1.6):
+        # the fluid follows the wall so that the two stay in touch
+        shift = np.array([0.5 * min(t, 1.4) ** 2, 0.0])
+        u_t = (u + 0.995 * shift).astype(eltype)
+        dv = gpu_kick(semi, ode, u_t, v, t)
+        ref = adapter.kick_moving_wall(fluid, wall, u_t, v)
+        assert wall.ismoving == (t < 1.5)
+        assert np.allclose(wall.coordinates[tank.face_indices[1]],
+                           wall.initial_condition.coordinates[tank.face_indices[1]] + shift, atol=1e-6)
+        assert rel_inf(dv[:, :2], ref["dv"][:, :2]) <= tol and rel_inf(dv[:, 2], ref["dv"][:, 2]) <= tol, t
+        assert rel_inf(semi.system_field(wall, "pressure"), ref["pressure_wall"]) <= 10 * tol, t
+        if t == 1.4:
+            static = dv
+        if t == 1.6:
+            # same geometry as at t = 1.4 (u_t equal), but the wall is at rest now
+            assert np.abs(dv - static).max() > 1e-3 * np.abs(static).max()
+    semi.close()
+
+
+@pytest.mark.parametrize("boundary_model", ["monaghan_kajtar", "dummy_particles", "dummy_bernoulli"])
+def test_structure_with_moving_clamped_particles(boundary_model):
+    """`TotalLagrangianSPHSystem(...; clamped_particles_motion)` (system.jl:108-184, :403-447): the clamped base of
+    the plate of dam_break_plate_2d.jl is shaken sideways; the plate's stress, the fluid's continuity equation and
+    (Bernoulli) the extrapolated pressure see the prescribed positions and velocities."""
+    from test_gpu_fsi import fsi_state
+    motion = tp.PrescribedMotion(lambda x, t: x + np.array([[0.004 * np.sin(40.0 * t), 0.0]]), lambda t: True)
+    fluid, wall, structure, _ = examples.dam_break_plate_2d(
+        0.01, eltype=np.float64, coordinates_eltype=np.float64, initial_fluid_size=(0.15, 0.29),
+        plate_position=(0.165, 0.0), clamped_particles_motion=motion,
+        structure_boundary_model="monaghan_kajtar" if boundary_model == "monaghan_kajtar" else "dummy_particles",
+        structure_pressure_extrapolation=tp.BernoulliPressureExtrapolation() if boundary_model == "dummy_bernoulli" else None)
+    assert structure.n_clamped_particles > 0 and structure.prescribed_motion is motion
+    u, v = fsi_state(fluid, structure)
+    semi = tp.Semidiscretization(fluid, wall, structure, parallelization_backend=tp.B200Backend())
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    results = []
+    for t in (0.0, 0.03):
+        dv = np.full_like(v, np.nan)
+        ode.f1(dv, v, u, ode.p, t)
+        ref = adapter.kick_fsi(fluid, wall, structure, u, v)
+        n_f = fluid.nparticles
+        for name, a, b in (("fluid", dv[: 3 * n_f], ref["dv"][: 3 * n_f]), ("structure", dv[3 * n_f:], ref["dv"][3 * n_f:])):
+            assert rel_inf(a, b) <= 1e-11, (name, t, rel_inf(a, b))
+        for name, key in (("deformation_grad", "F"), ("pk1_rho2", "pk1_rho2")):
+            assert rel_inf(semi.system_field(structure, name), ref[key]) <= 1e-11, name
+        results.append(dv.copy())
+    n_f = fluid.nparticles
+    assert np.abs(results[0][3 * n_f:] - results[1][3 * n_f:]).max() > 1.0    # the shaken base strains the plate
+    assert np.abs(results[0][: 3 * n_f] - results[1][: 3 * n_f]).max() > 1e-6
+    semi.close()
+
+
+def test_accelerated_tank_time_loop():
+    """accelerated_tank_2d.jl integrated in time: in the tank's frame the water column stays the hydrostatic one --
+    the same run as hydrostatic_water_column_2d.jl up to rounding."""
+    from trixiparticles.jl_b200.time_integration import CarpenterKennedy2N54, solve
+    g = 9.81
+    fluid_a, wall_a, _ = examples.accelerated_tank_2d(0.05)
+    fluid_h, wall_h, _ = examples.hydrostatic_water_column_2d(0.05, eltype=np.float64, coordinates_eltype=np.float64)
+    out = {}
+    for name, fluid, wall, nhs in (("acc", fluid_a, wall_a, BOX), ("hyd", fluid_h, wall_h, None)):
+        semi = tp.Semidiscretization(fluid, wall, neighborhood_search=nhs,
+                                     parallelization_backend=tp.B200Backend(ode_memory="device"))
+        ode = tp.semidiscretize(semi, (0.0, 0.05))
+        sol = solve(ode, CarpenterKennedy2N54(), dt=2.5e-4, cuda_graph=True)   # (a moving wall switches the graph off)
+        out[name] = (sol.u.cpu().numpy().reshape(-1, 2), sol.v.cpu().numpy().reshape(-1, 3), sol.t)
+        semi.close()
+    (u_a, v_a, t_a), (u_h, v_h, t_h) = out["acc"], out["hyd"]
+    assert t_a == t_h
+    assert np.abs(u_a - [0.0, 0.5 * g * t_a ** 2] - u_h).max() <= 1e-9
+    assert np.abs(v_a[:, :2] - [0.0, g * t_a] - v_h[:, :2]).max() <= 1e-7
+    assert rel_inf(v_a[:, 2], v_h[:, 2]) <= 1e-10

@@ -13,14 +13,14 @@ from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan, Ber
                     SourceTermDamping, StateEquationAdaptiveCole, StateEquationCole, SummationDensity,
                     ViscosityAdami, ViscosityMorris,
                     WallBoundarySystem, TotalLagrangianSPHSystem, BoundaryModelMonaghanKajtar,
-                    PenaltyForceGanzenmueller,
+                    PenaltyForceGanzenmueller, PrescribedMotion, OscillatingMotion2D,
                     WeaklyCompressibleSPHSystem, WendlandC2Kernel, WendlandC4Kernel, WendlandC6Kernel,
                     compact_support)
 from .semidiscretization import (B200Backend, DynamicalODEProblem, FullGridCellList,
                                  GridNeighborhoodSearch, Semidiscretization, drift_, kick_,
                                  semidiscretize)
 from .interpolation import interpolate_line, interpolate_points
-from .setups import InitialCondition, RectangularShape, RectangularTank, union
+from .setups import InitialCondition, RectangularShape, RectangularTank, reset_wall_, union
 
 __all__ = [
     "AdamiPressureExtrapolation", "ArtificialViscosityMonaghan", "BernoulliPressureExtrapolation",
@@ -30,10 +30,10 @@ __all__ = [
     "SourceTermDamping", "StateEquationAdaptiveCole", "StateEquationCole", "SummationDensity",
     "ViscosityAdami", "ViscosityMorris",
     "WallBoundarySystem", "TotalLagrangianSPHSystem", "BoundaryModelMonaghanKajtar",
-    "PenaltyForceGanzenmueller",
+    "PenaltyForceGanzenmueller", "PrescribedMotion", "OscillatingMotion2D",
     "WeaklyCompressibleSPHSystem", "WendlandC2Kernel", "WendlandC4Kernel", "WendlandC6Kernel",
     "compact_support", "B200Backend",
     "DynamicalODEProblem", "FullGridCellList", "GridNeighborhoodSearch", "Semidiscretization",
     "drift_", "kick_", "semidiscretize", "InitialCondition", "RectangularShape",
-    "RectangularTank", "union", "interpolate_line", "interpolate_points",
+    "RectangularTank", "reset_wall_", "union", "interpolate_line", "interpolate_points",
 ]

@@ -77,6 +77,11 @@ struct Semi {
     // structure with BoundaryModelDummyParticles: sorted -> own index, Adami pressure (sorted / own order), density
     int *d_sperm = nullptr;
     void *d_Ps = nullptr, *d_p_s = nullptr, *d_rhoh_s = nullptr;
+    // prescribed motion of the clamped particles (tpb_set_clamped_motion): d_xcl_s = where every particle is when
+    // u_ode does not say (n_s x ND, the clamped tail is what counts; starts as the initial coordinates);
+    // velocity / acceleration of the clamped particles ((n_s - n_s_int) x ND), used while clamped_moving
+    void *d_xcl_s = nullptr, *d_vcl_s = nullptr, *d_acl_s = nullptr;
+    int clamped_moving = 0;
 
     // geometry of the shared cell grid (double; typed copies are built per call)
     double cell_size = 0, origin[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
@@ -535,6 +540,9 @@ struct Ops {
         k.clip = s.sp.bm_clip_negative_pressure;
         k.almostzero_fs = pc.almostzero;
         k.almostzero_sf = std::sqrt(eps_of<T>(pc.kern.h * pc.kern.h));
+        // BernoulliPressureExtrapolation (dummy_particles.jl:674-707): a wall has the term only while it moves
+        k.bernoulli = s.sp.bm_bernoulli_factor != 0.0 && (!s.sp.bm_wall_semantics || s.clamped_moving)
+                          ? (T)s.sp.bm_bernoulli_factor : (T)0;
         return k;
     }
     static int kernel_template_id(int kernel) { return kernel <= 1 ? kernel : kernel <= TPB_KERNEL_WENDLAND_C6 ? 2 : 3; }
@@ -606,6 +614,7 @@ struct Ops {
         const size_t nz = (size_t)std::max(n, 1);
         CUDA_TRY(&s, cudaMemcpy(s.d_x0_s, s.h_x0_s.data(), sizeof(CT) * ND * (size_t)n, cudaMemcpyHostToDevice));
         CUDA_TRY(&s, cudaMemcpy(s.d_xcur_s, s.h_x0_s.data(), sizeof(CT) * ND * (size_t)n, cudaMemcpyHostToDevice));
+        CUDA_TRY(&s, cudaMemcpy(s.d_xcl_s, s.h_x0_s.data(), sizeof(CT) * ND * (size_t)n, cudaMemcpyHostToDevice));
         CUDA_TRY(&s, cudaMemcpy(s.d_mass_s, s.h_mass_s.data(), sizeof(T) * (size_t)n, cudaMemcpyHostToDevice));
         CUDA_TRY(&s, cudaMemcpy(s.d_rho_s, s.h_rho_s.data(), sizeof(T) * (size_t)n, cudaMemcpyHostToDevice));
         if (!s.h_hydro_s.empty())
@@ -637,7 +646,7 @@ struct Ops {
         const int n = (int)s.n_s, n_int = (int)s.n_s_int;
         if (n == 0) return TPB_OK;
         LAUNCH(s, (k_struct_positions<ND, CT>), cdiv((int64_t)n * ND, 256), 256, 0, n, n_int, d_u_s,
-               (const CT *)s.d_x0_s, (CT *)s.d_xcur_s);
+               (const CT *)s.d_xcl_s, (CT *)s.d_xcur_s);
         if (s.sp.boundary_model != TPB_BOUNDARY_NONE) {
             int rc = bin_points(s, (const CT *)s.d_xcur_s, n, n, s.d_scell_start);
             if (rc) return rc;
@@ -646,7 +655,8 @@ struct Ops {
                 // (rebuild_fluid has run: positions, density and pressure of the fluid are in place)
                 LAUNCH(s, (k_reorder_struct<ND, T, CT>), cdiv(n, 256), 256, 0, (const CT *)s.d_xcur_s, d_v_s,
                        (const T *)s.d_hydro_s, s.d_key, s.d_scell_start, s.d_tmp_perm, n, n_int, (T)1,
-                       (V4<CT> *)s.d_As, (V4<T> *)s.d_Bs, s.d_sperm);
+                       (V4<CT> *)s.d_As, (V4<T> *)s.d_Bs, s.d_sperm,
+                       s.clamped_moving ? (const T *)s.d_vcl_s : (const T *)nullptr);
                 const DummyConst<T> dk = make_dummy_const(s, pc);
                 const int enabled = s.struct_fluid[0] && s.n_act > 0;
                 switch (kernel_template_id(s.sp.bm_kernel)) {
@@ -654,7 +664,8 @@ struct Ops {
     case KID:                                                                                                     \
         LAUNCH(s, (k_struct_adami<ND, T, CT, KID>), cdiv(n, 128), 128, 0, n, g, (const V4<CT> *)s.d_As, s.d_sperm, \
                s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, (const T *)s.d_P, enabled, dk,        \
-               (V4<T> *)s.d_Bs, (T *)s.d_Ps, (T *)s.d_p_s, (T *)s.d_rhoh_s, s.d_flags);                            \
+               (V4<T> *)s.d_Bs, (T *)s.d_Ps, (T *)s.d_p_s, (T *)s.d_rhoh_s, s.d_flags,                             \
+               s.clamped_moving && s.sp.bm_wall_semantics ? (const T *)s.d_acl_s : (const T *)nullptr, n_int);     \
         break;
                     TPB_SADAMI(0) TPB_SADAMI(1) TPB_SADAMI(2) TPB_SADAMI(3)
 #undef TPB_SADAMI
@@ -663,7 +674,8 @@ struct Ops {
                 const MKConst<T> mk = make_mk_const(s, pc);
                 LAUNCH(s, (k_reorder_struct<ND, T, CT>), cdiv(n, 256), 256, 0, (const CT *)s.d_xcur_s, d_v_s,
                        (const T *)s.d_hydro_s, s.d_key, s.d_scell_start, s.d_tmp_perm, n, n_int, mk.vol,
-                       (V4<CT> *)s.d_As, (V4<T> *)s.d_Bs);
+                       (V4<CT> *)s.d_As, (V4<T> *)s.d_Bs, (int *)nullptr,
+                       s.clamped_moving ? (const T *)s.d_vcl_s : (const T *)nullptr);
             }
         }
         return structure_deformation(s);
@@ -768,7 +780,7 @@ struct Ops {
         const int n = (int)s.n_s, n_int = (int)s.n_s_int;
         if (n_int == 0) return TPB_OK;
         LAUNCH(s, (k_struct_positions<ND, CT>), cdiv((int64_t)n * ND, 256), 256, 0, n, n_int, (const CT *)u_split,
-               (const CT *)s.d_x0_s, (CT *)s.d_xcur_s);
+               (const CT *)s.d_xcl_s, (CT *)s.d_xcur_s);
         int rc = structure_deformation(s);
         if (rc) return rc;
         if (dv_const)
@@ -1596,7 +1608,7 @@ static void free_device(Semi &s)
                     s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_Vw, s.d_Pw, s.d_perm_w,
                     s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2, s.d_adapt, s.d_x0_s, s.d_xcur_s, s.d_mass_s, s.d_rho_s, s.d_hydro_s,
                     s.d_L_s, s.d_F_s, s.d_pk1_s, s.d_As, s.d_Bs, s.d_nbr_start, s.d_nbr, s.d_scell_start, s.d_sperm,
-                    s.d_Ps, s.d_p_s, s.d_rhoh_s};
+                    s.d_Ps, s.d_p_s, s.d_rhoh_s, s.d_xcl_s, s.d_vcl_s, s.d_acl_s};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     tiles_free(s.tiles);
@@ -1977,6 +1989,14 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     if (s->struct_index >= 0) {
         CUDA_TRY(s, cudaMalloc(&s->d_x0_s, cs * nd * ns));
         CUDA_TRY(s, cudaMalloc(&s->d_xcur_s, cs * nd * ns));
+        CUDA_TRY(s, cudaMalloc(&s->d_xcl_s, cs * nd * ns));
+        {
+            const size_t ncl = (size_t)(s->n_s - s->n_s_int) + 8;
+            CUDA_TRY(s, cudaMalloc(&s->d_vcl_s, ts * nd * ncl));
+            CUDA_TRY(s, cudaMalloc(&s->d_acl_s, ts * nd * ncl));
+            CUDA_TRY(s, cudaMemset(s->d_vcl_s, 0, ts * nd * ncl));
+            CUDA_TRY(s, cudaMemset(s->d_acl_s, 0, ts * nd * ncl));
+        }
         CUDA_TRY(s, cudaMalloc(&s->d_mass_s, ts * ns));
         CUDA_TRY(s, cudaMalloc(&s->d_rho_s, ts * ns));
         CUDA_TRY(s, cudaMalloc(&s->d_hydro_s, ts * ns));
@@ -2224,6 +2244,31 @@ int32_t tpb_set_integrate_structure(tpb_semi_t semi, int32_t enabled)
     if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
     if (s->struct_index < 0) return fail(s, TPB_ERR_STATE, "no structure system");
     s->integrate_structure = enabled ? 1 : 0;
+    return TPB_OK;
+}
+
+int32_t tpb_set_clamped_motion(tpb_semi_t semi, const void *coords, const void *velocity, const void *acceleration,
+                               int32_t is_moving)
+{
+    Semi *s = (Semi *)semi;
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    if (!s->ready || s->struct_index < 0)
+        return fail(s, TPB_ERR_STATE, "needs a semidiscretized handle with a structure (or moving wall) system");
+    if (is_moving && (!velocity || !acceleration))
+        return fail(s, TPB_ERR_INVALID_ARGUMENT, "a moving system needs velocity and acceleration");
+    const size_t ncl = (size_t)(s->n_s - s->n_s_int), nd = (size_t)s->cfg.ndims;
+    const size_t ts = tsize(s->cfg.eltype), cs = tsize(s->cfg.coords_eltype);
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    // synchronous copies from pageable host memory: the caller's arrays are free on return
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    if (ncl > 0 && coords)
+        CUDA_TRY(s, cudaMemcpy((char *)s->d_xcl_s + cs * nd * (size_t)s->n_s_int, coords, cs * nd * ncl,
+                               cudaMemcpyHostToDevice));
+    if (ncl > 0 && is_moving) {
+        CUDA_TRY(s, cudaMemcpy(s->d_vcl_s, velocity, ts * nd * ncl, cudaMemcpyHostToDevice));
+        CUDA_TRY(s, cudaMemcpy(s->d_acl_s, acceleration, ts * nd * ncl, cudaMemcpyHostToDevice));
+    }
+    s->clamped_moving = is_moving ? 1 : 0;
     return TPB_OK;
 }
 

@@ -75,21 +75,22 @@ __device__ __forceinline__ void mk_pressure_acceleration(const MKConst<T> &k, co
 // current_coordinates <- u (integrated particles); clamped particles keep their initial position
 template <int ND, typename CT>
 __global__ void __launch_bounds__(256)
-k_struct_positions(int n, int n_int, const CT *__restrict__ u_s, const CT *__restrict__ x0, CT *__restrict__ x_cur)
+k_struct_positions(int n, int n_int, const CT *__restrict__ u_s, const CT *__restrict__ x_clamped,
+                   CT *__restrict__ x_cur)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n * ND) return;
-    x_cur[q] = q < n_int * ND ? u_s[q] : x0[q];
+    x_cur[q] = q < n_int * ND ? u_s[q] : x_clamped[q];
 }
 
 // sorted records of the structure as a neighbour of the fluid: A = (x, hydrodynamic mass),
-// B = (velocity (0 for clamped particles), m / spacing^ND)
+// B = (velocity (clamped particles: the prescribed one while they move, else 0; system.jl:302-321), m / spacing^ND)
 template <int ND, typename T, typename CT>
 __global__ void __launch_bounds__(256)
 k_reorder_struct(const CT *__restrict__ x_cur, const T *__restrict__ v_s, const T *__restrict__ hydro_mass,
                  const int *__restrict__ key, const int *__restrict__ cell_start,
                  const int *__restrict__ tmp_perm, int n, int n_int, T mk_vol, V4<CT> *__restrict__ A,
-                 V4<T> *__restrict__ B, int *__restrict__ sperm = nullptr)
+                 V4<T> *__restrict__ B, int *__restrict__ sperm = nullptr, const T *__restrict__ v_clamped = nullptr)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -103,10 +104,11 @@ k_reorder_struct(const CT *__restrict__ x_cur, const T *__restrict__ v_s, const 
     ra.z = ND == 3 ? x_cur[(int64_t)i * ND + 2] : (CT)0;
     ra.w = (CT)hydro_mass[i];
     V4<T> rb;
-    const bool moving = i < n_int;
-    rb.x = moving ? v_s[(int64_t)i * ND + 0] : (T)0;
-    rb.y = moving ? v_s[(int64_t)i * ND + 1] : (T)0;
-    rb.z = ND == 3 && moving ? v_s[(int64_t)i * ND + 2] : (T)0;
+    const bool moving = i < n_int || v_clamped != nullptr;
+    const T *vp = i < n_int ? v_s + (int64_t)i * ND : v_clamped + (int64_t)(i - n_int) * ND;
+    rb.x = moving ? vp[0] : (T)0;
+    rb.y = moving ? vp[1] : (T)0;
+    rb.z = ND == 3 && moving ? vp[ND - 1] : (T)0;
     rb.w = hydro_mass[i] / mk_vol;
     A[dst] = ra;
     B[dst] = rb;
@@ -430,6 +432,7 @@ struct DummyConst {
     int clip;
     T almostzero_fs;       // fluid <- structure: sqrt(eps(compact_support_fluid^2))
     T almostzero_sf;       // structure <- fluid: sqrt(eps(h_fluid^2))
+    T bernoulli;           // BernoulliPressureExtrapolation's factor when the dynamic term applies, else 0
 };
 
 // update_boundary_interpolation! for the structure's particles at their CURRENT positions (dummy_particles.jl:
@@ -440,13 +443,23 @@ __global__ void __launch_bounds__(128)
 k_struct_adami(int n_s, GridConst<CT> g, const V4<CT> *__restrict__ As, const int *__restrict__ sperm,
                const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A, const V4<T> *__restrict__ B,
                const T *__restrict__ P, int enabled, DummyConst<T> k, V4<T> *__restrict__ Bs, T *__restrict__ Ps,
-               T *__restrict__ p_orig, T *__restrict__ rho_orig, int *__restrict__ flags)
+               T *__restrict__ p_orig, T *__restrict__ rho_orig, int *__restrict__ flags,
+               const T *__restrict__ a_clamped = nullptr, int n_int = 0)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_s) return;
     const V4<CT> xi = As[w];
+    const int i = sperm[w];
     int cx, cy, cz;
     T p = (T)0, vol = (T)0;
+    // resulting_acceleration = acceleration_source(fluid) - current_acceleration(system, particle): the prescribed
+    // acceleration of a moving WALL particle (wall_boundary/system.jl:133-142, dummy_particles.jl:652-654)
+    T acc[3] = {k.acc[0], k.acc[1], k.acc[2]};
+    if (a_clamped != nullptr && i >= n_int) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) acc[d] -= a_clamped[(int64_t)(i - n_int) * ND + d];
+    }
+    const V4<T> vi = Bs[w];  // (velocity, .) of this particle, written by k_reorder_struct
     if (!cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz)) atomicOr(flags, 1);
     else if (enabled) {
         for_neighbor_rows<ND, CT>(g, fcell_start, cx, cy, cz, [&](int j0, int j1) {
@@ -456,10 +469,18 @@ k_struct_adami(int n_s, GridConst<CT> g, const V4<CT> *__restrict__ As, const in
                 const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
                 if (d2 <= k.radius2_b) {
                     const T dist = sqrt_rn(d2);
-                    const T rho_f = B[j].w;
-                    T hyd = k.acc[0] * (rho_f * pd[0]) + k.acc[1] * (rho_f * pd[1]);
-                    if (ND == 3) hyd += k.acc[2] * (rho_f * pd[2]);
-                    const T sum_p = k.p_off + P[j] + hyd;
+                    const V4<T> bj = B[j];
+                    const T rho_f = bj.w;
+                    T hyd = acc[0] * (rho_f * pd[0]) + acc[1] * (rho_f * pd[1]);
+                    if (ND == 3) hyd += acc[2] * (rho_f * pd[2]);
+                    T dyn = (T)0;
+                    if (k.bernoulli != (T)0) {  // dummy_particles.jl:680-707
+                        T vn = (vi.x - bj.x) * pd[0] + (vi.y - bj.y) * pd[1];
+                        if (ND == 3) vn += (vi.z - bj.z) * pd[2];
+                        vn = vn / dist;
+                        dyn = k.bernoulli * rho_f * (vn * vn) / (T)2;
+                    }
+                    const T sum_p = k.p_off + P[j] + dyn + hyd;
                     const T kw = kernel_safe<KERNEL, T>(k.kern, dist);
                     p += sum_p * kw;
                     vol += kw;
@@ -472,7 +493,6 @@ k_struct_adami(int n_s, GridConst<CT> g, const V4<CT> *__restrict__ As, const in
     const T rho = eos_inverse(k.eos, p);
     Bs[w].w = rho;
     Ps[w] = p;
-    const int i = sperm[w];
     p_orig[i] = p;
     rho_orig[i] = rho;
 }

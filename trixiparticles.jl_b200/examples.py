@@ -57,8 +57,10 @@ def dam_break_2d(particles_per_height=40, *, eltype=np.float64, coordinates_elty
 
 
 def hydrostatic_water_column_2d(fluid_particle_spacing=0.05, *, eltype=np.float32,
-                                coordinates_eltype=np.float32, density_calculator=None):
-    """examples/fluid/hydrostatic_water_column_2d.jl:13-69 (BASELINE config 2)."""
+                                coordinates_eltype=np.float32, density_calculator=None,
+                                prescribed_motion=None, system_acceleration=None):
+    """examples/fluid/hydrostatic_water_column_2d.jl:13-69 (BASELINE config 2); `prescribed_motion` /
+    `system_acceleration` as overridden by examples/fluid/accelerated_tank_2d.jl."""
     gravity = 9.81
     dx = fluid_particle_spacing
     state_equation = StateEquationCole(sound_speed=10.0, reference_density=1000.0, exponent=7,
@@ -72,11 +74,53 @@ def hydrostatic_water_column_2d(fluid_particle_spacing=0.05, *, eltype=np.float3
         tank.fluid, smoothing_kernel=kernel, smoothing_length=h,
         density_calculator=density_calculator or ContinuityDensity(),
         state_equation=state_equation, viscosity=ArtificialViscosityMonaghan(alpha=0.02, beta=0.0),
-        acceleration=(0.0, -gravity))
+        acceleration=(0.0, -gravity) if system_acceleration is None else tuple(system_acceleration))
     model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass,
                                         AdamiPressureExtrapolation(), kernel, h,
                                         state_equation=state_equation)
-    wall = WallBoundarySystem(tank.boundary, model)
+    wall = WallBoundarySystem(tank.boundary, model, prescribed_motion=prescribed_motion)
+    return fluid, wall, tank
+
+
+def accelerated_tank_2d(fluid_particle_spacing=0.05, *, eltype=np.float64, coordinates_eltype=np.float64):
+    """examples/fluid/accelerated_tank_2d.jl: the hydrostatic water column without gravity in a tank that is
+    accelerated upwards with g -- in the tank's frame the same problem."""
+    from .model import PrescribedMotion
+    g = 9.81
+    motion = PrescribedMotion(lambda x, t: x + np.array([0.0, 0.5 * g * t * t])[None, :], lambda t: True,
+                              velocity_function=lambda x, t: np.broadcast_to(np.array([0.0, g * t]), x.shape),
+                              acceleration_function=lambda x, t: np.broadcast_to(np.array([0.0, g]), x.shape))
+    return hydrostatic_water_column_2d(fluid_particle_spacing, eltype=eltype, coordinates_eltype=coordinates_eltype,
+                                       prescribed_motion=motion, system_acceleration=(0.0, 0.0))
+
+
+def moving_wall_2d(fluid_particle_spacing=0.05, *, eltype=np.float64, coordinates_eltype=np.float64):
+    """examples/fluid/moving_wall_2d.jl:13-77: a water column in a tank whose right wall, reset to the edge of
+    the column, moves away with x + t^2 / 2 for t < 1.5.  Returns (fluid, wall, tank)."""
+    from .model import PrescribedMotion
+    from .setups import reset_wall_
+    gravity = 9.81
+    dx = fluid_particle_spacing
+    initial_fluid_size, tank_size = (1.0, 0.8), (4.0, 1.0)
+    sound_speed = 10 * np.sqrt(gravity * initial_fluid_size[1])
+    state_equation = StateEquationCole(sound_speed=sound_speed, reference_density=1000.0, exponent=7)
+    tank = RectangularTank(dx, initial_fluid_size, tank_size, 1000.0, n_layers=3, spacing_ratio=1.0,
+                           acceleration=(0.0, -gravity), state_equation=state_equation,
+                           coordinates_eltype=coordinates_eltype, eltype=eltype)
+    reset_wall_(tank, (False, True, False, False), (0.0, tank.fluid_size[0], 0.0, 0.0))
+    motion = PrescribedMotion(lambda x, t: x + np.array([0.5 * t * t, 0.0])[None, :], lambda t: t < 1.5,
+                              moving_particles=tank.face_indices[1],
+                              velocity_function=lambda x, t: np.broadcast_to(np.array([t, 0.0]), x.shape),
+                              acceleration_function=lambda x, t: np.broadcast_to(np.array([1.0, 0.0]), x.shape))
+    h = 1.2 * dx
+    kernel = SchoenbergCubicSplineKernel(2)
+    fluid = WeaklyCompressibleSPHSystem(
+        tank.fluid, smoothing_kernel=kernel, smoothing_length=h, density_calculator=ContinuityDensity(),
+        state_equation=state_equation, viscosity=ArtificialViscosityMonaghan(alpha=0.1, beta=0.0),
+        acceleration=(0.0, -gravity))
+    model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass,
+                                        AdamiPressureExtrapolation(), kernel, h, state_equation=state_equation)
+    wall = WallBoundarySystem(tank.boundary, model, prescribed_motion=motion)
     return fluid, wall, tank
 
 
@@ -143,7 +187,8 @@ def perturbed_state(fluid, seed=1234, position_jitter=0.1, velocity_scale=0.05,
 
 def dam_break_plate_2d(fluid_particle_spacing=0.01, *, n_particles_x=5, eltype=np.float64,
                        coordinates_eltype=None, initial_fluid_size=(0.146, 2 * 0.146), plate_position=None,
-                       E=1e6, nu=0.0, structure_boundary_model="monaghan_kajtar"):
+                       E=1e6, nu=0.0, structure_boundary_model="monaghan_kajtar", clamped_particles_motion=None,
+                       structure_pressure_extrapolation=None):
     """examples/fsi/dam_break_plate_2d.jl:19-134 (BASELINE config 5): dam break against an elastic
     plate clamped at its base; WCSPH fluid, dummy-particle tank, TLSPH plate with a
     BoundaryModelMonaghanKajtar towards the fluid and a PenaltyForceGanzenmueller.  The reference's
@@ -188,13 +233,14 @@ def dam_break_plate_2d(fluid_particle_spacing=0.01, *, n_particles_x=5, eltype=n
         # the alternative the example keeps in a comment (dam_break_plate_2d.jl:120-133) and
         # examples/fsi/hydrostatic_water_column_2d.jl:109-124 uses
         model_structure = BoundaryModelDummyParticles(hydrodynamic_densities, hydrodynamic_masses,
-                                                      AdamiPressureExtrapolation(), kernel, h,
-                                                      state_equation=state_equation)
+                                                      structure_pressure_extrapolation or AdamiPressureExtrapolation(),
+                                                      kernel, h, state_equation=state_equation)
     else:
         model_structure = BoundaryModelMonaghanKajtar(k_structure, dx / ds, ds, hydrodynamic_masses)
     structure_system = TotalLagrangianSPHSystem(
         structure, smoothing_kernel=WendlandC2Kernel(2), smoothing_length=np.sqrt(2) * ds, young_modulus=E,
         poisson_ratio=nu, boundary_model=model_structure, clamped_particles=range(clamped.nparticles),
+        clamped_particles_motion=clamped_particles_motion,
         acceleration=(0.0, -gravity), penalty_force=PenaltyForceGanzenmueller(alpha=0.01))
     return fluid, wall, structure_system, tank
 

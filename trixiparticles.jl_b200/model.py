@@ -200,9 +200,9 @@ class AdamiPressureExtrapolation:
 
 @dataclass(frozen=True)
 class BernoulliPressureExtrapolation:
-    """dummy_particles.jl:150-187.  Its dynamic-pressure term applies to *moving* boundaries only
-    (`if system.ismoving[]`, dummy_particles.jl:680-694); for the static walls of the accelerated
-    path it is exactly `AdamiPressureExtrapolation` with the same `pressure_offset`."""
+    """dummy_particles.jl:150-187.  Its dynamic-pressure term `factor * rho_f * (v_rel . n)^2 / 2` applies to a
+    wall only while it moves (`if system.ismoving[]`, dummy_particles.jl:680-694) -- for a static wall it is exactly
+    `AdamiPressureExtrapolation` with the same `pressure_offset` -- and always to a structure (:696-707)."""
     pressure_offset: float = 0.0
     factor: float = 1.0
     allow_loop_flipping: bool = True
@@ -297,18 +297,141 @@ class BoundaryModelDummyParticles:
         self.cache = dict(density=self.initial_density.copy(), volume=np.zeros(n, dtype=self.eltype))
 
 
-class WallBoundarySystem:
-    """wall_boundary/system.jl:22-60 (static wall: `prescribed_motion=nothing`)."""
+class PrescribedMotion:
+    """schemes/boundary/prescribed_motion.jl:1-121: `PrescribedMotion(movement_function, is_moving;
+    moving_particles=nothing)`.
+
+    `movement_function(x, t)`: here `x` is the (n, ND) float64 array of the INITIAL positions of the moving
+    particles (the reference calls it per particle with an SVector; write it with `x[:, 0]`, `x[:, 1]`, ...) and
+    the return value the (n, ND) array of their positions at time `t`.  `is_moving(t)` -> bool.
+    `moving_particles`: 0-based indices into the system (default: every particle of a `WallBoundarySystem`, every
+    clamped particle of a `TotalLagrangianSPHSystem`).
+
+    The reference differentiates the movement function twice with ForwardDiff (:107-111).  Without automatic
+    differentiation the caller can hand over the exact `velocity_function(x, t)` / `acceleration_function(x, t)`;
+    otherwise fourth-order central differences in float64 with step `fd_step` are used (exact up to rounding for
+    polynomials in t up to degree 4)."""
+
+    def __init__(self, movement_function, is_moving, *, moving_particles=None, velocity_function=None,
+                 acceleration_function=None, fd_step=1e-3):
+        self.movement_function = movement_function
+        self.is_moving = is_moving
+        self.moving_particles = None if moving_particles is None else np.asarray(moving_particles, dtype=np.int64).ravel()
+        self.velocity_function = velocity_function
+        self.acceleration_function = acceleration_function
+        self.fd_step = float(fd_step)
+
+    def initialize(self, n_particles, n_clamped=None):
+        """initialize_prescribed_motion! (:65-88): an empty `moving_particles` means all clamped particles (the
+        last `n_clamped` of the system; a wall: all)."""
+        n_clamped = n_particles if n_clamped is None else n_clamped
+        if self.moving_particles is None or self.moving_particles.size == 0:
+            self.moving_particles = np.arange(n_particles - n_clamped, n_particles, dtype=np.int64)
+        if len(self.moving_particles) and (self.moving_particles.min() < n_particles - n_clamped
+                                            or self.moving_particles.max() >= n_particles):
+            raise ValueError("`moving_particles` must be clamped particles of the system")
+        return self
+
+    def __call__(self, x0, t):
+        """(:95-121) positions, velocities and accelerations (float64, (n, ND)) of the moving particles whose
+        initial positions are `x0`, at time `t`."""
+        x0 = np.asarray(x0, dtype=np.float64)
+        t = float(t)
+        f = lambda tt: np.asarray(self.movement_function(x0, tt), dtype=np.float64).reshape(x0.shape)
+        pos = f(t)
+        h = self.fd_step
+        if self.velocity_function is None or self.acceleration_function is None:
+            fm2, fm1, fp1, fp2 = f(t - 2 * h), f(t - h), f(t + h), f(t + 2 * h)
+        if self.velocity_function is not None:
+            vel = np.asarray(self.velocity_function(x0, t), dtype=np.float64).reshape(x0.shape)
+        else:
+            vel = (fm2 - 8.0 * fm1 + 8.0 * fp1 - fp2) / (12.0 * h)
+        if self.acceleration_function is not None:
+            acc = np.asarray(self.acceleration_function(x0, t), dtype=np.float64).reshape(x0.shape)
+        else:
+            acc = (-fm2 + 16.0 * fm1 - 30.0 * pos + 16.0 * fp1 - fp2) / (12.0 * h * h)
+        return pos, vel, acc
+
+
+def OscillatingMotion2D(*, frequency, translation_vector, rotation_angle, rotation_center,
+                        rotation_phase_offset=0, tspan=(-np.inf, np.inf), ramp_up_tspan=(0.0, 0.0),
+                        moving_particles=None):
+    """prescribed_motion.jl:123-203: translation + rotation about a centre with the same frequency, optional
+    smoothstep ramp-up."""
+    tv = np.asarray(translation_vector, dtype=np.float64).reshape(2)
+    rc = np.asarray(rotation_center, dtype=np.float64).reshape(2)
+
+    def movement_function(x, t):
+        if np.isfinite(tspan[0]):
+            t = t - tspan[0]
+        sin_scaled = np.sin(frequency * 2 * np.pi * t)
+        xc = x - rc[None, :]
+        angle = rotation_angle * np.sin(2 * np.pi * (frequency * t - rotation_phase_offset))
+        rotated = np.stack([xc[:, 0] * np.cos(angle) - xc[:, 1] * np.sin(angle),
+                            xc[:, 0] * np.sin(angle) + xc[:, 1] * np.cos(angle)], axis=1)
+        result = rotated + rc[None, :] + sin_scaled * tv[None, :]
+        if ramp_up_tspan[1] > ramp_up_tspan[0] and ramp_up_tspan[0] <= t <= ramp_up_tspan[1]:
+            t_rel = (t - ramp_up_tspan[0]) / (ramp_up_tspan[1] - ramp_up_tspan[0])
+            ramp = 3 * t_rel ** 2 - 2 * t_rel ** 3
+            return result * ramp + (1 - ramp) * x
+        return result
+
+    return PrescribedMotion(movement_function, lambda t: tspan[0] <= t <= tspan[1], moving_particles=moving_particles)
+
+
+class _MovingParticles:
+    """The host side of apply_prescribed_motion! (wall_boundary/system.jl:199-205, total_lagrangian_sph/
+    system.jl:436-447) for the clamped tail of a system: where those particles are, how they move."""
+
+    def _init_motion(self, motion, initial_coordinates, n_clamped):
+        n = initial_coordinates.shape[0]
+        self.prescribed_motion = motion
+        self.ismoving = motion is not None
+        if motion is None:
+            return
+        motion.initialize(n, n_clamped)
+        self._x0_clamped = np.array(initial_coordinates[n - n_clamped:], dtype=np.float64)
+        self._moving_local = motion.moving_particles - (n - n_clamped)
+        self.clamped_coordinates = self._x0_clamped.copy()
+        self.clamped_velocity = np.zeros_like(self._x0_clamped)
+        self.clamped_acceleration = np.zeros_like(self._x0_clamped)
+
+    def apply_prescribed_motion(self, t):
+        """-> is_moving(t); updates clamped_coordinates / _velocity / _acceleration (float64)."""
+        m = self.prescribed_motion
+        self.ismoving = bool(m.is_moving(t))
+        if not self.ismoving:
+            return False
+        idx = self._moving_local
+        pos, vel, acc = m(self._x0_clamped[idx], t)
+        self.clamped_coordinates[idx] = pos
+        self.clamped_velocity[idx] = vel
+        self.clamped_acceleration[idx] = acc
+        return True
+
+
+class WallBoundarySystem(_MovingParticles):
+    """wall_boundary/system.jl:22-60.  With `prescribed_motion` the wall is registered with the library as a
+    system of clamped, moving dummy particles (free-slip Adami / Bernoulli extrapolation)."""
 
     def __init__(self, initial_condition: InitialCondition, boundary_model, *,
                  prescribed_motion=None, adhesion_coefficient=0.0):
-        if prescribed_motion is not None or adhesion_coefficient != 0.0:
-            raise ValueError("moving walls / adhesion are outside the accelerated hot path")
+        if adhesion_coefficient != 0.0:
+            raise ValueError("adhesion is outside the accelerated hot path")
+        if prescribed_motion is not None:
+            if not isinstance(prescribed_motion, PrescribedMotion):
+                raise TypeError("`prescribed_motion` must be a PrescribedMotion")
+            if (not isinstance(boundary_model, BoundaryModelDummyParticles)
+                    or isinstance(boundary_model.density_calculator, ContinuityDensity)
+                    or boundary_model.viscosity is not None):
+                raise ValueError("a moving wall on the accelerated path: BoundaryModelDummyParticles with Adami / "
+                                 "Bernoulli pressure extrapolation and no viscosity (free-slip)")
         self.initial_condition = initial_condition
         self.coordinates = initial_condition.coordinates
         self.boundary_model = boundary_model
         self.eltype = boundary_model.eltype
         self.coordinates_eltype = initial_condition.coordinates_eltype
+        self._init_motion(prescribed_motion, initial_condition.coordinates, initial_condition.nparticles)
 
     ndims = property(lambda self: self.initial_condition.ndims)
     nparticles = property(lambda self: self.initial_condition.nparticles)
@@ -342,10 +465,12 @@ class BoundaryModelMonaghanKajtar:
         self.viscosity = None
 
 
-class TotalLagrangianSPHSystem:
+class TotalLagrangianSPHSystem(_MovingParticles):
     """structure/total_lagrangian_sph/system.jl:76-184 on the accelerated path (BASELINE config 5):
-    scalar `young_modulus` / `poisson_ratio`, fixed clamped particles, optional
-    `PenaltyForceGanzenmueller`, `boundary_model` = `BoundaryModelMonaghanKajtar` or None.
+    scalar `young_modulus` / `poisson_ratio`, clamped particles fixed or moved by
+    `clamped_particles_motion=PrescribedMotion(...)` (whose `moving_particles` index the sorted system), optional
+    `PenaltyForceGanzenmueller`, `boundary_model` = `BoundaryModelMonaghanKajtar`, `BoundaryModelDummyParticles`
+    or None.
     As in the reference, the clamped particles are moved to the end of the particle list
     (`move_particles_to_end!`); `clamped_particles` are 0-based indices here."""
 
@@ -361,7 +486,9 @@ class TotalLagrangianSPHSystem:
             acceleration = (0.0,) * nd
         if len(acceleration) != nd:
             raise ValueError(f"`acceleration` must be of length {nd} for a {nd}D problem")
-        for name, val in (("clamped_particles_motion", clamped_particles_motion), ("viscosity", viscosity),
+        if clamped_particles_motion is not None and not isinstance(clamped_particles_motion, PrescribedMotion):
+            raise TypeError("`clamped_particles_motion` must be a PrescribedMotion")
+        for name, val in (("viscosity", viscosity),
                           ("source_terms", source_terms), ("velocity_averaging", velocity_averaging)):
             if val is not None:
                 raise ValueError(f"`{name}` is outside the accelerated hot path (see DESIGN.md)")
@@ -410,6 +537,7 @@ class TotalLagrangianSPHSystem:
         self.initial_coordinates = self.initial_condition.coordinates
         self.mass = self.initial_condition.mass
         self.material_density = self.initial_condition.density
+        self._init_motion(clamped_particles_motion, self.initial_coordinates, self.n_clamped_particles)
 
     ndims = property(lambda self: self.initial_condition.ndims)
     nparticles = property(lambda self: self.initial_condition.nparticles)

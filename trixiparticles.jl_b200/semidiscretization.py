@@ -105,6 +105,18 @@ class Semidiscretization:
         self.ranges_u = tuple((sum(sizes_u[:i]), sum(sizes_u[:i + 1])) for i in range(n))
         self.ranges_v = tuple((sum(sizes_v[:i]), sum(sizes_v[:i + 1])) for i in range(n))
         self._handle = None
+        # the system whose clamped particles follow a PrescribedMotion (a moving wall or a structure), if any
+        movers = [s for s in systems if getattr(s, "prescribed_motion", None) is not None]
+        if len(movers) > 1:
+            raise ValueError("at most one system with a PrescribedMotion is on the accelerated path")
+        self._motion_system = movers[0] if movers else None
+        # inside the library a moving wall and a Monaghan-Kajtar wall occupy the (single) structure slot
+        slot = [s for s in systems if isinstance(s, TotalLagrangianSPHSystem)
+                or (isinstance(s, WallBoundarySystem)
+                    and (s.prescribed_motion is not None or isinstance(s.boundary_model, BoundaryModelMonaghanKajtar)))]
+        if len(slot) > 1:
+            raise ValueError("a structure system, a moving wall and a Monaghan-Kajtar wall exclude each other on the "
+                             "accelerated path (one of them per semidiscretization)")
 
     # -- helpers ---------------------------------------------------------------------------
     @property
@@ -238,6 +250,8 @@ class Semidiscretization:
             p.bm_reference_density = float(t(se.reference_density))
             p.bm_background_pressure = float(t(se.background_pressure))
             p.bm_pressure_offset = float(t(m.density_calculator.pressure_offset))
+            # BernoulliPressureExtrapolation on a structure: the dynamic term always applies (dummy_particles.jl:696-707)
+            p.bm_bernoulli_factor = float(t(getattr(m.density_calculator, "factor", 0.0)))
         elif m is not None:
             p.boundary_model = _lib.BOUNDARY_MONAGHAN_KAJTAR
             p.mk_K, p.mk_beta, p.mk_spacing = float(t(m.K)), float(t(m.beta)), float(t(m.boundary_particle_spacing))
@@ -290,6 +304,35 @@ class Semidiscretization:
                     _lib.check(h, L.tpb_add_structure_system(h, C.byref(sp), s.nparticles, s.n_integrated_particles,
                                                              x0.ctypes.data, mass.ctypes.data, rho.ctypes.data,
                                                              hyd.ctypes.data if hyd is not None else None,
+                                                             C.byref(idx)))
+                elif s.prescribed_motion is not None:
+                    # a moving wall (wall_boundary/system.jl:22-60 with prescribed_motion): dummy particles whose
+                    # positions / velocities / accelerations are prescribed -- inside the library a structure
+                    # without integrated particles carrying the wall's boundary model (tpb200.h, bm_wall_semantics)
+                    if be.ghost_capacity:
+                        raise ValueError("slab ghosts are not combined with a moving wall")
+                    m, t = s.boundary_model, self.eltype.type
+                    se = m.state_equation
+                    sp = _lib.StructureParams()
+                    sp.struct_size = C.sizeof(_lib.StructureParams)
+                    sp.kernel = self.fluid.smoothing_kernel.kernel_id
+                    sp.smoothing_length = float(t(self.fluid.smoothing_length))
+                    sp.young_modulus, sp.poisson_ratio = 1.0, 0.0
+                    sp.boundary_model = _lib.BOUNDARY_DUMMY_PARTICLES
+                    sp.bm_kernel = m.smoothing_kernel.kernel_id
+                    sp.bm_clip_negative_pressure = int(m.clip_negative_pressure)
+                    sp.bm_smoothing_length = float(t(m.smoothing_length))
+                    sp.bm_sound_speed, sp.bm_exponent = float(t(se.sound_speed)), float(t(se.exponent))
+                    sp.bm_reference_density = float(t(se.reference_density))
+                    sp.bm_background_pressure = float(t(se.background_pressure))
+                    sp.bm_pressure_offset = float(t(m.density_calculator.pressure_offset))
+                    sp.bm_wall_semantics = 1
+                    sp.bm_bernoulli_factor = float(t(getattr(m.density_calculator, "factor", 0.0)))
+                    x0 = np.ascontiguousarray(s.coordinates, dtype=self.coordinates_eltype)
+                    hyd = np.ascontiguousarray(m.hydrodynamic_mass, dtype=self.eltype)
+                    rho = np.ascontiguousarray(m.initial_density, dtype=self.eltype)
+                    _lib.check(h, L.tpb_add_structure_system(h, C.byref(sp), s.nparticles, 0, x0.ctypes.data,
+                                                             hyd.ctypes.data, rho.ctypes.data, hyd.ctypes.data,
                                                              C.byref(idx)))
                 elif isinstance(s.boundary_model, BoundaryModelMonaghanKajtar):
                     # a wall of repulsive particles (test/examples/gpu.jl:219-253): inside the library the
@@ -376,6 +419,25 @@ class Semidiscretization:
         out = C.c_double(0.0)
         _lib.check(self._handle, _lib.load().tpb_get_sound_speed(self._handle, C.byref(out)))
         return out.value
+
+    def apply_prescribed_motion(self, t):
+        """update_positions! -> apply_prescribed_motion! (wall_boundary/system.jl:192-205, total_lagrangian_sph/
+        system.jl:403-447) for the system that has a PrescribedMotion: the movement function runs on the host, the
+        library gets the clamped particles' positions, velocities and accelerations for the next kick."""
+        s = self._motion_system
+        if s is None:
+            return
+        L = _lib.load()
+        if s.apply_prescribed_motion(t):
+            x = np.ascontiguousarray(s.clamped_coordinates, dtype=self.coordinates_eltype)
+            v = np.ascontiguousarray(s.clamped_velocity, dtype=self.eltype)
+            a = np.ascontiguousarray(s.clamped_acceleration, dtype=self.eltype)
+            _lib.check(self._handle, L.tpb_set_clamped_motion(self._handle, x.ctypes.data, v.ctypes.data,
+                                                              a.ctypes.data, 1))
+            if isinstance(s, WallBoundarySystem):
+                s.coordinates = x    # current_coordinates(u, wall) = system.coordinates
+        else:
+            _lib.check(self._handle, L.tpb_set_clamped_motion(self._handle, None, None, None, 0))
 
     def set_integrate_structure(self, enabled: bool):
         """`semi.integrate_tlsph[] = enabled` (semidiscretization.jl:149): with a SplitIntegrationCallback kick! /
@@ -525,6 +587,7 @@ def kick_(dv_ode, v_ode, u_ode, p, t):
     pv = semi._ptr(v_ode, nv, semi.eltype, "v_ode")
     pu = semi._ptr(u_ode, nu, semi.coordinates_eltype, "u_ode")
     semi._bind_stream()
+    semi.apply_prescribed_motion(float(t))
     _lib.check(semi._handle, _lib.load().tpb_kick(semi._handle, pdv, pv, pu, float(t)))
     return dv_ode
 

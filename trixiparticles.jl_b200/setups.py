@@ -215,6 +215,12 @@ class RectangularTankResult:
     n_layers: int
     n_particles_per_dimension: tuple
     face_ranges: dict = field(default_factory=dict)
+    # `face_indices[f]`: 0-based indices (into `boundary`) of the particles of face f's own block (edges and
+    # corners excluded), faces numbered left, right, bottom, top(, front, back) from 0 (rectangular_tank.jl:93,
+    # :535-620, :701-832); empty when the tank was built with an x window
+    face_indices: tuple = ()
+    particle_spacing: float = 0.0
+    spacing_ratio: float = 1.0
 
 
 def _tank_boundary_blocks(ndims, spacing, tank_size, n_b, n_layers, faces):
@@ -315,6 +321,19 @@ def RectangularTank(particle_spacing, fluid_size: Sequence[float], tank_size: Se
     parts = [rectangular_shape_coords(b_spacing, npd, mc, loop_order=lo, coordinates_eltype=coordinates_eltype,
                                       x_range=xr(b_spacing, npd[0], mc[0], b_win))
              for npd, mc, lo in blocks if int(np.prod(npd)) > 0]
+    face_indices = ()
+    if b_win is None:
+        # the face blocks come first, in face order (only the faces that exist)
+        sizes = [int(np.prod(npd)) for npd, mc, lo in blocks if int(np.prod(npd)) > 0]
+        starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        fi, k = [], 0
+        for present in faces:
+            if present and k < len(sizes):
+                fi.append(np.arange(starts[k], starts[k + 1], dtype=np.int64))
+                k += 1
+            else:
+                fi.append(np.zeros(0, dtype=np.int64))
+        face_indices = tuple(fi)
     if parts:
         b_coords = np.concatenate(parts)
     else:
@@ -351,4 +370,25 @@ def RectangularTank(particle_spacing, fluid_size: Sequence[float], tank_size: Se
                                  np.zeros((0, ndims), dtype=t), np.zeros(0, dtype=t),
                                  np.zeros(0, dtype=t), np.zeros(0, dtype=t), spacing)
     return RectangularTankResult(fluid, boundary, tuple(fluid_size_), tuple(tank_size_),
-                                 n_layers, tuple(n_f))
+                                 n_layers, tuple(n_f), face_indices=face_indices, particle_spacing=spacing,
+                                 spacing_ratio=spacing_ratio)
+
+
+def reset_wall_(tank: RectangularTankResult, reset_faces, positions):
+    """`reset_wall!(tank, reset_faces, positions)` (rectangular_tank.jl:1160-1191): moves the particles of the
+    given faces so that the face's inner surface is at `positions[face]`; layer l (1 = next to the fluid) lands at
+    positions + (l - 1) dx + dx/2 for the even (right/top/back) faces, positions - (l - 1) dx - dx/2 for the odd."""
+    dx = tank.particle_spacing / tank.spacing_ratio
+    x = tank.boundary.coordinates
+    for face, do in enumerate(reset_faces):
+        if not do or face >= len(tank.face_indices) or tank.face_indices[face].size == 0:
+            continue
+        dim, idx = face // 2, tank.face_indices[face]
+        c = x[idx, dim].astype(np.float64)
+        if face % 2 == 1:   # right / top / back: layers count away from the tank's far side
+            layer = np.rint((c - c.min()) / dx)
+            x[idx, dim] = (positions[face] + layer * dx + 0.5 * dx).astype(x.dtype)
+        else:
+            layer = np.rint((c.max() - c) / dx)
+            x[idx, dim] = (positions[face] - layer * dx - dx + 0.5 * dx).astype(x.dtype)
+    return tank

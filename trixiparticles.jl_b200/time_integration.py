@@ -391,6 +391,8 @@ def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
     if split is not None:
         split.initialize(semi, ode.v0, ode.u0, ode.tspan[0])   # (also: the StepsizeCallback skips the structure)
         cuda_graph = False                                      # the number of sub-steps varies from stage to stage
+    if getattr(semi, "_motion_system", None) is not None:
+        cuda_graph = False                                      # the movement function runs on the host, per kick
     if stepsize is not None:
         dt = stepsize.dt(semi)
     if dt is None or not dt > 0:
