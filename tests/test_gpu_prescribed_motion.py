@@ -142,3 +142,27 @@ def test_accelerated_tank_time_loop():
     assert np.abs(u_a - [0.0, 0.5 * g * t_a ** 2] - u_h).max() <= 1e-9
     assert np.abs(v_a[:, :2] - [0.0, g * t_a] - v_h[:, :2]).max() <= 1e-7
     assert rel_inf(v_a[:, 2], v_h[:, 2]) <= 1e-10
+
+
+def test_moving_wall_2d_time_loop():
+    """examples/fluid/moving_wall_2d.jl:71-77 as the reference's example test runs it (test/examples/
+    examples_fluid.jl:690-700: retcode Success, no NaN), shortened to t = 0.8: `solve(ode, RDPK3SpFSAL35(),
+    abstol=1e-6, reltol=1e-4, dtmax=1e-2)`.  The right wall recedes with x = 1 + t^2/2, the column collapses behind
+    it: the front follows the wall, nothing passes through it, the mass stays in the tank."""
+    from trixiparticles.jl_b200.time_integration import RDPK3SpFSAL35, solve
+    fluid, wall, tank = examples.moving_wall_2d(0.05)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 0.8))
+    sol = solve(ode, RDPK3SpFSAL35(), abstol=1e-6, reltol=1e-4, dtmax=1e-2)
+    assert sol.retcode == "Success" and sol.t == 0.8
+    u = sol.u.cpu().numpy().reshape(-1, 2)
+    v = sol.v.cpu().numpy().reshape(-1, 3)
+    assert np.isfinite(u).all() and np.isfinite(v).all()
+    x_wall = tank.fluid_size[0] + 0.5 * 0.8 ** 2            # inner surface of the moving wall
+    mov = tank.face_indices[1]
+    assert np.allclose(wall.coordinates[mov, 0].min(), x_wall + 0.025, atol=1e-9)
+    assert u[:, 0].max() < x_wall and u[:, 0].min() > 0.0 and u[:, 1].min() > 0.0
+    assert u[:, 0].max() > 1.1                              # the front has followed the wall
+    assert u[:, 1].max() < 0.8 + 1e-3                       # and the column has not grown
+    assert 950.0 < v[:, 2].min() and v[:, 2].max() < 1100.0
+    semi.close()
