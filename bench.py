@@ -273,6 +273,17 @@ def run_single(args):
         u_d, v_d = sol.u.contiguous(), sol.v.contiguous()
         semi.synchronize()
 
+    if args.sort:
+        # SortingCallback (callbacks/sorting.jl): one tpb_sort_system undoes --shuffle; timed separately
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        semi.sort_particles(v_d, u_d)
+        e1.record()
+        torch.cuda.synchronize()
+        sort_ms = e0.elapsed_time(e1)
+    else:
+        sort_ms = None
+
     def step():
         ode.f1(dv_d, v_d, u_d, ode.p, 0.0)
         ode.f2(du_d, v_d, u_d, ode.p, 0.0)
@@ -319,7 +330,8 @@ def run_single(args):
     if args.quick:
         print(json.dumps({"quick": True, "workload": args.workload, "ms_per_step": total_ms / args.steps,
                           "value": value, "phases_ms": phases, "kick_ms": float(ms_kick.mean()),
-                          "variant": int(st1.interact_variant_used),
+                          "variant": int(st1.interact_variant_used), "shuffle": bool(args.shuffle),
+                          "sort_ms": sort_ms,
                           "env": {k: v for k, v in os.environ.items() if k.startswith("TPB_")}}))
         return
 
@@ -566,6 +578,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the other precision set-ups")
     ap.add_argument("--shuffle", action="store_true", help="random particle order in the ODE vectors")
+    ap.add_argument("--sort", action="store_true", help="tpb_sort_system (SortingCallback) before timing; with --shuffle")
     ap.add_argument("--no-slip", action="store_true", help="no-slip wall (wall viscosity = fluid viscosity) on a "
                     "synthetic velocity field instead of the free-slip headline workload")
     ap.add_argument("--evolve", type=int, default=0, help="time steps to run before measuring (evolved state)")

@@ -82,6 +82,8 @@ struct Semi {
     // velocity / acceleration of the clamped particles ((n_s - n_s_int) x ND), used while clamped_moving
     void *d_xcl_s = nullptr, *d_vcl_s = nullptr, *d_acl_s = nullptr;
     int clamped_moving = 0;
+    // tpb_sort_system on device vectors: gather targets (allocated at the first call; host mode uses d_du / d_dv)
+    void *d_sort_u = nullptr, *d_sort_v = nullptr;
 
     // geometry of the shared cell grid (double; typed copies are built per call)
     double cell_size = 0, origin[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
@@ -102,6 +104,7 @@ struct Semi {
     unsigned long long *d_scan_status = nullptr;
     unsigned long long *d_scan_ticket = nullptr;
     int scan_blocks = 0, scan_rows_per_block = 0;  // 0 blocks: grid shape not supported, three-kernel scan instead
+    int subkey_mode = 1;           // order inside a cell: 0 previous index, 1.. position key (tpb_nhs.cuh, TPB_SUBKEY)
     bool count_clean = false;      // the cell histogram is all zero (left so by k_scan_cells_tiles)
     bool wall_prep_done = false;   // this kick's rebuild launch has sorted the wall tiles into empty / active
     int *h_flags = nullptr;  // pinned
@@ -342,19 +345,23 @@ struct Ops {
     static constexpr int nv(const Semi &s) { return s.fp.density_calculator == TPB_DENSITY_SUMMATION ? ND : ND + 1; }
 
     // ---- counting sort of one point set into the shared grid: key/slot/count/scan/scatter
+    // bits of a tmp_perm entry that hold the particle index (the position key sits above them)
+    static int perm_bits(const Semi &s, int64_t n) { return s.subkey_mode && n < (1 << PERM_IDX_BITS) ? PERM_IDX_BITS : 31; }
+
     static int bin_points(Semi &s, const CT *d_coords, int n, int n_targets, int *d_cell_start)
     {
         GridConst<CT> g = make_grid_const<CT>(s);
+        const int pb = perm_bits(s, n);
         CUDA_TRY(&s, cudaMemsetAsync(s.d_count, 0, sizeof(int) * (size_t)s.ncells, s.stream));
         s.count_clean = false;
         if (n > 0)
             LAUNCH(s, (k_cell_count<ND, CT>), cdiv(n, 256), 256, 0, d_coords, n, n_targets, g, s.d_key,
-                   s.d_slot, s.d_count, s.d_flags);
+                   s.d_slot, s.d_count, s.d_flags, pb < 31 ? s.subkey_mode : 0);
         int rc = exclusive_scan(s, s.d_count, (int)s.ncells, d_cell_start);
         if (rc) return rc;
         if (n > 0)
             LAUNCH(s, k_scatter, cdiv(n, 256), 256, 0, s.d_key, s.d_slot, d_cell_start, n,
-                   s.d_tmp_perm);
+                   s.d_tmp_perm, pb);
         return TPB_OK;
     }
 
@@ -412,7 +419,7 @@ struct Ops {
         }
         if (n > 0)
             LAUNCH(s, (k_cell_count<ND, CT>), cdiv(n, 256), 256, 0, d_u, n, (int)s.n_tgt, g, s.d_key, s.d_slot,
-                   s.d_count, s.d_flags);
+                   s.d_count, s.d_flags, perm_bits(s, n) < 31 ? s.subkey_mode : 0);
         const bool has_wall = s.n_w > 0;                           // a second neighbour set for the fluid tiles
         const bool wall = has_wall && !wall_integrates_density(s);  // Adami walls: sort the wall tiles as well
         LAUNCH(s, k_scan_cells_tiles, s.scan_blocks, CSCAN_THREADS, 0, s.d_count, s.ncell[0], s.tiles.nrows,
@@ -425,7 +432,7 @@ struct Ops {
         LAUNCH(s, (k_post_scan<ND, T, CT>), nb_scatter + nb_ranges + nb_wprep, 256, 0, nb_scatter, nb_ranges, s.d_key,
                s.d_slot, s.d_fcell_start, n, s.d_tmp_perm, g, s.tiles.d_frow_tile_start + s.tiles.nrows,
                s.tiles.d_ftile_desc, has_wall ? s.d_wcell_start : (const int *)nullptr, s.tiles.d_ftile_rng,
-               s.tiles.d_ftile_ext, wpa);
+               s.tiles.d_ftile_ext, wpa, perm_bits(s, n));
         s.wall_prep_done = wall;
         return TPB_OK;
     }
@@ -446,12 +453,12 @@ struct Ops {
                 LAUNCH(s, (k_reorder_fluid<ND, T, CT, 0>), cdiv(n, 256), 256, 0, d_u, d_v,
                        (const T *)s.d_mass_f, s.d_key, s.d_fcell_start, s.d_tmp_perm, n,
                        s.d_fcell_start + s.ncells, s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
-                       s.d_perm_f, g.fref, (V4<float> *)s.d_Ff, (const AdaptConsts<T> *)s.ad_kick);
+                       s.d_perm_f, g.fref, (V4<float> *)s.d_Ff, (const AdaptConsts<T> *)s.ad_kick, perm_bits(s, n));
             else
                 LAUNCH(s, (k_reorder_fluid<ND, T, CT, 1>), cdiv(n, 256), 256, 0, d_u, d_v,
                        (const T *)s.d_mass_f, s.d_key, s.d_fcell_start, s.d_tmp_perm, n,
                        s.d_fcell_start + s.ncells, s.cfg.deterministic, eos, (V4<CT> *)s.d_A, (V4<T> *)s.d_B, (T *)s.d_P,
-                       s.d_perm_f, g.fref, (V4<float> *)s.d_Ff);
+                       s.d_perm_f, g.fref, (V4<float> *)s.d_Ff, (const AdaptConsts<T> *)nullptr, perm_bits(s, n));
         }
         if (use_tiles(s) && !fused) {
             rc = build_tile_table(s, s.d_fcell_start, s.tiles.d_frow_tile_start, s.tiles.d_ftile_desc);
@@ -484,7 +491,7 @@ struct Ops {
         if (n > 0)
             LAUNCH(s, (k_reorder_wall<ND, T, CT>), cdiv(n, 256), 256, 0, d_coords, d_mass, d_dens,
                    s.d_key, s.d_wcell_start, s.d_tmp_perm, n, (V4<CT> *)s.d_Aw, (V2<T> *)s.d_Ww,
-                   s.d_perm_w, make_grid_const<CT>(s).fref, (V4<float> *)s.d_Fw);
+                   s.d_perm_w, make_grid_const<CT>(s).fref, (V4<float> *)s.d_Fw, perm_bits(s, n));
         CUDA_TRY(&s, cudaMemsetAsync(s.d_volw, 0, sizeof(T) * (size_t)std::max(n, 1), s.stream));
         rc = build_tile_table(s, s.d_wcell_start, s.tiles.d_wrow_tile_start, s.tiles.d_wtile_desc, true);
         if (rc) return rc;
@@ -656,7 +663,7 @@ struct Ops {
                 LAUNCH(s, (k_reorder_struct<ND, T, CT>), cdiv(n, 256), 256, 0, (const CT *)s.d_xcur_s, d_v_s,
                        (const T *)s.d_hydro_s, s.d_key, s.d_scell_start, s.d_tmp_perm, n, n_int, (T)1,
                        (V4<CT> *)s.d_As, (V4<T> *)s.d_Bs, s.d_sperm,
-                       s.clamped_moving ? (const T *)s.d_vcl_s : (const T *)nullptr);
+                       s.clamped_moving ? (const T *)s.d_vcl_s : (const T *)nullptr, perm_bits(s, n));
                 const DummyConst<T> dk = make_dummy_const(s, pc);
                 const int enabled = s.struct_fluid[0] && s.n_act > 0;
                 switch (kernel_template_id(s.sp.bm_kernel)) {
@@ -675,7 +682,7 @@ struct Ops {
                 LAUNCH(s, (k_reorder_struct<ND, T, CT>), cdiv(n, 256), 256, 0, (const CT *)s.d_xcur_s, d_v_s,
                        (const T *)s.d_hydro_s, s.d_key, s.d_scell_start, s.d_tmp_perm, n, n_int, mk.vol,
                        (V4<CT> *)s.d_As, (V4<T> *)s.d_Bs, (int *)nullptr,
-                       s.clamped_moving ? (const T *)s.d_vcl_s : (const T *)nullptr);
+                       s.clamped_moving ? (const T *)s.d_vcl_s : (const T *)nullptr, perm_bits(s, n));
             }
         }
         return structure_deformation(s);
@@ -1343,6 +1350,55 @@ struct Ops {
         return TPB_OK;
     }
 
+    // `SortingCallback` (callbacks/sorting.jl:100-157): the fluid's rows of (v_ode, u_ode) -- and the library's
+    // per-particle masses -- reordered by the cell of their current coordinates.  Scratch: the sorted pressure
+    // array (rewritten by the next kick) and the handle's dv / du staging buffers (host mode) or two buffers of
+    // their own (device mode).
+    static int sort_system(Semi &s, void *v_ode, void *u_ode)
+    {
+        const int n = (int)s.n_act;
+        if (s.n_tgt != s.n_act)
+            return fail(&s, TPB_ERR_UNSUPPORTED, "tpb_sort_system: not with slab ghosts (the exchange owns the row order)");
+        if (n == 0) return TPB_OK;
+        const OdeLayout lay = ode_layout(s);
+        const int NV = nv(s);
+        const bool host = s.cfg.ode_memory == TPB_MEM_HOST;
+        const size_t ub = sizeof(CT) * ND * (size_t)n, vb = sizeof(T) * NV * (size_t)n;
+        CT *u = host ? (CT *)s.d_u : (CT *)u_ode + lay.off_u_f;
+        T *v = host ? (T *)s.d_v : (T *)v_ode + lay.off_v_f;
+        if (host) {
+            CUDA_TRY(&s, cudaMemcpyAsync(u, (const CT *)u_ode + lay.off_u_f, ub, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(&s, cudaMemcpyAsync(v, (const T *)v_ode + lay.off_v_f, vb, cudaMemcpyHostToDevice, s.stream));
+        }
+        if (!host && !s.d_sort_u) {
+            CUDA_TRY(&s, cudaMalloc(&s.d_sort_u, sizeof(CT) * ND * (size_t)s.n_f));
+            CUDA_TRY(&s, cudaMalloc(&s.d_sort_v, sizeof(T) * NV * (size_t)s.n_f));
+        }
+        CT *out_u = host ? (CT *)s.d_du : (CT *)s.d_sort_u;
+        T *out_v = host ? (T *)s.d_dv : (T *)s.d_sort_v;
+        int rc = bin_points(s, u, n, n, s.d_fcell_start);
+        if (rc) return rc;
+        LAUNCH(s, (k_sort_gather<ND, T, CT>), cdiv(n, 256), 256, 0, (const CT *)u, (const T *)v, (const T *)s.d_mass_f,
+               s.d_key, s.d_fcell_start, s.d_tmp_perm, n, NV, out_u, out_v, (T *)s.d_P, perm_bits(s, n));
+        CUDA_TRY(&s, cudaMemcpyAsync(s.d_mass_f, s.d_P, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, s.stream));
+        // the fused rebuild (and a CUDA graph that captured it) counts into a histogram its scan left at zero
+        CUDA_TRY(&s, cudaMemsetAsync(s.d_count, 0, sizeof(int) * (size_t)s.ncells, s.stream));
+        s.count_clean = true;
+        if (host) {
+            CUDA_TRY(&s, cudaMemcpyAsync((CT *)u_ode + lay.off_u_f, out_u, ub, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(&s, cudaMemcpyAsync((T *)v_ode + lay.off_v_f, out_v, vb, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(&s, cudaMemcpyAsync(s.h_flags, s.d_flags, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
+            if (*s.h_flags & 1)
+                return fail(&s, TPB_ERR_OUT_OF_BOUNDS,
+                            "particle coordinates are NaN or outside the FullGridCellList bounding box");
+        } else {
+            CUDA_TRY(&s, cudaMemcpyAsync(u, out_u, ub, cudaMemcpyDeviceToDevice, s.stream));
+            CUDA_TRY(&s, cudaMemcpyAsync(v, out_v, vb, cudaMemcpyDeviceToDevice, s.stream));
+        }
+        return TPB_OK;
+    }
+
     static int get_field(Semi &s, int system, int field, void *out, int64_t n)
     {
         if (field == TPB_FIELD_WALL_VELOCITY) {
@@ -1515,7 +1571,8 @@ struct Ops {
                              int64_t *cnt);                                                              \
     int TPB_CAT(max_speed2_, TAG)(Semi &s, const void *v, void *out_bits);                               \
     int TPB_CAT(struct_force_, TAG)(Semi &s, void *out, const void *v, const void *u);                   \
-    int TPB_CAT(kick_struct_, TAG)(Semi &s, void *dv, const void *v, const void *u, const void *dv_const);
+    int TPB_CAT(kick_struct_, TAG)(Semi &s, void *dv, const void *v, const void *u, const void *dv_const); \
+    int TPB_CAT(sort_system_, TAG)(Semi &s, void *v, void *u);
 #define TPB_DEFINE_ENTRIES(TAG, ND, T, CT)                                                               \
     int TPB_CAT(init_wall_, TAG)(Semi &s) { return Ops<ND, T, CT>::init_wall(s); }                       \
     int TPB_CAT(init_structure_, TAG)(Semi &s) { return Ops<ND, T, CT>::init_structure(s); }             \
@@ -1548,7 +1605,8 @@ struct Ops {
     int TPB_CAT(kick_struct_, TAG)(Semi &s, void *dv, const void *v, const void *u, const void *dv_const) \
     {                                                                                                    \
         return Ops<ND, T, CT>::kick_structure(s, dv, v, u, dv_const);                                    \
-    }
+    }                                                                                                    \
+    int TPB_CAT(sort_system_, TAG)(Semi &s, void *v, void *u) { return Ops<ND, T, CT>::sort_system(s, v, u); }
 TPB_DECLARE_ENTRIES(2ff)
 TPB_DECLARE_ENTRIES(3ff)
 TPB_DECLARE_ENTRIES(2fd)
@@ -1600,6 +1658,8 @@ static int dispatch_kick_struct(Semi &s, void *dv, const void *v, const void *u,
     DISPATCH(s, kick_struct_, s, dv, v, u, c);
 }
 
+static int dispatch_sort_system(Semi &s, void *v, void *u) { DISPATCH(s, sort_system_, s, v, u); }
+
 static void free_device(Semi &s)
 {
     void *ptrs[] = {s.d_mass_f, s.d_u, s.d_v, s.d_dv, s.d_du, s.d_key, s.d_slot, s.d_tmp_perm,
@@ -1608,7 +1668,7 @@ static void free_device(Semi &s)
                     s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_Vw, s.d_Pw, s.d_perm_w,
                     s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2, s.d_adapt, s.d_x0_s, s.d_xcur_s, s.d_mass_s, s.d_rho_s, s.d_hydro_s,
                     s.d_L_s, s.d_F_s, s.d_pk1_s, s.d_As, s.d_Bs, s.d_nbr_start, s.d_nbr, s.d_scell_start, s.d_sperm,
-                    s.d_Ps, s.d_p_s, s.d_rhoh_s, s.d_xcl_s, s.d_vcl_s, s.d_acl_s};
+                    s.d_Ps, s.d_p_s, s.d_rhoh_s, s.d_xcl_s, s.d_vcl_s, s.d_acl_s, s.d_sort_u, s.d_sort_v};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     tiles_free(s.tiles);
@@ -2028,6 +2088,7 @@ int32_t tpb_semidiscretize(tpb_semi_t semi, const void *u0_ode)
     CUDA_TRY(s, cudaMalloc(&s->d_wcell_start, sizeof(int) * (size_t)(s->ncells + 4)));
     CUDA_TRY(s, cudaMemset(s->d_wcell_start, 0, sizeof(int) * (size_t)(s->ncells + 4)));
     CUDA_TRY(s, cudaMalloc(&s->d_block_sums, sizeof(int) * (size_t)SCAN_TILE));
+    if (const char *e = getenv("TPB_SUBKEY")) s->subkey_mode = atoi(e);  // tuning: order inside a cell (tpb_nhs.cuh)
     {
         // k_scan_cells_tiles: whole cell rows per block
         const int n0 = s->ncell[0], nrows = s->ncell[1] * s->ncell[2];
@@ -2245,6 +2306,18 @@ int32_t tpb_set_integrate_structure(tpb_semi_t semi, int32_t enabled)
     if (s->struct_index < 0) return fail(s, TPB_ERR_STATE, "no structure system");
     s->integrate_structure = enabled ? 1 : 0;
     return TPB_OK;
+}
+
+int32_t tpb_sort_system(tpb_semi_t semi, int32_t system, void *v_ode, void *u_ode)
+{
+    Semi *s = (Semi *)semi;
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    if (!s->ready) return fail(s, TPB_ERR_STATE, "tpb_sort_system before tpb_semidiscretize");
+    if (system < 0 || system >= s->n_systems) return fail(s, TPB_ERR_INVALID_ARGUMENT, "system index out of range");
+    if (system != s->fluid_index) return TPB_OK;  // sort_particles!(system, v, u, semi) = system for everything else
+    if (s->n_f > 0 && (!v_ode || !u_ode)) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null ODE vector");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    return dispatch_sort_system(*s, v_ode, u_ode);
 }
 
 int32_t tpb_set_clamped_motion(tpb_semi_t semi, const void *coords, const void *velocity, const void *acceleration,

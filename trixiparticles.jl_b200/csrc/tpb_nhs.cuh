@@ -18,11 +18,49 @@
 namespace tpb {
 
 // ------------------------------------------------------------------ cell keys + histogram
+// Order of the particles INSIDE a cell.  Consecutive sorted particles are consecutive lanes of the tile sweeps,
+// and lanes whose targets sit next to each other accept nearly the same candidates: their shared-memory reads
+// fall into the same 128-byte lines (the sweeps are bound by that pipe).  By previous index alone the order inside
+// a cell is whatever the ODE vectors happen to hold -- lattice order at t = 0, arbitrary once the fluid has
+// mixed.  So the entries of tmp_perm carry a 6-bit position key above the particle index,
+//   entry = sub << pbits | i,   sub = the particle's place among 4 x 4 x 4 sub-boxes of its cell,
+// and rank_in_cell orders by (sub, i): still a total order independent of the atomics' arrival order.
+// pbits = PERM_IDX_BITS when the set has fewer than 2^25 particles, else 31 (no position key).
+// Measured at 1 M particles (interact! phase; profiles/r2_y_order_inside_cells.txt): lattice order in the ODE vectors
+// 0.853 ms with or without the key; a random order 0.887 ms without, 0.854 ms with it.  Sub-boxes in lexicographic
+// order with the row axis fastest are the best of those tried: the row axis slowest 0.860, Morton order 0.884 (no
+// better than random), 8 x 8 x 1 boxes 0.871, 2 x 2 x 16 0.880, 4 x 2 x 8 0.884, 3 x 3 x 7 0.855.
+// TPB_SUBKEY=0 switches the key off.
+constexpr int SLOT_BITS = 24;       // arrival number inside a cell: low 24 bits of slot[i]
+constexpr int PERM_IDX_BITS = 25;
+__host__ __device__ __forceinline__ int perm_index(int entry, int pbits) { return entry & (int)((1u << pbits) - 1u); }
+
+template <int ND, typename CT>
+__device__ __forceinline__ int cell_subkey(const GridConst<CT> &g, CT x, CT y, CT z, int cx, int cy, int cz, int mode)
+{
+    if (g.ax == 1) {
+        const CT t = x;
+        x = y;
+        y = t;
+    } else if (ND == 3 && g.ax == 2) {
+        const CT t = x;
+        x = z;
+        z = t;
+    }
+    const float fx = (float)((x - g.origin[0]) * g.inv_cell_x - (CT)cx);
+    const float fy = (float)((y - g.origin[1]) * g.inv_cell - (CT)cy);
+    const float fz = ND == 3 ? (float)((z - g.origin[2]) * g.inv_cell - (CT)cz) : 0.f;
+    const int sx = min(max((int)(fx * 4.f), 0), 3), sy = min(max((int)(fy * 4.f), 0), 3);
+    const int sz = min(max((int)(fz * 4.f), 0), 3);
+    (void)mode;
+    return (sz * 4 + sy) * 4 + sx;  // lexicographic, the row axis fastest
+}
+
 template <int ND, typename CT>
 __global__ void __launch_bounds__(256)
 k_cell_count(const CT *__restrict__ coords /* ND x n, AoS */, int n, int n_targets, GridConst<CT> g,
              int *__restrict__ key, int *__restrict__ slot, int *__restrict__ count,
-             int *__restrict__ flags)
+             int *__restrict__ flags, int sub_mode = 0)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -38,7 +76,8 @@ k_cell_count(const CT *__restrict__ coords /* ND x n, AoS */, int n, int n_targe
     if (!cell_coords<ND, CT>(g, x, y, z, cx, cy, cz)) atomicOr(flags, 1);
     int c = cell_linear(g, cx, cy, cz);
     key[i] = c;
-    slot[i] = atomicAdd(&count[c], 1);
+    const int sub = sub_mode ? cell_subkey<ND, CT>(g, x, y, z, cx, cy, cz, sub_mode) : 0;
+    slot[i] = atomicAdd(&count[c], 1) | (sub << SLOT_BITS);
 }
 
 // ------------------------------------------------------------------ exclusive scan (int32)
@@ -142,20 +181,44 @@ k_scan_final(const int *__restrict__ in, int n, const int *__restrict__ block_of
 // ------------------------------------------------------------------ scatter of indices
 static __global__ void __launch_bounds__(256)
 k_scatter(const int *__restrict__ key, const int *__restrict__ slot,
-          const int *__restrict__ cell_start, int n, int *__restrict__ tmp_perm)
+          const int *__restrict__ cell_start, int n, int *__restrict__ tmp_perm, int pbits = 31)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (key[i] < 0) return;  // empty slab-ghost slot
-    tmp_perm[cell_start[key[i]] + slot[i]] = i;
+    const int sl = slot[i];
+    tmp_perm[cell_start[key[i]] + (sl & ((1 << SLOT_BITS) - 1))] = pbits < 31 ? ((sl >> SLOT_BITS) << pbits) | i : i;
 }
 
-// rank of particle index i among the indices of its cell [a, b) in tmp_perm
+// rank of the entry i (position key, particle index) among the entries of its cell [a, b) in tmp_perm
 __device__ __forceinline__ int rank_in_cell(const int *__restrict__ tmp_perm, int a, int b, int i)
 {
     int r = 0;
     for (int t = a; t < b; ++t) r += tmp_perm[t] < i;
     return r;
+}
+
+// ------------------------------------------------------------------ SortingCallback
+// sort_system! (callbacks/sorting.jl:146-157): the rows of the caller's ODE vectors (and the masses, which the
+// reference leaves as a TODO for non-uniform particles) in cell order; inside a cell by previous index, so the
+// summation order of every later kick is unchanged.
+template <int ND, typename T, typename CT>
+__global__ void __launch_bounds__(256)
+k_sort_gather(const CT *__restrict__ u, const T *__restrict__ v, const T *__restrict__ mass,
+              const int *__restrict__ key, const int *__restrict__ cell_start, const int *__restrict__ tmp_perm,
+              int n, int nv, CT *__restrict__ out_u, T *__restrict__ out_v, T *__restrict__ out_m, int pbits = 31)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int e = tmp_perm[s];
+    const int i = perm_index(e, pbits);
+    const int c = key[i];
+    const int a = cell_start[c], b = cell_start[c + 1];
+    const int dst = a + rank_in_cell(tmp_perm, a, b, e);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) out_u[(int64_t)dst * ND + d] = u[(int64_t)i * ND + d];
+    for (int q = 0; q < nv; ++q) out_v[(int64_t)dst * nv + q] = v[(int64_t)i * nv + q];
+    out_m[dst] = mass[i];
 }
 
 // ------------------------------------------------------------------ fluid reorder + EOS
@@ -169,18 +232,19 @@ k_reorder_fluid(const CT *__restrict__ u, const T *__restrict__ v, const T *__re
                 const int *__restrict__ tmp_perm, int n, const int *__restrict__ n_sorted,
                 int deterministic, EosConst<T> eos, V4<CT> *__restrict__ A, V4<T> *__restrict__ B,
                 T *__restrict__ P, int *__restrict__ perm, FilterRef<CT> fref, V4<float> *__restrict__ F,
-                const AdaptConsts<T> *__restrict__ ad = nullptr)
+                const AdaptConsts<T> *__restrict__ ad = nullptr, int pbits = 31)
 {
     constexpr int NV = DENS == 0 ? ND + 1 : ND;
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n || s >= *n_sorted) return;  // n_sorted < n when ghost slots are empty
     if (ad) eos.B = ad->B_f;  // StateEquationAdaptiveCole: this kick's speed of sound (k_adaptive_consts)
-    int i = tmp_perm[s];
+    const int e = tmp_perm[s];
+    const int i = perm_index(e, pbits);
     int dst = s;
     if (deterministic) {
         int c = key[i];
         int a = cell_start[c], b = cell_start[c + 1];
-        dst = a + rank_in_cell(tmp_perm, a, b, i);
+        dst = a + rank_in_cell(tmp_perm, a, b, e);
     }
     V4<CT> ra;
     ra.x = u[(int64_t)i * ND + 0];
@@ -211,14 +275,15 @@ k_reorder_wall(const CT *__restrict__ coords, const T *__restrict__ mass,
                const T *__restrict__ density0, const int *__restrict__ key,
                const int *__restrict__ cell_start, const int *__restrict__ tmp_perm, int n,
                V4<CT> *__restrict__ A, V2<T> *__restrict__ W, int *__restrict__ perm, FilterRef<CT> fref,
-               V4<float> *__restrict__ F)
+               V4<float> *__restrict__ F, int pbits = 31)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    int i = tmp_perm[s];
+    const int e = tmp_perm[s];
+    const int i = perm_index(e, pbits);
     int c = key[i];
     int a = cell_start[c], b = cell_start[c + 1];
-    int dst = a + rank_in_cell(tmp_perm, a, b, i);
+    int dst = a + rank_in_cell(tmp_perm, a, b, e);
     V4<CT> ra;
     ra.x = coords[(int64_t)i * ND + 0];
     ra.y = coords[(int64_t)i * ND + 1];

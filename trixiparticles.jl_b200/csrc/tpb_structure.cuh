@@ -90,14 +90,16 @@ __global__ void __launch_bounds__(256)
 k_reorder_struct(const CT *__restrict__ x_cur, const T *__restrict__ v_s, const T *__restrict__ hydro_mass,
                  const int *__restrict__ key, const int *__restrict__ cell_start,
                  const int *__restrict__ tmp_perm, int n, int n_int, T mk_vol, V4<CT> *__restrict__ A,
-                 V4<T> *__restrict__ B, int *__restrict__ sperm = nullptr, const T *__restrict__ v_clamped = nullptr)
+                 V4<T> *__restrict__ B, int *__restrict__ sperm = nullptr, const T *__restrict__ v_clamped = nullptr,
+                 int pbits = 31)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const int i = tmp_perm[s];
+    const int e = tmp_perm[s];
+    const int i = perm_index(e, pbits);
     const int c = key[i];
     const int a = cell_start[c], b = cell_start[c + 1];
-    const int dst = a + rank_in_cell(tmp_perm, a, b, i);
+    const int dst = a + rank_in_cell(tmp_perm, a, b, e);
     V4<CT> ra;
     ra.x = x_cur[(int64_t)i * ND + 0];
     ra.y = x_cur[(int64_t)i * ND + 1];

@@ -1409,12 +1409,16 @@ k_post_scan(int nb_scatter, int nb_ranges, const int *__restrict__ key, const in
             const int *__restrict__ fcell_start, int n, int *__restrict__ tmp_perm, GridConst<CT> g,
             const int *__restrict__ n_ftiles, const int4 *__restrict__ fdesc,
             const int *__restrict__ wcell_start, int2 *__restrict__ frng, int4 *__restrict__ fext,
-            WallPrepArgs<T, CT> wp)
+            WallPrepArgs<T, CT> wp, int pbits = 31)
 {
     int vb = blockIdx.x;
     if (vb < nb_scatter) {
         const int i = vb * blockDim.x + threadIdx.x;
-        if (i < n && key[i] >= 0) tmp_perm[fcell_start[key[i]] + slot[i]] = i;
+        if (i < n && key[i] >= 0) {
+            const int sl = slot[i];  // arrival number | position key << SLOT_BITS (k_cell_count)
+            tmp_perm[fcell_start[key[i]] + (sl & ((1 << SLOT_BITS) - 1))] =
+                pbits < 31 ? ((sl >> SLOT_BITS) << pbits) | i : i;
+        }
         return;
     }
     vb -= nb_scatter;

@@ -439,6 +439,17 @@ class Semidiscretization:
         else:
             _lib.check(self._handle, L.tpb_set_clamped_motion(self._handle, None, None, None, 0))
 
+    def sort_particles(self, v_ode, u_ode):
+        """`sort_particles!` of every fluid system (callbacks/sorting.jl:123-157): the rows of (v_ode, u_ode) in
+        place in grid-cell order (tpb_sort_system); later kicks give bit-identical results, row for row."""
+        nu, nv = self.ranges_u[-1][1], self.ranges_v[-1][1]
+        pv = self._ptr(v_ode, nv, self.eltype, "v_ode")
+        pu = self._ptr(u_ode, nu, self.coordinates_eltype, "u_ode")
+        self._bind_stream()
+        for s in self.systems:
+            if isinstance(s, WeaklyCompressibleSPHSystem):
+                _lib.check(self._handle, _lib.load().tpb_sort_system(self._handle, self.system_index(s), pv, pu))
+
     def set_integrate_structure(self, enabled: bool):
         """`semi.integrate_tlsph[] = enabled` (semidiscretization.jl:149): with a SplitIntegrationCallback kick! /
         drift! leave the structure's rows zero."""

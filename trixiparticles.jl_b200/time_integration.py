@@ -251,6 +251,43 @@ def max_x_coord(system, v_ode, u_ode, semi, t) -> float:
     return out.value
 
 
+class SortingCallback:
+    """callbacks/sorting.jl:9-57: `SortingCallback(; interval=-1, dt=0.0, initial_sort=true)` -- reorders the fluid
+    particles in the ODE vectors by neighbourhood-search cell, every `interval` steps or at the first step after
+    each `dt` of simulation time.  The reference needs it against a 3-4x slowdown of its per-particle kernels on
+    shuffled particles; here the library sorts its own records at every kick and only the gather / scatter between
+    the ODE vectors and those records profits (5-9 % for a random order)."""
+
+    def __init__(self, *, interval: int = -1, dt: float = 0.0, initial_sort: bool = True):
+        if dt > 0 and interval > 0:
+            raise ValueError("setting both `interval` and `dt` is not supported")
+        if not dt > 0 and interval <= 0:
+            raise ValueError("either `interval` or `dt` must be set to a positive value")
+        self.interval = float(dt) if dt > 0 else int(interval)
+        self.initial_sort = bool(initial_sort)
+        self.last_t = 0.0
+        self.n_sorts = 0
+
+    def initialize(self, semi, v, u, t) -> bool:
+        self.last_t = float(t)
+        if self.initial_sort:
+            self._sort(semi, v, u, t)
+        return self.initial_sort
+
+    def _sort(self, semi, v, u, t):
+        semi.sort_particles(v, u)
+        self.last_t = float(t)
+        self.n_sorts += 1
+
+    def __call__(self, semi, v, u, t, nsteps) -> bool:
+        """condition + affect! (sorting.jl:76-112); True when the vectors were reordered (the integrator then has a
+        derivative discontinuity: FSAL right-hand sides are stale)."""
+        due = (nsteps % self.interval == 0) if isinstance(self.interval, int) else (t - self.last_t >= self.interval)
+        if due:
+            self._sort(semi, v, u, t)
+        return bool(due)
+
+
 class PostprocessCallback:
     """Records `name -> f(system, v_ode, u_ode, semi, t)` for the fluid system every `dt`."""
 
@@ -388,6 +425,7 @@ def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
     stepsize = next((c for c in callbacks if isinstance(c, StepsizeCallback)), None)
     posts = [c for c in callbacks if isinstance(c, PostprocessCallback)]
     split = next((c for c in callbacks if isinstance(c, SplitIntegrationCallback)), None)
+    sorting = next((c for c in callbacks if isinstance(c, SortingCallback)), None)   # (fluid rows only, sorting.jl:5)
     if split is not None:
         split.initialize(semi, ode.v0, ode.u0, ode.tspan[0])   # (also: the StepsizeCallback skips the structure)
         cuda_graph = False                                      # the number of sub-steps varies from stage to stage
@@ -405,6 +443,8 @@ def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
     dv, du = ops.zeros_like(v), ops.zeros_like(u)
     tmp_v, tmp_u = ops.zeros_like(v), ops.zeros_like(u)
     t, t_end = float(ode.tspan[0]), float(ode.tspan[1])
+    if sorting is not None:
+        sorting.initialize(semi, v, u, t)
     next_stop = [t + p.dt for p in posts]
     for p in posts:
         p(t, v, u, semi)
@@ -449,6 +489,8 @@ def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
         nsteps += 1
         if split is not None:
             split.integrate_to(v, u, t)                    # the callback's affect! at the end of every step
+        if sorting is not None:
+            sorting(semi, v, u, t, nsteps)                 # in place: a captured graph keeps replaying on the same vectors
         if stepsize is not None and adaptive_eos:
             # StateEquationAdaptiveCole: the StepsizeCallback sees the speed of sound of the last
             # right-hand-side evaluation (stepsize.jl:63-79, fluid.jl:199-239)
@@ -481,10 +523,13 @@ def _solve_rdpk3(ode, alg: RDPK3SpFSAL35, callbacks, *, dt, abstol, reltol, dtma
     semi = ode.p.semi
     ops = _VecOps(semi)
     posts = [c for c in callbacks if isinstance(c, PostprocessCallback)]
+    sorting = next((c for c in callbacks if isinstance(c, SortingCallback)), None)
     t, t_end = float(ode.tspan[0]), float(ode.tspan[1])
     dtmax = float(dtmax) if dtmax is not None else t_end - t
     v = ode.v0.clone() if ops.device else ode.v0.copy()
     u = ode.u0.clone() if ops.device else ode.u0.copy()
+    if sorting is not None:
+        sorting.initialize(semi, v, u, t)
     Z = ops.zeros_like
     kv, ku, k0v, k0u = Z(v), Z(u), Z(v), Z(u)           # stage rhs / FSAL rhs
     tv, tu, pv, pu, ev, eu = Z(v), Z(u), Z(v), Z(u), Z(v), Z(u)   # tmp register, uprev, error estimate
@@ -568,6 +613,9 @@ def _solve_rdpk3(ode, alg: RDPK3SpFSAL35, callbacks, *, dt, abstol, reltol, dtma
                 dts.append(step)
             if step == dt:                       # a step shortened for an output time keeps the controller's dt
                 dt = min(dt * factor, dtmax)
+            if sorting is not None and sorting(semi, v, u, t, nsteps):
+                _rhs(ode, k0v, k0u, v, u, t)     # derivative_discontinuity!(integrator, true): the FSAL value is stale
+                nf += 1
             for i, p in enumerate(posts):
                 if t >= next_stop[i] - 1e-12 * max(1.0, abs(t)):
                     p(t, v, u, semi)
@@ -602,6 +650,9 @@ def _solve_verlet(ode, callbacks, *, dt, maxiters, save_everystep):
     Z = ops.zeros_like
     pv, pu, kdu, ku = Z(v), Z(u), Z(v), Z(u)
     t, t_end = float(ode.tspan[0]), float(ode.tspan[1])
+    sorting = next((c for c in callbacks if isinstance(c, SortingCallback)), None)
+    if sorting is not None:
+        sorting.initialize(semi, v, u, t)
     next_stop = [t + p.dt for p in posts]
     for p in posts:
         p(t, v, u, semi)
@@ -624,6 +675,8 @@ def _solve_verlet(ode, callbacks, *, dt, maxiters, save_everystep):
         nf += 2
         t = stop if step != dt else t + step
         nsteps += 1
+        if sorting is not None:
+            sorting(semi, v, u, t, nsteps)                 # (no state but v, u survives a step)
         if save_everystep:
             dts.append(step)
         for i, p in enumerate(posts):
