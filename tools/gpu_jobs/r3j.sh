@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 out=gpurun_out/r3j_subkey.txt; : > $out
-for sk in 1 4 5 6 7; do
-for sh in "--shuffle --sort"; do
+for sk in 1 2 1 2; do
+for sh in "" "--shuffle --sort"; do
   echo "== TPB_SUBKEY=$sk dam_break_3d_1m $sh" >> $out
   TPB_SUBKEY=$sk timeout 300 python bench.py --quick --workload dam_break_3d_1m --steps 30 --warmup 5 $sh 2>/dev/null | python -c "
 import sys, json

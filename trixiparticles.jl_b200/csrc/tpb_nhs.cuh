@@ -29,7 +29,7 @@ namespace tpb {
 // Measured at 1 M particles (interact! phase; profiles/r2_y_order_inside_cells.txt): lattice order in the ODE vectors
 // 0.853 ms with or without the key; a random order 0.887 ms without, 0.854 ms with it.  Sub-boxes in lexicographic
 // order with the row axis fastest are the best of those tried: the row axis slowest 0.860, Morton order 0.884 (no
-// better than random), 8 x 8 x 1 boxes 0.871, 2 x 2 x 16 0.880, 4 x 2 x 8 0.884, 3 x 3 x 7 0.855.
+// better than random), serpentine 0.867, 8 x 8 x 1 boxes 0.871, 2 x 2 x 16 0.880, 4 x 2 x 8 0.884, 3 x 3 x 7 0.855.
 // TPB_SUBKEY=0 switches the key off.
 constexpr int SLOT_BITS = 24;       // arrival number inside a cell: low 24 bits of slot[i]
 constexpr int PERM_IDX_BITS = 25;
