@@ -328,6 +328,10 @@ GridConst<CT> make_grid_const(const Semi &s)
 // ---------------------------------------------------------------------------------------
 static int exclusive_scan(Semi &s, const int *d_in, int n, int *d_out)
 {
+    if (n <= SCAN_SINGLE_MAX) {
+        LAUNCH(s, k_scan_single, 1, SCAN_THREADS, 0, d_in, n, d_out);
+        return TPB_OK;
+    }
     int nblocks = cdiv(n, SCAN_TILE);
     if (nblocks > SCAN_TILE) return fail(&s, TPB_ERR_UNSUPPORTED, "cell grid too large for the scan");
     LAUNCH(s, k_scan_block_sums, nblocks, SCAN_THREADS, 0, d_in, n, s.d_block_sums);
@@ -348,7 +352,8 @@ struct Ops {
     // bits of a tmp_perm entry that hold the particle index (the position key sits above them)
     static int perm_bits(const Semi &s, int64_t n) { return s.subkey_mode && n < (1 << PERM_IDX_BITS) ? PERM_IDX_BITS : 31; }
 
-    static int bin_points(Semi &s, const CT *d_coords, int n, int n_targets, int *d_cell_start)
+    static int bin_points(Semi &s, const CT *d_coords, int n, int n_targets, int *d_cell_start,
+                          const CT *d_tail_coords = nullptr, int n_head = 0, CT *d_out_coords = nullptr)
     {
         GridConst<CT> g = make_grid_const<CT>(s);
         const int pb = perm_bits(s, n);
@@ -356,7 +361,7 @@ struct Ops {
         s.count_clean = false;
         if (n > 0)
             LAUNCH(s, (k_cell_count<ND, CT>), cdiv(n, 256), 256, 0, d_coords, n, n_targets, g, s.d_key,
-                   s.d_slot, s.d_count, s.d_flags, pb < 31 ? s.subkey_mode : 0);
+                   s.d_slot, s.d_count, s.d_flags, pb < 31 ? s.subkey_mode : 0, d_tail_coords, n_head, d_out_coords);
         int rc = exclusive_scan(s, s.d_count, (int)s.ncells, d_cell_start);
         if (rc) return rc;
         if (n > 0)
@@ -652,10 +657,13 @@ struct Ops {
     {
         const int n = (int)s.n_s, n_int = (int)s.n_s_int;
         if (n == 0) return TPB_OK;
-        LAUNCH(s, (k_struct_positions<ND, CT>), cdiv((int64_t)n * ND, 256), 256, 0, n, n_int, d_u_s,
-               (const CT *)s.d_xcl_s, (CT *)s.d_xcur_s);
+        if (s.sp.boundary_model == TPB_BOUNDARY_NONE)
+            LAUNCH(s, (k_struct_positions<ND, CT>), cdiv((int64_t)n * ND, 256), 256, 0, n, n_int, d_u_s,
+                   (const CT *)s.d_xcl_s, (CT *)s.d_xcur_s);
         if (s.sp.boundary_model != TPB_BOUNDARY_NONE) {
-            int rc = bin_points(s, (const CT *)s.d_xcur_s, n, n, s.d_scell_start);
+            // current coordinates (integrated particles from u_ode, clamped ones from d_xcl_s) written by the
+            // cell count itself
+            int rc = bin_points(s, d_u_s, n, n, s.d_scell_start, (const CT *)s.d_xcl_s, n_int, (CT *)s.d_xcur_s);
             if (rc) return rc;
             if (s.sp.boundary_model == TPB_BOUNDARY_DUMMY_PARTICLES) {
                 // dummy particles: sorted records first, then the Adami pass over the fluid's sorted records
@@ -1319,13 +1327,12 @@ struct Ops {
         s.launches_this_call = 0;
         if (total_f + total_s == 0) return TPB_OK;
         auto launch = [&](const T *v_base, CT *du_base) {
-            if (total_f > 0)
-                LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total_f, 256), 256, 0, total_f, nv(s), v_base + lay.off_v_f,
-                       du_base + lay.off_u_f);
-            if (total_s > 0 && s.integrate_structure)  // structure: v holds ND entries per integrated particle, du = v
-                LAUNCH(s, (k_drift<ND, T, CT>), cdiv(total_s, 256), 256, 0, total_s, ND, v_base + lay.off_v_s,
-                       du_base + lay.off_u_s);
-            else if (total_s > 0)  // set_velocity!(..., ::TotalLagrangianSPHSystem) without integrate_tlsph: du = 0
+            // fluid and (integrated) structure in one launch; structure: v holds ND entries per particle, du = v
+            const int64_t n_s = s.integrate_structure ? total_s : 0;
+            if (total_f + n_s > 0)
+                LAUNCH(s, (k_drift2<ND, T, CT>), cdiv(total_f + n_s, 256), 256, 0, total_f, nv(s), v_base + lay.off_v_f,
+                       du_base + lay.off_u_f, n_s, v_base + lay.off_v_s, du_base + lay.off_u_s);
+            if (total_s > 0 && !s.integrate_structure)  // set_velocity! without integrate_tlsph: du = 0
                 cudaMemsetAsync(du_base + lay.off_u_s, 0, sizeof(CT) * (size_t)total_s, s.stream);
         };
         if (s.cfg.ode_memory == TPB_MEM_HOST) {

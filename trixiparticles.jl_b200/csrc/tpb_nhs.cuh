@@ -60,18 +60,27 @@ template <int ND, typename CT>
 __global__ void __launch_bounds__(256)
 k_cell_count(const CT *__restrict__ coords /* ND x n, AoS */, int n, int n_targets, GridConst<CT> g,
              int *__restrict__ key, int *__restrict__ slot, int *__restrict__ count,
-             int *__restrict__ flags, int sub_mode = 0)
+             int *__restrict__ flags, int sub_mode = 0, const CT *__restrict__ tail_coords = nullptr,
+             int n_head = 0, CT *__restrict__ out_coords = nullptr)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    CT x = coords[(int64_t)i * ND + 0];
+    // structure: the integrated particles come from u_ode, the clamped tail from where it was put
+    // (update_positions!, total_lagrangian_sph/system.jl:403-433); the merged coordinates are kept
+    const CT *src = tail_coords != nullptr && i >= n_head ? tail_coords : coords;
+    CT x = src[(int64_t)i * ND + 0];
     if (i >= n_targets && !(x == x)) {  // empty slab-ghost slot (NaN x): not binned, not an error
         key[i] = -1;
         slot[i] = 0;
         return;
     }
-    CT y = coords[(int64_t)i * ND + 1];
-    CT z = ND == 3 ? coords[(int64_t)i * ND + 2] : (CT)0;
+    CT y = src[(int64_t)i * ND + 1];
+    CT z = ND == 3 ? src[(int64_t)i * ND + 2] : (CT)0;
+    if (out_coords != nullptr) {
+        out_coords[(int64_t)i * ND + 0] = x;
+        out_coords[(int64_t)i * ND + 1] = y;
+        if (ND == 3) out_coords[(int64_t)i * ND + 2] = z;
+    }
     int cx, cy, cz;
     if (!cell_coords<ND, CT>(g, x, y, z, cx, cy, cz)) atomicOr(flags, 1);
     int c = cell_linear(g, cx, cy, cz);
@@ -176,6 +185,35 @@ k_scan_final(const int *__restrict__ in, int n, const int *__restrict__ block_of
         run += v[k];
         if (base + k == n - 1) out[n] = run;
     }
+}
+
+// small grids (up to SCAN_SINGLE_MAX cells: 2-D set-ups, the structure of an FSI case): one block walks the
+// histogram tile by tile with a running carry -- one launch instead of three, which is what such a step consists of
+constexpr int SCAN_SINGLE_MAX = 2 * SCAN_TILE;
+static __global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_single(const int *__restrict__ in, int n, int *__restrict__ out)
+{
+    int carry = 0;
+    for (int tile = 0; tile < n; tile += SCAN_TILE) {
+        const int base = tile + (int)threadIdx.x * SCAN_ITEMS;
+        int v[SCAN_ITEMS];
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            v[k] = base + k < n ? in[base + k] : 0;
+            s += v[k];
+        }
+        int total;
+        const int inc = block_inclusive_scan(s, total);
+        int run = carry + inc - s;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (base + k < n) out[base + k] = run;
+            run += v[k];
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0) out[n] = carry;
 }
 
 // ------------------------------------------------------------------ scatter of indices

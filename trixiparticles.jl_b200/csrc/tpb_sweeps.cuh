@@ -446,6 +446,22 @@ k_drift(int64_t n_total /* n_f * ND */, int nv, const T *__restrict__ v, CT *__r
     du[q] = (CT)v[a * nv + d];
 }
 
+// drift! of two systems in one launch: the fluid (nv entries per particle in v) and the structure (ND entries)
+template <int ND, typename T, typename CT>
+__global__ void __launch_bounds__(256)
+k_drift2(int64_t n_f /* n_fluid * ND */, int nv, const T *__restrict__ v_f, CT *__restrict__ du_f,
+         int64_t n_s /* n_integrated * ND */, const T *__restrict__ v_s, CT *__restrict__ du_s)
+{
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_f) {
+        const int64_t a = q / ND;
+        const int d = (int)(q - a * ND);
+        du_f[q] = (CT)v_f[a * nv + d];
+    } else if (q - n_f < n_s) {
+        du_s[q - n_f] = (CT)v_s[q - n_f];
+    }
+}
+
 // test hook behind tpb_vec_div_fast: out[i] = div_fast(x, y[i]) (test/examples/gpu.jl:30-78)
 template <typename T>
 __global__ void __launch_bounds__(256)
