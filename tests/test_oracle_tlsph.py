@@ -172,3 +172,75 @@ def test_dummy_particle_structure_conserves_momentum_with_the_fluid():
     still = adapter.kick_fsi(fluid, None, st, u_ode, np.concatenate([v_f.reshape(-1), 0 * v_s.reshape(-1)]))
     drho = out["dv"][: v_f.size].reshape(v_f.shape)[:, 2]
     assert np.abs(drho - still["dv"][: v_f.size].reshape(v_f.shape)[:, 2]).max() > 0
+
+
+# ---------------------------------------------------------------------------------------------- three dimensions
+def _rot3(ax, ay, az):
+    cx, sx, cy, sy, cz, sz = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay), np.cos(az), np.sin(az)
+    rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return rz @ ry @ rx
+
+
+def _grid_3d(n=7, dx=0.1):
+    r = np.arange(1, n + 1) * dx
+    return np.array([[x, y, z] for z in r for y in r for x in r])
+
+
+@pytest.mark.parametrize("name,J", [("rotation", _rot3(0.3, -0.2, 0.5)), ("stretch", np.diag([2.0, 3.0, 0.5])),
+                                    ("rotation * stretch", _rot3(0.1, 0.7, -0.4) @ np.diag([1.5, 0.8, 1.2]))])
+def test_deformation_gradient_and_stress_3d(name, J):
+    """The 3-D counterpart of test/systems/tlsph_system.jl:194-303 (the reference tests these in 2-D only): on a
+    7^3 grid the corrected gradient reproduces an affine deformation exactly, F = J in the interior, and
+    PK1 = F (lambda tr(E) I + 2 mu E) with E = (F^T F - I) / 2; a rigid rotation is stress free."""
+    x0 = _grid_3d()
+    n = len(x0)
+    mass, rho = np.full(n, 1.0), np.full(n, 1000.0)
+    sp = params(0.12, E=2.5, nu=0.25)     # lambda = mu = 1
+    sp.ndims = 3
+    L = O.tlsph_correction_matrix(sp, x0, mass, rho, np.float64)
+    cur = x0 @ J.T
+    F, P = O.tlsph_update(sp, x0, cur, mass, rho, L, np.float64)
+    mid = n // 2
+    assert np.allclose(F[mid].T, J, atol=1e-12)
+    E = 0.5 * (J.T @ J - np.eye(3))
+    pk1 = J @ (np.trace(E) * np.eye(3) + 2 * E)
+    got = 1000.0 ** 2 * P[mid].T @ np.linalg.inv(L[mid].T)
+    assert np.allclose(got, pk1, atol=1e-9)
+    if name == "rotation":
+        dv = O.tlsph_interact(sp, n, x0, cur, mass, rho, F, P, np.float64)
+        assert np.abs(dv).max() <= 1e-9          # no stress, no penalty force: hourglass-free rigid motion
+
+
+def test_fsi_3d_momentum_balance():
+    """3-D plate next to the water column (examples.dam_break_plate_3d): with gravity switched off the forces between
+    the fluid and the plate's dummy particles are equal and opposite -- sum m_a dv_a over the fluid's share of the
+    coupling + sum m_s dv_s over the plate's vanishes (the Adami coupling uses the same pair term on both sides,
+    structure.jl:20-102)."""
+    from trixiparticles.jl_b200 import examples
+    from oracle import adapter
+    import trixiparticles.jl_b200 as tp
+    fluid, wall, st0, _ = examples.dam_break_plate_3d(0.03, structure_boundary_model="dummy_particles",
+                                                      plate_position=(0.19, 0.0, 0.0075))
+    # every plate particle integrated, so that the whole reaction shows up in dv_s
+    st = tp.TotalLagrangianSPHSystem(st0.initial_condition, smoothing_kernel=st0.smoothing_kernel,
+                                     smoothing_length=st0.smoothing_length, young_modulus=st0.young_modulus,
+                                     poisson_ratio=st0.poisson_ratio, boundary_model=st0.boundary_model,
+                                     acceleration=st0.acceleration, penalty_force=st0.penalty_force)
+    n_f, n_int = fluid.nparticles, st.n_integrated_particles
+    assert n_int == st.nparticles
+    rng = np.random.default_rng(3)
+    u_f = fluid.initial_condition.coordinates + rng.uniform(-0.002, 0.002, (n_f, 3))
+    v_f = np.concatenate([rng.uniform(-0.1, 0.1, (n_f, 3)), fluid.initial_condition.density[:, None] * 1.001], axis=1)
+    u = np.concatenate([u_f.reshape(-1), st.initial_coordinates.reshape(-1)])
+    v = np.concatenate([v_f.reshape(-1), np.zeros(3 * n_int)])
+    with_plate = adapter.kick_fsi(fluid, wall, st, u, v)["dv"]
+    # the same fluid without the plate: the difference is the plate's force on the fluid
+    no_plate = adapter.kick(fluid, wall, u_f, v_f)["dv"]
+    f_fluid = ((with_plate[: 4 * n_f].reshape(n_f, 4) - no_plate)[:, :3] * fluid.mass[:, None]).sum(axis=0)
+    # the plate at rest in its initial configuration: no stress, so dv_s = coupling + gravity
+    dv_s = with_plate[4 * n_f:].reshape(n_int, 3) - st.acceleration[None, :]
+    f_plate = (dv_s * st.mass[:, None]).sum(axis=0)
+    assert np.linalg.norm(f_fluid) > 1e-3
+    assert np.linalg.norm(f_fluid + f_plate) <= 1e-10 * np.linalg.norm(f_fluid)

@@ -74,6 +74,11 @@ def main():
                                                         initial_fluid_size=(0.15, 0.29), structure_boundary_model="dummy_particles")
     case("config 5 with BoundaryModelDummyParticles on the plate, dx=0.005", (fluid, wall, plate),
          lambda u, v, f=fluid, w=wall, p=plate: adapter.kick_fsi(f, w, p, u, v), steps_dt=(400, 1e-5))
+    for dx in (0.02, 0.01):
+        fluid, wall, plate, _ = examples.dam_break_plate_3d(dx, n_particles_x=3 if dx == 0.02 else 5, eltype=np.float32,
+                                                            coordinates_eltype=np.float32, plate_position=(0.175, 0.0, 0.0075))
+        case(f"config 5 in 3-D: dam_break_plate_3d dx={dx} (Float32, Monaghan-Kajtar coupling)", (fluid, wall, plate),
+             lambda u, v, f=fluid, w=wall, p=plate: adapter.kick_fsi(f, w, p, u, v), steps_dt=(400, 2e-5 * dx / 0.02))
     for dx in (0.05, 0.005):
         fluid, wall, _ = examples.hydrostatic_water_column_2d(dx)
         case(f"config 2: hydrostatic_water_column_2d dx={dx} (Float32)", (fluid, wall),

@@ -31,7 +31,7 @@ namespace tpb {
 // order with the row axis fastest are the best of those tried: the row axis slowest 0.860, Morton order 0.884 (no
 // better than random), serpentine 0.867, 8 x 8 x 1 boxes 0.871, 2 x 2 x 16 0.880, 4 x 2 x 8 0.884, 3 x 3 x 7 0.855.
 // TPB_SUBKEY=0 switches the key off.
-constexpr int SLOT_BITS = 24;       // arrival number inside a cell: low 24 bits of slot[i]
+constexpr int SLOT_BITS = 25;       // arrival number inside a cell (< n < 2^25 whenever a key is stored): low bits of slot[i]
 constexpr int PERM_IDX_BITS = 25;
 __host__ __device__ __forceinline__ int perm_index(int entry, int pbits) { return entry & (int)((1u << pbits) - 1u); }
 
@@ -225,7 +225,10 @@ k_scatter(const int *__restrict__ key, const int *__restrict__ slot,
     if (i >= n) return;
     if (key[i] < 0) return;  // empty slab-ghost slot
     const int sl = slot[i];
-    tmp_perm[cell_start[key[i]] + (sl & ((1 << SLOT_BITS) - 1))] = pbits < 31 ? ((sl >> SLOT_BITS) << pbits) | i : i;
+    if (pbits < 31)
+        tmp_perm[cell_start[key[i]] + (sl & ((1 << SLOT_BITS) - 1))] = ((sl >> SLOT_BITS) << pbits) | i;
+    else
+        tmp_perm[cell_start[key[i]] + sl] = i;
 }
 
 // rank of the entry i (position key, particle index) among the entries of its cell [a, b) in tmp_perm

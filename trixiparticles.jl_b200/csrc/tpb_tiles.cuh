@@ -1416,8 +1416,10 @@ k_post_scan(int nb_scatter, int nb_ranges, const int *__restrict__ key, const in
         const int i = vb * blockDim.x + threadIdx.x;
         if (i < n && key[i] >= 0) {
             const int sl = slot[i];  // arrival number | position key << SLOT_BITS (k_cell_count)
-            tmp_perm[fcell_start[key[i]] + (sl & ((1 << SLOT_BITS) - 1))] =
-                pbits < 31 ? ((sl >> SLOT_BITS) << pbits) | i : i;
+            if (pbits < 31)
+                tmp_perm[fcell_start[key[i]] + (sl & ((1 << SLOT_BITS) - 1))] = ((sl >> SLOT_BITS) << pbits) | i;
+            else
+                tmp_perm[fcell_start[key[i]] + sl] = i;
         }
         return;
     }

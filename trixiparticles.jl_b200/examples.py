@@ -245,6 +245,61 @@ def dam_break_plate_2d(fluid_particle_spacing=0.01, *, n_particles_x=5, eltype=n
     return fluid, wall, structure_system, tank
 
 
+def dam_break_plate_3d(fluid_particle_spacing=0.02, *, n_particles_x=3, eltype=np.float64, coordinates_eltype=None,
+                       initial_fluid_size=(0.16, 0.3, 0.12), plate_position=None, E=1e6, nu=0.3,
+                       structure_boundary_model="monaghan_kajtar", clamped_particles_motion=None):
+    """The set-up of examples/fsi/dam_break_plate_2d.jl extruded along z (BASELINE config 5 names "2D/3D"; the
+    reference ships the plate example in 2-D only, its 3-D FSI example is falling_sphere_3d.jl): a water column in a
+    closed tank next to an elastic plate that spans the tank's depth and is clamped along its base.  Same models as
+    the 2-D example (WendlandC2, h = 1.75 dx fluid, sqrt(2) ds structure, Monaghan-Kajtar or dummy-particle coupling,
+    PenaltyForceGanzenmueller).  Returns (fluid_system, boundary_system, structure_system, tank)."""
+    t = np.dtype(eltype).type
+    coordinates_eltype = coordinates_eltype or np.float64
+    gravity = 9.81
+    dx = fluid_particle_spacing
+    tank_size = (4 * initial_fluid_size[0], 2 * initial_fluid_size[1], initial_fluid_size[2])
+    fluid_density = 1000.0
+    sound_speed = 20 * np.sqrt(gravity * initial_fluid_size[1])
+    state_equation = StateEquationCole(sound_speed=float(t(sound_speed)), reference_density=fluid_density, exponent=1)
+    acc = (0.0, -gravity, 0.0)
+    tank = RectangularTank(dx, initial_fluid_size, tank_size, fluid_density, n_layers=3, spacing_ratio=1,
+                           acceleration=acc, state_equation=state_equation,
+                           coordinates_eltype=coordinates_eltype, eltype=eltype)
+    length_beam, thickness, structure_density = 0.12, 0.03, 2500
+    ds = thickness / (n_particles_x - 1)
+    n_y = int(np.rint(length_beam / ds)) + 1
+    n_z = int(np.rint(tank.tank_size[2] / ds))
+    if plate_position is None:
+        plate_position = (1.5 * initial_fluid_size[0], 0.0, 0.5 * (tank.tank_size[2] - (n_z - 1) * ds))
+    px, py, pz = plate_position
+    plate = RectangularShape(ds, (n_particles_x, n_y - 1, n_z), (px, py + ds, pz), density=structure_density,
+                             place_on_shell=True, coordinates_eltype=coordinates_eltype, eltype=eltype)
+    clamped = RectangularShape(ds, (n_particles_x, 1, n_z), (px, py, pz), density=structure_density,
+                               place_on_shell=True, coordinates_eltype=coordinates_eltype, eltype=eltype)
+    structure = union(clamped, plate)
+    h = 1.75 * dx
+    kernel = WendlandC2Kernel(3)
+    fluid = WeaklyCompressibleSPHSystem(
+        tank.fluid, smoothing_kernel=kernel, smoothing_length=h, density_calculator=ContinuityDensity(),
+        state_equation=state_equation, viscosity=ArtificialViscosityMonaghan(alpha=0.02, beta=0.0), acceleration=acc)
+    model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass, AdamiPressureExtrapolation(),
+                                        kernel, h, state_equation=state_equation, clip_negative_pressure=True)
+    wall = WallBoundarySystem(tank.boundary, model)
+    hyd_rho = t(fluid_density) * np.ones(structure.nparticles, dtype=eltype)
+    hyd_mass = (hyd_rho * t(ds) ** 3).astype(eltype)
+    if structure_boundary_model == "dummy_particles":
+        model_structure = BoundaryModelDummyParticles(hyd_rho, hyd_mass, AdamiPressureExtrapolation(), kernel, h,
+                                                      state_equation=state_equation)
+    else:
+        model_structure = BoundaryModelMonaghanKajtar(gravity * initial_fluid_size[1], dx / ds, ds, hyd_mass)
+    structure_system = TotalLagrangianSPHSystem(
+        structure, smoothing_kernel=WendlandC2Kernel(3), smoothing_length=np.sqrt(2) * ds, young_modulus=E,
+        poisson_ratio=nu, boundary_model=model_structure, clamped_particles=range(clamped.nparticles),
+        clamped_particles_motion=clamped_particles_motion, acceleration=acc,
+        penalty_force=PenaltyForceGanzenmueller(alpha=0.01))
+    return fluid, wall, structure_system, tank
+
+
 def hydrostatic_water_column_fsi_2d(n_particles_plate_y=3, *, eltype=np.float64, coordinates_eltype=None,
                                     initial_fluid_size=(1.0, 2.0), plate_size=(1.0, 0.05), E=67.5e9, nu=0.3,
                                     sound_speed=50.0, damping_coefficient=0.05):
