@@ -300,3 +300,41 @@ def test_fsi_3d_time_loop_plate_bends_away_from_the_column():
     assert deflection.mean() > 1e-4                      # pushed away from the column
     assert deflection.std() < 0.5 * abs(deflection.mean())   # roughly uniform along the depth
     semi.close()
+
+
+def test_oscillating_beam_2d_validation_trace():
+    """validation/oscillating_beam_2d (test/validation/validation.jl:13-29): a clamped elastic beam swinging under
+    gravity, TLSPH only -- a structure-only semidiscretization (the large-deformation counterpart of the hydrostatic
+    plate above: the tip moves by a third of the beam's length).  The reference integrates with RDPK3SpFSAL49 at
+    abstol 1e-8 / reltol 1e-6, i.e. to time-step convergence; CarpenterKennedy2N54 with dt = 2e-5 is converged as well,
+    and the deflection of the mid particle of the free end follows the reference's own trace
+    (tests/golden/oscillating_beam_2d_5_trace.json, 101 samples to t = 1)."""
+    import json
+    import os
+    from trixiparticles.jl_b200.model import PenaltyForceGanzenmueller
+    from trixiparticles.jl_b200.time_integration import CarpenterKennedy2N54, PostprocessCallback, solve
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                      "oscillating_beam_2d_5_trace.json")))
+    beam, info = examples.oscillating_beam_2d(5, penalty_force=PenaltyForceGanzenmueller(alpha=0.01))
+    semi = tp.Semidiscretization(beam, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    assert semi.ranges_u[-1][1] == 2 * beam.n_integrated_particles
+    mid, x0 = info["mid_particle"], info["start_position"]
+    pp = PostprocessCallback(0.01,
+                             deflection_x=lambda sys_, v, u, s, t: float(u[2 * mid].item()) - x0[0],
+                             deflection_y=lambda sys_, v, u, s, t: float(u[2 * mid + 1].item()) - x0[1])
+    sol = solve(ode, CarpenterKennedy2N54(), dt=2e-5, callback=(pp,), cuda_graph=True)
+    assert sol.retcode == "Success"
+    n = len(pp.times)
+    rt = np.array(ref["time"][:n])
+    assert n == 101 and np.allclose(pp.times, rt, atol=1e-9)
+    dx, dy = np.array(pp.values["deflection_x"]), np.array(pp.values["deflection_y"])
+    rx, ry = np.array(ref["deflection_x_structure_1"][:n]), np.array(ref["deflection_y_structure_1"][:n])
+    amp = np.abs(ry).max()
+    ex, ey = np.abs(dx - rx).max() / amp, np.abs(dy - ry).max() / amp
+    print(f"oscillating beam: max |deflection - reference| / amplitude: x {ex:.2e}, y {ey:.2e}; "
+          f"amplitude {amp:.4f} m; mse x {np.mean((dx - rx) ** 2):.2e}, y {np.mean((dy - ry) ** 2):.2e}")
+    assert amp > 0.1                                     # a third of the beam's length
+    assert ex <= 1e-5 and ey <= 1e-5, (ex, ey)         # measured: 1.1e-7 / 2.6e-7
+    assert np.mean((dx - rx) ** 2) <= 1e-14 and np.mean((dy - ry) ** 2) <= 1e-14   # the reference's own check: MSE ~ 0
+    semi.close()

@@ -20,7 +20,7 @@ from .semidiscretization import (B200Backend, DynamicalODEProblem, FullGridCellL
                                  GridNeighborhoodSearch, Semidiscretization, drift_, kick_,
                                  semidiscretize)
 from .interpolation import interpolate_line, interpolate_points
-from .setups import InitialCondition, RectangularShape, RectangularTank, reset_wall_, union
+from .setups import InitialCondition, RectangularShape, RectangularTank, SphereShape, reset_wall_, union
 
 __all__ = [
     "AdamiPressureExtrapolation", "ArtificialViscosityMonaghan", "BernoulliPressureExtrapolation",
@@ -35,5 +35,5 @@ __all__ = [
     "compact_support", "B200Backend",
     "DynamicalODEProblem", "FullGridCellList", "GridNeighborhoodSearch", "Semidiscretization",
     "drift_", "kick_", "semidiscretize", "InitialCondition", "RectangularShape",
-    "RectangularTank", "reset_wall_", "union", "interpolate_line", "interpolate_points",
+    "RectangularTank", "SphereShape", "reset_wall_", "union", "interpolate_line", "interpolate_points",
 ]

@@ -749,9 +749,11 @@ struct Ops {
                    s.d_fcell_start, (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.d_perm_f, s.d_scell_start,
                    (const V4<CT> *)s.d_As, (const V4<T> *)s.d_Bs, pc.kern, mk, d_dv_f, (int)s.n_tgt);
         if (n_int == 0 || !structure_side) return TPB_OK;
-        LAUNCH(s, (k_struct_from_fluid<ND, T, CT>), cdiv(n_int, 128), 128, 0, n_int, g, (const CT *)s.d_xcur_s,
-               (const T *)s.d_mass_s, s.d_fcell_start, (const V4<CT> *)s.d_A,
-               (int)(coupled && s.struct_fluid[0] && s.n_act > 0), mk, d_dv_s, s.d_flags);
+        if (coupled && s.struct_fluid[0] && s.n_act > 0)
+            LAUNCH(s, (k_struct_from_fluid<ND, T, CT>), cdiv(n_int, 128), 128, 0, n_int, g, (const CT *)s.d_xcur_s,
+                   (const T *)s.d_mass_s, s.d_fcell_start, (const V4<CT> *)s.d_A, 1, mk, d_dv_s, s.d_flags);
+        else  // nothing to feel (no boundary model, no fluid particles): the structure need not stay inside the grid
+            CUDA_TRY(&s, cudaMemsetAsync(d_dv_s, 0, sizeof(T) * ND * (size_t)n_int, s.stream));
         return mode == 2 ? TPB_OK : interact_structure_self(s, d_dv_s);
     }
 

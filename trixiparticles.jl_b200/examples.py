@@ -300,6 +300,37 @@ def dam_break_plate_3d(fluid_particle_spacing=0.02, *, n_particles_x=3, eltype=n
     return fluid, wall, structure_system, tank
 
 
+def oscillating_beam_2d(n_particles_y=5, *, eltype=np.float64, coordinates_eltype=np.float64, penalty_force=None):
+    """examples/structure/oscillating_beam_2d.jl:13-92: an elastic beam (0.35 x 0.02, E = 1.4e6, nu = 0.4) clamped in
+    a disc of fixed particles, swinging under gravity 2.0 -- a structure-only semidiscretization.  The validation run
+    (validation/oscillating_beam_2d/validation_oscillating_beam_2d.jl) adds PenaltyForceGanzenmueller(alpha=0.01) and
+    records the deflection of the particle in the middle of the free end.
+    Returns (structure_system, info) with info["mid_particle"] the 0-based index of that particle in the system."""
+    from .setups import SphereShape
+    gravity = 2.0
+    length, thickness = 0.35, 0.02
+    density, E, nu = 1000.0, 1.4e6, 0.4
+    clamp_radius = 0.05
+    ds = thickness / (n_particles_y - 1)
+    clamped = SphereShape(ds, clamp_radius + ds / 2, (0.0, thickness / 2), density, cutout_min=(0.0, 0.0),
+                          cutout_max=(clamp_radius, thickness), place_on_shell=True,
+                          coordinates_eltype=coordinates_eltype, eltype=eltype)
+    n_clamp_x = int(np.rint(clamp_radius / ds))
+    n_per_dim = (int(np.rint(length / ds)) + n_clamp_x + 1, n_particles_y)
+    beam = RectangularShape(ds, n_per_dim, (0.0, 0.0), density=density, place_on_shell=True,
+                            coordinates_eltype=coordinates_eltype, eltype=eltype)
+    structure = union(clamped, beam)
+    system = TotalLagrangianSPHSystem(
+        structure, smoothing_kernel=WendlandC2Kernel(2), smoothing_length=np.sqrt(2) * ds, young_modulus=E,
+        poisson_ratio=nu, clamped_particles=range(clamped.nparticles), acceleration=(0.0, -gravity),
+        penalty_force=penalty_force)
+    # middle_particle_id (1-based, in the beam = in the system, whose clamped particles sit behind the beam's)
+    mid = n_per_dim[0] * (n_per_dim[1] + 1) // 2
+    info = dict(mid_particle=mid - 1, start_position=beam.coordinates[mid - 1].astype(np.float64), particle_spacing=ds,
+                n_particles_per_dimension=n_per_dim)
+    return system, info
+
+
 def hydrostatic_water_column_fsi_2d(n_particles_plate_y=3, *, eltype=np.float64, coordinates_eltype=None,
                                     initial_fluid_size=(1.0, 2.0), plate_size=(1.0, 0.05), E=67.5e9, nu=0.3,
                                     sound_speed=50.0, damping_coefficient=0.05):

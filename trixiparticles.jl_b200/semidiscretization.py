@@ -74,9 +74,9 @@ class Semidiscretization:
         if len(fluids) + len(walls) + len(structures) != len(systems):
             raise ValueError("only WeaklyCompressibleSPHSystem, WallBoundarySystem and TotalLagrangianSPHSystem "
                              "are on the accelerated path")
-        if len(fluids) != 1 or len(structures) > 1:
-            raise ValueError("the accelerated path takes exactly one fluid system, any number of wall systems "
-                             "with the same boundary model and at most one structure system")
+        if len(fluids) > 1 or len(structures) > 1 or (not fluids and not structures):
+            raise ValueError("the accelerated path takes one fluid system (none for a structure-only set-up), any "
+                             "number of wall systems with the same boundary model and at most one structure system")
         nd = {s.ndims for s in systems}
         if len(nd) != 1:
             raise ValueError("all systems must have the same number of dimensions")
@@ -120,8 +120,23 @@ class Semidiscretization:
 
     # -- helpers ---------------------------------------------------------------------------
     @property
-    def fluid(self) -> WeaklyCompressibleSPHSystem:
-        return next(s for s in self.systems if isinstance(s, WeaklyCompressibleSPHSystem))
+    def fluid(self) -> Optional[WeaklyCompressibleSPHSystem]:
+        return next((s for s in self.systems if isinstance(s, WeaklyCompressibleSPHSystem)), None)
+
+    def _placeholder_fluid(self) -> WeaklyCompressibleSPHSystem:
+        """`Semidiscretization(structure_system)` (examples/structure/oscillating_beam_2d.jl): the library's grid
+        belongs to a fluid system, so a structure-only set-up registers an EMPTY one behind the user's systems -- no
+        particles, no rows in the ODE vectors; its kernel and smoothing length (the structure's) only size the cells."""
+        from .model import StateEquationCole
+        from .setups import InitialCondition
+        st, nd, t = self.structure, self.ndims, self.eltype
+        ic = InitialCondition(np.zeros((0, nd), dtype=self.coordinates_eltype), np.zeros((0, nd), dtype=t),
+                              np.zeros(0, dtype=t), np.zeros(0, dtype=t), np.zeros(0, dtype=t),
+                              st.initial_condition.particle_spacing)
+        return WeaklyCompressibleSPHSystem(ic, smoothing_kernel=st.smoothing_kernel, smoothing_length=st.smoothing_length,
+                                           density_calculator=ContinuityDensity(),
+                                           state_equation=StateEquationCole(sound_speed=1.0, reference_density=1.0,
+                                                                            exponent=1))
 
     @property
     def wall(self) -> Optional[WallBoundarySystem]:
@@ -365,6 +380,10 @@ class Semidiscretization:
                                                         coords.ctypes.data, mass.ctypes.data,
                                                         dens.ctypes.data, C.byref(idx)))
                 assert idx.value == self.system_index(s)
+            if self.fluid is None:
+                ph, idx = self._placeholder_fluid(), C.c_int32(-1)
+                fp = self._fluid_params(ph)
+                _lib.check(h, L.tpb_add_fluid_system(h, C.byref(fp), 0, None, C.byref(idx)))
             n = len(self.systems)
             for i in range(n):
                 for j in range(n):

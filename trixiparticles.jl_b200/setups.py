@@ -198,6 +198,56 @@ def RectangularShape(particle_spacing, n_particles_per_dimension, min_coordinate
     return InitialCondition(coords, vel, masses, densities, press, float(particle_spacing))
 
 
+def SphereShape(particle_spacing, radius, center_position, density, *, n_layers=-1, layer_outwards=False,
+                cutout_min=None, cutout_max=None, place_on_shell=False, velocity=None, mass=None, pressure=0.0,
+                coordinates_eltype=np.float64, eltype=np.float64) -> InitialCondition:
+    """sphere_shape.jl:97-134 with `sphere_type = VoxelSphere()` (:183-237): the points center + spacing * (i, j[, k])
+    with inner_radius + 10 eps < |x - center| <= outer_radius + 10 eps, the first index running fastest
+    (CartesianIndices), minus those inside the closed box [cutout_min, cutout_max]."""
+    t = np.dtype(eltype)
+    ct = np.dtype(coordinates_eltype)
+    center = np.asarray(center_position, dtype=np.float64)
+    ndims = center.size
+    dx = float(ct.type(particle_spacing))
+    if n_layers > 0:
+        if layer_outwards:
+            inner, outer = radius, radius + n_layers * dx
+            if not place_on_shell:
+                inner, outer = inner + dx / 2, outer + dx / 2
+        else:
+            inner, outer = radius - n_layers * dx, radius
+            if not place_on_shell:
+                inner, outer = inner - dx / 2, outer - dx / 2
+    else:
+        inner, outer = -1.0, radius
+        if not place_on_shell:
+            outer -= dx / 2
+    n_cube = int(np.rint(outer / dx))
+    r = np.arange(-n_cube, n_cube + 1)
+    idx = np.stack(np.meshgrid(*([r] * ndims), indexing="ij"), axis=-1).reshape(-1, ndims)
+    # CartesianIndices: the first index fastest
+    order = np.lexsort(tuple(idx[:, d] for d in range(ndims)))
+    idx = idx[order]
+    x = center[None, :] + dx * idx
+    dist = np.linalg.norm(x - center[None, :], axis=1)
+    eps = np.finfo(np.float64).eps
+    keep = (inner + 10 * eps < dist) & (dist <= outer + 10 * eps)
+    x = x[keep]
+    if cutout_min is not None and cutout_max is not None:
+        lo, hi = np.asarray(cutout_min, dtype=np.float64), np.asarray(cutout_max, dtype=np.float64)
+        if np.linalg.norm(hi - lo) > eps:
+            inside = np.all((lo[None, :] <= x) & (x <= hi[None, :]), axis=1)
+            x = x[~inside]
+    n = x.shape[0]
+    dens = np.full(n, density, dtype=t)
+    masses = (t.type(particle_spacing) ** ndims * dens).astype(t) if mass is None else np.full(n, mass, dtype=t)
+    vel = np.zeros((n, ndims), dtype=t)
+    if velocity is not None:
+        vel[:] = np.asarray(velocity, dtype=t)[None, :]
+    return InitialCondition(np.ascontiguousarray(x.astype(ct)), vel, masses, dens, np.full(n, pressure, dtype=t),
+                            float(particle_spacing))
+
+
 def _round_n_particles(size, spacing, t=np.float64):
     # rectangular_tank.jl:406-416 (Julia `round` = ties-to-even, as np.rint); evaluated in
     # ELTYPE like the reference (`size` and `spacing` are ELTYPE values there)
