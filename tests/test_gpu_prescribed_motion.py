@@ -166,3 +166,65 @@ def test_moving_wall_2d_time_loop():
     assert u[:, 1].max() < 0.8 + 1e-3                       # and the column has not grown
     assert 950.0 < v[:, 2].min() and v[:, 2].max() < 1100.0
     semi.close()
+
+
+def test_dam_break_gate_kick_is_the_superposition_of_its_parts():
+    """examples/fsi/dam_break_gate_2d.jl: fluid + tank + moving gate + elastic plate.  Inside the library the gate's
+    dummy particles share the plate's slot (clamped particles with a prescribed motion).  Independent check by
+    superposition of pair sums: the fluid's dv with gate AND plate = (with the plate) + (with the gate) - (with
+    neither), each from its own oracle path; the plate's dv and both Adami pressure fields as in the separate cases."""
+    from test_gpu_fsi import fsi_state
+    fluid, tank_w, gate_w, plate, _ = examples.dam_break_gate_2d(0.02)
+    u, v = fsi_state(fluid, plate, seed=11)
+    n_f, n_int = fluid.nparticles, plate.n_integrated_particles
+    u_f = u[: 2 * n_f].reshape(n_f, 2)
+    u_f[: n_f // 2, 0] += 0.33                   # half of the water already at the plate
+    v_f = v[: 3 * n_f].reshape(n_f, 3)
+    t = 0.05                                     # the gate is on its way up: velocity 5.2, acceleration 59
+    semi = tp.Semidiscretization(fluid, tank_w, gate_w, plate, parallelization_backend=tp.B200Backend())
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    assert semi.lib_index(gate_w) == semi.lib_index(plate) == 2 and semi.ranges_u[-1][1] == u.size
+    dv = np.full_like(v, np.nan)
+    ode.f1(dv, v, u, ode.p, t)
+    assert np.isfinite(dv).all() and gate_w.ismoving
+    lift = -285.115 * t ** 3 + 72.305 * t ** 2 + 0.1463 * t
+    assert np.allclose(gate_w.coordinates, gate_w.initial_condition.coordinates + [0.0, lift])
+    with_plate = adapter.kick_fsi(fluid, tank_w, plate, u, v)
+    with_gate = adapter.kick_moving_wall(fluid, gate_w, u_f, v_f, static_wall=tank_w)
+    neither = adapter.kick(fluid, tank_w, u_f, v_f)
+    want_f = with_plate["dv"][: 3 * n_f].reshape(n_f, 3) + with_gate["dv"] - neither["dv"]
+    got_f, got_s = dv[: 3 * n_f].reshape(n_f, 3), dv[3 * n_f:]
+    # both couplings are active
+    assert np.abs(with_gate["dv"] - neither["dv"]).max() > 1.0
+    assert np.abs(with_plate["dv"][: 3 * n_f].reshape(n_f, 3) - neither["dv"]).max() > 1.0
+    assert rel_inf(got_f[:, :2], want_f[:, :2]) <= 1e-11 and rel_inf(got_f[:, 2], want_f[:, 2]) <= 1e-11
+    assert rel_inf(got_s, with_plate["dv"][3 * n_f:]) <= 1e-11
+    assert rel_inf(semi.system_field(gate_w, "pressure"), with_gate["pressure_wall"]) <= 1e-10
+    assert rel_inf(semi.system_field(plate, "pressure"), with_plate["structure_pressure"]) <= 1e-10
+    assert rel_inf(semi.system_field(plate, "deformation_grad"), with_plate["F"]) <= 1e-11
+    assert semi.system_field(gate_w, "density").shape == (gate_w.nparticles,)
+    semi.close()
+
+
+def test_dam_break_gate_2d_time_loop():
+    """The example run to t = 0.25 (CarpenterKennedy2N54; the movement function runs on the host per kick): the gate
+    stops at its prescribed height, the released water reaches the plate and bends it downstream."""
+    from trixiparticles.jl_b200.time_integration import CarpenterKennedy2N54, solve
+    fluid, tank_w, gate_w, plate, _ = examples.dam_break_gate_2d(0.02)
+    semi = tp.Semidiscretization(fluid, tank_w, gate_w, plate, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 0.25))
+    sol = solve(ode, CarpenterKennedy2N54(), dt=5e-5)
+    assert sol.retcode == "Success"
+    u = sol.u.cpu().numpy()
+    assert np.isfinite(u).all()
+    n_f, n_int = fluid.nparticles, plate.n_integrated_particles
+    lift = -285.115 * 0.1 ** 3 + 72.305 * 0.1 ** 2 + 0.1463 * 0.1
+    assert not gate_w.ismoving
+    assert np.allclose(gate_w.coordinates[:, 1] - gate_w.initial_condition.coordinates[:, 1], lift, atol=2e-3)
+    x_f = u[: 2 * n_f].reshape(n_f, 2)
+    assert x_f[:, 0].max() > 0.5                          # the front has passed under the gate and reached the plate
+    x_s = u[2 * n_f:].reshape(n_int, 2)
+    x0 = plate.initial_coordinates[:n_int]
+    top = x0[:, 1] > x0[:, 1].max() - 1e-9
+    assert (x_s[top, 0] - x0[top, 0]).mean() > 1e-4       # bent downstream
+    semi.close()

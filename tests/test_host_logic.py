@@ -134,3 +134,36 @@ def test_product_path_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in text.lower() or fn == "tpb_tiles.cuh" and False, fn
+
+
+def test_moving_wall_next_to_a_structure_shares_the_slot_only_when_exact():
+    """A moving dummy-particle wall and a structure with the same boundary model share the library's structure slot
+    (dam_break_gate_2d.jl); a different boundary model or a gate inside the structure's kernel support is refused."""
+    import numpy as np
+    import pytest
+    import trixiparticles.jl_b200 as tp
+    from trixiparticles.jl_b200 import examples
+    fluid, tank_w, gate_w, plate, _ = examples.dam_break_gate_2d(0.02)
+    semi = tp.Semidiscretization(fluid, tank_w, gate_w, plate)
+    assert semi._gate is gate_w and semi.lib_index(gate_w) == semi.lib_index(plate) == 2
+    assert semi.system_index(gate_w) == 2 and semi.system_index(plate) == 3
+    assert semi.ranges_u[2] == (400, 400)          # the gate has no rows in the ODE vectors
+    # another pressure offset on the gate: not the same boundary model any more
+    m = gate_w.boundary_model
+    other = tp.BoundaryModelDummyParticles(m.initial_density, m.hydrodynamic_mass,
+                                           tp.AdamiPressureExtrapolation(pressure_offset=10.0), m.smoothing_kernel,
+                                           m.smoothing_length, state_equation=m.state_equation,
+                                           clip_negative_pressure=True)
+    gate2 = tp.WallBoundarySystem(gate_w.initial_condition, other, prescribed_motion=gate_w.prescribed_motion)
+    with pytest.raises(ValueError, match="share one slot"):
+        tp.Semidiscretization(fluid, tank_w, gate2, plate)
+    # a gate that starts inside the plate's kernel support
+    ic = gate_w.initial_condition
+    near = tp.InitialCondition(ic.coordinates + [plate.initial_coordinates[:, 0].min() - ic.coordinates[:, 0].max() - 0.005, 0.0],
+                               ic.velocity, ic.mass, ic.density, ic.pressure, ic.particle_spacing)
+    m2 = tp.BoundaryModelDummyParticles(m.initial_density, m.hydrodynamic_mass, tp.AdamiPressureExtrapolation(),
+                                        m.smoothing_kernel, m.smoothing_length, state_equation=m.state_equation,
+                                        clip_negative_pressure=True)
+    gate3 = tp.WallBoundarySystem(near, m2, prescribed_motion=gate_w.prescribed_motion)
+    with pytest.raises(ValueError, match="kernel support"):
+        tp.Semidiscretization(fluid, tank_w, gate3, plate)

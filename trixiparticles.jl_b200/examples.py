@@ -300,6 +300,61 @@ def dam_break_plate_3d(fluid_particle_spacing=0.02, *, n_particles_x=3, eltype=n
     return fluid, wall, structure_system, tank
 
 
+def dam_break_gate_2d(fluid_particle_spacing=0.02, *, n_particles_x=4, eltype=np.float64, coordinates_eltype=np.float64):
+    """examples/fsi/dam_break_gate_2d.jl:18-160: a water column behind a gate that is pulled up with
+    y + (-285.115 t^3 + 72.305 t^2 + 0.1463 t) for t < 0.1, the released water hitting an elastic plate.  Four systems:
+    fluid, tank (static dummy-particle wall), gate (moving dummy-particle wall), plate (TLSPH with the same dummy-particle
+    boundary model).  Returns (fluid, tank_wall, gate_wall, plate, tank)."""
+    from .model import PrescribedMotion
+    t = np.dtype(eltype).type
+    gravity = 9.81
+    dx = fluid_particle_spacing
+    boundary_layers, spacing_ratio = 3, 1
+    bdx = dx / spacing_ratio
+    initial_fluid_size, tank_size = (0.2, 0.4), (0.8, 0.8)
+    fluid_density = 997.0
+    sound_speed = 10 * np.sqrt(2 * gravity * initial_fluid_size[1])
+    state_equation = StateEquationCole(sound_speed=float(t(sound_speed)), reference_density=fluid_density, exponent=7)
+    tank = RectangularTank(dx, initial_fluid_size, tank_size, fluid_density, n_layers=boundary_layers,
+                           spacing_ratio=spacing_ratio, acceleration=(0.0, -gravity), state_equation=state_equation,
+                           coordinates_eltype=coordinates_eltype, eltype=eltype)
+    gate_height = initial_fluid_size[1] + 4 * dx
+    gate = RectangularShape(bdx, (boundary_layers, int(np.rint(gate_height / bdx))), (initial_fluid_size[0], 0.0),
+                            density=fluid_density, coordinates_eltype=coordinates_eltype, eltype=eltype)
+    lift = lambda tt: -285.115 * tt ** 3 + 72.305 * tt ** 2 + 0.1463 * tt
+    motion = PrescribedMotion(
+        lambda x, tt: x + np.array([0.0, lift(tt)])[None, :], lambda tt: tt < 0.1,
+        velocity_function=lambda x, tt: np.broadcast_to(np.array([0.0, -855.345 * tt ** 2 + 144.61 * tt + 0.1463]), x.shape),
+        acceleration_function=lambda x, tt: np.broadcast_to(np.array([0.0, -1710.69 * tt + 144.61]), x.shape))
+    length_beam, thickness = 0.09, 0.004 * 10
+    structure_density, E, nu = 1161.54, 3.5e6 / 10, 0.45
+    ds = thickness / (n_particles_x - 1)
+    n_particles_y = int(np.rint(length_beam / ds)) + 1
+    plate_position = 0.6 - n_particles_x * ds
+    plate = RectangularShape(ds, (n_particles_x, n_particles_y - 1), (plate_position, ds), density=structure_density,
+                             place_on_shell=True, coordinates_eltype=coordinates_eltype, eltype=eltype)
+    clamped = RectangularShape(ds, (n_particles_x, 1), (plate_position, 0.0), density=structure_density,
+                               place_on_shell=True, coordinates_eltype=coordinates_eltype, eltype=eltype)
+    structure = union(clamped, plate)
+    h = 1.75 * dx
+    kernel = WendlandC2Kernel(2)
+    fluid = WeaklyCompressibleSPHSystem(
+        tank.fluid, smoothing_kernel=kernel, smoothing_length=h, density_calculator=ContinuityDensity(),
+        state_equation=state_equation, viscosity=ArtificialViscosityMonaghan(alpha=0.1, beta=0.0),
+        acceleration=(0.0, -gravity))
+    model = lambda dens, mass: BoundaryModelDummyParticles(dens, mass, AdamiPressureExtrapolation(), kernel, h,
+                                                           state_equation=state_equation, clip_negative_pressure=True)
+    tank_wall = WallBoundarySystem(tank.boundary, model(tank.boundary.density, tank.boundary.mass))
+    gate_wall = WallBoundarySystem(gate, model(gate.density, gate.mass), prescribed_motion=motion)
+    hyd_rho = t(fluid_density) * np.ones(structure.nparticles, dtype=eltype)
+    hyd_mass = (hyd_rho * t(ds) ** 2).astype(eltype)
+    plate_system = TotalLagrangianSPHSystem(
+        structure, smoothing_kernel=WendlandC2Kernel(2), smoothing_length=np.sqrt(2) * ds, young_modulus=E,
+        poisson_ratio=nu, boundary_model=model(hyd_rho, hyd_mass), clamped_particles=range(clamped.nparticles),
+        acceleration=(0.0, -gravity))
+    return fluid, tank_wall, gate_wall, plate_system, tank
+
+
 def oscillating_beam_2d(n_particles_y=5, *, eltype=np.float64, coordinates_eltype=np.float64, penalty_force=None):
     """examples/structure/oscillating_beam_2d.jl:13-92: an elastic beam (0.35 x 0.02, E = 1.4e6, nu = 0.4) clamped in
     a disc of fixed particles, swinging under gravity 2.0 -- a structure-only semidiscretization.  The validation run

@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from .model import (AdamiPressureExtrapolation, ArtificialViscosityMonaghan, BoundaryModelDummyParticles,
+from .model import (compact_support, AdamiPressureExtrapolation, ArtificialViscosityMonaghan, BoundaryModelDummyParticles,
                     BoundaryModelMonaghanKajtar,
                     ContinuityDensity,
                     DensityDiffusionMolteniColagrossi, SourceTermDamping, StateEquationAdaptiveCole,
@@ -114,9 +114,60 @@ class Semidiscretization:
         slot = [s for s in systems if isinstance(s, TotalLagrangianSPHSystem)
                 or (isinstance(s, WallBoundarySystem)
                     and (s.prescribed_motion is not None or isinstance(s.boundary_model, BoundaryModelMonaghanKajtar)))]
-        if len(slot) > 1:
-            raise ValueError("a structure system, a moving wall and a Monaghan-Kajtar wall exclude each other on the "
-                             "accelerated path (one of them per semidiscretization)")
+        # A moving wall NEXT TO a structure (examples/fsi/dam_break_gate_2d.jl: the gate and the plate): when both
+        # carry dummy particles with the same boundary model, the gate's particles join the structure's slot as
+        # additional clamped particles.  Exact as long as no gate particle is within the structure's own kernel
+        # support of a structure particle in the initial configuration -- TLSPH pairs its particles once, there
+        # (total_lagrangian_sph/system.jl:391-401) -- which is checked here.
+        self._gate = None
+        if len(slot) == 2 and self._mergeable(slot):
+            self._gate = next(s for s in slot if isinstance(s, WallBoundarySystem))
+        elif len(slot) > 1:
+            raise ValueError("a structure system, a moving wall and a Monaghan-Kajtar wall share one slot on the "
+                             "accelerated path: one of them per semidiscretization, or a moving dummy-particle wall "
+                             "together with a structure that carries the same BoundaryModelDummyParticles")
+        # library system numbers (call order of tpb_add_*_system): the merged gate has the structure's
+        self._lib_index, k = {}, 0
+        for s_ in systems:
+            if s_ is self._gate:
+                continue
+            self._lib_index[id(s_)] = k
+            k += 1
+        if self._gate is not None:
+            self._lib_index[id(self._gate)] = self._lib_index[id(self.structure)]
+
+    def _mergeable(self, slot) -> bool:
+        gate = next((s for s in slot if isinstance(s, WallBoundarySystem) and s.prescribed_motion is not None), None)
+        st = next((s for s in slot if isinstance(s, TotalLagrangianSPHSystem)), None)
+        if gate is None or st is None or st.prescribed_motion is not None:
+            return False
+        a, b = gate.boundary_model, st.boundary_model
+        if not (isinstance(a, BoundaryModelDummyParticles) and isinstance(b, BoundaryModelDummyParticles)):
+            return False
+        sa, sb = a.state_equation, b.state_equation
+        same = (a.smoothing_kernel.kernel_id == b.smoothing_kernel.kernel_id
+                and float(a.smoothing_length) == float(b.smoothing_length)
+                and bool(a.clip_negative_pressure) == bool(b.clip_negative_pressure)
+                and type(a.density_calculator) is type(b.density_calculator)
+                and float(a.density_calculator.pressure_offset) == float(b.density_calculator.pressure_offset)
+                and getattr(a.density_calculator, "factor", 0.0) == 0.0 == getattr(b.density_calculator, "factor", 0.0)
+                and a.viscosity is None and b.viscosity is None
+                and all(float(getattr(sa, f)) == float(getattr(sb, f))
+                        for f in ("sound_speed", "exponent", "reference_density", "background_pressure")))
+        if not same:
+            return False
+        from scipy.spatial import cKDTree
+        support = float(compact_support(st.smoothing_kernel, st.smoothing_length))
+        d, _ = cKDTree(np.asarray(st.initial_coordinates, dtype=np.float64)).query(
+            np.asarray(gate.initial_condition.coordinates, dtype=np.float64))
+        if d.min() <= support * (1 + 1e-6):
+            raise ValueError("the moving wall starts within the structure's kernel support of the structure: the two "
+                             "cannot share the structure slot (see DESIGN.md)")
+        return True
+
+    def lib_index(self, system) -> int:
+        """The system's number inside the library (differs from `system_index` behind a merged moving wall)."""
+        return self._lib_index[id(system)]
 
     # -- helpers ---------------------------------------------------------------------------
     @property
@@ -300,6 +351,8 @@ class Semidiscretization:
         try:
             for s in self.systems:
                 idx = C.c_int32(-1)
+                if s is self._gate:
+                    continue    # registered with the structure (below)
                 if isinstance(s, WeaklyCompressibleSPHSystem):
                     mass = np.ascontiguousarray(s.mass, dtype=self.eltype)
                     if be.ghost_capacity:
@@ -316,7 +369,19 @@ class Semidiscretization:
                     hyd = (np.ascontiguousarray(s.boundary_model.hydrodynamic_mass, dtype=self.eltype)
                            if s.boundary_model is not None else None)
                     sp = self._structure_params(s)
-                    _lib.check(h, L.tpb_add_structure_system(h, C.byref(sp), s.nparticles, s.n_integrated_particles,
+                    n_total = s.nparticles
+                    if self._gate is not None:
+                        # the gate's dummy particles behind the structure's clamped ones; their "material" mass and
+                        # density never enter (no structure particle has them as a neighbour)
+                        g = self._gate
+                        gm = np.ascontiguousarray(g.boundary_model.hydrodynamic_mass, dtype=self.eltype)
+                        x0 = np.ascontiguousarray(np.concatenate(
+                            [x0, np.asarray(g.initial_condition.coordinates, dtype=self.coordinates_eltype)]))
+                        mass, hyd = np.concatenate([mass, gm]), np.concatenate([hyd, gm])
+                        rho = np.concatenate([rho, np.asarray(g.boundary_model.initial_density, dtype=self.eltype)])
+                        sp.bm_wall_semantics = 1   # the acceleration of the gate's particles enters their Adami sum;
+                        n_total += g.nparticles    # the structure's own clamped particles have none
+                    _lib.check(h, L.tpb_add_structure_system(h, C.byref(sp), n_total, s.n_integrated_particles,
                                                              x0.ctypes.data, mass.ctypes.data, rho.ctypes.data,
                                                              hyd.ctypes.data if hyd is not None else None,
                                                              C.byref(idx)))
@@ -379,16 +444,24 @@ class Semidiscretization:
                     _lib.check(h, L.tpb_add_wall_system(h, C.byref(wp), s.nparticles,
                                                         coords.ctypes.data, mass.ctypes.data,
                                                         dens.ctypes.data, C.byref(idx)))
-                assert idx.value == self.system_index(s)
+                assert idx.value == self.lib_index(s)
             if self.fluid is None:
                 ph, idx = self._placeholder_fluid(), C.c_int32(-1)
                 fp = self._fluid_params(ph)
                 _lib.check(h, L.tpb_add_fluid_system(h, C.byref(fp), 0, None, C.byref(idx)))
             n = len(self.systems)
+            if self._gate is not None:
+                gi, si = self.system_index(self._gate), self.system_index(self.structure)
+                others = [k for k in range(n) if k not in (gi, si)]
+                im = self.interaction_matrix
+                if not (np.array_equal(im[gi, others], im[si, others]) and np.array_equal(im[others, gi], im[others, si])):
+                    raise ValueError("a moving wall that shares the structure's slot needs the structure's "
+                                     "interaction switches")
             for i in range(n):
                 for j in range(n):
-                    if not self.interaction_matrix[i, j]:
-                        _lib.check(h, L.tpb_set_interaction(h, i, j, 0))
+                    li, lj = self.lib_index(self.systems[i]), self.lib_index(self.systems[j])
+                    if not self.interaction_matrix[i, j] and not (self._gate is not None and li == lj and i != j):
+                        _lib.check(h, L.tpb_set_interaction(h, li, lj, 0))
             _lib.check(h, L.tpb_semidiscretize(h, u0_ode.ctypes.data))
             if be.ghost_capacity:
                 n_own = self.fluid.nparticles
@@ -448,13 +521,22 @@ class Semidiscretization:
             return
         L = _lib.load()
         if s.apply_prescribed_motion(t):
-            x = np.ascontiguousarray(s.clamped_coordinates, dtype=self.coordinates_eltype)
-            v = np.ascontiguousarray(s.clamped_velocity, dtype=self.eltype)
-            a = np.ascontiguousarray(s.clamped_acceleration, dtype=self.eltype)
+            xs, vs, as_ = s.clamped_coordinates, s.clamped_velocity, s.clamped_acceleration
+            if s is self._gate:
+                # the structure's own clamped particles come first in the slot: fixed
+                st = self.structure
+                fixed = np.asarray(st.initial_coordinates[st.n_integrated_particles:], dtype=np.float64)
+                xs = np.concatenate([fixed, xs])
+                vs = np.concatenate([np.zeros_like(fixed), vs])
+                as_ = np.concatenate([np.zeros_like(fixed), as_])
+            x = np.ascontiguousarray(xs, dtype=self.coordinates_eltype)
+            v = np.ascontiguousarray(vs, dtype=self.eltype)
+            a = np.ascontiguousarray(as_, dtype=self.eltype)
             _lib.check(self._handle, L.tpb_set_clamped_motion(self._handle, x.ctypes.data, v.ctypes.data,
                                                               a.ctypes.data, 1))
             if isinstance(s, WallBoundarySystem):
-                s.coordinates = x    # current_coordinates(u, wall) = system.coordinates
+                # current_coordinates(u, wall) = system.coordinates
+                s.coordinates = np.ascontiguousarray(s.clamped_coordinates, dtype=self.coordinates_eltype)
         else:
             _lib.check(self._handle, L.tpb_set_clamped_motion(self._handle, None, None, None, 0))
 
@@ -467,7 +549,7 @@ class Semidiscretization:
         self._bind_stream()
         for s in self.systems:
             if isinstance(s, WeaklyCompressibleSPHSystem):
-                _lib.check(self._handle, _lib.load().tpb_sort_system(self._handle, self.system_index(s), pv, pu))
+                _lib.check(self._handle, _lib.load().tpb_sort_system(self._handle, self.lib_index(s), pv, pu))
 
     def set_integrate_structure(self, enabled: bool):
         """`semi.integrate_tlsph[] = enabled` (semidiscretization.jl:149): with a SplitIntegrationCallback kick! /
@@ -511,21 +593,24 @@ class Semidiscretization:
                "volume": _lib.FIELD_VOLUME, "wall_velocity": _lib.FIELD_WALL_VELOCITY,
                "deformation_grad": _lib.FIELD_DEFORMATION_GRADIENT, "pk1_rho2": _lib.FIELD_PK1_RHO2,
                "correction_matrix": _lib.FIELD_CORRECTION_MATRIX}[field]
+        li = self.lib_index(system)
+        # a moving wall merged into the structure's slot: the library's system holds [structure | gate]
+        n_lib, lo = system.nparticles, 0
+        if self._gate is not None and system in (self._gate, self.structure):
+            n_lib = self.structure.nparticles + self._gate.nparticles
+            lo = self.structure.nparticles if system is self._gate else 0
         if fid >= _lib.FIELD_DEFORMATION_GRADIENT:
             # structure: (n, ND, ND) with [p, j, i] = M[i, j, p] (the reference's ND x ND x n memory layout)
-            out = np.zeros((system.nparticles, self.ndims, self.ndims), dtype=self.eltype)
-            _lib.check(self._handle, _lib.load().tpb_get_system_field(
-                self._handle, self.system_index(system), fid, out.ctypes.data, system.nparticles))
-            return out
+            out = np.zeros((n_lib, self.ndims, self.ndims), dtype=self.eltype)
+            _lib.check(self._handle, _lib.load().tpb_get_system_field(self._handle, li, fid, out.ctypes.data, n_lib))
+            return out[lo:lo + system.nparticles]
         if field == "wall_velocity":   # boundary_model.cache.wall_velocity, (n, ND)
-            out = np.zeros((system.nparticles, self.ndims), dtype=self.eltype)
-            _lib.check(self._handle, _lib.load().tpb_get_system_field(
-                self._handle, self.system_index(system), fid, out.ctypes.data, system.nparticles))
-            return out
-        out = np.zeros(system.nparticles, dtype=self.eltype)
-        _lib.check(self._handle, _lib.load().tpb_get_system_field(
-            self._handle, self.system_index(system), fid, out.ctypes.data, out.size))
-        return out
+            out = np.zeros((n_lib, self.ndims), dtype=self.eltype)
+            _lib.check(self._handle, _lib.load().tpb_get_system_field(self._handle, li, fid, out.ctypes.data, n_lib))
+            return out[lo:lo + system.nparticles]
+        out = np.zeros(n_lib, dtype=self.eltype)
+        _lib.check(self._handle, _lib.load().tpb_get_system_field(self._handle, li, fid, out.ctypes.data, out.size))
+        return out[lo:lo + system.nparticles]
 
     def count_neighbor_pairs(self, system, neighbor, u_ode) -> int:
         """Number of ordered neighbour pairs of (system, neighbor) for coordinates `u_ode`."""
@@ -533,8 +618,8 @@ class Semidiscretization:
         ptr = self._ptr(u_ode, self.ranges_u[-1][1], self.coordinates_eltype, "u_ode")
         self._bind_stream()
         cnt = C.c_int64(0)
-        rc = L.tpb_neighbor_pairs(self._handle, self.system_index(system),
-                                  self.system_index(neighbor), ptr, 0, None, None, C.byref(cnt))
+        rc = L.tpb_neighbor_pairs(self._handle, self.lib_index(system),
+                                  self.lib_index(neighbor), ptr, 0, None, None, C.byref(cnt))
         if rc not in (0, 6):  # TPB_ERR_CAPACITY is expected: only the count is wanted
             _lib.check(self._handle, rc)
         return int(cnt.value)
@@ -550,8 +635,8 @@ class Semidiscretization:
             oi = np.empty(cap, dtype=np.int32)
             oj = np.empty(cap, dtype=np.int32)
             cnt = C.c_int64(0)
-            rc = L.tpb_neighbor_pairs(self._handle, self.system_index(system),
-                                      self.system_index(neighbor), ptr, cap, oi.ctypes.data,
+            rc = L.tpb_neighbor_pairs(self._handle, self.lib_index(system),
+                                      self.lib_index(neighbor), ptr, cap, oi.ctypes.data,
                                       oj.ctypes.data, C.byref(cnt))
             if rc == 6:  # TPB_ERR_CAPACITY
                 cap = int(cnt.value)
