@@ -338,3 +338,60 @@ def test_oscillating_beam_2d_validation_trace():
     assert ex <= 1e-5 and ey <= 1e-5, (ex, ey)         # measured: 1.1e-7 / 2.6e-7
     assert np.mean((dx - rx) ** 2) <= 1e-14 and np.mean((dy - ry) ** 2) <= 1e-14   # the reference's own check: MSE ~ 0
     semi.close()
+
+
+@pytest.mark.parametrize("eltype,tol", [(np.float64, 1e-11), (np.float32, 3e-5)])
+def test_falling_sphere_2d_kick_matches_oracle(eltype, tol):
+    """examples/fsi/falling_sphere_2d.jl: an elastic TLSPH sphere without clamped particles whose dummy particles use
+    `BernoulliPressureExtrapolation` -- on a structure the dynamic pressure term factor rho_f (v_rel . n)^2 / 2 always
+    applies (dummy_particles.jl:696-707), on the static tank it never does.  The sphere half way into the water,
+    moving down at 2 m/s."""
+    fluid, wall, sphere, _ = examples.falling_sphere_2d(0.04, eltype=eltype, coordinates_eltype=eltype)
+    assert sphere.n_integrated_particles == sphere.nparticles
+    u_f, v_f = examples.perturbed_state(fluid, seed=3, position_jitter=0.05)
+    rng = np.random.default_rng(4)
+    x_s = sphere.initial_coordinates.astype(np.float64) + [0.0, -0.7]          # centre at y = 0.9: the free surface
+    x_s = x_s * [1.02, 0.98] + rng.uniform(-2e-4, 2e-4, x_s.shape)             # squeezed a little
+    v_s = np.tile([0.1, -2.0], (sphere.nparticles, 1)) + rng.uniform(-0.05, 0.05, x_s.shape)
+    # the water the sphere has displaced is gone
+    keep = np.linalg.norm(u_f.astype(np.float64) - [0.5 * 1.02, 0.9 * 0.98], axis=1) > 0.3 + 0.03
+    u_f[~keep] += [0.0, 0.45]                                                  # parked above the surface, out of reach
+    u = np.concatenate([u_f.reshape(-1), x_s.astype(eltype).reshape(-1)])
+    v = np.concatenate([v_f.reshape(-1), v_s.astype(eltype).reshape(-1)])
+    ref = adapter.kick_fsi(fluid, wall, sphere, u, v)
+    # the Bernoulli term matters: with the factor switched off the sphere's pressure differs
+    sphere.boundary_model.density_calculator = tp.AdamiPressureExtrapolation()
+    ref_adami = adapter.kick_fsi(fluid, wall, sphere, u, v)
+    sphere.boundary_model.density_calculator = tp.BernoulliPressureExtrapolation()
+    assert np.abs(ref["structure_pressure"] - ref_adami["structure_pressure"]).max() > 100.0
+    semi = tp.Semidiscretization(fluid, wall, sphere, parallelization_backend=tp.B200Backend())
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    dv = np.full_like(v, np.nan)
+    ode.f1(dv, v, u, ode.p, 0.0)
+    n_f = fluid.nparticles
+    assert np.isfinite(dv).all()
+    for name, a, b in (("fluid", dv[: 3 * n_f], ref["dv"][: 3 * n_f]), ("sphere", dv[3 * n_f:], ref["dv"][3 * n_f:])):
+        assert np.abs(a - b).max() <= tol * np.abs(b).max(), (name, np.abs(a - b).max() / np.abs(b).max())
+    p_err = np.abs(semi.system_field(sphere, "pressure") - ref["structure_pressure"]).max()
+    assert p_err <= 10 * tol * np.abs(ref["structure_pressure"]).max()
+    semi.close()
+
+
+def test_falling_sphere_2d_time_loop():
+    """The example for 0.5 s (RDPK3SpFSAL35 with the example's tolerances): free fall until the sphere meets the water
+    at t = 0.29, then it is slowed down; the lighter-than-water sphere (density 500) does not sink to the bottom."""
+    from trixiparticles.jl_b200.time_integration import RDPK3SpFSAL35, solve
+    fluid, wall, sphere, _ = examples.falling_sphere_2d(0.04, eltype=np.float64)
+    semi = tp.Semidiscretization(fluid, wall, sphere, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 0.5))
+    sol = solve(ode, RDPK3SpFSAL35(), abstol=1e-6, reltol=1e-3)
+    assert sol.retcode == "Success"
+    u, v = sol.u.cpu().numpy(), sol.v.cpu().numpy()
+    assert np.isfinite(u).all() and np.isfinite(v).all()
+    n_f, n_s = fluid.nparticles, sphere.nparticles
+    y = u[2 * n_f:].reshape(n_s, 2)[:, 1].mean()
+    vy = v[3 * n_f:].reshape(n_s, 2)[:, 1].mean()
+    free_fall_v = -9.81 * 0.5
+    assert 0.6 < y < 1.2                        # in the water, not at the bottom (centre starts at 1.6, surface at 0.9)
+    assert vy > 0.5 * free_fall_v               # decelerated by the water
+    semi.close()

@@ -355,6 +355,43 @@ def dam_break_gate_2d(fluid_particle_spacing=0.02, *, n_particles_x=4, eltype=np
     return fluid, tank_wall, gate_wall, plate_system, tank
 
 
+def falling_sphere_2d(fluid_particle_spacing=0.02, *, eltype=np.float64, coordinates_eltype=np.float64,
+                      initial_fluid_size=(1.0, 0.9), tank_size=(1.0, 1.0), sphere_center=(0.5, 1.6)):
+    """examples/fsi/falling_sphere_2d.jl (= falling_spheres_2d.jl:18-140 with `structure_system_2 = nothing`): an
+    elastic sphere (radius 0.3, density 500, E = 7e4, nu = 0) dropped into a tank without lid.  Tank and sphere carry
+    dummy particles with BernoulliPressureExtrapolation: for the static tank that is Adami's extrapolation, for the
+    sphere the dynamic pressure term always applies (dummy_particles.jl:696-707).
+    Returns (fluid_system, boundary_system, structure_system, tank)."""
+    from .model import BernoulliPressureExtrapolation
+    from .setups import SphereShape
+    t = np.dtype(eltype).type
+    gravity = 9.81
+    dx = ds = fluid_particle_spacing
+    fluid_density = 1000.0
+    sound_speed = 10 * np.sqrt(gravity * initial_fluid_size[1])
+    state_equation = StateEquationCole(sound_speed=float(t(sound_speed)), reference_density=fluid_density, exponent=1)
+    tank = RectangularTank(dx, initial_fluid_size, tank_size, fluid_density, n_layers=3, spacing_ratio=1,
+                           faces=(True, True, True, False), acceleration=(0.0, -gravity), state_equation=state_equation,
+                           coordinates_eltype=coordinates_eltype, eltype=eltype)
+    sphere = SphereShape(ds, 0.3, sphere_center, 500.0, coordinates_eltype=coordinates_eltype, eltype=eltype)
+    h = 1.5 * dx
+    kernel = WendlandC2Kernel(2)
+    fluid = WeaklyCompressibleSPHSystem(
+        tank.fluid, smoothing_kernel=kernel, smoothing_length=h, density_calculator=ContinuityDensity(),
+        state_equation=state_equation, viscosity=ArtificialViscosityMonaghan(alpha=0.02, beta=0.0),
+        density_diffusion=DensityDiffusionMolteniColagrossi(delta=0.1), acceleration=(0.0, -gravity))
+    model = lambda dens, mass: BoundaryModelDummyParticles(dens, mass, BernoulliPressureExtrapolation(), kernel, h,
+                                                           state_equation=state_equation, clip_negative_pressure=True)
+    wall = WallBoundarySystem(tank.boundary, model(tank.boundary.density, tank.boundary.mass))
+    hyd_rho = t(fluid_density) * np.ones(sphere.nparticles, dtype=eltype)
+    hyd_mass = (hyd_rho * t(ds) ** 2).astype(eltype)
+    structure = TotalLagrangianSPHSystem(
+        sphere, smoothing_kernel=WendlandC2Kernel(2), smoothing_length=np.sqrt(2) * ds, young_modulus=7e4,
+        poisson_ratio=0.0, acceleration=(0.0, -gravity), boundary_model=model(hyd_rho, hyd_mass),
+        penalty_force=PenaltyForceGanzenmueller(alpha=0.3))
+    return fluid, wall, structure, tank
+
+
 def oscillating_beam_2d(n_particles_y=5, *, eltype=np.float64, coordinates_eltype=np.float64, penalty_force=None):
     """examples/structure/oscillating_beam_2d.jl:13-92: an elastic beam (0.35 x 0.02, E = 1.4e6, nu = 0.4) clamped in
     a disc of fixed particles, swinging under gravity 2.0 -- a structure-only semidiscretization.  The validation run
