@@ -395,3 +395,36 @@ def test_falling_sphere_2d_time_loop():
     assert 0.6 < y < 1.2                        # in the water, not at the bottom (centre starts at 1.6, surface at 0.9)
     assert vy > 0.5 * free_fall_v               # decelerated by the water
     semi.close()
+
+
+def test_falling_water_column_fsi_2d():
+    """examples/fsi/falling_water_column_2d.jl: water dropped onto the clamped beam of oscillating_beam_2d.jl -- fluid +
+    structure without any wall, cubic-spline fluid kernel, Monaghan-Kajtar coupling with three structure particles per
+    fluid particle spacing.  Kick against the oracle with the water lowered onto the beam, then the example for
+    0.25 s: the beam is bent down by the water."""
+    from trixiparticles.jl_b200.time_integration import RDPK3SpFSAL35, solve
+    fluid, beam, info = examples.falling_water_column_fsi_2d()
+    box = tp.GridNeighborhoodSearch(2, cell_list=tp.FullGridCellList((-0.5, -3.0), (1.5, 1.5)))
+    u, v = fsi_state(fluid, beam, seed=21, deform=0.02)
+    n_f, n_int = fluid.nparticles, beam.n_integrated_particles
+    u[: 2 * n_f].reshape(n_f, 2)[:, 1] -= 0.13            # the water touches the beam (top at y = 0.05)
+    ref = adapter.kick_fsi(fluid, None, beam, u, v)
+    semi = tp.Semidiscretization(fluid, beam, neighborhood_search=box, parallelization_backend=tp.B200Backend())
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    dv = np.full_like(v, np.nan)
+    ode.f1(dv, v, u, ode.p, 0.0)
+    free = adapter.kick(fluid, None, u[: 2 * n_f].reshape(n_f, 2), v[: 3 * n_f].reshape(n_f, 3))["dv"]
+    assert np.abs(ref["dv"][: 3 * n_f].reshape(n_f, 3) - free).max() > 1.0      # the beam pushes back
+    for name, a, b in (("fluid", dv[: 3 * n_f], ref["dv"][: 3 * n_f]), ("beam", dv[3 * n_f:], ref["dv"][3 * n_f:])):
+        assert np.abs(a - b).max() <= 1e-11 * np.abs(b).max(), (name, np.abs(a - b).max() / np.abs(b).max())
+    semi.close()
+    semi = tp.Semidiscretization(fluid, beam, neighborhood_search=box,
+                                 parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 0.25))
+    sol = solve(ode, RDPK3SpFSAL35(), abstol=1e-6, reltol=1e-4, dtmax=1e-3)
+    assert sol.retcode == "Success"
+    uu = sol.u.cpu().numpy()
+    assert np.isfinite(uu).all()
+    tip_y = uu[2 * n_f:].reshape(n_int, 2)[info["mid_particle"], 1] - info["start_position"][1]
+    assert tip_y < -5e-3                                    # bent down (gravity alone: about -2e-3 by then)
+    semi.close()

@@ -392,15 +392,15 @@ def falling_sphere_2d(fluid_particle_spacing=0.02, *, eltype=np.float64, coordin
     return fluid, wall, structure, tank
 
 
-def oscillating_beam_2d(n_particles_y=5, *, eltype=np.float64, coordinates_eltype=np.float64, penalty_force=None):
+def oscillating_beam_2d(n_particles_y=5, *, eltype=np.float64, coordinates_eltype=np.float64, penalty_force=None,
+                        thickness=0.02, gravity=2.0, boundary_model_factory=None):
     """examples/structure/oscillating_beam_2d.jl:13-92: an elastic beam (0.35 x 0.02, E = 1.4e6, nu = 0.4) clamped in
     a disc of fixed particles, swinging under gravity 2.0 -- a structure-only semidiscretization.  The validation run
     (validation/oscillating_beam_2d/validation_oscillating_beam_2d.jl) adds PenaltyForceGanzenmueller(alpha=0.01) and
     records the deflection of the particle in the middle of the free end.
     Returns (structure_system, info) with info["mid_particle"] the 0-based index of that particle in the system."""
     from .setups import SphereShape
-    gravity = 2.0
-    length, thickness = 0.35, 0.02
+    length = 0.35
     density, E, nu = 1000.0, 1.4e6, 0.4
     clamp_radius = 0.05
     ds = thickness / (n_particles_y - 1)
@@ -415,12 +415,44 @@ def oscillating_beam_2d(n_particles_y=5, *, eltype=np.float64, coordinates_eltyp
     system = TotalLagrangianSPHSystem(
         structure, smoothing_kernel=WendlandC2Kernel(2), smoothing_length=np.sqrt(2) * ds, young_modulus=E,
         poisson_ratio=nu, clamped_particles=range(clamped.nparticles), acceleration=(0.0, -gravity),
-        penalty_force=penalty_force)
+        penalty_force=penalty_force,
+        boundary_model=None if boundary_model_factory is None else boundary_model_factory(structure, ds))
     # middle_particle_id (1-based, in the beam = in the system, whose clamped particles sit behind the beam's)
     mid = n_per_dim[0] * (n_per_dim[1] + 1) // 2
     info = dict(mid_particle=mid - 1, start_position=beam.coordinates[mid - 1].astype(np.float64), particle_spacing=ds,
                 n_particles_per_dimension=n_per_dim)
     return system, info
+
+
+def falling_water_column_fsi_2d(n_particles_y=5, *, eltype=np.float64, coordinates_eltype=np.float64):
+    """examples/fsi/falling_water_column_2d.jl:13-85: a block of water (0.525 x 1.0125, three structure spacings per
+    fluid particle) dropped onto the clamped beam of oscillating_beam_2d.jl (thickness 0.05); no tank -- the water
+    runs off into the void, so the caller supplies a bounding box.  Cubic-spline fluid kernel, Monaghan-Kajtar
+    coupling.  Returns (fluid_system, structure_system, info)."""
+    t = np.dtype(eltype).type
+    gravity = 9.81
+    initial_fluid_size = (0.525, 1.0125)
+    fluid_density = 1000.0
+    info_ds = 0.05 / (n_particles_y - 1)
+    dx = 3 * info_ds
+    sound_speed = 10 * np.sqrt(gravity * initial_fluid_size[1])
+    state_equation = StateEquationCole(sound_speed=float(t(sound_speed)), reference_density=fluid_density, exponent=7)
+    n_f = tuple(int(np.rint(sz / dx)) for sz in initial_fluid_size)
+    water = RectangularShape(dx, n_f, (0.1, 0.2), density=fluid_density, coordinates_eltype=coordinates_eltype,
+                             eltype=eltype)
+    fluid = WeaklyCompressibleSPHSystem(
+        water, smoothing_kernel=SchoenbergCubicSplineKernel(2), smoothing_length=1.2 * dx,
+        density_calculator=ContinuityDensity(), state_equation=state_equation,
+        viscosity=ArtificialViscosityMonaghan(alpha=0.02, beta=0.0), acceleration=(0.0, -gravity))
+    k = gravity * initial_fluid_size[1]
+
+    def model(structure, ds):
+        hyd_mass = (t(fluid_density) * np.ones(structure.nparticles, dtype=eltype) * t(ds) ** 2).astype(eltype)
+        return BoundaryModelMonaghanKajtar(k, dx / ds, ds, hyd_mass)
+
+    beam, info = oscillating_beam_2d(n_particles_y, eltype=eltype, coordinates_eltype=coordinates_eltype,
+                                     thickness=0.05, gravity=gravity, boundary_model_factory=model)
+    return fluid, beam, info
 
 
 def hydrostatic_water_column_fsi_2d(n_particles_plate_y=3, *, eltype=np.float64, coordinates_eltype=None,
