@@ -304,6 +304,12 @@ int32_t tpb_structure_fluid_force(tpb_semi_t semi, void *dv_split, const void *v
 int32_t tpb_kick_structure(tpb_semi_t semi, void *dv_split, const void *v_split, const void *u_split,
                            const void *dv_const);
 int32_t tpb_set_max_speed2(tpb_semi_t semi, const void *bits);
+/* `young_modulus` / `poisson_ratio` of the structure given per particle (total_lagrangian_sph/system.jl:108-161: scalars
+ * or vectors; penalty_force.jl:42-53 uses E of both particles of a pair): T[n] each in the system's particle order
+ * (integrated particles first), HOST pointers, copied.  Overrides the scalars of tpb_structure_params from the next
+ * kick on.  Also what lets several `TotalLagrangianSPHSystem`s with different materials share the one structure slot
+ * (TLSPH pairs its particles in the initial configuration, so bodies that start apart never interact elastically). */
+int32_t tpb_set_structure_material(tpb_semi_t semi, const void *young_modulus, const void *poisson_ratio);
 /* ---- SortingCallback (callbacks/sorting.jl:100-157: sort_particles! / sort_system!): reorders the rows of
  * `system` inside the caller's (v_ode, u_ode) -- in place -- by the grid cell of their current coordinates (linear
  * cell index, x fastest; inside a cell the previous order is kept, so every later kick sums its neighbours in the

@@ -428,3 +428,81 @@ def test_falling_water_column_fsi_2d():
     tip_y = uu[2 * n_f:].reshape(n_int, 2)[info["mid_particle"], 1] - info["start_position"][1]
     assert tip_y < -5e-3                                    # bent down (gravity alone: about -2e-3 by then)
     semi.close()
+
+
+def test_falling_spheres_2d_two_structure_systems():
+    """examples/fsi/falling_spheres_2d.jl: two `TotalLagrangianSPHSystem`s with different radius, density and Young's
+    modulus.  Inside the library they share the structure slot (per-particle material constants,
+    tpb_set_structure_material).  Independent check by superposition against three oracle runs with ONE sphere each:
+    fluid dv = (with sphere 1) + (with sphere 2) - (with neither); each sphere's dv, stress and pressure as alone."""
+    fluid, wall, s1, s2, _ = examples.falling_spheres_2d(0.04)
+    n_f, n1, n2 = fluid.nparticles, s1.nparticles, s2.nparticles
+    u_f, v_f = examples.perturbed_state(fluid, seed=5, position_jitter=0.05)
+    rng = np.random.default_rng(6)
+
+    def sphere_state(sph, drop, squeeze):
+        x = sph.initial_coordinates.astype(np.float64) + [0.0, -drop]
+        c = x.mean(axis=0)
+        x = c + (x - c) * squeeze + rng.uniform(-2e-4, 2e-4, x.shape)
+        vel = np.tile([0.05, -1.5], (sph.nparticles, 1)) + rng.uniform(-0.05, 0.05, x.shape)
+        return x, vel
+    x1, w1 = sphere_state(s1, 0.75, [1.03, 0.97])
+    x2, w2 = sphere_state(s2, 0.65, [0.98, 1.02])
+    for c, r in ((x1.mean(axis=0), 0.3), (x2.mean(axis=0), 0.2)):       # the displaced water is parked out of reach
+        inside = np.linalg.norm(u_f - c, axis=1) < r + 0.04
+        u_f[inside] += [0.0, 0.5]
+    u = np.concatenate([u_f.reshape(-1), x1.reshape(-1), x2.reshape(-1)])
+    v = np.concatenate([v_f.reshape(-1), w1.reshape(-1), w2.reshape(-1)])
+    semi = tp.Semidiscretization(fluid, wall, s1, s2, parallelization_backend=tp.B200Backend())
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    assert semi.lib_index(s1) == semi.lib_index(s2) == 2 and semi.ranges_u[-1][1] == u.size
+    dv = np.full_like(v, np.nan)
+    ode.f1(dv, v, u, ode.p, 0.0)
+    assert np.isfinite(dv).all()
+    cat = lambda *a: np.concatenate([np.asarray(q).reshape(-1) for q in a])
+    r1 = adapter.kick_fsi(fluid, wall, s1, cat(u_f, x1), cat(v_f, w1))
+    r2 = adapter.kick_fsi(fluid, wall, s2, cat(u_f, x2), cat(v_f, w2))
+    r0 = adapter.kick(fluid, wall, u_f, v_f)["dv"].reshape(-1)
+    want_f = r1["dv"][: 3 * n_f] + r2["dv"][: 3 * n_f] - r0
+    assert np.abs(r1["dv"][: 3 * n_f] - r0).max() > 1.0 and np.abs(r2["dv"][: 3 * n_f] - r0).max() > 1.0
+    tol = 1e-11
+    got_f, got_1, got_2 = dv[: 3 * n_f], dv[3 * n_f: 3 * n_f + 2 * n1], dv[3 * n_f + 2 * n1:]
+    assert np.abs(got_f - want_f).max() <= tol * np.abs(want_f).max()
+    assert np.abs(got_1 - r1["dv"][3 * n_f:]).max() <= tol * np.abs(r1["dv"][3 * n_f:]).max()
+    assert np.abs(got_2 - r2["dv"][3 * n_f:]).max() <= tol * np.abs(r2["dv"][3 * n_f:]).max()
+    # the two materials differ: swapping the spheres' moduli would change sphere 2's acceleration
+    for sph, r in ((s1, r1), (s2, r2)):
+        for name, key in (("pressure", "structure_pressure"), ("deformation_grad", "F"), ("pk1_rho2", "pk1_rho2")):
+            got = semi.system_field(sph, name)
+            assert np.abs(got - r[key]).max() <= 10 * tol * max(np.abs(r[key]).max(), 1e-300), (name, sph.nparticles)
+    assert np.abs(r2["pk1_rho2"]).max() > 0
+    semi.close()
+
+
+def test_young_modulus_per_particle():
+    """`young_modulus` / `poisson_ratio` as vectors (system.jl:108-161): constant vectors give the scalar result bit
+    for bit; with the upper part of the plate ten times softer the stress there is a tenth, elsewhere unchanged."""
+    fluid, wall, plate, _ = examples.dam_break_plate_2d(0.01, initial_fluid_size=(0.15, 0.29), plate_position=(0.165, 0.0))
+    u, v = fsi_state(fluid, plate)
+    n = plate.nparticles
+    out = {}
+    for name, E, nu in (("scalar", 1e6, 0.0), ("vector", np.full(n, 1e6), np.zeros(n)),
+                        ("soft top", np.where(plate.initial_coordinates[:, 1] > 0.04, 1e5, 1e6), np.zeros(n))):
+        st = tp.TotalLagrangianSPHSystem(
+            examples.dam_break_plate_2d(0.01, initial_fluid_size=(0.15, 0.29), plate_position=(0.165, 0.0))[2].initial_condition,
+            smoothing_kernel=plate.smoothing_kernel, smoothing_length=plate.smoothing_length, young_modulus=E,
+            poisson_ratio=nu, boundary_model=plate.boundary_model, acceleration=plate.acceleration,
+            penalty_force=plate.penalty_force, clamped_particles=range(n - plate.n_clamped_particles, n))
+        semi = tp.Semidiscretization(fluid, wall, st, parallelization_backend=tp.B200Backend())
+        ode = tp.semidiscretize(semi, (0.0, 1.0))
+        dv = np.full_like(v, np.nan)
+        ode.f1(dv, v, u, ode.p, 0.0)
+        out[name] = (dv.copy(), semi.system_field(st, "pk1_rho2"))
+        semi.close()
+    assert np.array_equal(out["scalar"][0], out["vector"][0]) and np.array_equal(out["scalar"][1], out["vector"][1])
+    y = plate.initial_coordinates[:, 1]
+    soft, stiff = y > 0.04, y <= 0.04
+    assert soft.sum() > 10 and np.abs(out["scalar"][1][soft]).max() > 0
+    # nu = 0: S = E * strain, so the stress scales with E where E was lowered ...
+    assert np.allclose(out["soft top"][1][soft], 0.1 * out["scalar"][1][soft], rtol=1e-13, atol=0)
+    assert np.array_equal(out["soft top"][1][stiff], out["scalar"][1][stiff])      # ... and only there

@@ -82,6 +82,7 @@ struct Semi {
     // velocity / acceleration of the clamped particles ((n_s - n_s_int) x ND), used while clamped_moving
     void *d_xcl_s = nullptr, *d_vcl_s = nullptr, *d_acl_s = nullptr;
     int clamped_moving = 0;
+    void *d_mat_s = nullptr;  // per-particle (lambda, mu, E) of the structure (tpb_set_structure_material), else scalars
     // tpb_sort_system on device vectors: gather targets (allocated at the first call; host mode uses d_du / d_dv)
     void *d_sort_u = nullptr, *d_sort_v = nullptr;
 
@@ -706,7 +707,7 @@ struct Ops {
     case KID:                                                                                                     \
         LAUNCH(s, (k_struct_defgrad_pk1<ND, T, CT, KID>), cdiv(n, 128), 128, 0, n, k, s.d_nbr_start, s.d_nbr,      \
                (const CT *)s.d_x0_s, (const CT *)s.d_xcur_s, (const T *)s.d_mass_s, (const T *)s.d_rho_s,         \
-               (const T *)s.d_L_s, (T *)s.d_F_s, (T *)s.d_pk1_s);                                                 \
+               (const T *)s.d_L_s, (T *)s.d_F_s, (T *)s.d_pk1_s, (const T *)s.d_mat_s);                           \
         break;
             TPB_DEFGRAD(0) TPB_DEFGRAD(1) TPB_DEFGRAD(2) TPB_DEFGRAD(3)
 #undef TPB_DEFGRAD
@@ -820,7 +821,8 @@ struct Ops {
     case KID:                                                                                                    \
         LAUNCH(s, (k_struct_interact<ND, T, CT, KID>), cdiv(n_int, 128), 128, 0, n_int, k,                        \
                s.d_nbr_start, s.d_nbr,                                      (const CT *)s.d_x0_s, (const CT *)s.d_xcur_s,   \
-               (const T *)s.d_mass_s, (const T *)s.d_rho_s, (const T *)s.d_F_s, (const T *)s.d_pk1_s, d_dv_s);   \
+               (const T *)s.d_mass_s, (const T *)s.d_rho_s, (const T *)s.d_F_s, (const T *)s.d_pk1_s, d_dv_s,    \
+               (const T *)s.d_mat_s);                                                                            \
         break;
             TPB_SINTERACT(0) TPB_SINTERACT(1) TPB_SINTERACT(2) TPB_SINTERACT(3)
 #undef TPB_SINTERACT
@@ -1677,7 +1679,7 @@ static void free_device(Semi &s)
                     s.d_flags, s.d_A, s.d_B, s.d_P, s.d_Aw, s.d_Ww, s.d_volw, s.d_Vw, s.d_Pw, s.d_perm_w,
                     s.d_scratch, s.d_Ff, s.d_Fw, s.d_vmax2, s.d_adapt, s.d_x0_s, s.d_xcur_s, s.d_mass_s, s.d_rho_s, s.d_hydro_s,
                     s.d_L_s, s.d_F_s, s.d_pk1_s, s.d_As, s.d_Bs, s.d_nbr_start, s.d_nbr, s.d_scell_start, s.d_sperm,
-                    s.d_Ps, s.d_p_s, s.d_rhoh_s, s.d_xcl_s, s.d_vcl_s, s.d_acl_s, s.d_sort_u, s.d_sort_v};
+                    s.d_Ps, s.d_p_s, s.d_rhoh_s, s.d_xcl_s, s.d_vcl_s, s.d_acl_s, s.d_sort_u, s.d_sort_v, s.d_mat_s};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     tiles_free(s.tiles);
@@ -2314,6 +2316,33 @@ int32_t tpb_set_integrate_structure(tpb_semi_t semi, int32_t enabled)
     if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
     if (s->struct_index < 0) return fail(s, TPB_ERR_STATE, "no structure system");
     s->integrate_structure = enabled ? 1 : 0;
+    return TPB_OK;
+}
+
+int32_t tpb_set_structure_material(tpb_semi_t semi, const void *young_modulus, const void *poisson_ratio)
+{
+    Semi *s = (Semi *)semi;
+    if (!s || !young_modulus || !poisson_ratio) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->ready || s->struct_index < 0) return fail(s, TPB_ERR_STATE, "needs a semidiscretized handle with a structure system");
+    const size_t n = (size_t)s->n_s;
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    // (lambda, mu, E) per particle in the system's eltype, with the reference's roundings (system.jl:158-161)
+    auto fill = [&](auto tag) {
+        using T = decltype(tag);
+        const T *E = (const T *)young_modulus, *nu = (const T *)poisson_ratio;
+        std::vector<T> m(3 * n);
+        for (size_t a = 0; a < n; ++a) {
+            if (!(E[a] > (T)0)) return false;
+            m[3 * a] = E[a] * nu[a] / (((T)1 + nu[a]) * ((T)1 - (T)2 * nu[a]));
+            m[3 * a + 1] = (E[a] / (T)2) / ((T)1 + nu[a]);
+            m[3 * a + 2] = E[a];
+        }
+        if (!s->d_mat_s && cudaMalloc(&s->d_mat_s, sizeof(T) * 3 * (n + 8)) != cudaSuccess) return false;
+        cudaStreamSynchronize(s->stream);
+        return cudaMemcpy(s->d_mat_s, m.data(), sizeof(T) * 3 * n, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    const bool ok = s->cfg.eltype == TPB_F64 ? fill(double()) : fill(float());
+    if (!ok) return fail(s, TPB_ERR_INVALID_ARGUMENT, "young_modulus must be positive (or the device copy failed)");
     return TPB_OK;
 }
 

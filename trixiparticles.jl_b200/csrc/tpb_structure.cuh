@@ -191,10 +191,13 @@ __global__ void __launch_bounds__(128)
 k_struct_defgrad_pk1(int n, StructConst<T> k, const int *__restrict__ nbr_start, const int *__restrict__ nbr,
                      const CT *__restrict__ x0, const CT *__restrict__ x_cur, const T *__restrict__ mass,
                      const T *__restrict__ rho, const T *__restrict__ L, T *__restrict__ F_out,
-                     T *__restrict__ pk1_rho2)
+                     T *__restrict__ pk1_rho2, const T *__restrict__ material = nullptr)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
+    // per-particle material constants (young_modulus / poisson_ratio given as vectors, system.jl:108-161):
+    // (lambda, mu, E) per particle
+    if (material != nullptr) k.lambda = material[3 * (int64_t)a], k.mu = material[3 * (int64_t)a + 1];
     T La[ND * ND], F[ND * ND];
 #pragma unroll
     for (int q = 0; q < ND * ND; ++q) {
@@ -271,11 +274,12 @@ __global__ void __launch_bounds__(128)
 k_struct_interact(int n_int, StructConst<T> k, const int *__restrict__ nbr_start, const int *__restrict__ nbr,
                   const CT *__restrict__ x0, const CT *__restrict__ x_cur, const T *__restrict__ mass,
                   const T *__restrict__ rho, const T *__restrict__ F, const T *__restrict__ pk1_rho2,
-                  T *__restrict__ dv_s)
+                  T *__restrict__ dv_s, const T *__restrict__ material = nullptr)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n_int) return;
     const T m_a = mass[a], rho_a = rho[a];
+    const T young_a = material != nullptr ? material[3 * (int64_t)a + 2] : k.young;
     T Pa[ND * ND], Fa[ND * ND];
 #pragma unroll
     for (int q = 0; q < ND * ND; ++q) {
@@ -315,7 +319,9 @@ k_struct_interact(int n_int, StructConst<T> k, const int *__restrict__ nbr_start
                 da = i == 0 ? (sa - cpd[0]) * cpd[0] : da + (sa - cpd[i]) * cpd[i];
                 db = i == 0 ? (sb - cpd[0]) * cpd[0] : db + (sb - cpd[i]) * cpd[i];
             }
-            const T delta_sum = k.young * da + k.young * db;
+            // E_a dot(eps_a, r) + E_b dot(eps_b, r) (penalty_force.jl:42-53)
+            const T young_b = material != nullptr ? material[3 * (int64_t)b + 2] : k.young;
+            const T delta_sum = young_a * da + young_b * db;
             // current_distance^2 = (sqrt(d2))^2 in the reference
             const T cdist = sqrt_rn(cd2);
             const T f = div_fast(k.half_alpha * volume_a * volume_b * kw * delta_sum,

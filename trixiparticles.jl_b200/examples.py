@@ -392,6 +392,31 @@ def falling_sphere_2d(fluid_particle_spacing=0.02, *, eltype=np.float64, coordin
     return fluid, wall, structure, tank
 
 
+def falling_spheres_2d(fluid_particle_spacing=0.02, *, eltype=np.float64, coordinates_eltype=np.float64,
+                       sphere1_center=(0.5, 1.6), sphere2_center=(1.5, 1.6)):
+    """examples/fsi/falling_spheres_2d.jl:18-140: two elastic spheres of different size, density and stiffness
+    (radius 0.3 / 0.2, density 500 / 1100, E = 7e4 / 1e5) dropped into a tank -- two `TotalLagrangianSPHSystem`s.
+    Returns (fluid_system, boundary_system, structure_system_1, structure_system_2, tank)."""
+    from .model import BernoulliPressureExtrapolation
+    from .setups import SphereShape
+    t = np.dtype(eltype).type
+    fluid, wall, sphere1, tank = falling_sphere_2d(fluid_particle_spacing, eltype=eltype,
+                                                   coordinates_eltype=coordinates_eltype, initial_fluid_size=(2.0, 0.9),
+                                                   tank_size=(2.0, 1.0), sphere_center=sphere1_center)
+    ds = fluid_particle_spacing
+    ball = SphereShape(ds, 0.2, sphere2_center, 1100.0, coordinates_eltype=coordinates_eltype, eltype=eltype)
+    m1 = sphere1.boundary_model
+    hyd_rho = t(1000.0) * np.ones(ball.nparticles, dtype=eltype)
+    model = BoundaryModelDummyParticles(hyd_rho, (hyd_rho * t(ds) ** 2).astype(eltype), BernoulliPressureExtrapolation(),
+                                        m1.smoothing_kernel, m1.smoothing_length, state_equation=m1.state_equation,
+                                        clip_negative_pressure=True)
+    sphere2 = TotalLagrangianSPHSystem(
+        ball, smoothing_kernel=WendlandC2Kernel(2), smoothing_length=np.sqrt(2) * ds, young_modulus=1e5,
+        poisson_ratio=0.0, acceleration=(0.0, -9.81), boundary_model=model,
+        penalty_force=PenaltyForceGanzenmueller(alpha=0.3))
+    return fluid, wall, sphere1, sphere2, tank
+
+
 def oscillating_beam_2d(n_particles_y=5, *, eltype=np.float64, coordinates_eltype=np.float64, penalty_force=None,
                         thickness=0.02, gravity=2.0, boundary_model_factory=None):
     """examples/structure/oscillating_beam_2d.jl:13-92: an elastic beam (0.35 x 0.02, E = 1.4e6, nu = 0.4) clamped in

@@ -492,8 +492,12 @@ class TotalLagrangianSPHSystem(_MovingParticles):
                           ("source_terms", source_terms), ("velocity_averaging", velocity_averaging)):
             if val is not None:
                 raise ValueError(f"`{name}` is outside the accelerated hot path (see DESIGN.md)")
-        if not (np.isscalar(young_modulus) and np.isscalar(poisson_ratio)):
-            raise ValueError("per-particle material constants are outside the accelerated hot path")
+        # scalars or one value per particle (system.jl:108-161); vectors follow the particles to their sorted places
+        per_particle = not (np.isscalar(young_modulus) and np.isscalar(poisson_ratio))
+        if per_particle:
+            n_ = initial_condition.nparticles
+            young_modulus = np.broadcast_to(np.asarray(young_modulus, dtype=np.float64), (n_,)).copy()
+            poisson_ratio = np.broadcast_to(np.asarray(poisson_ratio, dtype=np.float64), (n_,)).copy()
         if penalty_force is not None and not isinstance(penalty_force, PenaltyForceGanzenmueller):
             raise ValueError("`penalty_force` must be a PenaltyForceGanzenmueller")
         dummy = isinstance(boundary_model, BoundaryModelDummyParticles)
@@ -529,8 +533,12 @@ class TotalLagrangianSPHSystem(_MovingParticles):
         self.eltype = ic.eltype
         self.coordinates_eltype = ic.coordinates_eltype
         self.smoothing_length = self.eltype.type(smoothing_length)
-        self.young_modulus = self.eltype.type(young_modulus)
-        self.poisson_ratio = self.eltype.type(poisson_ratio)
+        if per_particle:
+            self.young_modulus = young_modulus[order].astype(self.eltype)
+            self.poisson_ratio = poisson_ratio[order].astype(self.eltype)
+        else:
+            self.young_modulus = self.eltype.type(young_modulus)
+            self.poisson_ratio = self.eltype.type(poisson_ratio)
         self.acceleration = np.asarray(acceleration, dtype=self.eltype)
         self.penalty_force = penalty_force
         self.boundary_model = boundary_model

@@ -63,6 +63,79 @@ def _dtype_id(dt):
     raise ValueError(f"unsupported eltype {dt}")
 
 
+def _same_boundary_model(a, b) -> bool:
+    """Two structure boundary models that the library's one structure slot can serve together."""
+    if a is None or b is None:
+        return a is b
+    if type(a) is not type(b):
+        return False
+    if isinstance(a, BoundaryModelMonaghanKajtar):
+        return (float(a.K) == float(b.K) and float(a.beta) == float(b.beta)
+                and float(a.boundary_particle_spacing) == float(b.boundary_particle_spacing))
+    sa, sb = a.state_equation, b.state_equation
+    return (a.smoothing_kernel.kernel_id == b.smoothing_kernel.kernel_id
+            and float(a.smoothing_length) == float(b.smoothing_length)
+            and bool(a.clip_negative_pressure) == bool(b.clip_negative_pressure)
+            and type(a.density_calculator) is type(b.density_calculator)
+            and float(a.density_calculator.pressure_offset) == float(b.density_calculator.pressure_offset)
+            and getattr(a.density_calculator, "factor", 0.0) == getattr(b.density_calculator, "factor", 0.0)
+            and a.viscosity is None and b.viscosity is None
+            and all(float(getattr(sa, f)) == float(getattr(sb, f))
+                    for f in ("sound_speed", "exponent", "reference_density", "background_pressure")))
+
+
+class _MergedStructure:
+    """Several `TotalLagrangianSPHSystem`s (examples/fsi/falling_spheres_2d.jl) in the library's one structure slot.
+    Exact, because TLSPH pairs its particles once, in the initial configuration (system.jl:391-401): bodies that start
+    further apart than the kernel support never see each other.  Same kernel, smoothing length, acceleration, penalty
+    force and boundary model; Young's modulus and Poisson ratio go to the library per particle
+    (tpb_set_structure_material).  Library order: the integrated particles of all parts, then the clamped ones --
+    the ODE rows [part 1 | part 2 | ...] are the library's rows."""
+
+    def __init__(self, parts):
+        from scipy.spatial import cKDTree
+        p0 = parts[0]
+        for q in parts[1:]:
+            if not (q.smoothing_kernel.kernel_id == p0.smoothing_kernel.kernel_id
+                    and float(q.smoothing_length) == float(p0.smoothing_length)
+                    and np.array_equal(q.acceleration, p0.acceleration)
+                    and (q.penalty_force is None) == (p0.penalty_force is None)
+                    and (q.penalty_force is None or q.penalty_force.alpha == p0.penalty_force.alpha)
+                    and _same_boundary_model(q.boundary_model, p0.boundary_model)
+                    and q.prescribed_motion is None and p0.prescribed_motion is None):
+                raise ValueError("several structure systems share the library's structure slot only with the same "
+                                 "kernel, smoothing length, acceleration, penalty force and boundary model, and without "
+                                 "a PrescribedMotion")
+        support = float(compact_support(p0.smoothing_kernel, p0.smoothing_length))
+        for i, a in enumerate(parts):
+            tree = cKDTree(np.asarray(a.initial_coordinates, dtype=np.float64))
+            for b in parts[i + 1:]:
+                d, _ = tree.query(np.asarray(b.initial_coordinates, dtype=np.float64))
+                if d.min() <= support * (1 + 1e-6):
+                    raise ValueError("structure systems that start within each other's kernel support cannot share "
+                                     "the structure slot")
+        self.parts = tuple(parts)
+        n_int = [q.n_integrated_particles for q in parts]
+        n_cl = [q.nparticles - q.n_integrated_particles for q in parts]
+        io = np.concatenate([[0], np.cumsum(n_int)])
+        co = io[-1] + np.concatenate([[0], np.cumsum(n_cl)])
+        # library index of every particle of part k, in the part's own order (integrated first, then clamped)
+        self.index_of = [np.concatenate([np.arange(io[k], io[k + 1]), np.arange(co[k], co[k + 1])]).astype(np.int64)
+                         for k in range(len(parts))]
+        self.nparticles = int(co[-1])
+        self.n_integrated_particles = int(io[-1])
+        gather = lambda get: np.concatenate([get(q)[:n_int[k]] for k, q in enumerate(parts)]
+                                            + [get(q)[n_int[k]:] for k, q in enumerate(parts)])
+        self.initial_coordinates = gather(lambda q: np.asarray(q.initial_coordinates))
+        self.mass = gather(lambda q: np.asarray(q.mass))
+        self.material_density = gather(lambda q: np.asarray(q.material_density))
+        full = lambda q, v: np.broadcast_to(np.asarray(v, dtype=np.float64), (q.nparticles,))
+        self.young_modulus = gather(lambda q: full(q, q.young_modulus))
+        self.poisson_ratio = gather(lambda q: full(q, q.poisson_ratio))
+        self.hydrodynamic_mass = (None if p0.boundary_model is None
+                                  else gather(lambda q: np.asarray(q.boundary_model.hydrodynamic_mass)))
+
+
 class Semidiscretization:
     def __init__(self, *systems, neighborhood_search: Optional[GridNeighborhoodSearch] = None,
                  parallelization_backend: Optional[B200Backend] = None, interaction_matrix=None):
@@ -74,9 +147,16 @@ class Semidiscretization:
         if len(fluids) + len(walls) + len(structures) != len(systems):
             raise ValueError("only WeaklyCompressibleSPHSystem, WallBoundarySystem and TotalLagrangianSPHSystem "
                              "are on the accelerated path")
-        if len(fluids) > 1 or len(structures) > 1 or (not fluids and not structures):
+        if len(fluids) > 1 or (not fluids and not structures):
             raise ValueError("the accelerated path takes one fluid system (none for a structure-only set-up), any "
-                             "number of wall systems with the same boundary model and at most one structure system")
+                             "number of wall systems with the same boundary model and structure systems that can "
+                             "share one slot")
+        self._merged = _MergedStructure(structures) if len(structures) > 1 else None
+        if self._merged is not None:
+            ks = [i for i, s_ in enumerate(systems) if isinstance(s_, TotalLagrangianSPHSystem)]
+            between = [s_ for s_ in systems[ks[0]:ks[-1] + 1] if not isinstance(s_, TotalLagrangianSPHSystem)]
+            if any(s_.n_integrated_particles > 0 for s_ in between):
+                raise ValueError("structure systems that share the slot must follow each other in the ODE vectors")
         nd = {s.ndims for s in systems}
         if len(nd) != 1:
             raise ValueError("all systems must have the same number of dimensions")
@@ -111,9 +191,12 @@ class Semidiscretization:
             raise ValueError("at most one system with a PrescribedMotion is on the accelerated path")
         self._motion_system = movers[0] if movers else None
         # inside the library a moving wall and a Monaghan-Kajtar wall occupy the (single) structure slot
-        slot = [s for s in systems if isinstance(s, TotalLagrangianSPHSystem)
+        slot = [s for s in systems if (isinstance(s, TotalLagrangianSPHSystem) and s is structures[0])
                 or (isinstance(s, WallBoundarySystem)
                     and (s.prescribed_motion is not None or isinstance(s.boundary_model, BoundaryModelMonaghanKajtar)))]
+        if self._merged is not None and len(slot) > 1:
+            raise ValueError("several structure systems and a moving / Monaghan-Kajtar wall in one semidiscretization "
+                             "are outside the accelerated path")
         # A moving wall NEXT TO a structure (examples/fsi/dam_break_gate_2d.jl: the gate and the plate): when both
         # carry dummy particles with the same boundary model, the gate's particles join the structure's slot as
         # additional clamped particles.  Exact as long as no gate particle is within the structure's own kernel
@@ -130,6 +213,9 @@ class Semidiscretization:
         self._lib_index, k = {}, 0
         for s_ in systems:
             if s_ is self._gate:
+                continue
+            if isinstance(s_, TotalLagrangianSPHSystem) and s_ is not structures[0]:
+                self._lib_index[id(s_)] = self._lib_index[id(structures[0])]   # shares the first structure's slot
                 continue
             self._lib_index[id(s_)] = k
             k += 1
@@ -298,8 +384,9 @@ class Semidiscretization:
         p.struct_size = C.sizeof(_lib.StructureParams)
         p.kernel = st.smoothing_kernel.kernel_id
         p.smoothing_length = float(t(st.smoothing_length))
-        p.young_modulus = float(t(st.young_modulus))
-        p.poisson_ratio = float(t(st.poisson_ratio))
+        # (vectors: the library gets them per particle after tpb_semidiscretize; the scalars only have to be valid)
+        p.young_modulus = float(t(np.ravel(st.young_modulus)[0]))
+        p.poisson_ratio = float(t(np.ravel(st.poisson_ratio)[0]))
         if st.penalty_force is not None:
             p.has_penalty_force = 1
             p.penalty_alpha = float(t(st.penalty_force.alpha))
@@ -351,8 +438,8 @@ class Semidiscretization:
         try:
             for s in self.systems:
                 idx = C.c_int32(-1)
-                if s is self._gate:
-                    continue    # registered with the structure (below)
+                if s is self._gate or (isinstance(s, TotalLagrangianSPHSystem) and s is not self.structure):
+                    continue    # registered with the (first) structure
                 if isinstance(s, WeaklyCompressibleSPHSystem):
                     mass = np.ascontiguousarray(s.mass, dtype=self.eltype)
                     if be.ghost_capacity:
@@ -363,13 +450,15 @@ class Semidiscretization:
                 elif isinstance(s, TotalLagrangianSPHSystem):
                     if be.ghost_capacity:
                         raise ValueError("slab ghosts are not combined with a structure system")
-                    x0 = np.ascontiguousarray(s.initial_coordinates, dtype=self.coordinates_eltype)
-                    mass = np.ascontiguousarray(s.mass, dtype=self.eltype)
-                    rho = np.ascontiguousarray(s.material_density, dtype=self.eltype)
-                    hyd = (np.ascontiguousarray(s.boundary_model.hydrodynamic_mass, dtype=self.eltype)
-                           if s.boundary_model is not None else None)
+                    src = self._merged if self._merged is not None else s
+                    x0 = np.ascontiguousarray(src.initial_coordinates, dtype=self.coordinates_eltype)
+                    mass = np.ascontiguousarray(src.mass, dtype=self.eltype)
+                    rho = np.ascontiguousarray(src.material_density, dtype=self.eltype)
+                    hyd_src = (self._merged.hydrodynamic_mass if self._merged is not None
+                               else (s.boundary_model.hydrodynamic_mass if s.boundary_model is not None else None))
+                    hyd = np.ascontiguousarray(hyd_src, dtype=self.eltype) if hyd_src is not None else None
                     sp = self._structure_params(s)
-                    n_total = s.nparticles
+                    n_total = src.nparticles
                     if self._gate is not None:
                         # the gate's dummy particles behind the structure's clamped ones; their "material" mass and
                         # density never enter (no structure particle has them as a neighbour)
@@ -381,7 +470,7 @@ class Semidiscretization:
                         rho = np.concatenate([rho, np.asarray(g.boundary_model.initial_density, dtype=self.eltype)])
                         sp.bm_wall_semantics = 1   # the acceleration of the gate's particles enters their Adami sum;
                         n_total += g.nparticles    # the structure's own clamped particles have none
-                    _lib.check(h, L.tpb_add_structure_system(h, C.byref(sp), n_total, s.n_integrated_particles,
+                    _lib.check(h, L.tpb_add_structure_system(h, C.byref(sp), n_total, src.n_integrated_particles,
                                                              x0.ctypes.data, mass.ctypes.data, rho.ctypes.data,
                                                              hyd.ctypes.data if hyd is not None else None,
                                                              C.byref(idx)))
@@ -463,6 +552,14 @@ class Semidiscretization:
                     if not self.interaction_matrix[i, j] and not (self._gate is not None and li == lj and i != j):
                         _lib.check(h, L.tpb_set_interaction(h, li, lj, 0))
             _lib.check(h, L.tpb_semidiscretize(h, u0_ode.ctypes.data))
+            st_ = self._merged if self._merged is not None else self.structure
+            if st_ is not None and np.ndim(st_.young_modulus) > 0:
+                n_lib = st_.nparticles + (self._gate.nparticles if self._gate is not None else 0)
+                pad = lambda a: np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64),
+                                                                     np.full(n_lib - st_.nparticles, np.ravel(a)[0])]),
+                                                     dtype=self.eltype)
+                E_, nu_ = pad(st_.young_modulus), pad(st_.poisson_ratio)
+                _lib.check(h, L.tpb_set_structure_material(h, E_.ctypes.data, nu_.ctypes.data))
             if be.ghost_capacity:
                 n_own = self.fluid.nparticles
                 _lib.check(h, L.tpb_set_fluid_count(h, n_own, n_own))
@@ -599,18 +696,22 @@ class Semidiscretization:
         if self._gate is not None and system in (self._gate, self.structure):
             n_lib = self.structure.nparticles + self._gate.nparticles
             lo = self.structure.nparticles if system is self._gate else 0
+        pick = None
+        if self._merged is not None and isinstance(system, TotalLagrangianSPHSystem):
+            n_lib = self._merged.nparticles
+            pick = self._merged.index_of[self._merged.parts.index(system)]
         if fid >= _lib.FIELD_DEFORMATION_GRADIENT:
             # structure: (n, ND, ND) with [p, j, i] = M[i, j, p] (the reference's ND x ND x n memory layout)
             out = np.zeros((n_lib, self.ndims, self.ndims), dtype=self.eltype)
             _lib.check(self._handle, _lib.load().tpb_get_system_field(self._handle, li, fid, out.ctypes.data, n_lib))
-            return out[lo:lo + system.nparticles]
+            return out[pick] if pick is not None else out[lo:lo + system.nparticles]
         if field == "wall_velocity":   # boundary_model.cache.wall_velocity, (n, ND)
             out = np.zeros((n_lib, self.ndims), dtype=self.eltype)
             _lib.check(self._handle, _lib.load().tpb_get_system_field(self._handle, li, fid, out.ctypes.data, n_lib))
             return out[lo:lo + system.nparticles]
         out = np.zeros(n_lib, dtype=self.eltype)
         _lib.check(self._handle, _lib.load().tpb_get_system_field(self._handle, li, fid, out.ctypes.data, out.size))
-        return out[lo:lo + system.nparticles]
+        return out[pick] if pick is not None else out[lo:lo + system.nparticles]
 
     def count_neighbor_pairs(self, system, neighbor, u_ode) -> int:
         """Number of ordered neighbour pairs of (system, neighbor) for coordinates `u_ode`."""

@@ -134,8 +134,9 @@ def calculate_dt(system: WeaklyCompressibleSPHSystem, cfl_number: float) -> floa
 def calculate_dt_structure(system, cfl_number: float) -> float:
     """total_lagrangian_sph/system.jl:701-717: cfl h / sqrt(K / rho_min), bulk modulus
     K = E / (ND (1 - 2 nu))."""
-    E, nu = float(system.young_modulus), float(system.poisson_ratio)
-    K = E / (system.ndims * (1 - 2 * nu))
+    # (vectors: the stiffest particle decides)
+    E, nu = np.asarray(system.young_modulus, dtype=np.float64), np.asarray(system.poisson_ratio, dtype=np.float64)
+    K = float(np.max(E / (system.ndims * (1 - 2 * nu))))
     sound_speed = math.sqrt(K / float(np.min(system.material_density)))
     return cfl_number * float(system.smoothing_length) / sound_speed
 
@@ -177,6 +178,8 @@ class SplitIntegrationCallback:
             raise ValueError("`SplitIntegrationCallback` must be used with a `TotalLagrangianSPHSystem`")
         if semi.parallelization_backend.ode_memory != "device":
             raise ValueError("SplitIntegrationCallback needs B200Backend(ode_memory='device')")
+        if getattr(semi, "_merged", None) is not None:
+            raise ValueError("SplitIntegrationCallback with several structure systems is outside the accelerated path")
         self.semi, self.system = semi, st
         i = semi.system_index(st)
         self.rv, self.ru = semi.ranges_v[i], semi.ranges_u[i]
