@@ -24,6 +24,12 @@ out = {
     "kinetic_energy_fluid_1": d["kinetic_energy_fluid_1"]["values"],
 }
 json.dump(out, open(DST, "w"))
+# second resolution (5 particles across the plate)
+d5 = json.load(open(SRC.replace("_3.json", "_5.json")))
+json.dump({"source": SRC.replace("_3.json", "_5.json"), "n_particles_plate_y": 5,
+           "analytical_value": d5["analytical_solution"]["values"][0], "time": d5["y_deflection_structure_1"]["time"],
+           "y_deflection_structure_1": d5["y_deflection_structure_1"]["values"]},
+          open(DST.replace("_3_trace", "_5_trace"), "w"))
 t, y = out["time"], out["y_deflection_structure_1"]
 late = [v for tt, v in zip(t, y) if tt >= 0.25]
 print(f"{len(t)} samples to t = {t[-1]}; mean deflection over t >= 0.25: {sum(late) / len(late):.6e}; "

@@ -26,5 +26,13 @@ out = {
     "deflection_y_structure_1": d["deflection_y_structure_1"]["values"][:n],
 }
 json.dump(out, open(DST, "w"))
+# second resolution (9 particles across the beam), to t = 1
+d9 = json.load(open(SRC.replace("_5.json", "_9.json")))
+t9 = d9["deflection_x_structure_1"]["time"]
+n9 = sum(1 for tt in t9 if tt <= 1.0 + 1e-12)
+json.dump({"source": SRC.replace("_5.json", "_9.json"), "n_particles_y": 9, "time": t9[:n9],
+           "deflection_x_structure_1": d9["deflection_x_structure_1"]["values"][:n9],
+           "deflection_y_structure_1": d9["deflection_y_structure_1"]["values"][:n9]},
+          open(DST.replace("_5_trace", "_9_trace"), "w"))
 print(f"{n} samples to t = {out['time'][-1]}; min deflection_y = {min(out['deflection_y_structure_1']):.6e}, "
       f"min deflection_x = {min(out['deflection_x_structure_1']):.6e}")
