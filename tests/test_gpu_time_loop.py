@@ -344,3 +344,30 @@ def test_hydrostatic_water_column_2d_with_shipped_integrator():
     assert np.abs(v[:, :2]).max() < 0.02 * 10.0
     assert np.abs(u - fluid.initial_condition.coordinates).max() < 0.025
     semi.close()
+
+
+def test_hydrostatic_water_column_3d_and_falling_water_column_2d():
+    """examples/fluid/hydrostatic_water_column_3d.jl (Float32, RDPK3SpFSAL35 as shipped): the column stays at rest;
+    examples/fluid/falling_water_column_2d.jl: the block is in free fall for the first 0.2 s (y = y0 - g t^2 / 2 to
+    within the weak pressure waves of a block without initial hydrostatic pressure), then spreads on the floor."""
+    import trixiparticles.jl_b200 as tp
+    from trixiparticles.jl_b200 import examples
+    from trixiparticles.jl_b200.time_integration import RDPK3SpFSAL35, solve
+    fluid, wall, _ = examples.hydrostatic_water_column_3d(0.1)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 0.3))
+    sol = solve(ode, RDPK3SpFSAL35(), abstol=1e-6, reltol=1e-3)
+    assert sol.retcode == "Success"
+    u, v = sol.u.cpu().numpy().reshape(-1, 3), sol.v.cpu().numpy().reshape(-1, 4)
+    assert np.isfinite(u).all()
+    assert np.abs(u - fluid.initial_condition.coordinates).max() < 0.03 and np.abs(v[:, :3]).max() < 0.5
+    semi.close()
+    fluid, wall, _ = examples.falling_water_column_2d(0.05)
+    semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+    ode = tp.semidiscretize(semi, (0.0, 0.15))
+    sol = solve(ode, RDPK3SpFSAL35(), abstol=1e-5, reltol=1e-3, dtmax=1e-2)
+    assert sol.retcode == "Success"
+    u, v = sol.u.cpu().numpy().reshape(-1, 2), sol.v.cpu().numpy().reshape(-1, 3)
+    drop = (fluid.initial_condition.coordinates[:, 1] - u[:, 1]).mean()
+    assert abs(drop - 0.5 * 9.81 * 0.15 ** 2) < 0.01 and abs(v[:, 1].mean() + 9.81 * 0.15) < 0.1     # free fall
+    semi.close()

@@ -82,6 +82,49 @@ def hydrostatic_water_column_2d(fluid_particle_spacing=0.05, *, eltype=np.float3
     return fluid, wall, tank
 
 
+def hydrostatic_water_column_3d(fluid_particle_spacing=0.05, *, eltype=np.float32, coordinates_eltype=np.float32):
+    """examples/fluid/hydrostatic_water_column_3d.jl: the 2-D example with `initial_fluid_size = (1, 1, 0.9)`,
+    `tank_size = (1, 1, 1.2)`, gravity along z and the 3-D cubic spline."""
+    gravity = 9.81
+    dx = fluid_particle_spacing
+    acc = (0.0, 0.0, -gravity)
+    state_equation = StateEquationCole(sound_speed=10.0, reference_density=1000.0, exponent=7,
+                                       clip_negative_pressure=False)
+    tank = RectangularTank(dx, (1.0, 1.0, 0.9), (1.0, 1.0, 1.2), 1000.0, n_layers=3, acceleration=acc,
+                           state_equation=state_equation, coordinates_eltype=coordinates_eltype, eltype=eltype)
+    h = 1.2 * dx
+    kernel = SchoenbergCubicSplineKernel(3)
+    fluid = WeaklyCompressibleSPHSystem(
+        tank.fluid, smoothing_kernel=kernel, smoothing_length=h, density_calculator=ContinuityDensity(),
+        state_equation=state_equation, viscosity=ArtificialViscosityMonaghan(alpha=0.02, beta=0.0), acceleration=acc)
+    model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass, AdamiPressureExtrapolation(), kernel, h,
+                                        state_equation=state_equation)
+    return fluid, WallBoundarySystem(tank.boundary, model), tank
+
+
+def falling_water_column_2d(fluid_particle_spacing=0.02, *, eltype=np.float64, coordinates_eltype=np.float64):
+    """examples/fluid/falling_water_column_2d.jl:13-75: a 0.5 x 1 block of water released 0.2 above the floor in the
+    middle of a 4 x 4 tank (no initial hydrostatic pressure: the block is in free fall)."""
+    gravity = 9.81
+    dx = fluid_particle_spacing
+    initial_fluid_size, tank_size = (0.5, 1.0), (4.0, 4.0)
+    sound_speed = 10 * np.sqrt(gravity * initial_fluid_size[1])
+    state_equation = StateEquationCole(sound_speed=sound_speed, reference_density=1000.0, exponent=7)
+    tank = RectangularTank(dx, initial_fluid_size, tank_size, 1000.0, n_layers=3, spacing_ratio=1,
+                           coordinates_eltype=coordinates_eltype, eltype=eltype)
+    shift = np.array([0.5 * tank_size[0] - 0.5 * initial_fluid_size[0], 0.2])
+    tank.fluid.coordinates = (tank.fluid.coordinates + shift[None, :]).astype(coordinates_eltype)
+    h = 1.2 * dx
+    kernel = SchoenbergCubicSplineKernel(2)
+    fluid = WeaklyCompressibleSPHSystem(
+        tank.fluid, smoothing_kernel=kernel, smoothing_length=h, density_calculator=ContinuityDensity(),
+        state_equation=state_equation, viscosity=ArtificialViscosityMonaghan(alpha=0.02, beta=0.0),
+        acceleration=(0.0, -gravity))
+    model = BoundaryModelDummyParticles(tank.boundary.density, tank.boundary.mass, AdamiPressureExtrapolation(), kernel, h,
+                                        state_equation=state_equation, clip_negative_pressure=True)
+    return fluid, WallBoundarySystem(tank.boundary, model), tank
+
+
 def accelerated_tank_2d(fluid_particle_spacing=0.05, *, eltype=np.float64, coordinates_eltype=np.float64):
     """examples/fluid/accelerated_tank_2d.jl: the hydrostatic water column without gravity in a tank that is
     accelerated upwards with g -- in the tank's frame the same problem."""
