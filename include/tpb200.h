@@ -162,8 +162,9 @@ typedef struct {
  * (structure/total_lagrangian_sph/system.jl:76-184, penalty_force.jl:11-16,
  * wall_boundary/monaghan_kajtar.jl:18-34) -- BASELINE config 5 (examples/fsi/dam_break_plate_2d.jl).
  * Scalar material constants; the clamped particles are the LAST n - n_integrated particles (the
- * reference's constructor moves them there, system.jl:131-147) and are fixed
- * (clamped_particles_motion = nothing). */
+ * reference's constructor moves them there, system.jl:131-147); they rest at their initial positions unless
+ * tpb_set_clamped_motion prescribes otherwise (clamped_particles_motion).  Scalar material constants here;
+ * per particle: tpb_set_structure_material. */
 #define TPB_BOUNDARY_NONE 0            /* boundary_model = nothing: no coupling with the fluid */
 #define TPB_BOUNDARY_MONAGHAN_KAJTAR 1
 #define TPB_BOUNDARY_DUMMY_PARTICLES 2 /* BoundaryModelDummyParticles{AdamiPressureExtrapolation} on the structure
@@ -229,7 +230,10 @@ int32_t tpb_add_wall_system(tpb_semi_t semi, const tpb_wall_params *params, int6
 /* `initial_coords`: cT[ND x n] (integrated particles first); `mass`, `material_density`: T[n];
  * `hydrodynamic_mass`: T[n] (boundary_model.hydrodynamic_mass; may be NULL with TPB_BOUNDARY_NONE).
  * The system contributes ND x n_integrated entries to u_ode and to v_ode
- * (system.jl:277-289).  At most one structure system; not combined with slab ghosts. */
+ * (system.jl:277-289).  One structure system per handle -- which may hold several bodies (several
+ * `TotalLagrangianSPHSystem`s, a moving wall's dummy particles as extra clamped particles): TLSPH pairs its particles
+ * once, in the initial configuration, so bodies that start further apart than the kernel support never interact
+ * elastically.  Not combined with slab ghosts. */
 int32_t tpb_add_structure_system(tpb_semi_t semi, const tpb_structure_params *params, int64_t n,
                                  int64_t n_integrated, const void *initial_coords, const void *mass,
                                  const void *material_density, const void *hydrodynamic_mass,
