@@ -52,6 +52,8 @@ WORKLOADS = {
     "dam_break_3d_1m": ("dam_break_3d", 0.0126),     # 992 319 fluid + 1 599 800 wall
     "dam_break_3d_10m": ("dam_break_3d", 0.00585),   # ~10 M fluid
     "dam_break_3d_12m5": ("dam_break_3d", 0.00543),  # ~12.5 M fluid: the per-GPU size of the --gpus N run
+    "dam_break_3d_30m": ("dam_break_3d", 0.0040),    # SURVEY 8(d) M4 on ONE GPU: ~31 M fluid
+    "dam_break_3d_100m": ("dam_break_3d", 0.0027),   # ~101 M fluid + 34 M wall on one GPU (records ~5 GB of the 180 GB)
     "dam_break_3d_250k": ("dam_break_3d", 0.02),     # reduced sample for slow CPU legs
     "dam_break_3d_small": ("dam_break_3d", 0.05),    # quick functional check
     "dam_break_2d": ("dam_break_2d", 40),            # config 1 (Float64)
