@@ -105,7 +105,7 @@ struct Semi {
     unsigned long long *d_scan_status = nullptr;
     unsigned long long *d_scan_ticket = nullptr;
     int scan_blocks = 0, scan_rows_per_block = 0;  // 0 blocks: grid shape not supported, three-kernel scan instead
-    int subkey_mode = 1;           // order inside a cell: 0 previous index, 1.. position key (tpb_nhs.cuh, TPB_SUBKEY)
+    int subkey_mode = 1;           // order inside a cell: 0 previous index, 1 position key (tpb_nhs.cuh, TPB_SUBKEY)
     bool count_clean = false;      // the cell histogram is all zero (left so by k_scan_cells_tiles)
     bool wall_prep_done = false;   // this kick's rebuild launch has sorted the wall tiles into empty / active
     int *h_flags = nullptr;  // pinned
@@ -351,7 +351,14 @@ struct Ops {
 
     // ---- counting sort of one point set into the shared grid: key/slot/count/scan/scatter
     // bits of a tmp_perm entry that hold the particle index (the position key sits above them)
-    static int perm_bits(const Semi &s, int64_t n) { return s.subkey_mode && n < (1 << PERM_IDX_BITS) ? PERM_IDX_BITS : 31; }
+    static int perm_bits(const Semi &s, int64_t n)
+    {
+        if (!s.subkey_mode) return 31;
+        if (s.subkey_mode > 1) return std::min(std::max(s.subkey_mode, PERM_IDX_BITS), 27);  // TPB_SUBKEY=26 / 27: test hook
+        for (int b = PERM_IDX_BITS; b <= 27; ++b)
+            if (n < ((int64_t)1 << b)) return b;
+        return 31;
+    }
 
     static int bin_points(Semi &s, const CT *d_coords, int n, int n_targets, int *d_cell_start,
                           const CT *d_tail_coords = nullptr, int n_head = 0, CT *d_out_coords = nullptr)
@@ -362,7 +369,7 @@ struct Ops {
         s.count_clean = false;
         if (n > 0)
             LAUNCH(s, (k_cell_count<ND, CT>), cdiv(n, 256), 256, 0, d_coords, n, n_targets, g, s.d_key,
-                   s.d_slot, s.d_count, s.d_flags, pb < 31 ? s.subkey_mode : 0, d_tail_coords, n_head, d_out_coords);
+                   s.d_slot, s.d_count, s.d_flags, pb, d_tail_coords, n_head, d_out_coords);
         int rc = exclusive_scan(s, s.d_count, (int)s.ncells, d_cell_start);
         if (rc) return rc;
         if (n > 0)
@@ -425,7 +432,7 @@ struct Ops {
         }
         if (n > 0)
             LAUNCH(s, (k_cell_count<ND, CT>), cdiv(n, 256), 256, 0, d_u, n, (int)s.n_tgt, g, s.d_key, s.d_slot,
-                   s.d_count, s.d_flags, perm_bits(s, n) < 31 ? s.subkey_mode : 0);
+                   s.d_count, s.d_flags, perm_bits(s, n));
         const bool has_wall = s.n_w > 0;                           // a second neighbour set for the fluid tiles
         const bool wall = has_wall && !wall_integrates_density(s);  // Adami walls: sort the wall tiles as well
         LAUNCH(s, k_scan_cells_tiles, s.scan_blocks, CSCAN_THREADS, 0, s.d_count, s.ncell[0], s.tiles.nrows,

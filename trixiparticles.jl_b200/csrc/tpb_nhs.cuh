@@ -25,18 +25,19 @@ namespace tpb {
 // mixed.  So the entries of tmp_perm carry a 6-bit position key above the particle index,
 //   entry = sub << pbits | i,   sub = the particle's place among 4 x 4 x 4 sub-boxes of its cell,
 // and rank_in_cell orders by (sub, i): still a total order independent of the atomics' arrival order.
-// pbits = PERM_IDX_BITS when the set has fewer than 2^25 particles, else 31 (no position key).
+// pbits = bits left for the particle index: 25 (6-bit key, 4 x 4 x 4 sub-boxes) for sets of fewer than 2^25
+// particles, 26 (5 bits: 4 x 4 x 2) below 2^26, 27 (4 bits: 4 x 4 x 1) below 2^27 -- the library's size limit --
+// and 31 (no key) when the key is switched off.
 // Measured at 1 M particles (interact! phase; profiles/r2_y_order_inside_cells.txt): lattice order in the ODE vectors
 // 0.853 ms with or without the key; a random order 0.887 ms without, 0.854 ms with it.  Sub-boxes in lexicographic
 // order with the row axis fastest are the best of those tried: the row axis slowest 0.860, Morton order 0.884 (no
 // better than random), serpentine 0.867, 8 x 8 x 1 boxes 0.871, 2 x 2 x 16 0.880, 4 x 2 x 8 0.884, 3 x 3 x 7 0.855.
 // TPB_SUBKEY=0 switches the key off.
-constexpr int SLOT_BITS = 25;       // arrival number inside a cell (< n < 2^25 whenever a key is stored): low bits of slot[i]
-constexpr int PERM_IDX_BITS = 25;
+constexpr int PERM_IDX_BITS = 25;   // smallest index width (largest key); slot[i] = arrival number | key << pbits
 __host__ __device__ __forceinline__ int perm_index(int entry, int pbits) { return entry & (int)((1u << pbits) - 1u); }
 
 template <int ND, typename CT>
-__device__ __forceinline__ int cell_subkey(const GridConst<CT> &g, CT x, CT y, CT z, int cx, int cy, int cz, int mode)
+__device__ __forceinline__ int cell_subkey(const GridConst<CT> &g, CT x, CT y, CT z, int cx, int cy, int cz, int pbits)
 {
     if (g.ax == 1) {
         const CT t = x;
@@ -52,15 +53,17 @@ __device__ __forceinline__ int cell_subkey(const GridConst<CT> &g, CT x, CT y, C
     const float fz = ND == 3 ? (float)((z - g.origin[2]) * g.inv_cell - (CT)cz) : 0.f;
     const int sx = min(max((int)(fx * 4.f), 0), 3), sy = min(max((int)(fy * 4.f), 0), 3);
     const int sz = min(max((int)(fz * 4.f), 0), 3);
-    (void)mode;
-    return (sz * 4 + sy) * 4 + sx;  // lexicographic, the row axis fastest
+    // lexicographic, the row axis fastest; fewer sub-boxes along the row when the index needs the bits
+    if (pbits <= PERM_IDX_BITS) return (sz * 4 + sy) * 4 + sx;
+    if (pbits == PERM_IDX_BITS + 1) return (sz * 4 + sy) * 2 + (sx >> 1);
+    return sz * 4 + sy;
 }
 
 template <int ND, typename CT>
 __global__ void __launch_bounds__(256)
 k_cell_count(const CT *__restrict__ coords /* ND x n, AoS */, int n, int n_targets, GridConst<CT> g,
              int *__restrict__ key, int *__restrict__ slot, int *__restrict__ count,
-             int *__restrict__ flags, int sub_mode = 0, const CT *__restrict__ tail_coords = nullptr,
+             int *__restrict__ flags, int pbits = 31, const CT *__restrict__ tail_coords = nullptr,
              int n_head = 0, CT *__restrict__ out_coords = nullptr)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,8 +88,8 @@ k_cell_count(const CT *__restrict__ coords /* ND x n, AoS */, int n, int n_targe
     if (!cell_coords<ND, CT>(g, x, y, z, cx, cy, cz)) atomicOr(flags, 1);
     int c = cell_linear(g, cx, cy, cz);
     key[i] = c;
-    const int sub = sub_mode ? cell_subkey<ND, CT>(g, x, y, z, cx, cy, cz, sub_mode) : 0;
-    slot[i] = atomicAdd(&count[c], 1) | (sub << SLOT_BITS);
+    const int sub = pbits < 31 ? cell_subkey<ND, CT>(g, x, y, z, cx, cy, cz, pbits) : 0;
+    slot[i] = atomicAdd(&count[c], 1) | (pbits < 31 ? sub << pbits : 0);
 }
 
 // ------------------------------------------------------------------ exclusive scan (int32)
@@ -225,8 +228,8 @@ k_scatter(const int *__restrict__ key, const int *__restrict__ slot,
     if (i >= n) return;
     if (key[i] < 0) return;  // empty slab-ghost slot
     const int sl = slot[i];
-    if (pbits < 31)
-        tmp_perm[cell_start[key[i]] + (sl & ((1 << SLOT_BITS) - 1))] = ((sl >> SLOT_BITS) << pbits) | i;
+    if (pbits < 31)  // slot = arrival number | key << pbits: the key moves over to the entry
+        tmp_perm[cell_start[key[i]] + (sl & ((1 << pbits) - 1))] = (sl & ~((1 << pbits) - 1)) | i;
     else
         tmp_perm[cell_start[key[i]] + sl] = i;
 }

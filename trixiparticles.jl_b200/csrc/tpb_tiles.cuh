@@ -1415,9 +1415,9 @@ k_post_scan(int nb_scatter, int nb_ranges, const int *__restrict__ key, const in
     if (vb < nb_scatter) {
         const int i = vb * blockDim.x + threadIdx.x;
         if (i < n && key[i] >= 0) {
-            const int sl = slot[i];  // arrival number | position key << SLOT_BITS (k_cell_count)
+            const int sl = slot[i];  // arrival number | position key << pbits (k_cell_count)
             if (pbits < 31)
-                tmp_perm[fcell_start[key[i]] + (sl & ((1 << SLOT_BITS) - 1))] = ((sl >> SLOT_BITS) << pbits) | i;
+                tmp_perm[fcell_start[key[i]] + (sl & ((1 << pbits) - 1))] = (sl & ~((1 << pbits) - 1)) | i;
             else
                 tmp_perm[fcell_start[key[i]] + sl] = i;
         }
