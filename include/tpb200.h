@@ -325,6 +325,16 @@ int32_t tpb_set_structure_material(tpb_semi_t semi, const void *young_modulus, c
  * 10 M 8.8 %.  Host or device pointers according to ode_memory; stream-ordered on device
  * vectors.  Not with slab ghosts. */
 int32_t tpb_sort_system(tpb_semi_t semi, int32_t system, void *v_ode, void *u_ode);
+/* ---- DensityReinitializationCallback (callbacks/density_reinit.jl:83-121 -> reinit_density!, schemes/fluid/
+ * weakly_compressible_sph/system.jl:398-415; Panizzo 2007): the fluid's density rows of `v_ode` are replaced, in place,
+ * by the Shepard-corrected summation density
+ *     rho~_a = sum_b m_b W_ab (fluid + wall),   c_a = sum_b (m_b / rho_b) W_ab,   rho_a = rho~_a / c_a,
+ * where a fluid neighbour enters c with rho~_b (the reference overwrites v before it computes the coefficient; its
+ * `v[end, :]` is a view for the CPU's PtrArray) and a wall neighbour with its boundary-model density, which is updated
+ * here for the given state first (initialize_reinit_cb!, :100-112).  ContinuityDensity fluids only (SummationDensity:
+ * no-op); fluid + Adami walls.  The reference has no numerical test for this callback: parity rests on the
+ * restatement in oracle/ and on "a uniform field stays uniform". */
+int32_t tpb_reinit_density(tpb_semi_t semi, void *v_ode, const void *u_ode);
 /* ---- PrescribedMotion (schemes/boundary/prescribed_motion.jl:95-121; apply_prescribed_motion!,
  * wall_boundary/system.jl:199-205 and total_lagrangian_sph/system.jl:436-447).  The movement function is the
  * caller's: before a kick it hands over where the clamped particles of the structure system (all particles of

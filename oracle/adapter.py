@@ -106,6 +106,14 @@ def kick(fluid, wall, u, v, use_grid=True, nthreads=0, fluid_wall_interaction=Tr
                   nthreads=nthreads, v_wall=v_wall)
 
 
+def reinit_density(fluid, wall, u, v):
+    """Oracle `reinit_density!` (DensityReinitializationCallback) for Semidiscretization(fluid[, wall])."""
+    fp = fluid_params(fluid)
+    wp = wall_params(wall) if wall is not None else None
+    return O.reinit_density(fp, wp, fluid.mass, wall.coordinates if wall is not None else None,
+                            wall.boundary_model.hydrodynamic_mass if wall is not None else None, v, u, fluid.eltype)
+
+
 def structure_params(st) -> O.TlsphParams:
     t = np.dtype(st.eltype).type
     p = O.TlsphParams()

@@ -131,6 +131,8 @@ def _declare(L):
                       p, p, p, p, p, p, i, i]
         f = getattr(L, f"orc_drift_{s}"); f.restype = None
         f.argtypes = [i, i, i64, p, p]
+        f = getattr(L, f"orc_reinit_density_{s}"); f.restype = i
+        f.argtypes = [C.POINTER(FluidParams), C.POINTER(WallParams), i64, p, i64, p, p, p, p, p]
         TP = C.POINTER(TlsphParams)
         f = getattr(L, f"orc_tlsph_correction_matrix_{s}"); f.restype = i
         f.argtypes = [TP, i64, p, p, p, p]
@@ -364,6 +366,29 @@ def tlsph_interact(sp: TlsphParams, n_int, x0, x_cur, mass, rho, F, pk1_rho2, dt
                                                     _ptr(rho), _ptr(F), _ptr(P), _ptr(dv))
     assert rc == 0
     return dv
+
+
+def reinit_density(fp: FluidParams, wp, mass_f, coords_w, mass_w, v_ode, u_ode, dtype):
+    """`reinit_density!` of the DensityReinitializationCallback (orc_reinit_density): the new fluid densities (n_f,)."""
+    dtype = np.dtype(dtype)
+    u_ode = np.ascontiguousarray(u_ode)
+    cdt = u_ode.dtype
+    s = suffix(dtype, cdt)
+    v_ode = np.ascontiguousarray(v_ode, dtype=dtype)
+    mass_f = np.ascontiguousarray(mass_f, dtype=dtype)
+    n_f = mass_f.size
+    if wp is not None and coords_w is not None and len(coords_w) > 0:
+        coords_w = np.ascontiguousarray(coords_w, dtype=cdt)
+        mass_w = np.ascontiguousarray(mass_w, dtype=dtype)
+        n_w, wpp = coords_w.shape[0], C.byref(wp)
+    else:
+        coords_w, mass_w, n_w, wpp = np.zeros((0, fp.ndims), dtype=cdt), np.zeros(0, dtype=dtype), 0, None
+    out = np.zeros(n_f, dtype=dtype)
+    rc = getattr(lib(), f"orc_reinit_density_{s}")(C.byref(fp), wpp, n_f, _ptr(mass_f), n_w, _ptr(coords_w),
+                                                    _ptr(mass_w), _ptr(v_ode), _ptr(u_ode), _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_reinit_density failed: {rc}")
+    return out
 
 
 def kick_fsi(fp: FluidParams, wp, sp: TlsphParams, mass_f, coords_w, mass_w, n_s_int, x0_s, mass_s, rho_s,

@@ -147,6 +147,11 @@ typedef struct {
                        T *density_f, T *pressure_w, T *density_w, T *volume_w,               \
                        T *wall_velocity_w, int use_grid, int nthreads);                      \
     void orc_drift_##SUF(int ndims, int nvars_v, int64_t n_f, const T *v_ode, CT *du_ode);    \
+    /* DensityReinitializationCallback: Shepard-corrected summation density (see the .inc) */ \
+    int orc_reinit_density_##SUF(const orc_fluid_params *fp, const orc_wall_params *wp,      \
+                                 int64_t n_f, const T *mass_f, int64_t n_w,                   \
+                                 const CT *coords_w, const T *mass_w, const T *v_ode,         \
+                                 const CT *u_ode, T *out_density);                            \
     int orc_tlsph_correction_matrix_##SUF(const orc_tlsph_params *sp, int64_t n, const CT *x0, \
                                           const T *mass, const T *rho, T *L);                \
     int orc_tlsph_update_##SUF(const orc_tlsph_params *sp, int64_t n, const CT *x0,          \

@@ -94,3 +94,69 @@ def test_sorting_callback_time_loop_is_a_permutation_of_the_unsorted_run():
             assert np.allclose(res[True][1], res[False][1], rtol=1e-4, atol=1e-3)
         else:
             assert np.array_equal(res[True][0], res[False][0]) and np.array_equal(res[True][1], res[False][1])
+
+
+@pytest.mark.parametrize("memory", ["device", "host"])
+@pytest.mark.parametrize("config", ["dam_break_2d f64", "dam_break_3d f32", "fluid only"])
+def test_reinit_density_matches_oracle(memory, config):
+    """DensityReinitializationCallback -> tpb_reinit_density: Shepard-corrected summation density into the density
+    rows of v_ode (in place; velocities and coordinates untouched) against the oracle's restatement."""
+    import torch
+    from oracle import adapter
+    if config == "dam_break_3d f32":
+        fluid, wall, _ = examples.dam_break_3d(0.1, eltype=np.float32, coordinates_eltype=np.float32)
+        tol = 2e-6
+    else:
+        fluid, wall, _ = examples.dam_break_2d(20, eltype=np.float64, coordinates_eltype=np.float64)
+        tol = 1e-12
+    if config == "fluid only":
+        wall = None
+    u, v = examples.perturbed_state(fluid)
+    nd = fluid.ndims
+    ref = adapter.reinit_density(fluid, wall, u, v)
+    systems = (fluid,) if wall is None else (fluid, wall)
+    semi = tp.Semidiscretization(*systems, parallelization_backend=tp.B200Backend(ode_memory=memory))
+    ode = tp.semidiscretize(semi, (0.0, 1.0))
+    if memory == "device":
+        u_d = torch.from_numpy(u.reshape(-1).copy()).to(ode.u0.device)
+        v_d = torch.from_numpy(v.reshape(-1).copy()).to(ode.u0.device)
+        semi.reinit_density(v_d, u_d)
+        semi.synchronize()
+        v2, u2 = v_d.cpu().numpy().reshape(v.shape), u_d.cpu().numpy().reshape(u.shape)
+    else:
+        v2, u2 = v.reshape(-1).copy(), u.reshape(-1).copy()
+        semi.reinit_density(v2, u2)
+        v2, u2 = v2.reshape(v.shape), u2.reshape(u.shape)
+    assert np.array_equal(u2, u) and np.array_equal(v2[:, :nd], v[:, :nd])
+    assert np.abs(v2[:, nd] - ref).max() <= tol * np.abs(ref).max()
+    assert np.abs(v2[:, nd] - v[:, nd]).max() > 1.0           # it did something
+    # the next kick works on the new densities
+    dv = np.full(v.size, np.nan, dtype=v.dtype)
+    if memory == "host":
+        tp.kick_(dv, v2.reshape(-1).copy(), u2.reshape(-1).copy(), ode.p, 0.0)
+        assert np.isfinite(dv).all()
+    semi.close()
+
+
+def test_density_reinitialization_callback_in_the_time_loop():
+    """`DensityReinitializationCallback(interval=10)` as in examples/fluid/dam_break_2d.jl:113-118 (`use_reinit`): the
+    run stays stable, the callback fires at the start and every tenth step, and the density field differs from the
+    run without it."""
+    from trixiparticles.jl_b200.time_integration import (CarpenterKennedy2N54, DensityReinitializationCallback,
+                                                          StepsizeCallback, solve)
+    out = {}
+    for use_reinit in (False, True):
+        fluid, wall, _ = examples.dam_break_2d(20, eltype=np.float64, coordinates_eltype=np.float64)
+        semi = tp.Semidiscretization(fluid, wall, parallelization_backend=tp.B200Backend(ode_memory="device"))
+        ode = tp.semidiscretize(semi, (0.0, 0.1))
+        cb = DensityReinitializationCallback(fluid, semi, interval=10)
+        sol = solve(ode, CarpenterKennedy2N54(williamson_condition=False), callback=(StepsizeCallback(cfl=0.9),) +
+                    ((cb,) if use_reinit else ()), cuda_graph=True)
+        assert sol.retcode == "Success"
+        v = sol.v.cpu().numpy().reshape(-1, 3)
+        assert np.isfinite(v).all()
+        assert cb.n_reinits == (1 + sol.nsteps // 10 if use_reinit else 0)
+        out[use_reinit] = v
+        semi.close()
+    assert 900.0 < out[True][:, 2].min() and out[True][:, 2].max() < 1100.0
+    assert np.abs(out[True][:, 2] - out[False][:, 2]).max() > 0.1

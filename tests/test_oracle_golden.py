@@ -522,3 +522,37 @@ def test_neighbor_counts_match_survey(oracle):
         centre = np.argmin(np.abs(x - x.mean(axis=0)).sum(axis=1))
         i, j = oracle.neighbor_pairs(x[centre:centre + 1], x, factor)
         assert len(j) == expected
+
+
+def test_density_reinitialisation_properties():
+    """DensityReinitializationCallback -> reinit_density! (callbacks/density_reinit.jl:83-121, wcsph/system.jl:398-415).
+    The reference has no numerical test for it; the restatement is pinned by what the formula implies:
+    without a wall the result depends on positions and masses only -- the integrated density is forgotten --, deep
+    inside a uniform lattice the Shepard coefficient is exactly 1 and the density is the plain kernel sum, and at a free
+    surface the correction raises the deficient kernel sum."""
+    import numpy as np
+    import trixiparticles.jl_b200 as tp
+    from oracle import adapter
+    n, dx = 21, 0.05
+    r = (np.arange(n) + 0.5) * dx
+    x = np.array([[a, b] for b in r for a in r])
+    ic = tp.InitialCondition(x, np.zeros_like(x), np.full(len(x), 1000.0 * dx * dx), np.full(len(x), 1000.0),
+                             np.zeros(len(x)), dx)
+    fluid = tp.WeaklyCompressibleSPHSystem(
+        ic, smoothing_kernel=tp.WendlandC2Kernel(2), smoothing_length=2 * dx, density_calculator=tp.ContinuityDensity(),
+        state_equation=tp.StateEquationCole(sound_speed=20.0, reference_density=1000.0, exponent=7))
+    rng = np.random.default_rng(0)
+    v1 = np.concatenate([np.zeros_like(x), np.full((len(x), 1), 1000.0)], axis=1)
+    v2 = v1.copy()
+    v2[:, 2] *= 1 + 0.05 * rng.uniform(-1, 1, len(x))
+    a, b = adapter.reinit_density(fluid, None, x, v1), adapter.reinit_density(fluid, None, x, v2)
+    assert np.array_equal(a, b)                                   # the integrated density is forgotten
+    from oracle import oracle as O
+    mid = (n // 2) * n + n // 2
+    w = sum(1000.0 * dx * dx * O.kernel(O.KERNEL_WENDLAND_C2, 2, float(np.linalg.norm(x[mid] - xb)), 2 * dx)
+            for xb in x if np.linalg.norm(x[mid] - xb) < 4 * dx)
+    assert abs(a[mid] - w) <= 1e-9 * w and abs(a[mid] - 1000.0) < 5.0     # c = 1: the plain kernel sum
+    corner = 0
+    plain = sum(1000.0 * dx * dx * O.kernel(O.KERNEL_WENDLAND_C2, 2, float(np.linalg.norm(x[corner] - xb)), 2 * dx)
+                for xb in x if np.linalg.norm(x[corner] - xb) < 4 * dx)
+    assert plain < 500.0 and plain + 100.0 < a[corner] < 1000.0   # a quarter of the support is filled; corrected upwards

@@ -24,7 +24,7 @@ EXPORTS = [
     "tpb_system_range", "tpb_kick", "tpb_drift", "tpb_get_system_field", "tpb_neighbor_pairs",
     "tpb_synchronize", "tpb_set_stream", "tpb_get_stats", "tpb_get_sound_speed", "tpb_max_speed2",
     "tpb_set_max_speed2", "tpb_set_integrate_structure", "tpb_structure_fluid_force", "tpb_kick_structure",
-    "tpb_set_clamped_motion", "tpb_sort_system", "tpb_set_structure_material",
+    "tpb_set_clamped_motion", "tpb_sort_system", "tpb_set_structure_material", "tpb_reinit_density",
     "tpb_host_register",
     "tpb_host_unregister", "tpb_set_profiling", "tpb_get_phase_times",
     "tpb_set_fluid_count", "tpb_set_fluid_mass",
@@ -150,6 +150,7 @@ def load():
     L.tpb_set_clamped_motion.restype = i32; L.tpb_set_clamped_motion.argtypes = [p, p, p, p, i32]
     L.tpb_sort_system.restype = i32; L.tpb_sort_system.argtypes = [p, i32, p, p]
     L.tpb_set_structure_material.restype = i32; L.tpb_set_structure_material.argtypes = [p, p, p]
+    L.tpb_reinit_density.restype = i32; L.tpb_reinit_density.argtypes = [p, p, p]
     u32 = C.c_uint32
     L.tpb_peer_alloc.restype = i32; L.tpb_peer_alloc.argtypes = [i64, C.POINTER(p)]
     L.tpb_peer_free.restype = i32; L.tpb_peer_free.argtypes = [p]

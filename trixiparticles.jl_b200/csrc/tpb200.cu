@@ -1368,6 +1368,66 @@ struct Ops {
         return TPB_OK;
     }
 
+    // `DensityReinitializationCallback` (callbacks/density_reinit.jl:83-121; reinit_density!, wcsph/system.jl:398-415):
+    // the density rows of the fluid in v_ode are replaced by the Shepard-corrected summation density.  Systems are
+    // updated for the given state first (sorted records, wall densities), as initialize_reinit_cb! does.
+    static int reinit_density(Semi &s, void *v_ode, const void *u_ode)
+    {
+        if (s.fp.density_calculator != TPB_DENSITY_CONTINUITY) return TPB_OK;  // reinit_density!(..., ::SummationDensity) = nothing
+        if (s.struct_index >= 0 || s.n_tgt != s.n_act || s.fp.adaptive_sound_speed || wall_integrates_density(s))
+            return fail(&s, TPB_ERR_UNSUPPORTED, "tpb_reinit_density: fluid + Adami walls with a fixed speed of sound only "
+                                                 "(no structure, slab ghosts, ContinuityDensity wall, adaptive state equation)");
+        const int n = (int)s.n_act;
+        if (n == 0) return TPB_OK;
+        const OdeLayout lay = ode_layout(s);
+        const int NV = nv(s);
+        const bool host = s.cfg.ode_memory == TPB_MEM_HOST;
+        const size_t ub = sizeof(CT) * (size_t)lay.tot_u, vb = sizeof(T) * (size_t)lay.tot_v;
+        const CT *u = host ? (const CT *)s.d_u : (const CT *)u_ode;
+        T *v = host ? (T *)s.d_v : (T *)v_ode;
+        if (host) {
+            CUDA_TRY(&s, cudaMemcpyAsync(s.d_u, u_ode, ub, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(&s, cudaMemcpyAsync(s.d_v, v_ode, vb, cudaMemcpyHostToDevice, s.stream));
+        }
+        s.ad_kick = nullptr;
+        int rc = rebuild_fluid(s, u + lay.off_u_f, v + lay.off_v_f);
+        if (rc) return rc;
+        GridConst<CT> g = make_grid_const<CT>(s);
+        PairConst<T> pc = make_pair_const<T>(s.fp, ND);
+        EosConst<T> eos = make_eos_const<T>(s.fp.sound_speed, s.fp.exponent, s.fp.reference_density,
+                                            s.fp.background_pressure, s.fp.clip_negative_pressure, false);
+        auto tk = [](int kernel) { return kernel <= 1 ? kernel : kernel <= TPB_KERNEL_WENDLAND_C6 ? 2 : 3; };
+        const int fk = tk(s.fp.kernel), wk = tk(s.wp.kernel);
+        const bool has_wall = s.n_w > 0 && s.interaction[0][1];
+        if (s.n_w > 0) {  // wall densities of the state before the reinitialisation
+            rc = wk == 0 ? launch_adami<0>(s, g) : wk == 1 ? launch_adami<1>(s, g) : wk == 2 ? launch_adami<2>(s, g)
+                                                                                              : launch_adami<3>(s, g);
+            if (rc) return rc;
+        }
+        switch (fk) {  // first pass: rho~ = sum m W into the sorted records
+#define TPB_REINIT(K)                                                                                              \
+    case K:                                                                                                        \
+        launch_summation<K>(s, g, pc, eos);                                                                        \
+        LAUNCH(s, (k_shepard_reinit<ND, T, CT, K>), cdiv(n, 128), 128, 0, n, g, s.d_fcell_start,                   \
+               (const V4<CT> *)s.d_A, (const V4<T> *)s.d_B, s.d_perm_f, (int)has_wall, s.d_wcell_start,            \
+               (const V4<CT> *)s.d_Aw, (const V2<T> *)s.d_Ww, pc.kern, pc.radius2, NV, (int)s.n_tgt,               \
+               v + lay.off_v_f);                                                                                   \
+        break;
+            TPB_REINIT(0) TPB_REINIT(1) TPB_REINIT(2) TPB_REINIT(3)
+#undef TPB_REINIT
+        }
+        if (host) {
+            CUDA_TRY(&s, cudaMemcpyAsync(v_ode, s.d_v, vb, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(&s, cudaMemcpyAsync(s.h_flags, s.d_flags, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(&s, cudaStreamSynchronize(s.stream));
+            if (*s.h_flags & 1)
+                return fail(&s, TPB_ERR_OUT_OF_BOUNDS,
+                            "particle coordinates are NaN or outside the FullGridCellList bounding box");
+        }
+        CUDA_TRY(&s, cudaGetLastError());
+        return TPB_OK;
+    }
+
     // `SortingCallback` (callbacks/sorting.jl:100-157): the fluid's rows of (v_ode, u_ode) -- and the library's
     // per-particle masses -- reordered by the cell of their current coordinates.  Scratch: the sorted pressure
     // array (rewritten by the next kick) and the handle's dv / du staging buffers (host mode) or two buffers of
@@ -1590,7 +1650,8 @@ struct Ops {
     int TPB_CAT(max_speed2_, TAG)(Semi &s, const void *v, void *out_bits);                               \
     int TPB_CAT(struct_force_, TAG)(Semi &s, void *out, const void *v, const void *u);                   \
     int TPB_CAT(kick_struct_, TAG)(Semi &s, void *dv, const void *v, const void *u, const void *dv_const); \
-    int TPB_CAT(sort_system_, TAG)(Semi &s, void *v, void *u);
+    int TPB_CAT(sort_system_, TAG)(Semi &s, void *v, void *u);                                           \
+    int TPB_CAT(reinit_density_, TAG)(Semi &s, void *v, const void *u);
 #define TPB_DEFINE_ENTRIES(TAG, ND, T, CT)                                                               \
     int TPB_CAT(init_wall_, TAG)(Semi &s) { return Ops<ND, T, CT>::init_wall(s); }                       \
     int TPB_CAT(init_structure_, TAG)(Semi &s) { return Ops<ND, T, CT>::init_structure(s); }             \
@@ -1624,7 +1685,8 @@ struct Ops {
     {                                                                                                    \
         return Ops<ND, T, CT>::kick_structure(s, dv, v, u, dv_const);                                    \
     }                                                                                                    \
-    int TPB_CAT(sort_system_, TAG)(Semi &s, void *v, void *u) { return Ops<ND, T, CT>::sort_system(s, v, u); }
+    int TPB_CAT(sort_system_, TAG)(Semi &s, void *v, void *u) { return Ops<ND, T, CT>::sort_system(s, v, u); } \
+    int TPB_CAT(reinit_density_, TAG)(Semi &s, void *v, const void *u) { return Ops<ND, T, CT>::reinit_density(s, v, u); }
 TPB_DECLARE_ENTRIES(2ff)
 TPB_DECLARE_ENTRIES(3ff)
 TPB_DECLARE_ENTRIES(2fd)
@@ -1677,6 +1739,7 @@ static int dispatch_kick_struct(Semi &s, void *dv, const void *v, const void *u,
 }
 
 static int dispatch_sort_system(Semi &s, void *v, void *u) { DISPATCH(s, sort_system_, s, v, u); }
+static int dispatch_reinit_density(Semi &s, void *v, const void *u) { DISPATCH(s, reinit_density_, s, v, u); }
 
 static void free_device(Semi &s)
 {
@@ -2324,6 +2387,16 @@ int32_t tpb_set_integrate_structure(tpb_semi_t semi, int32_t enabled)
     if (s->struct_index < 0) return fail(s, TPB_ERR_STATE, "no structure system");
     s->integrate_structure = enabled ? 1 : 0;
     return TPB_OK;
+}
+
+int32_t tpb_reinit_density(tpb_semi_t semi, void *v_ode, const void *u_ode)
+{
+    Semi *s = (Semi *)semi;
+    if (!s) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null handle");
+    if (!s->ready) return fail(s, TPB_ERR_STATE, "tpb_reinit_density before tpb_semidiscretize");
+    if (s->n_f > 0 && (!v_ode || !u_ode)) return fail(s, TPB_ERR_INVALID_ARGUMENT, "null ODE vector");
+    CUDA_TRY(s, cudaSetDevice(s->cfg.device));
+    return dispatch_reinit_density(*s, v_ode, u_ode);
 }
 
 int32_t tpb_set_structure_material(tpb_semi_t semi, const void *young_modulus, const void *poisson_ratio)

@@ -71,6 +71,47 @@ k_summation_density(int n_f_cap, GridConst<CT> g, const int *__restrict__ fcell_
     P[s] = eos_pressure(eos, rho);
 }
 
+// ------------------------------------------------------------------ density reinitialisation
+// Second pass of reinit_density! (wcsph/system.jl:398-415; callbacks/density_reinit.jl:83-121): the summation
+// density rho~ is in the sorted records (B.w, first pass = the SummationDensity sweep); here the Shepard
+// coefficient c_a = sum_b (m_b / rho_b) W_ab (general/corrections.jl:138-170) over the fluid (rho~_b) and the wall
+// (boundary-model density), and rho_a = rho~_a / c_a goes into the density row of the caller's v_ode.
+template <int ND, typename T, typename CT, int KERNEL>
+__global__ void __launch_bounds__(128)
+k_shepard_reinit(int n_f_cap, GridConst<CT> g, const int *__restrict__ fcell_start, const V4<CT> *__restrict__ A,
+                 const V4<T> *__restrict__ B, const int *__restrict__ perm, int has_wall,
+                 const int *__restrict__ wcell_start, const V4<CT> *__restrict__ Aw, const V2<T> *__restrict__ Ww,
+                 KernelConst<T> kern, T radius2, int nv, int n_targets, T *__restrict__ v_out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_f_cap || s >= fcell_start[g.ncells]) return;
+    const int orig = perm[s];
+    if (orig >= n_targets) return;
+    const V4<CT> xi = A[s];
+    int cx, cy, cz;
+    cell_coords<ND, CT>(g, xi.x, xi.y, xi.z, cx, cy, cz);
+    T c = (T)0;
+    for_neighbor_rows<ND, CT>(g, fcell_start, cx, cy, cz, [&](int j0, int j1) {
+        for (int j = j0; j < j1; ++j) {
+            const V4<CT> xj = A[j];
+            T pd[3];
+            const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+            if (d2 <= radius2) c += ((T)xj.w / B[j].w) * kernel_safe<KERNEL, T>(kern, sqrt_rn(d2));
+        }
+    });
+    if (has_wall) {
+        for_neighbor_rows<ND, CT>(g, wcell_start, cx, cy, cz, [&](int j0, int j1) {
+            for (int j = j0; j < j1; ++j) {
+                const V4<CT> xj = Aw[j];
+                T pd[3];
+                const T d2 = pos_diff_d2<ND, T, CT>(xi, xj, pd);
+                if (d2 <= radius2) c += ((T)xj.w / Ww[j].y) * kernel_safe<KERNEL, T>(kern, sqrt_rn(d2));
+            }
+        });
+    }
+    v_out[(int64_t)orig * nv + ND] = B[s].w / c;
+}
+
 // ------------------------------------------------------------------ Adami extrapolation
 // One thread per sorted wall particle; fluid neighbours from the fluid grid.
 //   p_w = sum_f (p_off + p_f + rho_f (g - a_w).r_wf) W(r_wf) / sum_f W(r_wf)   if sum W > eps()

@@ -637,6 +637,15 @@ class Semidiscretization:
         else:
             _lib.check(self._handle, L.tpb_set_clamped_motion(self._handle, None, None, None, 0))
 
+    def reinit_density(self, v_ode, u_ode):
+        """`reinit_density!` (DensityReinitializationCallback; wcsph/system.jl:398-415): the fluid's density rows of
+        `v_ode` become the Shepard-corrected summation density, in place (tpb_reinit_density)."""
+        nu, nv = self.ranges_u[-1][1], self.ranges_v[-1][1]
+        pv = self._ptr(v_ode, nv, self.eltype, "v_ode")
+        pu = self._ptr(u_ode, nu, self.coordinates_eltype, "u_ode")
+        self._bind_stream()
+        _lib.check(self._handle, _lib.load().tpb_reinit_density(self._handle, pv, pu))
+
     def sort_particles(self, v_ode, u_ode):
         """`sort_particles!` of every fluid system (callbacks/sorting.jl:123-157): the rows of (v_ode, u_ode) in
         place in grid-cell order (tpb_sort_system); later kicks give bit-identical results, row for row."""

@@ -291,6 +291,46 @@ class SortingCallback:
         return bool(due)
 
 
+class DensityReinitializationCallback:
+    """callbacks/density_reinit.jl:33-121: `DensityReinitializationCallback(system, semi; interval=0, dt=0.0,
+    reinit_initial_solution=true)` -- every `interval` steps (or at the first step after each `dt`) the integrated
+    density of the fluid is replaced by the Shepard-corrected summation density (Panizzo 2007)."""
+
+    def __init__(self, system=None, semi=None, *, interval: int = 0, dt: float = 0.0, reinit_initial_solution: bool = True):
+        if dt > 0 and interval > 0:
+            raise ValueError("Setting both interval and dt is not supported!")
+        if system is not None and not isinstance(getattr(system, "density_calculator", None), ContinuityDensityType()):
+            raise ValueError("DensityReinitializationCallback: the system must integrate its density (ContinuityDensity)")
+        self.interval = float(dt) if dt > 0 else int(interval)
+        self.reinit_initial_solution = bool(reinit_initial_solution)
+        self.last_t = -math.inf
+        self.n_reinits = 0
+
+    def initialize(self, semi, v, u, t):
+        if self.reinit_initial_solution:
+            self._apply(semi, v, u, t)
+        self.last_t = float(t)
+
+    def _apply(self, semi, v, u, t):
+        semi.reinit_density(v, u)
+        self.last_t = float(t)
+        self.n_reinits += 1
+
+    def __call__(self, semi, v, u, t, nsteps) -> bool:
+        if isinstance(self.interval, int):
+            due = self.interval > 0 and nsteps % self.interval == 0
+        else:
+            due = (t - self.last_t) > self.interval
+        if due:
+            self._apply(semi, v, u, t)
+        return bool(due)
+
+
+def ContinuityDensityType():
+    from .model import ContinuityDensity
+    return ContinuityDensity
+
+
 class PostprocessCallback:
     """Records `name -> f(system, v_ode, u_ode, semi, t)` for the fluid system every `dt`."""
 
@@ -429,6 +469,7 @@ def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
     posts = [c for c in callbacks if isinstance(c, PostprocessCallback)]
     split = next((c for c in callbacks if isinstance(c, SplitIntegrationCallback)), None)
     sorting = next((c for c in callbacks if isinstance(c, SortingCallback)), None)   # (fluid rows only, sorting.jl:5)
+    reinit = next((c for c in callbacks if isinstance(c, DensityReinitializationCallback)), None)
     if split is not None:
         split.initialize(semi, ode.v0, ode.u0, ode.tspan[0])   # (also: the StepsizeCallback skips the structure)
         cuda_graph = False                                      # the number of sub-steps varies from stage to stage
@@ -448,6 +489,8 @@ def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
     t, t_end = float(ode.tspan[0]), float(ode.tspan[1])
     if sorting is not None:
         sorting.initialize(semi, v, u, t)
+    if reinit is not None:
+        reinit.initialize(semi, v, u, t)
     next_stop = [t + p.dt for p in posts]
     for p in posts:
         p(t, v, u, semi)
@@ -494,6 +537,8 @@ def solve(ode, alg, *, dt: Optional[float] = None, save_everystep: bool = False,
             split.integrate_to(v, u, t)                    # the callback's affect! at the end of every step
         if sorting is not None:
             sorting(semi, v, u, t, nsteps)                 # in place: a captured graph keeps replaying on the same vectors
+        if reinit is not None:
+            reinit(semi, v, u, t, nsteps)
         if stepsize is not None and adaptive_eos:
             # StateEquationAdaptiveCole: the StepsizeCallback sees the speed of sound of the last
             # right-hand-side evaluation (stepsize.jl:63-79, fluid.jl:199-239)
@@ -531,8 +576,11 @@ def _solve_rdpk3(ode, alg: RDPK3SpFSAL35, callbacks, *, dt, abstol, reltol, dtma
     dtmax = float(dtmax) if dtmax is not None else t_end - t
     v = ode.v0.clone() if ops.device else ode.v0.copy()
     u = ode.u0.clone() if ops.device else ode.u0.copy()
+    reinit = next((c for c in callbacks if isinstance(c, DensityReinitializationCallback)), None)
     if sorting is not None:
         sorting.initialize(semi, v, u, t)
+    if reinit is not None:
+        reinit.initialize(semi, v, u, t)
     Z = ops.zeros_like
     kv, ku, k0v, k0u = Z(v), Z(u), Z(v), Z(u)           # stage rhs / FSAL rhs
     tv, tu, pv, pu, ev, eu = Z(v), Z(u), Z(v), Z(u), Z(v), Z(u)   # tmp register, uprev, error estimate
@@ -616,7 +664,9 @@ def _solve_rdpk3(ode, alg: RDPK3SpFSAL35, callbacks, *, dt, abstol, reltol, dtma
                 dts.append(step)
             if step == dt:                       # a step shortened for an output time keeps the controller's dt
                 dt = min(dt * factor, dtmax)
-            if sorting is not None and sorting(semi, v, u, t, nsteps):
+            changed = sorting is not None and sorting(semi, v, u, t, nsteps)
+            changed = (reinit is not None and reinit(semi, v, u, t, nsteps)) or changed
+            if changed:
                 _rhs(ode, k0v, k0u, v, u, t)     # derivative_discontinuity!(integrator, true): the FSAL value is stale
                 nf += 1
             for i, p in enumerate(posts):
